@@ -1,0 +1,164 @@
+// compress_b200/csrc/b2c_common.cuh -- device-side utilities shared by all kernels:
+// warp/block scans, named barriers, unaligned shared-memory loads, the
+// cooperative bit-run writer, 1-D TMA bulk loads.  sm_100a only.
+//
+// The same sources also compile under tests/emu/simt_emu.h (B2C_EMU) so kernel
+// logic can be exercised on the GPU-less dev box; that build is test
+// infrastructure and is never part of libb200comp.so.
+#pragma once
+#ifdef B2C_EMU
+#include "simt_emu.h"
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#endif
+
+#define B2C_DEV __device__ __forceinline__
+#define FULLMASK 0xffffffffu
+
+namespace b2c {
+
+B2C_DEV unsigned lane_id() { return threadIdx.x & 31; }
+B2C_DEV unsigned warp_id() { return threadIdx.x >> 5; }
+B2C_DEV uint32_t highbit32(uint32_t v) { return 31u - (uint32_t)__clz((int)v); }  // v != 0
+
+// Named barrier over a warp-multiple subset of the CTA (id 1..15; 0 is __syncthreads).
+B2C_DEV void bar_sync(int id, int nthreads) {
+#ifdef B2C_EMU
+    emu_named_barrier(id, nthreads);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
+// ---- unaligned little-endian loads from a 4-byte aligned base (shared or global).
+// Reads the aligned words covering [pos, pos+len); the buffer must be padded.
+B2C_DEV uint32_t ld32u(const uint8_t *base, uint32_t pos) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (pos & ~3u));
+    uint32_t sh = (pos & 3u) * 8u;
+    uint32_t a = w[0];
+    if (sh == 0) return a;
+    return __funnelshift_r(a, w[1], sh);
+}
+B2C_DEV uint64_t ld64u(const uint8_t *base, uint32_t pos) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (pos & ~3u));
+    uint32_t sh = (pos & 3u) * 8u;
+    uint32_t a = w[0], b = w[1];
+    if (sh == 0) return ((uint64_t)b << 32) | a;
+    uint32_t c = w[2];
+    return ((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh);
+}
+
+// ---- warp scans (inclusive) ----
+B2C_DEV uint32_t warp_scan_incl(uint32_t v) {
+    unsigned lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULLMASK, v, d);
+        if (lane >= (unsigned)d) v += t;
+    }
+    return v;
+}
+B2C_DEV uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULLMASK, v, d);
+    return v;
+}
+B2C_DEV uint32_t warp_max(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        uint32_t t = __shfl_xor_sync(FULLMASK, v, d);
+        v = t > v ? t : v;
+    }
+    return v;
+}
+
+// Exclusive scan of one value per thread across `nthreads` (multiple of 32, <= 1024) threads
+// that all call this with the same barrier id.  ws: shared scratch of >= 33 uint32.
+// Returns the exclusive prefix; *total receives the sum over all threads.
+B2C_DEV uint32_t group_scan_excl(uint32_t v, uint32_t *ws, int bar_id, int nthreads, unsigned tid_in_group,
+                                 uint32_t *total) {
+    unsigned lane = tid_in_group & 31, w = tid_in_group >> 5;
+    uint32_t incl = warp_scan_incl(v);
+    if (lane == 31) ws[w] = incl;
+    if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, nthreads);
+    if (w == 0) {
+        int nw = nthreads >> 5;
+        uint32_t x = (lane < (unsigned)nw) ? ws[lane] : 0;
+        uint32_t xi = warp_scan_incl(x);
+        ws[lane] = xi - x;  // exclusive warp bases
+        if (lane == 31) ws[32] = xi;
+    }
+    if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, nthreads);
+    uint32_t base = ws[w];
+    *total = ws[32];
+    // callers must place a barrier before reusing ws
+    return base + incl - v;
+}
+
+// ---- cooperative bit-run writer ----
+// Many threads append disjoint, contiguous bit ranges of one little-endian,
+// LSB-first bitstream held in zero-initialised shared memory (32-bit words).
+// Words wholly inside a thread's range are stored plainly; the first and last
+// (possibly shared) words are merged with atomicOr.
+struct BitRun {
+    uint32_t *words;   // stream base (4-byte aligned)
+    uint32_t bitpos;   // absolute bit position of the next bit to add
+    uint64_t acc;      // pending bits, LSB = bit `wordbit` of the current word
+    uint32_t nacc;     // number of pending bits in acc (including the leading offset)
+    uint32_t widx;     // index of the current (unflushed) word
+    bool first;        // the current word is the first word of this run
+
+    B2C_DEV void init(uint32_t *w, uint32_t startbit) {
+        words = w; bitpos = startbit; widx = startbit >> 5; nacc = startbit & 31; acc = 0; first = true;
+    }
+    B2C_DEV void flush_word() {
+        uint32_t wv = (uint32_t)acc;
+        if (first) { if (wv) atomicOr(&words[widx], wv); first = false; }
+        else words[widx] = wv;
+        widx++; acc >>= 32; nacc -= 32;
+    }
+    // add up to 32 bits (value must already be masked to nbits)
+    B2C_DEV void add(uint32_t value, uint32_t nbits) {
+        acc |= (uint64_t)value << nacc;
+        nacc += nbits; bitpos += nbits;
+        if (nacc >= 32) flush_word();
+    }
+    B2C_DEV void finish() {
+        if (nacc > 0) {
+            uint32_t wv = (uint32_t)acc;
+            if (wv) atomicOr(&words[widx], wv);
+        }
+    }
+};
+
+#ifndef B2C_EMU
+// ---- 1-D TMA bulk copy global -> shared with mbarrier completion (UBLKCP) ----
+B2C_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+B2C_DEV void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+B2C_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+B2C_DEV void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+B2C_DEV void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+B2C_DEV void mbar_wait(uint64_t *bar, unsigned phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+#endif
+
+}  // namespace b2c
