@@ -1,0 +1,371 @@
+// compress_b200/csrc/b2c_api.cu -- C ABI (include/b2c.h) over the sm_100a kernels.
+// Plain CUDA runtime: no torch types cross this boundary.  No CPU fallback: without a device
+// every call fails with B2C_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../include/b2c.h"
+#include "b2c_zstd_enc.cuh"
+
+using namespace b2c;
+
+struct b2c_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t max_chunks = 0;
+    uint8_t *d_scratch = nullptr;       // sm_count * ENC_SCRATCH_BYTES
+    // host-buffer path staging (slot 0 of the pipeline doubles as the pointer-table path's buffers)
+    uint8_t *h_in = nullptr;            // pinned, max_chunks * 64 KiB
+    uint8_t *h_out = nullptr;           // pinned, max_chunks * slot
+    int64_t *h_sizes = nullptr;         // pinned
+    uint8_t *d_in = nullptr;
+    uint8_t *d_out = nullptr;           // slots
+    uint8_t *d_packed = nullptr;        // packed output
+    int64_t *d_sizes = nullptr;
+    uint64_t *d_offsets = nullptr;
+    uint32_t *d_src_sizes = nullptr;
+    uint32_t *h_src_sizes = nullptr;
+    cudaStream_t stream = nullptr;
+    // second pipeline slot for b2c_zstd_encode_packed (H2D / encode / D2H overlap)
+    uint8_t *d_in2 = nullptr, *d_out2 = nullptr, *d_packed2 = nullptr;
+    int64_t *d_sizes2 = nullptr, *h_sizes2 = nullptr;
+    uint64_t *d_offsets2 = nullptr;
+    uint32_t *d_src_sizes2 = nullptr, *h_src_sizes2 = nullptr;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    uint64_t launches = 0;
+    char err[256] = {0};
+};
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            if (ctx) snprintf(ctx->err, sizeof(ctx->err), "%s: %s", #call, cudaGetErrorString(e_));    \
+            return B2C_ERR_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+static const uint32_t kSlot = 65536 + 512;  // >= MaxEncodedSize(65536) = 65536 + 3 + 7 + 4, 16-byte multiple
+
+// ---- small helper kernels -------------------------------------------------------------------
+// exclusive scan of the (non-negative) chunk sizes -> packed offsets; single CTA
+__global__ void b2c_scan_sizes_kernel(const int64_t *sizes, uint64_t *offsets, uint32_t n) {
+    __shared__ uint64_t carry;
+    __shared__ uint64_t wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x) {
+        uint32_t i = base + threadIdx.x;
+        uint64_t v = (i < n && sizes[i] > 0) ? (uint64_t)sizes[i] : 0;
+        uint64_t incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((threadIdx.x & 31) >= (unsigned)d) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint64_t x = (threadIdx.x < (blockDim.x >> 5)) ? wsum[threadIdx.x] : 0, xi = x;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t t = __shfl_up_sync(0xffffffffu, xi, d);
+                if (threadIdx.x >= (unsigned)d) xi += t;
+            }
+            wsum[threadIdx.x] = xi - x;
+        }
+        __syncthreads();
+        uint64_t ex = carry + wsum[threadIdx.x >> 5] + incl - v;
+        if (i < n) offsets[i] = ex;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = ex + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offsets[n] = carry;
+}
+// copy chunk i's bytes from its slot to packed[offsets[i]]
+__global__ void b2c_pack_kernel(const uint8_t *slots, uint64_t slot_stride, const int64_t *sizes,
+                                const uint64_t *offsets, uint8_t *packed, uint32_t n) {
+    for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+        int64_t sz = sizes[c];
+        if (sz <= 0) continue;
+        const uint8_t *s = slots + (uint64_t)c * slot_stride;
+        uint8_t *d = packed + offsets[c];
+        uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15);
+        if (head > (uint32_t)sz) head = (uint32_t)sz;
+        for (uint32_t i = threadIdx.x; i < head; i += blockDim.x) d[i] = s[i];
+        // aligned body: 4-byte stores assembled from (possibly unaligned) source words
+        uint32_t body = ((uint32_t)sz - head) & ~3u;
+        for (uint32_t i = threadIdx.x * 4; i < body; i += blockDim.x * 4) {
+            uint32_t v = ld32u(s, head + i);
+            *reinterpret_cast<uint32_t *>(d + head + i) = v;
+        }
+        for (uint32_t i = head + body + threadIdx.x; i < (uint32_t)sz; i += blockDim.x) d[i] = s[i];
+    }
+}
+
+// ---- context -----------------------------------------------------------------------------------
+extern "C" {
+
+int b2c_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device >= n) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    b2c_ctx *ctx = new b2c_ctx();
+    ctx->device = device;
+    ctx->max_chunks = max_chunks;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return nullptr; }
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = true;
+    ok = ok && cudaMalloc(&ctx->d_scratch, (size_t)ctx->sm_count * ENC_SCRATCH_BYTES) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)ENC_SMEM_BYTES) == cudaSuccess;
+    if (ok && max_chunks) {
+        ok = ok && cudaMallocHost(&ctx->h_in, max_chunks * (size_t)ENC_MAX_CHUNK) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ctx->h_out, max_chunks * (size_t)kSlot) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ctx->h_sizes, (max_chunks + 1) * sizeof(int64_t) * 2) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ctx->h_src_sizes, max_chunks * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_in, max_chunks * (size_t)ENC_MAX_CHUNK) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_out, max_chunks * (size_t)kSlot) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_packed, max_chunks * (size_t)kSlot) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_sizes, max_chunks * sizeof(int64_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_offsets, (max_chunks + 1) * sizeof(uint64_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_src_sizes, max_chunks * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ctx->h_sizes2, (max_chunks + 1) * sizeof(int64_t) * 2) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ctx->h_src_sizes2, max_chunks * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_in2, max_chunks * (size_t)ENC_MAX_CHUNK) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_out2, max_chunks * (size_t)kSlot) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_packed2, max_chunks * (size_t)kSlot) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_sizes2, max_chunks * sizeof(int64_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_offsets2, (max_chunks + 1) * sizeof(uint64_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_src_sizes2, max_chunks * sizeof(uint32_t)) == cudaSuccess;
+    }
+    if (!ok) { b2c_ctx_destroy(ctx); return nullptr; }
+    return ctx;
+}
+
+void b2c_ctx_destroy(b2c_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_scratch); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
+    cudaFree(ctx->d_sizes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_src_sizes);
+    cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_sizes); cudaFreeHost(ctx->h_src_sizes);
+    cudaFree(ctx->d_in2); cudaFree(ctx->d_out2); cudaFree(ctx->d_packed2); cudaFree(ctx->d_sizes2);
+    cudaFree(ctx->d_offsets2); cudaFree(ctx->d_src_sizes2); cudaFreeHost(ctx->h_sizes2); cudaFreeHost(ctx->h_src_sizes2);
+    if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
+    if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *b2c_strerror(int code) {
+    switch (code) {
+    case B2C_OK: return "ok";
+    case B2C_ERR_NO_DEVICE: return "no CUDA device (libb200comp has no CPU fallback)";
+    case B2C_ERR_CUDA: return "CUDA runtime error";
+    case B2C_ERR_ARG: return "invalid argument";
+    case B2C_ERR_TOO_BIG: return "chunk too big for this level's block size";
+    case B2C_ERR_DST_SMALL: return "destination too small";
+    case B2C_ERR_CORRUPT: return "corrupt input";
+    case B2C_ERR_UNSUPPORTED: return "unsupported";
+    default: return "unknown error";
+    }
+}
+const char *b2c_last_cuda_error(b2c_ctx *ctx) { return ctx ? ctx->err : "no context"; }
+int b2c_sm_count(b2c_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t b2c_launch_count(b2c_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+size_t b2c_zstd_bound(size_t size, int level) {
+    // Encoder.MaxEncodedSize, zstd/encoder.go:843-873 (crc on)
+    size_t blockSize = (level == B2C_LEVEL_FASTEST) ? (1u << 16) : (128u << 10);
+    size_t fh = 4 + 2;
+    if (size < 256) fh++;
+    else if (size < 65536 + 256) fh += 2;
+    else if (size < 0x7fffffff) fh += 4;
+    else fh += 8;
+    fh += 4;
+    size_t blocks = (size + blockSize) / blockSize;
+    return fh + 3 * blocks + size;
+}
+
+static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
+                         const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
+                         int64_t *d_out_sizes, uint32_t nchunks, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
+                         uint8_t *dbg_lits, uint32_t dbg_cap, cudaStream_t st) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (level != B2C_LEVEL_FASTEST) return B2C_ERR_UNSUPPORTED;
+    if (nchunks == 0) return B2C_OK;
+    if (dst_stride > 0xffffffffull) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ZstdEncParams P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_sizes = d_sizes; P.src_size_all = size_all;
+    P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
+    P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.flags = (uint32_t)flags; P.scratch = ctx->d_scratch;
+    P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_cap;
+    unsigned grid = (unsigned)ctx->sm_count;
+    if (grid > nchunks) grid = nchunks;
+    b2c_zstd_encode_kernel<<<grid, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_zstd_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
+                           const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
+                           int64_t *d_out_sizes, uint32_t nchunks, void *stream) {
+    return launch_encode(ctx, level, flags, d_src, src_stride, d_sizes, size_all, d_dst, dst_stride, d_out_sizes,
+                         nchunks, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+int b2c_zstd_encode_device_debug(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride,
+                                 const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
+                                 int64_t *d_out_sizes, uint32_t nchunks, uint32_t *d_dbg_hdr, uint32_t *d_dbg_seqs,
+                                 uint8_t *d_dbg_lits, uint32_t dbg_seq_cap, void *stream) {
+    return launch_encode(ctx, B2C_LEVEL_FASTEST, flags, d_src, src_stride, d_sizes, size_all, d_dst, dst_stride,
+                         d_out_sizes, nchunks, d_dbg_hdr, d_dbg_seqs, d_dbg_lits, dbg_seq_cap, (cudaStream_t)stream);
+}
+
+int b2c_zstd_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const *srcs, const size_t *src_sizes,
+                           void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (level != B2C_LEVEL_FASTEST) return B2C_ERR_UNSUPPORTED;
+    if (!ctx->max_chunks) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (size_t base = 0; base < n; base += ctx->max_chunks) {
+        size_t m = n - base;
+        if (m > ctx->max_chunks) m = ctx->max_chunks;
+        // contiguous equal-sized input needs no host-side staging copy
+        bool contiguous = true;
+        for (size_t i = 0; i < m; i++) {
+            if (src_sizes[base + i] > ENC_MAX_CHUNK) { contiguous = false; }
+            if (i + 1 < m && ((const uint8_t *)srcs[base + i] + src_sizes[base + i] != (const uint8_t *)srcs[base + i + 1] ||
+                              src_sizes[base + i] != ENC_MAX_CHUNK))
+                contiguous = false;
+            ctx->h_src_sizes[i] = (uint32_t)(src_sizes[base + i] > ENC_MAX_CHUNK ? ENC_MAX_CHUNK + 1 : src_sizes[base + i]);
+        }
+        size_t in_bytes = 0;
+        for (size_t i = 0; i < m; i++) in_bytes += src_sizes[base + i];
+        if (contiguous) {
+            CK(cudaMemcpyAsync(ctx->d_in, srcs[base], in_bytes, cudaMemcpyHostToDevice, st));
+        } else {
+            for (size_t i = 0; i < m; i++) {
+                size_t sz = src_sizes[base + i] > ENC_MAX_CHUNK ? 0 : src_sizes[base + i];
+                memcpy(ctx->h_in + i * (size_t)ENC_MAX_CHUNK, srcs[base + i], sz);
+            }
+            CK(cudaMemcpyAsync(ctx->d_in, ctx->h_in, m * (size_t)ENC_MAX_CHUNK, cudaMemcpyHostToDevice, st));
+        }
+        CK(cudaMemcpyAsync(ctx->d_src_sizes, ctx->h_src_sizes, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        int rc = launch_encode(ctx, level, flags, ctx->d_in, ENC_MAX_CHUNK, ctx->d_src_sizes, 0, ctx->d_out, kSlot,
+                               ctx->d_sizes, (uint32_t)m, nullptr, nullptr, nullptr, 0, st);
+        if (rc) return rc;
+        b2c_scan_sizes_kernel<<<1, 1024, 0, st>>>(ctx->d_sizes, ctx->d_offsets, (uint32_t)m);
+        b2c_pack_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_out, kSlot, ctx->d_sizes, ctx->d_offsets, ctx->d_packed, (uint32_t)m);
+        ctx->launches += 2;
+        int64_t *h_sz = ctx->h_sizes;
+        uint64_t *h_off = reinterpret_cast<uint64_t *>(ctx->h_sizes + m);
+        CK(cudaMemcpyAsync(h_sz, ctx->d_sizes, m * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_off, ctx->d_offsets, (m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint64_t total = h_off[m];
+        CK(cudaMemcpyAsync(ctx->h_out, ctx->d_packed, total, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < m; i++) {
+            int64_t sz = h_sz[i];
+            if (sz > 0 && (size_t)sz > dst_caps[base + i]) sz = B2C_ERR_DST_SMALL;
+            if (sz > 0) memcpy(dsts[base + i], ctx->h_out + h_off[i], (size_t)sz);
+            sizes_out[base + i] = sz;
+        }
+    }
+    return B2C_OK;
+}
+
+
+// Contiguous host input -> packed host output (concatenated frames), double-buffered so the H2D copy of
+// batch b+1 and the D2H copy of batch b-1 overlap the kernels of batch b.  This is the shape of a large
+// EncodeAll / of a WithConcurrentBlocks job (zstd/enc_jobs.go): the caller gets one valid zstd stream plus
+// the per-chunk frame table.  h_src / h_dst should be pinned (cudaHostRegister / torch pin_memory) for
+// full PCIe rate; pageable memory works but is staged by the driver.
+int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src, size_t src_bytes,
+                           uint32_t chunk_size, void *h_dst, size_t dst_cap, int64_t *sizes_out,
+                           uint64_t *offsets_out, size_t *total_out) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (level != B2C_LEVEL_FASTEST) return B2C_ERR_UNSUPPORTED;
+    if (!ctx->max_chunks || chunk_size == 0 || chunk_size > ENC_MAX_CHUNK) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nchunks = src_bytes == 0 ? 1 : (src_bytes + chunk_size - 1) / chunk_size;
+    const size_t B = ctx->max_chunks;
+    const size_t nb = (nchunks + B - 1) / B;
+    struct Slot { cudaStream_t st; uint8_t *d_in, *d_out, *d_packed; int64_t *d_sizes, *h_sizes; uint64_t *d_off;
+                  uint32_t *d_ss, *h_ss; } slot[2] = {
+        {ctx->stream, ctx->d_in, ctx->d_out, ctx->d_packed, ctx->d_sizes, ctx->h_sizes, ctx->d_offsets, ctx->d_src_sizes, ctx->h_src_sizes},
+        {ctx->stream2, ctx->d_in2, ctx->d_out2, ctx->d_packed2, ctx->d_sizes2, ctx->h_sizes2, ctx->d_offsets2, ctx->d_src_sizes2, ctx->h_src_sizes2}};
+    uint64_t out_pos = 0;
+    int rc = B2C_OK;
+    auto finish = [&](size_t b) -> int {
+        Slot &S = slot[b & 1];
+        size_t c0 = b * B, m = (nchunks - c0 < B) ? nchunks - c0 : B;
+        if (cudaEventSynchronize(ctx->ev[b & 1]) != cudaSuccess) return B2C_ERR_CUDA;
+        const int64_t *h_sz = S.h_sizes;
+        const uint64_t *h_off = reinterpret_cast<const uint64_t *>(S.h_sizes + m);
+        uint64_t total = h_off[m];
+        if (out_pos + total > dst_cap) return B2C_ERR_DST_SMALL;
+        if (cudaMemcpyAsync((uint8_t *)h_dst + out_pos, S.d_packed, total, cudaMemcpyDeviceToHost, S.st) != cudaSuccess)
+            return B2C_ERR_CUDA;
+        for (size_t i = 0; i < m; i++) {
+            sizes_out[c0 + i] = h_sz[i];
+            if (offsets_out) offsets_out[c0 + i] = out_pos + h_off[i];
+            if (h_sz[i] < 0) rc = (int)h_sz[i];
+        }
+        out_pos += total;
+        return B2C_OK;
+    };
+    for (size_t b = 0; b < nb; b++) {
+        Slot &S = slot[b & 1];
+        size_t c0 = b * B, m = (nchunks - c0 < B) ? nchunks - c0 : B;
+        size_t off = c0 * (size_t)chunk_size;
+        size_t bytes = (off + m * (size_t)chunk_size <= src_bytes) ? m * (size_t)chunk_size : src_bytes - off;
+        // slot reuse: batch b-2's D2H (enqueued in finish(b-2)) is on the same stream, so stream order protects it
+        if (bytes) CK(cudaMemcpyAsync(S.d_in, (const uint8_t *)h_src + off, bytes, cudaMemcpyHostToDevice, S.st));
+        const uint32_t *d_ss = nullptr;
+        if (bytes != m * (size_t)chunk_size) {  // ragged last chunk (or empty input): explicit sizes
+            for (size_t i = 0; i < m; i++) {
+                size_t o = i * (size_t)chunk_size;
+                S.h_ss[i] = (uint32_t)(o >= bytes ? 0 : (bytes - o < chunk_size ? bytes - o : chunk_size));
+            }
+            CK(cudaMemcpyAsync(S.d_ss, S.h_ss, m * sizeof(uint32_t), cudaMemcpyHostToDevice, S.st));
+            d_ss = S.d_ss;
+        }
+        int r = launch_encode(ctx, level, flags, S.d_in, chunk_size, d_ss, chunk_size, S.d_out, kSlot, S.d_sizes,
+                              (uint32_t)m, nullptr, nullptr, nullptr, 0, S.st);
+        if (r) return r;
+        b2c_scan_sizes_kernel<<<1, 1024, 0, S.st>>>(S.d_sizes, S.d_off, (uint32_t)m);
+        b2c_pack_kernel<<<ctx->sm_count * 4, 256, 0, S.st>>>(S.d_out, kSlot, S.d_sizes, S.d_off, S.d_packed, (uint32_t)m);
+        ctx->launches += 2;
+        CK(cudaMemcpyAsync(S.h_sizes, S.d_sizes, m * sizeof(int64_t), cudaMemcpyDeviceToHost, S.st));
+        CK(cudaMemcpyAsync(S.h_sizes + m, S.d_off, (m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, S.st));
+        CK(cudaEventRecord(ctx->ev[b & 1], S.st));
+        if (b >= 1) { int r2 = finish(b - 1); if (r2) return r2; }
+    }
+    { int r2 = finish(nb - 1); if (r2) return r2; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream2));
+    if (total_out) *total_out = out_pos;
+    return rc;
+}
+
+}  // extern "C"

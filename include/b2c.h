@@ -1,0 +1,108 @@
+/*
+ * include/b2c.h -- C ABI of libb200comp.so, the B200 (sm_100a) block-compression engine.
+ *
+ * This is the drop-in boundary for klauspost/compress's block codec hot path.  The reference
+ * has no FFI of its own (pure Go + Go assembler, CGO_ENABLED=0); the entry points below are what a
+ * cgo shim would bind in place of the per-block work of
+ *     zstd.Encoder.EncodeAll / encodeAll        zstd/encoder.go:722,731   -> b2c_zstd_encode_*
+ *     zstd.Decoder.DecodeAll / runDecoder       zstd/decoder.go:319, framedec.go:330 -> b2c_zstd_decode_*
+ *     huff0.Compress4X / Compress1X             huff0/compress.go:27,14   -> b2c_huf_compress_device
+ *     s2.Encode / s2.Writer custom encoder hook s2/encode.go:29, s2/writer.go:1052 -> b2c_s2_*
+ * (see INTEGRATION.md for the cgo stubs).  Conventions follow the reference's Go<->asm seam
+ * (zstd/seqdec_asm.go:17-78, s2/encodeblock_amd64.go:14-42): the caller owns all memory, nothing is
+ * retained past return, sizes are plain integers, results are byte counts or negative error codes.
+ *
+ * Batched on purpose: one call = N independent chunks (a 64 KiB chunk per kernel launch would be
+ * launch-bound); a chunk is what one EncodeAll call / one s2 block is in the reference.
+ * No CPU fallback exists: every entry point fails with B2C_ERR_NO_DEVICE without a CUDA device.
+ */
+#ifndef B2C_H
+#define B2C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2C_API __attribute__((visibility("default")))
+
+/* error codes (returned negative, also stored per chunk in sizes_out) */
+enum {
+    B2C_OK = 0,
+    B2C_ERR_NO_DEVICE = -100,   /* no CUDA device / driver: the product never falls back to the CPU */
+    B2C_ERR_CUDA = -101,        /* a CUDA runtime call failed (see b2c_last_cuda_error) */
+    B2C_ERR_ARG = -102,
+    B2C_ERR_TOO_BIG = -3,       /* chunk larger than the level's block size (zstd: 64 KiB at level 1) */
+    B2C_ERR_DST_SMALL = -4,     /* destination slot smaller than the encoded chunk */
+    B2C_ERR_CORRUPT = -5,       /* decoder: invalid stream (maps to the zstd package's decode errors) */
+    B2C_ERR_UNSUPPORTED = -11
+};
+
+/* flags for the zstd encoder */
+enum {
+    B2C_ZSTD_CRC = 1,    /* append XXH64 content checksum (zstd.WithEncoderCRC, default true) */
+    B2C_ZSTD_FRAME = 2   /* emit one complete frame per chunk (EncodeAll); otherwise bare blocks */
+};
+
+/* zstd levels (zstd.EncoderLevel, zstd/encoder_options.go) */
+enum { B2C_LEVEL_FASTEST = 1, B2C_LEVEL_DEFAULT = 2 };
+
+typedef struct b2c_ctx b2c_ctx;
+
+B2C_API int b2c_device_count(void);
+/* One context per GPU per host thread.  max_chunks bounds the batch size of the host-buffer calls. */
+B2C_API b2c_ctx *b2c_ctx_create(int device, size_t max_chunks);
+B2C_API void b2c_ctx_destroy(b2c_ctx *ctx);
+B2C_API const char *b2c_strerror(int code);
+B2C_API const char *b2c_last_cuda_error(b2c_ctx *ctx);
+B2C_API int b2c_sm_count(b2c_ctx *ctx);
+/* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
+B2C_API uint64_t b2c_launch_count(b2c_ctx *ctx);
+
+/* Encoder.MaxEncodedSize for one chunk of n bytes (zstd/encoder.go:843-873) */
+B2C_API size_t b2c_zstd_bound(size_t n, int level);
+
+/*
+ * Device-resident batch (throughput path; bench `value`).  Chunk i is read from
+ * d_src + i*src_stride (size d_sizes[i], or size_all when d_sizes == NULL) and written to
+ * d_dst + i*dst_stride (capacity dst_stride); d_out_sizes[i] receives the encoded size or a
+ * negative error.  All pointers are device pointers; `stream` is a cudaStream_t (NULL = default).
+ * Asynchronous: returns after enqueueing.
+ */
+B2C_API int b2c_zstd_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
+                                   const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
+                                   int64_t *d_out_sizes, uint32_t nchunks, void *stream);
+
+/*
+ * Host-buffer batch (the call a cgo shim makes; bench `e2e`).  srcs[i]/dsts[i] are host pointers;
+ * the library stages through pinned memory, copies H2D, encodes, packs and copies D2H.
+ * sizes_out[i] = encoded bytes or negative error.  Synchronous.
+ */
+B2C_API int b2c_zstd_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const *srcs,
+                                   const size_t *src_sizes, void *const *dsts, const size_t *dst_caps,
+                                   int64_t *sizes_out, size_t n);
+
+/*
+ * Contiguous host input -> packed host output: src is cut into chunk_size pieces (<= 64 KiB at level 1), each
+ * encoded as one frame, frames written back to back into h_dst (a valid zstd stream: concatenated frames,
+ * zstd/encoder.go:719).  sizes_out[i] / offsets_out[i] describe frame i; *total_out is the stream length.
+ * Double-buffered: H2D, kernels and D2H of consecutive batches overlap.  Synchronous.
+ */
+B2C_API int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src, size_t src_bytes,
+                                   uint32_t chunk_size, void *h_dst, size_t dst_cap, int64_t *sizes_out,
+                                   uint64_t *offsets_out, size_t *total_out);
+
+/* Debug/parity hook used by tests: encode device-resident chunks and also dump, per chunk,
+ * {nseq, nlit, kind, litMode}, the (litLen, matchLen-3, offset) triples and the literal bytes, so the
+ * entropy stage can be compared byte-for-byte with the oracle's blockEnc.encode. */
+B2C_API int b2c_zstd_encode_device_debug(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride,
+                                         const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
+                                         int64_t *d_out_sizes, uint32_t nchunks, uint32_t *d_dbg_hdr,
+                                         uint32_t *d_dbg_seqs, uint8_t *d_dbg_lits, uint32_t dbg_seq_cap, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -56,37 +56,40 @@ typedef struct {
     size_t cap;
     size_t pos;     /* bytes written */
     uint64_t acc;
-    unsigned nbits; /* < 8 after every add */
+    unsigned nbits; /* < 32 after every add */
     int overflow;
 } orc_bw;
 
 static inline void orc_bw_init(orc_bw *b, uint8_t *out, size_t cap) {
     b->out = out; b->cap = cap; b->pos = 0; b->acc = 0; b->nbits = 0; b->overflow = 0;
 }
-static inline void orc_bw_add(orc_bw *b, uint64_t value, unsigned bits) { /* bits <= 56 */
+static inline void orc_bw_add(orc_bw *b, uint64_t value, unsigned bits) { /* bits <= 32 */
     if (bits == 0) return;
-    value &= (bits >= 64) ? ~0ull : ((1ull << bits) - 1);
+    value &= ((1ull << bits) - 1);
     b->acc |= value << b->nbits;
     b->nbits += bits;
-    while (b->nbits >= 8) {
-        if (b->pos < b->cap) b->out[b->pos] = (uint8_t)b->acc; else b->overflow = 1;
-        b->pos++;
-        b->acc >>= 8;
-        b->nbits -= 8;
+    if (b->nbits >= 32) { /* flush32 (zstd/bitwriter.go:78-88) */
+        if (b->pos + 4 <= b->cap) { uint32_t w = (uint32_t)b->acc; memcpy(b->out + b->pos, &w, 4); }
+        else b->overflow = 1;
+        b->pos += 4;
+        b->acc >>= 32;
+        b->nbits -= 32;
     }
 }
 static inline void orc_bw_add64(orc_bw *b, uint64_t value, unsigned bits) { /* up to 64 bits */
     if (bits > 32) { orc_bw_add(b, value & 0xffffffffull, 32); orc_bw_add(b, value >> 32, bits - 32); }
     else orc_bw_add(b, value, bits);
 }
-/* close(): end-mark bit then pad to byte (bitwriter.go:100-105) */
+/* close(): end-mark bit then flush to the next byte boundary (bitwriter.go:100-105) */
 static inline void orc_bw_close(orc_bw *b) {
     orc_bw_add(b, 1, 1);
-    if (b->nbits) {
+    while (b->nbits > 0) {
         if (b->pos < b->cap) b->out[b->pos] = (uint8_t)b->acc; else b->overflow = 1;
         b->pos++;
-        b->acc = 0; b->nbits = 0;
+        b->acc >>= 8;
+        b->nbits = b->nbits > 8 ? b->nbits - 8 : 0;
     }
+    b->acc = 0;
 }
 /* flush whole bytes only, no end mark (fse cState.flush -> bw.flush, fse/compress.go:118) */
 

@@ -42,6 +42,7 @@ typedef struct {
     uint32_t recentOffsets[3], prevRecentOffsets[3];
     int last;
     size_t extraLits;
+    uint8_t *tmp; /* huff0 output staging (Scratch.Out) */
 } orc_blockenc; /* blockEnc, zstd/blockenc.go:17-33 */
 
 orc_blockenc *orc_blockenc_new(void);

@@ -178,6 +178,7 @@ ORC_API orc_blockenc *orc_blockenc_new(void) {
     if (!b) return NULL;
     b->lit_cap = ORC_ZSTD_MAX_BLOCK + 64;
     b->literals = (uint8_t *)malloc(b->lit_cap);
+    b->tmp = (uint8_t *)malloc(ORC_ZSTD_MAX_BLOCK + 1024);
     b->seq_cap = 2000;
     b->seqs = (orc_seq *)malloc(b->seq_cap * sizeof(orc_seq));
     b->llEnc = &b->store[0]; b->llPrev = &b->store[1];
@@ -189,7 +190,7 @@ ORC_API orc_blockenc *orc_blockenc_new(void) {
 }
 ORC_API void orc_blockenc_free(orc_blockenc *b) {
     if (!b) return;
-    free(b->literals); free(b->seqs); free(b);
+    free(b->literals); free(b->seqs); free(b->tmp); free(b);
 }
 
 static void compare_swap(orc_fse_enc *used, orc_fse_enc **current, orc_fse_enc **prev) { /* seqenc.go:22-38 */
@@ -295,7 +296,7 @@ static int encode_lits(orc_blockenc *b, const uint8_t *lits, size_t n, int raw, 
         PUT(lits, n);
         return 0;
     }
-    uint8_t *tmp = (uint8_t *)malloc(n + 512);
+    uint8_t *tmp = b->tmp;
     int reUsed = 0, single = 0;
     int64_t out;
     if (n >= 1024) out = orc_huf_compress(&b->litEnc, lits, n, 1, tmp, n + 512, &reUsed);
@@ -325,7 +326,6 @@ static int encode_lits(orc_blockenc *b, const uint8_t *lits, size_t n, int raw, 
             else { memcpy(dst + *pos, tmp, (size_t)out); *pos += (size_t)out; dst[(*pos)++] = 0; }
         }
     }
-    free(tmp);
     return e;
 }
 
@@ -394,7 +394,7 @@ ORC_API int orc_blockenc_encode(orc_blockenc *b, const uint8_t *org, size_t orgL
     /* literals */
     {
         size_t n = b->nlit;
-        uint8_t *tmp = (uint8_t *)malloc(n + 512);
+        uint8_t *tmp = b->tmp;
         int reUsed = 0, single = 0;
         int64_t out;
         if (n >= 1024 && !raw) out = orc_huf_compress(&b->litEnc, b->literals, n, 1, tmp, n + 512, &reUsed);
@@ -420,7 +420,6 @@ ORC_API int orc_blockenc_encode(orc_blockenc *b, const uint8_t *org, size_t orgL
             if (!e) { if (*pos + (size_t)out > cap) e = ORC_ERR_DST_SMALL; else { memcpy(dst + *pos, tmp, (size_t)out); *pos += (size_t)out; } }
             b->litEnc.reuse = ORC_HUF_REUSE_ALLOW;
         }
-        free(tmp);
         if (e) return e;
     }
     /* number of sequences, blockenc.go:601-610 */
@@ -580,6 +579,7 @@ typedef struct { uint32_t val; int32_t offset; } tentry;
 typedef struct {
     tentry table[FAST_TABLE_SIZE];
     int32_t maxMatchOff;
+    int32_t cur; /* fastBase.cur: table offsets are stored as position + cur so stale entries fall out of the window */
 } fast_state;
 
 static void add_lits(orc_blockenc *b, const uint8_t *src, int32_t from, int32_t until) {
@@ -621,8 +621,8 @@ static void fast_encode_block(fast_state *e, orc_blockenc *blk, const uint8_t *s
             tentry candidate = e->table[nextHash];
             tentry candidate2 = e->table[nextHash2];
             int32_t repIndex = s - offset1 + 2;
-            e->table[nextHash].offset = s; e->table[nextHash].val = (uint32_t)cv;
-            e->table[nextHash2].offset = s + 1; e->table[nextHash2].val = (uint32_t)(cv >> 8);
+            e->table[nextHash].offset = s + e->cur; e->table[nextHash].val = (uint32_t)cv;
+            e->table[nextHash2].offset = s + 1 + e->cur; e->table[nextHash2].val = (uint32_t)(cv >> 8);
 
             int repOK = nohist ? (blk->nseq > 2) : (canRepeat && repIndex >= 0);
             if (repOK && orc_ld32(src + repIndex) == (uint32_t)(cv >> 16)) {
@@ -644,13 +644,13 @@ static void fast_encode_block(fast_state *e, orc_blockenc *blk, const uint8_t *s
                 cv = orc_ld64(src + s);
                 continue;
             }
-            int32_t coffset0 = s - candidate.offset;
-            int32_t coffset1 = s - candidate2.offset + 1;
-            if (coffset0 < e->maxMatchOff && (uint32_t)cv == candidate.val && candidate.offset >= 0) {
-                t = candidate.offset; found = 1; break;
+            int32_t coffset0 = s - (candidate.offset - e->cur);
+            int32_t coffset1 = s - (candidate2.offset - e->cur) + 1;
+            if (coffset0 < e->maxMatchOff && (uint32_t)cv == candidate.val) {
+                t = candidate.offset - e->cur; found = 1; break;
             }
-            if (coffset1 < e->maxMatchOff && (uint32_t)(cv >> 8) == candidate2.val && candidate2.offset >= 0) {
-                t = candidate2.offset; s++; found = 1; break;
+            if (coffset1 < e->maxMatchOff && (uint32_t)(cv >> 8) == candidate2.val) {
+                t = candidate2.offset - e->cur; s++; found = 1; break;
             }
             s += stepSize + ((s - nextEmit) >> (kSearchStrength - 1));
             if (s >= sLimit) goto done;
@@ -678,7 +678,7 @@ static void fast_encode_block(fast_state *e, orc_blockenc *blk, const uint8_t *s
             if (can2 && orc_ld32(src + o2) == (uint32_t)cv) {
                 int32_t l2 = 4 + match_len(src, s + 4, o2 + 4, end);
                 uint32_t nextHash = hash6(cv, hashLog);
-                e->table[nextHash].offset = s; e->table[nextHash].val = (uint32_t)cv;
+                e->table[nextHash].offset = s + e->cur; e->table[nextHash].val = (uint32_t)cv;
                 orc_blockenc_add_seq(blk, 0, (uint32_t)l2 - ORC_ZSTD_MINMATCH, 1);
                 s += l2;
                 nextEmit = s;
@@ -700,16 +700,49 @@ done:
 }
 
 static fast_state *fast_state_new(int32_t window) {
-    fast_state *e = (fast_state *)malloc(sizeof(*e));
-    for (int i = 0; i < FAST_TABLE_SIZE; i++) { e->table[i].val = 0; e->table[i].offset = -0x40000000; }
+    fast_state *e = (fast_state *)calloc(1, sizeof(*e));
     e->maxMatchOff = window;
+    e->cur = window; /* Reset on a fresh encoder: cur += maxMatchOff (enc_base.go:183-187) */
     return e;
+}
+/* fastBase.resetBase + the cur bump at the end of EncodeNoHist: everything already in the table ends
+ * up >= maxMatchOff away.  histLen = bytes the previous use put behind cur. */
+static void fast_state_reset(fast_state *e, int32_t histLen) {
+    const int32_t bufferReset = 0x7fffffff - 2 * e->maxMatchOff; /* encoder_options.go:51-73 */
+    if (e->cur >= bufferReset) {
+        memset(e->table, 0, sizeof(e->table));
+        e->cur = e->maxMatchOff;
+        return;
+    }
+    e->cur += e->maxMatchOff + histLen;
 }
 
 ORC_API void orc_enc_fast_nohist(orc_blockenc *b, const uint8_t *src, size_t n) {
     fast_state *e = fast_state_new(4 << 20);
     fast_encode_block(e, b, src, 0, (int32_t)n, 1);
     free(e);
+}
+
+/* Reusable encoder (one per host thread), the shape of the reference's pooled encoders
+ * (zstd/encoder.go:90-99,722-729): no allocation and no table clearing per EncodeAll call. */
+typedef struct {
+    orc_blockenc *blk;
+    fast_state *fast;
+    int32_t lastLen;
+} orc_zstd_cctx;
+
+ORC_API orc_zstd_cctx *orc_zstd_cctx_new(void) {
+    init_predef();
+    orc_zstd_cctx *c = (orc_zstd_cctx *)calloc(1, sizeof(*c));
+    c->blk = orc_blockenc_new();
+    c->fast = fast_state_new(4 << 20);
+    c->fast->cur = 0;
+    c->lastLen = 0;
+    return c;
+}
+ORC_API void orc_zstd_cctx_free(orc_zstd_cctx *c) {
+    if (!c) return;
+    orc_blockenc_free(c->blk); free(c->fast); free(c);
 }
 
 /* ----------------------------------------------------------------- frames */
@@ -751,7 +784,18 @@ static int32_t window_size_for(int64_t size, int32_t maxMatchOff) { /* fastBase.
 void orc_dfast_encode_all_blocks(orc_blockenc *blk, const uint8_t *src, size_t n, size_t blockSize,
                                  uint8_t *dst, size_t cap, size_t *pos, int *err);
 
+static int64_t encode_all_impl(orc_zstd_cctx *cc, const uint8_t *src, size_t n, int level, int crc, uint8_t *dst, size_t cap);
+
 ORC_API int64_t orc_zstd_encode_all(const uint8_t *src, size_t n, int level, int crc, uint8_t *dst, size_t cap) {
+    return encode_all_impl(NULL, src, n, level, crc, dst, cap);
+}
+/* EncodeAll on a reused encoder (level 1 only reuses state; other levels fall back to fresh state) */
+ORC_API int64_t orc_zstd_encode_all_ctx(orc_zstd_cctx *cc, const uint8_t *src, size_t n, int level, int crc,
+                                        uint8_t *dst, size_t cap) {
+    return encode_all_impl(level == 1 ? cc : NULL, src, n, level, crc, dst, cap);
+}
+
+static int64_t encode_all_impl(orc_zstd_cctx *cc, const uint8_t *src, size_t n, int level, int crc, uint8_t *dst, size_t cap) {
     init_predef();
     if (level != 1 && level != 2) return ORC_ERR_UNSUPPORTED;
     const size_t blockSize = (level == 1) ? (1u << 16) : ORC_ZSTD_MAX_BLOCK; /* encoder_options.go:41,248-252 */
@@ -765,17 +809,25 @@ ORC_API int64_t orc_zstd_encode_all(const uint8_t *src, size_t n, int level, int
     }
     int single = (n <= (size_t)windowSize) && (n > 1024);
     pos = frame_header(dst, n, (uint32_t)window_size_for((int64_t)n, windowSize), single, crc);
-    orc_blockenc *blk = orc_blockenc_new();
+    orc_blockenc *blk = cc ? cc->blk : orc_blockenc_new();
+    if (cc) { orc_blockenc_reset(blk); orc_blockenc_init_new_encode(blk); }
     int err = 0;
     if (level == 2) {
         orc_dfast_encode_all_blocks(blk, src, n, blockSize, dst, cap, &pos, &err);
     } else if (n <= blockSize) {
         orc_blockenc_reset(blk);
         blk->last = 1;
-        orc_enc_fast_nohist(blk, src, n);
+        if (cc) {
+            fast_state_reset(cc->fast, cc->lastLen);
+            fast_encode_block(cc->fast, blk, src, 0, (int32_t)n, 1);
+            cc->lastLen = (int32_t)n;
+        } else {
+            orc_enc_fast_nohist(blk, src, n);
+        }
         err = orc_blockenc_encode(blk, src, n, 0, 1, dst, cap, &pos);
     } else {
-        fast_state *e = fast_state_new(windowSize);
+        fast_state *e = cc ? cc->fast : fast_state_new(windowSize);
+        if (cc) { fast_state_reset(e, cc->lastLen); cc->lastLen = (int32_t)n; }
         size_t off = 0;
         while (off < n && !err) {
             size_t todo = n - off; if (todo > blockSize) todo = blockSize;
@@ -786,9 +838,9 @@ ORC_API int64_t orc_zstd_encode_all(const uint8_t *src, size_t n, int level, int
             orc_blockenc_reset(blk);
             off += todo;
         }
-        free(e);
+        if (!cc) free(e);
     }
-    orc_blockenc_free(blk);
+    if (!cc) orc_blockenc_free(blk);
     if (err) return err;
     if (crc) {
         if (pos + 4 > cap) return ORC_ERR_DST_SMALL;
