@@ -235,6 +235,8 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
             }
             __syncthreads();
             if (tid == 0) {
+                // order the previous chunk's generic-proxy accesses to this buffer before the async-proxy write
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(&sh->mbar, n);
                 tma_load_1d(src, gsrc, n, &sh->mbar);
             }
