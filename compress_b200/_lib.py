@@ -52,6 +52,10 @@ def _load():
     lib.b2c_zstd_encode_packed.argtypes = [
         c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_size_t, c.c_uint32, c.c_void_p, c.c_size_t, c.c_void_p,
         c.c_void_p, c.c_void_p]
+    lib.b2c_zstd_encode_device_timed.restype = c.c_int
+    lib.b2c_zstd_encode_device_timed.argtypes = [
+        c.c_void_p, c.c_int, c.c_void_p, c.c_size_t, c.c_uint32, c.c_void_p, c.c_size_t, c.c_void_p, c.c_uint32,
+        c.c_void_p, c.c_void_p]
     return lib
 
 
@@ -61,7 +65,7 @@ lib = _load()
 EXPORTED_SYMBOLS = [
     "b2c_device_count", "b2c_ctx_create", "b2c_ctx_destroy", "b2c_strerror", "b2c_last_cuda_error",
     "b2c_sm_count", "b2c_launch_count", "b2c_zstd_bound", "b2c_zstd_encode_device",
-    "b2c_zstd_encode_chunks", "b2c_zstd_encode_device_debug", "b2c_zstd_encode_packed",
+    "b2c_zstd_encode_chunks", "b2c_zstd_encode_device_debug", "b2c_zstd_encode_packed", "b2c_zstd_encode_device_timed",
 ]
 
 

@@ -204,7 +204,7 @@ size_t b2c_zstd_bound(size_t size, int level) {
 static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
                          const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
                          int64_t *d_out_sizes, uint32_t nchunks, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
-                         uint8_t *dbg_lits, uint32_t dbg_cap, cudaStream_t st) {
+                         uint8_t *dbg_lits, uint32_t dbg_cap, cudaStream_t st, unsigned long long *dbg_cycles = nullptr) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     if (level != B2C_LEVEL_FASTEST) return B2C_ERR_UNSUPPORTED;
     if (nchunks == 0) return B2C_OK;
@@ -216,6 +216,7 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
     P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.flags = (uint32_t)flags; P.scratch = ctx->d_scratch;
     P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_cap;
+    P.dbg_cycles = dbg_cycles;
     unsigned grid = (unsigned)ctx->sm_count;
     if (grid > nchunks) grid = nchunks;
     b2c_zstd_encode_kernel<<<grid, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
@@ -237,6 +238,13 @@ int b2c_zstd_encode_device_debug(b2c_ctx *ctx, int flags, const void *d_src, siz
                                  uint8_t *d_dbg_lits, uint32_t dbg_seq_cap, void *stream) {
     return launch_encode(ctx, B2C_LEVEL_FASTEST, flags, d_src, src_stride, d_sizes, size_all, d_dst, dst_stride,
                          d_out_sizes, nchunks, d_dbg_hdr, d_dbg_seqs, d_dbg_lits, dbg_seq_cap, (cudaStream_t)stream);
+}
+
+int b2c_zstd_encode_device_timed(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride, uint32_t size_all,
+                                 void *d_dst, size_t dst_stride, int64_t *d_out_sizes, uint32_t nchunks,
+                                 unsigned long long *d_cycles, void *stream) {
+    return launch_encode(ctx, B2C_LEVEL_FASTEST, flags, d_src, src_stride, nullptr, size_all, d_dst, dst_stride,
+                         d_out_sizes, nchunks, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream, d_cycles);
 }
 
 int b2c_zstd_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const *srcs, const size_t *src_sizes,

@@ -103,7 +103,21 @@ struct ZstdEncParams {
     uint32_t *dbg_seqs;           // [nchunks][dbg_seq_cap][3]
     uint8_t *dbg_lits;            // [nchunks][65536]
     uint32_t dbg_seq_cap;
+    unsigned long long *dbg_cycles;  // optional [nchunks][16][32] per-warp arrival stamps (clock64)
 };
+
+#ifdef B2C_EMU
+#define B2C_PHASE(k) do { } while (0)
+#else
+// Every warp's lane 0 stamps clock64 right after each barrier.  BAR.SYNC does not block at issue (the wait is
+// deferred to the next access of barrier-protected state), so the stamp captures the warp's ARRIVAL time at the
+// preceding barrier; the barrier's release time is the maximum over warps (tools/phase_times.py).
+#define B2C_PHASE(k)                                                                                   \
+    do {                                                                                               \
+        if (P.dbg_cycles && (threadIdx.x & 31) == 0)                                                   \
+            P.dbg_cycles[((uint64_t)chunk * 16 + (k)) * 32 + (threadIdx.x >> 5)] = (unsigned long long)clock64(); \
+    } while (0)
+#endif
 
 // zstd/hash.go:27 hashLen(u, 32, 6): top 32 bits of ((u << 16) * prime6bytes)
 B2C_DEV uint32_t enc_hash6(uint64_t u) {
@@ -224,6 +238,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
         return;
     }
 
+    B2C_PHASE(0);
     // ---------------------------------------------------------------- P0: stage the chunk
     {
 #ifndef B2C_EMU
@@ -258,6 +273,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
 #endif
     }
     const uint32_t sub = (((n + ENC_NPARSE - 1) / ENC_NPARSE) + 31) & ~31u;  // sub-range size
+    B2C_PHASE(1);
 
     // ---------------------------------------------------------------- P1: earliest-occurrence table
     const uint32_t npos = (n >= 8) ? n - 7 : 0;  // positions with 8 readable bytes
@@ -279,6 +295,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
         }
     }
 
+    B2C_PHASE(2);
     // ---------------------------------------------------------------- P2: parse (warps 0..30), XXH64 (warp 31)
     if (w == ENC_NPARSE) {
         if (crc) {
@@ -361,6 +378,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
         }
     }
     __syncthreads();
+    B2C_PHASE(3);
 
     // ---------------------------------------------------------------- P3: global sequence/literal layout
     if (tid == 0) {
@@ -447,6 +465,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
     }
     __syncthreads();
     kind = sh->kind;
+    B2C_PHASE(4);
 
     if (kind == 0) {
         // ------------------------------------------------------------ P5: histograms
@@ -489,12 +508,14 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
         if (nlit > 16) huf_histogram(lit, nlit, whist, &sh->hw, tid, ENC_NT, 0);
         else __syncthreads();
 
+        B2C_PHASE(5);
         // ------------------------------------------------------------ P6: tables
         if (nlit > 16) { huf_bt_stats(&sh->hw, nlit, tid); } else if (tid == 0) sh->hw.status = HUF_INCOMPRESSIBLE;
         __syncthreads();
         const bool hufTry = sh->hw.status == HUF_OK;
         if (hufTry) huf_bt_sort(&sh->hw, tid, ENC_NT);
         __syncthreads();
+        B2C_PHASE(6);
         // serial table builders side by side: warp 0 Huffman tree, warps 1..3 the FSE tables
         if (tid == 0 && hufTry) huf_bt_tree(&sh->hw, nlit);
         if (lane == 0 && w >= 1 && w <= 3) {
@@ -502,6 +523,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
             seq_build_table(&sh->sw, which, nseq, codes[which * codeStride + 0]);
         }
         __syncthreads();
+        B2C_PHASE(7);
         if (hufTry) huf_bt_bits(&sh->hw, tid, ENC_NT);
         __syncthreads();
         if (hufTry) huf_bt_vals(&sh->hw, tid, ENC_NT);
@@ -515,6 +537,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
         }
         __syncthreads();
 
+        B2C_PHASE(8);
         // ------------------------------------------------------------ P7: literals section
         const bool four = nlit >= 1024;
         HufEncState hst;
@@ -558,6 +581,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
         const uint32_t tblOff = seqOff + nsHdr + 1;
         const uint32_t bsOff = tblOff + sh->sw.ncountLen[0] + sh->sw.ncountLen[1] + sh->sw.ncountLen[2];
 
+        B2C_PHASE(9);
         // P8 sizes of the sequence bitstream (every thread owns a run of consecutive t = nseq-1-idx)
         const uint16_t *stbLL = reinterpret_cast<const uint16_t *>(scratch + SCR_STB);
         const uint16_t *stbOF = stbLL + ENC_MAXSEQ;
@@ -583,6 +607,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
         // blockenc.go:811-817: not smaller than the input => raw block.  Also covers staging overflow.
         const bool useRaw = (blockBytes >= n) || (total + 8 > ENC_SRC_BYTES) || sh->sw.err;
         __syncthreads();  // everyone is done reading src/stage-overlapping data? (src no longer needed)
+        B2C_PHASE(10);
         if (!useRaw) {
             // zero the staging words that receive bit-granular output
             uint32_t zw = (total + 8 + 3) / 4;
@@ -597,6 +622,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
                 stage[litOff] = lit[0];
             }
             __syncthreads();  // byte stores above must not race the word atomics below
+            B2C_PHASE(11);
             // sequence bitstream
             {
                 BitRun br;
@@ -625,6 +651,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
                 br.finish();
             }
             __syncthreads();
+            B2C_PHASE(12);
             // byte-granular headers (after all word-granular atomics)
             if (tid == 0) {
                 uint32_t o = 0;
@@ -675,6 +702,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
                 sh->outBytes = total;
             }
             __syncthreads();
+            B2C_PHASE(13);
             // one coalesced write-back
             if (total <= P.dst_cap) {
                 if ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) {
@@ -693,6 +721,7 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
                 d[0] = nseq; d[1] = nlit; d[2] = 0; d[3] = litMode;
             }
             __syncthreads();
+            B2C_PHASE(14);
             return;
         }
         kind = 1;  // fall through to the raw block
