@@ -15,7 +15,9 @@ struct b2c_ctx {
     int device = 0;
     int sm_count = 0;
     size_t max_chunks = 0;
-    uint8_t *d_scratch = nullptr;       // sm_count * ENC_SCRATCH_BYTES
+    uint8_t *d_scratch = nullptr;       // sm_count * ENC_SCRATCH_BYTES (two sets: one per pipeline slot)
+    ChunkWork *d_work[2] = {nullptr, nullptr};   // per-chunk work records, grown on demand
+    size_t work_cap[2] = {0, 0};
     // host-buffer path staging (slot 0 of the pipeline doubles as the pointer-table path's buffers)
     uint8_t *h_in = nullptr;            // pinned, max_chunks * 64 KiB
     uint8_t *h_out = nullptr;           // pinned, max_chunks * slot
@@ -125,10 +127,14 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return nullptr; }
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = true;
-    ok = ok && cudaMalloc(&ctx->d_scratch, (size_t)ctx->sm_count * ENC_SCRATCH_BYTES) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_scratch, 2 * (size_t)ctx->sm_count * ENC_SCRATCH_BYTES) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(b2c_zstd_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)ENC_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)CHAIN_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)PACK_SMEM_BYTES) == cudaSuccess;
     if (ok && max_chunks) {
         ok = ok && cudaMallocHost(&ctx->h_in, max_chunks * (size_t)ENC_MAX_CHUNK) == cudaSuccess;
         ok = ok && cudaMallocHost(&ctx->h_out, max_chunks * (size_t)kSlot) == cudaSuccess;
@@ -159,7 +165,7 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
 void b2c_ctx_destroy(b2c_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_scratch); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
+    cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
     cudaFree(ctx->d_sizes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_src_sizes);
     cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_sizes); cudaFreeHost(ctx->h_src_sizes);
     cudaFree(ctx->d_in2); cudaFree(ctx->d_out2); cudaFree(ctx->d_packed2); cudaFree(ctx->d_sizes2);
@@ -204,23 +210,40 @@ size_t b2c_zstd_bound(size_t size, int level) {
 static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
                          const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
                          int64_t *d_out_sizes, uint32_t nchunks, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
-                         uint8_t *dbg_lits, uint32_t dbg_cap, cudaStream_t st, unsigned long long *dbg_cycles = nullptr) {
+                         uint8_t *dbg_lits, uint32_t dbg_cap, cudaStream_t st, unsigned long long *dbg_cycles = nullptr,
+                         int slot = 0) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     if (level != B2C_LEVEL_FASTEST) return B2C_ERR_UNSUPPORTED;
     if (nchunks == 0) return B2C_OK;
     if (dst_stride > 0xffffffffull) return B2C_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    if (ctx->work_cap[slot] < nchunks) {
+        // grow the per-chunk work records (kernels of earlier calls on other streams may still use the old one)
+        CK(cudaDeviceSynchronize());
+        if (ctx->d_work[slot]) CK(cudaFree(ctx->d_work[slot]));
+        ctx->d_work[slot] = nullptr; ctx->work_cap[slot] = 0;
+        CK(cudaMalloc(&ctx->d_work[slot], (size_t)nchunks * sizeof(ChunkWork)));
+        ctx->work_cap[slot] = nchunks;
+    }
     ZstdEncParams P;
     memset(&P, 0, sizeof(P));
     P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_sizes = d_sizes; P.src_size_all = size_all;
     P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
-    P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.flags = (uint32_t)flags; P.scratch = ctx->d_scratch;
+    P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.flags = (uint32_t)flags;
+    P.scratch = ctx->d_scratch + (size_t)slot * ctx->sm_count * ENC_SCRATCH_BYTES;
+    P.work = ctx->d_work[slot];
     P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_cap;
     P.dbg_cycles = dbg_cycles;
-    unsigned grid = (unsigned)ctx->sm_count;
-    if (grid > nchunks) grid = nchunks;
-    b2c_zstd_encode_kernel<<<grid, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
-    ctx->launches++;
+    unsigned sms = (unsigned)ctx->sm_count;
+    unsigned g1 = sms < nchunks ? sms : nchunks;
+    unsigned g2 = sms * 8 < nchunks ? sms * 8 : nchunks;
+    if ((flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC))
+        b2c_zstd_xxh_kernel<<<(4 * nchunks + 127) / 128, 128, 0, st>>>(P);
+    b2c_zstd_parse_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+    b2c_zstd_tables_kernel<<<g2, 128, 0, st>>>(P);
+    b2c_zstd_chains_kernel<<<(nchunks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, st>>>(P);
+    b2c_zstd_pack_kernel<<<nchunks, PACK_NT, PACK_SMEM_BYTES, st>>>(P);
+    ctx->launches += 5;
     CK(cudaGetLastError());
     return B2C_OK;
 }
@@ -359,7 +382,7 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
             d_ss = S.d_ss;
         }
         int r = launch_encode(ctx, level, flags, S.d_in, chunk_size, d_ss, chunk_size, S.d_out, kSlot, S.d_sizes,
-                              (uint32_t)m, nullptr, nullptr, nullptr, 0, S.st);
+                              (uint32_t)m, nullptr, nullptr, nullptr, 0, S.st, nullptr, (int)(b & 1));
         if (r) return r;
         b2c_scan_sizes_kernel<<<1, 1024, 0, S.st>>>(S.d_sizes, S.d_off, (uint32_t)m);
         b2c_pack_kernel<<<ctx->sm_count * 4, 256, 0, S.st>>>(S.d_out, kSlot, S.d_sizes, S.d_off, S.d_packed, (uint32_t)m);

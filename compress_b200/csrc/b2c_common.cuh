@@ -31,6 +31,13 @@ B2C_DEV void bar_sync(int id, int nthreads) {
 #endif
 }
 
+// Barrier over a thread group: bar_id 0 = whole CTA, 1..15 = named barrier over nthreads, < 0 = one warp.
+B2C_DEV void group_sync(int bar_id, int nthreads) {
+    if (bar_id == 0) __syncthreads();
+    else if (bar_id < 0) __syncwarp();
+    else bar_sync(bar_id, nthreads);
+}
+
 // ---- unaligned little-endian loads from a 4-byte aligned base (shared or global).
 // Reads the aligned words covering [pos, pos+len); the buffer must be padded.
 B2C_DEV uint32_t ld32u(const uint8_t *base, uint32_t pos) {
@@ -81,7 +88,7 @@ B2C_DEV uint32_t group_scan_excl(uint32_t v, uint32_t *ws, int bar_id, int nthre
     unsigned lane = tid_in_group & 31, w = tid_in_group >> 5;
     uint32_t incl = warp_scan_incl(v);
     if (lane == 31) ws[w] = incl;
-    if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, nthreads);
+    group_sync(bar_id, nthreads);
     if (w == 0) {
         int nw = nthreads >> 5;
         uint32_t x = (lane < (unsigned)nw) ? ws[lane] : 0;
@@ -89,7 +96,7 @@ B2C_DEV uint32_t group_scan_excl(uint32_t v, uint32_t *ws, int bar_id, int nthre
         ws[lane] = xi - x;  // exclusive warp bases
         if (lane == 31) ws[32] = xi;
     }
-    if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, nthreads);
+    group_sync(bar_id, nthreads);
     uint32_t base = ws[w];
     *total = ws[32];
     // callers must place a barrier before reusing ws

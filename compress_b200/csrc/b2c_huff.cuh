@@ -63,13 +63,13 @@ B2C_DEV void huf_histogram(const uint8_t *in, uint32_t n, uint32_t *whist, HufWo
         }
         __syncwarp();
     }
-    if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, (int)nthreads);
+    group_sync(bar_id, (int)nthreads);
     for (unsigned s = tid; s < 256; s += nthreads) {
         uint32_t c = 0;
         for (unsigned k = 0; k < nw; k++) c += whist[k * 256 + s];
         hw->count[s] = c;
     }
-    if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, (int)nthreads);
+    group_sync(bar_id, (int)nthreads);
 }
 
 // ---------------------------------------------------------------- serial helpers (one thread)
@@ -370,7 +370,7 @@ B2C_DEV void huf_bt_write(HufWork *hw) {
 }
 // Convenience: whole build with barriers (all threads of the group call).
 B2C_DEV void huf_build_table(HufWork *hw, uint32_t n, unsigned tid, unsigned nthreads, int bar_id) {
-#define HSYNC() do { if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, (int)nthreads); } while (0)
+#define HSYNC() do { group_sync(bar_id, (int)nthreads); } while (0)
     huf_bt_stats(hw, n, tid);
     HSYNC();
     if (hw->status != HUF_OK) return;
@@ -424,7 +424,7 @@ struct HufEncState {
 // returns payload bytes = table desc + (jump table) + streams
 B2C_DEV uint32_t huf_enc_sizes(HufWork *hw, const uint8_t *lit, uint32_t n, int four, unsigned tid,
                                unsigned nthreads, int bar_id, HufEncState *st) {
-#define HSYNC() do { if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, (int)nthreads); } while (0)
+#define HSYNC() do { group_sync(bar_id, (int)nthreads); } while (0)
     int nstreams = four ? 4 : 1;
     HufSeg sg = huf_thread_seg(n, nstreams, tid, nthreads);
     unsigned per = nthreads / (unsigned)nstreams;
@@ -453,7 +453,7 @@ B2C_DEV uint32_t huf_enc_sizes(HufWork *hw, const uint8_t *lit, uint32_t n, int 
 // stageBase: 4-byte aligned, zero-initialised words; payload starts at byte offset byteOff.
 B2C_DEV void huf_enc_pack(HufWork *hw, const uint8_t *lit, int four, uint8_t *stageBase, uint32_t byteOff,
                           unsigned tid, unsigned nthreads, int bar_id, const HufEncState *st) {
-#define HSYNC() do { if (bar_id == 0) __syncthreads(); else bar_sync(bar_id, (int)nthreads); } while (0)
+#define HSYNC() do { group_sync(bar_id, (int)nthreads); } while (0)
     const HufSeg &sg = st->sg;
     {
         BitRun br;

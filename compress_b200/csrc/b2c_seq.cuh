@@ -21,6 +21,7 @@ namespace b2c {
 
 enum { TBL_LL = 0, TBL_OF = 1, TBL_ML = 2 };
 constexpr int SEQ_WARMUP = 24;
+constexpr uint32_t SEQ_TABLE_ERR = 0xffffffffu;  // ncountLen marker: table construction failed
 
 struct SeqWork {
     FseCTable cur[3];
@@ -135,7 +136,9 @@ B2C_DEV void seq_build_table(SeqWork *sw, int which, uint32_t nseq, uint32_t fir
     }
     ct->useRLE = 0;
     for (uint32_t i = 0; i < FSE_MAX_SYM; i++) ct->norm[i] = 0;
-    if (fse_normalize(hist, symbolLen, nseq, ct->tableLog, ct->norm) || fse_build_ctable(ct)) { sw->err = 1; return; }
+    if (fse_normalize(hist, symbolLen, nseq, ct->tableLog, ct->norm) || fse_build_ctable(ct)) {
+        sw->mode[which] = 0; sw->used[which] = 0; sw->ncountLen[which] = SEQ_TABLE_ERR; return;
+    }
     // chooseComp, blockenc.go:633-661 (prev == never valid for an independent block)
     uint32_t nSize = fse_approx_size(ct, hist, symbolLen) + (((symbolLen * ct->tableLog) >> 3) + 3) * 8;
     uint32_t predefSize = fse_approx_size(&sw->predef[which], hist, symbolLen);
@@ -143,7 +146,7 @@ B2C_DEV void seq_build_table(SeqWork *sw, int which, uint32_t nseq, uint32_t fir
     if (predefSize <= nSize) { sw->mode[which] = 0; sw->used[which] = 0; sw->ncountLen[which] = 0; return; }
     sw->mode[which] = 2; sw->used[which] = 1;
     int w = fse_write_ncount(ct->norm, symbolLen, ct->tableLog, sw->ncount[which]);
-    if (w < 0) { sw->err = 1; return; }
+    if (w < 0) { sw->mode[which] = 0; sw->used[which] = 0; sw->ncountLen[which] = SEQ_TABLE_ERR; return; }
     sw->ncountLen[which] = (uint32_t)w;
 }
 

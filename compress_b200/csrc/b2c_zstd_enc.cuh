@@ -1,28 +1,31 @@
-// compress_b200/csrc/b2c_zstd_enc.cuh -- fused zstd "SpeedFastest" chunk encoder for sm_100a.
+// compress_b200/csrc/b2c_zstd_enc.cuh -- zstd "SpeedFastest" chunk encoder for sm_100a.
 //
-// One persistent CTA (1024 threads, one per SM) turns one independent <= 64 KiB chunk into one
-// complete zstd frame (what zstd.Encoder.EncodeAll does per call, zstd/encoder.go:722-839) or a
-// bare block.  It replaces, for the GPU path, the reference's
+// Turns N independent <= 64 KiB chunks into N complete zstd frames (what one zstd.Encoder.EncodeAll call does
+// per chunk, zstd/encoder.go:722-839) or bare blocks.  Replaces, for the GPU path, the reference's
 //   zstd/enc_fast.go:294-531  fastEncoder.EncodeNoHist      (match finding)
-//   zstd/blockenc.go:481-826  blockEnc.encode               (entropy stage, bit-exact here)
+//   zstd/blockenc.go:481-826  blockEnc.encode               (entropy stage, byte-identical here)
 //   zstd/frameenc.go:25-92    frameHeader.appendTo
 //   zstd/internal/xxhash      XXH64 frame checksum
 //
-// B200-first design (not a port of the serial Go loop):
-//   * the chunk is staged into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier);
-//   * match finding is split over 31 warps, each parsing its own 2 KiB sub-range 32 positions at a
-//     time: every lane hashes its position (hash6, zstd/hash.go), probes a private per-warp table
-//     (most recent occurrence in the sub-range) and a CTA-wide table holding the EARLIEST
-//     occurrence of each hash in the whole chunk (built by a race-free min-reduction pre-pass, so
-//     every candidate lies before the probing position and the output is deterministic), verifies
-//     4 bytes in shared memory, and the warp picks matches greedily with ballot/ffs and extends
-//     them 128 bytes per step with ballot.  The 32nd warp computes XXH64 meanwhile;
-//   * literals are gathered into shared memory, Huffman/FSE tables are built with the
-//     reference's exact tie-breaking, the three tANS chains are walked speculatively in parallel
-//     (b2c_seq.cuh) and all bitstreams are packed at prefix-summed bit offsets into a staging
-//     buffer that is written back with one coalesced copy.
-// Sequences differ from the reference's greedy parse (the parse is position-parallel), the
-// entropy stage is byte-identical to blockEnc.encode for the same (literals, sequences).
+// B200-first design: a pipeline of five kernels on one stream, each shaped after the parallelism its
+// stage really has, with a per-chunk work record (ChunkWork) in HBM/L2 between them:
+//   K1 parse    one CTA per chunk (persistent grid = #SMs, 1024 threads).  The chunk is staged into shared
+//               memory with one TMA bulk copy.  32 warps each parse a 2 KiB sub-range 32 positions per
+//               step: every lane hashes its position, probes a private per-warp table (most recent
+//               occurrence in the sub-range) and a CTA-wide table of the EARLIEST occurrence of each hash
+//               in the chunk (built by a race-free min-reduction, so candidates always precede the
+//               position and the output is deterministic), compares 8 bytes in shared memory, and the warp
+//               selects matches greedily with ballot/ffs.  Then literals are gathered, sequences
+//               compacted, codes and histograms computed with all threads.
+//   K2 tables   one 4-warp CTA per chunk: the Huffman table (reference tie-breaking) and the three FSE
+//               tables are tiny serial problems -- thousands of them run side by side.
+//   K3 chains   one LANE per (chunk, tANS chain): the reference's serial state walk, 32 chunks per warp.
+//   K4 pack     one CTA per chunk: code-length / bit-count prefix sums, every thread packs its own bit
+//               range of the 4 Huffman streams and of the sequence bitstream into a staging buffer,
+//               headers, one coalesced write-back (raw / RLE block fallbacks included).
+//   K5 xxh64    four lanes per chunk (the four XXH64 accumulators).
+// The parse differs from the reference's serial greedy parse; the entropy stage is byte-identical to
+// blockEnc.encode for the same (literals, sequences) -- tests/check_util.py verifies both properties.
 #pragma once
 #include "b2c_common.cuh"
 #include "b2c_fse.cuh"
@@ -31,87 +34,71 @@
 
 namespace b2c {
 
-constexpr int ENC_NT = 1024;              // threads per CTA
-constexpr int ENC_NW = ENC_NT / 32;       // 32 warps
-constexpr int ENC_NPARSE = ENC_NW - 1;    // 31 parsing warps, warp 31 hashes (XXH64)
+constexpr int ENC_NT = 1024;              // K1 threads per CTA
+constexpr int ENC_NW = ENC_NT / 32;       // 32 parsing warps
 constexpr int ENC_EBITS = 15;             // earliest-occurrence table: 32 Ki x u16
 constexpr int ENC_LBITS = 10;             // per-warp recent table: 1 Ki x u16
 constexpr uint32_t ENC_MAX_CHUNK = 1u << 16;
 constexpr uint32_t ENC_SRC_BYTES = ENC_MAX_CHUNK + 128;   // chunk + zero padding
 constexpr uint32_t ENC_E_BYTES = (1u << ENC_EBITS) * 2;
-constexpr uint32_t ENC_L_BYTES = ENC_NPARSE * (1u << ENC_LBITS) * 2;
-constexpr uint32_t ENC_SEGCAP = 560;      // max records per parse warp: ceil(2144 / 4) + slack
+constexpr uint32_t ENC_L_BYTES = ENC_NW * (1u << ENC_LBITS) * 2;
+constexpr uint32_t ENC_SEGCAP = 528;      // max records per parse warp: 2048 / 4 + slack
 constexpr uint32_t ENC_MAXSEQ = 16384 + 64;
-constexpr uint32_t ENC_CODES_SMEM_CAP = 8192;
-
-// per-CTA global scratch layout (bytes)
-constexpr uint32_t SCR_REC = 0;                                   // parse records: NPARSE x SEGCAP x 8
-constexpr uint32_t SCR_LL = SCR_REC + ENC_NPARSE * ENC_SEGCAP * 8;  // u16[MAXSEQ]
-constexpr uint32_t SCR_ML = SCR_LL + ENC_MAXSEQ * 2;              // u16[MAXSEQ]
-constexpr uint32_t SCR_OF = SCR_ML + ENC_MAXSEQ * 2;              // u32[MAXSEQ]
-constexpr uint32_t SCR_STB = SCR_OF + ENC_MAXSEQ * 4;             // u16[3][MAXSEQ]
-constexpr uint32_t SCR_CODES = SCR_STB + ENC_MAXSEQ * 6;          // u8[3][MAXSEQ] (only if nseq > smem cap)
-constexpr uint32_t ENC_SCRATCH_BYTES = ((SCR_CODES + ENC_MAXSEQ * 3 + 255) / 256) * 256;
+constexpr int PACK_NT = 512;              // K4 threads per CTA
+constexpr uint32_t ENC_SCRATCH_BYTES = ENC_NW * ENC_SEGCAP * 8;  // per-CTA parse records
 
 enum { ENC_FLAG_CRC = 1, ENC_FLAG_FRAME = 2 };
 
-struct EncShared {
-    uint32_t cnt[32];       // records per parse warp
-    uint32_t tail[32];      // trailing literal bytes of each sub-range
-    uint32_t sumLL[32];     // literal bytes inside each sub-range (incl. tail)
-    uint32_t seqBase[32];
-    uint32_t litBase[32];
-    uint32_t carry[32];     // literal bytes carried into the warp's first sequence
-    uint32_t nseq, nlit, n, sub;
-    uint32_t kind;          // 0 compressed, 1 raw block, 2 RLE block
-    uint32_t rleLen;
-    uint32_t litMode;       // 0 raw, 1 RLE, 2 compressed
-    uint32_t litPayload;    // compressed literal payload bytes
-    uint32_t lhSize;
-    uint32_t pos;           // running output byte offset inside the staging buffer
-    uint32_t seqBitsBase;   // bit offset where the sequence bitstream starts (inside staging)
-    uint32_t outBytes;
-    uint32_t fhSize;
-    uint64_t xxh;
-    uint64_t mbar;
-    HufWork hw;
-    SeqWork sw;
+// Per-chunk work record handed from kernel to kernel (global memory, L2 resident for the active chunks).
+struct alignas(16) ChunkWork {
+    uint32_t n, nseq, nlit, kind;          // kind: 0 compressed candidate, 1 raw block, 2 RLE block, 3 too big
+    uint32_t rleLen, hufStatus, hufTableLog, tableDescLen;
+    uint32_t maxSym[3], pad0;
+    uint32_t mode[3], pad1;                // 0 predefined, 1 RLE, 2 FSE
+    uint32_t ncountLen[3], pad2;
+    uint32_t finalState[3], pad3;
+    unsigned long long xxh;
+    uint32_t litHist[256];
+    uint32_t seqHist[3][64];
+    uint16_t ctVal[256];
+    uint8_t ctBits[256];
+    uint8_t tableDesc[320];
+    uint8_t ncount[3][96];
+    FseCTable tbl[3];                      // the table each chain uses (new, predefined copy, or RLE)
+    alignas(16) uint8_t lit[ENC_MAX_CHUNK + 64];
+    uint16_t seqLL[ENC_MAXSEQ];
+    uint16_t seqML[ENC_MAXSEQ];
+    uint32_t seqOF[ENC_MAXSEQ];
+    uint8_t codes[3][ENC_MAXSEQ];
+    uint16_t stb[3][ENC_MAXSEQ];
 };
 
-constexpr uint32_t ENC_SMEM_SRC = 0;
-constexpr uint32_t ENC_SMEM_E = ENC_SMEM_SRC + ENC_SRC_BYTES;
-constexpr uint32_t ENC_SMEM_L = ENC_SMEM_E + ENC_E_BYTES;
-constexpr uint32_t ENC_SMEM_SH = ENC_SMEM_L + ENC_L_BYTES;
-constexpr uint32_t ENC_SMEM_BYTES = ENC_SMEM_SH + ((sizeof(EncShared) + 15) / 16) * 16;
-
 struct ZstdEncParams {
-    const uint8_t *const *srcs;   // per-chunk source pointers (device) or nullptr
-    const uint8_t *src_base;      // used when srcs == nullptr: chunk i at src_base + i * src_stride
+    const uint8_t *src_base;      // chunk i at src_base + i * src_stride
     uint64_t src_stride;
     const uint32_t *src_sizes;    // per-chunk sizes (<= 65536); nullptr => all chunks are src_size_all
     uint32_t src_size_all;
-    uint8_t *const *dsts;         // per-chunk destination pointers or nullptr
-    uint8_t *dst_base;            // used when dsts == nullptr
+    uint8_t *dst_base;
     uint64_t dst_stride;
     uint32_t dst_cap;             // capacity of every destination slot
     int64_t *out_sizes;           // bytes written per chunk, negative = error
     uint32_t nchunks;
     uint32_t flags;
-    uint8_t *scratch;             // gridDim.x * ENC_SCRATCH_BYTES
+    uint8_t *scratch;             // gridDim.x(K1) * ENC_SCRATCH_BYTES
+    ChunkWork *work;              // [nchunks]
     // optional debug dump (tests): per chunk {nseq, nlit, kind, litMode} + seq triples + literals
     uint32_t *dbg_hdr;            // [nchunks][4]
     uint32_t *dbg_seqs;           // [nchunks][dbg_seq_cap][3]
     uint8_t *dbg_lits;            // [nchunks][65536]
     uint32_t dbg_seq_cap;
-    unsigned long long *dbg_cycles;  // optional [nchunks][16][32] per-warp arrival stamps (clock64)
+    unsigned long long *dbg_cycles;  // optional [nchunks][16][32] per-warp stamps inside K1 (clock64)
 };
 
 #ifdef B2C_EMU
 #define B2C_PHASE(k) do { } while (0)
 #else
-// Every warp's lane 0 stamps clock64 right after each barrier.  BAR.SYNC does not block at issue (the wait is
-// deferred to the next access of barrier-protected state), so the stamp captures the warp's ARRIVAL time at the
-// preceding barrier; the barrier's release time is the maximum over warps (tools/phase_times.py).
+// Every warp's lane 0 stamps clock64 right after each barrier.  BAR.SYNC does not block at issue, so the stamp
+// captures the warp's ARRIVAL time at the preceding barrier; the release time is the maximum over warps.
 #define B2C_PHASE(k)                                                                                   \
     do {                                                                                               \
         if (P.dbg_cycles && (threadIdx.x & 31) == 0)                                                   \
@@ -119,9 +106,12 @@ struct ZstdEncParams {
     } while (0)
 #endif
 
-// zstd/hash.go:27 hashLen(u, 32, 6): top 32 bits of ((u << 16) * prime6bytes)
-B2C_DEV uint32_t enc_hash6(uint64_t u) {
+B2C_DEV uint32_t chunk_size(const ZstdEncParams &P, uint32_t c) { return P.src_sizes ? P.src_sizes[c] : P.src_size_all; }
+
+// 6-byte multiplicative hash (same construction as zstd/hash.go hashLen(u, 32, 6))
+B2C_DEV uint32_t enc_hash6(uint32_t lo, uint32_t hi) {
     const uint64_t prime6 = 227718039650203ull;
+    uint64_t u = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(((u << 16) * prime6) >> 32);
 }
 
@@ -148,96 +138,41 @@ B2C_DEV uint32_t warp_match_len(const uint8_t *src, uint32_t a, uint32_t b, uint
         k += 128;
     }
 }
-// number of equal bytes going backwards: src[a-1-i] == src[b-1-i], i < maxBack
-B2C_DEV uint32_t warp_match_back(const uint8_t *src, uint32_t a, uint32_t b, uint32_t maxBack) {
-    unsigned lane = lane_id();
-    uint32_t k = 0;
-    for (;;) {
-        uint32_t i = k + lane;
-        bool ok = (i < maxBack) && (src[a - 1 - i] == src[b - 1 - i]);
-        unsigned stop = __ballot_sync(FULLMASK, !ok);
-        if (stop) return k + (uint32_t)(__ffs((int)stop) - 1);
-        k += 32;
-    }
-}
 
-// XXH64 of src[0..n) (8-byte aligned shared memory), computed by lanes 0..3 of one warp
-B2C_DEV uint64_t warp_xxh64(const uint8_t *src, uint32_t n) {
-    const uint64_t P1 = 11400714785074694791ull, P2 = 14029467366897019727ull, P3 = 1609587929392839161ull,
-                   P4 = 9650029242287828579ull, P5 = 2870177450012600261ull;
-    unsigned lane = lane_id();
-    uint64_t h = 0;
-    uint32_t p = 0;
-    if (n >= 32) {
-        uint64_t v = (lane == 0) ? P1 + P2 : (lane == 1) ? P2 : (lane == 2) ? 0ull : (0ull - P1);
-        uint32_t stripes = n / 32;
-        if (lane < 4) {
-            const uint64_t *q = reinterpret_cast<const uint64_t *>(src) + lane;
-            for (uint32_t i = 0; i < stripes; i++) {
-                uint64_t in = q[4 * i];
-                v += in * P2;
-                v = (v << 31) | (v >> 33);
-                v *= P1;
-            }
-        }
-        p = stripes * 32;
-        uint64_t v1 = __shfl_sync(FULLMASK, v, 0), v2 = __shfl_sync(FULLMASK, v, 1), v3 = __shfl_sync(FULLMASK, v, 2),
-                 v4 = __shfl_sync(FULLMASK, v, 3);
-        h = ((v1 << 1) | (v1 >> 63)) + ((v2 << 7) | (v2 >> 57)) + ((v3 << 12) | (v3 >> 52)) + ((v4 << 18) | (v4 >> 46));
-#define XMERGE(vv)                                                                                     \
-    do {                                                                                               \
-        uint64_t t_ = (vv) * P2; t_ = (t_ << 31) | (t_ >> 33); t_ *= P1;                               \
-        h ^= t_; h = h * P1 + P4;                                                                      \
-    } while (0)
-        XMERGE(v1); XMERGE(v2); XMERGE(v3); XMERGE(v4);
-#undef XMERGE
-    } else {
-        h = P5;
-    }
-    h += (uint64_t)n;
-    while (p + 8 <= n) {
-        uint64_t k1 = ld64u(src, p) * P2; k1 = (k1 << 31) | (k1 >> 33); k1 *= P1;
-        h ^= k1; h = ((h << 27) | (h >> 37)) * P1 + P4;
-        p += 8;
-    }
-    if (p + 4 <= n) {
-        h ^= (uint64_t)ld32u(src, p) * P1;
-        h = ((h << 23) | (h >> 41)) * P2 + P3;
-        p += 4;
-    }
-    while (p < n) {
-        h ^= (uint64_t)src[p] * P5;
-        h = ((h << 11) | (h >> 53)) * P1;
-        p++;
-    }
-    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
-    return h;
-}
+struct ParseShared {
+    uint32_t cnt[32];       // records per parse warp
+    uint32_t tail[32];      // trailing literal bytes of each sub-range
+    uint32_t sumLL[32];     // literal bytes inside each sub-range (incl. tail)
+    uint32_t seqBase[32];
+    uint32_t litBase[32];
+    uint32_t carry[32];     // literal bytes carried into the warp's first sequence
+    uint32_t nseq, nlit, kind, rleLen;
+    uint64_t mbar;
+};
+constexpr uint32_t ENC_SMEM_SRC = 0;
+constexpr uint32_t ENC_SMEM_E = ENC_SMEM_SRC + ENC_SRC_BYTES;
+constexpr uint32_t ENC_SMEM_L = ENC_SMEM_E + ENC_E_BYTES;
+constexpr uint32_t ENC_SMEM_SH = ENC_SMEM_L + ENC_L_BYTES;
+constexpr uint32_t ENC_SMEM_BYTES = ENC_SMEM_SH + ((sizeof(ParseShared) + 15) / 16) * 16;
 
-// ------------------------------------------------------------------------------------------------
-// The chunk encoder.  All 1024 threads call.  smem = dynamic shared memory base (16-byte aligned).
-B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk, uint8_t *scratch) {
+// ------------------------------------------------------------------------------------------------ K1
+B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk, uint8_t *scratch) {
     const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     uint8_t *src = smem + ENC_SMEM_SRC;
     uint16_t *E = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_E);
     uint16_t *Lall = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_L);
-    EncShared *sh = reinterpret_cast<EncShared *>(smem + ENC_SMEM_SH);
+    ParseShared *sh = reinterpret_cast<ParseShared *>(smem + ENC_SMEM_SH);
     uint8_t *lit = smem + ENC_SMEM_E;                                      // after the parse
-    uint8_t *stage = smem + ENC_SMEM_SRC;                                  // after the literal gather
-    uint32_t *whist = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L);     // [32][256] literal histograms
-    uint8_t *codesS = smem + ENC_SMEM_L + 32 * 256 * 4;                    // u8[3][CODES_SMEM_CAP]
+    uint16_t *lhist = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_L);     // [4][256][32] u16 lane-column counters
+    uint32_t *shist = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_SRC);   // [32][192] seq-code histograms (src is dead)
+    ChunkWork *W = P.work + chunk;
 
-    const uint8_t *gsrc = P.srcs ? P.srcs[chunk] : P.src_base + (uint64_t)chunk * P.src_stride;
-    uint8_t *gdst = P.dsts ? P.dsts[chunk] : P.dst_base + (uint64_t)chunk * P.dst_stride;
-    const uint32_t n = P.src_sizes ? P.src_sizes[chunk] : P.src_size_all;
-    const bool frame = (P.flags & ENC_FLAG_FRAME) != 0;
-    const bool crc = frame && (P.flags & ENC_FLAG_CRC) != 0;
-
+    const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
+    const uint32_t n = chunk_size(P, chunk);
     if (n > ENC_MAX_CHUNK) {
-        if (tid == 0) P.out_sizes[chunk] = -3;  // too big for this kernel
+        if (tid == 0) { W->n = n; W->kind = 3; }  // reported as B2C_ERR_TOO_BIG by the pack kernel
         return;
     }
-
     B2C_PHASE(0);
     // ---------------------------------------------------------------- P0: stage the chunk
     {
@@ -266,43 +201,62 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
 #ifndef B2C_EMU
         if (bulk) mbar_wait(&sh->mbar, 0);
 #endif
-        if (tid == 0) { sh->n = n; sh->kind = 0; sh->sw.err = 0; }
         __syncthreads();
 #ifndef B2C_EMU
         if (bulk && tid == 0) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh->mbar))); }
 #endif
     }
-    const uint32_t sub = (((n + ENC_NPARSE - 1) / ENC_NPARSE) + 31) & ~31u;  // sub-range size
+    const uint32_t sub = (((n + ENC_NW - 1) / ENC_NW) + 31) & ~31u;  // sub-range size (2048 for a full chunk)
     B2C_PHASE(1);
 
     // ---------------------------------------------------------------- P1: earliest-occurrence table
+    // Each thread owns groups of 4 consecutive positions (three aligned word loads serve four hashes).
     const uint32_t npos = (n >= 8) ? n - 7 : 0;  // positions with 8 readable bytes
     {
+        const uint32_t ngroups = (npos + 3) / 4;
+        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
         // round 1: plain stores, highest positions first so low positions tend to land last
-        for (int32_t k = (int32_t)((npos + ENC_NT - 1) / ENC_NT) - 1; k >= 0; k--) {
-            uint32_t p = (uint32_t)k * ENC_NT + tid;
-            if (p < npos) E[enc_hash6(ld64u(src, p)) >> (32 - ENC_EBITS)] = (uint16_t)p;
+        for (int32_t k = (int32_t)((ngroups + ENC_NT - 1) / ENC_NT) - 1; k >= 0; k--) {
+            uint32_t g = (uint32_t)k * ENC_NT + tid;
+            if (g < ngroups) {
+                uint32_t w0 = srcw[g], w1 = srcw[g + 1], w2 = srcw[g + 2];
+                uint32_t p = 4 * g;
+#pragma unroll
+                for (int j = 3; j >= 0; j--) {
+                    uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
+                    uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
+                    if (p + j < npos) E[enc_hash6(lo, hi) >> (32 - ENC_EBITS)] = (uint16_t)(p + j);
+                }
+            }
         }
         __syncthreads();
         // fix-up rounds: a slot only ever decreases, so this converges to the exact minimum
         for (;;) {
             int changed = 0;
-            for (uint32_t p = tid; p < npos; p += ENC_NT) {
-                uint32_t h = enc_hash6(ld64u(src, p)) >> (32 - ENC_EBITS);
-                if (E[h] > p) { E[h] = (uint16_t)p; changed = 1; }
+            for (uint32_t g = tid; g < ngroups; g += ENC_NT) {
+                uint32_t w0 = srcw[g], w1 = srcw[g + 1], w2 = srcw[g + 2];
+                uint32_t p = 4 * g;
+                uint32_t h[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
+                    uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
+                    h[j] = enc_hash6(lo, hi) >> (32 - ENC_EBITS);
+                }
+                uint32_t e[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) e[j] = E[h[j]];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (p + j < npos && e[j] > p + j && E[h[j]] > p + j) { E[h[j]] = (uint16_t)(p + j); changed = 1; }
             }
             if (!__syncthreads_or(changed)) break;
         }
     }
-
     B2C_PHASE(2);
-    // ---------------------------------------------------------------- P2: parse (warps 0..30), XXH64 (warp 31)
-    if (w == ENC_NPARSE) {
-        if (crc) {
-            uint64_t h = warp_xxh64(src, n);
-            if (lane == 0) sh->xxh = h;
-        }
-    } else {
+
+    // ---------------------------------------------------------------- P2: parse (all 32 warps)
+    {
         uint16_t *L = Lall + w * (1u << ENC_LBITS);
         for (uint32_t i = lane; i < (1u << ENC_LBITS) / 2; i += 32) reinterpret_cast<uint32_t *>(L)[i] = 0xffffffffu;
         __syncwarp();
@@ -311,19 +265,20 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
         uint32_t nrec = 0, sumML = 0;
         uint32_t nextEmit = b0;
         if (b0 < n) {
-            uint2 *rec = reinterpret_cast<uint2 *>(scratch + SCR_REC) + w * ENC_SEGCAP;
+            uint2 *rec = reinterpret_cast<uint2 *>(scratch) + w * ENC_SEGCAP;
             uint32_t cur = b0, ownNew = 0, rep0 = 0;
             while (cur < e0) {
-                uint32_t p = cur + lane;
-                bool valid = (p < e0) && (p < npos);
+                const uint32_t p = cur + lane;
+                const bool valid = (p < e0) && (p < npos);
                 uint64_t cv = valid ? ld64u(src, p) : 0;
-                uint32_t h32 = enc_hash6(cv);
-                uint32_t hL = h32 >> (32 - ENC_LBITS), hE = h32 >> (32 - ENC_EBITS);
+                const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
+                const uint32_t h32 = enc_hash6(c_lo, c_hi);
+                const uint32_t hL = h32 >> (32 - ENC_LBITS), hE = h32 >> (32 - ENC_EBITS);
                 uint32_t candL = 0xffff, candE = 0xffff;
                 if (valid) { candL = L[hL]; candE = E[hE]; }
                 __syncwarp();
                 // insert the window's positions; the highest position wins a slot (deterministic)
-                uint32_t rel = p - b0;
+                const uint32_t rel = p - b0;
                 if (valid) L[hL] = (uint16_t)rel;
                 __syncwarp();
                 for (;;) {
@@ -332,31 +287,50 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
                     if (lose) L[hL] = (uint16_t)rel;
                     __syncwarp();
                 }
-                // verify candidates: recent-in-sub-range, earliest-in-chunk, then the repeat offset
-                int32_t q = -1;
+                // candidates: recent-in-sub-range first, else earliest-in-chunk; 8 bytes compared at once
+                uint32_t q = 0, mlen = 0, bk = 0;
                 if (valid) {
-                    uint32_t c32 = (uint32_t)cv;
-                    if (candL != 0xffff && ld32u(src, b0 + candL) == c32) q = (int32_t)(b0 + candL);
-                    else if (candE < p && ld32u(src, candE) == c32) q = (int32_t)candE;
-                    else if (ownNew >= 1 && p >= rep0 && ld32u(src, p - rep0) == c32) q = (int32_t)(p - rep0);
+                    uint32_t eq = 0;
+                    if (candL != 0xffff) {
+                        uint64_t x = cv ^ ld64u(src, b0 + candL);
+                        eq = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
+                        q = b0 + candL;
+                    }
+                    if (eq < 4 && candE < p) {
+                        uint64_t x = cv ^ ld64u(src, candE);
+                        eq = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
+                        q = candE;
+                    }
+                    if (eq >= 4) {
+                        uint32_t room = e0 - p;             // matches never cross the sub-range end
+                        mlen = eq < room ? eq : room;
+                        if (mlen < 4) mlen = 0;
+                    }
+                    if (mlen) {
+                        // bytes equal just before the match (at most 4, never before position 0)
+                        if (q >= 4) {
+                            uint32_t xb = ld32u(src, p - 4) ^ ld32u(src, q - 4);
+                            bk = xb ? (uint32_t)__clz((int)xb) >> 3 : 4u;
+                        }
+                    }
                 }
-                unsigned mask = __ballot_sync(FULLMASK, q >= 0);
+                unsigned mask = __ballot_sync(FULLMASK, mlen != 0);
                 uint32_t next = cur + 32;
                 uint32_t from = 0;
                 while (true) {
                     unsigned m = (from < 32) ? (mask & (0xffffffffu << from)) : 0u;
                     if (m == 0) break;
-                    int f = __ffs((int)m) - 1;
-                    uint32_t pf = cur + (uint32_t)f;
-                    uint32_t qf = (uint32_t)__shfl_sync(FULLMASK, q, f);
-                    uint32_t len = warp_match_len(src, pf, qf, e0);
-                    if (len < 4) { mask &= ~(1u << f); continue; }
-                    uint32_t off = pf - qf;
-                    uint32_t maxBack = pf - nextEmit; if (qf < maxBack) maxBack = qf;
-                    uint32_t back = warp_match_back(src, pf, qf, maxBack);
-                    uint32_t s = pf - back;
+                    const int f = __ffs((int)m) - 1;
+                    const uint32_t pf = cur + (uint32_t)f;
+                    const uint32_t qf = __shfl_sync(FULLMASK, q, f);
+                    uint32_t len = __shfl_sync(FULLMASK, mlen, f);
+                    uint32_t back = __shfl_sync(FULLMASK, bk, f);
+                    if (len == 8 && pf + 8 < e0) len = 8 + warp_match_len(src, pf + 8, qf + 8, e0);
+                    const uint32_t off = pf - qf;
+                    if (back > pf - nextEmit) back = pf - nextEmit;
+                    const uint32_t s = pf - back;
                     len += back;
-                    bool isrep = (ownNew >= 1) && (off == rep0) && (s > nextEmit);
+                    const bool isrep = (ownNew >= 1) && (off == rep0) && (s > nextEmit);
                     if (lane == 0) {
                         // record: x = litLen | (matchLen-3) << 16 ; y = dist (0 = repeat) | matchStart << 16
                         rec[nrec] = make_uint2((s - nextEmit) | ((len - 3) << 16), (isrep ? 0u : off) | (s << 16));
@@ -381,110 +355,101 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
     B2C_PHASE(3);
 
     // ---------------------------------------------------------------- P3: global sequence/literal layout
-    if (tid == 0) {
-        uint32_t nseq = 0, nlit = 0, carry = 0;
-        for (int v = 0; v < ENC_NPARSE; v++) {
-            sh->seqBase[v] = nseq; sh->litBase[v] = nlit; sh->carry[v] = carry;
-            nseq += sh->cnt[v]; nlit += sh->sumLL[v];
-            if (sh->cnt[v]) carry = sh->tail[v]; else carry += sh->tail[v];
+    if (w == 0) {
+        uint32_t c = sh->cnt[lane], l = sh->sumLL[lane], t = sh->tail[lane];
+        uint32_t ci = warp_scan_incl(c), li = warp_scan_incl(l), ti = warp_scan_incl(t);
+        sh->seqBase[lane] = ci - c;
+        sh->litBase[lane] = li - l;
+        // carry into warp v = tails of the warps after the last warp (< v) that had sequences
+        unsigned has = __ballot_sync(FULLMASK, c != 0);
+        unsigned below = has & ((1u << lane) - 1);
+        int last = below ? 31 - __clz((int)below) : -1;
+        uint32_t tiLast = __shfl_sync(FULLMASK, ti, last < 0 ? 0 : last);   // inclusive tail prefix at `last`
+        uint32_t tLast = __shfl_sync(FULLMASK, t, last < 0 ? 0 : last);
+        uint32_t texcl = ti - t;                                            // tails of lanes < me
+        uint32_t upToLastExcl = (last < 0) ? 0u : tiLast - tLast;           // tails of lanes < last
+        sh->carry[lane] = texcl - upToLastExcl;                             // tails of lanes in [last, me)
+        if (lane == 31) {
+            uint32_t nseq = ci, nlit = li;
+            sh->nseq = nseq; sh->nlit = nlit;
+            // blockEnc.encode early decisions (blockenc.go:481-503)
+            uint32_t kind = 0;
+            if (nseq == 0) kind = 1;  // encodeLits(..., rawAllLits=true) => raw block
+            else {
+                int saved = (int)n - (int)nlit - (int)(n >> 6);
+                if (saved < 16) kind = 1;
+            }
+            sh->kind = kind; sh->rleLen = 0;
         }
-        sh->nseq = nseq; sh->nlit = nlit;
-        // blockEnc.encode early decisions (blockenc.go:481-503)
-        uint32_t kind = 0;
-        if (nseq == 0) kind = 1;  // encodeLits(..., rawAllLits=true) => raw block
-        else {
-            int saved = (int)n - (int)nlit - (int)(n >> 6);
-            if (saved < 16) kind = 1;
-        }
-        sh->kind = kind;
-        // frame header size (frameenc.go:25-92); single segment when 1024 < n <= window
-        uint32_t fh = 0;
-        if (frame) {
-            bool single = n > 1024;
-            fh = 4 + 1 + (single ? 0 : 1);
-            if (n >= 256) fh += (n >= 65536 + 256) ? 4 : 2; else if (single) fh += 1;
-        }
-        sh->fhSize = fh;
     }
     __syncthreads();
-    const uint32_t nseq = sh->nseq, nlit = sh->nlit, fh = sh->fhSize;
-    uint16_t *seqLL = reinterpret_cast<uint16_t *>(scratch + SCR_LL);
-    uint16_t *seqML = reinterpret_cast<uint16_t *>(scratch + SCR_ML);
-    uint32_t *seqOF = reinterpret_cast<uint32_t *>(scratch + SCR_OF);
-    uint8_t *codes = (nseq <= ENC_CODES_SMEM_CAP) ? codesS : scratch + SCR_CODES;
-    const uint32_t codeStride = (nseq <= ENC_CODES_SMEM_CAP) ? ENC_CODES_SMEM_CAP : ENC_MAXSEQ;
+    const uint32_t nseq = sh->nseq, nlit = sh->nlit;
     uint32_t kind = sh->kind;
 
     // ---------------------------------------------------------------- P4: gather literals, compact sequences, codes
     if (kind == 0) {
-        if (w < ENC_NPARSE) {
-            const uint2 *rec = reinterpret_cast<const uint2 *>(scratch + SCR_REC) + w * ENC_SEGCAP;
-            const uint32_t cntw = sh->cnt[w], sbase = sh->seqBase[w], carry = sh->carry[w];
-            uint32_t lbase = sh->litBase[w];
-            const uint32_t b0 = w * sub;
-            const uint32_t e0 = (b0 + sub < n) ? b0 + sub : n;
-            for (uint32_t i0 = 0; i0 < cntw; i0 += 32) {
-                uint32_t i = i0 + lane;
-                uint32_t ll = 0, ml3 = 0, dist = 0, ms = 0;
-                if (i < cntw) {
-                    uint2 r = rec[i];
-                    ll = r.x & 0xffff; ml3 = r.x >> 16; dist = r.y & 0xffff; ms = r.y >> 16;
-                }
-                uint32_t incl = warp_scan_incl(ll);
-                uint32_t lpos = lbase + incl - ll;  // literal index of my run
-                // copy my literal run src[ms-ll .. ms) -> lit[lpos ..)
-                for (uint32_t k = 0; k < ll; k++) lit[lpos + k] = src[ms - ll + k];
-                if (i < cntw) {
-                    uint32_t llt = ll + ((i == 0) ? carry : 0u);
-                    uint32_t ofv = dist ? dist + 3 : 1u;
-                    uint32_t gi = sbase + i;
-                    seqLL[gi] = (uint16_t)llt; seqML[gi] = (uint16_t)ml3; seqOF[gi] = ofv;
-                    codes[gi] = (uint8_t)seq_ll_code(llt);
-                    codes[codeStride + gi] = (uint8_t)highbit32(ofv);
-                    codes[2 * codeStride + gi] = (uint8_t)seq_ml_code(ml3);
-                }
-                lbase += __shfl_sync(FULLMASK, incl, 31);
+        const uint2 *rec = reinterpret_cast<const uint2 *>(scratch) + w * ENC_SEGCAP;
+        const uint32_t cntw = sh->cnt[w], sbase = sh->seqBase[w], carry = sh->carry[w];
+        uint32_t lbase = sh->litBase[w];
+        const uint32_t b0 = w * sub;
+        const uint32_t e0 = (b0 + sub < n) ? b0 + sub : n;
+        for (uint32_t i0 = 0; i0 < cntw; i0 += 32) {
+            uint32_t i = i0 + lane;
+            uint32_t ll = 0, ml3 = 0, dist = 0, ms = 0;
+            if (i < cntw) {
+                uint2 r = rec[i];
+                ll = r.x & 0xffff; ml3 = r.x >> 16; dist = r.y & 0xffff; ms = r.y >> 16;
             }
-            // trailing literals of the sub-range
-            uint32_t tl = sh->tail[w];
-            for (uint32_t k = lane; k < tl; k += 32) lit[lbase + k] = src[e0 - tl + k];
+            uint32_t incl = warp_scan_incl(ll);
+            uint32_t lpos = lbase + incl - ll;  // literal index of my run
+            for (uint32_t k = 0; k < ll; k++) lit[lpos + k] = src[ms - ll + k];
+            if (i < cntw) {
+                uint32_t llt = ll + ((i == 0) ? carry : 0u);
+                uint32_t ofv = dist ? dist + 3 : 1u;
+                uint32_t gi = sbase + i;
+                W->seqLL[gi] = (uint16_t)llt; W->seqML[gi] = (uint16_t)ml3; W->seqOF[gi] = ofv;
+                W->codes[TBL_LL][gi] = (uint8_t)seq_ll_code(llt);
+                W->codes[TBL_OF][gi] = (uint8_t)highbit32(ofv);
+                W->codes[TBL_ML][gi] = (uint8_t)seq_ml_code(ml3);
+            }
+            lbase += __shfl_sync(FULLMASK, incl, 31);
         }
+        uint32_t tl = sh->tail[w];
+        for (uint32_t k = lane; k < tl; k += 32) lit[lbase + k] = src[e0 - tl + k];
     }
     __syncthreads();
-    // single-sequence RLE block test (blockenc.go:484-493) needs org[0]; nlit <= 1
+    // single-sequence RLE block test (blockenc.go:484-493); nlit <= 1
     if (kind == 0 && nseq == 1 && nlit <= 1 && tid == 0) {
-        uint32_t ll0 = seqLL[0], of0 = seqOF[0];
-        if (ll0 == nlit && of0 - 3 == 1) { sh->kind = 2; sh->rleLen = (uint32_t)seqML[0] + 3 + ll0; }
-    }
-    if (P.dbg_hdr && kind == 0) {
-        for (uint32_t i = tid; i < nseq && i < P.dbg_seq_cap; i += ENC_NT) {
-            uint32_t *d = P.dbg_seqs + ((uint64_t)chunk * P.dbg_seq_cap + i) * 3;
-            d[0] = seqLL[i]; d[1] = seqML[i]; d[2] = seqOF[i];
-        }
-        for (uint32_t i = tid; i < nlit; i += ENC_NT) P.dbg_lits[(uint64_t)chunk * 65536 + i] = lit[i];
+        uint32_t ll0 = W->seqLL[0], of0 = W->seqOF[0];
+        if (ll0 == nlit && of0 - 3 == 1) { sh->kind = 2; sh->rleLen = (uint32_t)W->seqML[0] + 3 + ll0; }
     }
     __syncthreads();
     kind = sh->kind;
     B2C_PHASE(4);
 
+    // ---------------------------------------------------------------- P5: histograms (src is dead from here on)
     if (kind == 0) {
-        // ------------------------------------------------------------ P5: histograms
-        // sequence code histograms: per-warp match.any merge into sh->sw.hist
-        for (uint32_t i = tid; i < 3 * 64; i += ENC_NT) (&sh->sw.hist[0][0])[i] = 0;
-        if (tid < 3) sh->sw.maxSym[tid] = 0;
-        for (uint32_t i = tid; i < 32 * 256; i += ENC_NT) whist[i] = 0;
+        for (uint32_t i = tid; i < 32 * 192; i += ENC_NT) shist[i] = 0;
+        for (uint32_t i = tid; i < 4 * 256 * 32 / 2; i += ENC_NT) reinterpret_cast<uint32_t *>(lhist)[i] = 0;
         __syncthreads();
-        {
-            // reuse whist rows [w][0..191] as this warp's private (3 x 64) code histogram
-            uint32_t *hw3 = whist + w * 256;
-            for (uint32_t base = w * 32; base < nseq; base += ENC_NT) {
+        if (w < 4) {
+            // literal histogram: warps 0..3, private u16 counter per (symbol, lane): conflict-free, no atomics
+            uint16_t *hcol = lhist + w * 256 * 32;
+            uint32_t per = (nlit + 3) / 4;
+            uint32_t a = w * per, b = a + per;
+            if (b > nlit) b = nlit;
+            for (uint32_t i = a + lane; i < b; i += 32) hcol[(uint32_t)lit[i] * 32 + lane]++;
+        } else {
+            // sequence code histograms: warps 4..31, per-warp private bins merged with match.any
+            uint32_t *hw3 = shist + w * 192;
+            for (uint32_t base = (w - 4) * 32; base < nseq; base += (ENC_NW - 4) * 32) {
                 uint32_t i = base + lane;
                 bool valid = i < nseq;
                 unsigned act = __ballot_sync(FULLMASK, valid);
                 if (valid) {
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
-                        unsigned code = codes[c * codeStride + i];
+                        unsigned code = W->codes[c][i];
                         unsigned peers = __match_any_sync(act, code);
                         if (lane == (unsigned)(__ffs((int)peers) - 1)) hw3[c * 64 + code] += (uint32_t)__popc(peers);
                     }
@@ -493,61 +458,219 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
             }
         }
         __syncthreads();
-        if (tid < 192) {
+        if (tid < 256) {
             uint32_t c = 0;
-            for (int k = 0; k < ENC_NW; k++) c += whist[k * 256 + tid];
-            (&sh->sw.hist[0][0])[tid] = c;
+            for (int k = 0; k < 4; k++) {
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(lhist + (k * 256 + tid) * 32);
+#pragma unroll
+                for (int j = 0; j < 16; j++) { uint32_t v = row[j]; c += (v & 0xffff) + (v >> 16); }
+            }
+            W->litHist[tid] = c;
+        } else if (tid < 256 + 192) {
+            uint32_t s = tid - 256, c = 0;
+            for (int k = 4; k < ENC_NW; k++) c += shist[k * 192 + s];
+            W->seqHist[s / 64][s % 64] = c;
+            shist[s] = c;  // row 0 (unused by the counting warps) now holds the totals
         }
         __syncthreads();
         if (tid < 3) {
             uint32_t mx = 0;
-            for (uint32_t s = 0; s < 64; s++) if (sh->sw.hist[tid][s]) mx = s;
-            sh->sw.maxSym[tid] = mx;
+            for (uint32_t s = 0; s < 64; s++) if (shist[tid * 64 + s]) mx = s;
+            W->maxSym[tid] = mx;
         }
-        // literal histogram (only needed when Huffman is attempted: nlit > 16)
-        if (nlit > 16) huf_histogram(lit, nlit, whist, &sh->hw, tid, ENC_NT, 0);
-        else __syncthreads();
+        // literals to the work record (coalesced 16-byte stores)
+        {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(lit);
+            uint4 *d4 = reinterpret_cast<uint4 *>(W->lit);
+            uint32_t n16 = (nlit + 15) / 16;
+            for (uint32_t i = tid; i < n16; i += ENC_NT) d4[i] = s4[i];
+        }
+        if (P.dbg_hdr) {
+            for (uint32_t i = tid; i < nseq && i < P.dbg_seq_cap; i += ENC_NT) {
+                uint32_t *d = P.dbg_seqs + ((uint64_t)chunk * P.dbg_seq_cap + i) * 3;
+                d[0] = W->seqLL[i]; d[1] = W->seqML[i]; d[2] = W->seqOF[i];
+            }
+            for (uint32_t i = tid; i < nlit; i += ENC_NT) P.dbg_lits[(uint64_t)chunk * 65536 + i] = lit[i];
+        }
+    }
+    if (tid == 0) { W->n = n; W->nseq = nseq; W->nlit = nlit; W->kind = kind; W->rleLen = sh->rleLen; }
+    __syncthreads();
+    B2C_PHASE(5);
+}
 
-        B2C_PHASE(5);
-        // ------------------------------------------------------------ P6: tables
-        if (nlit > 16) { huf_bt_stats(&sh->hw, nlit, tid); } else if (tid == 0) sh->hw.status = HUF_INCOMPRESSIBLE;
-        __syncthreads();
-        const bool hufTry = sh->hw.status == HUF_OK;
-        if (hufTry) huf_bt_sort(&sh->hw, tid, ENC_NT);
-        __syncthreads();
-        B2C_PHASE(6);
-        // serial table builders side by side: warp 0 Huffman tree, warps 1..3 the FSE tables
-        if (tid == 0 && hufTry) huf_bt_tree(&sh->hw, nlit);
-        if (lane == 0 && w >= 1 && w <= 3) {
-            int which = (int)w - 1;
-            seq_build_table(&sh->sw, which, nseq, codes[which * codeStride + 0]);
+// ------------------------------------------------------------------------------------------------ K2
+// One 128-thread CTA per chunk.  Warp 0 builds the Huffman table cooperatively (rank sort with 32 lanes, the
+// serial tree / setMaxHeight / table serialisation on lane 0); lane 0 of warps 1..3 builds one FSE table each.
+struct TablesShared {
+    HufWork hw;
+    SeqWork sw;
+};
+B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_t chunk) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    ChunkWork *W = P.work + chunk;
+    if (W->kind != 0) return;
+    const uint32_t nseq = W->nseq, nlit = W->nlit;
+    if (w == 0) {
+        HufWork *hw = &ts->hw;
+        for (uint32_t s = lane; s < 256; s += 32) hw->count[s] = W->litHist[s];
+        if (lane == 0) { hw->status = HUF_INCOMPRESSIBLE; hw->tableDescLen = 0; hw->tableLog = 0; }
+        __syncwarp();
+        if (nlit > 16) huf_build_table(hw, nlit, lane, 32, -1);
+        __syncwarp();
+        if (hw->status == HUF_OK) {
+            for (uint32_t s = lane; s < 256; s += 32) { W->ctVal[s] = hw->ctVal[s]; W->ctBits[s] = hw->ctBits[s]; }
+            for (uint32_t i = lane; i < hw->tableDescLen; i += 32) W->tableDesc[i] = hw->tableDesc[i];
         }
-        __syncthreads();
-        B2C_PHASE(7);
-        if (hufTry) huf_bt_bits(&sh->hw, tid, ENC_NT);
-        __syncthreads();
-        if (hufTry) huf_bt_vals(&sh->hw, tid, ENC_NT);
-        __syncthreads();
-        if (tid == 0 && hufTry) huf_bt_write(&sh->hw);
-        // meanwhile: the three state chains only need codes + FSE tables
-        if (w >= 1 && w <= 3) {
-            int which = (int)w - 1;
-            uint16_t *stb = reinterpret_cast<uint16_t *>(scratch + SCR_STB) + which * ENC_MAXSEQ;
-            seq_chain(&sh->sw, which, codes + which * codeStride, nseq, stb);
+        if (lane == 0) { W->hufStatus = (uint32_t)hw->status; W->hufTableLog = hw->tableLog; W->tableDescLen = hw->tableDescLen; }
+    } else {
+        const int which = (int)w - 1;
+        SeqWork *sw = &ts->sw;
+        for (uint32_t s = lane; s < 64; s += 32) sw->hist[which][s] = W->seqHist[which][s];
+        if (lane == 0) sw->maxSym[which] = W->maxSym[which];
+        __syncwarp();
+        if (lane == 0) seq_build_table(sw, which, nseq, W->codes[which][0]);
+        __syncwarp();
+        // publish the table this chain will use
+        const FseCTable *t = seq_table(sw, which);
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(t);
+        uint32_t *d32 = reinterpret_cast<uint32_t *>(&W->tbl[which]);
+        for (uint32_t i = lane; i < sizeof(FseCTable) / 4; i += 32) d32[i] = s32[i];
+        for (uint32_t i = lane; i < sw->ncountLen[which] && i < 96; i += 32) W->ncount[which][i] = sw->ncount[which][i];
+        if (lane == 0) {
+            W->mode[which] = sw->mode[which]; W->ncountLen[which] = sw->ncountLen[which];
+            if (sw->ncountLen[which] == SEQ_TABLE_ERR) { W->ncountLen[which] = 0; W->kind = 1; }  // internal error: store raw
         }
-        __syncthreads();
+    }
+}
 
-        B2C_PHASE(8);
-        // ------------------------------------------------------------ P7: literals section
+// ------------------------------------------------------------------------------------------------ K3
+// One lane per (chunk, chain): CTA = 96 threads = 3 warps; warp c walks chain c of 32 consecutive chunks.
+// Per-lane tables live in shared memory, interleaved so that lane l only ever touches bank l.
+constexpr int CHAIN_NT = 96;
+constexpr uint32_t CHAIN_SMEM_WORDS_PER_LANE = 128 + 64 + 64;  // stateTable (256 x u16), deltaNbBits, deltaFindState
+constexpr uint32_t CHAIN_SMEM_BYTES = CHAIN_NT * CHAIN_SMEM_WORDS_PER_LANE * 4;
+B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_t chunk0) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, which = tid >> 5;
+    const uint32_t chunk = chunk0 + lane;
+    const bool live = chunk < P.nchunks && P.work[chunk < P.nchunks ? chunk : 0].kind == 0;
+    ChunkWork *W = P.work + (live ? chunk : 0);
+    uint32_t *st32 = smem32 + which * 32 * CHAIN_SMEM_WORDS_PER_LANE;  // this warp's region
+    // element i of lane l at st32[i * 32 + l]
+    uint32_t *tState = st32 + lane;                 // 128 words: two u16 states per word
+    uint32_t *tNb = st32 + 128 * 32 + lane;         // 64 words
+    uint32_t *tFs = st32 + (128 + 64) * 32 + lane;  // 64 words (sign-extended int16)
+    uint32_t nseq = 0, useRLE = 1, tableLog = 0;
+    if (live) {
+        const FseCTable *t = &W->tbl[which];
+        nseq = W->nseq; useRLE = t->useRLE; tableLog = t->tableLog;
+        if (!useRLE) {
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(t->stateTable);
+            uint32_t ts2 = (1u << tableLog) / 2;
+            for (uint32_t i = 0; i < ts2; i++) tState[i * 32] = sw[i];
+            uint32_t sl = t->symbolLen;
+            for (uint32_t i = 0; i < sl; i++) { tNb[i * 32] = t->deltaNbBits[i]; tFs[i * 32] = (uint32_t)(int32_t)t->deltaFindState[i]; }
+        }
+    }
+    __syncwarp();
+    const uint8_t *codes = W->codes[which];
+    uint16_t *stb = W->stb[which];
+    uint32_t state = 0;
+    if (live && !useRLE) {
+        uint32_t sym = codes[nseq - 1];
+        uint32_t dnb = tNb[sym * 32];
+        uint32_t nbBitsOut = (dnb + (1u << 15)) >> 16;
+        int32_t im = (int32_t)((nbBitsOut << 16) - dnb);
+        int32_t lu = (im >> nbBitsOut) + (int32_t)tFs[sym * 32];
+        uint32_t wv = tState[(lu >> 1) * 32];
+        state = (lu & 1) ? (wv >> 16) : (wv & 0xffff);
+    }
+    uint32_t steps = (live && !useRLE && nseq) ? nseq - 1 : 0;
+    uint32_t maxSteps = warp_max(steps);
+    for (uint32_t t = 1; t <= maxSteps; t++) {
+        if (t <= steps) {
+            uint32_t idx = nseq - 1 - t;
+            uint32_t sym = codes[idx];
+            uint32_t nb = (state + tNb[sym * 32]) >> 16;
+            stb[idx] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
+            int32_t lu = (int32_t)(state >> nb) + (int32_t)tFs[sym * 32];
+            uint32_t wv = tState[(lu >> 1) * 32];
+            state = (lu & 1) ? (wv >> 16) : (wv & 0xffff);
+        }
+    }
+    if (live) {
+        if (useRLE) { for (uint32_t i = 0; i + 1 < nseq; i++) stb[i] = 0; state = 0; }
+        W->finalState[which] = state;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4
+struct PackShared {
+    HufWork hw;               // only ctVal/ctBits/tableDesc*/scan/stream* are used here
+    uint32_t scan[40];
+    uint32_t litMode, lhSize, litPayload, pos;
+};
+constexpr uint32_t PACK_STAGE_BYTES = ENC_MAX_CHUNK + 128;
+constexpr uint32_t PACK_SMEM_BYTES = PACK_STAGE_BYTES + ((sizeof(PackShared) + 15) / 16) * 16;
+
+B2C_DEV uint32_t frame_header_bytes(uint32_t n) {
+    if (n == 0) return 6;
+    bool single = n > 1024;
+    uint32_t fh = 4 + 1 + (single ? 0 : 1);
+    if (n >= 256) fh += (n >= 65536 + 256) ? 4 : 2; else if (single) fh += 1;
+    return fh;
+}
+// frameHeader.appendTo (frameenc.go:25-92), single chunk, no dictionary
+B2C_DEV uint32_t write_frame_header(uint8_t *o8, uint32_t n, bool crc) {
+    uint32_t o = 0;
+    o8[o++] = 0x28; o8[o++] = 0xB5; o8[o++] = 0x2F; o8[o++] = 0xFD;
+    if (n == 0) { o8[o++] = 32; o8[o++] = 0; return o; }  // WithZeroFrames (encoder.go:732-751)
+    bool single = n > 1024;
+    uint32_t fcs = (n >= 256) ? ((n >= 65536 + 256) ? 2u : 1u) : 0u;
+    o8[o++] = (uint8_t)((crc ? 4u : 0u) | (single ? 32u : 0u) | (fcs << 6));
+    if (!single) {
+        uint32_t ws = 1u << (32 - (uint32_t)__clz((int)n));  // WindowSize(n) (enc_base.go:42-50)
+        if (ws < 1024) ws = 1024;
+        o8[o++] = (uint8_t)(((32 - (uint32_t)__clz((int)(ws - 1))) - 10) << 3);
+    }
+    if (fcs == 0) { if (single) o8[o++] = (uint8_t)n; }
+    else if (fcs == 1) { uint32_t v = n - 256; o8[o++] = (uint8_t)v; o8[o++] = (uint8_t)(v >> 8); }
+    else { o8[o++] = (uint8_t)n; o8[o++] = (uint8_t)(n >> 8); o8[o++] = (uint8_t)(n >> 16); o8[o++] = (uint8_t)(n >> 24); }
+    return o;
+}
+
+B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk) {
+    const unsigned tid = threadIdx.x;
+    uint8_t *stage = smem;
+    PackShared *ps = reinterpret_cast<PackShared *>(smem + PACK_STAGE_BYTES);
+    ChunkWork *W = P.work + chunk;
+    const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
+    uint8_t *gdst = P.dst_base + (uint64_t)chunk * P.dst_stride;
+    const uint32_t n = W->n;
+    const bool frame = (P.flags & ENC_FLAG_FRAME) != 0;
+    const bool crc = frame && (P.flags & ENC_FLAG_CRC) != 0;
+    uint32_t kind = W->kind;
+    if (kind == 3) { if (tid == 0) P.out_sizes[chunk] = -3; return; }
+    const uint32_t nseq = W->nseq, nlit = W->nlit;
+    const uint32_t fh = frame ? frame_header_bytes(n) : 0;
+
+    if (kind == 0) {
+        const uint8_t *lit = W->lit;
+        HufWork *hw = &ps->hw;
+        // Huffman table into shared memory
+        for (uint32_t s = tid; s < 256; s += PACK_NT) { hw->ctVal[s] = W->ctVal[s]; hw->ctBits[s] = W->ctBits[s]; }
+        for (uint32_t i = tid; i < W->tableDescLen; i += PACK_NT) hw->tableDesc[i] = W->tableDesc[i];
+        if (tid == 0) { hw->tableDescLen = W->tableDescLen; hw->status = (int32_t)W->hufStatus; }
+        __syncthreads();
+        // ------------------------------------------------------------ literals section sizes
         const bool four = nlit >= 1024;
         HufEncState hst;
         uint32_t payload = 0;
-        const bool hufOK = sh->hw.status == HUF_OK;   // may have turned INCOMPRESSIBLE in huf_bt_write
-        if (hufOK) payload = huf_enc_sizes(&sh->hw, lit, nlit, four ? 1 : 0, tid, ENC_NT, 0, &hst);
+        const bool hufOK = hw->status == HUF_OK;
+        if (hufOK) payload = huf_enc_sizes(hw, lit, nlit, four ? 1 : 0, tid, PACK_NT, 0, &hst);
         if (tid == 0) {
             // huff0 compress(): out >= wantSize => ErrIncompressible (compress.go:155-158, WantLogLess 4)
             uint32_t mode = 2;
-            if (!hufOK) mode = (sh->hw.status == HUF_USE_RLE) ? 1u : 0u;
+            if (!hufOK) mode = (hw->status == HUF_USE_RLE) ? 1u : 0u;
             else {
                 uint32_t wantSize = nlit - (nlit >> 4);
                 if (payload >= wantSize) mode = 0;
@@ -569,67 +692,58 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
                 uint32_t inBits = nlit ? 32 - (uint32_t)__clz((int)nlit) : 0;
                 lh = inBits < 5 ? 1 : (inBits < 12 ? 2 : 3);
             }
-            sh->litMode = mode; sh->lhSize = lh; sh->litPayload = payload;
+            ps->litMode = mode; ps->lhSize = lh; ps->litPayload = payload;
         }
         __syncthreads();
-        const uint32_t litMode = sh->litMode, lhSize = sh->lhSize;
+        const uint32_t litMode = ps->litMode, lhSize = ps->lhSize;
         const uint32_t litOff = fh + 3 + lhSize;  // staging offset of the literal payload
-        const uint32_t litBytes = (litMode == 2) ? sh->litPayload : (litMode == 1 ? 1u : nlit);
-        // sequence section header: nSeq (1..3 bytes) + modes byte + NCount tables (LL, OF, ML)
+        const uint32_t litBytes = (litMode == 2) ? ps->litPayload : (litMode == 1 ? 1u : nlit);
         const uint32_t nsHdr = (nseq < 128) ? 1u : (nseq < 0x7f00 ? 2u : 3u);
         const uint32_t seqOff = litOff + litBytes;
         const uint32_t tblOff = seqOff + nsHdr + 1;
-        const uint32_t bsOff = tblOff + sh->sw.ncountLen[0] + sh->sw.ncountLen[1] + sh->sw.ncountLen[2];
+        const uint32_t bsOff = tblOff + W->ncountLen[0] + W->ncountLen[1] + W->ncountLen[2];
 
-        B2C_PHASE(9);
-        // P8 sizes of the sequence bitstream (every thread owns a run of consecutive t = nseq-1-idx)
-        const uint16_t *stbLL = reinterpret_cast<const uint16_t *>(scratch + SCR_STB);
-        const uint16_t *stbOF = stbLL + ENC_MAXSEQ;
-        const uint16_t *stbML = stbOF + ENC_MAXSEQ;
-        const uint32_t per = (nseq + ENC_NT - 1) / ENC_NT;
+        // ------------------------------------------------------------ sequence bitstream sizes
+        const uint8_t *cLL = W->codes[TBL_LL], *cOF = W->codes[TBL_OF], *cML = W->codes[TBL_ML];
+        const uint16_t *stbLL = W->stb[TBL_LL], *stbOF = W->stb[TBL_OF], *stbML = W->stb[TBL_ML];
+        const uint32_t per = (nseq + PACK_NT - 1) / PACK_NT;
         uint32_t tA = tid * per, tB = tA + per;
         if (tA > nseq) tA = nseq;
         if (tB > nseq) tB = nseq;
         uint32_t mybits = 0;
         for (uint32_t t = tA; t < tB; t++) {
             uint32_t idx = nseq - 1 - t;
-            uint32_t cl = codes[idx], co = codes[codeStride + idx], cm = codes[2 * codeStride + idx];
+            uint32_t cl = cLL[idx], co = cOF[idx], cm = cML[idx];
             mybits += seq_ll_bits(cl) + seq_ml_bits(cm) + co;
             if (t) mybits += (stbLL[idx] >> 12) + (stbOF[idx] >> 12) + (stbML[idx] >> 12);
         }
         uint32_t totalBits;
-        uint32_t exBits = group_scan_excl(mybits, sh->sw.scan, 0, ENC_NT, tid, &totalBits);
-        const FseCTable *tLL = seq_table(&sh->sw, TBL_LL), *tOF = seq_table(&sh->sw, TBL_OF), *tML = seq_table(&sh->sw, TBL_ML);
-        const uint32_t flushBits = tML->tableLog + tOF->tableLog + tLL->tableLog;
+        uint32_t exBits = group_scan_excl(mybits, ps->scan, 0, PACK_NT, tid, &totalBits);
+        const uint32_t tlLL = W->tbl[TBL_LL].tableLog, tlOF = W->tbl[TBL_OF].tableLog, tlML = W->tbl[TBL_ML].tableLog;
+        const uint32_t flushBits = tlML + tlOF + tlLL;
         const uint32_t bsBytes = (totalBits + flushBits + 1 + 7) >> 3;
         const uint32_t blockBytes = (bsOff - fh - 3) + bsBytes;  // block content size
         const uint32_t total = fh + 3 + blockBytes + (crc ? 4u : 0u);
         // blockenc.go:811-817: not smaller than the input => raw block.  Also covers staging overflow.
-        const bool useRaw = (blockBytes >= n) || (total + 8 > ENC_SRC_BYTES) || sh->sw.err;
-        __syncthreads();  // everyone is done reading src/stage-overlapping data? (src no longer needed)
-        B2C_PHASE(10);
+        const bool useRaw = (blockBytes >= n) || (total + 8 > PACK_STAGE_BYTES);
         if (!useRaw) {
-            // zero the staging words that receive bit-granular output
             uint32_t zw = (total + 8 + 3) / 4;
-            for (uint32_t i = tid; i < zw; i += ENC_NT) reinterpret_cast<uint32_t *>(stage)[i] = 0;
+            for (uint32_t i = tid; i < zw; i += PACK_NT) reinterpret_cast<uint32_t *>(stage)[i] = 0;
             __syncthreads();
-            // literals
             if (litMode == 2) {
-                huf_enc_pack(&sh->hw, lit, four ? 1 : 0, stage, litOff, tid, ENC_NT, 0, &hst);
+                huf_enc_pack(hw, lit, four ? 1 : 0, stage, litOff, tid, PACK_NT, 0, &hst);
             } else if (litMode == 0) {
-                for (uint32_t i = tid; i < nlit; i += ENC_NT) stage[litOff + i] = lit[i];
+                for (uint32_t i = tid; i < nlit; i += PACK_NT) stage[litOff + i] = lit[i];
             } else if (tid == 0) {
                 stage[litOff] = lit[0];
             }
             __syncthreads();  // byte stores above must not race the word atomics below
-            B2C_PHASE(11);
-            // sequence bitstream
             {
                 BitRun br;
                 br.init(reinterpret_cast<uint32_t *>(stage), bsOff * 8 + exBits);
                 for (uint32_t t = tA; t < tB; t++) {
                     uint32_t idx = nseq - 1 - t;
-                    uint32_t cl = codes[idx], co = codes[codeStride + idx], cm = codes[2 * codeStride + idx];
+                    uint32_t cl = cLL[idx], co = cOF[idx], cm = cML[idx];
                     if (t) {
                         uint32_t so = stbOF[idx], sm = stbML[idx], sl = stbLL[idx];
                         br.add(so & 0xfff, so >> 12);
@@ -637,45 +751,30 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
                         br.add(sl & 0xfff, sl >> 12);
                     }
                     uint32_t lb = seq_ll_bits(cl), mb = seq_ml_bits(cm);
-                    br.add((uint32_t)seqLL[idx] & ((1u << lb) - 1), lb);
-                    br.add((uint32_t)seqML[idx] & ((1u << mb) - 1), mb);
-                    br.add(seqOF[idx] & ((1u << co) - 1), co);
+                    br.add((uint32_t)W->seqLL[idx] & ((1u << lb) - 1), lb);
+                    br.add((uint32_t)W->seqML[idx] & ((1u << mb) - 1), mb);
+                    br.add(W->seqOF[idx] & ((1u << co) - 1), co);
                 }
                 if (tB == nseq && tA < tB) {
                     // final states: ml, of, ll (blockenc.go:804-806) + end mark
-                    br.add(sh->sw.finalState[TBL_ML] & ((1u << tML->tableLog) - 1), tML->tableLog);
-                    br.add(sh->sw.finalState[TBL_OF] & ((1u << tOF->tableLog) - 1), tOF->tableLog);
-                    br.add(sh->sw.finalState[TBL_LL] & ((1u << tLL->tableLog) - 1), tLL->tableLog);
+                    br.add(W->finalState[TBL_ML] & ((1u << tlML) - 1), tlML);
+                    br.add(W->finalState[TBL_OF] & ((1u << tlOF) - 1), tlOF);
+                    br.add(W->finalState[TBL_LL] & ((1u << tlLL) - 1), tlLL);
                     br.add(1u, 1);
                 }
                 br.finish();
             }
             __syncthreads();
-            B2C_PHASE(12);
             // byte-granular headers (after all word-granular atomics)
             if (tid == 0) {
                 uint32_t o = 0;
-                if (frame) {
-                    stage[o++] = 0x28; stage[o++] = 0xB5; stage[o++] = 0x2F; stage[o++] = 0xFD;
-                    bool single = n > 1024;
-                    uint32_t fcs = (n >= 256) ? ((n >= 65536 + 256) ? 2u : 1u) : 0u;
-                    stage[o++] = (uint8_t)((crc ? 4u : 0u) | (single ? 32u : 0u) | (fcs << 6));
-                    if (!single) {
-                        // WindowSize(n) (enc_base.go:42-50): max(1 << bits.Len(n), 1024)
-                        uint32_t ws = 1u << (32 - (uint32_t)__clz((int)n));
-                        if (ws < 1024) ws = 1024;
-                        stage[o++] = (uint8_t)(((32 - (uint32_t)__clz((int)(ws - 1))) - 10) << 3);
-                    }
-                    if (fcs == 0) { if (single) stage[o++] = (uint8_t)n; }
-                    else if (fcs == 1) { uint32_t v = n - 256; stage[o++] = (uint8_t)v; stage[o++] = (uint8_t)(v >> 8); }
-                    else { stage[o++] = (uint8_t)n; stage[o++] = (uint8_t)(n >> 8); stage[o++] = (uint8_t)(n >> 16); stage[o++] = (uint8_t)(n >> 24); }
-                }
+                if (frame) o = write_frame_header(stage, n, crc);
                 uint32_t bh = 1u | (2u << 1) | (blockBytes << 3);  // last block, compressed
                 stage[o++] = (uint8_t)bh; stage[o++] = (uint8_t)(bh >> 8); stage[o++] = (uint8_t)(bh >> 16);
                 // literals header (blockenc.go:153-238)
                 uint64_t lh;
                 if (litMode == 2) {
-                    uint64_t comp = sh->litPayload;
+                    uint64_t comp = ps->litPayload;
                     if (lhSize == 3) lh = 2u | ((four ? 1u : 0u) << 2) | ((uint64_t)nlit << 4) | (comp << 14);
                     else if (lhSize == 4) lh = 2u | (2u << 2) | ((uint64_t)nlit << 4) | (comp << 18);
                     else lh = 2u | (3u << 2) | ((uint64_t)nlit << 4) | (comp << 22);
@@ -686,33 +785,30 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
                     else lh = ty | (3u << 2) | ((uint64_t)nlit << 4);
                 }
                 for (uint32_t k = 0; k < lhSize; k++) stage[o++] = (uint8_t)(lh >> (8 * k));
-                // sequences header
                 o = seqOff;
                 if (nseq < 128) stage[o++] = (uint8_t)nseq;
                 else if (nseq < 0x7f00) { stage[o++] = (uint8_t)(128 + (nseq >> 8)); stage[o++] = (uint8_t)nseq; }
                 else { uint32_t v = nseq - 0x7f00; stage[o++] = 255; stage[o++] = (uint8_t)v; stage[o++] = (uint8_t)(v >> 8); }
-                stage[o++] = (uint8_t)((sh->sw.mode[TBL_LL] << 6) | (sh->sw.mode[TBL_OF] << 4) | (sh->sw.mode[TBL_ML] << 2));
+                stage[o++] = (uint8_t)((W->mode[TBL_LL] << 6) | (W->mode[TBL_OF] << 4) | (W->mode[TBL_ML] << 2));
                 for (int c = 0; c < 3; c++)
-                    for (uint32_t k = 0; k < sh->sw.ncountLen[c]; k++) stage[o++] = sh->sw.ncount[c][k];
+                    for (uint32_t k = 0; k < W->ncountLen[c]; k++) stage[o++] = W->ncount[c][k];
                 if (crc) {
-                    uint32_t c32 = (uint32_t)sh->xxh;
+                    uint32_t c32 = (uint32_t)W->xxh;
                     uint32_t e = total - 4;
                     stage[e] = (uint8_t)c32; stage[e + 1] = (uint8_t)(c32 >> 8); stage[e + 2] = (uint8_t)(c32 >> 16); stage[e + 3] = (uint8_t)(c32 >> 24);
                 }
-                sh->outBytes = total;
             }
             __syncthreads();
-            B2C_PHASE(13);
             // one coalesced write-back
             if (total <= P.dst_cap) {
                 if ((reinterpret_cast<uintptr_t>(gdst) & 15) == 0) {
                     const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
                     uint4 *d4 = reinterpret_cast<uint4 *>(gdst);
                     uint32_t n16 = total / 16;
-                    for (uint32_t i = tid; i < n16; i += ENC_NT) d4[i] = s4[i];
-                    for (uint32_t i = n16 * 16 + tid; i < total; i += ENC_NT) gdst[i] = stage[i];
+                    for (uint32_t i = tid; i < n16; i += PACK_NT) d4[i] = s4[i];
+                    for (uint32_t i = n16 * 16 + tid; i < total; i += PACK_NT) gdst[i] = stage[i];
                 } else {
-                    for (uint32_t i = tid; i < total; i += ENC_NT) gdst[i] = stage[i];
+                    for (uint32_t i = tid; i < total; i += PACK_NT) gdst[i] = stage[i];
                 }
                 if (tid == 0) P.out_sizes[chunk] = (int64_t)total;
             } else if (tid == 0) P.out_sizes[chunk] = -4;  // destination too small
@@ -720,8 +816,6 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
                 uint32_t *d = P.dbg_hdr + (uint64_t)chunk * 4;
                 d[0] = nseq; d[1] = nlit; d[2] = 0; d[3] = litMode;
             }
-            __syncthreads();
-            B2C_PHASE(14);
             return;
         }
         kind = 1;  // fall through to the raw block
@@ -730,61 +824,118 @@ B2C_DEV void zstd_encode_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t c
     // ---------------------------------------------------------------- raw / RLE block (+ frame)
     {
         __syncthreads();
-        // header assembled in the (now free) L region; payload streamed from global memory
-        uint8_t *hdr = smem + ENC_SMEM_L;
+        uint8_t *hdr = stage;
         if (tid == 0) {
             uint32_t o = 0;
-            if (frame) {
-                hdr[o++] = 0x28; hdr[o++] = 0xB5; hdr[o++] = 0x2F; hdr[o++] = 0xFD;
-                if (n == 0) {
-                    // WithZeroFrames: single segment, no checksum, FCS byte 0 (encoder.go:732-751)
-                    hdr[o++] = 32; hdr[o++] = 0;
-                } else {
-                    bool single = n > 1024;
-                    uint32_t fcs = (n >= 256) ? ((n >= 65536 + 256) ? 2u : 1u) : 0u;
-                    hdr[o++] = (uint8_t)((crc ? 4u : 0u) | (single ? 32u : 0u) | (fcs << 6));
-                    if (!single) {
-                        uint32_t ws = 1u << (32 - (uint32_t)__clz((int)n));
-                        if (ws < 1024) ws = 1024;
-                        hdr[o++] = (uint8_t)(((32 - (uint32_t)__clz((int)(ws - 1))) - 10) << 3);
-                    }
-                    if (fcs == 0) { if (single) hdr[o++] = (uint8_t)n; }
-                    else if (fcs == 1) { uint32_t v = n - 256; hdr[o++] = (uint8_t)v; hdr[o++] = (uint8_t)(v >> 8); }
-                    else { hdr[o++] = (uint8_t)n; hdr[o++] = (uint8_t)(n >> 8); hdr[o++] = (uint8_t)(n >> 16); hdr[o++] = (uint8_t)(n >> 24); }
-                }
-            }
-            uint32_t bh = (kind == 2) ? (1u | (1u << 1) | (sh->rleLen << 3)) : (1u | (0u << 1) | (n << 3));
+            if (frame) o = write_frame_header(hdr, n, crc);
+            uint32_t bh = (kind == 2) ? (1u | (1u << 1) | (W->rleLen << 3)) : (1u | (0u << 1) | (n << 3));
             hdr[o++] = (uint8_t)bh; hdr[o++] = (uint8_t)(bh >> 8); hdr[o++] = (uint8_t)(bh >> 16);
-            sh->pos = o;
+            ps->pos = o;
         }
         __syncthreads();
-        const uint32_t hlen = sh->pos;
+        const uint32_t hlen = ps->pos;
         const uint32_t body = (kind == 2) ? 1u : n;
         const bool crcHere = crc && n > 0;
         const uint32_t total = hlen + body + (crcHere ? 4u : 0u);
         if (total <= P.dst_cap) {
-            for (uint32_t i = tid; i < hlen; i += ENC_NT) gdst[i] = hdr[i];
-            for (uint32_t i = tid; i < body; i += ENC_NT) gdst[hlen + i] = gsrc[i];
-            if (crcHere && tid < 4) gdst[hlen + body + tid] = (uint8_t)((uint32_t)sh->xxh >> (8 * tid));
+            for (uint32_t i = tid; i < hlen; i += PACK_NT) gdst[i] = hdr[i];
+            for (uint32_t i = tid; i < body; i += PACK_NT) gdst[hlen + i] = gsrc[i];
+            if (crcHere && tid < 4) gdst[hlen + body + tid] = (uint8_t)((uint32_t)W->xxh >> (8 * tid));
             if (tid == 0) P.out_sizes[chunk] = (int64_t)total;
         } else if (tid == 0) P.out_sizes[chunk] = -4;
         if (P.dbg_hdr && tid == 0) {
             uint32_t *d = P.dbg_hdr + (uint64_t)chunk * 4;
             d[0] = nseq; d[1] = nlit; d[2] = kind; d[3] = 0;
         }
-        __syncthreads();
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K5
+// XXH64 (zstd/internal/xxhash/xxhash.go:62-160): four lanes per chunk hold the four accumulators.
+B2C_DEV void zstd_xxh_quad(const ZstdEncParams &P, uint32_t chunk, unsigned q /*0..3*/, unsigned quadBaseLane) {
+    const uint64_t P1 = 11400714785074694791ull, P2 = 14029467366897019727ull, P3 = 1609587929392839161ull,
+                   P4 = 9650029242287828579ull, P5 = 2870177450012600261ull;
+    const bool live = chunk < P.nchunks;
+    const uint8_t *src = P.src_base + (uint64_t)(live ? chunk : 0) * P.src_stride;
+    const uint32_t n = live ? chunk_size(P, chunk) : 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
+    uint64_t v = (q == 0) ? P1 + P2 : (q == 1) ? P2 : (q == 2) ? 0ull : (0ull - P1);
+    uint32_t stripes = (n <= ENC_MAX_CHUNK) ? n / 32 : 0;
+    for (uint32_t i = 0; i < stripes; i++) {
+        uint64_t in;
+        if (aligned) in = reinterpret_cast<const uint64_t *>(src)[4 * i + q];
+        else { in = 0; for (int b = 0; b < 8; b++) in |= (uint64_t)src[32 * i + 8 * q + b] << (8 * b); }
+        v += in * P2;
+        v = (v << 31) | (v >> 33);
+        v *= P1;
+    }
+    uint64_t v1 = __shfl_sync(FULLMASK, v, quadBaseLane), v2 = __shfl_sync(FULLMASK, v, quadBaseLane + 1),
+             v3 = __shfl_sync(FULLMASK, v, quadBaseLane + 2), v4 = __shfl_sync(FULLMASK, v, quadBaseLane + 3);
+    if (q != 0 || !live || n > ENC_MAX_CHUNK) return;
+    uint64_t h;
+    uint32_t p = stripes * 32;
+    if (n >= 32) {
+        h = ((v1 << 1) | (v1 >> 63)) + ((v2 << 7) | (v2 >> 57)) + ((v3 << 12) | (v3 >> 52)) + ((v4 << 18) | (v4 >> 46));
+#define XMERGE(vv)                                                                                     \
+    do {                                                                                               \
+        uint64_t t_ = (vv) * P2; t_ = (t_ << 31) | (t_ >> 33); t_ *= P1;                               \
+        h ^= t_; h = h * P1 + P4;                                                                      \
+    } while (0)
+        XMERGE(v1); XMERGE(v2); XMERGE(v3); XMERGE(v4);
+#undef XMERGE
+    } else {
+        h = P5;
+    }
+    h += (uint64_t)n;
+    while (p + 8 <= n) {
+        uint64_t k1 = 0;
+        for (int b = 0; b < 8; b++) k1 |= (uint64_t)src[p + b] << (8 * b);
+        k1 *= P2; k1 = (k1 << 31) | (k1 >> 33); k1 *= P1;
+        h ^= k1; h = ((h << 27) | (h >> 37)) * P1 + P4;
+        p += 8;
+    }
+    if (p + 4 <= n) {
+        uint32_t k4 = 0;
+        for (int b = 0; b < 4; b++) k4 |= (uint32_t)src[p + b] << (8 * b);
+        h ^= (uint64_t)k4 * P1;
+        h = ((h << 23) | (h >> 41)) * P2 + P3;
+        p += 4;
+    }
+    while (p < n) {
+        h ^= (uint64_t)src[p] * P5;
+        h = ((h << 11) | (h >> 53)) * P1;
+        p++;
+    }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    P.work[chunk].xxh = h;
+}
+
 #ifndef B2C_EMU
-extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_zstd_encode_kernel(ZstdEncParams P) {
+extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_zstd_parse_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
-    // predefined FSE tables: once per CTA
-    EncShared *sh = reinterpret_cast<EncShared *>(smem + ENC_SMEM_SH);
-    if (threadIdx.x < 3) seq_build_predef(&sh->sw, (int)threadIdx.x);
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk(smem, P, c, scratch);
+}
+extern "C" __global__ void __launch_bounds__(128) b2c_zstd_tables_kernel(ZstdEncParams P) {
+    __shared__ TablesShared ts;
+    if (threadIdx.x < 3) seq_build_predef(&ts.sw, (int)threadIdx.x);
     __syncthreads();
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_encode_chunk(smem, P, c, scratch);
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) {
+        zstd_tables_chunk(&ts, P, c);
+        __syncthreads();
+    }
+}
+extern "C" __global__ void __launch_bounds__(CHAIN_NT) b2c_zstd_chains_kernel(ZstdEncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    zstd_chains_block(reinterpret_cast<uint32_t *>(smem), P, blockIdx.x * 32);
+}
+extern "C" __global__ void __launch_bounds__(PACK_NT) b2c_zstd_pack_kernel(ZstdEncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    zstd_pack_chunk(smem, P, blockIdx.x);
+}
+extern "C" __global__ void __launch_bounds__(128) b2c_zstd_xxh_kernel(ZstdEncParams P) {
+    unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+    zstd_xxh_quad(P, gt >> 2, gt & 3, (threadIdx.x & 31) & ~3u);
 }
 #endif
 

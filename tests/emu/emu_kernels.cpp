@@ -11,27 +11,47 @@ extern "C" {
 
 void emu_set_lane_order(int desc) { emu::lane_order_desc = desc; }
 
-// Encode nchunks chunks laid out contiguously (chunk i = src + i*stride, size sizes[i]).
-// dst slots of dst_stride bytes.  Optional debug dumps (may be null).
+// Encode nchunks chunks laid out contiguously (chunk i = src + i*stride, size sizes[i]) with the same five
+// kernels the device runs.  dst slots of dst_stride bytes.  Optional debug dumps (may be null).
 int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
                     uint64_t dst_stride, int64_t *out_sizes, uint32_t flags, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
                     uint8_t *dbg_lits, uint32_t dbg_seq_cap) {
     std::vector<uint8_t> scratch(ENC_SCRATCH_BYTES, 0xCD);
+    ChunkWork *work = (ChunkWork *)aligned_alloc(16, sizeof(ChunkWork) * (size_t)nchunks);
+    memset(work, 0xCD, sizeof(ChunkWork) * (size_t)nchunks);
     ZstdEncParams P;
     memset(&P, 0, sizeof(P));
-    P.srcs = nullptr; P.src_base = src; P.src_stride = stride; P.src_sizes = sizes; P.src_size_all = 0;
-    P.dsts = nullptr; P.dst_base = dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
-    P.out_sizes = out_sizes; P.nchunks = nchunks; P.flags = flags; P.scratch = scratch.data();
+    P.src_base = src; P.src_stride = stride; P.src_sizes = sizes; P.src_size_all = 0;
+    P.dst_base = dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
+    P.out_sizes = out_sizes; P.nchunks = nchunks; P.flags = flags; P.scratch = scratch.data(); P.work = work;
     P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_seq_cap;
-    emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
-        uint8_t *smem = emu::dyn_smem;
-        EncShared *sh = reinterpret_cast<EncShared *>(smem + ENC_SMEM_SH);
-        if (threadIdx.x < 3) seq_build_predef(&sh->sw, (int)threadIdx.x);
-        __syncthreads();
-        for (uint32_t c = 0; c < P.nchunks; c++) zstd_encode_chunk(smem, P, c, P.scratch);
+    // K5 xxh64
+    emu::launch((4 * nchunks + 127) / 128, 128, 0, [&]() {
+        unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+        zstd_xxh_quad(P, gt >> 2, gt & 3, (threadIdx.x & 31) & ~3u);
     });
+    // K1 parse
+    emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
+        for (uint32_t c = 0; c < P.nchunks; c++) zstd_parse_chunk(emu::dyn_smem, P, c, P.scratch);
+    });
+    // K2 tables
+    static TablesShared ts;
+    emu::launch(1, 128, 0, [&]() {
+        if (threadIdx.x < 3) seq_build_predef(&ts.sw, (int)threadIdx.x);
+        __syncthreads();
+        for (uint32_t c = 0; c < P.nchunks; c++) { zstd_tables_chunk(&ts, P, c); __syncthreads(); }
+    });
+    // K3 chains
+    emu::launch((nchunks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, [&]() {
+        zstd_chains_block(reinterpret_cast<uint32_t *>(emu::dyn_smem), P, blockIdx.x * 32);
+    });
+    // K4 pack
+    emu::launch(nchunks, PACK_NT, PACK_SMEM_BYTES, [&]() { zstd_pack_chunk(emu::dyn_smem, P, blockIdx.x); });
+    free(work);
     return 0;
 }
 
 uint32_t emu_enc_smem_bytes() { return ENC_SMEM_BYTES; }
+uint32_t emu_pack_smem_bytes() { return PACK_SMEM_BYTES; }
+uint64_t emu_chunkwork_bytes() { return sizeof(ChunkWork); }
 }

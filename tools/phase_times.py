@@ -24,13 +24,11 @@ def main():
         check(rc, enc._ctx)
         torch.cuda.synchronize()
     c = cyc.cpu().numpy().astype(np.int64)       # [n, 16, 32] arrival of warp w at the barrier before stamp k
-    rel = c[:, :15, :].max(axis=2)                 # release time of each barrier
-    tot = rel[:, 14] - c[:, 0, :].min(axis=1)
-    print("chunks", n, "mean cycles/chunk %.0f" % tot.mean(), "min", tot.min(), "max", tot.max())
-    names = ["load", "Ebuild", "parse", "layout+gather+rle", "hist", "huf stats+sort", "tree | fse tables",
-             "bits,vals,write | chains", "lit sizes+decide", "seq sizes", "zero + lit pack", "seq pack", "headers",
-             "writeback"]
-    for k in range(14):
+    rel = c[:, :6, :].max(axis=2)                  # release time of each barrier (K1 has stamps 0..5)
+    tot = rel[:, 5] - c[:, 0, :].min(axis=1)
+    print("K1 parse kernel: chunks", n, "mean cycles/chunk %.0f" % tot.mean(), "min", tot.min(), "max", tot.max())
+    names = ["load", "Ebuild", "parse", "layout+gather+rle", "hist+writeout"]
+    for k in range(5):
         dur = rel[:, k + 1] - rel[:, k]
         work = c[:, k + 1, :] - rel[:, k][:, None]          # per-warp busy time in this phase
         wmean = work.mean(axis=0)
