@@ -69,8 +69,8 @@ struct alignas(16) ChunkWork {
     uint16_t seqLL[ENC_MAXSEQ];
     uint16_t seqML[ENC_MAXSEQ];
     uint32_t seqOF[ENC_MAXSEQ];
-    uint8_t codes[3][ENC_MAXSEQ];
-    uint16_t stb[3][ENC_MAXSEQ];
+    alignas(16) uint8_t codes[3][ENC_MAXSEQ];
+    alignas(16) uint16_t stb[3][ENC_MAXSEQ];
 };
 
 struct ZstdEncParams {
@@ -108,11 +108,11 @@ struct ZstdEncParams {
 
 B2C_DEV uint32_t chunk_size(const ZstdEncParams &P, uint32_t c) { return P.src_sizes ? P.src_sizes[c] : P.src_size_all; }
 
-// 6-byte multiplicative hash (same construction as zstd/hash.go hashLen(u, 32, 6))
+// 6-byte multiplicative hash: two 32-bit multiply-adds (the reference's hashLen(u, bits, 6), zstd/hash.go:27,
+// is a 64-bit multiply = ~8 integer instructions per position on the SM; table contents are an
+// implementation detail, only the verified matches reach the output).
 B2C_DEV uint32_t enc_hash6(uint32_t lo, uint32_t hi) {
-    const uint64_t prime6 = 227718039650203ull;
-    uint64_t u = ((uint64_t)hi << 32) | lo;
-    return (uint32_t)(((u << 16) * prime6) >> 32);
+    return lo * 0x9E3779B1u + (hi & 0xffffu) * 0x85EBCA6Bu;
 }
 
 // length of the common prefix of src[a..limitA) and src[b..], cooperative over the warp
@@ -230,28 +230,41 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             }
         }
         __syncthreads();
-        // fix-up rounds: a slot only ever decreases, so this converges to the exact minimum
-        for (;;) {
-            int changed = 0;
+        // fix-up pass: every position checks its slot once; the (rare) losers of a write race take the slot with an
+        // atomic compare-and-swap minimum on the containing 32-bit word, so the table is exactly the minimum.
+        {
+            uint32_t *E32 = reinterpret_cast<uint32_t *>(E);
             for (uint32_t g = tid; g < ngroups; g += ENC_NT) {
                 uint32_t w0 = srcw[g], w1 = srcw[g + 1], w2 = srcw[g + 2];
                 uint32_t p = 4 * g;
-                uint32_t h[4];
+                uint32_t h[4], e[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
                     uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
                     h[j] = enc_hash6(lo, hi) >> (32 - ENC_EBITS);
                 }
-                uint32_t e[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) e[j] = E[h[j]];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (p + j < npos && e[j] > p + j && E[h[j]] > p + j) { E[h[j]] = (uint16_t)(p + j); changed = 1; }
+                for (int j = 0; j < 4; j++) {
+                    uint32_t pj = p + j;
+                    if (pj < npos && e[j] > pj) {
+                        uint32_t widx = h[j] >> 1, shft = (h[j] & 1) * 16;
+                        uint32_t old = E32[widx];
+                        for (;;) {
+                            uint32_t curv = (old >> shft) & 0xffffu;
+                            if (curv <= pj) break;
+                            uint32_t nv = (old & ~(0xffffu << shft)) | (pj << shft);
+                            uint32_t prev = atomicCAS(&E32[widx], old, nv);
+                            if (prev == old) break;
+                            old = prev;
+                        }
+                    }
+                }
             }
-            if (!__syncthreads_or(changed)) break;
         }
+        __syncthreads();
     }
     B2C_PHASE(2);
 
@@ -287,28 +300,20 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                     if (lose) L[hL] = (uint16_t)rel;
                     __syncwarp();
                 }
-                // candidates: recent-in-sub-range first, else earliest-in-chunk; 8 bytes compared at once
+                // candidates: recent-in-sub-range first, else earliest-in-chunk; 4 bytes verify, 4 more extend
                 uint32_t q = 0, mlen = 0, bk = 0;
                 if (valid) {
-                    uint32_t eq = 0;
-                    if (candL != 0xffff) {
-                        uint64_t x = cv ^ ld64u(src, b0 + candL);
-                        eq = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
-                        q = b0 + candL;
-                    }
-                    if (eq < 4 && candE < p) {
-                        uint64_t x = cv ^ ld64u(src, candE);
-                        eq = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
-                        q = candE;
-                    }
-                    if (eq >= 4) {
+                    bool ok = false;
+                    if (candL != 0xffff) { q = b0 + candL; ok = ld32u(src, q) == c_lo; }
+                    if (!ok && candE < p) { q = candE; ok = ld32u(src, q) == c_lo; }
+                    if (ok) {
+                        uint32_t x = ld32u(src, q + 4) ^ c_hi;
+                        uint32_t eq = 4 + (x ? (uint32_t)(__ffs((int)x) - 1) >> 3 : 4u);
                         uint32_t room = e0 - p;             // matches never cross the sub-range end
                         mlen = eq < room ? eq : room;
                         if (mlen < 4) mlen = 0;
-                    }
-                    if (mlen) {
-                        // bytes equal just before the match (at most 4, never before position 0)
-                        if (q >= 4) {
+                        else if (q >= 4) {
+                            // bytes equal just before the match (at most 4, never before position 0)
                             uint32_t xb = ld32u(src, p - 4) ^ ld32u(src, q - 4);
                             bk = xb ? (uint32_t)__clz((int)xb) >> 3 : 4u;
                         }
@@ -317,6 +322,8 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                 unsigned mask = __ballot_sync(FULLMASK, mlen != 0);
                 uint32_t next = cur + 32;
                 uint32_t from = 0;
+                bool sel = false;
+                uint32_t recx = 0, recy = 0;
                 while (true) {
                     unsigned m = (from < 32) ? (mask & (0xffffffffu << from)) : 0u;
                     if (m == 0) break;
@@ -331,16 +338,23 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                     const uint32_t s = pf - back;
                     len += back;
                     const bool isrep = (ownNew >= 1) && (off == rep0) && (s > nextEmit);
-                    if (lane == 0) {
+                    if (lane == (unsigned)f) {
                         // record: x = litLen | (matchLen-3) << 16 ; y = dist (0 = repeat) | matchStart << 16
-                        rec[nrec] = make_uint2((s - nextEmit) | ((len - 3) << 16), (isrep ? 0u : off) | (s << 16));
+                        sel = true;
+                        recx = (s - nextEmit) | ((len - 3) << 16);
+                        recy = (isrep ? 0u : off) | (s << 16);
                     }
-                    nrec++;
                     sumML += len;
                     if (!isrep) { rep0 = off; ownNew++; }
                     nextEmit = s + len;
                     if (nextEmit >= cur + 32) { next = nextEmit; break; }
                     from = nextEmit - cur;
+                }
+                // the selected lanes store their records side by side (window order = lane order)
+                {
+                    unsigned selmask = __ballot_sync(FULLMASK, sel);
+                    if (sel) rec[nrec + (uint32_t)__popc(selmask & ((1u << lane) - 1))] = make_uint2(recx, recy);
+                    nrec += (uint32_t)__popc(selmask);
                 }
                 cur = next;
             }
@@ -545,9 +559,10 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
 
 // ------------------------------------------------------------------------------------------------ K3
 // One lane per (chunk, chain): CTA = 96 threads = 3 warps; warp c walks chain c of 32 consecutive chunks.
-// Per-lane tables live in shared memory, interleaved so that lane l only ever touches bank l.
+// Per-lane tables live in shared memory, interleaved so that lane l only ever touches bank l:
+// 128 words of packed u16 next-states + 64 words of (deltaNbBits | (deltaFindState + 512) << 21).
 constexpr int CHAIN_NT = 96;
-constexpr uint32_t CHAIN_SMEM_WORDS_PER_LANE = 128 + 64 + 64;  // stateTable (256 x u16), deltaNbBits, deltaFindState
+constexpr uint32_t CHAIN_SMEM_WORDS_PER_LANE = 128 + 64 + 4;   // + 8 x u16 output staging
 constexpr uint32_t CHAIN_SMEM_BYTES = CHAIN_NT * CHAIN_SMEM_WORDS_PER_LANE * 4;
 B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_t chunk0) {
     const unsigned tid = threadIdx.x, lane = tid & 31, which = tid >> 5;
@@ -555,10 +570,9 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
     const bool live = chunk < P.nchunks && P.work[chunk < P.nchunks ? chunk : 0].kind == 0;
     ChunkWork *W = P.work + (live ? chunk : 0);
     uint32_t *st32 = smem32 + which * 32 * CHAIN_SMEM_WORDS_PER_LANE;  // this warp's region
-    // element i of lane l at st32[i * 32 + l]
-    uint32_t *tState = st32 + lane;                 // 128 words: two u16 states per word
-    uint32_t *tNb = st32 + 128 * 32 + lane;         // 64 words
-    uint32_t *tFs = st32 + (128 + 64) * 32 + lane;  // 64 words (sign-extended int16)
+    uint32_t *tState = st32 + lane;            // element i of lane l at [i * 32 + l]
+    uint32_t *tSym = st32 + 128 * 32 + lane;
+    uint16_t *outq = reinterpret_cast<uint16_t *>(st32 + (128 + 64) * 32) + lane * 8;  // 16 bytes per lane
     uint32_t nseq = 0, useRLE = 1, tableLog = 0;
     if (live) {
         const FseCTable *t = &W->tbl[which];
@@ -568,7 +582,8 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
             uint32_t ts2 = (1u << tableLog) / 2;
             for (uint32_t i = 0; i < ts2; i++) tState[i * 32] = sw[i];
             uint32_t sl = t->symbolLen;
-            for (uint32_t i = 0; i < sl; i++) { tNb[i * 32] = t->deltaNbBits[i]; tFs[i * 32] = (uint32_t)(int32_t)t->deltaFindState[i]; }
+            for (uint32_t i = 0; i < sl; i++)
+                tSym[i * 32] = t->deltaNbBits[i] | ((uint32_t)((int32_t)t->deltaFindState[i] + 512) << 21);
         }
     }
     __syncwarp();
@@ -577,24 +592,48 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
     uint32_t state = 0;
     if (live && !useRLE) {
         uint32_t sym = codes[nseq - 1];
-        uint32_t dnb = tNb[sym * 32];
+        uint32_t e = tSym[sym * 32];
+        uint32_t dnb = e & 0x1fffffu;
+        int32_t dfs = (int32_t)(e >> 21) - 512;
         uint32_t nbBitsOut = (dnb + (1u << 15)) >> 16;
         int32_t im = (int32_t)((nbBitsOut << 16) - dnb);
-        int32_t lu = (im >> nbBitsOut) + (int32_t)tFs[sym * 32];
+        int32_t lu = (im >> nbBitsOut) + dfs;
         uint32_t wv = tState[(lu >> 1) * 32];
         state = (lu & 1) ? (wv >> 16) : (wv & 0xffff);
     }
-    uint32_t steps = (live && !useRLE && nseq) ? nseq - 1 : 0;
-    uint32_t maxSteps = warp_max(steps);
+    const uint32_t steps = (live && !useRLE && nseq) ? nseq - 1 : 0;
+    const uint32_t maxSteps = warp_max(steps);
+    // codes are consumed from index nseq-2 downwards, one aligned 32-bit word (4 codes) per load, the next word
+    // requested one word ahead of its use
+    const uint32_t *cw32 = reinterpret_cast<const uint32_t *>(codes);
+    int32_t idx = (int32_t)nseq - 2;
+    uint32_t cw = 0, cwNext = 0;
+    if (steps) {
+        cw = cw32[idx >> 2];
+        cwNext = (idx >= 4) ? cw32[(idx >> 2) - 1] : 0;
+    }
     for (uint32_t t = 1; t <= maxSteps; t++) {
         if (t <= steps) {
-            uint32_t idx = nseq - 1 - t;
-            uint32_t sym = codes[idx];
-            uint32_t nb = (state + tNb[sym * 32]) >> 16;
-            stb[idx] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
-            int32_t lu = (int32_t)(state >> nb) + (int32_t)tFs[sym * 32];
+            uint32_t sym = (cw >> (8 * (idx & 3))) & 0xffu;
+            uint32_t e = tSym[sym * 32];
+            uint32_t nb = (state + (e & 0x1fffffu)) >> 16;
+            // eight results are staged in shared memory and leave as one 16-byte store (a 2-byte store per step
+            // from 32 lanes to 32 different sectors costs 16x the write traffic)
+            outq[idx & 7] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
+            if ((idx & 7) == 0) {
+                if (idx + 8 <= (int32_t)nseq - 1)
+                    *reinterpret_cast<uint4 *>(stb + idx) = *reinterpret_cast<const uint4 *>(outq);
+                else
+                    for (int32_t k = idx; k <= (int32_t)nseq - 2; k++) stb[k] = outq[k & 7];
+            }
+            int32_t lu = (int32_t)(state >> nb) + ((int32_t)(e >> 21) - 512);
             uint32_t wv = tState[(lu >> 1) * 32];
             state = (lu & 1) ? (wv >> 16) : (wv & 0xffff);
+            if ((idx & 3) == 0) {
+                cw = cwNext;
+                if (idx >= 8) cwNext = cw32[(idx >> 2) - 2];
+            }
+            idx--;
         }
     }
     if (live) {
@@ -610,7 +649,9 @@ struct PackShared {
     uint32_t litMode, lhSize, litPayload, pos;
 };
 constexpr uint32_t PACK_STAGE_BYTES = ENC_MAX_CHUNK + 128;
-constexpr uint32_t PACK_SMEM_BYTES = PACK_STAGE_BYTES + ((sizeof(PackShared) + 15) / 16) * 16;
+constexpr uint32_t PACK_LIT_SMEM = 40 * 1024;   // literals are staged in shared memory when they fit
+constexpr uint32_t PACK_SMEM_SH = PACK_STAGE_BYTES + PACK_LIT_SMEM;
+constexpr uint32_t PACK_SMEM_BYTES = PACK_SMEM_SH + ((sizeof(PackShared) + 15) / 16) * 16;
 
 B2C_DEV uint32_t frame_header_bytes(uint32_t n) {
     if (n == 0) return 6;
@@ -641,7 +682,7 @@ B2C_DEV uint32_t write_frame_header(uint8_t *o8, uint32_t n, bool crc) {
 B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk) {
     const unsigned tid = threadIdx.x;
     uint8_t *stage = smem;
-    PackShared *ps = reinterpret_cast<PackShared *>(smem + PACK_STAGE_BYTES);
+    PackShared *ps = reinterpret_cast<PackShared *>(smem + PACK_SMEM_SH);
     ChunkWork *W = P.work + chunk;
     const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
     uint8_t *gdst = P.dst_base + (uint64_t)chunk * P.dst_stride;
@@ -655,6 +696,13 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
 
     if (kind == 0) {
         const uint8_t *lit = W->lit;
+        if (nlit <= PACK_LIT_SMEM) {
+            uint8_t *ls = smem + PACK_STAGE_BYTES;
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(W->lit);
+            uint4 *s4 = reinterpret_cast<uint4 *>(ls);
+            for (uint32_t i = tid; i < (nlit + 15) / 16; i += PACK_NT) s4[i] = g4[i];
+            lit = ls;
+        }
         HufWork *hw = &ps->hw;
         // Huffman table into shared memory
         for (uint32_t s = tid; s < 256; s += PACK_NT) { hw->ctVal[s] = W->ctVal[s]; hw->ctBits[s] = W->ctBits[s]; }
