@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../include/b2c.h"
 #include "b2c_zstd_enc.cuh"
+#include "b2c_zstd_dec.cuh"
 
 using namespace b2c;
 
@@ -37,6 +38,14 @@ struct b2c_ctx {
     uint32_t *d_src_sizes2 = nullptr, *h_src_sizes2 = nullptr;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // decoder: per-warp literal scratch, host-path staging (grown on demand)
+    uint8_t *d_dec_lit = nullptr; size_t dec_lit_cap = 0;
+    uint8_t *d_dec_in = nullptr, *d_dec_out = nullptr; size_t dec_in_cap = 0, dec_out_cap = 0;
+    uint8_t *d_dec_meta = nullptr; size_t dec_meta_cap = 0;
+    // optional per-kernel timing of the encode pipeline (b2c_profile_*): 6 events per encode call
+    bool prof = false;
+    std::vector<cudaEvent_t> pev;
+    size_t pev_used = 0;
     uint64_t launches = 0;
     char err[256] = {0};
 };
@@ -133,6 +142,8 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)ENC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)CHAIN_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)PACK_SMEM_BYTES) == cudaSuccess;
     if (ok && max_chunks) {
@@ -165,11 +176,13 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
 void b2c_ctx_destroy(b2c_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_dec_lit); cudaFree(ctx->d_dec_in); cudaFree(ctx->d_dec_out); cudaFree(ctx->d_dec_meta);
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
     cudaFree(ctx->d_sizes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_src_sizes);
     cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_sizes); cudaFreeHost(ctx->h_src_sizes);
     cudaFree(ctx->d_in2); cudaFree(ctx->d_out2); cudaFree(ctx->d_packed2); cudaFree(ctx->d_sizes2);
     cudaFree(ctx->d_offsets2); cudaFree(ctx->d_src_sizes2); cudaFreeHost(ctx->h_sizes2); cudaFreeHost(ctx->h_src_sizes2);
+    for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
     if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
     if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -186,6 +199,10 @@ const char *b2c_strerror(int code) {
     case B2C_ERR_TOO_BIG: return "chunk too big for this level's block size";
     case B2C_ERR_DST_SMALL: return "destination too small";
     case B2C_ERR_CORRUPT: return "corrupt input";
+    case B2C_ERR_MAGIC: return "invalid input: magic number mismatch";
+    case B2C_ERR_WINDOW: return "window size exceeded";
+    case B2C_ERR_CRC: return "CRC check failed";
+    case B2C_ERR_SIZE: return "frame size exceeded / mismatch";
     case B2C_ERR_UNSUPPORTED: return "unsupported";
     default: return "unknown error";
     }
@@ -193,6 +210,30 @@ const char *b2c_strerror(int code) {
 const char *b2c_last_cuda_error(b2c_ctx *ctx) { return ctx ? ctx->err : "no context"; }
 int b2c_sm_count(b2c_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t b2c_launch_count(b2c_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b2c_profile_enable(b2c_ctx *ctx, int on) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    ctx->prof = on != 0;
+    ctx->pev_used = 0;
+    return B2C_OK;
+}
+// ms[k] = summed duration of kernel k (0 xxh64, 1 parse, 2 tables, 3 chains, 4 pack) over the encode calls issued
+// since b2c_profile_enable(ctx, 1); *ncalls = number of encode calls.  Synchronises the device.
+int b2c_profile_read(b2c_ctx *ctx, double *ms, uint32_t *ncalls) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < 5; k++) ms[k] = 0.0;
+    for (size_t c = 0; c + 6 <= ctx->pev_used; c += 6)
+        for (int k = 0; k < 5; k++) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, ctx->pev[c + k], ctx->pev[c + k + 1]));
+            ms[k] += (double)t;
+        }
+    if (ncalls) *ncalls = (uint32_t)(ctx->pev_used / 6);
+    ctx->pev_used = 0;
+    return B2C_OK;
+}
 
 size_t b2c_zstd_bound(size_t size, int level) {
     // Encoder.MaxEncodedSize, zstd/encoder.go:843-873 (crc on)
@@ -237,13 +278,33 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     unsigned sms = (unsigned)ctx->sm_count;
     unsigned g1 = sms < nchunks ? sms : nchunks;
     unsigned g2 = sms * 8 < nchunks ? sms * 8 : nchunks;
-    if ((flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC))
+    cudaEvent_t *pe = nullptr;
+    if (ctx->prof) {
+        while (ctx->pev.size() < ctx->pev_used + 6) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            ctx->pev.push_back(e);
+        }
+        pe = ctx->pev.data() + ctx->pev_used;
+        ctx->pev_used += 6;
+    }
+#define PEV(k) do { if (pe) cudaEventRecord(pe[k], st); } while (0)
+    PEV(0);
+    if ((flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC)) {
         b2c_zstd_xxh_kernel<<<(4 * nchunks + 127) / 128, 128, 0, st>>>(P);
+        ctx->launches += 1;
+    }
+    PEV(1);
     b2c_zstd_parse_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+    PEV(2);
     b2c_zstd_tables_kernel<<<g2, 128, 0, st>>>(P);
+    PEV(3);
     b2c_zstd_chains_kernel<<<(nchunks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, st>>>(P);
+    PEV(4);
     b2c_zstd_pack_kernel<<<nchunks, PACK_NT, PACK_SMEM_BYTES, st>>>(P);
-    ctx->launches += 5;
+    PEV(5);
+#undef PEV
+    ctx->launches += 4;
     CK(cudaGetLastError());
     return B2C_OK;
 }
@@ -397,6 +458,91 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
     CK(cudaStreamSynchronize(ctx->stream2));
     if (total_out) *total_out = out_pos;
     return rc;
+}
+
+
+// ---- decoder ------------------------------------------------------------------------------------
+static int grow(b2c_ctx *ctx, uint8_t **p, size_t *cap, size_t need) {
+    if (*cap >= need) return B2C_OK;
+    CK(cudaDeviceSynchronize());
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    need += need / 4;
+    CK(cudaMalloc(p, need));
+    *cap = need;
+    return B2C_OK;
+}
+
+static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st) {
+    if (P.nchunks == 0) return B2C_OK;
+    const unsigned ctasPerSm = (227u * 1024u) / (DEC_SMEM_BYTES + 1024u);
+    unsigned grid = (P.nchunks + DEC_WARPS - 1) / DEC_WARPS;
+    unsigned maxGrid = (unsigned)ctx->sm_count * (ctasPerSm ? ctasPerSm : 1);
+    if (grid > maxGrid) grid = maxGrid;
+    int rc = grow(ctx, &ctx->d_dec_lit, &ctx->dec_lit_cap, (size_t)maxGrid * DEC_WARPS * DEC_LIT_SCRATCH);
+    if (rc) return rc;
+    P.lit_scratch = ctx->d_dec_lit;
+    b2c_zstd_decode_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, st>>>(P);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_zstd_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, const uint64_t *d_src_offsets,
+                           const uint32_t *d_src_sizes, void *d_dst, size_t dst_stride, const uint64_t *d_dst_offsets,
+                           uint32_t dst_cap, int64_t *d_out_sizes, uint32_t nchunks, void *stream) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (!d_src_sizes || !d_out_sizes) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ZstdDecParams P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_offsets = d_src_offsets; P.src_sizes = d_src_sizes;
+    P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_offsets = d_dst_offsets; P.dst_cap = dst_cap;
+    P.out_sizes = d_out_sizes; P.nchunks = nchunks;
+    return launch_decode(ctx, P, (cudaStream_t)stream);
+}
+
+// Host-buffer batch decode: inputs are packed back to back, copied H2D, decoded, outputs copied back.
+int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
+                           const size_t *dst_caps, int64_t *sizes_out, size_t n) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (n == 0) return B2C_OK;
+    if (n > 0xffffffffull) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // meta: src_off[n] u64 | dst_off[n] u64 | out_sizes[n] i64 | src_sizes[n] u32 | dst_caps[n] u32
+    std::vector<uint64_t> meta(3 * n + n);
+    uint64_t *so = meta.data(), *dof = so + n;
+    uint32_t *ss = reinterpret_cast<uint32_t *>(meta.data() + 3 * n), *dc = ss + n;
+    uint64_t inb = 0, outb = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (src_sizes[i] > 0xffffffffull) return B2C_ERR_ARG;
+        so[i] = inb; dof[i] = outb;
+        ss[i] = (uint32_t)src_sizes[i];
+        dc[i] = (uint32_t)(dst_caps[i] > 0xffffffffull ? 0xffffffffull : dst_caps[i]);
+        inb += (src_sizes[i] + 15) & ~(size_t)15;
+        outb += ((size_t)dc[i] + 15) & ~(size_t)15;
+    }
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_dec_in, &ctx->dec_in_cap, inb + 64))) return rc;
+    if ((rc = grow(ctx, &ctx->d_dec_out, &ctx->dec_out_cap, outb + 64))) return rc;
+    if ((rc = grow(ctx, &ctx->d_dec_meta, &ctx->dec_meta_cap, meta.size() * 8))) return rc;
+    for (size_t i = 0; i < n; i++)
+        if (src_sizes[i]) CK(cudaMemcpyAsync(ctx->d_dec_in + so[i], srcs[i], src_sizes[i], cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_dec_meta, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, st));
+    ZstdDecParams P;
+    memset(&P, 0, sizeof(P));
+    uint64_t *dm = reinterpret_cast<uint64_t *>(ctx->d_dec_meta);
+    P.src_base = ctx->d_dec_in; P.src_offsets = dm; P.src_sizes = reinterpret_cast<uint32_t *>(dm + 3 * n);
+    P.dst_base = ctx->d_dec_out; P.dst_offsets = dm + n; P.dst_caps = P.src_sizes + n;
+    P.out_sizes = reinterpret_cast<int64_t *>(dm + 2 * n); P.nchunks = (uint32_t)n;
+    if ((rc = launch_decode(ctx, P, st))) return rc;
+    CK(cudaMemcpyAsync(sizes_out, P.out_sizes, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; i++)
+        if (sizes_out[i] > 0) CK(cudaMemcpyAsync(dsts[i], ctx->d_dec_out + dof[i], (size_t)sizes_out[i], cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B2C_OK;
 }
 
 }  // extern "C"

@@ -1,8 +1,9 @@
-"""Host-side mirror of the reference's zstd encoder interface for the accelerated path.
+"""Host-side mirror of the reference's zstd encoder / decoder interface for the accelerated path.
 
 Names follow klauspost/compress/zstd: ``Encoder.EncodeAll`` (zstd/encoder.go:722),
 ``Encoder.MaxEncodedSize`` (:843), levels ``SpeedFastest``/``SpeedDefault``
-(zstd/encoder_options.go), ``WithEncoderCRC``.  The work is done by libb200comp.so
+(zstd/encoder_options.go), ``WithEncoderCRC``; ``Decoder.DecodeAll`` (zstd/decoder.go:319) with the package's
+error values (zstd/zstd.go:40-96).  The work is done by libb200comp.so
 (hand-written sm_100a kernels) through the C ABI in include/b2c.h; PyTorch is only the owner of
 device buffers and streams.
 """
@@ -61,6 +62,19 @@ class Encoder:
     @property
     def sm_count(self):
         return int(lib.b2c_sm_count(self._ctx))
+
+    KERNELS = ("b2c_zstd_xxh_kernel", "b2c_zstd_parse_kernel", "b2c_zstd_tables_kernel", "b2c_zstd_chains_kernel",
+               "b2c_zstd_pack_kernel")
+
+    def profile(self, on=True):
+        check(lib.b2c_profile_enable(self._ctx, 1 if on else 0), self._ctx)
+
+    def profile_read(self):
+        """-> ({kernel name: summed ms}, encode calls) since profile(True); synchronises the device."""
+        ms = (ctypes.c_double * 5)()
+        nc = ctypes.c_uint32(0)
+        check(lib.b2c_profile_read(self._ctx, ms, ctypes.byref(nc)), self._ctx)
+        return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}, int(nc.value)
 
     def MaxEncodedSize(self, size):
         return int(lib.b2c_zstd_bound(size, self.level))
@@ -154,3 +168,98 @@ class Encoder:
             dst += out
             return dst
         return out
+
+
+# ---- decoder ------------------------------------------------------------------------------------
+class ZstdError(B2CError):
+    """Decode error; ``code`` is the C-ABI error code, ``str`` the reference's message class."""
+
+    def __init__(self, code):
+        self.code = int(code)
+        super().__init__(lib.b2c_strerror(self.code).decode())
+
+
+ErrMagicMismatch = -7
+ErrWindowSizeExceeded = -8
+ErrCRCMismatch = -9
+ErrFrameSizeMismatch = -10
+ErrCorrupt = -5
+ErrDecoderSizeExceeded = -4
+
+
+class Decoder:
+    """zstd.Decoder for batches of independent streams on one B200 (one warp per stream)."""
+
+    def __init__(self, device=0, max_decoded=64 << 20):
+        if not torch.cuda.is_available() or lib.b2c_device_count() == 0:
+            raise B2CError("no CUDA device: compress_b200 has no CPU fallback")
+        self.device = device
+        self.max_decoded = max_decoded       # WithDecoderMaxMemory analogue for DecodeAll without a known size
+        self._ctx = lib.b2c_ctx_create(device, 0)
+        if not self._ctx:
+            raise B2CError("b2c_ctx_create failed")
+
+    def close(self):
+        if self._ctx:
+            lib.b2c_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(lib.b2c_launch_count(self._ctx))
+
+    def decode_device(self, src, src_sizes, src_offsets=None, src_stride=0, dst=None, dst_cap=CHUNK, dst_offsets=None,
+                      out_sizes=None, dst_stride=None):
+        """src: uint8 CUDA tensor; stream i is src[off_i : off_i + src_sizes[i]] with off_i = src_offsets[i]
+        (uint64/int64 CUDA tensor) or i*src_stride.  Output i goes to dst[i*dst_cap ...] (or dst_offsets[i]),
+        at most dst_cap bytes.  Returns (dst, out_sizes int64 CUDA tensor: bytes or negative error).  Async."""
+        assert src.is_cuda and src.dtype == torch.uint8
+        n = src_sizes.numel()
+        dev = src.device
+        if dst is None:
+            dst = torch.empty((n, dst_cap), dtype=torch.uint8, device=dev)
+        if out_sizes is None:
+            out_sizes = torch.empty((n,), dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.b2c_zstd_decode_device(
+            self._ctx, src.data_ptr(), src_stride, None if src_offsets is None else src_offsets.data_ptr(),
+            src_sizes.data_ptr(), dst.data_ptr(), dst_cap if dst_stride is None else dst_stride, None if dst_offsets is None else dst_offsets.data_ptr(),
+            dst_cap, out_sizes.data_ptr(), n, ctypes.c_void_p(stream))
+        check(rc, self._ctx)
+        return dst, out_sizes
+
+    def decode_chunks(self, streams, caps=None):
+        """streams: list of bytes-like zstd streams.  Returns (list of bytes or None, list of codes)."""
+        n = len(streams)
+        if n == 0:
+            return [], []
+        if caps is None:
+            caps = [self.max_decoded] * n
+        bufs = [np.frombuffer(bytes(c), dtype=np.uint8) if len(c) else np.zeros(0, dtype=np.uint8) for c in streams]
+        outs = [np.empty(max(int(cp), 1), dtype=np.uint8) for cp in caps]
+        srcs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        ssz = (ctypes.c_size_t * n)(*[len(c) for c in streams])
+        dsts = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+        dcap = (ctypes.c_size_t * n)(*[int(cp) for cp in caps])
+        res = (ctypes.c_int64 * n)()
+        rc = lib.b2c_zstd_decode_chunks(self._ctx, srcs, ssz, dsts, dcap, res, n)
+        check(rc, self._ctx)
+        codes = [int(r) for r in res]
+        return [outs[i][:codes[i]].tobytes() if codes[i] >= 0 else None for i in range(n)], codes
+
+    def DecodeAll(self, input, dst=None, size_hint=None):
+        """DecodeAll decodes a full zstd stream and appends it to dst (zstd/decoder.go:311-385)."""
+        cap = self.max_decoded if size_hint is None else size_hint
+        outs, codes = self.decode_chunks([input], [cap])
+        if codes[0] < 0:
+            raise ZstdError(codes[0])
+        if dst is not None:
+            dst += outs[0]
+            return dst
+        return outs[0]

@@ -37,6 +37,10 @@ enum {
     B2C_ERR_TOO_BIG = -3,       /* chunk larger than the level's block size (zstd: 64 KiB at level 1) */
     B2C_ERR_DST_SMALL = -4,     /* destination slot smaller than the encoded chunk */
     B2C_ERR_CORRUPT = -5,       /* decoder: invalid stream (maps to the zstd package's decode errors) */
+    B2C_ERR_MAGIC = -7,         /* zstd.ErrMagicMismatch */
+    B2C_ERR_WINDOW = -8,        /* zstd.ErrWindowSizeExceeded / ErrWindowSizeTooSmall / ErrBlockTooBig-class */
+    B2C_ERR_CRC = -9,           /* zstd.ErrCRCMismatch */
+    B2C_ERR_SIZE = -10,         /* zstd.ErrFrameSizeExceeded / ErrFrameSizeMismatch / ErrDecoderSizeExceeded */
     B2C_ERR_UNSUPPORTED = -11
 };
 
@@ -60,6 +64,12 @@ B2C_API const char *b2c_last_cuda_error(b2c_ctx *ctx);
 B2C_API int b2c_sm_count(b2c_ctx *ctx);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 B2C_API uint64_t b2c_launch_count(b2c_ctx *ctx);
+
+/* Per-kernel timing of the encode pipeline with CUDA events recorded on the launching stream (bench.py's
+ * roofline).  b2c_profile_enable(ctx, 1) starts collecting; b2c_profile_read synchronises the device and returns in
+ * ms[0..4] the summed durations of {xxh64, parse, tables, chains, pack} over the *ncalls encode calls since. */
+B2C_API int b2c_profile_enable(b2c_ctx *ctx, int on);
+B2C_API int b2c_profile_read(b2c_ctx *ctx, double *ms, uint32_t *ncalls);
 
 /* Encoder.MaxEncodedSize for one chunk of n bytes (zstd/encoder.go:843-873) */
 B2C_API size_t b2c_zstd_bound(size_t n, int level);
@@ -107,6 +117,24 @@ B2C_API int b2c_zstd_encode_device_debug(b2c_ctx *ctx, int flags, const void *d_
 B2C_API int b2c_zstd_encode_device_timed(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride,
                                          uint32_t size_all, void *d_dst, size_t dst_stride, int64_t *d_out_sizes,
                                          uint32_t nchunks, unsigned long long *d_cycles, void *stream);
+
+/*
+ * zstd decode (zstd.Decoder.DecodeAll, zstd/decoder.go:319; per-block work of frameDec.runDecoder,
+ * zstd/framedec.go:330).  Input i is a complete zstd stream (one or more frames, skippable frames allowed,
+ * no dictionary) of d_src_sizes[i] bytes at d_src + (d_src_offsets ? d_src_offsets[i] : i*src_stride); its
+ * content is written to d_dst + (d_dst_offsets ? d_dst_offsets[i] : i*dst_stride), at most dst_cap bytes.
+ * d_out_sizes[i] = decoded bytes, or a negative error (B2C_ERR_CORRUPT, B2C_ERR_DST_SMALL, ...; checksum,
+ * window and frame-size violations are reported as the reference reports them, see b2c_strerror).
+ * One warp decodes one input: throughput comes from batching many inputs.  Asynchronous.
+ */
+B2C_API int b2c_zstd_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, const uint64_t *d_src_offsets,
+                                   const uint32_t *d_src_sizes, void *d_dst, size_t dst_stride,
+                                   const uint64_t *d_dst_offsets, uint32_t dst_cap, int64_t *d_out_sizes,
+                                   uint32_t nchunks, void *stream);
+
+/* Host-buffer batch decode (the call a cgo shim makes for a batch of DecodeAll calls).  Synchronous. */
+B2C_API int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
+                                   const size_t *dst_caps, int64_t *sizes_out, size_t n);
 
 #ifdef __cplusplus
 }

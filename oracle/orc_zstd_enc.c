@@ -795,6 +795,32 @@ ORC_API int64_t orc_zstd_encode_all_ctx(orc_zstd_cctx *cc, const uint8_t *src, s
     return encode_all_impl(level == 1 ? cc : NULL, src, n, level, crc, dst, cap);
 }
 
+/* Benchmark helper (bench.py cpu_baseline / --impl reference): one EncodeAll per `chunk` bytes of src on a
+ * pooled encoder, repeated over the sample until `seconds` of wall time have passed (checked once per pass).
+ * Returns encoded bytes of the last pass; *in_bytes receives the total input bytes encoded. */
+#include <time.h>
+ORC_API int64_t orc_zstd_bench_chunks(orc_zstd_cctx *cc, const uint8_t *src, size_t chunk, size_t nchunks, int level,
+                                      int crc, uint8_t *dst, size_t cap, double seconds, uint64_t *in_bytes) {
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    uint64_t done = 0;
+    int64_t outb = 0;
+    for (;;) {
+        outb = 0;
+        for (size_t i = 0; i < nchunks; i++) {
+            int64_t r = orc_zstd_encode_all_ctx(cc, src + i * chunk, chunk, level, crc, dst, cap);
+            if (r < 0) return r;
+            outb += r;
+        }
+        done += (uint64_t)chunk * nchunks;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        double el = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+        if (el >= seconds) break;
+    }
+    if (in_bytes) *in_bytes = done;
+    return outb;
+}
+
 static int64_t encode_all_impl(orc_zstd_cctx *cc, const uint8_t *src, size_t n, int level, int crc, uint8_t *dst, size_t cap) {
     init_predef();
     if (level != 1 && level != 2) return ORC_ERR_UNSUPPORTED;

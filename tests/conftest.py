@@ -27,4 +27,6 @@ def emu_lib():
     c = ctypes
     E.emu_zstd_encode.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p,
                                   c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32]
+    E.emu_zstd_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
+                                  c.c_void_p]
     return E

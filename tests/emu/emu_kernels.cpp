@@ -2,6 +2,7 @@
 // SIMT emulator and exposes C entry points for pytest.  TEST INFRASTRUCTURE ONLY (see simt_emu.h).
 #include "simt_emu.h"
 #include "../../compress_b200/csrc/b2c_zstd_enc.cuh"
+#include "../../compress_b200/csrc/b2c_zstd_dec.cuh"
 #include <vector>
 #include <cstdlib>
 
@@ -48,6 +49,23 @@ int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, 
     // K4 pack
     emu::launch(nchunks, PACK_NT, PACK_SMEM_BYTES, [&]() { zstd_pack_chunk(emu::dyn_smem, P, blockIdx.x); });
     free(work);
+    return 0;
+}
+
+// Decode n inputs (input i = src + src_off[i], src_sizes[i] bytes) into dst + dst_off[i] (capacity dst_caps[i]).
+int emu_zstd_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t *src_sizes, uint32_t n, uint8_t *dst,
+                    const uint64_t *dst_off, const uint32_t *dst_caps, int64_t *out_sizes) {
+    uint32_t grid = (n + DEC_WARPS - 1) / DEC_WARPS;
+    if (grid > 2) grid = 2;
+    std::vector<uint8_t> lit((size_t)grid * DEC_WARPS * DEC_LIT_SCRATCH, 0xCD);
+    ZstdDecParams P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = src; P.src_offsets = src_off; P.src_sizes = src_sizes;
+    P.dst_base = dst; P.dst_offsets = dst_off; P.dst_caps = dst_caps;
+    P.out_sizes = out_sizes; P.nchunks = n; P.lit_scratch = lit.data();
+    emu::launch(grid, DEC_WARPS * 32, DEC_SMEM_BYTES, [&]() {
+        zstd_decode_warp(emu::dyn_smem, P, blockIdx.x * DEC_WARPS + (threadIdx.x >> 5), gridDim.x * DEC_WARPS);
+    });
     return 0;
 }
 

@@ -32,3 +32,28 @@ def frame_header_len(n):
     elif single:
         fh += 1
     return fh
+
+
+def emu_decode(E, inputs, caps, desc=0):
+    """Run the emulated decode kernel on a list of compressed byte strings; returns (sizes, outputs)."""
+    E.emu_set_lane_order(desc)
+    n = len(inputs)
+    src_off = np.zeros(n, dtype=np.uint64)
+    dst_off = np.zeros(n, dtype=np.uint64)
+    sizes = np.array([len(b) for b in inputs], dtype=np.uint32)
+    capv = np.array(caps, dtype=np.uint32)
+    so = do = 0
+    for i in range(n):
+        src_off[i] = so
+        dst_off[i] = do
+        so += (len(inputs[i]) + 15) & ~15
+        do += (int(capv[i]) + 15) & ~15
+    src = np.full(so + 64, 0xA5, dtype=np.uint8)
+    for i, b in enumerate(inputs):
+        src[int(src_off[i]):int(src_off[i]) + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    dst = np.zeros(do + 64, dtype=np.uint8)
+    outs = np.zeros(n, dtype=np.int64)
+    E.emu_zstd_decode(src.ctypes.data, src_off.ctypes.data, sizes.ctypes.data, n, dst.ctypes.data, dst_off.ctypes.data,
+                      capv.ctypes.data, outs.ctypes.data)
+    res = [bytes(dst[int(dst_off[i]):int(dst_off[i]) + max(int(outs[i]), 0)]) for i in range(n)]
+    return outs, res

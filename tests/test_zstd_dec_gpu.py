@@ -1,0 +1,113 @@
+"""GPU parity tests for the zstd decoder (one warp per stream), through the C ABI (libb200comp.so).
+Golden vectors are the reference's own (zstd/testdata/*.zip, committed under tests/golden/)."""
+import os
+import zipfile
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dec():
+    from compress_b200 import zstd
+    d = zstd.Decoder()
+    yield d
+    d.close()
+
+
+def _pairs(zf):
+    names = set(zf.namelist())
+    for nm in sorted(names):
+        if nm.endswith(".zst") and nm[:-4] in names:
+            yield nm, zf.read(nm), zf.read(nm[:-4])
+
+
+def test_decoder_zip_subset(dec):
+    # zstd/decoder_test.go:201-216 TestNewDecoder
+    items = list(_pairs(zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_decoder_subset.zip"))))
+    outs, codes = dec.decode_chunks([c for _, c, _ in items], [len(w) + 64 for _, _, w in items])
+    for (nm, _, want), got, code in zip(items, outs, codes):
+        assert code == len(want) and got == want, (nm, code)
+
+
+def test_good_and_bad_zip(dec, oracle_lib):
+    # zstd/decoder_test.go:393 TestNewDecoderGood, :409 TestNewDecoderBad; the oracle gives the expected bytes
+    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_good.zip"))
+    comps = [zf.read(nm) for nm in zf.namelist() if nm.endswith(".zst")]
+    wants = []
+    for c in comps:
+        r, got = H.oracle_decode(c, 64 << 20)
+        assert r >= 0
+        wants.append(got)
+    outs, codes = dec.decode_chunks(comps, [len(w) + 64 for w in wants])
+    for want, got, code in zip(wants, outs, codes):
+        assert code == len(want) and got == want
+    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_bad.zip"))
+    bad = [zf.read(nm) for nm in zf.namelist() if nm.endswith(".zst")]
+    assert len(bad) == 32
+    outs, codes = dec.decode_chunks(bad, [4 << 20] * len(bad))
+    assert all(c < 0 for c in codes), codes
+    # same error class as the oracle (which restates the reference's checks)
+    for c, code in zip(bad, codes):
+        ro, _ = H.oracle_decode(c, 4 << 20)
+        assert ro == code, (ro, code)
+
+
+def test_decode_oracle_frames(dec, oracle_lib):
+    rng = np.random.default_rng(7)
+    srcs = [b"", b"a", b"abc" * 7, bytes(1000), bytes(rng.integers(0, 256, 3000, dtype=np.uint8)),
+            H.golden("twain.txt"), H.golden("html.txt"), H.golden("e.txt"), H.synth_text(1 << 20),
+            bytes(rng.integers(0, 4, 300000, dtype=np.uint8))]
+    enc = lambda b: H.oracle_encode(b)[1]
+    comps = [enc(s) for s in srcs]
+    srcs.append(srcs[5][:5000] + srcs[6][:5000])
+    comps.append(enc(srcs[5][:5000]) + b"\x50\x2a\x4d\x18\x03\x00\x00\x00xyz" + enc(srcs[6][:5000]))
+    outs, codes = dec.decode_chunks(comps, [len(s) + 16 for s in srcs])
+    for i, (s, got, code) in enumerate(zip(srcs, outs, codes)):
+        assert code == len(s) and got == s, (i, code)
+    # DecodeAll mirror + error values
+    from compress_b200 import zstd
+    assert dec.DecodeAll(comps[5]) == srcs[5]
+    with pytest.raises(zstd.ZstdError) as ei:
+        dec.DecodeAll(comps[5][:-1] + bytes([comps[5][-1] ^ 1]))
+    assert ei.value.code == zstd.ErrCRCMismatch
+    with pytest.raises(zstd.ZstdError) as ei:
+        dec.DecodeAll(b"\x00\x01\x02\x03\x04\x05")
+    assert ei.value.code == zstd.ErrMagicMismatch
+    with pytest.raises(zstd.ZstdError):
+        dec.DecodeAll(comps[5][:1000])
+    with pytest.raises(zstd.ZstdError) as ei:
+        dec.DecodeAll(comps[5], size_hint=1000)
+    assert ei.value.code == zstd.ErrDecoderSizeExceeded
+
+
+def test_roundtrip_device_256mib(dec):
+    # encode -> decode on the device, 4096 chunks of 64 KiB of the bench workload + mixed corpora
+    from compress_b200 import zstd
+    e = zstd.Encoder(max_chunks=64)
+    n = 4096
+    src = H.synth_text_torch(n * 65536, "cuda")
+    tw = np.frombuffer(H.golden("twain.txt")[:5 * 65536], dtype=np.uint8)
+    src[:tw.size] = torch.from_numpy(tw.copy()).cuda()
+    src[10 * 65536:11 * 65536] = 0
+    src[11 * 65536:12 * 65536] = torch.randint(0, 256, (65536,), dtype=torch.uint8, device="cuda")
+    frames, sizes = e.encode_device(src)
+    torch.cuda.synchronize()
+    assert int(sizes.min()) > 0
+    out, osz = dec.decode_device(frames, sizes.to(torch.int32), src_stride=frames.stride(0), dst_cap=65536)
+    torch.cuda.synchronize()
+    assert bool((osz == 65536).all()), osz[osz != 65536][:10]
+    assert torch.equal(out.view(-1), src)
+    # too small destination -> every stream reports an error, nothing is written past the capacity
+    out2 = torch.full((n, 1024 + 64), 0x5A, dtype=torch.uint8, device="cuda")
+    _, osz2 = dec.decode_device(frames, sizes.to(torch.int32), src_stride=frames.stride(0), dst=out2, dst_cap=1024,
+                                dst_stride=1024 + 64)
+    torch.cuda.synchronize()
+    assert bool((osz2 < 0).all())
+    assert bool((out2[:, 1024:] == 0x5A).all())
+    e.close()
