@@ -123,7 +123,7 @@ def main():
               "parallelism": "chunks sharded over %d GPU(s), no collective" % world}
 
     import helpers as H
-    nthreads = os.cpu_count() or 1
+    nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
     if args.impl == "reference":
         if rank != 0:
@@ -190,6 +190,24 @@ def main():
     assert (outs_h > 0).all(), "encode error"
     out_bytes = int(outs_h.sum())
 
+    # ---- secondary: decode of the frames just produced (SURVEY 8d "decode GB/s (output bytes)"), device-resident
+    dec = zstd.Decoder(device=local_rank)
+    dsz = outs.to(torch.int32)
+    dout = torch.empty((n, CHUNK), dtype=torch.uint8, device=dev)
+    dres = torch.empty((n,), dtype=torch.int64, device=dev)
+    for _ in range(2):
+        dec.decode_device(dst, dsz, src_stride=zstd.SLOT, dst=dout, dst_cap=CHUNK, out_sizes=dres)
+    torch.cuda.synchronize()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(3):
+        dec.decode_device(dst, dsz, src_stride=zstd.SLOT, dst=dout, dst_cap=CHUNK, out_sizes=dres)
+    d1.record()
+    torch.cuda.synchronize()
+    dec_ms = d0.elapsed_time(d1) / 3
+    assert bool((dres == CHUNK).all()) and torch.equal(dout.view(-1), src), "decode mismatch"
+    del dout
+
     # ---- end to end through the host-buffer C-ABI call (pinned host in/out)
     ne = min(args.e2e_chunks, n)
     host_in = src[: ne * CHUNK].cpu().pin_memory()
@@ -241,6 +259,9 @@ def main():
                              "pipeline_frac": (in_bytes + out_bytes) / step_s / 1e9 / peak},
                 "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": ne * CHUNK, "d2h_bytes_per_step": int(e_total),
                         "api": "b2c_zstd_encode_packed (pinned host in/out, double-buffered)", "chunks_per_step": ne}}
+        line["decode"] = {"value": in_bytes / (dec_ms / 1e3) / 1e9, "unit": "GB/s (output bytes, this rank)", "ms": dec_ms,
+                          "roofline_frac": (in_bytes + out_bytes) / (dec_ms / 1e3) / 1e9 / peak,
+                          "note": "b2c_zstd_decode_kernel on the frames produced above; verified equal to the input"}
         if not args.no_cpu_baseline and world == 1:
             sample = H.synth_chunks("text", 2048, seed=77)
             gbs, dt, ratio = cpu_reference_rate(sample, nthreads, 10.0)

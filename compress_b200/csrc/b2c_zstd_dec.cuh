@@ -422,8 +422,12 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, u
         }
         bool hasCheck = (fhd & 4) != 0;
         if (windowSize > (1ull << 29)) DFAIL(DEC_ERR_WINDOW);
-        if (windowSize == 0 && singleSegment) windowSize = fcs > 1024 ? fcs : 1024;
+        if (windowSize == 0 && singleSegment) {
+            windowSize = fcs > 1024 ? fcs : 1024;
+            if (windowSize > (64ull << 30)) DFAIL(DEC_ERR_SIZE);   // ErrDecoderSizeExceeded (maxDecodedSize default)
+        }
         if (windowSize < 1024) DFAIL(DEC_ERR_WINDOW);
+        if (fcs != ~0ull && fcs > (64ull << 30) - total) DFAIL(DEC_ERR_SIZE);
 
         // history.reset
         bool haveHuff = false;
