@@ -37,7 +37,10 @@ struct b2c_ctx {
     uint64_t *d_offsets2 = nullptr;
     uint32_t *d_src_sizes2 = nullptr, *h_src_sizes2 = nullptr;
     cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t stream3 = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};       // compute of the batch in slot s finished
+    cudaEvent_t ev_in[2] = {nullptr, nullptr};    // H2D of slot s finished
+    cudaEvent_t ev_out[2] = {nullptr, nullptr};   // D2H of slot s finished
     // decoder: per-warp literal scratch, host-path staging (grown on demand)
     uint8_t *d_dec_lit = nullptr; size_t dec_lit_cap = 0;
     uint8_t *d_dec_in = nullptr, *d_dec_out = nullptr; size_t dec_in_cap = 0, dec_out_cap = 0;
@@ -158,8 +161,12 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
         ok = ok && cudaMalloc(&ctx->d_offsets, (max_chunks + 1) * sizeof(uint64_t)) == cudaSuccess;
         ok = ok && cudaMalloc(&ctx->d_src_sizes, max_chunks * sizeof(uint32_t)) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) == cudaSuccess;
+        for (int k = 0; k < 2; k++) {
+            ok = ok && cudaEventCreateWithFlags(&ctx->ev[k], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&ctx->ev_out[k], cudaEventDisableTiming) == cudaSuccess;
+        }
         ok = ok && cudaMallocHost(&ctx->h_sizes2, (max_chunks + 1) * sizeof(int64_t) * 2) == cudaSuccess;
         ok = ok && cudaMallocHost(&ctx->h_src_sizes2, max_chunks * sizeof(uint32_t)) == cudaSuccess;
         ok = ok && cudaMalloc(&ctx->d_in2, max_chunks * (size_t)ENC_MAX_CHUNK) == cudaSuccess;
@@ -183,8 +190,12 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     cudaFree(ctx->d_in2); cudaFree(ctx->d_out2); cudaFree(ctx->d_packed2); cudaFree(ctx->d_sizes2);
     cudaFree(ctx->d_offsets2); cudaFree(ctx->d_src_sizes2); cudaFreeHost(ctx->h_sizes2); cudaFreeHost(ctx->h_src_sizes2);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
-    if (ctx->ev[0]) cudaEventDestroy(ctx->ev[0]);
-    if (ctx->ev[1]) cudaEventDestroy(ctx->ev[1]);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+        if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+        if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
+    }
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -387,11 +398,11 @@ int b2c_zstd_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const
 }
 
 
-// Contiguous host input -> packed host output (concatenated frames), double-buffered so the H2D copy of
-// batch b+1 and the D2H copy of batch b-1 overlap the kernels of batch b.  This is the shape of a large
-// EncodeAll / of a WithConcurrentBlocks job (zstd/enc_jobs.go): the caller gets one valid zstd stream plus
-// the per-chunk frame table.  h_src / h_dst should be pinned (cudaHostRegister / torch pin_memory) for
-// full PCIe rate; pageable memory works but is staged by the driver.
+// Contiguous host input -> packed host output (concatenated frames).  Three streams (H2D, kernels, D2H) and two
+// buffer slots: the H2D copy of batch b+1 and the D2H copy of batch b-1 overlap the kernels of batch b.  This is the
+// shape of a large EncodeAll / of a WithConcurrentBlocks job (zstd/enc_jobs.go): the caller gets one valid zstd
+// stream plus the per-chunk frame table.  h_src / h_dst should be pinned (cudaHostRegister / torch pin_memory)
+// for full PCIe rate; pageable memory works but is staged by the driver.
 int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src, size_t src_bytes,
                            uint32_t chunk_size, void *h_dst, size_t dst_cap, int64_t *sizes_out,
                            uint64_t *offsets_out, size_t *total_out) {
@@ -402,22 +413,26 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
     const size_t nchunks = src_bytes == 0 ? 1 : (src_bytes + chunk_size - 1) / chunk_size;
     const size_t B = ctx->max_chunks;
     const size_t nb = (nchunks + B - 1) / B;
-    struct Slot { cudaStream_t st; uint8_t *d_in, *d_out, *d_packed; int64_t *d_sizes, *h_sizes; uint64_t *d_off;
+    cudaStream_t st_c = ctx->stream, st_in = ctx->stream2, st_out = ctx->stream3;
+    struct Slot { uint8_t *d_in, *d_out, *d_packed; int64_t *d_sizes, *h_sizes; uint64_t *d_off;
                   uint32_t *d_ss, *h_ss; } slot[2] = {
-        {ctx->stream, ctx->d_in, ctx->d_out, ctx->d_packed, ctx->d_sizes, ctx->h_sizes, ctx->d_offsets, ctx->d_src_sizes, ctx->h_src_sizes},
-        {ctx->stream2, ctx->d_in2, ctx->d_out2, ctx->d_packed2, ctx->d_sizes2, ctx->h_sizes2, ctx->d_offsets2, ctx->d_src_sizes2, ctx->h_src_sizes2}};
+        {ctx->d_in, ctx->d_out, ctx->d_packed, ctx->d_sizes, ctx->h_sizes, ctx->d_offsets, ctx->d_src_sizes, ctx->h_src_sizes},
+        {ctx->d_in2, ctx->d_out2, ctx->d_packed2, ctx->d_sizes2, ctx->h_sizes2, ctx->d_offsets2, ctx->d_src_sizes2, ctx->h_src_sizes2}};
     uint64_t out_pos = 0;
     int rc = B2C_OK;
+    // batch b's kernels are done: place its frames in the output stream and start the D2H copy
     auto finish = [&](size_t b) -> int {
-        Slot &S = slot[b & 1];
+        const int sl = (int)(b & 1);
+        Slot &S = slot[sl];
         size_t c0 = b * B, m = (nchunks - c0 < B) ? nchunks - c0 : B;
-        if (cudaEventSynchronize(ctx->ev[b & 1]) != cudaSuccess) return B2C_ERR_CUDA;
+        if (cudaEventSynchronize(ctx->ev[sl]) != cudaSuccess) return B2C_ERR_CUDA;
         const int64_t *h_sz = S.h_sizes;
         const uint64_t *h_off = reinterpret_cast<const uint64_t *>(S.h_sizes + m);
         uint64_t total = h_off[m];
         if (out_pos + total > dst_cap) return B2C_ERR_DST_SMALL;
-        if (cudaMemcpyAsync((uint8_t *)h_dst + out_pos, S.d_packed, total, cudaMemcpyDeviceToHost, S.st) != cudaSuccess)
+        if (cudaMemcpyAsync((uint8_t *)h_dst + out_pos, S.d_packed, total, cudaMemcpyDeviceToHost, st_out) != cudaSuccess)
             return B2C_ERR_CUDA;
+        if (cudaEventRecord(ctx->ev_out[sl], st_out) != cudaSuccess) return B2C_ERR_CUDA;
         for (size_t i = 0; i < m; i++) {
             sizes_out[c0 + i] = h_sz[i];
             if (offsets_out) offsets_out[c0 + i] = out_pos + h_off[i];
@@ -427,39 +442,45 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
         return B2C_OK;
     };
     for (size_t b = 0; b < nb; b++) {
-        Slot &S = slot[b & 1];
+        const int sl = (int)(b & 1);
+        Slot &S = slot[sl];
         size_t c0 = b * B, m = (nchunks - c0 < B) ? nchunks - c0 : B;
         size_t off = c0 * (size_t)chunk_size;
         size_t bytes = (off + m * (size_t)chunk_size <= src_bytes) ? m * (size_t)chunk_size : src_bytes - off;
-        // slot reuse: batch b-2's D2H (enqueued in finish(b-2)) is on the same stream, so stream order protects it
-        if (bytes) CK(cudaMemcpyAsync(S.d_in, (const uint8_t *)h_src + off, bytes, cudaMemcpyHostToDevice, S.st));
+        // H2D: the input slot is free once the kernels of batch b-2 have run
+        if (b >= 2) CK(cudaStreamWaitEvent(st_in, ctx->ev[sl], 0));
+        if (bytes) CK(cudaMemcpyAsync(S.d_in, (const uint8_t *)h_src + off, bytes, cudaMemcpyHostToDevice, st_in));
         const uint32_t *d_ss = nullptr;
         if (bytes != m * (size_t)chunk_size) {  // ragged last chunk (or empty input): explicit sizes
             for (size_t i = 0; i < m; i++) {
                 size_t o = i * (size_t)chunk_size;
                 S.h_ss[i] = (uint32_t)(o >= bytes ? 0 : (bytes - o < chunk_size ? bytes - o : chunk_size));
             }
-            CK(cudaMemcpyAsync(S.d_ss, S.h_ss, m * sizeof(uint32_t), cudaMemcpyHostToDevice, S.st));
+            CK(cudaMemcpyAsync(S.d_ss, S.h_ss, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st_in));
             d_ss = S.d_ss;
         }
+        CK(cudaEventRecord(ctx->ev_in[sl], st_in));
+        // kernels: need the input; the packed-output slot is free once batch b-2's D2H copy is done
+        CK(cudaStreamWaitEvent(st_c, ctx->ev_in[sl], 0));
+        if (b >= 2) CK(cudaStreamWaitEvent(st_c, ctx->ev_out[sl], 0));
         int r = launch_encode(ctx, level, flags, S.d_in, chunk_size, d_ss, chunk_size, S.d_out, kSlot, S.d_sizes,
-                              (uint32_t)m, nullptr, nullptr, nullptr, 0, S.st, nullptr, (int)(b & 1));
+                              (uint32_t)m, nullptr, nullptr, nullptr, 0, st_c, nullptr, sl);
         if (r) return r;
-        b2c_scan_sizes_kernel<<<1, 1024, 0, S.st>>>(S.d_sizes, S.d_off, (uint32_t)m);
-        b2c_pack_kernel<<<ctx->sm_count * 4, 256, 0, S.st>>>(S.d_out, kSlot, S.d_sizes, S.d_off, S.d_packed, (uint32_t)m);
+        b2c_scan_sizes_kernel<<<1, 1024, 0, st_c>>>(S.d_sizes, S.d_off, (uint32_t)m);
+        b2c_pack_kernel<<<ctx->sm_count * 4, 256, 0, st_c>>>(S.d_out, kSlot, S.d_sizes, S.d_off, S.d_packed, (uint32_t)m);
         ctx->launches += 2;
-        CK(cudaMemcpyAsync(S.h_sizes, S.d_sizes, m * sizeof(int64_t), cudaMemcpyDeviceToHost, S.st));
-        CK(cudaMemcpyAsync(S.h_sizes + m, S.d_off, (m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, S.st));
-        CK(cudaEventRecord(ctx->ev[b & 1], S.st));
+        CK(cudaMemcpyAsync(S.h_sizes, S.d_sizes, m * sizeof(int64_t), cudaMemcpyDeviceToHost, st_c));
+        CK(cudaMemcpyAsync(S.h_sizes + m, S.d_off, (m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st_c));
+        CK(cudaEventRecord(ctx->ev[sl], st_c));
         if (b >= 1) { int r2 = finish(b - 1); if (r2) return r2; }
     }
     { int r2 = finish(nb - 1); if (r2) return r2; }
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream2));
+    CK(cudaStreamSynchronize(st_in));
+    CK(cudaStreamSynchronize(st_c));
+    CK(cudaStreamSynchronize(st_out));
     if (total_out) *total_out = out_pos;
     return rc;
 }
-
 
 // ---- decoder ------------------------------------------------------------------------------------
 static int grow(b2c_ctx *ctx, uint8_t **p, size_t *cap, size_t need) {

@@ -59,33 +59,49 @@ struct ZstdDecParams {
     uint8_t *lit_scratch;                                                      // [gridDim.x * DEC_WARPS][DEC_LIT_SCRATCH]
 };
 
-// ---- backward bit reader over global memory (zstd/bitreader.go semantics: exact consumption required)
+// ---- backward bit reader over global memory (zstd/bitreader.go semantics: exact consumption required).
+// The stream is a little-endian integer; `total` payload bits sit below the end mark; reads take bits from the top
+// down; bits below bit 0 read as zero (pos > total is the over-read condition the callers test).
+// A 64-bit window of the stream is cached in registers and refilled (two aligned 8-byte loads) every >= 57 bits.
 struct BrB {
     const uint8_t *in; uint32_t len; int64_t total; int64_t pos;
+    uint64_t cbuf; int64_t cbase;    // cbuf = stream bits [cbase, cbase + 64)
     B2C_DEV int init(const uint8_t *p, uint32_t n) {
-        in = p; len = n; total = 0; pos = 0;
+        in = p; len = n; total = 0; pos = 0; cbuf = 0; cbase = (int64_t)1 << 40;
         if (n < 1) return -1;
         uint8_t v = p[n - 1];
         if (v == 0) return -1;
         total = (int64_t)8 * (n - 1) + (int64_t)highbit32(v);
         return 0;
     }
-    // peek n <= 32 bits at the current position; bits before the start of the buffer read as zero
-    B2C_DEV uint32_t peek(uint32_t n) const {
-        if (n == 0) return 0;
-        int64_t lo = total - pos - (int64_t)n;
-        int64_t start = lo < 0 ? 0 : lo;
-        int64_t end = lo + (int64_t)n;
-        if (end <= 0) return 0;
-        uint32_t byte0 = (uint32_t)(start >> 3), sh = (uint32_t)(start & 7);
-        uint64_t acc = 0;
+    B2C_DEV void refill(int64_t top) {
+        // window = the 8 bytes ending at the byte that holds bit top-1
+        int64_t byteTop = (top + 7) >> 3;          // arithmetic shift: floor for negative values too
+        int64_t cbyte = byteTop - 8;
+        cbase = cbyte * 8;
+        if (cbyte >= 0 && cbyte + 16 <= (int64_t)len) {
+            const uint8_t *p = in + cbyte;
+            uintptr_t a = reinterpret_cast<uintptr_t>(p);
+            const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+            uint32_t sh = (uint32_t)(a & 7) * 8;
+            uint64_t lo = w[0];
+            cbuf = sh ? ((lo >> sh) | (w[1] << (64 - sh))) : lo;
+        } else {
+            uint64_t acc = 0;
 #pragma unroll
-        for (uint32_t i = 0; i < 6; i++) { uint32_t bi = byte0 + i; if (bi < len) acc |= (uint64_t)in[bi] << (8 * i); }
-        acc >>= sh;
-        uint32_t got = (uint32_t)(end - start);
-        uint64_t v = acc & ((1ull << got) - 1);
-        if (lo < 0) v <<= (uint32_t)(-lo);
-        return (uint32_t)v;
+            for (int i = 0; i < 8; i++) {
+                int64_t bi = cbyte + i;
+                if (bi >= 0 && bi < (int64_t)len) acc |= (uint64_t)in[bi] << (8 * i);
+            }
+            cbuf = acc;
+        }
+    }
+    // peek n <= 32 bits at the current position
+    B2C_DEV uint32_t peek(uint32_t n) {
+        if (n == 0) return 0;
+        int64_t top = total - pos, lo = top - (int64_t)n;
+        if (lo < cbase || top > cbase + 64) refill(top);
+        return (uint32_t)((cbuf >> (uint32_t)(lo - cbase)) & ((1ull << n) - 1));
     }
     B2C_DEV uint32_t read(uint32_t n) { uint32_t v = peek(n); pos += n; return v; }
     B2C_DEV bool finished() const { return pos >= total; }
@@ -665,12 +681,20 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, u
                 uint64_t v = (lane == 0) ? P1 + P2 : (lane == 1) ? P2 : (lane == 2) ? 0ull : (0ull - P1);
                 uint64_t stripes = o / 32;
                 if (lane < 4) {
-                    for (uint64_t i = 0; i < stripes; i++) {
-                        const uint8_t *q = out + 32 * i + 8 * lane;
-                        uint64_t inw = 0;
+                    if ((reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+                        const uint64_t *q8 = reinterpret_cast<const uint64_t *>(out) + lane;
+                        for (uint64_t i = 0; i < stripes; i++) {
+                            uint64_t inw = q8[4 * i];
+                            v += inw * P2; v = (v << 31) | (v >> 33); v *= P1;
+                        }
+                    } else {
+                        for (uint64_t i = 0; i < stripes; i++) {
+                            const uint8_t *q = out + 32 * i + 8 * lane;
+                            uint64_t inw = 0;
 #pragma unroll
-                        for (int b = 0; b < 8; b++) inw |= (uint64_t)q[b] << (8 * b);
-                        v += inw * P2; v = (v << 31) | (v >> 33); v *= P1;
+                            for (int b = 0; b < 8; b++) inw |= (uint64_t)q[b] << (8 * b);
+                            v += inw * P2; v = (v << 31) | (v >> 33); v *= P1;
+                        }
                     }
                 }
                 p = stripes * 32;

@@ -163,7 +163,6 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     uint16_t *Lall = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_L);
     ParseShared *sh = reinterpret_cast<ParseShared *>(smem + ENC_SMEM_SH);
     uint8_t *lit = smem + ENC_SMEM_E;                                      // after the parse
-    uint16_t *lhist = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_L);     // [4][256][32] u16 lane-column counters
     uint32_t *shist = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_SRC);   // [32][192] seq-code histograms (src is dead)
     ChunkWork *W = P.work + chunk;
 
@@ -300,26 +299,15 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                     if (lose) L[hL] = (uint16_t)rel;
                     __syncwarp();
                 }
-                // candidates: recent-in-sub-range first, else earliest-in-chunk; 4 bytes verify, 4 more extend
-                uint32_t q = 0, mlen = 0, bk = 0;
-                if (valid) {
-                    bool ok = false;
-                    if (candL != 0xffff) { q = b0 + candL; ok = ld32u(src, q) == c_lo; }
-                    if (!ok && candE < p) { q = candE; ok = ld32u(src, q) == c_lo; }
-                    if (ok) {
-                        uint32_t x = ld32u(src, q + 4) ^ c_hi;
-                        uint32_t eq = 4 + (x ? (uint32_t)(__ffs((int)x) - 1) >> 3 : 4u);
-                        uint32_t room = e0 - p;             // matches never cross the sub-range end
-                        mlen = eq < room ? eq : room;
-                        if (mlen < 4) mlen = 0;
-                        else if (q >= 4) {
-                            // bytes equal just before the match (at most 4, never before position 0)
-                            uint32_t xb = ld32u(src, p - 4) ^ ld32u(src, q - 4);
-                            bk = xb ? (uint32_t)__clz((int)xb) >> 3 : 4u;
-                        }
-                    }
+                // candidates: recent-in-sub-range first, else earliest-in-chunk; 4 bytes verify here, the length of
+                // a *selected* match is measured cooperatively below (one byte per lane)
+                uint32_t q = 0;
+                bool has = false;
+                if (valid && e0 - p >= 4) {              // matches never cross the sub-range end
+                    if (candL != 0xffff) { q = b0 + candL; has = ld32u(src, q) == c_lo; }
+                    if (!has && candE < p) { q = candE; has = ld32u(src, q) == c_lo; }
                 }
-                unsigned mask = __ballot_sync(FULLMASK, mlen != 0);
+                unsigned mask = __ballot_sync(FULLMASK, has);
                 uint32_t next = cur + 32;
                 uint32_t from = 0;
                 bool sel = false;
@@ -330,11 +318,22 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                     const int f = __ffs((int)m) - 1;
                     const uint32_t pf = cur + (uint32_t)f;
                     const uint32_t qf = __shfl_sync(FULLMASK, q, f);
-                    uint32_t len = __shfl_sync(FULLMASK, mlen, f);
-                    uint32_t back = __shfl_sync(FULLMASK, bk, f);
-                    if (len == 8 && pf + 8 < e0) len = 8 + warp_match_len(src, pf + 8, qf + 8, e0);
+                    // lanes 0..27: byte 4+lane after the verified prefix; lanes 28..31: byte 1+(lane-28) before the match
+                    // (at most 4 back, never before the pending literals or position 0)
+                    bool ne;
+                    if (lane < 28) {
+                        const uint32_t a = pf + 4 + lane;
+                        ne = (a >= e0) || (src[a] != src[qf + 4 + lane]);
+                    } else {
+                        const uint32_t b = lane - 28;
+                        ne = (qf < 4) || (b >= pf - nextEmit) || (src[pf - 1 - b] != src[qf - 1 - b]);
+                    }
+                    const unsigned neq = __ballot_sync(FULLMASK, ne);
+                    const uint32_t fwd = (uint32_t)__ffs((int)((neq & 0x0fffffffu) | 0x10000000u)) - 1;
+                    const uint32_t back = (uint32_t)__ffs((int)((neq >> 28) | 16u)) - 1;
+                    uint32_t len = 4 + fwd;
+                    if (fwd == 28 && pf + 32 < e0) len = 32 + warp_match_len(src, pf + 32, qf + 32, e0);
                     const uint32_t off = pf - qf;
-                    if (back > pf - nextEmit) back = pf - nextEmit;
                     const uint32_t s = pf - back;
                     len += back;
                     const bool isrep = (ownNew >= 1) && (off == rep0) && (s > nextEmit);
@@ -443,20 +442,34 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
 
     // ---------------------------------------------------------------- P5: histograms (src is dead from here on)
     if (kind == 0) {
+        // per-warp private bins, lanes holding equal symbols merged with match.any (no atomics, no RMW races):
+        // shist[w][192] sequence-code bins (LL, OF, ML), lhist32[w][256] literal bins
+        uint32_t *lhist32 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L);
         for (uint32_t i = tid; i < 32 * 192; i += ENC_NT) shist[i] = 0;
-        for (uint32_t i = tid; i < 4 * 256 * 32 / 2; i += ENC_NT) reinterpret_cast<uint32_t *>(lhist)[i] = 0;
+        for (uint32_t i = tid; i < 32 * 256; i += ENC_NT) lhist32[i] = 0;
         __syncthreads();
-        if (w < 4) {
-            // literal histogram: warps 0..3, private u16 counter per (symbol, lane): conflict-free, no atomics
-            uint16_t *hcol = lhist + w * 256 * 32;
-            uint32_t per = (nlit + 3) / 4;
-            uint32_t a = w * per, b = a + per;
-            if (b > nlit) b = nlit;
-            for (uint32_t i = a + lane; i < b; i += 32) hcol[(uint32_t)lit[i] * 32 + lane]++;
-        } else {
-            // sequence code histograms: warps 4..31, per-warp private bins merged with match.any
+        {
+            uint32_t *hl = lhist32 + w * 256;
+            const uint32_t nl4 = (nlit + 3) / 4;            // literal words; bytes past nlit are masked below
+            const uint32_t *lit32 = reinterpret_cast<const uint32_t *>(lit);
+            for (uint32_t base = w * 32; base < nl4; base += ENC_NW * 32) {
+                uint32_t i = base + lane;
+                bool valid = i < nl4;
+                uint32_t v = valid ? lit32[i] : 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    bool ok = valid && (4 * i + k < nlit);
+                    unsigned act = __ballot_sync(FULLMASK, ok);
+                    if (ok) {
+                        unsigned sym = (v >> (8 * k)) & 0xff;
+                        unsigned peers = __match_any_sync(act, sym);
+                        if (lane == (unsigned)(__ffs((int)peers) - 1)) hl[sym] += (uint32_t)__popc(peers);
+                    }
+                    __syncwarp();
+                }
+            }
             uint32_t *hw3 = shist + w * 192;
-            for (uint32_t base = (w - 4) * 32; base < nseq; base += (ENC_NW - 4) * 32) {
+            for (uint32_t base = w * 32; base < nseq; base += ENC_NW * 32) {
                 uint32_t i = base + lane;
                 bool valid = i < nseq;
                 unsigned act = __ballot_sync(FULLMASK, valid);
@@ -474,17 +487,13 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         __syncthreads();
         if (tid < 256) {
             uint32_t c = 0;
-            for (int k = 0; k < 4; k++) {
-                const uint32_t *row = reinterpret_cast<const uint32_t *>(lhist + (k * 256 + tid) * 32);
-#pragma unroll
-                for (int j = 0; j < 16; j++) { uint32_t v = row[j]; c += (v & 0xffff) + (v >> 16); }
-            }
+            for (int k = 0; k < ENC_NW; k++) c += lhist32[k * 256 + tid];
             W->litHist[tid] = c;
         } else if (tid < 256 + 192) {
             uint32_t s = tid - 256, c = 0;
-            for (int k = 4; k < ENC_NW; k++) c += shist[k * 192 + s];
+            for (int k = 0; k < ENC_NW; k++) c += shist[k * 192 + s];
             W->seqHist[s / 64][s % 64] = c;
-            shist[s] = c;  // row 0 (unused by the counting warps) now holds the totals
+            shist[s] = c;  // thread s only ever touches column s: row 0 now holds the totals
         }
         __syncthreads();
         if (tid < 3) {
