@@ -103,6 +103,40 @@ B2C_DEV uint32_t group_scan_excl(uint32_t v, uint32_t *ws, int bar_id, int nthre
     return base + incl - v;
 }
 
+B2C_DEV uint32_t warp_scan_incl_max(uint32_t v) {
+    unsigned lane = lane_id();
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(FULLMASK, v, d);
+        if (lane >= (unsigned)d && t > v) v = t;
+    }
+    return v;
+}
+// Exclusive prefix maximum (identity 0) with the same calling convention as group_scan_excl; *total = overall maximum.
+B2C_DEV uint32_t group_scan_excl_max(uint32_t v, uint32_t *ws, int bar_id, int nthreads, unsigned tid_in_group,
+                                     uint32_t *total) {
+    unsigned lane = tid_in_group & 31, w = tid_in_group >> 5;
+    uint32_t incl = warp_scan_incl_max(v);
+    uint32_t excl = __shfl_up_sync(FULLMASK, incl, 1);
+    if (lane == 0) excl = 0;
+    group_sync(bar_id, nthreads);      // ws may still be read by a previous scan
+    if (lane == 31) ws[w] = incl;
+    group_sync(bar_id, nthreads);
+    if (w == 0) {
+        int nw = nthreads >> 5;
+        uint32_t x = (lane < (unsigned)nw) ? ws[lane] : 0;
+        uint32_t xi = warp_scan_incl_max(x);
+        uint32_t xe = __shfl_up_sync(FULLMASK, xi, 1);
+        if (lane == 0) xe = 0;
+        ws[lane] = xe;  // exclusive warp bases
+        if (lane == 31) ws[32] = xi;
+    }
+    group_sync(bar_id, nthreads);
+    uint32_t base = ws[w];
+    *total = ws[32];
+    return base > excl ? base : excl;
+}
+
 // ---- cooperative bit-run writer ----
 // Many threads append disjoint, contiguous bit ranges of one little-endian,
 // LSB-first bitstream held in zero-initialised shared memory (32-bit words).

@@ -37,15 +37,16 @@ namespace b2c {
 constexpr int ENC_NT = 1024;              // K1 threads per CTA
 constexpr int ENC_NW = ENC_NT / 32;       // 32 parsing warps
 constexpr int ENC_EBITS = 15;             // earliest-occurrence table: 32 Ki x u16
-constexpr int ENC_LBITS = 10;             // per-warp recent table: 1 Ki x u16
+constexpr uint32_t ENC_LANE_BYTES = 68;   // bytes parsed by one thread (17 words: lanes start in distinct banks)
+constexpr uint32_t ENC_MAXREC = 17;       // matches a thread can start inside its 68 bytes (min match 4)
+constexpr uint32_t ENC_EXT_CAP = 256;     // per-thread forward extension limit; longer matches are finished by warp 0
 constexpr uint32_t ENC_MAX_CHUNK = 1u << 16;
 constexpr uint32_t ENC_SRC_BYTES = ENC_MAX_CHUNK + 128;   // chunk + zero padding
 constexpr uint32_t ENC_E_BYTES = (1u << ENC_EBITS) * 2;
-constexpr uint32_t ENC_L_BYTES = ENC_NW * (1u << ENC_LBITS) * 2;
-constexpr uint32_t ENC_SEGCAP = 528;      // max records per parse warp: 2048 / 4 + slack
+constexpr uint32_t ENC_L_BYTES = 48 * 1024;   // per-thread merge state, later the per-warp histograms
 constexpr uint32_t ENC_MAXSEQ = 16384 + 64;
 constexpr int PACK_NT = 512;              // K4 threads per CTA
-constexpr uint32_t ENC_SCRATCH_BYTES = ENC_NW * ENC_SEGCAP * 8;  // per-CTA parse records
+constexpr uint32_t ENC_SCRATCH_BYTES = ENC_MAXREC * ENC_NT * 8;  // per-CTA match records [k][thread]
 
 enum { ENC_FLAG_CRC = 1, ENC_FLAG_FRAME = 2 };
 
@@ -139,13 +140,27 @@ B2C_DEV uint32_t warp_match_len(const uint8_t *src, uint32_t a, uint32_t b, uint
     }
 }
 
+// Ballot histogram step: every lane contributes one symbol (NBITS wide); lane l counts the symbols whose low 5 bits
+// equal l, split by the remaining high bits: cnt[k] += #symbols == (k << 5 | l).
+template <int NBITS>
+B2C_DEV void warp_hist_acc(uint32_t sym, bool valid, uint32_t *cnt, unsigned lane) {
+    unsigned b[NBITS];
+#pragma unroll
+    for (int j = 0; j < NBITS; j++) b[j] = __ballot_sync(FULLMASK, valid && ((sym >> j) & 1));
+    unsigned m = __ballot_sync(FULLMASK, valid);
+#pragma unroll
+    for (int j = 0; j < 5; j++) m &= ((lane >> j) & 1) ? b[j] : ~b[j];
+#pragma unroll
+    for (int k = 0; k < (1 << (NBITS - 5)); k++) {
+        unsigned mk = m;
+#pragma unroll
+        for (int j = 5; j < NBITS; j++) mk &= ((k >> (j - 5)) & 1) ? b[j] : ~b[j];
+        cnt[k] += (uint32_t)__popc(mk);
+    }
+}
+
 struct ParseShared {
-    uint32_t cnt[32];       // records per parse warp
-    uint32_t tail[32];      // trailing literal bytes of each sub-range
-    uint32_t sumLL[32];     // literal bytes inside each sub-range (incl. tail)
-    uint32_t seqBase[32];
-    uint32_t litBase[32];
-    uint32_t carry[32];     // literal bytes carried into the warp's first sequence
+    uint32_t ws[40];        // block scan scratch
     uint32_t nseq, nlit, kind, rleLen;
     uint64_t mbar;
 };
@@ -160,7 +175,6 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     uint8_t *src = smem + ENC_SMEM_SRC;
     uint16_t *E = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_E);
-    uint16_t *Lall = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_L);
     ParseShared *sh = reinterpret_cast<ParseShared *>(smem + ENC_SMEM_SH);
     uint8_t *lit = smem + ENC_SMEM_E;                                      // after the parse
     uint32_t *shist = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_SRC);   // [32][192] seq-code histograms (src is dead)
@@ -205,7 +219,6 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         if (bulk && tid == 0) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh->mbar))); }
 #endif
     }
-    const uint32_t sub = (((n + ENC_NW - 1) / ENC_NW) + 31) & ~31u;  // sub-range size (2048 for a full chunk)
     B2C_PHASE(1);
 
     // ---------------------------------------------------------------- P1: earliest-occurrence table
@@ -267,169 +280,135 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     }
     B2C_PHASE(2);
 
-    // ---------------------------------------------------------------- P2: parse (all 32 warps)
-    {
-        uint16_t *L = Lall + w * (1u << ENC_LBITS);
-        for (uint32_t i = lane; i < (1u << ENC_LBITS) / 2; i += 32) reinterpret_cast<uint32_t *>(L)[i] = 0xffffffffu;
-        __syncwarp();
-        const uint32_t b0 = w * sub;
-        const uint32_t e0 = (b0 + sub < n) ? b0 + sub : n;
-        uint32_t nrec = 0, sumML = 0;
-        uint32_t nextEmit = b0;
-        if (b0 < n) {
-            uint2 *rec = reinterpret_cast<uint2 *>(scratch) + w * ENC_SEGCAP;
-            uint32_t cur = b0, ownNew = 0, rep0 = 0;
-            while (cur < e0) {
-                const uint32_t p = cur + lane;
-                const bool valid = (p < e0) && (p < npos);
-                uint64_t cv = valid ? ld64u(src, p) : 0;
-                const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
-                const uint32_t h32 = enc_hash6(c_lo, c_hi);
-                const uint32_t hL = h32 >> (32 - ENC_LBITS), hE = h32 >> (32 - ENC_EBITS);
-                uint32_t candL = 0xffff, candE = 0xffff;
-                if (valid) { candL = L[hL]; candE = E[hE]; }
-                __syncwarp();
-                // insert the window's positions; the highest position wins a slot (deterministic)
-                const uint32_t rel = p - b0;
-                if (valid) L[hL] = (uint16_t)rel;
-                __syncwarp();
+    // ---------------------------------------------------------------- P2: parse, one thread per 68-byte range
+    // Every thread runs the serial greedy scan of fastEncoder over its own range (probe E at each position, verify 4
+    // bytes, extend forwards/backwards, skip past the match).  Threads never communicate: E is read-only here, so the
+    // result does not depend on scheduling.  A match may run past the end of the thread's range; the merge step (P3)
+    // trims whatever a later thread found inside it.
+    uint2 *rec = reinterpret_cast<uint2 *>(scratch);             // rec[k * ENC_NT + tid]: x = start | len << 16, y = dist
+    uint32_t *keptEndA = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L);   // [1024]
+    uint16_t *lastOffA = reinterpret_cast<uint16_t *>(keptEndA + ENC_NT);   // [1024]
+    uint8_t *cntA = reinterpret_cast<uint8_t *>(lastOffA + ENC_NT);         // [1024]
+    uint8_t *capA = cntA + ENC_NT;                                          // [1024]
+    const uint32_t nlanes = (n + ENC_LANE_BYTES - 1) / ENC_LANE_BYTES;
+    uint32_t cnt = 0, lastE = 0;
+    bool capped = false;
+    if (tid < nlanes) {
+        const uint32_t b = tid * ENC_LANE_BYTES;
+        const uint32_t e = (b + ENC_LANE_BYTES < n) ? b + ENC_LANE_BYTES : n;
+        const uint32_t pend = e < npos ? e : npos;           // probe positions need 8 readable bytes
+        uint32_t p = b, nextEmit = b;
+        while (p < pend) {
+            const uint64_t cv = ld64u(src, p);
+            const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
+            const uint32_t cand = E[enc_hash6(c_lo, c_hi) >> (32 - ENC_EBITS)];
+            if (cand < p && ld32u(src, cand) == c_lo) {
+                const uint32_t lim = (p + ENC_EXT_CAP < n) ? p + ENC_EXT_CAP : n;
+                uint32_t len = 4;
                 for (;;) {
-                    bool lose = valid && (L[hL] < rel);
-                    if (!__any_sync(FULLMASK, lose)) break;
-                    if (lose) L[hL] = (uint16_t)rel;
-                    __syncwarp();
+                    if (p + len >= lim) break;
+                    uint32_t x = ld32u(src, p + len) ^ ld32u(src, cand + len);
+                    if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                    len += 4;
                 }
-                // candidates: recent-in-sub-range first, else earliest-in-chunk; 4 bytes verify here, the length of
-                // a *selected* match is measured cooperatively below (one byte per lane)
-                uint32_t q = 0;
-                bool has = false;
-                if (valid && e0 - p >= 4) {              // matches never cross the sub-range end
-                    if (candL != 0xffff) { q = b0 + candL; has = ld32u(src, q) == c_lo; }
-                    if (!has && candE < p) { q = candE; has = ld32u(src, q) == c_lo; }
-                }
-                unsigned mask = __ballot_sync(FULLMASK, has);
-                uint32_t next = cur + 32;
-                uint32_t from = 0;
-                bool sel = false;
-                uint32_t recx = 0, recy = 0;
-                while (true) {
-                    unsigned m = (from < 32) ? (mask & (0xffffffffu << from)) : 0u;
-                    if (m == 0) break;
-                    const int f = __ffs((int)m) - 1;
-                    const uint32_t pf = cur + (uint32_t)f;
-                    const uint32_t qf = __shfl_sync(FULLMASK, q, f);
-                    // lanes 0..27: byte 4+lane after the verified prefix; lanes 28..31: byte 1+(lane-28) before the match
-                    // (at most 4 back, never before the pending literals or position 0)
-                    bool ne;
-                    if (lane < 28) {
-                        const uint32_t a = pf + 4 + lane;
-                        ne = (a >= e0) || (src[a] != src[qf + 4 + lane]);
-                    } else {
-                        const uint32_t b = lane - 28;
-                        ne = (qf < 4) || (b >= pf - nextEmit) || (src[pf - 1 - b] != src[qf - 1 - b]);
-                    }
-                    const unsigned neq = __ballot_sync(FULLMASK, ne);
-                    const uint32_t fwd = (uint32_t)__ffs((int)((neq & 0x0fffffffu) | 0x10000000u)) - 1;
-                    const uint32_t back = (uint32_t)__ffs((int)((neq >> 28) | 16u)) - 1;
-                    uint32_t len = 4 + fwd;
-                    if (fwd == 28 && pf + 32 < e0) len = 32 + warp_match_len(src, pf + 32, qf + 32, e0);
-                    const uint32_t off = pf - qf;
-                    const uint32_t s = pf - back;
-                    len += back;
-                    const bool isrep = (ownNew >= 1) && (off == rep0) && (s > nextEmit);
-                    if (lane == (unsigned)f) {
-                        // record: x = litLen | (matchLen-3) << 16 ; y = dist (0 = repeat) | matchStart << 16
-                        sel = true;
-                        recx = (s - nextEmit) | ((len - 3) << 16);
-                        recy = (isrep ? 0u : off) | (s << 16);
-                    }
-                    sumML += len;
-                    if (!isrep) { rep0 = off; ownNew++; }
-                    nextEmit = s + len;
-                    if (nextEmit >= cur + 32) { next = nextEmit; break; }
-                    from = nextEmit - cur;
-                }
-                // the selected lanes store their records side by side (window order = lane order)
-                {
-                    unsigned selmask = __ballot_sync(FULLMASK, sel);
-                    if (sel) rec[nrec + (uint32_t)__popc(selmask & ((1u << lane) - 1))] = make_uint2(recx, recy);
-                    nrec += (uint32_t)__popc(selmask);
-                }
-                cur = next;
+                capped = false;
+                if (p + len >= lim) { len = lim - p; capped = lim < n; }
+                uint32_t s = p, t = cand;
+                while (s > nextEmit && t > 0 && src[s - 1] == src[t - 1]) { s--; t--; len++; }
+                rec[cnt * ENC_NT + tid] = make_uint2(s | (len << 16), p - cand);
+                cnt++;
+                p = s + len;
+                nextEmit = p;
+            } else {
+                p++;
             }
         }
-        if (lane == 0) {
-            sh->cnt[w] = nrec;
-            sh->tail[w] = (b0 < n) ? e0 - nextEmit : 0;
-            sh->sumLL[w] = (b0 < n) ? (e0 - b0) - sumML : 0;
+        if (cnt) lastE = nextEmit;
+    }
+    cntA[tid] = (uint8_t)cnt;
+    capA[tid] = (uint8_t)((cnt != 0) && capped);
+    __syncthreads();
+    // long matches: warp 0 walks the capped records in order and finishes them cooperatively (128 bytes per step);
+    // a capped record that already lies inside an earlier finished one is skipped, so a chunk of zeros costs one pass
+    if (w == 0) {
+        uint32_t covered = 0;
+        for (uint32_t base = 0; base < nlanes; base += 32) {
+            const uint32_t t = base + lane;
+            unsigned m = __ballot_sync(FULLMASK, t < nlanes && capA[t]);
+            while (m) {
+                const uint32_t tt = base + (uint32_t)(__ffs((int)m) - 1);
+                m &= m - 1;
+                const uint32_t slot = ((uint32_t)cntA[tt] - 1) * ENC_NT + tt;
+                const uint2 r = rec[slot];
+                const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
+                const uint32_t e0 = s0 + l0;
+                if (e0 > covered) {
+                    const uint32_t ext = warp_match_len(src, e0, e0 - d0, n);
+                    if (lane == 0) rec[slot] = make_uint2(s0 | ((l0 + ext) << 16), d0);
+                    covered = e0 + ext;
+                }
+            }
         }
     }
     __syncthreads();
+    if (capped && cnt) { const uint2 r = rec[(cnt - 1) * ENC_NT + tid]; lastE = (r.x & 0xffff) + (r.x >> 16); }
     B2C_PHASE(3);
 
-    // ---------------------------------------------------------------- P3: global sequence/literal layout
-    if (w == 0) {
-        uint32_t c = sh->cnt[lane], l = sh->sumLL[lane], t = sh->tail[lane];
-        uint32_t ci = warp_scan_incl(c), li = warp_scan_incl(l), ti = warp_scan_incl(t);
-        sh->seqBase[lane] = ci - c;
-        sh->litBase[lane] = li - l;
-        // carry into warp v = tails of the warps after the last warp (< v) that had sequences
-        unsigned has = __ballot_sync(FULLMASK, c != 0);
-        unsigned below = has & ((1u << lane) - 1);
-        int last = below ? 31 - __clz((int)below) : -1;
-        uint32_t tiLast = __shfl_sync(FULLMASK, ti, last < 0 ? 0 : last);   // inclusive tail prefix at `last`
-        uint32_t tLast = __shfl_sync(FULLMASK, t, last < 0 ? 0 : last);
-        uint32_t texcl = ti - t;                                            // tails of lanes < me
-        uint32_t upToLastExcl = (last < 0) ? 0u : tiLast - tLast;           // tails of lanes < last
-        sh->carry[lane] = texcl - upToLastExcl;                             // tails of lanes in [last, me)
-        if (lane == 31) {
-            uint32_t nseq = ci, nlit = li;
-            sh->nseq = nseq; sh->nlit = nlit;
-            // blockEnc.encode early decisions (blockenc.go:481-503)
-            uint32_t kind = 0;
-            if (nseq == 0) kind = 1;  // encodeLits(..., rawAllLits=true) => raw block
-            else {
-                int saved = (int)n - (int)nlit - (int)(n >> 6);
-                if (saved < 16) kind = 1;
-            }
-            sh->kind = kind; sh->rleLen = 0;
-        }
+    // ---------------------------------------------------------------- P3: merge (trim overlaps), global layout
+    uint32_t dummyTotal;
+    const uint32_t R = group_scan_excl_max(lastE, sh->ws, 0, ENC_NT, tid, &dummyTotal);   // everything before R is taken
+    uint32_t kept = 0, sumLen = 0, keptE = 0, lastOff = 0;
+    for (uint32_t j = 0; j < cnt; j++) {
+        const uint2 r = rec[j * ENC_NT + tid];
+        const uint32_t s0 = r.x & 0xffff, e0 = s0 + (r.x >> 16);
+        if (e0 <= R) continue;
+        const uint32_t s2 = s0 > R ? s0 : R, l2 = e0 - s2;
+        if (l2 < 4) continue;
+        rec[kept * ENC_NT + tid] = make_uint2(s2 | (l2 << 16), r.y);
+        kept++; sumLen += l2; keptE = e0; lastOff = r.y;
     }
+    keptEndA[tid] = keptE;
+    lastOffA[tid] = (uint16_t)lastOff;
+    uint32_t packedTotal, keyTotal;
+    __syncthreads();   // sh->ws is reused by the next scan
+    const uint32_t packedEx = group_scan_excl((kept << 17) | sumLen, sh->ws, 0, ENC_NT, tid, &packedTotal);
     __syncthreads();
-    const uint32_t nseq = sh->nseq, nlit = sh->nlit;
-    uint32_t kind = sh->kind;
-
-    // ---------------------------------------------------------------- P4: gather literals, compact sequences, codes
-    if (kind == 0) {
-        const uint2 *rec = reinterpret_cast<const uint2 *>(scratch) + w * ENC_SEGCAP;
-        const uint32_t cntw = sh->cnt[w], sbase = sh->seqBase[w], carry = sh->carry[w];
-        uint32_t lbase = sh->litBase[w];
-        const uint32_t b0 = w * sub;
-        const uint32_t e0 = (b0 + sub < n) ? b0 + sub : n;
-        for (uint32_t i0 = 0; i0 < cntw; i0 += 32) {
-            uint32_t i = i0 + lane;
-            uint32_t ll = 0, ml3 = 0, dist = 0, ms = 0;
-            if (i < cntw) {
-                uint2 r = rec[i];
-                ll = r.x & 0xffff; ml3 = r.x >> 16; dist = r.y & 0xffff; ms = r.y >> 16;
-            }
-            uint32_t incl = warp_scan_incl(ll);
-            uint32_t lpos = lbase + incl - ll;  // literal index of my run
-            for (uint32_t k = 0; k < ll; k++) lit[lpos + k] = src[ms - ll + k];
-            if (i < cntw) {
-                uint32_t llt = ll + ((i == 0) ? carry : 0u);
-                uint32_t ofv = dist ? dist + 3 : 1u;
-                uint32_t gi = sbase + i;
-                W->seqLL[gi] = (uint16_t)llt; W->seqML[gi] = (uint16_t)ml3; W->seqOF[gi] = ofv;
-                W->codes[TBL_LL][gi] = (uint8_t)seq_ll_code(llt);
-                W->codes[TBL_OF][gi] = (uint8_t)highbit32(ofv);
-                W->codes[TBL_ML][gi] = (uint8_t)seq_ml_code(ml3);
-            }
-            lbase += __shfl_sync(FULLMASK, incl, 31);
-        }
-        uint32_t tl = sh->tail[w];
-        for (uint32_t k = lane; k < tl; k += 32) lit[lbase + k] = src[e0 - tl + k];
+    // nearest earlier thread that kept something: gives the end of the previous sequence and its offset
+    const uint32_t keyEx = group_scan_excl_max(kept ? tid + 1 : 0u, sh->ws, 0, ENC_NT, tid, &keyTotal);
+    const uint32_t nseq = packedTotal >> 17, nlit = n - (packedTotal & 0x1ffffu);
+    const uint32_t lastEnd = keyTotal ? keptEndA[keyTotal - 1] : 0u;      // end of the last sequence of the chunk
+    uint32_t kind = 0;
+    // blockEnc.encode early decisions (blockenc.go:481-503)
+    if (nseq == 0) kind = 1;  // encodeLits(..., rawAllLits=true) => raw block
+    else {
+        int saved = (int)n - (int)nlit - (int)(n >> 6);
+        if (saved < 16) kind = 1;
     }
+
+    // ---------------------------------------------------------------- P4: gather literals, sequences, codes
+    if (kind == 0) {
+        uint32_t prevE = keyEx ? keptEndA[keyEx - 1] : 0u;
+        uint32_t pOff = keyEx ? (uint32_t)lastOffA[keyEx - 1] : 0u;
+        uint32_t gi = packedEx >> 17, mrun = packedEx & 0x1ffffu;
+        for (uint32_t j = 0; j < kept; j++) {
+            const uint2 r = rec[j * ENC_NT + tid];
+            const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
+            const uint32_t ll = s0 - prevE;
+            const uint32_t lpos = prevE - mrun;          // literal index = source position - match bytes before it
+            for (uint32_t k = 0; k < ll; k++) lit[lpos + k] = src[prevE + k];
+            // repeat code 1 (= offset of the previous sequence, valid with litLen > 0; seqdec.go:463-500)
+            const bool isrep = (gi > 0) && (d0 == pOff) && (ll > 0);
+            const uint32_t ofv = isrep ? 1u : d0 + 3;
+            W->seqLL[gi] = (uint16_t)ll; W->seqML[gi] = (uint16_t)(l0 - 3); W->seqOF[gi] = ofv;
+            W->codes[TBL_LL][gi] = (uint8_t)seq_ll_code(ll);
+            W->codes[TBL_OF][gi] = (uint8_t)highbit32(ofv);
+            W->codes[TBL_ML][gi] = (uint8_t)seq_ml_code(l0 - 3);
+            prevE = s0 + l0; mrun += l0; pOff = d0; gi++;
+        }
+        const uint32_t tl = n - lastEnd;
+        for (uint32_t k = tid; k < tl; k += ENC_NT) lit[nlit - tl + k] = src[lastEnd + k];
+    }
+    if (tid == 0) { sh->kind = kind; sh->rleLen = 0; }
     __syncthreads();
     // single-sequence RLE block test (blockenc.go:484-493); nlit <= 1
     if (kind == 0 && nseq == 1 && nlit <= 1 && tid == 0) {
@@ -442,48 +421,37 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
 
     // ---------------------------------------------------------------- P5: histograms (src is dead from here on)
     if (kind == 0) {
-        // per-warp private bins, lanes holding equal symbols merged with match.any (no atomics, no RMW races):
-        // shist[w][192] sequence-code bins (LL, OF, ML), lhist32[w][256] literal bins
-        uint32_t *lhist32 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L);
-        for (uint32_t i = tid; i < 32 * 192; i += ENC_NT) shist[i] = 0;
-        for (uint32_t i = tid; i < 32 * 256; i += ENC_NT) lhist32[i] = 0;
-        __syncthreads();
+        // Ballot histograms: lane l owns the symbols whose low 5 bits equal l and keeps one register counter per value
+        // of the high bits; 8 (6) ballots per 32 symbols, no shared-memory read-modify-write, no atomics.
+        uint32_t *lhist32 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L);   // [32 warps][256]
+        uint32_t lc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) lc[k] = 0;
         {
-            uint32_t *hl = lhist32 + w * 256;
-            const uint32_t nl4 = (nlit + 3) / 4;            // literal words; bytes past nlit are masked below
+            const uint32_t nl4 = (nlit + 3) / 4;
             const uint32_t *lit32 = reinterpret_cast<const uint32_t *>(lit);
             for (uint32_t base = w * 32; base < nl4; base += ENC_NW * 32) {
-                uint32_t i = base + lane;
-                bool valid = i < nl4;
-                uint32_t v = valid ? lit32[i] : 0;
+                const uint32_t i = base + lane;
+                const uint32_t v = (i < nl4) ? lit32[i] : 0;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    bool ok = valid && (4 * i + k < nlit);
-                    unsigned act = __ballot_sync(FULLMASK, ok);
-                    if (ok) {
-                        unsigned sym = (v >> (8 * k)) & 0xff;
-                        unsigned peers = __match_any_sync(act, sym);
-                        if (lane == (unsigned)(__ffs((int)peers) - 1)) hl[sym] += (uint32_t)__popc(peers);
-                    }
-                    __syncwarp();
-                }
-            }
-            uint32_t *hw3 = shist + w * 192;
-            for (uint32_t base = w * 32; base < nseq; base += ENC_NW * 32) {
-                uint32_t i = base + lane;
-                bool valid = i < nseq;
-                unsigned act = __ballot_sync(FULLMASK, valid);
-                if (valid) {
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        unsigned code = W->codes[c][i];
-                        unsigned peers = __match_any_sync(act, code);
-                        if (lane == (unsigned)(__ffs((int)peers) - 1)) hw3[c * 64 + code] += (uint32_t)__popc(peers);
-                    }
-                }
-                __syncwarp();
+                for (int k4 = 0; k4 < 4; k4++)
+                    warp_hist_acc<8>((v >> (8 * k4)) & 0xff, (i < nl4) && (4 * i + k4 < nlit), lc, lane);
             }
         }
+        uint32_t sc[3][2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { sc[c][0] = 0; sc[c][1] = 0; }
+        for (uint32_t base = w * 32; base < nseq; base += ENC_NW * 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < nseq;
+#pragma unroll
+            for (int c = 0; c < 3; c++) warp_hist_acc<6>(valid ? (uint32_t)W->codes[c][i] : 0u, valid, sc[c], lane);
+        }
+        __syncthreads();   // keptEndA / lastOffA (same region) are dead now
+#pragma unroll
+        for (int k = 0; k < 8; k++) lhist32[w * 256 + k * 32 + lane] = lc[k];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { shist[w * 192 + c * 64 + lane] = sc[c][0]; shist[w * 192 + c * 64 + 32 + lane] = sc[c][1]; }
         __syncthreads();
         if (tid < 256) {
             uint32_t c = 0;
