@@ -43,10 +43,11 @@ constexpr uint32_t ENC_EXT_CAP = 256;     // per-thread forward extension limit;
 constexpr uint32_t ENC_MAX_CHUNK = 1u << 16;
 constexpr uint32_t ENC_SRC_BYTES = ENC_MAX_CHUNK + 128;   // chunk + zero padding
 constexpr uint32_t ENC_E_BYTES = (1u << ENC_EBITS) * 2;
-constexpr uint32_t ENC_L_BYTES = 48 * 1024;   // per-thread merge state, later the per-warp histograms
+constexpr uint32_t ENC_SREC = 7;           // match records per thread kept in shared memory (the rest spill to HBM)
+constexpr uint32_t ENC_L_BYTES = 64 * 1024;   // 7 records + 8 bytes of merge state per thread; later the literal counters
 constexpr uint32_t ENC_MAXSEQ = 16384 + 64;
 constexpr int PACK_NT = 512;              // K4 threads per CTA
-constexpr uint32_t ENC_SCRATCH_BYTES = ENC_MAXREC * ENC_NT * 8;  // per-CTA match records [k][thread]
+constexpr uint32_t ENC_SCRATCH_BYTES = (ENC_MAXREC - ENC_SREC) * ENC_NT * 8;  // per-CTA spilled match records [k][thread]
 
 enum { ENC_FLAG_CRC = 1, ENC_FLAG_FRAME = 2 };
 
@@ -177,7 +178,6 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     uint16_t *E = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_E);
     ParseShared *sh = reinterpret_cast<ParseShared *>(smem + ENC_SMEM_SH);
     uint8_t *lit = smem + ENC_SMEM_E;                                      // after the parse
-    uint32_t *shist = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_SRC);   // [32][192] seq-code histograms (src is dead)
     ChunkWork *W = P.work + chunk;
 
     const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
@@ -285,42 +285,71 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     // bytes, extend forwards/backwards, skip past the match).  Threads never communicate: E is read-only here, so the
     // result does not depend on scheduling.  A match may run past the end of the thread's range; the merge step (P3)
     // trims whatever a later thread found inside it.
-    uint2 *rec = reinterpret_cast<uint2 *>(scratch);             // rec[k * ENC_NT + tid]: x = start | len << 16, y = dist
-    uint32_t *keptEndA = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L);   // [1024]
+    // record k of thread t: x = start | len << 16, y = dist; k < ENC_SREC in shared memory, the rest in the HBM scratch
+    uint2 *recS = reinterpret_cast<uint2 *>(smem + ENC_SMEM_L);
+    uint2 *recG = reinterpret_cast<uint2 *>(scratch);
+#define REC(k, t) (*(((k) < ENC_SREC) ? &recS[(k) * ENC_NT + (t)] : &recG[((k) - ENC_SREC) * ENC_NT + (t)]))
+    uint32_t *keptEndA = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L + ENC_SREC * 8 * ENC_NT);   // [1024]
     uint16_t *lastOffA = reinterpret_cast<uint16_t *>(keptEndA + ENC_NT);   // [1024]
     uint8_t *cntA = reinterpret_cast<uint8_t *>(lastOffA + ENC_NT);         // [1024]
     uint8_t *capA = cntA + ENC_NT;                                          // [1024]
     const uint32_t nlanes = (n + ENC_LANE_BYTES - 1) / ENC_LANE_BYTES;
     uint32_t cnt = 0, lastE = 0;
     bool capped = false;
-    if (tid < nlanes) {
+    {
+        // The loop alternates two kinds of steps so that each runs with many active lanes: a probe step for the lanes
+        // that are scanning, and -- once enough lanes of the warp hold an unverified-length match (or nobody is left
+        // scanning) -- an extend-and-emit step for those.  The per-thread sequence of operations is unchanged by the
+        // batching, so the parse does not depend on it.
+        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
         const uint32_t b = tid * ENC_LANE_BYTES;
         const uint32_t e = (b + ENC_LANE_BYTES < n) ? b + ENC_LANE_BYTES : n;
-        const uint32_t pend = e < npos ? e : npos;           // probe positions need 8 readable bytes
-        uint32_t p = b, nextEmit = b;
-        while (p < pend) {
-            const uint64_t cv = ld64u(src, p);
-            const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
-            const uint32_t cand = E[enc_hash6(c_lo, c_hi) >> (32 - ENC_EBITS)];
-            if (cand < p && ld32u(src, cand) == c_lo) {
-                const uint32_t lim = (p + ENC_EXT_CAP < n) ? p + ENC_EXT_CAP : n;
-                uint32_t len = 4;
-                for (;;) {
-                    if (p + len >= lim) break;
-                    uint32_t x = ld32u(src, p + len) ^ ld32u(src, cand + len);
-                    if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                    len += 4;
+        const uint32_t pend = (tid < nlanes) ? (e < npos ? e : npos) : 0u;   // probe positions need 8 readable bytes
+        uint32_t p = b, nextEmit = b, cand = 0;
+        bool scanning = p < pend, waiting = false;
+        uint64_t cv = scanning ? ld64u(src, p) : 0ull;
+        for (;;) {
+            if (scanning) {
+                const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
+                cand = E[enc_hash6(c_lo, c_hi) >> (32 - ENC_EBITS)];
+                if (cand < p && ld32u(src, cand) == c_lo) { waiting = true; scanning = false; }
+                else {
+                    p++;
+                    cv = (cv >> 8) | ((uint64_t)src[p + 7] << 56);
+                    scanning = p < pend;
                 }
-                capped = false;
-                if (p + len >= lim) { len = lim - p; capped = lim < n; }
-                uint32_t s = p, t = cand;
-                while (s > nextEmit && t > 0 && src[s - 1] == src[t - 1]) { s--; t--; len++; }
-                rec[cnt * ENC_NT + tid] = make_uint2(s | (len << 16), p - cand);
-                cnt++;
-                p = s + len;
-                nextEmit = p;
-            } else {
-                p++;
+            }
+            const unsigned wm = __ballot_sync(FULLMASK, waiting);
+            const unsigned sm = __ballot_sync(FULLMASK, scanning);
+            if ((wm | sm) == 0) break;
+            if (__popc(wm) >= 8 || sm == 0) {
+                if (waiting) {
+                    const uint32_t lim = (p + ENC_EXT_CAP < n) ? p + ENC_EXT_CAP : n;
+                    // forward: 4 bytes per step from two unaligned streams (aligned word loads + funnel shifts)
+                    uint32_t len = 4;
+                    {
+                        uint32_t ia = (p + 4) >> 2, ib = (cand + 4) >> 2;
+                        const uint32_t sha = ((p + 4) & 3) * 8, shb = ((cand + 4) & 3) * 8;
+                        uint32_t wa0 = srcw[ia], wb0 = srcw[ib];
+                        while (p + len < lim) {
+                            const uint32_t wa1 = srcw[++ia], wb1 = srcw[++ib];
+                            const uint32_t x = __funnelshift_r(wa0, wa1, sha) ^ __funnelshift_r(wb0, wb1, shb);
+                            if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                            len += 4; wa0 = wa1; wb0 = wb1;
+                        }
+                    }
+                    capped = false;
+                    if (p + len >= lim) { len = lim - p; capped = lim < n; }
+                    uint32_t s = p, t = cand;
+                    while (s > nextEmit && t > 0 && src[s - 1] == src[t - 1]) { s--; t--; len++; }
+                    REC(cnt, tid) = make_uint2(s | (len << 16), p - cand);
+                    cnt++;
+                    p = s + len;
+                    nextEmit = p;
+                    waiting = false;
+                    scanning = p < pend;
+                    if (scanning) cv = ld64u(src, p);
+                }
             }
         }
         if (cnt) lastE = nextEmit;
@@ -338,20 +367,20 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             while (m) {
                 const uint32_t tt = base + (uint32_t)(__ffs((int)m) - 1);
                 m &= m - 1;
-                const uint32_t slot = ((uint32_t)cntA[tt] - 1) * ENC_NT + tt;
-                const uint2 r = rec[slot];
+                const uint32_t kk = (uint32_t)cntA[tt] - 1;
+                const uint2 r = REC(kk, tt);
                 const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
                 const uint32_t e0 = s0 + l0;
                 if (e0 > covered) {
                     const uint32_t ext = warp_match_len(src, e0, e0 - d0, n);
-                    if (lane == 0) rec[slot] = make_uint2(s0 | ((l0 + ext) << 16), d0);
+                    if (lane == 0) REC(kk, tt) = make_uint2(s0 | ((l0 + ext) << 16), d0);
                     covered = e0 + ext;
                 }
             }
         }
     }
     __syncthreads();
-    if (capped && cnt) { const uint2 r = rec[(cnt - 1) * ENC_NT + tid]; lastE = (r.x & 0xffff) + (r.x >> 16); }
+    if (capped && cnt) { const uint2 r = REC(cnt - 1, tid); lastE = (r.x & 0xffff) + (r.x >> 16); }
     B2C_PHASE(3);
 
     // ---------------------------------------------------------------- P3: merge (trim overlaps), global layout
@@ -359,12 +388,12 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     const uint32_t R = group_scan_excl_max(lastE, sh->ws, 0, ENC_NT, tid, &dummyTotal);   // everything before R is taken
     uint32_t kept = 0, sumLen = 0, keptE = 0, lastOff = 0;
     for (uint32_t j = 0; j < cnt; j++) {
-        const uint2 r = rec[j * ENC_NT + tid];
+        const uint2 r = REC(j, tid);
         const uint32_t s0 = r.x & 0xffff, e0 = s0 + (r.x >> 16);
         if (e0 <= R) continue;
         const uint32_t s2 = s0 > R ? s0 : R, l2 = e0 - s2;
         if (l2 < 4) continue;
-        rec[kept * ENC_NT + tid] = make_uint2(s2 | (l2 << 16), r.y);
+        REC(kept, tid) = make_uint2(s2 | (l2 << 16), r.y);
         kept++; sumLen += l2; keptE = e0; lastOff = r.y;
     }
     keptEndA[tid] = keptE;
@@ -391,7 +420,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         uint32_t pOff = keyEx ? (uint32_t)lastOffA[keyEx - 1] : 0u;
         uint32_t gi = packedEx >> 17, mrun = packedEx & 0x1ffffu;
         for (uint32_t j = 0; j < kept; j++) {
-            const uint2 r = rec[j * ENC_NT + tid];
+            const uint2 r = REC(j, tid);
             const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
             const uint32_t ll = s0 - prevE;
             const uint32_t lpos = prevE - mrun;          // literal index = source position - match bytes before it
@@ -421,60 +450,74 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
 
     // ---------------------------------------------------------------- P5: histograms (src is dead from here on)
     if (kind == 0) {
-        // Ballot histograms: lane l owns the symbols whose low 5 bits equal l and keeps one register counter per value
-        // of the high bits; 8 (6) ballots per 32 symbols, no shared-memory read-modify-write, no atomics.
-        uint32_t *lhist32 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L);   // [32 warps][256]
-        uint32_t lc[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) lc[k] = 0;
-        {
+        // literal histogram: warps 0..3, one private u16 counter per (symbol, lane) -- conflict-free, no atomics;
+        // four literals per load, the four counter updates of a word are made independent by merging equal symbols.
+        // meanwhile warps 4..31 count the sequence codes with ballots (lane l owns codes with low 5 bits == l) and
+        // copy the literals out.
+        uint16_t *lcol = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_L);       // [4][256][32] u16 = 64 KiB
+        uint32_t *shist2 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_SRC);   // [28][192] code counters (src is dead)
+        for (uint32_t i = tid; i < 4 * 256 * 32 / 2; i += ENC_NT) reinterpret_cast<uint32_t *>(lcol)[i] = 0;
+        __syncthreads();
+        if (w < 4) {
+            uint16_t *hcol = lcol + w * 256 * 32 + lane;
             const uint32_t nl4 = (nlit + 3) / 4;
             const uint32_t *lit32 = reinterpret_cast<const uint32_t *>(lit);
-            for (uint32_t base = w * 32; base < nl4; base += ENC_NW * 32) {
-                const uint32_t i = base + lane;
-                const uint32_t v = (i < nl4) ? lit32[i] : 0;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; k4++)
-                    warp_hist_acc<8>((v >> (8 * k4)) & 0xff, (i < nl4) && (4 * i + k4 < nlit), lc, lane);
+            for (uint32_t i = w * 32 + lane; i < nl4; i += 4 * 32) {
+                const uint32_t v = lit32[i];
+                const uint32_t nv = (4 * i + 4 <= nlit) ? 4u : nlit - 4 * i;
+                const uint32_t s0 = v & 0xff, s1 = (v >> 8) & 0xff, s2 = (v >> 16) & 0xff, s3 = v >> 24;
+                // increments with duplicates folded into the first occurrence
+                uint32_t i0 = 1, i1 = nv > 1, i2 = nv > 2, i3 = nv > 3;
+                if (s1 == s0) { i0 += i1; i1 = 0; }
+                if (s2 == s0) { i0 += i2; i2 = 0; } else if (s2 == s1) { i1 += i2; i2 = 0; }
+                if (s3 == s0) { i0 += i3; i3 = 0; } else if (s3 == s1) { i1 += i3; i3 = 0; } else if (s3 == s2) { i2 += i3; i3 = 0; }
+                const uint32_t c0 = hcol[s0 * 32], c1 = hcol[s1 * 32], c2 = hcol[s2 * 32], c3 = hcol[s3 * 32];
+                hcol[s0 * 32] = (uint16_t)(c0 + i0);
+                if (i1) hcol[s1 * 32] = (uint16_t)(c1 + i1);
+                if (i2) hcol[s2 * 32] = (uint16_t)(c2 + i2);
+                if (i3) hcol[s3 * 32] = (uint16_t)(c3 + i3);
             }
+        } else {
+            uint32_t sc[3][2];
+#pragma unroll
+            for (int c = 0; c < 3; c++) { sc[c][0] = 0; sc[c][1] = 0; }
+            for (uint32_t base = (w - 4) * 32; base < nseq; base += (ENC_NW - 4) * 32) {
+                const uint32_t i = base + lane;
+                const bool valid = i < nseq;
+#pragma unroll
+                for (int c = 0; c < 3; c++) warp_hist_acc<6>(valid ? (uint32_t)W->codes[c][i] : 0u, valid, sc[c], lane);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                shist2[(w - 4) * 192 + c * 64 + lane] = sc[c][0];
+                shist2[(w - 4) * 192 + c * 64 + 32 + lane] = sc[c][1];
+            }
+            // literals to the work record (coalesced 16-byte stores)
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(lit);
+            uint4 *d4 = reinterpret_cast<uint4 *>(W->lit);
+            const uint32_t n16 = (nlit + 15) / 16;
+            for (uint32_t i = tid - 128; i < n16; i += ENC_NT - 128) d4[i] = s4[i];
         }
-        uint32_t sc[3][2];
-#pragma unroll
-        for (int c = 0; c < 3; c++) { sc[c][0] = 0; sc[c][1] = 0; }
-        for (uint32_t base = w * 32; base < nseq; base += ENC_NW * 32) {
-            const uint32_t i = base + lane;
-            const bool valid = i < nseq;
-#pragma unroll
-            for (int c = 0; c < 3; c++) warp_hist_acc<6>(valid ? (uint32_t)W->codes[c][i] : 0u, valid, sc[c], lane);
-        }
-        __syncthreads();   // keptEndA / lastOffA (same region) are dead now
-#pragma unroll
-        for (int k = 0; k < 8; k++) lhist32[w * 256 + k * 32 + lane] = lc[k];
-#pragma unroll
-        for (int c = 0; c < 3; c++) { shist[w * 192 + c * 64 + lane] = sc[c][0]; shist[w * 192 + c * 64 + 32 + lane] = sc[c][1]; }
         __syncthreads();
         if (tid < 256) {
             uint32_t c = 0;
-            for (int k = 0; k < ENC_NW; k++) c += lhist32[k * 256 + tid];
+            for (int k = 0; k < 4; k++) {
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(lcol + (k * 256 + tid) * 32);
+#pragma unroll
+                for (int j = 0; j < 16; j++) { uint32_t v = row[j]; c += (v & 0xffff) + (v >> 16); }
+            }
             W->litHist[tid] = c;
         } else if (tid < 256 + 192) {
             uint32_t s = tid - 256, c = 0;
-            for (int k = 0; k < ENC_NW; k++) c += shist[k * 192 + s];
+            for (int k = 0; k < ENC_NW - 4; k++) c += shist2[k * 192 + s];
             W->seqHist[s / 64][s % 64] = c;
-            shist[s] = c;  // thread s only ever touches column s: row 0 now holds the totals
+            shist2[s] = c;  // thread s only ever touches column s: row 0 now holds the totals
         }
         __syncthreads();
         if (tid < 3) {
             uint32_t mx = 0;
-            for (uint32_t s = 0; s < 64; s++) if (shist[tid * 64 + s]) mx = s;
+            for (uint32_t s = 0; s < 64; s++) if (shist2[tid * 64 + s]) mx = s;
             W->maxSym[tid] = mx;
-        }
-        // literals to the work record (coalesced 16-byte stores)
-        {
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(lit);
-            uint4 *d4 = reinterpret_cast<uint4 *>(W->lit);
-            uint32_t n16 = (nlit + 15) / 16;
-            for (uint32_t i = tid; i < n16; i += ENC_NT) d4[i] = s4[i];
         }
         if (P.dbg_hdr) {
             for (uint32_t i = tid; i < nseq && i < P.dbg_seq_cap; i += ENC_NT) {
@@ -484,6 +527,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             for (uint32_t i = tid; i < nlit; i += ENC_NT) P.dbg_lits[(uint64_t)chunk * 65536 + i] = lit[i];
         }
     }
+#undef REC
     if (tid == 0) { W->n = n; W->nseq = nseq; W->nlit = nlit; W->kind = kind; W->rleLen = sh->rleLen; }
     __syncthreads();
     B2C_PHASE(5);
