@@ -172,18 +172,83 @@ constexpr uint32_t ENC_SMEM_SH = ENC_SMEM_L + ENC_L_BYTES;
 constexpr uint32_t ENC_SMEM_BYTES = ENC_SMEM_SH + ((sizeof(ParseShared) + 15) / 16) * 16;
 
 // ------------------------------------------------------------------------------------------------ K1
+// ---- S2 / Snappy byte-tag emitters for offsets < 65536 (s2/encode_go.go:80-289; byte layouts pinned by the KATs of
+// s2/s2_test.go:827-942).  *_size give the bytes the matching put would write.
+enum { LZ_MODE_ZSTD = 0, LZ_MODE_S2 = 1, LZ_MODE_SNAPPY = 2 };
+
+B2C_DEV uint32_t s2_lit_hdr_size(uint32_t ll) { return ll == 0 ? 0u : (ll <= 60 ? 1u : (ll <= 256 ? 2u : 3u)); }
+B2C_DEV uint32_t s2_put_lit_hdr(uint8_t *d, uint32_t ll) {   // emitLiteral's tag bytes (ll <= 65536)
+    if (ll == 0) return 0;
+    const uint32_t n = ll - 1;
+    if (n < 60) { d[0] = (uint8_t)(n << 2); return 1; }
+    if (n < 256) { d[0] = 60 << 2; d[1] = (uint8_t)n; return 2; }
+    d[0] = 61 << 2; d[1] = (uint8_t)n; d[2] = (uint8_t)(n >> 8);
+    return 3;
+}
+B2C_DEV uint32_t s2_repeat_size(uint32_t off, uint32_t len) {
+    len -= 4;
+    if (len <= 4) return 2;
+    if (len < 8 && off < 2048) return 2;
+    if (len < (1 << 8) + 4) return 3;
+    if (len < (1 << 16) + (1 << 8)) return 4;
+    return 5;
+}
+B2C_DEV uint32_t s2_put_repeat(uint8_t *d, uint32_t off, uint32_t len) {   // emitRepeat, len < 2^16 + 2^8 + 4 here
+    len -= 4;
+    if (len <= 4) { d[0] = (uint8_t)(len << 2 | 1); d[1] = 0; return 2; }
+    if (len < 8 && off < 2048) { d[1] = (uint8_t)off; d[0] = (uint8_t)((off >> 8) << 5 | len << 2 | 1); return 2; }
+    if (len < (1 << 8) + 4) { len -= 4; d[2] = (uint8_t)len; d[1] = 0; d[0] = 5 << 2 | 1; return 3; }
+    if (len < (1 << 16) + (1 << 8)) { len -= 1 << 8; d[3] = (uint8_t)(len >> 8); d[2] = (uint8_t)len; d[1] = 0; d[0] = 6 << 2 | 1; return 4; }
+    len -= 1 << 16;
+    d[4] = (uint8_t)(len >> 16); d[3] = (uint8_t)(len >> 8); d[2] = (uint8_t)len; d[1] = 0; d[0] = 7 << 2 | 1;
+    return 5;
+}
+B2C_DEV uint32_t s2_copy_size(uint32_t off, uint32_t len) {
+    if (len > 64) return (off < 2048) ? 2 + s2_repeat_size(off, len - 8) : 3 + s2_repeat_size(off, len - 60);
+    return (len >= 12 || off >= 2048) ? 3u : 2u;
+}
+B2C_DEV uint32_t s2_put_copy(uint8_t *d, uint32_t off, uint32_t len) {   // emitCopy, offset < 65536
+    if (len > 64) {
+        uint32_t o;
+        if (off < 2048) { d[1] = (uint8_t)off; d[0] = (uint8_t)((off >> 8) << 5 | (8 - 4) << 2 | 1); len -= 8; o = 2; }
+        else { d[2] = (uint8_t)(off >> 8); d[1] = (uint8_t)off; d[0] = 59 << 2 | 2; len -= 60; o = 3; }
+        return o + s2_put_repeat(d + o, off, len);
+    }
+    if (len >= 12 || off >= 2048) { d[2] = (uint8_t)(off >> 8); d[1] = (uint8_t)off; d[0] = (uint8_t)((len - 1) << 2 | 2); return 3; }
+    d[1] = (uint8_t)off; d[0] = (uint8_t)((off >> 8) << 5 | (len - 4) << 2 | 1);
+    return 2;
+}
+B2C_DEV uint32_t snappy_copy_size(uint32_t off, uint32_t len) {
+    uint32_t sz = 0;
+    while (len > 64) { sz += 3; len -= 60; }
+    return sz + ((len >= 12 || off >= 2048) ? 3u : 2u);
+}
+B2C_DEV uint32_t snappy_put_copy(uint8_t *d, uint32_t off, uint32_t len) {   // emitCopyNoRepeat, offset < 65536
+    uint32_t o = 0;
+    while (len > 64) { d[o + 2] = (uint8_t)(off >> 8); d[o + 1] = (uint8_t)off; d[o] = 59 << 2 | 2; len -= 60; o += 3; }
+    if (len >= 12 || off >= 2048) { d[o + 2] = (uint8_t)(off >> 8); d[o + 1] = (uint8_t)off; d[o] = (uint8_t)((len - 1) << 2 | 2); return o + 3; }
+    d[o + 1] = (uint8_t)off; d[o] = (uint8_t)((off >> 8) << 5 | (len - 4) << 2 | 1);
+    return o + 2;
+}
+
+// MODE: LZ_MODE_ZSTD -> fills the ChunkWork record for K2..K4; LZ_MODE_S2 / LZ_MODE_SNAPPY -> writes the finished
+// S2 block (uvarint length + tag stream, s2/encode.go:29-60) straight to the destination slot.
+template <int MODE>
 B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk, uint8_t *scratch) {
     const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     uint8_t *src = smem + ENC_SMEM_SRC;
     uint16_t *E = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_E);
     ParseShared *sh = reinterpret_cast<ParseShared *>(smem + ENC_SMEM_SH);
     uint8_t *lit = smem + ENC_SMEM_E;                                      // after the parse
-    ChunkWork *W = P.work + chunk;
+    ChunkWork *W = (MODE == LZ_MODE_ZSTD) ? P.work + chunk : nullptr;
 
     const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
     const uint32_t n = chunk_size(P, chunk);
     if (n > ENC_MAX_CHUNK) {
-        if (tid == 0) { W->n = n; W->kind = 3; }  // reported as B2C_ERR_TOO_BIG by the pack kernel
+        if (tid == 0) {
+            if constexpr (MODE == LZ_MODE_ZSTD) { W->n = n; W->kind = 3; }  // reported as B2C_ERR_TOO_BIG by the pack kernel
+            else P.out_sizes[chunk] = -3;
+        }
         return;
     }
     B2C_PHASE(0);
@@ -406,6 +471,96 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     const uint32_t keyEx = group_scan_excl_max(kept ? tid + 1 : 0u, sh->ws, 0, ENC_NT, tid, &keyTotal);
     const uint32_t nseq = packedTotal >> 17, nlit = n - (packedTotal & 0x1ffffu);
     const uint32_t lastEnd = keyTotal ? keptEndA[keyTotal - 1] : 0u;      // end of the last sequence of the chunk
+    if constexpr (MODE != LZ_MODE_ZSTD) {
+        // -------------------------------------------------------------- S2 / Snappy emission
+        // sizes per thread -> block scan -> every thread writes its own literal runs and copy tags into the staging
+        // buffer (the hash-table region, dead by now) -> one coalesced copy to the destination slot.
+        constexpr bool SNAPPY = (MODE == LZ_MODE_SNAPPY);
+        uint8_t *out = smem + ENC_SMEM_E;
+        const uint32_t hdrLen = n < 128 ? 1u : (n < 16384 ? 2u : 3u);       // uvarint(n), n <= 65536
+        uint32_t prevE = keyEx ? keptEndA[keyEx - 1] : 0u;
+        uint32_t pOff = keyEx ? (uint32_t)lastOffA[keyEx - 1] : 0u;
+        const bool first = (packedEx >> 17) == 0;                            // no sequence before this thread's
+        uint32_t mySize = 0;
+        {
+            uint32_t pe = prevE, po = pOff;
+            bool fst = first;
+            for (uint32_t j = 0; j < kept; j++) {
+                const uint2 r = REC(j, tid);
+                const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
+                const uint32_t ll = s0 - pe;
+                mySize += s2_lit_hdr_size(ll) + ll;
+                if (SNAPPY) mySize += snappy_copy_size(d0, l0);
+                else mySize += (!fst && d0 == po) ? s2_repeat_size(d0, l0) : s2_copy_size(d0, l0);
+                pe = s0 + l0; po = d0; fst = false;
+            }
+        }
+        uint32_t bodyNoTail;
+        __syncthreads();
+        const uint32_t myOff = group_scan_excl(mySize, sh->ws, 0, ENC_NT, tid, &bodyNoTail);
+        const uint32_t tl = n - lastEnd;
+        const uint32_t body = bodyNoTail + s2_lit_hdr_size(tl) + tl;
+        uint8_t *gdst = P.dst_base + (uint64_t)chunk * P.dst_stride;
+        // encodeBlock's "not compressible" rule (s2/encode_all.go:88: dstLimit), blocks below minNonLiteralBlockSize
+        // (s2/encode.go:375) and the empty input are stored as one literal
+        const bool store = (n < 32) || (nseq == 0) || (body > n - (n >> 5) - 5);
+        const uint32_t total = hdrLen + (store ? s2_lit_hdr_size(n) + n : body);
+        if (total > P.dst_cap) {
+            if (tid == 0) P.out_sizes[chunk] = -4;
+        } else if (store) {
+            if (tid == 0) {
+                uint32_t o = 0, v = n;
+                while (v >= 0x80) { gdst[o++] = (uint8_t)(v | 0x80); v >>= 7; }
+                gdst[o++] = (uint8_t)v;
+                s2_put_lit_hdr(gdst + o, n);
+                P.out_sizes[chunk] = (int64_t)total;
+            }
+            const uint32_t o0 = hdrLen + s2_lit_hdr_size(n);
+            for (uint32_t i = tid; i < n; i += ENC_NT) gdst[o0 + i] = src[i];
+        } else {
+            if (tid == 0) {
+                uint32_t o = 0, v = n;
+                while (v >= 0x80) { out[o++] = (uint8_t)(v | 0x80); v >>= 7; }
+                out[o++] = (uint8_t)v;
+            }
+            uint8_t *d = out + hdrLen + myOff;
+            bool fst = first;
+            for (uint32_t j = 0; j < kept; j++) {
+                const uint2 r = REC(j, tid);
+                const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
+                const uint32_t ll = s0 - prevE;
+                d += s2_put_lit_hdr(d, ll);
+                for (uint32_t k = 0; k < ll; k++) d[k] = src[prevE + k];
+                d += ll;
+                if (SNAPPY) d += snappy_put_copy(d, d0, l0);
+                else d += (!fst && d0 == pOff) ? s2_put_repeat(d, d0, l0) : s2_put_copy(d, d0, l0);
+                prevE = s0 + l0; pOff = d0; fst = false;
+            }
+            {   // trailing literals: header by one thread, bytes by everybody
+                uint8_t *dt = out + hdrLen + bodyNoTail;
+                const uint32_t th = s2_lit_hdr_size(tl);
+                if (tid == 0) s2_put_lit_hdr(dt, tl);
+                for (uint32_t k = tid; k < tl; k += ENC_NT) dt[th + k] = src[lastEnd + k];
+            }
+            __syncthreads();
+            // write-back: bytes up to the first 16-byte boundary of the destination, then 16-byte stores
+            const uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(gdst) & 15)) & 15);
+            if (head == 0) {
+                const uint32_t n16 = total / 16;
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(out);
+                uint4 *d4 = reinterpret_cast<uint4 *>(gdst);
+                for (uint32_t i = tid; i < n16; i += ENC_NT) d4[i] = s4[i];
+                for (uint32_t i = n16 * 16 + tid; i < total; i += ENC_NT) gdst[i] = out[i];
+            } else {
+                for (uint32_t i = tid; i < total; i += ENC_NT) gdst[i] = out[i];
+            }
+            if (tid == 0) P.out_sizes[chunk] = (int64_t)total;
+        }
+        __syncthreads();
+        B2C_PHASE(4);
+        B2C_PHASE(5);
+        return;
+    }
     uint32_t kind = 0;
     // blockEnc.encode early decisions (blockenc.go:481-503)
     if (nseq == 0) kind = 1;  // encodeLits(..., rawAllLits=true) => raw block
@@ -583,78 +738,81 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
 // Per-lane tables live in shared memory, interleaved so that lane l only ever touches bank l:
 // 128 words of packed u16 next-states + 64 words of (deltaNbBits | (deltaFindState + 512) << 21).
 constexpr int CHAIN_NT = 96;
-constexpr uint32_t CHAIN_SMEM_WORDS_PER_LANE = 128 + 64 + 4;   // + 8 x u16 output staging
+constexpr uint32_t CHAIN_SMEM_WORDS_PER_LANE = 128 + 64;   // 256 x u16 state table + 64 x u32 symbol transforms
 constexpr uint32_t CHAIN_SMEM_BYTES = CHAIN_NT * CHAIN_SMEM_WORDS_PER_LANE * 4;
+// K3: one lane per (chunk, table) walks the tANS state chain from the last sequence to the first
+// (blockenc.go:757-803 restated as three independent recurrences) and stores, per sequence, the bits it emits:
+// stb[i] = value | nbBits << 12.  The recurrence is latency-bound, so the loop keeps the dependent path to
+// add/shift/add + one shared-memory load per step: codes arrive eight at a time (one 8-byte load, requested two
+// blocks ahead), their symbol transforms are fetched up front, results leave as one 16-byte store per 8 steps.
 B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_t chunk0) {
     const unsigned tid = threadIdx.x, lane = tid & 31, which = tid >> 5;
     const uint32_t chunk = chunk0 + lane;
     const bool live = chunk < P.nchunks && P.work[chunk < P.nchunks ? chunk : 0].kind == 0;
     ChunkWork *W = P.work + (live ? chunk : 0);
     uint32_t *st32 = smem32 + which * 32 * CHAIN_SMEM_WORDS_PER_LANE;  // this warp's region
-    uint32_t *tState = st32 + lane;            // element i of lane l at [i * 32 + l]
-    uint32_t *tSym = st32 + 128 * 32 + lane;
-    uint16_t *outq = reinterpret_cast<uint16_t *>(st32 + (128 + 64) * 32) + lane * 8;  // 16 bytes per lane
+    uint16_t *tState = reinterpret_cast<uint16_t *>(st32) + lane;      // element i of lane l at u16 index i * 32 + l
+    uint32_t *tSym = st32 + 128 * 32 + lane;                           // element i of lane l at word i * 32 + l
     uint32_t nseq = 0, useRLE = 1, tableLog = 0;
     if (live) {
         const FseCTable *t = &W->tbl[which];
         nseq = W->nseq; useRLE = t->useRLE; tableLog = t->tableLog;
         if (!useRLE) {
             const uint32_t *sw = reinterpret_cast<const uint32_t *>(t->stateTable);
-            uint32_t ts2 = (1u << tableLog) / 2;
-            for (uint32_t i = 0; i < ts2; i++) tState[i * 32] = sw[i];
-            uint32_t sl = t->symbolLen;
-            for (uint32_t i = 0; i < sl; i++)
-                tSym[i * 32] = t->deltaNbBits[i] | ((uint32_t)((int32_t)t->deltaFindState[i] + 512) << 21);
+            const uint32_t ts2 = (1u << tableLog) / 2;
+            for (uint32_t i = 0; i < ts2; i++) {
+                const uint32_t v = sw[i];
+                tState[(2 * i) * 32] = (uint16_t)v;
+                tState[(2 * i + 1) * 32] = (uint16_t)(v >> 16);
+            }
+            const uint32_t sl = t->symbolLen;
+            for (uint32_t i = 0; i < 64; i++)
+                tSym[i * 32] = (i < sl) ? (t->deltaNbBits[i] | ((uint32_t)((int32_t)t->deltaFindState[i] + 512) << 21)) : 0u;
         }
     }
     __syncwarp();
     const uint8_t *codes = W->codes[which];
     uint16_t *stb = W->stb[which];
     uint32_t state = 0;
-    if (live && !useRLE) {
-        uint32_t sym = codes[nseq - 1];
-        uint32_t e = tSym[sym * 32];
-        uint32_t dnb = e & 0x1fffffu;
-        int32_t dfs = (int32_t)(e >> 21) - 512;
-        uint32_t nbBitsOut = (dnb + (1u << 15)) >> 16;
-        int32_t im = (int32_t)((nbBitsOut << 16) - dnb);
-        int32_t lu = (im >> nbBitsOut) + dfs;
-        uint32_t wv = tState[(lu >> 1) * 32];
-        state = (lu & 1) ? (wv >> 16) : (wv & 0xffff);
+    const bool run = live && !useRLE && nseq >= 1;
+    if (run) {
+        const uint32_t e = tSym[(codes[nseq - 1] & 63u) * 32];
+        const uint32_t dnb = e & 0x1fffffu;
+        const int32_t dfs = (int32_t)(e >> 21) - 512;
+        const uint32_t nbBitsOut = (dnb + (1u << 15)) >> 16;
+        const int32_t im = (int32_t)((nbBitsOut << 16) - dnb);
+        state = tState[((im >> nbBitsOut) + dfs) * 32];
     }
-    const uint32_t steps = (live && !useRLE && nseq) ? nseq - 1 : 0;
-    const uint32_t maxSteps = warp_max(steps);
-    // codes are consumed from index nseq-2 downwards, one aligned 32-bit word (4 codes) per load, the next word
-    // requested one word ahead of its use
-    const uint32_t *cw32 = reinterpret_cast<const uint32_t *>(codes);
-    int32_t idx = (int32_t)nseq - 2;
-    uint32_t cw = 0, cwNext = 0;
-    if (steps) {
-        cw = cw32[idx >> 2];
-        cwNext = (idx >= 4) ? cw32[(idx >> 2) - 1] : 0;
-    }
-    for (uint32_t t = 1; t <= maxSteps; t++) {
-        if (t <= steps) {
-            uint32_t sym = (cw >> (8 * (idx & 3))) & 0xffu;
-            uint32_t e = tSym[sym * 32];
-            uint32_t nb = (state + (e & 0x1fffffu)) >> 16;
-            // eight results are staged in shared memory and leave as one 16-byte store (a 2-byte store per step
-            // from 32 lanes to 32 different sectors costs 16x the write traffic)
-            outq[idx & 7] = (uint16_t)((state & ((1u << nb) - 1)) | (nb << 12));
-            if ((idx & 7) == 0) {
-                if (idx + 8 <= (int32_t)nseq - 1)
-                    *reinterpret_cast<uint4 *>(stb + idx) = *reinterpret_cast<const uint4 *>(outq);
-                else
-                    for (int32_t k = idx; k <= (int32_t)nseq - 2; k++) stb[k] = outq[k & 7];
+    // sequences nseq-2 .. 0 in blocks of eight (block k = sequences 8k .. 8k+7), top block first
+    const int32_t top = run ? (int32_t)nseq - 2 : -1;
+    const int32_t blk = top >> 3;                                  // -1 when there is nothing to do
+    const uint32_t nblk = warp_max((uint32_t)(blk + 1));
+    const uint2 *c8 = reinterpret_cast<const uint2 *>(codes);
+    uint2 cwA = make_uint2(0, 0), cwB = make_uint2(0, 0);
+    if (blk >= 0) cwA = c8[blk];
+    if (blk >= 1) cwB = c8[blk - 1];
+    for (uint32_t it = 0; it < nblk; it++) {
+        const int32_t k = blk - (int32_t)it;
+        if (k >= 0) {
+            uint2 cwC = make_uint2(0, 0);
+            if (k >= 2) cwC = c8[k - 2];
+            uint32_t e[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t code = (((j < 4) ? cwA.x : cwA.y) >> (8 * (j & 3))) & 63u;
+                e[j] = tSym[code * 32];
             }
-            int32_t lu = (int32_t)(state >> nb) + ((int32_t)(e >> 21) - 512);
-            uint32_t wv = tState[(lu >> 1) * 32];
-            state = (lu & 1) ? (wv >> 16) : (wv & 0xffff);
-            if ((idx & 3) == 0) {
-                cw = cwNext;
-                if (idx >= 8) cwNext = cw32[(idx >> 2) - 2];
+            uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int pos = 7; pos >= 0; pos--) {
+                if (8 * k + pos <= top) {
+                    const uint32_t nb = (state + (e[pos] & 0x1fffffu)) >> 16;
+                    o[pos >> 1] |= ((state & ((1u << nb) - 1)) | (nb << 12)) << (16 * (pos & 1));
+                    state = tState[((int32_t)(state >> nb) + (int32_t)(e[pos] >> 21) - 512) * 32];
+                }
             }
-            idx--;
+            *reinterpret_cast<uint4 *>(stb + 8 * k) = make_uint4(o[0], o[1], o[2], o[3]);
+            cwA = cwB; cwB = cwC;
         }
     }
     if (live) {
@@ -980,10 +1138,21 @@ B2C_DEV void zstd_xxh_quad(const ZstdEncParams &P, uint32_t chunk, unsigned q /*
 }
 
 #ifndef B2C_EMU
+// S2 / Snappy block encode: the same parse, tag-stream emission instead of the entropy stages (one kernel).
+extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_s2_encode_kernel(ZstdEncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_S2>(smem, P, c, scratch);
+}
+extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_snappy_encode_kernel(ZstdEncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_SNAPPY>(smem, P, c, scratch);
+}
 extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_zstd_parse_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk(smem, P, c, scratch);
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_ZSTD>(smem, P, c, scratch);
 }
 extern "C" __global__ void __launch_bounds__(128) b2c_zstd_tables_kernel(ZstdEncParams P) {
     __shared__ TablesShared ts;

@@ -3,6 +3,7 @@
 #include "simt_emu.h"
 #include "../../compress_b200/csrc/b2c_zstd_enc.cuh"
 #include "../../compress_b200/csrc/b2c_zstd_dec.cuh"
+#include "../../compress_b200/csrc/b2c_s2_dec.cuh"
 #include <vector>
 #include <cstdlib>
 
@@ -33,7 +34,7 @@ int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, 
     });
     // K1 parse
     emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
-        for (uint32_t c = 0; c < P.nchunks; c++) zstd_parse_chunk(emu::dyn_smem, P, c, P.scratch);
+        for (uint32_t c = 0; c < P.nchunks; c++) zstd_parse_chunk<LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
     });
     // K2 tables
     static TablesShared ts;
@@ -65,6 +66,37 @@ int emu_zstd_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t 
     P.out_sizes = out_sizes; P.nchunks = n; P.lit_scratch = lit.data();
     emu::launch(grid, DEC_WARPS * 32, DEC_SMEM_BYTES, [&]() {
         zstd_decode_warp(emu::dyn_smem, P, blockIdx.x * DEC_WARPS + (threadIdx.x >> 5), gridDim.x * DEC_WARPS);
+    });
+    return 0;
+}
+
+// S2 (snappy = 0) / Snappy-compatible (snappy = 1) block encode of nchunks chunks (chunk i = src + i*stride).
+int emu_s2_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
+                  uint64_t dst_stride, int64_t *out_sizes, int snappy) {
+    std::vector<uint8_t> scratch(ENC_SCRATCH_BYTES, 0xCD);
+    ZstdEncParams P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = src; P.src_stride = stride; P.src_sizes = sizes;
+    P.dst_base = dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
+    P.out_sizes = out_sizes; P.nchunks = nchunks; P.scratch = scratch.data();
+    emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
+        for (uint32_t c = 0; c < P.nchunks; c++) {
+            if (snappy) zstd_parse_chunk<LZ_MODE_SNAPPY>(emu::dyn_smem, P, c, P.scratch);
+            else zstd_parse_chunk<LZ_MODE_S2>(emu::dyn_smem, P, c, P.scratch);
+        }
+    });
+    return 0;
+}
+
+int emu_s2_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t *src_sizes, uint32_t n, uint8_t *dst,
+                  const uint64_t *dst_off, const uint32_t *dst_caps, int64_t *out_sizes) {
+    S2DecParams P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = src; P.src_offsets = src_off; P.src_sizes = src_sizes;
+    P.dst_base = dst; P.dst_offsets = dst_off; P.dst_caps = dst_caps;
+    P.out_sizes = out_sizes; P.nchunks = n;
+    emu::launch(2, S2DEC_WARPS * 32, 0, [&]() {
+        s2_decode_warp(P, blockIdx.x * S2DEC_WARPS + (threadIdx.x >> 5), gridDim.x * S2DEC_WARPS);
     });
     return 0;
 }
