@@ -9,6 +9,7 @@
 #include "../../include/b2c.h"
 #include "b2c_zstd_enc.cuh"
 #include "b2c_zstd_dec.cuh"
+#include "b2c_s2_dec.cuh"
 
 using namespace b2c;
 
@@ -145,6 +146,10 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)ENC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)CHAIN_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_s2_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)ENC_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_snappy_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)ENC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -564,6 +569,134 @@ int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *
         if (sizes_out[i] > 0) CK(cudaMemcpyAsync(dsts[i], ctx->d_dec_out + dof[i], (size_t)sizes_out[i], cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return B2C_OK;
+}
+
+
+// ---- S2 / Snappy blocks ---------------------------------------------------------------------------
+size_t b2c_s2_bound(size_t n) {
+    // s2.MaxEncodedLen (s2/encode.go:389-418), 64-bit platform; 0 when the block is too large
+    if (n > 0xffffffffull) return 0;
+    size_t bits = 0;
+    for (size_t v = n; v; v >>= 1) bits++;
+    size_t r = n + (bits + 7) / 7;
+    if (n) r += n < 60 ? 1 : n < (1u << 8) ? 2 : n < (1u << 16) ? 3 : n < (1u << 24) ? 4 : 5;
+    return r > 0xffffffffull ? 0 : r;
+}
+
+int b2c_s2_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
+                         const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
+                         int64_t *d_out_sizes, uint32_t nchunks, void *stream) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (level != B2C_S2_FAST) return B2C_ERR_UNSUPPORTED;
+    if (nchunks == 0) return B2C_OK;
+    if (dst_stride > 0xffffffffull) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ZstdEncParams P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_sizes = d_sizes; P.src_size_all = size_all;
+    P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
+    P.out_sizes = d_out_sizes; P.nchunks = nchunks;
+    P.scratch = ctx->d_scratch;
+    unsigned sms = (unsigned)ctx->sm_count;
+    unsigned g1 = sms < nchunks ? sms : nchunks;
+    if (flags & B2C_S2_SNAPPY) b2c_snappy_encode_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+    else b2c_s2_encode_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_s2_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, const uint64_t *d_src_offsets,
+                         const uint32_t *d_src_sizes, void *d_dst, size_t dst_stride, const uint64_t *d_dst_offsets,
+                         uint32_t dst_cap, int64_t *d_out_sizes, uint32_t nchunks, void *stream) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (!d_src_sizes || !d_out_sizes) return B2C_ERR_ARG;
+    if (nchunks == 0) return B2C_OK;
+    CK(cudaSetDevice(ctx->device));
+    S2DecParams P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_offsets = d_src_offsets; P.src_sizes = d_src_sizes;
+    P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_offsets = d_dst_offsets; P.dst_cap = dst_cap;
+    P.out_sizes = d_out_sizes; P.nchunks = nchunks;
+    unsigned grid = (nchunks + S2DEC_WARPS - 1) / S2DEC_WARPS, maxGrid = (unsigned)ctx->sm_count * 16;
+    if (grid > maxGrid) grid = maxGrid;
+    b2c_s2_decode_kernel<<<grid, S2DEC_WARPS * 32, 0, (cudaStream_t)stream>>>(P);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+// Host-buffer batches for the block API (s2.Encode / s2.EncodeSnappy / s2.Decode per element).  Inputs are packed
+// back to back on the device, outputs land in per-element slots; one kernel per call.
+static int s2_host_batch(b2c_ctx *ctx, bool encode, int flags, const void *const *srcs, const size_t *src_sizes,
+                         void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (n == 0) return B2C_OK;
+    if (n > 0xffffffffull) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<uint64_t> meta(3 * n + n);
+    uint64_t *so = meta.data(), *dof = so + n;
+    uint32_t *ss = reinterpret_cast<uint32_t *>(meta.data() + 3 * n), *dc = ss + n;
+    uint64_t inb = 0, outb = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (src_sizes[i] > 0xffffffffull) return B2C_ERR_ARG;
+        so[i] = inb; dof[i] = outb;
+        ss[i] = (uint32_t)src_sizes[i];
+        dc[i] = (uint32_t)(dst_caps[i] > 0xffffffffull ? 0xffffffffull : dst_caps[i]);
+        // encode: fixed strides (the kernel addresses chunks by stride)
+        inb += encode ? (size_t)ENC_MAX_CHUNK : ((src_sizes[i] + 15) & ~(size_t)15);
+        outb += encode ? (size_t)kSlot : (((size_t)dc[i] + 15) & ~(size_t)15);
+    }
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_dec_in, &ctx->dec_in_cap, inb + 256))) return rc;
+    if ((rc = grow(ctx, &ctx->d_dec_out, &ctx->dec_out_cap, outb + 256))) return rc;
+    if ((rc = grow(ctx, &ctx->d_dec_meta, &ctx->dec_meta_cap, meta.size() * 8))) return rc;
+    for (size_t i = 0; i < n; i++) {
+        if (encode && src_sizes[i] > ENC_MAX_CHUNK) { ss[i] = ENC_MAX_CHUNK + 1; continue; }   // reported as too big
+        if (src_sizes[i]) CK(cudaMemcpyAsync(ctx->d_dec_in + so[i], srcs[i], src_sizes[i], cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(ctx->d_dec_meta, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, st));
+    uint64_t *dm = reinterpret_cast<uint64_t *>(ctx->d_dec_meta);
+    uint32_t *d_ss = reinterpret_cast<uint32_t *>(dm + 3 * n);
+    int64_t *d_res = reinterpret_cast<int64_t *>(dm + 2 * n);
+    if (encode)
+        rc = b2c_s2_encode_device(ctx, B2C_S2_FAST, flags, ctx->d_dec_in, ENC_MAX_CHUNK, d_ss, 0, ctx->d_dec_out, kSlot, d_res,
+                                  (uint32_t)n, st);
+    else {
+        S2DecParams P;
+        memset(&P, 0, sizeof(P));
+        P.src_base = ctx->d_dec_in; P.src_offsets = dm; P.src_sizes = d_ss;
+        P.dst_base = ctx->d_dec_out; P.dst_offsets = dm + n; P.dst_caps = d_ss + n;
+        P.out_sizes = d_res; P.nchunks = (uint32_t)n;
+        unsigned grid = ((unsigned)n + S2DEC_WARPS - 1) / S2DEC_WARPS, maxGrid = (unsigned)ctx->sm_count * 16;
+        if (grid > maxGrid) grid = maxGrid;
+        b2c_s2_decode_kernel<<<grid, S2DEC_WARPS * 32, 0, st>>>(P);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        rc = B2C_OK;
+    }
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(sizes_out, d_res, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; i++) {
+        if (sizes_out[i] > 0 && (size_t)sizes_out[i] > dst_caps[i]) { sizes_out[i] = B2C_ERR_DST_SMALL; continue; }
+        if (sizes_out[i] > 0)
+            CK(cudaMemcpyAsync(dsts[i], ctx->d_dec_out + dof[i], (size_t)sizes_out[i], cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return B2C_OK;
+}
+
+int b2c_s2_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const *srcs, const size_t *src_sizes,
+                         void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n) {
+    if (level != B2C_S2_FAST) return ctx ? B2C_ERR_UNSUPPORTED : B2C_ERR_NO_DEVICE;
+    return s2_host_batch(ctx, true, flags, srcs, src_sizes, dsts, dst_caps, sizes_out, n);
+}
+int b2c_s2_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
+                         const size_t *dst_caps, int64_t *sizes_out, size_t n) {
+    return s2_host_batch(ctx, false, 0, srcs, src_sizes, dsts, dst_caps, sizes_out, n);
 }
 
 }  // extern "C"

@@ -1,0 +1,132 @@
+"""Host-side mirror of the reference's S2 block interface for the accelerated path.
+
+Names follow klauspost/compress/s2: ``Encode`` (s2/encode.go:29), ``EncodeSnappy`` (:204), ``Decode``
+(s2/decode.go:58), ``MaxEncodedLen`` (s2/encode.go:389), ``ErrCorrupt`` / ``ErrTooLarge`` (s2/decode.go:17-26).
+The work is done by libb200comp.so through the C ABI in include/b2c.h; blocks are at most 64 KiB (the
+``WriterBlockSize`` the GPU path is built for), larger inputs raise ``ErrTooLarge``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import lib, check, B2CError
+
+BLOCK = 1 << 16
+SLOT = BLOCK + 512
+FAST = 1
+FLAG_SNAPPY = 1
+
+
+class ErrCorrupt(B2CError):
+    pass
+
+
+class ErrTooLarge(B2CError):
+    pass
+
+
+def MaxEncodedLen(n):
+    r = int(lib.b2c_s2_bound(n))
+    return r if (r or n == 0) and n <= 0xffffffff else -1
+
+
+class Codec:
+    """Batch S2 block encoder/decoder on one B200."""
+
+    def __init__(self, device=0):
+        if not torch.cuda.is_available() or lib.b2c_device_count() == 0:
+            raise B2CError("no CUDA device: compress_b200 has no CPU fallback")
+        self._ctx = lib.b2c_ctx_create(device, 0)
+        if not self._ctx:
+            raise B2CError("b2c_ctx_create failed")
+
+    def close(self):
+        if self._ctx:
+            lib.b2c_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(lib.b2c_launch_count(self._ctx))
+
+    # ---- device-resident batches --------------------------------------------------------------
+    def encode_device(self, src, sizes=None, block=BLOCK, snappy=False, dst=None, out_sizes=None):
+        """src: uint8 CUDA tensor, block i at i*block.  Returns (dst [n, SLOT], out_sizes int64).  Async."""
+        assert src.is_cuda and src.dtype == torch.uint8
+        n = src.numel() // block if sizes is None else sizes.numel()
+        if dst is None:
+            dst = torch.empty((n, SLOT), dtype=torch.uint8, device=src.device)
+        if out_sizes is None:
+            out_sizes = torch.empty((n,), dtype=torch.int64, device=src.device)
+        stream = torch.cuda.current_stream(src.device).cuda_stream
+        check(lib.b2c_s2_encode_device(self._ctx, FAST, FLAG_SNAPPY if snappy else 0, src.data_ptr(), block,
+                                       None if sizes is None else sizes.data_ptr(), block, dst.data_ptr(), SLOT,
+                                       out_sizes.data_ptr(), n, ctypes.c_void_p(stream)), self._ctx)
+        return dst, out_sizes
+
+    def decode_device(self, src, src_sizes, src_stride, dst=None, dst_cap=BLOCK, out_sizes=None):
+        assert src.is_cuda and src.dtype == torch.uint8
+        n = src_sizes.numel()
+        if dst is None:
+            dst = torch.empty((n, dst_cap), dtype=torch.uint8, device=src.device)
+        if out_sizes is None:
+            out_sizes = torch.empty((n,), dtype=torch.int64, device=src.device)
+        stream = torch.cuda.current_stream(src.device).cuda_stream
+        check(lib.b2c_s2_decode_device(self._ctx, src.data_ptr(), src_stride, None, src_sizes.data_ptr(), dst.data_ptr(),
+                                       dst_cap, None, dst_cap, out_sizes.data_ptr(), n, ctypes.c_void_p(stream)), self._ctx)
+        return dst, out_sizes
+
+    # ---- host buffers ------------------------------------------------------------------------------
+    def _host(self, fn, blobs, caps, *pre):
+        n = len(blobs)
+        bufs = [np.frombuffer(bytes(b), dtype=np.uint8) if len(b) else np.zeros(0, dtype=np.uint8) for b in blobs]
+        outs = [np.empty(max(int(c), 1), dtype=np.uint8) for c in caps]
+        srcs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        ssz = (ctypes.c_size_t * n)(*[len(b) for b in blobs])
+        dsts = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+        dcap = (ctypes.c_size_t * n)(*[int(c) for c in caps])
+        res = (ctypes.c_int64 * n)()
+        check(fn(self._ctx, *pre, srcs, ssz, dsts, dcap, res, n), self._ctx)
+        codes = [int(r) for r in res]
+        return [outs[i][:codes[i]].tobytes() if codes[i] >= 0 else None for i in range(n)], codes
+
+    def encode_blocks(self, blocks, snappy=False):
+        if not blocks:
+            return []
+        outs, codes = self._host(lib.b2c_s2_encode_chunks, blocks, [MaxEncodedLen(len(b)) + 16 for b in blocks], FAST,
+                                 FLAG_SNAPPY if snappy else 0)
+        for c in codes:
+            if c == -3:
+                raise ErrTooLarge("s2: block larger than the GPU path's 64 KiB block size")
+            if c < 0:
+                raise B2CError(lib.b2c_strerror(c).decode())
+        return outs
+
+    def decode_blocks(self, blocks, caps):
+        if not blocks:
+            return [], []
+        return self._host(lib.b2c_s2_decode_chunks, blocks, caps)
+
+    def Encode(self, src):
+        """s2.Encode(nil, src) for one block (s2/encode.go:29)."""
+        return self.encode_blocks([src])[0]
+
+    def EncodeSnappy(self, src):
+        """s2.EncodeSnappy(nil, src) (s2/encode.go:204): output any Snappy decoder accepts."""
+        return self.encode_blocks([src], snappy=True)[0]
+
+    def Decode(self, src, max_len=BLOCK):
+        """s2.Decode(nil, src) (s2/decode.go:58)."""
+        outs, codes = self.decode_blocks([src], [max_len])
+        if codes[0] == -4:
+            raise ErrTooLarge("s2: decoded block is too large")
+        if codes[0] < 0:
+            raise ErrCorrupt("s2: corrupt input")
+        return outs[0]

@@ -50,6 +50,11 @@ enum {
     B2C_ZSTD_FRAME = 2   /* emit one complete frame per chunk (EncodeAll); otherwise bare blocks */
 };
 
+/* S2 block encoder: level and flags.  B2C_S2_FAST = s2.Encode's match finder class (s2/encode.go:29);
+ * B2C_S2_SNAPPY selects Snappy-compatible output (s2.EncodeSnappy, s2/encode.go:204: no repeat tags, copies <= 64). */
+enum { B2C_S2_FAST = 1 };
+enum { B2C_S2_SNAPPY = 1 };
+
 /* zstd levels (zstd.EncoderLevel, zstd/encoder_options.go) */
 enum { B2C_LEVEL_FASTEST = 1, B2C_LEVEL_DEFAULT = 2 };
 
@@ -135,6 +140,27 @@ B2C_API int b2c_zstd_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_s
 /* Host-buffer batch decode (the call a cgo shim makes for a batch of DecodeAll calls).  Synchronous. */
 B2C_API int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
                                    const size_t *dst_caps, int64_t *sizes_out, size_t n);
+
+/*
+ * S2 / Snappy blocks (s2.Encode / s2.EncodeSnappy / s2.Decode, s2/encode.go:29,204, s2/decode.go:58; per-block work
+ * of s2.Writer with WriterBlockSize(64 KiB), the seam WriterCustomEncoder exposes, s2/writer.go:1052).
+ * Block i (<= 64 KiB of input) becomes uvarint(len) + tag stream, or uvarint + one literal when it does not shrink.
+ * Argument conventions are those of the zstd calls above.  Decode accepts any S2 or Snappy block whose decoded
+ * length fits dst_cap (repeat tags, 4-byte offsets and long literals included); results are decoded bytes or
+ * B2C_ERR_CORRUPT (s2.ErrCorrupt) / B2C_ERR_DST_SMALL.
+ */
+B2C_API size_t b2c_s2_bound(size_t n);   /* s2.MaxEncodedLen, s2/encode.go:389; 0 = too large */
+B2C_API int b2c_s2_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
+                                 const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
+                                 int64_t *d_out_sizes, uint32_t nchunks, void *stream);
+B2C_API int b2c_s2_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, const uint64_t *d_src_offsets,
+                                 const uint32_t *d_src_sizes, void *d_dst, size_t dst_stride,
+                                 const uint64_t *d_dst_offsets, uint32_t dst_cap, int64_t *d_out_sizes,
+                                 uint32_t nchunks, void *stream);
+B2C_API int b2c_s2_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const *srcs, const size_t *src_sizes,
+                                 void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n);
+B2C_API int b2c_s2_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
+                                 const size_t *dst_caps, int64_t *sizes_out, size_t n);
 
 #ifdef __cplusplus
 }

@@ -29,4 +29,7 @@ def emu_lib():
                                   c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32]
     E.emu_zstd_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
                                   c.c_void_p]
+    E.emu_s2_encode.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
+    E.emu_s2_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
+                                c.c_void_p]
     return E

@@ -57,3 +57,44 @@ def emu_decode(E, inputs, caps, desc=0):
                       capv.ctypes.data, outs.ctypes.data)
     res = [bytes(dst[int(dst_off[i]):int(dst_off[i]) + max(int(outs[i]), 0)]) for i in range(n)]
     return outs, res
+
+
+def emu_s2_encode(E, blocks, snappy=False, desc=0):
+    E.emu_set_lane_order(desc)
+    n = len(blocks)
+    stride = 65536
+    src = np.zeros(n * stride + 64, dtype=np.uint8)
+    sizes = np.zeros(n, dtype=np.uint32)
+    for i, c in enumerate(blocks):
+        src[i * stride:i * stride + len(c)] = np.frombuffer(c, dtype=np.uint8)
+        sizes[i] = len(c)
+    dstride = 65536 + 512
+    dst = np.zeros(n * dstride, dtype=np.uint8)
+    outs = np.zeros(n, dtype=np.int64)
+    E.emu_s2_encode(src.ctypes.data, stride, sizes.ctypes.data, n, dst.ctypes.data, dstride, outs.ctypes.data,
+                    1 if snappy else 0)
+    return [bytes(dst[i * dstride:i * dstride + max(int(outs[i]), 0)]) for i in range(n)], outs
+
+
+def emu_s2_decode(E, inputs, caps, desc=0):
+    E.emu_set_lane_order(desc)
+    n = len(inputs)
+    src_off = np.zeros(n, dtype=np.uint64)
+    dst_off = np.zeros(n, dtype=np.uint64)
+    sizes = np.array([len(b) for b in inputs], dtype=np.uint32)
+    capv = np.array(caps, dtype=np.uint32)
+    so = do = 0
+    for i in range(n):
+        src_off[i] = so
+        dst_off[i] = do
+        so += (len(inputs[i]) + 15) & ~15
+        do += (int(capv[i]) + 15) & ~15
+    src = np.full(so + 64, 0xA5, dtype=np.uint8)
+    for i, b in enumerate(inputs):
+        src[int(src_off[i]):int(src_off[i]) + len(b)] = np.frombuffer(b, dtype=np.uint8)
+    dst = np.full(do + 64, 0x5A, dtype=np.uint8)
+    outs = np.zeros(n, dtype=np.int64)
+    E.emu_s2_decode(src.ctypes.data, src_off.ctypes.data, sizes.ctypes.data, n, dst.ctypes.data, dst_off.ctypes.data,
+                    capv.ctypes.data, outs.ctypes.data)
+    res = [bytes(dst[int(dst_off[i]):int(dst_off[i]) + max(int(outs[i]), 0)]) for i in range(n)]
+    return outs, res, dst, dst_off

@@ -1,0 +1,80 @@
+"""S2 / Snappy block kernels (encode tail of b2c_zstd_enc.cuh, b2c_s2_dec.cuh) under the SIMT emulator, checked
+against the S2 oracle, the reference's decode vectors and pyarrow's Snappy codec.  CPU only."""
+import numpy as np
+import pytest
+
+import helpers as H
+from emu_util import emu_s2_decode, emu_s2_encode
+from s2_vectors import DECODE_TABLE, INVALID_VARINT
+from test_oracle_s2 import s2_decode as orc_decode, s2_encode as orc_encode, _L
+
+
+def _blocks():
+    rng = np.random.default_rng(11)
+    tw = H.golden("twain.txt")
+    return [b"", b"a", b"abc" * 5, bytes(31), bytes(32), bytes(100), tw[:33], tw[:1000], tw[:65536], tw[70000:70000 + 65521],
+            H.golden("html.txt")[:65536], H.golden("e.txt")[:65536], H.synth_text(65536), bytes(65536), b"ab" * 32768,
+            b"abc" * 21845, bytes(rng.integers(0, 256, 5000, dtype=np.uint8)), bytes(rng.integers(0, 256, 65536, dtype=np.uint8)),
+            bytes(rng.integers(0, 3, 65536, dtype=np.uint8)), tw[:3000] + bytes(rng.integers(0, 256, 60000, dtype=np.uint8)),
+            (tw[:700] + bytes(rng.integers(0, 256, 300, dtype=np.uint8))) * 60]
+
+
+def test_emu_s2_encode_roundtrip(emu_lib, oracle_lib):
+    blocks = _blocks()
+    L = _L()
+    for snappy in (False, True):
+        for desc in (0, 1):
+            enc, outs = emu_s2_encode(emu_lib, blocks, snappy=snappy, desc=desc)
+            for i, (b, c, r) in enumerate(zip(blocks, enc, outs)):
+                assert r == len(c) > 0 and r <= L.orc_s2_max_encoded_len(len(b)), (i, r)
+                n, got = orc_decode(c, len(b))
+                assert n == len(b) and got == b, (snappy, desc, i)
+    # lane order must not change the bytes
+    a, _ = emu_s2_encode(emu_lib, blocks, desc=0)
+    b, _ = emu_s2_encode(emu_lib, blocks, desc=1)
+    assert a == b
+    # ratio next to the reference algorithm (oracle) on text: within 5 % of s2.Encode
+    tw = H.golden("twain.txt")[:65536]
+    ours = len(emu_s2_encode(emu_lib, [tw])[0][0])
+    ref = len(orc_encode(tw, 0))
+    assert ours < 1.05 * ref, (ours, ref)
+    # incompressible and tiny blocks are stored as one literal
+    enc, _ = emu_s2_encode(emu_lib, [blocks[17], blocks[2]])
+    assert len(enc[0]) == 65536 + 3 + 3 and enc[1] == bytes([15, 14 << 2]) + blocks[2]
+
+
+def test_emu_snappy_output_is_snappy(emu_lib):
+    pa = pytest.importorskip("pyarrow")
+    codec = pa.Codec("snappy")
+    blocks = [b for b in _blocks() if len(b)]
+    enc, _ = emu_s2_encode(emu_lib, blocks, snappy=True)
+    for i, (b, c) in enumerate(zip(blocks, enc)):
+        assert codec.decompress(c, decompressed_size=len(b)).to_pybytes() == b, i
+
+
+def test_emu_s2_decode(emu_lib, oracle_lib):
+    # reference vectors (s2/s2_test.go TestDecode / TestInvalidVarint): output, error and no write past dLen
+    ins = [v[0] for v in DECODE_TABLE] + INVALID_VARINT
+    for desc in (0, 1):
+        outs, res, dst, dst_off = emu_s2_decode(emu_lib, ins, [100] * len(ins), desc)
+        for i, (inp, want, ok) in enumerate(DECODE_TABLE):
+            if ok:
+                assert outs[i] == len(want) and res[i] == want, i
+            else:
+                assert outs[i] == -5, i
+            dlen = inp[0]
+            tail = dst[int(dst_off[i]) + dlen:int(dst_off[i]) + 112]
+            assert (tail == 0x5A).all(), i
+        assert (outs[len(DECODE_TABLE):] == -5).all()
+    # blocks from the oracle's encoders (repeat tags, long copies, Snappy form) and the golden Snappy block
+    blocks = _blocks()
+    comp = [orc_encode(b, m) for b in blocks for m in (0, 1, 2)]
+    want = [b for b in blocks for m in (0, 1, 2)]
+    comp.append(H.golden("s2_twain.txt.rawsnappy"))
+    want.append(H.golden("s2_twain.txt"))
+    outs, res, _, _ = emu_s2_decode(emu_lib, comp, [len(w) for w in want])
+    for i, (w, r, g) in enumerate(zip(want, outs, res)):
+        assert r == len(w) and g == w, i
+    # too small destination / truncated input
+    outs, _, _, _ = emu_s2_decode(emu_lib, [comp[24], comp[24][:-3]], [100, 65536])
+    assert outs[0] == -4 and outs[1] == -5

@@ -1,0 +1,94 @@
+"""GPU parity tests for the S2 / Snappy block codec through the C ABI (libb200comp.so)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from s2_vectors import DECODE_TABLE, INVALID_VARINT
+from test_oracle_s2 import s2_decode as orc_decode, s2_encode as orc_encode, _L
+from test_emu_s2 import _blocks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def codec():
+    from compress_b200 import s2
+    c = s2.Codec()
+    yield c
+    c.close()
+
+
+def test_s2_encode_blocks(codec, oracle_lib):
+    from compress_b200 import s2
+    blocks = _blocks()
+    L = _L()
+    for snappy in (False, True):
+        enc = codec.encode_blocks(blocks, snappy=snappy)
+        for i, (b, c) in enumerate(zip(blocks, enc)):
+            assert 0 < len(c) <= L.orc_s2_max_encoded_len(len(b)) == s2.MaxEncodedLen(len(b)), i
+            n, got = orc_decode(c, len(b))
+            assert n == len(b) and got == b, (snappy, i)
+    with pytest.raises(s2.ErrTooLarge):
+        codec.Encode(bytes(65537))
+    assert s2.MaxEncodedLen(0) == 1 and s2.MaxEncodedLen(0xffffffff) == -1
+
+
+def test_s2_gpu_matches_emulator(codec, emu_lib):
+    from emu_util import emu_s2_encode
+    blocks = _blocks()
+    for snappy in (False, True):
+        emu, _ = emu_s2_encode(emu_lib, blocks, snappy=snappy)
+        assert codec.encode_blocks(blocks, snappy=snappy) == emu
+
+
+def test_snappy_interop(codec):
+    pa = pytest.importorskip("pyarrow")
+    pc = pa.Codec("snappy")
+    blocks = [b for b in _blocks() if len(b)]
+    enc = codec.encode_blocks(blocks, snappy=True)
+    for b, c in zip(blocks, enc):
+        assert pc.decompress(c, decompressed_size=len(b)).to_pybytes() == b
+    # blocks written by an independent Snappy encoder decode on the GPU
+    comp = [pc.compress(b).to_pybytes() for b in blocks]
+    outs, codes = codec.decode_blocks(comp, [len(b) for b in blocks])
+    assert outs == blocks and codes == [len(b) for b in blocks]
+
+
+def test_s2_decode_vectors(codec, oracle_lib):
+    from compress_b200 import s2
+    ins = [v[0] for v in DECODE_TABLE] + INVALID_VARINT
+    outs, codes = codec.decode_blocks(ins, [100] * len(ins))
+    for i, (inp, want, ok) in enumerate(DECODE_TABLE):
+        if ok:
+            assert codes[i] == len(want) and outs[i] == want, i
+        else:
+            assert codes[i] == -5, i
+    assert all(c == -5 for c in codes[len(DECODE_TABLE):])
+    blocks = _blocks()
+    comp = [orc_encode(b, m) for b in blocks for m in (0, 1, 2)] + [H.golden("s2_twain.txt.rawsnappy")]
+    want = [b for b in blocks for m in (0, 1, 2)] + [H.golden("s2_twain.txt")]
+    outs, codes = codec.decode_blocks(comp, [len(w) for w in want])
+    assert outs == want
+    assert codec.Decode(comp[24]) == want[24]
+    with pytest.raises(s2.ErrCorrupt):
+        codec.Decode(comp[24][:-3])
+    with pytest.raises(s2.ErrTooLarge):
+        codec.Decode(comp[24], max_len=100)
+
+
+def test_s2_roundtrip_device_256mib(codec):
+    n = 4096
+    src = H.synth_text_torch(n * 65536, "cuda")
+    src[10 * 65536:11 * 65536] = 0
+    src[11 * 65536:12 * 65536] = torch.randint(0, 256, (65536,), dtype=torch.uint8, device="cuda")
+    for snappy in (False, True):
+        enc, sizes = codec.encode_device(src, snappy=snappy)
+        torch.cuda.synchronize()
+        assert int(sizes.min()) > 0
+        out, osz = codec.decode_device(enc, sizes.to(torch.int32), src_stride=enc.stride(0))
+        torch.cuda.synchronize()
+        assert bool((osz == 65536).all())
+        assert torch.equal(out.view(-1), src)
+        ratio = float(sizes.sum()) / src.numel()
+        assert 0.3 < ratio < 0.8, ratio
