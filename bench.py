@@ -220,6 +220,41 @@ def main():
     assert bool((dres == CHUNK).all()) and torch.equal(dout.view(-1), src), "decode mismatch"
     del dout
 
+    # ---- secondary (BASELINE config 3): S2 / Snappy block encode + decode of the same chunks, device-resident
+    from compress_b200 import s2 as s2mod
+    s2c = s2mod.Codec(device=local_rank)
+    s2res = {}
+    s2dst = torch.empty((n, s2mod.SLOT), dtype=torch.uint8, device=dev)
+    s2sz = torch.empty((n,), dtype=torch.int64, device=dev)
+    dout = torch.empty((n, CHUNK), dtype=torch.uint8, device=dev)
+    for name, snappy in (("s2", False), ("snappy", True)):
+        for _ in range(2):
+            s2c.encode_device(src, snappy=snappy, dst=s2dst, out_sizes=s2sz)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(3):
+            s2c.encode_device(src, snappy=snappy, dst=s2dst, out_sizes=s2sz)
+        a1.record()
+        torch.cuda.synchronize()
+        ems = a0.elapsed_time(a1) / 3
+        s2out = int(s2sz.sum())
+        s2i = s2sz.to(torch.int32)
+        for _ in range(2):
+            s2c.decode_device(s2dst, s2i, src_stride=s2mod.SLOT, dst=dout, dst_cap=CHUNK, out_sizes=dres)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(3):
+            s2c.decode_device(s2dst, s2i, src_stride=s2mod.SLOT, dst=dout, dst_cap=CHUNK, out_sizes=dres)
+        a1.record()
+        torch.cuda.synchronize()
+        dms = a0.elapsed_time(a1) / 3
+        assert bool((dres == CHUNK).all()) and torch.equal(dout.view(-1), src), "s2 decode mismatch"
+        s2res[name] = {"encode_gbs": n * CHUNK / (ems / 1e3) / 1e9, "encode_ms": ems, "ratio": s2out / (n * CHUNK),
+                       "decode_gbs": n * CHUNK / (dms / 1e3) / 1e9, "decode_ms": dms,
+                       "encode_roofline_frac": (n * CHUNK + s2out) / (ems / 1e3) / 1e9 / hbm_peak()[0]}
+    del dout, s2dst
+
     # ---- end to end through the host-buffer C-ABI call (pinned host in/out)
     ne = min(args.e2e_chunks, n)
     host_in = src[: ne * CHUNK].cpu().pin_memory()
@@ -272,6 +307,7 @@ def main():
         line["decode"] = {"value": in_bytes / (dec_ms / 1e3) / 1e9, "unit": "GB/s (output bytes, this rank)", "ms": dec_ms,
                           "roofline_frac": (in_bytes + out_bytes) / (dec_ms / 1e3) / 1e9 / peak,
                           "note": "b2c_zstd_decode_kernel on the frames produced above; verified equal to the input"}
+        line["s2"] = s2res
         if not args.no_cpu_baseline and world == 1:
             sample = H.synth_chunks("text", 2048, seed=77)
             gbs, dt, ratio = cpu_reference_rate(sample, nthreads, 10.0)
