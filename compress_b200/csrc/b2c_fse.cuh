@@ -231,6 +231,98 @@ B2C_DEV int fse_build_ctable(FseCTable *ct) {
     return 0;
 }
 
+// buildCTable by one warp (ct in shared memory; scratch: 3 * 66 uint16 of shared memory).  Same table as
+// fse_build_ctable (fse_encoder.go:102-203); the serial symbol spread and state fill are replaced by rank computations:
+//   cell order k -> position (k * step) & mask, skipped when above highThreshold; the j-th surviving cell receives the
+//   symbol whose cumulative positive count covers j; state slot of cell u = cumul[symbol] + #(earlier cells, same symbol).
+B2C_DEV int fse_build_ctable_warp(FseCTable *ct, uint16_t *scratch, unsigned lane) {
+    const int16_t *norm = ct->norm;
+    const uint32_t symbolLen = ct->symbolLen, tableLog = ct->tableLog, tableSize = 1u << tableLog;
+    uint16_t *cumul = scratch;          // [65] counts with -1 taken as 1
+    uint16_t *cpos = scratch + 66;      // [65] positive counts only
+    uint16_t *fill = scratch + 132;     // [64] running per-symbol fill counters
+    // ---- cumulative counts (two symbols per lane)
+    const uint32_t i0 = lane, i1 = lane + 32;
+    const int v0 = (i0 < symbolLen) ? norm[i0] : 0, v1 = (i1 < symbolLen) ? norm[i1] : 0;
+    const uint32_t a0 = v0 == -1 ? 1u : (uint32_t)v0, a1 = v1 == -1 ? 1u : (uint32_t)v1;
+    const uint32_t p0 = v0 > 0 ? (uint32_t)v0 : 0u, p1 = v1 > 0 ? (uint32_t)v1 : 0u;
+    const uint32_t packed0 = a0 | (p0 << 16), packed1 = a1 | (p1 << 16);
+    const uint32_t inc0 = warp_scan_incl(packed0);
+    const uint32_t tot0 = __shfl_sync(FULLMASK, inc0, 31);
+    const uint32_t inc1 = warp_scan_incl(packed1) + tot0;
+    const uint32_t ex0 = inc0 - packed0, ex1 = inc1 - packed1;
+    cumul[i0] = (uint16_t)ex0; cumul[i1] = (uint16_t)ex1;
+    cpos[i0] = (uint16_t)(ex0 >> 16); cpos[i1] = (uint16_t)(ex1 >> 16);
+    fill[i0] = 0; fill[i1] = 0;
+    const uint32_t grand = __shfl_sync(FULLMASK, inc1, 31);
+    if (lane == 31) { cumul[64] = (uint16_t)grand; cpos[64] = (uint16_t)(grand >> 16); }
+    if ((grand & 0xffff) != tableSize) return -1;
+    const uint32_t nPos = grand >> 16;            // cells filled by the spread
+    // low-probability symbols take the top cells, lowest symbol highest
+    const unsigned m0 = __ballot_sync(FULLMASK, v0 == -1), m1 = __ballot_sync(FULLMASK, v1 == -1);
+    const uint32_t nLow0 = (uint32_t)__popc(m0), nLow = nLow0 + (uint32_t)__popc(m1);
+    if (v0 == -1) ct->tableSymbol[tableSize - 1 - (uint32_t)__popc(m0 & ((1u << lane) - 1))] = (uint8_t)i0;
+    if (v1 == -1) ct->tableSymbol[tableSize - 1 - nLow0 - (uint32_t)__popc(m1 & ((1u << lane) - 1))] = (uint8_t)i1;
+    const uint32_t highThreshold = tableSize - 1 - nLow;
+    __syncwarp();
+    // ---- spread
+    {
+        const uint32_t step = (tableSize >> 1) + (tableSize >> 3) + 3, tableMask = tableSize - 1;
+        uint32_t base = 0;
+        for (uint32_t k0 = 0; k0 < tableSize; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            const uint32_t pos = (k * step) & tableMask;
+            const bool ok = (k < tableSize) && (pos <= highThreshold);
+            const unsigned okm = __ballot_sync(FULLMASK, ok);
+            if (ok) {
+                const uint32_t j = base + (uint32_t)__popc(okm & ((1u << lane) - 1));
+                // largest s with cpos[s] <= j (symbols with no cells share the value of their successor and are skipped)
+                uint32_t lo = 0, hi = symbolLen;         // invariant: cpos[lo] <= j < cpos[hi]
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (cpos[mid] <= j) lo = mid; else hi = mid;
+                }
+                ct->tableSymbol[pos] = (uint8_t)lo;
+            }
+            base += (uint32_t)__popc(okm);
+        }
+        if (base != nPos) return -1;
+    }
+    __syncwarp();
+    // ---- state table: cells in position order
+    for (uint32_t u0 = 0; u0 < tableSize; u0 += 32) {
+        const uint32_t u = u0 + lane;
+        const bool ok = u < tableSize;
+        const unsigned okm = __ballot_sync(FULLMASK, ok);
+        if (ok) {
+            const uint32_t sym = ct->tableSymbol[u];
+            const unsigned peers = __match_any_sync(okm, sym);
+            const uint32_t before = fill[sym];
+            __syncwarp(okm);
+            ct->stateTable[cumul[sym] + before + (uint32_t)__popc(peers & ((1u << lane) - 1))] = (uint16_t)(tableSize + u);
+            if (lane == (unsigned)(__ffs((int)peers) - 1)) fill[sym] = (uint16_t)(before + (uint32_t)__popc(peers));
+        }
+        __syncwarp();
+    }
+    // ---- symbol transforms
+    {
+        const uint32_t tl = (tableLog << 16) - (1u << tableLog);
+        for (uint32_t i = lane; i < symbolLen; i += 32) {
+            const int v = norm[i];
+            if (v == 0) { ct->deltaNbBits[i] = 0; ct->deltaFindState[i] = 0; }
+            else if (v == -1 || v == 1) { ct->deltaNbBits[i] = tl; ct->deltaFindState[i] = (int16_t)((int)cumul[i] - 1); }
+            else {
+                const uint32_t maxBitsOut = tableLog - highbit32((uint32_t)(v - 1));
+                const uint32_t minStatePlus = (uint32_t)v << maxBitsOut;
+                ct->deltaNbBits[i] = (maxBitsOut << 16) - minStatePlus;
+                ct->deltaFindState[i] = (int16_t)((int)cumul[i] - v);
+            }
+        }
+    }
+    __syncwarp();
+    return 0;
+}
+
 // cState.init
 B2C_DEV uint32_t fse_init_state(const FseCTable *ct, uint32_t sym) {
     if (ct->useRLE) return 0;

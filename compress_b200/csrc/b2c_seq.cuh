@@ -36,6 +36,7 @@ struct SeqWork {
     uint32_t scan[40];
     uint32_t totalBits;
     int32_t err;
+    uint16_t fseScratch[3][200];   // fse_build_ctable_warp
 };
 
 B2C_DEV uint32_t seq_ll_code(uint32_t litLength) {
@@ -115,39 +116,59 @@ B2C_DEV uint32_t seq_optimal_tablelog(uint32_t length, uint32_t symbolLen) {
     return tableLog;
 }
 
-// One thread builds table `which` from sw->hist[which] (fresh block: no previous tables).
-// firstCode = code of sequence 0 (setRLE uses b.sequences[0]).
-B2C_DEV void seq_build_table(SeqWork *sw, int which, uint32_t nseq, uint32_t firstCode) {
+// One warp builds table `which` from sw->hist[which] (fresh block: no previous tables); every lane calls.
+// firstCode = code of sequence 0 (setRLE uses b.sequences[0]).  Lane 0 runs the serial steps (normalisation, size
+// estimates, NCount), the table itself is filled by all lanes.
+B2C_DEV void seq_build_table(SeqWork *sw, int which, uint32_t nseq, uint32_t firstCode, unsigned lane) {
     FseCTable *ct = &sw->cur[which];
     const uint32_t *hist = sw->hist[which];
-    uint32_t symbolLen = sw->maxSym[which] + 1;
-    uint32_t maxCount = 0;
-    for (uint32_t i = 0; i < symbolLen; i++) if (hist[i] > maxCount) maxCount = hist[i];
-    ct->symbolLen = symbolLen;
-    ct->tableLog = seq_optimal_tablelog(nseq, symbolLen);
-    ct->rleVal = 0;
+    const uint32_t symbolLen = sw->maxSym[which] + 1;
+    uint32_t maxCount = warp_max(hist[lane] > hist[lane + 32] ? hist[lane] : hist[lane + 32]);   // bins >= symbolLen are zero
+    if (lane == 0) {
+        ct->symbolLen = symbolLen;
+        ct->tableLog = seq_optimal_tablelog(nseq, symbolLen);
+        ct->rleVal = 0;
+    }
     if (maxCount == nseq) {
         // useRLE: setRLE(b.sequences[0].code), fse_encoder.go:208-221
-        ct->useRLE = 1; ct->rleVal = firstCode; ct->tableLog = 0;
-        ct->stateTable[0] = 0; ct->deltaNbBits[firstCode] = 0; ct->deltaFindState[firstCode] = 0;
-        sw->mode[which] = 1; sw->used[which] = 1;
-        sw->ncount[which][0] = (uint8_t)firstCode; sw->ncountLen[which] = 1;
+        if (lane == 0) {
+            ct->useRLE = 1; ct->rleVal = firstCode; ct->tableLog = 0;
+            ct->stateTable[0] = 0; ct->deltaNbBits[firstCode] = 0; ct->deltaFindState[firstCode] = 0;
+            sw->mode[which] = 1; sw->used[which] = 1;
+            sw->ncount[which][0] = (uint8_t)firstCode; sw->ncountLen[which] = 1;
+        }
+        __syncwarp();
         return;
     }
-    ct->useRLE = 0;
-    for (uint32_t i = 0; i < FSE_MAX_SYM; i++) ct->norm[i] = 0;
-    if (fse_normalize(hist, symbolLen, nseq, ct->tableLog, ct->norm) || fse_build_ctable(ct)) {
-        sw->mode[which] = 0; sw->used[which] = 0; sw->ncountLen[which] = SEQ_TABLE_ERR; return;
+    ct->norm[lane] = 0; ct->norm[lane + 32] = 0;
+    __syncwarp();
+    int bad = 0;
+    if (lane == 0) {
+        ct->useRLE = 0;
+        bad = fse_normalize(hist, symbolLen, nseq, ct->tableLog, ct->norm);
     }
-    // chooseComp, blockenc.go:633-661 (prev == never valid for an independent block)
-    uint32_t nSize = fse_approx_size(ct, hist, symbolLen) + (((symbolLen * ct->tableLog) >> 3) + 3) * 8;
-    uint32_t predefSize = fse_approx_size(&sw->predef[which], hist, symbolLen);
-    nSize = nSize + ((nSize + 2 * 8 * 16) >> 4);
-    if (predefSize <= nSize) { sw->mode[which] = 0; sw->used[which] = 0; sw->ncountLen[which] = 0; return; }
-    sw->mode[which] = 2; sw->used[which] = 1;
-    int w = fse_write_ncount(ct->norm, symbolLen, ct->tableLog, sw->ncount[which]);
-    if (w < 0) { sw->mode[which] = 0; sw->used[which] = 0; sw->ncountLen[which] = SEQ_TABLE_ERR; return; }
-    sw->ncountLen[which] = (uint32_t)w;
+    bad = __shfl_sync(FULLMASK, bad, 0);
+    __syncwarp();
+    if (!bad) bad = fse_build_ctable_warp(ct, sw->fseScratch[which], lane);
+    if (bad) {
+        if (lane == 0) { sw->mode[which] = 0; sw->used[which] = 0; sw->ncountLen[which] = SEQ_TABLE_ERR; }
+        __syncwarp();
+        return;
+    }
+    if (lane == 0) {
+        // chooseComp, blockenc.go:633-661 (prev == never valid for an independent block)
+        uint32_t nSize = fse_approx_size(ct, hist, symbolLen) + (((symbolLen * ct->tableLog) >> 3) + 3) * 8;
+        uint32_t predefSize = fse_approx_size(&sw->predef[which], hist, symbolLen);
+        nSize = nSize + ((nSize + 2 * 8 * 16) >> 4);
+        if (predefSize <= nSize) { sw->mode[which] = 0; sw->used[which] = 0; sw->ncountLen[which] = 0; }
+        else {
+            sw->mode[which] = 2; sw->used[which] = 1;
+            int w = fse_write_ncount(ct->norm, symbolLen, ct->tableLog, sw->ncount[which]);
+            if (w < 0) { sw->mode[which] = 0; sw->used[which] = 0; sw->ncountLen[which] = SEQ_TABLE_ERR; }
+            else sw->ncountLen[which] = (uint32_t)w;
+        }
+    }
+    __syncwarp();
 }
 
 B2C_DEV const FseCTable *seq_table(const SeqWork *sw, int which) {

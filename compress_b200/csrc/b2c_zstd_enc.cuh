@@ -718,7 +718,7 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
         for (uint32_t s = lane; s < 64; s += 32) sw->hist[which][s] = W->seqHist[which][s];
         if (lane == 0) sw->maxSym[which] = W->maxSym[which];
         __syncwarp();
-        if (lane == 0) seq_build_table(sw, which, nseq, W->codes[which][0]);
+        seq_build_table(sw, which, nseq, W->codes[which][0], lane);
         __syncwarp();
         // publish the table this chain will use
         const FseCTable *t = seq_table(sw, which);
@@ -1088,7 +1088,24 @@ B2C_DEV void zstd_xxh_quad(const ZstdEncParams &P, uint32_t chunk, unsigned q /*
     const bool aligned = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
     uint64_t v = (q == 0) ? P1 + P2 : (q == 1) ? P2 : (q == 2) ? 0ull : (0ull - P1);
     uint32_t stripes = (n <= ENC_MAX_CHUNK) ? n / 32 : 0;
-    for (uint32_t i = 0; i < stripes; i++) {
+    uint32_t i = 0;
+    if (aligned) {
+        // sixteen stripes per batch: the loads are independent of the accumulator, so they are all in flight while
+        // the (serial) multiply-rotate chain of the previous ones runs
+        const uint64_t *s8 = reinterpret_cast<const uint64_t *>(src) + q;
+        for (; i + 16 <= stripes; i += 16) {
+            uint64_t in[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) in[k] = s8[4 * (i + k)];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                v += in[k] * P2;
+                v = (v << 31) | (v >> 33);
+                v *= P1;
+            }
+        }
+    }
+    for (; i < stripes; i++) {
         uint64_t in;
         if (aligned) in = reinterpret_cast<const uint64_t *>(src)[4 * i + q];
         else { in = 0; for (int b = 0; b < 8; b++) in |= (uint64_t)src[32 * i + 8 * q + b] << (8 * b); }
