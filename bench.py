@@ -255,6 +255,42 @@ def main():
                        "encode_roofline_frac": (n * CHUNK + s2out) / (ems / 1e3) / 1e9 / hbm_peak()[0]}
     del dout, s2dst
 
+    # ---- secondary (BASELINE config 4): standalone huff0 Compress4X / Decompress4X, 262143-byte blocks of the same text
+    from compress_b200 import huff0 as hufmod
+    hc = hufmod.Codec(device=local_rank)
+    hb, hstride = 262143, 262144
+    hn = (n * CHUNK) // hstride
+    hsz = torch.full((hn,), hb, dtype=torch.int32, device=dev)
+    hdst = torch.empty((hn, hstride), dtype=torch.uint8, device=dev)
+    hout = torch.empty((hn,), dtype=torch.int64, device=dev)
+    for _ in range(2):
+        hc.compress_device(src, hstride, hsz, True, dst=hdst, out_sizes=hout)
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(3):
+        hc.compress_device(src, hstride, hsz, True, dst=hdst, out_sizes=hout)
+    a1.record()
+    torch.cuda.synchronize()
+    hc_ms = a0.elapsed_time(a1) / 3
+    assert int(hout.min()) > 0
+    hcsz = hout.to(torch.int32)
+    hdec = torch.empty((hn, hstride), dtype=torch.uint8, device=dev)
+    hres = torch.empty((hn,), dtype=torch.int64, device=dev)
+    for _ in range(2):
+        hc.decompress_device(hdst.view(-1), hstride, hcsz, hsz, hstride, True, dst=hdec, out_sizes=hres)
+    torch.cuda.synchronize()
+    a0.record()
+    for _ in range(3):
+        hc.decompress_device(hdst.view(-1), hstride, hcsz, hsz, hstride, True, dst=hdec, out_sizes=hres)
+    a1.record()
+    torch.cuda.synchronize()
+    hd_ms = a0.elapsed_time(a1) / 3
+    assert bool((hres == hb).all()) and torch.equal(hdec[:, :hb], src.view(hn, hstride)[:, :hb]), "huff0 mismatch"
+    huf_res = {"blocks": hn, "block_bytes": hb, "compress4x_gbs": hn * hb / (hc_ms / 1e3) / 1e9, "compress_ms": hc_ms,
+               "ratio": float(hout.sum()) / (hn * hb), "decompress4x_gbs": hn * hb / (hd_ms / 1e3) / 1e9, "decompress_ms": hd_ms}
+    del hdec, hdst
+
     # ---- end to end through the host-buffer C-ABI call (pinned host in/out)
     ne = min(args.e2e_chunks, n)
     host_in = src[: ne * CHUNK].cpu().pin_memory()
@@ -308,6 +344,7 @@ def main():
                           "roofline_frac": (in_bytes + out_bytes) / (dec_ms / 1e3) / 1e9 / peak,
                           "note": "b2c_zstd_decode_kernel on the frames produced above; verified equal to the input"}
         line["s2"] = s2res
+        line["huff0"] = huf_res
         if not args.no_cpu_baseline and world == 1:
             sample = H.synth_chunks("text", 2048, seed=77)
             gbs, dt, ratio = cpu_reference_rate(sample, nthreads, 10.0)

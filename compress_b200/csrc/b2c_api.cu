@@ -10,6 +10,7 @@
 #include "b2c_zstd_enc.cuh"
 #include "b2c_zstd_dec.cuh"
 #include "b2c_s2_dec.cuh"
+#include "b2c_huf0.cuh"
 
 using namespace b2c;
 
@@ -146,6 +147,10 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)ENC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)CHAIN_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_huf_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)HUF0_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_huf_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_s2_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)ENC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_snappy_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -697,6 +702,48 @@ int b2c_s2_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const *
 int b2c_s2_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
                          const size_t *dst_caps, int64_t *sizes_out, size_t n) {
     return s2_host_batch(ctx, false, 0, srcs, src_sizes, dsts, dst_caps, sizes_out, n);
+}
+
+
+// ---- standalone huff0 blocks ------------------------------------------------------------------------
+int b2c_huf_compress_device(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride, const uint32_t *d_sizes,
+                            uint32_t size_all, void *d_dst, size_t dst_stride, int64_t *d_out_sizes, uint32_t nchunks,
+                            void *stream) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (nchunks == 0) return B2C_OK;
+    if ((dst_stride & 3) || (reinterpret_cast<uintptr_t>(d_dst) & 3) || dst_stride > 0xffffffffull) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Huf0Params P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_sizes = d_sizes; P.src_size_all = size_all;
+    P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
+    P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.flags = (flags & B2C_HUF_4X) ? HUF0_FLAG_4X : 0;
+    unsigned grid = (unsigned)ctx->sm_count * 2 < nchunks ? (unsigned)ctx->sm_count * 2 : nchunks;
+    b2c_huf_compress_kernel<<<grid, HUF0_NT, HUF0_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+int b2c_huf_decompress_device(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride, const uint32_t *d_src_sizes,
+                              void *d_dst, size_t dst_stride, const uint32_t *d_dst_sizes, int64_t *d_out_sizes,
+                              uint32_t nchunks, void *stream) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (!d_src_sizes || !d_dst_sizes || !d_out_sizes) return B2C_ERR_ARG;
+    if (nchunks == 0) return B2C_OK;
+    CK(cudaSetDevice(ctx->device));
+    Huf0Params P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_sizes = d_src_sizes;
+    P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_sizes = d_dst_sizes;
+    P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.flags = (flags & B2C_HUF_4X) ? HUF0_FLAG_4X : 0;
+    const unsigned ctasPerSm = (227u * 1024u) / (DEC_SMEM_BYTES + 1024u);
+    unsigned grid = (nchunks + DEC_WARPS - 1) / DEC_WARPS, maxGrid = (unsigned)ctx->sm_count * (ctasPerSm ? ctasPerSm : 1);
+    if (grid > maxGrid) grid = maxGrid;
+    b2c_huf_decompress_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return B2C_OK;
 }
 
 }  // extern "C"

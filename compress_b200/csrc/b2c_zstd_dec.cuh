@@ -385,6 +385,31 @@ B2C_DEV int dec_huf_stream(const uint16_t *dt, uint32_t tl, const uint8_t *src, 
     return br.pos == br.total ? 0 : -1;
 }
 
+// Decompress1X / Decompress4X body after the table (huff0/decompress.go:234-, :622-): 4 streams on 4 lanes.
+// Returns 0 or -1 per lane; callers vote.  Every lane must call.
+B2C_DEV int dec_huf_streams(const uint16_t *dt, uint32_t tl, const uint8_t *hs, uint32_t hl, uint8_t *dst, uint32_t dstSize,
+                            bool four, unsigned lane) {
+    int e = 0;
+    if (four) {
+        if (hl < 6 + 4) return -1;
+        const uint32_t dstEvery = (dstSize + 3) / 4;
+        const uint32_t l0 = hs[0] | ((uint32_t)hs[1] << 8), l1 = hs[2] | ((uint32_t)hs[3] << 8), l2 = hs[4] | ((uint32_t)hs[5] << 8);
+        const uint32_t s0 = 6, s1 = s0 + l0, s2 = s1 + l1, s3 = s2 + l2;
+        if (s1 >= hl || s2 >= hl || s3 >= hl) return -1;   // "truncated input (or invalid offset)"
+        if (3 * dstEvery > dstSize) return -1;
+        const uint32_t cnt3 = dstSize - 3 * dstEvery;
+        if (lane < 4) {
+            const uint32_t st = lane == 0 ? s0 : (lane == 1 ? s1 : (lane == 2 ? s2 : s3));
+            const uint32_t ln = lane == 0 ? l0 : (lane == 1 ? l1 : (lane == 2 ? l2 : hl - s3));
+            const uint32_t cnt = lane < 3 ? dstEvery : cnt3;
+            e = dec_huf_stream(dt, tl, hs + st, ln, dst + lane * dstEvery, cnt);
+        }
+    } else {
+        if (lane == 0) e = dec_huf_stream(dt, tl, hs, hl, dst, dstSize);
+    }
+    return e;
+}
+
 // ---- the decoder: one warp, one input ---------------------------------------------------------------
 B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t cap, uint8_t *litbuf,
                                   unsigned lane) {
@@ -526,24 +551,7 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, u
                         haveHuff = true;
                         hs += used; hl -= (uint32_t)used;
                     } else if (!haveHuff) DFAIL(DEC_ERR_CORRUPT);   // treeless without history
-                    int e = 0;
-                    if (four) {
-                        if (hl < 6 + 4) DFAIL(DEC_ERR_CORRUPT);
-                        uint32_t dstEvery = (litRegen + 3) / 4;
-                        uint32_t l0 = hs[0] | ((uint32_t)hs[1] << 8), l1 = hs[2] | ((uint32_t)hs[3] << 8), l2 = hs[4] | ((uint32_t)hs[5] << 8);
-                        uint32_t s0 = 6, s1 = s0 + l0, s2 = s1 + l1, s3 = s2 + l2;
-                        if (s1 >= hl || s2 >= hl || s3 >= hl) DFAIL(DEC_ERR_CORRUPT);   // "truncated input (or invalid offset)"
-                        uint32_t cnt3 = (3 * dstEvery < litRegen) ? litRegen - 3 * dstEvery : 0;
-                        if (3 * dstEvery > litRegen) DFAIL(DEC_ERR_CORRUPT);
-                        if (lane < 4) {
-                            uint32_t st = lane == 0 ? s0 : (lane == 1 ? s1 : (lane == 2 ? s2 : s3));
-                            uint32_t ln = lane == 0 ? l0 : (lane == 1 ? l1 : (lane == 2 ? l2 : hl - s3));
-                            uint32_t cnt = lane < 3 ? dstEvery : cnt3;
-                            e = dec_huf_stream(dw->hufDt, hufLog, hs + st, ln, litbuf + lane * dstEvery, cnt);
-                        }
-                    } else {
-                        if (lane == 0) e = dec_huf_stream(dw->hufDt, hufLog, hs, hl, litbuf, litRegen);
-                    }
+                    int e = dec_huf_streams(dw->hufDt, hufLog, hs, hl, litbuf, litRegen, four, lane);
                     if (__any_sync(FULLMASK, e != 0)) DFAIL(DEC_ERR_CORRUPT);
                     in += litComp; len -= litComp;
                 }

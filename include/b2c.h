@@ -55,6 +55,11 @@ enum {
 enum { B2C_S2_FAST = 1 };
 enum { B2C_S2_SNAPPY = 1 };
 
+/* huff0: number of streams (huff0.Compress4X / Compress1X, huff0/compress.go:27,14) */
+enum { B2C_HUF_1X = 0, B2C_HUF_4X = 1 };
+/* huff0 results besides byte counts: the package's sentinel errors (huff0/huff0.go:30-42) */
+enum { B2C_HUF_ERR_INCOMPRESSIBLE = -1, B2C_HUF_ERR_USE_RLE = -2 };   /* ErrTooBig = B2C_ERR_TOO_BIG */
+
 /* zstd levels (zstd.EncoderLevel, zstd/encoder_options.go) */
 enum { B2C_LEVEL_FASTEST = 1, B2C_LEVEL_DEFAULT = 2 };
 
@@ -161,6 +166,21 @@ B2C_API int b2c_s2_encode_chunks(b2c_ctx *ctx, int level, int flags, const void 
                                  void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n);
 B2C_API int b2c_s2_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
                                  const size_t *dst_caps, int64_t *sizes_out, size_t n);
+
+/*
+ * Standalone huff0 blocks (huff0.Compress4X / Compress1X with a fresh Scratch, huff0/compress.go:14-141;
+ * huff0.ReadTable + Decoder.Decompress4X / Decompress1X, huff0/decompress.go:29,234,622).  Block i (<= 262143
+ * bytes) -> table description + (jump table +) streams, byte-identical to the reference's output;
+ * d_out_sizes[i] = bytes, or B2C_HUF_ERR_INCOMPRESSIBLE / B2C_HUF_ERR_USE_RLE / B2C_ERR_TOO_BIG /
+ * B2C_ERR_DST_SMALL.  dst_stride (= slot capacity) and d_dst must be multiples of 4.
+ * Decompress needs the exact decoded size of every block (the dstSize argument of Decompress4X).
+ */
+B2C_API int b2c_huf_compress_device(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride, const uint32_t *d_sizes,
+                                    uint32_t size_all, void *d_dst, size_t dst_stride, int64_t *d_out_sizes,
+                                    uint32_t nchunks, void *stream);
+B2C_API int b2c_huf_decompress_device(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride,
+                                      const uint32_t *d_src_sizes, void *d_dst, size_t dst_stride,
+                                      const uint32_t *d_dst_sizes, int64_t *d_out_sizes, uint32_t nchunks, void *stream);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@
 #include "../../compress_b200/csrc/b2c_zstd_enc.cuh"
 #include "../../compress_b200/csrc/b2c_zstd_dec.cuh"
 #include "../../compress_b200/csrc/b2c_s2_dec.cuh"
+#include "../../compress_b200/csrc/b2c_huf0.cuh"
 #include <vector>
 #include <cstdlib>
 
@@ -97,6 +98,36 @@ int emu_s2_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t *s
     P.out_sizes = out_sizes; P.nchunks = n;
     emu::launch(2, S2DEC_WARPS * 32, 0, [&]() {
         s2_decode_warp(P, blockIdx.x * S2DEC_WARPS + (threadIdx.x >> 5), gridDim.x * S2DEC_WARPS);
+    });
+    return 0;
+}
+
+// standalone huff0: blocks at src + i*stride -> dst + i*dst_stride
+int emu_huf_compress(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t n, uint8_t *dst,
+                     uint64_t dst_stride, int64_t *out_sizes, int four) {
+    Huf0Params P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = src; P.src_stride = stride; P.src_sizes = sizes;
+    P.dst_base = dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
+    P.out_sizes = out_sizes; P.nchunks = n; P.flags = four ? HUF0_FLAG_4X : 0;
+    emu::launch(1, HUF0_NT, HUF0_SMEM_BYTES, [&]() {
+        Huf0Shared *sh = reinterpret_cast<Huf0Shared *>(emu::dyn_smem);
+        for (uint32_t c = 0; c < P.nchunks; c++) { huf0_compress_block(sh, P, c); __syncthreads(); }
+    });
+    return 0;
+}
+int emu_huf_decompress(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t n, uint8_t *dst,
+                       uint64_t dst_stride, const uint32_t *dst_sizes, int64_t *out_sizes, int four) {
+    emu::launch(1, DEC_WARPS * 32, DEC_SMEM_BYTES, [&]() {
+        const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        DecWarp *dw = reinterpret_cast<DecWarp *>(emu::dyn_smem + w * DEC_WARP_BYTES);
+        for (uint32_t c = w; c < n; c += DEC_WARPS) {
+            __syncwarp();
+            int64_t r = huf0_decompress_block(dw, src + (uint64_t)c * stride, sizes[c], dst + (uint64_t)c * dst_stride,
+                                              dst_sizes[c], four != 0, lane);
+            __syncwarp();
+            if (lane == 0) out_sizes[c] = r;
+        }
     });
     return 0;
 }

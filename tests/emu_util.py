@@ -98,3 +98,34 @@ def emu_s2_decode(E, inputs, caps, desc=0):
                     capv.ctypes.data, outs.ctypes.data)
     res = [bytes(dst[int(dst_off[i]):int(dst_off[i]) + max(int(outs[i]), 0)]) for i in range(n)]
     return outs, res, dst, dst_off
+
+
+def emu_huf_compress(E, blocks, four=True, desc=0):
+    E.emu_set_lane_order(desc)
+    n = len(blocks)
+    stride = max(16, (max(len(b) for b in blocks) + 15) // 16 * 16)
+    src = np.zeros((n, stride), dtype=np.uint8)
+    for i, b in enumerate(blocks):
+        src[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    sizes = np.array([len(b) for b in blocks], dtype=np.uint32)
+    dst = np.full((n, stride), 0xEE, dtype=np.uint8)
+    outs = np.zeros(n, dtype=np.int64)
+    E.emu_huf_compress(src.ctypes.data, stride, sizes.ctypes.data, n, dst.ctypes.data, stride, outs.ctypes.data, 1 if four else 0)
+    return [(bytes(dst[i, :outs[i]]) if outs[i] >= 0 else None, int(outs[i])) for i in range(n)]
+
+
+def emu_huf_decompress(E, blocks, dst_sizes, four=True, desc=0):
+    E.emu_set_lane_order(desc)
+    n = len(blocks)
+    stride = max(16, (max(len(b) for b in blocks) + 15) // 16 * 16)
+    src = np.zeros((n, stride), dtype=np.uint8)
+    for i, b in enumerate(blocks):
+        src[i, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    sizes = np.array([len(b) for b in blocks], dtype=np.uint32)
+    ds = np.array(dst_sizes, dtype=np.uint32)
+    dstride = max(16, (int(ds.max()) + 15) // 16 * 16)
+    dst = np.zeros((n, dstride), dtype=np.uint8)
+    outs = np.zeros(n, dtype=np.int64)
+    E.emu_huf_decompress(src.ctypes.data, stride, sizes.ctypes.data, n, dst.ctypes.data, dstride, ds.ctypes.data,
+                         outs.ctypes.data, 1 if four else 0)
+    return [(bytes(dst[i, :outs[i]]) if outs[i] >= 0 else None, int(outs[i])) for i in range(n)]

@@ -1,0 +1,72 @@
+"""GPU parity tests for the standalone huff0 block coder through the C ABI: bytes equal to the oracle's
+huff0.Compress4X / Compress1X, error values, decompress inverse (BASELINE config 4)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from test_emu_huf0 import _blocks, orc_compress, orc_decompress
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def codec():
+    from compress_b200 import huff0
+    c = huff0.Codec()
+    yield c
+    c.close()
+
+
+def test_huf_compress_parity(codec, oracle_lib):
+    from compress_b200 import huff0
+    blocks = _blocks()
+    for four in (True, False):
+        got = codec.compress_blocks(blocks, four)
+        for i, (g, b) in enumerate(zip(got, blocks)):
+            w = orc_compress(b, four)
+            assert g[1] == w[1] and g[0] == w[0], (four, i, g[1], w[1])
+    with pytest.raises(huff0.ErrUseRLE):
+        codec.Compress4X(bytes(1000))
+    with pytest.raises(huff0.ErrIncompressible):
+        codec.Compress1X(bytes(np.random.default_rng(0).integers(0, 256, 5000, dtype=np.uint8)))
+    with pytest.raises(huff0.ErrTooBig):
+        codec.Compress4X(bytes(np.random.default_rng(0).integers(0, 4, 262144, dtype=np.uint8)))
+
+
+def test_huf_decompress(codec, oracle_lib):
+    from compress_b200 import huff0
+    blocks = _blocks()
+    for four in (True, False):
+        ok = [(orc_compress(b, four)[0], b) for b in blocks if orc_compress(b, four)[1] > 0]
+        got = codec.decompress_blocks([c for c, _ in ok], [len(b) for _, b in ok], four)
+        for (g, code), (_, b) in zip(got, ok):
+            assert code == len(b) and g == b
+        c0, b0 = ok[-1]
+        cases = [(c0, len(b0) - 1), (c0[:-1], len(b0)), (c0[:40], len(b0)), (bytes([200]) * 50, 100)]
+        res = codec.decompress_blocks([c for c, _ in cases], [d for _, d in cases], four)
+        for (g, code), (c, d) in zip(res, cases):
+            wcode, wout = orc_decompress(c, d, four)
+            assert (code < 0) == (wcode < 0)
+            if code >= 0:
+                assert g == wout
+    tw = H.golden("twain.txt")[:100000]
+    assert codec.Decompress4X(codec.Compress4X(tw), len(tw)) == tw
+    assert codec.Decompress1X(codec.Compress1X(tw[:5000]), 5000) == tw[:5000]
+    with pytest.raises(huff0.ErrCorrupt):
+        codec.Decompress4X(codec.Compress4X(tw)[:-7], len(tw))
+
+
+def test_huf_roundtrip_config4(codec):
+    # 512 blocks of 262143 bytes of the bench text (BASELINE config 4 shape, 128 MiB)
+    n, bs = 512, 262143
+    stride = 262144
+    src = H.synth_text_torch(n * stride, "cuda").view(n, stride)
+    sizes = torch.full((n,), bs, dtype=torch.int32, device="cuda")
+    comp, csz = codec.compress_device(src.view(-1), stride, sizes, four=True)
+    torch.cuda.synchronize()
+    assert int(csz.min()) > 0 and float(csz.sum()) / (n * bs) < 0.75
+    out, osz = codec.decompress_device(comp.view(-1), comp.stride(0), csz.to(torch.int32), sizes, stride, four=True)
+    torch.cuda.synchronize()
+    assert bool((osz == bs).all())
+    assert torch.equal(out[:, :bs], src[:, :bs])
