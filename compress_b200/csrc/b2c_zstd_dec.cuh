@@ -32,11 +32,14 @@ enum {
     DEC_ERR_SIZE = -10, DEC_ERR_UNSUPPORTED = -11
 };
 
-struct DecSym { uint32_t bits; uint32_t baseline; };   // bits = nbBits | addBits << 8 | newState << 16
+struct DecSym { uint32_t bits; uint32_t baseline; };   // in registers: bits = nbBits | addBits << 8 | newState << 16
+// in shared memory a table entry is one word: nbBits | symbol << 8 | newState << 16 (what buildDtable produces);
+// the symbol's (baseline, extra bits) come from a 64-entry per-CTA table (DecCta) at lookup time.
+struct DecCta { uint2 codeTab[3][64]; };   // x = baseline, y = extra bits
 
 struct DecWarp {
-    DecSym fse[3][1u << DEC_TLOG_MAX];     // per-block tables (LL, OF, ML)
-    DecSym pre[3][64];                     // predefined tables (built once per warp)
+    uint32_t fse[3][1u << DEC_TLOG_MAX];   // per-block tables (LL, OF, ML)
+    uint32_t pre[3][64];                   // predefined tables (built once per warp)
     uint32_t dtb[1u << DEC_TLOG_MAX];      // dtable before the transform: nbBits | symbol << 8 | newState << 16
     uint16_t hufDt[2048];
     int16_t norm[256];
@@ -47,7 +50,8 @@ struct DecWarp {
     uint32_t flag;
 };
 constexpr uint32_t DEC_WARP_BYTES = ((sizeof(DecWarp) + 15) / 16) * 16;
-constexpr uint32_t DEC_SMEM_BYTES = DEC_WARPS * DEC_WARP_BYTES;
+constexpr uint32_t DEC_CTA_BYTES = ((sizeof(DecCta) + 15) / 16) * 16;
+constexpr uint32_t DEC_SMEM_BYTES = DEC_WARPS * DEC_WARP_BYTES + DEC_CTA_BYTES;
 
 struct ZstdDecParams {
     // input i: src_base + (src_offsets ? src_offsets[i] : i * src_stride), src_sizes[i] bytes
@@ -62,48 +66,59 @@ struct ZstdDecParams {
 // ---- backward bit reader over global memory (zstd/bitreader.go semantics: exact consumption required).
 // The stream is a little-endian integer; `total` payload bits sit below the end mark; reads take bits from the top
 // down; bits below bit 0 read as zero (pos > total is the over-read condition the callers test).
-// A 64-bit window of the stream is cached in registers and refilled (two aligned 8-byte loads) every >= 57 bits.
+// `bits` holds the next `avail` bits left-aligned (next bit = MSB); 32 more are appended whenever a read would run
+// dry, from two aligned word loads (byte loads with zero fill at the two ends of the buffer).  All 32-bit arithmetic:
+// a stream is at most one compressed block (128 KiB).
 struct BrB {
-    const uint8_t *in; uint32_t len; int64_t total; int64_t pos;
-    uint64_t cbuf; int64_t cbase;    // cbuf = stream bits [cbase, cbase + 64)
+    const uint8_t *in; uint32_t len; uint32_t total; uint32_t pos;
+    uint64_t bits; uint32_t avail; int32_t nextByte;     // stream bytes below nextByte are not loaded yet
+    B2C_DEV uint32_t load32(int32_t idx) const {
+        if (idx >= 0 && (uint32_t)idx + 8 <= len) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(in + idx);
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(a & 3) * 8;
+            const uint32_t w0 = w[0];
+            return sh ? __funnelshift_r(w0, w[1], sh) : w0;
+        }
+        uint32_t v = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int32_t bi = idx + i;
+            if (bi >= 0 && (uint32_t)bi < len) v |= (uint32_t)in[bi] << (8 * i);
+        }
+        return v;
+    }
     B2C_DEV int init(const uint8_t *p, uint32_t n) {
-        in = p; len = n; total = 0; pos = 0; cbuf = 0; cbase = (int64_t)1 << 40;
+        in = p; len = n; total = 0; pos = 0; bits = 0; avail = 0; nextByte = 0;
         if (n < 1) return -1;
-        uint8_t v = p[n - 1];
+        const uint8_t v = p[n - 1];
         if (v == 0) return -1;
-        total = (int64_t)8 * (n - 1) + (int64_t)highbit32(v);
+        total = 8 * (n - 1) + highbit32(v);
+        const int32_t cbyte = (int32_t)((total + 7) >> 3) - 8;        // window = the 8 bytes ending at the top payload byte
+        const uint64_t win = (uint64_t)load32(cbyte) | ((uint64_t)load32(cbyte + 4) << 32);
+        const uint32_t k = (uint32_t)((int32_t)total - 8 * cbyte);    // payload bits inside the window: 57..64
+        bits = win << (64 - k);
+        avail = k; nextByte = cbyte;
         return 0;
     }
-    B2C_DEV void refill(int64_t top) {
-        // window = the 8 bytes ending at the byte that holds bit top-1
-        int64_t byteTop = (top + 7) >> 3;          // arithmetic shift: floor for negative values too
-        int64_t cbyte = byteTop - 8;
-        cbase = cbyte * 8;
-        if (cbyte >= 0 && cbyte + 16 <= (int64_t)len) {
-            const uint8_t *p = in + cbyte;
-            uintptr_t a = reinterpret_cast<uintptr_t>(p);
-            const uint64_t *w = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
-            uint32_t sh = (uint32_t)(a & 7) * 8;
-            uint64_t lo = w[0];
-            cbuf = sh ? ((lo >> sh) | (w[1] << (64 - sh))) : lo;
-        } else {
-            uint64_t acc = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                int64_t bi = cbyte + i;
-                if (bi >= 0 && bi < (int64_t)len) acc |= (uint64_t)in[bi] << (8 * i);
-            }
-            cbuf = acc;
-        }
+    B2C_DEV void refill32() {     // requires avail <= 32
+        const int32_t idx = nextByte - 4;
+        bits |= (uint64_t)load32(idx) << (32 - avail);
+        avail += 32; nextByte = idx;
     }
-    // peek n <= 32 bits at the current position
+    // next n bits, 1 <= n <= 32, without consuming them
     B2C_DEV uint32_t peek(uint32_t n) {
-        if (n == 0) return 0;
-        int64_t top = total - pos, lo = top - (int64_t)n;
-        if (lo < cbase || top > cbase + 64) refill(top);
-        return (uint32_t)((cbuf >> (uint32_t)(lo - cbase)) & ((1ull << n) - 1));
+        if (avail < n) refill32();
+        return (uint32_t)(bits >> (64 - n));
     }
-    B2C_DEV uint32_t read(uint32_t n) { uint32_t v = peek(n); pos += n; return v; }
+    // consume n bits; n <= the n of the preceding peek
+    B2C_DEV void skip(uint32_t n) { bits <<= n; avail -= n; pos += n; }
+    B2C_DEV uint32_t read(uint32_t n) {
+        if (n == 0) return 0;
+        const uint32_t v = peek(n);
+        skip(n);
+        return v;
+    }
     B2C_DEV bool finished() const { return pos >= total; }
 };
 
@@ -171,7 +186,7 @@ B2C_DEV int dec_read_ncount(const uint8_t *in, uint32_t len, uint32_t maxSymbol,
 
 // buildDtable (zstd/fse_decoder_generic.go:11-72, fse/decompress.go:193-258): serial spread by lane 0.
 // dtb[u] = nbBits | symbol << 8 | newState << 16
-B2C_DEV int dec_build_dtable(DecWarp *dw, uint32_t symbolLen, uint32_t tableLog, unsigned lane) {
+B2C_DEV int dec_build_dtable(DecWarp *dw, uint32_t *outTab, uint32_t symbolLen, uint32_t tableLog, unsigned lane) {
     uint32_t tableSize = 1u << tableLog;
     if (lane == 0) {
         int err = 0;
@@ -202,7 +217,7 @@ B2C_DEV int dec_build_dtable(DecWarp *dw, uint32_t symbolLen, uint32_t tableLog,
                 uint32_t newState = ((nextState << nBits) - tableSize) & 0xffff;
                 if (newState >= tableSize) err = 1;
                 if (newState == u && nBits == 0) err = 1;   // "newState == oldState and no bits"
-                dw->dtb[u] = nBits | ((uint32_t)symbol << 8) | (newState << 16);
+                outTab[u] = nBits | ((uint32_t)symbol << 8) | (newState << 16);
             }
         }
         dw->flag = (uint32_t)err;
@@ -233,21 +248,22 @@ B2C_DEV void dec_code_base(int which, uint32_t c, uint32_t *base, uint32_t *bits
 }
 B2C_DEV uint32_t dec_code_limit(int which) { return which == 0 ? 36u : (which == 1 ? 31u : 53u); }
 
-// transform (zstd/fse_decoder.go:282-299): dtb -> dt
-B2C_DEV int dec_transform(const uint32_t *dtb, DecSym *dt, uint32_t tableSize, int which, unsigned lane) {
+// transform (zstd/fse_decoder.go:282-299) only has to reject symbols without a (baseline, bits) entry: the table
+// keeps the symbol, the mapping is applied at lookup (dec_lookup).
+B2C_DEV int dec_check_symbols(const uint32_t *tab, uint32_t tableSize, int which, unsigned lane) {
     bool bad = false;
-    for (uint32_t i = lane; i < tableSize; i += 32) {
-        uint32_t e = dtb[i];
-        uint32_t sym = (e >> 8) & 0xff;
-        uint32_t base = 0, bits = 0;
-        if (sym >= dec_code_limit(which)) { bad = true; sym = 0; }
-        dec_code_base(which, sym, &base, &bits);
-        dt[i].bits = (e & 0xffff00ffu) | (bits << 8);
-        dt[i].baseline = base;
-    }
-    bool anyBad = __any_sync(FULLMASK, bad);
+    for (uint32_t i = lane; i < tableSize; i += 32) bad = bad || (((tab[i] >> 8) & 0xff) >= dec_code_limit(which));
+    const bool anyBad = __any_sync(FULLMASK, bad);
     __syncwarp();
     return anyBad ? -1 : 0;
+}
+B2C_DEV DecSym dec_lookup(const uint32_t *tab, const uint2 *codeTab, uint32_t state) {
+    const uint32_t e = tab[state];
+    const uint2 c = codeTab[(e >> 8) & 63];
+    DecSym r;
+    r.bits = (e & 0xffff00ffu) | (c.y << 8);
+    r.baseline = c.x;
+    return r;
 }
 
 B2C_DEV void dec_build_predef(DecWarp *dw, unsigned lane) {
@@ -260,8 +276,7 @@ B2C_DEV void dec_build_predef(DecWarp *dw, unsigned lane) {
         if (lane == 0)
             for (uint32_t i = 0; i < sl; i++) dw->norm[i] = which == 0 ? llN[i] : (which == 1 ? ofN[i] : mlN[i]);
         __syncwarp();
-        dec_build_dtable(dw, sl, tl, lane);
-        dec_transform(dw->dtb, dw->pre[which], 1u << tl, which, lane);
+        dec_build_dtable(dw, dw->pre[which], sl, tl, lane);
     }
 }
 
@@ -272,7 +287,7 @@ B2C_DEV int dec_fse_weights(DecWarp *dw, const uint8_t *in, uint32_t n, unsigned
     int hdr = dec_read_ncount(in, n, 255, 15, dw->norm, &symbolLen, &tableLog, lane);
     if (hdr < 0) return -1;
     if (tableLog > DEC_TLOG_MAX) return -2;
-    if (dec_build_dtable(dw, symbolLen, tableLog, lane)) return -1;
+    if (dec_build_dtable(dw, dw->dtb, symbolLen, tableLog, lane)) return -1;
     if ((uint32_t)hdr > n) return -1;
     BrB br;
     if (br.init(in + hdr, n - (uint32_t)hdr)) return -1;
@@ -379,7 +394,7 @@ B2C_DEV int dec_huf_stream(const uint16_t *dt, uint32_t tl, const uint8_t *src, 
     for (uint32_t i = 0; i < count; i++) {
         if (br.finished()) return -1;
         uint16_t e = dt[br.peek(tl)];
-        br.pos += (e & 0xff);
+        br.skip(e & 0xff);
         dst[i] = (uint8_t)(e >> 8);
     }
     return br.pos == br.total ? 0 : -1;
@@ -411,8 +426,8 @@ B2C_DEV int dec_huf_streams(const uint16_t *dt, uint32_t tl, const uint8_t *hs, 
 }
 
 // ---- the decoder: one warp, one input ---------------------------------------------------------------
-B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t cap, uint8_t *litbuf,
-                                  unsigned lane) {
+B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const DecCta *dc, const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t cap,
+                                  uint8_t *litbuf, unsigned lane) {
     uint32_t ip = 0;
     uint64_t total = 0;
 #define DFAIL(code) return (int64_t)(code)
@@ -473,7 +488,7 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, u
         // history.reset
         bool haveHuff = false;
         uint32_t hufLog = 0;
-        const DecSym *cur[3] = {nullptr, nullptr, nullptr};
+        const uint32_t *cur[3] = {nullptr, nullptr, nullptr};
         uint32_t tlog[3] = {0, 0, 0};
         int64_t rep0 = 1, rep1 = 4, rep2 = 8;
         uint8_t *out = dst + total;
@@ -580,10 +595,8 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, u
                             if (len < 1) DFAIL(DEC_ERR_CORRUPT);
                             uint32_t v = in[0]; in += 1; len -= 1;
                             if (v >= dec_code_limit(i)) DFAIL(DEC_ERR_CORRUPT);
-                            uint32_t base, bits;
-                            dec_code_base(i, v, &base, &bits);
                             __syncwarp();
-                            if (lane == 0) { dw->fse[i][0].bits = bits << 8; dw->fse[i][0].baseline = base; }
+                            if (lane == 0) dw->fse[i][0] = v << 8;
                             __syncwarp();
                             cur[i] = dw->fse[i]; tlog[i] = 0;
                         } else if (mode == 2) {
@@ -593,8 +606,8 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, u
                             if (used < 0 || (uint32_t)used > len) DFAIL(DEC_ERR_CORRUPT);
                             in += used; len -= (uint32_t)used;
                             cur[i] = nullptr;
-                            if (dec_build_dtable(dw, symbolLen, tl, lane)) DFAIL(DEC_ERR_CORRUPT);
-                            if (dec_transform(dw->dtb, dw->fse[i], 1u << tl, i, lane)) DFAIL(DEC_ERR_CORRUPT);
+                            if (dec_build_dtable(dw, dw->fse[i], symbolLen, tl, lane)) DFAIL(DEC_ERR_CORRUPT);
+                            if (dec_check_symbols(dw->fse[i], 1u << tl, i, lane)) DFAIL(DEC_ERR_CORRUPT);
                             cur[i] = dw->fse[i]; tlog[i] = tl;
                         }  // mode 3: repeat, keep cur[i]
                     }
@@ -602,9 +615,9 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, u
                     // ---- decodeSync (seqdec.go:221-445)
                     BrB br;
                     if (br.init(in, len)) DFAIL(DEC_ERR_CORRUPT);
-                    DecSym llS = cur[0][br.read(tlog[0])];
-                    DecSym ofS = cur[1][br.read(tlog[1])];
-                    DecSym mlS = cur[2][br.read(tlog[2])];
+                    DecSym llS = dec_lookup(cur[0], dc->codeTab[0], br.read(tlog[0]));
+                    DecSym ofS = dec_lookup(cur[1], dc->codeTab[1], br.read(tlog[1]));
+                    DecSym mlS = dec_lookup(cur[2], dc->codeTab[2], br.read(tlog[2]));
                     const uint64_t startSize = o;
                     const uint64_t maxBlockSize = windowSize < DEC_MAX_BLOCK ? windowSize : DEC_MAX_BLOCK;
                     uint32_t litPos = 0;
@@ -657,9 +670,9 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, u
                         if (i == 0) break;
                         uint32_t nl = llS.bits & 0xff, nm = mlS.bits & 0xff, no = ofS.bits & 0xff;
                         uint32_t bl = br.read(nl), bm = br.read(nm), bo = br.read(no);
-                        llS = cur[0][((llS.bits >> 16) + bl) & ((1u << DEC_TLOG_MAX) - 1)];
-                        mlS = cur[2][((mlS.bits >> 16) + bm) & ((1u << DEC_TLOG_MAX) - 1)];
-                        ofS = cur[1][((ofS.bits >> 16) + bo) & ((1u << DEC_TLOG_MAX) - 1)];
+                        llS = dec_lookup(cur[0], dc->codeTab[0], ((llS.bits >> 16) + bl) & ((1u << DEC_TLOG_MAX) - 1));
+                        mlS = dec_lookup(cur[2], dc->codeTab[2], ((mlS.bits >> 16) + bm) & ((1u << DEC_TLOG_MAX) - 1));
+                        ofS = dec_lookup(cur[1], dc->codeTab[1], ((ofS.bits >> 16) + bo) & ((1u << DEC_TLOG_MAX) - 1));
                     }
                     uint32_t rest = litRegen - litPos;
                     if ((uint64_t)rest + o - startSize > maxBlockSize) DFAIL(DEC_ERR_CORRUPT);
@@ -738,14 +751,24 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const uint8_t *src, uint32_t n, u
 B2C_DEV void zstd_decode_warp(uint8_t *smem, const ZstdDecParams &P, uint32_t warpGlobal, uint32_t totalWarps) {
     const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     DecWarp *dw = reinterpret_cast<DecWarp *>(smem + w * DEC_WARP_BYTES);
+    DecCta *dc = reinterpret_cast<DecCta *>(smem + DEC_WARPS * DEC_WARP_BYTES);
     uint8_t *litbuf = P.lit_scratch + (uint64_t)warpGlobal * DEC_LIT_SCRATCH;
+    // code -> (baseline, extra bits) maps, one copy per CTA
+    for (uint32_t i = threadIdx.x; i < 3 * 64; i += blockDim.x) {
+        const int which = (int)(i / 64);
+        const uint32_t c = i % 64;
+        uint32_t base = 0, bits = 0;
+        if (c < dec_code_limit(which)) dec_code_base(which, c, &base, &bits);
+        dc->codeTab[which][c] = make_uint2(base, bits);
+    }
+    __syncthreads();
     dec_build_predef(dw, lane);
     for (uint32_t c = warpGlobal; c < P.nchunks; c += totalWarps) {
         const uint8_t *src = P.src_base + (P.src_offsets ? P.src_offsets[c] : (uint64_t)c * P.src_stride);
         uint8_t *dst = P.dst_base + (P.dst_offsets ? P.dst_offsets[c] : (uint64_t)c * P.dst_stride);
         uint32_t cap = P.dst_caps ? P.dst_caps[c] : P.dst_cap;
         __syncwarp();
-        int64_t r = zstd_decode_input(dw, src, P.src_sizes[c], dst, cap, litbuf, lane);
+        int64_t r = zstd_decode_input(dw, dc, src, P.src_sizes[c], dst, cap, litbuf, lane);
         __syncwarp();
         if (lane == 0) P.out_sizes[c] = r;
     }
