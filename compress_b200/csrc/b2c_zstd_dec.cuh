@@ -621,58 +621,112 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const DecCta *dc, const uint8_t *
                     const uint64_t startSize = o;
                     const uint64_t maxBlockSize = windowSize < DEC_MAX_BLOCK ? windowSize : DEC_MAX_BLOCK;
                     uint32_t litPos = 0;
-                    for (int32_t i = (int32_t)nSeqs - 1; i >= 0; i--) {
-                        if (br.pos > br.total) DFAIL(DEC_ERR_CORRUPT);
-                        int64_t ll = llS.baseline, ml = mlS.baseline, mo = ofS.baseline;
-                        uint32_t moB = (ofS.bits >> 8) & 0xff;
-                        mo += br.read(moB);
-                        ml += br.read((mlS.bits >> 8) & 0xff);
-                        ll += br.read((llS.bits >> 8) & 0xff);
-                        if (moB > 1) { rep2 = rep1; rep1 = rep0; rep0 = mo; }
-                        else {
-                            if (ll == 0) mo++;
-                            if (mo == 0) mo = rep0;
+                    // Sequences are handled 32 at a time.  Step 1 (every lane, redundantly): the serial bitstream walk;
+                    // lane j keeps sequence j.  Step 2: a warp scan places them; all literal runs are copied at once;
+                    // matches are copied in waves -- a match runs as soon as its source ends before the destination of
+                    // every match of the batch that is still pending (seqdec.go:221-445 executes them one by one).
+                    for (uint32_t base = 0; base < nSeqs; base += 32) {
+                        const uint32_t want = (nSeqs - base < 32) ? nSeqs - base : 32;
+                        uint32_t cnt = want;
+                        uint32_t myLL = 0, myML = 0, myMO = 0;
+                        bool myOver = false;
+                        for (uint32_t j = 0; j < want; j++) {
+                            if (br.pos > br.total) { if (lane == j) myOver = true; cnt = j + 1; break; }
+                            int64_t ll = llS.baseline, ml = mlS.baseline, mo = ofS.baseline;
+                            const uint32_t moB = (ofS.bits >> 8) & 0xff;
+                            mo += br.read(moB);
+                            ml += br.read((mlS.bits >> 8) & 0xff);
+                            ll += br.read((llS.bits >> 8) & 0xff);
+                            if (moB > 1) { rep2 = rep1; rep1 = rep0; rep0 = mo; }
                             else {
-                                int64_t temp = (mo == 3) ? rep0 - 1 : (mo == 1 ? rep1 : rep2);
-                                if (temp == 0) temp = 1;
-                                if (mo != 1) rep2 = rep1;
-                                rep1 = rep0; rep0 = temp; mo = temp;
-                            }
-                        }
-                        if ((uint64_t)ll > (uint64_t)(litRegen - litPos)) DFAIL(DEC_ERR_CORRUPT);
-                        uint64_t size = (uint64_t)ll + (uint64_t)ml + o;
-                        if (size - startSize > maxBlockSize) DFAIL(DEC_ERR_CORRUPT);
-                        if (ml > (int64_t)DEC_MAX_MATCHLEN) DFAIL(DEC_ERR_CORRUPT);
-                        if (size > outCap) DFAIL(DEC_ERR_DST);
-                        for (uint32_t k = lane; k < (uint32_t)ll; k += 32) out[o + k] = literals[litPos + k];
-                        o += (uint64_t)ll; litPos += (uint32_t)ll;
-                        if (mo == 0 && ml > 0) DFAIL(DEC_ERR_CORRUPT);
-                        if ((uint64_t)mo > o || (uint64_t)mo > windowSize) DFAIL(DEC_ERR_CORRUPT);
-                        if (ml > 0) {
-                            __syncwarp();   // the literals just written may be match source
-                            const uint8_t *from = out + o - mo;
-                            if ((uint64_t)mo >= (uint64_t)ml || mo >= 32) {
-                                // batches of 32 bytes never read a byte written by the same batch when mo >= 32;
-                                // when mo >= ml the source range is entirely before the destination
-                                for (uint32_t k0 = 0; k0 < (uint32_t)ml; k0 += 32) {
-                                    uint32_t k = k0 + lane;
-                                    if (k < (uint32_t)ml) out[o + k] = from[k];
-                                    if ((uint64_t)mo < (uint64_t)ml) __syncwarp();
+                                if (ll == 0) mo++;
+                                if (mo == 0) mo = rep0;
+                                else {
+                                    int64_t temp = (mo == 3) ? rep0 - 1 : (mo == 1 ? rep1 : rep2);
+                                    if (temp == 0) temp = 1;
+                                    if (mo != 1) rep2 = rep1;
+                                    rep1 = rep0; rep0 = temp; mo = temp;
                                 }
-                            } else {
-                                // short period: byte k equals from[k mod mo]
-                                uint32_t m32 = (uint32_t)mo;
-                                for (uint32_t k = lane; k < (uint32_t)ml; k += 32) out[o + k] = from[k % m32];
                             }
-                            o += (uint64_t)ml;
+                            if (lane == j) { myLL = (uint32_t)ll; myML = (uint32_t)ml; myMO = (uint32_t)mo; }
+                            if (base + j + 1 == nSeqs) break;
+                            const uint32_t nl = llS.bits & 0xff, nm = mlS.bits & 0xff, no = ofS.bits & 0xff;
+                            const uint32_t bl = br.read(nl), bm = br.read(nm), bo = br.read(no);
+                            llS = dec_lookup(cur[0], dc->codeTab[0], ((llS.bits >> 16) + bl) & ((1u << DEC_TLOG_MAX) - 1));
+                            mlS = dec_lookup(cur[2], dc->codeTab[2], ((mlS.bits >> 16) + bm) & ((1u << DEC_TLOG_MAX) - 1));
+                            ofS = dec_lookup(cur[1], dc->codeTab[1], ((ofS.bits >> 16) + bo) & ((1u << DEC_TLOG_MAX) - 1));
+                        }
+                        // ---- placement (ll, ml < 2^18 each, 32 of them: no overflow in 32 bits)
+                        const bool mine = lane < cnt;
+                        const uint32_t lenIncl = warp_scan_incl(mine ? myLL + myML : 0u);
+                        const uint32_t llIncl = warp_scan_incl(mine ? myLL : 0u);
+                        const uint64_t myOut = o + (lenIncl - (myLL + myML));        // where my literals go
+                        const uint32_t myLit = litPos + (llIncl - myLL);
+                        const uint64_t myDst = myOut + myLL;                          // where my match goes
+                        // ---- the reference's per-sequence checks, in its order; the first failing sequence decides
+                        int err = 0;
+                        if (mine) {
+                            if (myOver) err = DEC_ERR_CORRUPT;
+                            else if (myLit > litRegen || myLL > litRegen - myLit) err = DEC_ERR_CORRUPT;
+                            else if (myDst + myML - startSize > maxBlockSize) err = DEC_ERR_CORRUPT;
+                            else if (myML > DEC_MAX_MATCHLEN) err = DEC_ERR_CORRUPT;
+                            else if (myDst + myML > outCap) err = DEC_ERR_DST;
+                            else if (myMO == 0 && myML > 0) err = DEC_ERR_CORRUPT;
+                            else if ((uint64_t)myMO > myDst || (uint64_t)myMO > windowSize) err = DEC_ERR_CORRUPT;
+                        }
+                        const unsigned bad = __ballot_sync(FULLMASK, err != 0);
+                        if (bad) DFAIL(__shfl_sync(FULLMASK, err, __ffs((int)bad) - 1));
+                        // ---- literal runs: short ones by their lane, long ones by the warp
+                        const bool longLit = mine && myLL >= 96;
+                        if (mine && !longLit) for (uint32_t k = 0; k < myLL; k++) out[myOut + k] = literals[myLit + k];
+                        for (unsigned m = __ballot_sync(FULLMASK, longLit); m; m &= m - 1) {
+                            const int f = __ffs((int)m) - 1;
+                            const uint64_t fo = __shfl_sync(FULLMASK, myOut, f);
+                            const uint32_t fl = __shfl_sync(FULLMASK, myLit, f), fn = __shfl_sync(FULLMASK, myLL, f);
+                            for (uint32_t k = lane; k < fn; k += 32) out[fo + k] = literals[fl + k];
                         }
                         __syncwarp();
-                        if (i == 0) break;
-                        uint32_t nl = llS.bits & 0xff, nm = mlS.bits & 0xff, no = ofS.bits & 0xff;
-                        uint32_t bl = br.read(nl), bm = br.read(nm), bo = br.read(no);
-                        llS = dec_lookup(cur[0], dc->codeTab[0], ((llS.bits >> 16) + bl) & ((1u << DEC_TLOG_MAX) - 1));
-                        mlS = dec_lookup(cur[2], dc->codeTab[2], ((mlS.bits >> 16) + bm) & ((1u << DEC_TLOG_MAX) - 1));
-                        ofS = dec_lookup(cur[1], dc->codeTab[1], ((ofS.bits >> 16) + bo) & ((1u << DEC_TLOG_MAX) - 1));
+                        // ---- matches in waves
+                        bool pending = mine && myML > 0;
+                        const uint64_t srcEnd = (myMO >= myML) ? myDst - myMO + myML : myDst;   // self-overlap: source ends at dst
+                        for (;;) {
+                            uint64_t key = pending ? myDst : ~0ull;
+                            uint32_t khi = (uint32_t)(key >> 32), klo = (uint32_t)key;
+                            // 64-bit minimum over the warp
+#pragma unroll
+                            for (int d = 16; d > 0; d >>= 1) {
+                                const uint32_t ohi = __shfl_xor_sync(FULLMASK, khi, d), olo = __shfl_xor_sync(FULLMASK, klo, d);
+                                if (ohi < khi || (ohi == khi && olo < klo)) { khi = ohi; klo = olo; }
+                            }
+                            const uint64_t minDst = ((uint64_t)khi << 32) | klo;
+                            if (minDst == ~0ull) break;
+                            const bool ready = pending && (srcEnd <= minDst || myDst == minDst);
+                            const bool longM = ready && myML >= 96;
+                            if (ready && !longM) {
+                                const uint8_t *from = out + myDst - myMO;
+                                for (uint32_t k = 0; k < myML; k++) out[myDst + k] = from[k];
+                            }
+                            for (unsigned m = __ballot_sync(FULLMASK, longM); m; m &= m - 1) {
+                                const int f = __ffs((int)m) - 1;
+                                const uint64_t fd = __shfl_sync(FULLMASK, myDst, f);
+                                const uint32_t fo = __shfl_sync(FULLMASK, myMO, f), fn = __shfl_sync(FULLMASK, myML, f);
+                                const uint8_t *from = out + fd - fo;
+                                if (fo >= fn || fo >= 32) {
+                                    for (uint32_t k0 = 0; k0 < fn; k0 += 32) {
+                                        const uint32_t k = k0 + lane;
+                                        if (k < fn) out[fd + k] = from[k];
+                                        if (fo < fn) __syncwarp();
+                                    }
+                                } else {
+                                    for (uint32_t k = lane; k < fn; k += 32) out[fd + k] = from[k % fo];
+                                }
+                                __syncwarp();
+                            }
+                            if (ready) pending = false;
+                            __syncwarp();
+                        }
+                        o += __shfl_sync(FULLMASK, lenIncl, 31);
+                        litPos += __shfl_sync(FULLMASK, llIncl, 31);
                     }
                     uint32_t rest = litRegen - litPos;
                     if ((uint64_t)rest + o - startSize > maxBlockSize) DFAIL(DEC_ERR_CORRUPT);
