@@ -122,7 +122,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nchunks", type=int, default=NCHUNKS)
-    ap.add_argument("--e2e-chunks", type=int, default=8288, help="chunks per e2e step (14 batches of 4 x 148 chunks, 518 MiB)")
+    ap.add_argument("--e2e-chunks", type=int, default=8288, help="chunks per e2e step (7 batches of 8 x 148 chunks, 518 MiB)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -168,7 +168,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from compress_b200 import zstd
-    enc = zstd.Encoder(device=local_rank, max_chunks=592)  # host-path batch: 4 chunks per SM (short pipeline fill and drain)
+    enc = zstd.Encoder(device=local_rank, max_chunks=1184)  # host-path batch: 8 chunks per SM
     n = args.nchunks
     src = H.synth_text_torch(n * CHUNK, dev, seed=1000 + rank)
     dst = torch.empty((n, zstd.SLOT), dtype=torch.uint8, device=dev)

@@ -422,7 +422,23 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
     CK(cudaSetDevice(ctx->device));
     const size_t nchunks = src_bytes == 0 ? 1 : (src_bytes + chunk_size - 1) / chunk_size;
     const size_t B = ctx->max_chunks;
-    const size_t nb = (nchunks + B - 1) / B;
+    // Batch schedule: full batches, then a tail that halves down to about one chunk per SM.  The H2D stream is the
+    // bottleneck of the pipeline, so the time after the last H2D copy (kernels + D2H of the last batch) is pure
+    // overhead; a small last batch keeps it short.
+    std::vector<size_t> bstart, bcount;
+    {
+        size_t c0 = 0, rem = nchunks;
+        const size_t floorB = (size_t)ctx->sm_count < B ? (size_t)ctx->sm_count : B;
+        while (rem > 0) {
+            size_t m;
+            if (rem > B) m = B;
+            else if (rem > 2 * floorB) m = rem / 2;
+            else m = rem;
+            bstart.push_back(c0); bcount.push_back(m);
+            c0 += m; rem -= m;
+        }
+    }
+    const size_t nb = bcount.size();
     cudaStream_t st_c = ctx->stream, st_in = ctx->stream2, st_out = ctx->stream3;
     struct Slot { uint8_t *d_in, *d_out, *d_packed; int64_t *d_sizes, *h_sizes; uint64_t *d_off;
                   uint32_t *d_ss, *h_ss; } slot[2] = {
@@ -434,7 +450,7 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
     auto finish = [&](size_t b) -> int {
         const int sl = (int)(b & 1);
         Slot &S = slot[sl];
-        size_t c0 = b * B, m = (nchunks - c0 < B) ? nchunks - c0 : B;
+        size_t c0 = bstart[b], m = bcount[b];
         if (cudaEventSynchronize(ctx->ev[sl]) != cudaSuccess) return B2C_ERR_CUDA;
         const int64_t *h_sz = S.h_sizes;
         const uint64_t *h_off = reinterpret_cast<const uint64_t *>(S.h_sizes + m);
@@ -454,7 +470,7 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
     for (size_t b = 0; b < nb; b++) {
         const int sl = (int)(b & 1);
         Slot &S = slot[sl];
-        size_t c0 = b * B, m = (nchunks - c0 < B) ? nchunks - c0 : B;
+        size_t c0 = bstart[b], m = bcount[b];
         size_t off = c0 * (size_t)chunk_size;
         size_t bytes = (off + m * (size_t)chunk_size <= src_bytes) ? m * (size_t)chunk_size : src_bytes - off;
         // H2D: the input slot is free once the kernels of batch b-2 have run

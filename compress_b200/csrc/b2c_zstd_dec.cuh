@@ -71,7 +71,8 @@ struct ZstdDecParams {
 // a stream is at most one compressed block (128 KiB).
 struct BrB {
     const uint8_t *in; uint32_t len; uint32_t total; uint32_t pos;
-    uint64_t bits; uint32_t avail; int32_t nextByte;     // stream bytes below nextByte are not loaded yet
+    uint64_t bits; uint32_t avail; int32_t nextByte;     // stream bytes below nextByte are not in `bits` yet
+    uint32_t ahead;                                      // the 32 bits below nextByte, requested one refill early
     B2C_DEV uint32_t load32(int32_t idx) const {
         if (idx >= 0 && (uint32_t)idx + 8 <= len) {
             const uintptr_t a = reinterpret_cast<uintptr_t>(in + idx);
@@ -89,7 +90,7 @@ struct BrB {
         return v;
     }
     B2C_DEV int init(const uint8_t *p, uint32_t n) {
-        in = p; len = n; total = 0; pos = 0; bits = 0; avail = 0; nextByte = 0;
+        in = p; len = n; total = 0; pos = 0; bits = 0; avail = 0; nextByte = 0; ahead = 0;
         if (n < 1) return -1;
         const uint8_t v = p[n - 1];
         if (v == 0) return -1;
@@ -99,12 +100,13 @@ struct BrB {
         const uint32_t k = (uint32_t)((int32_t)total - 8 * cbyte);    // payload bits inside the window: 57..64
         bits = win << (64 - k);
         avail = k; nextByte = cbyte;
+        ahead = load32(cbyte - 4);
         return 0;
     }
     B2C_DEV void refill32() {     // requires avail <= 32
-        const int32_t idx = nextByte - 4;
-        bits |= (uint64_t)load32(idx) << (32 - avail);
-        avail += 32; nextByte = idx;
+        bits |= (uint64_t)ahead << (32 - avail);
+        avail += 32; nextByte -= 4;
+        ahead = load32(nextByte - 4);
     }
     // next n bits, 1 <= n <= 32, without consuming them
     B2C_DEV uint32_t peek(uint32_t n) {
@@ -635,8 +637,12 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const DecCta *dc, const uint8_t *
                             int64_t ll = llS.baseline, ml = mlS.baseline, mo = ofS.baseline;
                             const uint32_t moB = (ofS.bits >> 8) & 0xff;
                             mo += br.read(moB);
-                            ml += br.read((mlS.bits >> 8) & 0xff);
-                            ll += br.read((llS.bits >> 8) & 0xff);
+                            {   // match-length and literal-length extra bits in one read (<= 16 + 16)
+                                const uint32_t nML = (mlS.bits >> 8) & 0xff, nLL = (llS.bits >> 8) & 0xff;
+                                const uint32_t both = br.read(nML + nLL);
+                                ml += both >> nLL;
+                                ll += both & ((1u << nLL) - 1);
+                            }
                             if (moB > 1) { rep2 = rep1; rep1 = rep0; rep0 = mo; }
                             else {
                                 if (ll == 0) mo++;
@@ -651,7 +657,8 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const DecCta *dc, const uint8_t *
                             if (lane == j) { myLL = (uint32_t)ll; myML = (uint32_t)ml; myMO = (uint32_t)mo; }
                             if (base + j + 1 == nSeqs) break;
                             const uint32_t nl = llS.bits & 0xff, nm = mlS.bits & 0xff, no = ofS.bits & 0xff;
-                            const uint32_t bl = br.read(nl), bm = br.read(nm), bo = br.read(no);
+                            const uint32_t all = br.read(nl + nm + no);      // <= 9 + 9 + 8 state bits in one read
+                            const uint32_t bl = all >> (nm + no), bm = (all >> no) & ((1u << nm) - 1), bo = all & ((1u << no) - 1);
                             llS = dec_lookup(cur[0], dc->codeTab[0], ((llS.bits >> 16) + bl) & ((1u << DEC_TLOG_MAX) - 1));
                             mlS = dec_lookup(cur[2], dc->codeTab[2], ((mlS.bits >> 16) + bm) & ((1u << DEC_TLOG_MAX) - 1));
                             ofS = dec_lookup(cur[1], dc->codeTab[1], ((ofS.bits >> 16) + bo) & ((1u << DEC_TLOG_MAX) - 1));

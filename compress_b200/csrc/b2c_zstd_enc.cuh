@@ -374,14 +374,18 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         bool scanning = p < pend, waiting = false;
         uint64_t cv = scanning ? ld64u(src, p) : 0ull;
         for (;;) {
-            if (scanning) {
-                const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
-                cand = E[enc_hash6(c_lo, c_hi) >> (32 - ENC_EBITS)];
-                if (cand < p && ld32u(src, cand) == c_lo) { waiting = true; scanning = false; }
-                else {
-                    p++;
-                    cv = (cv >> 8) | ((uint64_t)src[p + 7] << 56);
-                    scanning = p < pend;
+            // four probe steps between two looks at the warp state (the votes are pure overhead for the scan)
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (scanning) {
+                    const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
+                    cand = E[enc_hash6(c_lo, c_hi) >> (32 - ENC_EBITS)];
+                    if (cand < p && ld32u(src, cand) == c_lo) { waiting = true; scanning = false; }
+                    else {
+                        p++;
+                        cv = (cv >> 8) | ((uint64_t)src[p + 7] << 56);
+                        scanning = p < pend;
+                    }
                 }
             }
             const unsigned wm = __ballot_sync(FULLMASK, waiting);
