@@ -467,29 +467,39 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
         out_pos += total;
         return B2C_OK;
     };
-    for (size_t b = 0; b < nb; b++) {
+    // H2D of batch b into its slot; the slot's input buffer is free once the kernels of batch b-2 have run
+    std::vector<const uint32_t *> bss(nb, nullptr);
+    auto upload = [&](size_t b) -> int {
         const int sl = (int)(b & 1);
         Slot &S = slot[sl];
         size_t c0 = bstart[b], m = bcount[b];
         size_t off = c0 * (size_t)chunk_size;
         size_t bytes = (off + m * (size_t)chunk_size <= src_bytes) ? m * (size_t)chunk_size : src_bytes - off;
-        // H2D: the input slot is free once the kernels of batch b-2 have run
         if (b >= 2) CK(cudaStreamWaitEvent(st_in, ctx->ev[sl], 0));
         if (bytes) CK(cudaMemcpyAsync(S.d_in, (const uint8_t *)h_src + off, bytes, cudaMemcpyHostToDevice, st_in));
-        const uint32_t *d_ss = nullptr;
         if (bytes != m * (size_t)chunk_size) {  // ragged last chunk (or empty input): explicit sizes
             for (size_t i = 0; i < m; i++) {
                 size_t o = i * (size_t)chunk_size;
                 S.h_ss[i] = (uint32_t)(o >= bytes ? 0 : (bytes - o < chunk_size ? bytes - o : chunk_size));
             }
             CK(cudaMemcpyAsync(S.d_ss, S.h_ss, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st_in));
-            d_ss = S.d_ss;
+            bss[b] = S.d_ss;
         }
         CK(cudaEventRecord(ctx->ev_in[sl], st_in));
+        return B2C_OK;
+    };
+    // The copy of batch b+2 is queued before the host waits for batch b-1, so the H2D engine (the bottleneck) always
+    // has the next copy in its queue.
+    { int r0 = upload(0); if (r0) return r0; }
+    if (nb > 1) { int r1 = upload(1); if (r1) return r1; }
+    for (size_t b = 0; b < nb; b++) {
+        const int sl = (int)(b & 1);
+        Slot &S = slot[sl];
+        size_t m = bcount[b];
         // kernels: need the input; the packed-output slot is free once batch b-2's D2H copy is done
         CK(cudaStreamWaitEvent(st_c, ctx->ev_in[sl], 0));
         if (b >= 2) CK(cudaStreamWaitEvent(st_c, ctx->ev_out[sl], 0));
-        int r = launch_encode(ctx, level, flags, S.d_in, chunk_size, d_ss, chunk_size, S.d_out, kSlot, S.d_sizes,
+        int r = launch_encode(ctx, level, flags, S.d_in, chunk_size, bss[b], chunk_size, S.d_out, kSlot, S.d_sizes,
                               (uint32_t)m, nullptr, nullptr, nullptr, 0, st_c, nullptr, sl);
         if (r) return r;
         b2c_scan_sizes_kernel<<<1, 1024, 0, st_c>>>(S.d_sizes, S.d_off, (uint32_t)m);
@@ -498,6 +508,7 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
         CK(cudaMemcpyAsync(S.h_sizes, S.d_sizes, m * sizeof(int64_t), cudaMemcpyDeviceToHost, st_c));
         CK(cudaMemcpyAsync(S.h_sizes + m, S.d_off, (m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st_c));
         CK(cudaEventRecord(ctx->ev[sl], st_c));
+        if (b + 2 < nb) { int r3 = upload(b + 2); if (r3) return r3; }
         if (b >= 1) { int r2 = finish(b - 1); if (r2) return r2; }
     }
     { int r2 = finish(nb - 1); if (r2) return r2; }

@@ -122,3 +122,32 @@ def test_full_size_properties(enc):
     assert (sizes == outs_h[:512]).all()
     r, dec = H.oracle_decode(bytes(buf[:total].numpy()), 512 * 65536 + 64)
     assert r == 512 * 65536 and dec == bytes(host.numpy())
+
+
+def test_packed_pipeline_many_batches(enc):
+    """b2c_zstd_encode_packed with many batches (tapered tail, ragged last chunk): frame table and bytes equal the
+    device-resident path, and the stream decodes back."""
+    from compress_b200 import zstd
+    n, last = 1237, 12345
+    src = H.synth_text_torch(n * 65536, "cuda", seed=99)
+    src[5 * 65536:6 * 65536] = 0
+    total_in = (n - 1) * 65536 + last
+    host = src[:total_in].cpu().pin_memory()
+    small = zstd.Encoder(max_chunks=100)
+    buf, total, sizes, offs = small.encode_packed(host)
+    small.close()
+    sz = torch.full((n,), 65536, dtype=torch.int32, device="cuda")
+    sz[-1] = last
+    dst, outs = enc.encode_device(src, sz)
+    torch.cuda.synchronize()
+    outs_h = outs.cpu().numpy()
+    assert (sizes == outs_h).all()
+    assert offs[0] == 0 and (np.diff(offs.astype(np.int64)) == sizes[:-1]).all() and int(offs[-1] + sizes[-1]) == total
+    dsth = dst.cpu().numpy()
+    packed = buf[:total].numpy()
+    for i in (0, 1, 5, 99, 100, 101, 617, 618, 1000, n - 2, n - 1):
+        assert bytes(packed[int(offs[i]):int(offs[i] + sizes[i])]) == bytes(dsth[i, :int(sizes[i])]), i
+    dec = zstd.Decoder()
+    out = dec.DecodeAll(bytes(packed), size_hint=total_in + 64)
+    dec.close()
+    assert out == bytes(host.numpy())
