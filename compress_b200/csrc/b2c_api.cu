@@ -422,13 +422,14 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
     CK(cudaSetDevice(ctx->device));
     const size_t nchunks = src_bytes == 0 ? 1 : (src_bytes + chunk_size - 1) / chunk_size;
     const size_t B = ctx->max_chunks;
-    // Batch schedule: full batches, then a tail that halves down to about one chunk per SM.  The H2D stream is the
+    // Batch schedule: full batches, then a tail that halves down to about four chunks per SM.  The H2D stream is the
     // bottleneck of the pipeline, so the time after the last H2D copy (kernels + D2H of the last batch) is pure
     // overhead; a small last batch keeps it short.
     std::vector<size_t> bstart, bcount;
     {
         size_t c0 = 0, rem = nchunks;
-        const size_t floorB = (size_t)ctx->sm_count < B ? (size_t)ctx->sm_count : B;
+        // (below about four chunks per SM a batch is bound by the latency of its serial kernels, not by its size)
+        const size_t floorB = (size_t)ctx->sm_count * 4 < B ? (size_t)ctx->sm_count * 4 : B;
         while (rem > 0) {
             size_t m;
             if (rem > B) m = B;
