@@ -14,6 +14,12 @@
 #endif
 
 #define B2C_DEV __device__ __forceinline__
+// read-only global load (data written by an earlier kernel): lets the compiler batch loads across loop iterations
+#ifdef B2C_EMU
+#define B2C_LDG(p) (*(p))
+#else
+#define B2C_LDG(p) __ldg(p)
+#endif
 #define FULLMASK 0xffffffffu
 
 namespace b2c {

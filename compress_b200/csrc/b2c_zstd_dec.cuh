@@ -389,16 +389,36 @@ B2C_DEV int dec_huf_read_table(DecWarp *dw, const uint8_t *in, uint32_t n, uint3
     return (int)(1 + iSize);
 }
 
-// one Huffman stream, one lane: exactly `count` symbols, exact consumption (huff0/decompress_generic.go)
+// one Huffman stream, one lane: exactly `count` symbols, exact consumption (huff0/decompress_generic.go).
+// Symbols are produced four at a time and leave as one aligned 32-bit store; an over-read shows up as pos > total at
+// the end (bits below the start of the stream read as zero), so the loop itself needs no per-symbol end test.
 B2C_DEV int dec_huf_stream(const uint16_t *dt, uint32_t tl, const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t count) {
     BrB br;
     if (br.init(src, n)) return -1;
-    for (uint32_t i = 0; i < count; i++) {
+    uint32_t i = 0;
+#define HUF_ONE(out)                                                                                   \
+    do {                                                                                               \
+        const uint16_t e_ = dt[br.peek(tl)];                                                           \
+        br.skip(e_ & 0xff);                                                                            \
+        (out) = (uint32_t)(e_ >> 8);                                                                   \
+    } while (0)
+    while (i < count && ((reinterpret_cast<uintptr_t>(dst + i) & 3) != 0)) {
         if (br.finished()) return -1;
-        uint16_t e = dt[br.peek(tl)];
-        br.skip(e & 0xff);
-        dst[i] = (uint8_t)(e >> 8);
+        uint32_t s0; HUF_ONE(s0);
+        dst[i++] = (uint8_t)s0;
     }
+    for (; i + 4 <= count; i += 4) {
+        if (br.finished()) return -1;
+        uint32_t s0, s1, s2, s3;
+        HUF_ONE(s0); HUF_ONE(s1); HUF_ONE(s2); HUF_ONE(s3);
+        *reinterpret_cast<uint32_t *>(dst + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+    }
+    for (; i < count; i++) {
+        if (br.finished()) return -1;
+        uint32_t s0; HUF_ONE(s0);
+        dst[i] = (uint8_t)s0;
+    }
+#undef HUF_ONE
     return br.pos == br.total ? 0 : -1;
 }
 

@@ -944,9 +944,9 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         uint32_t mybits = 0;
         for (uint32_t t = tA; t < tB; t++) {
             uint32_t idx = nseq - 1 - t;
-            uint32_t cl = cLL[idx], co = cOF[idx], cm = cML[idx];
+            uint32_t cl = B2C_LDG(cLL + idx), co = B2C_LDG(cOF + idx), cm = B2C_LDG(cML + idx);
             mybits += seq_ll_bits(cl) + seq_ml_bits(cm) + co;
-            if (t) mybits += (stbLL[idx] >> 12) + (stbOF[idx] >> 12) + (stbML[idx] >> 12);
+            if (t) mybits += (uint32_t)(B2C_LDG(stbLL + idx) >> 12) + (uint32_t)(B2C_LDG(stbOF + idx) >> 12) + (uint32_t)(B2C_LDG(stbML + idx) >> 12);
         }
         uint32_t totalBits;
         uint32_t exBits = group_scan_excl(mybits, ps->scan, 0, PACK_NT, tid, &totalBits);
@@ -974,17 +974,18 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
                 br.init(reinterpret_cast<uint32_t *>(stage), bsOff * 8 + exBits);
                 for (uint32_t t = tA; t < tB; t++) {
                     uint32_t idx = nseq - 1 - t;
-                    uint32_t cl = cLL[idx], co = cOF[idx], cm = cML[idx];
+                    uint32_t cl = B2C_LDG(cLL + idx), co = B2C_LDG(cOF + idx), cm = B2C_LDG(cML + idx);
+                    const uint32_t vLL = B2C_LDG(W->seqLL + idx), vML = B2C_LDG(W->seqML + idx), vOF = B2C_LDG(W->seqOF + idx);
                     if (t) {
-                        uint32_t so = stbOF[idx], sm = stbML[idx], sl = stbLL[idx];
+                        uint32_t so = B2C_LDG(stbOF + idx), sm = B2C_LDG(stbML + idx), sl = B2C_LDG(stbLL + idx);
                         br.add(so & 0xfff, so >> 12);
                         br.add(sm & 0xfff, sm >> 12);
                         br.add(sl & 0xfff, sl >> 12);
                     }
                     uint32_t lb = seq_ll_bits(cl), mb = seq_ml_bits(cm);
-                    br.add((uint32_t)W->seqLL[idx] & ((1u << lb) - 1), lb);
-                    br.add((uint32_t)W->seqML[idx] & ((1u << mb) - 1), mb);
-                    br.add(W->seqOF[idx] & ((1u << co) - 1), co);
+                    br.add(vLL & ((1u << lb) - 1), lb);
+                    br.add(vML & ((1u << mb) - 1), mb);
+                    br.add(vOF & ((1u << co) - 1), co);
                 }
                 if (tB == nseq && tA < tB) {
                     // final states: ml, of, ll (blockenc.go:804-806) + end mark

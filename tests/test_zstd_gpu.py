@@ -151,3 +151,41 @@ def test_packed_pipeline_many_batches(enc):
     out = dec.DecodeAll(bytes(packed), size_hint=total_in + 64)
     dec.close()
     assert out == bytes(host.numpy())
+
+
+def test_unaligned_layout_and_small_slots(enc):
+    """Chunks at an odd stride (no TMA bulk copy, unaligned XXH64 loads) give the same frames; a destination slot
+    that is too small is reported per chunk (B2C_ERR_DST_SMALL) without touching the neighbouring slots."""
+    import ctypes
+    from compress_b200 import zstd
+    from compress_b200._lib import lib
+    tw = H.golden("twain.txt")
+    chunks = [tw[i * 50001:i * 50001 + 50001] for i in range(6)] + [tw[:65536], b"", tw[:17]]
+    ref = enc.encode_chunks(chunks)
+    stride = 65536 + 13
+    n = len(chunks)
+    buf = np.zeros(n * stride + 64, dtype=np.uint8)
+    sizes = np.zeros(n, dtype=np.int32)
+    for i, c in enumerate(chunks):
+        buf[3 + i * stride:3 + i * stride + len(c)] = np.frombuffer(c, dtype=np.uint8)
+        sizes[i] = len(c)
+    dsrc = torch.from_numpy(buf).cuda()
+    dst, outs = enc.encode_device(dsrc[3:], torch.from_numpy(sizes).cuda(), chunk=stride)
+    torch.cuda.synchronize()
+    outs_h = outs.cpu().numpy()
+    got = [bytes(dst[i, :int(outs_h[i])].cpu().numpy()) for i in range(n)]
+    assert got == ref
+    # slots of 20000 bytes: the big chunks do not fit
+    small = torch.full((n, 20000 + 16), 0x5A, dtype=torch.uint8, device="cuda")
+    souts = torch.empty((n,), dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = lib.b2c_zstd_encode_device(enc._ctx, 1, 3, dsrc[3:].data_ptr(), stride, torch.from_numpy(sizes).cuda().data_ptr(), 0,
+                                    small.data_ptr(), 20000 + 16, souts.data_ptr(), n, ctypes.c_void_p(stream))
+    assert rc == 0
+    torch.cuda.synchronize()
+    s = souts.cpu().numpy()
+    for i, c in enumerate(chunks):
+        if len(ref[i]) <= 20000 + 16:
+            assert s[i] == len(ref[i]) and bytes(small[i, :int(s[i])].cpu().numpy()) == ref[i]
+        else:
+            assert s[i] == -4
