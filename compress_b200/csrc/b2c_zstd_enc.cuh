@@ -742,35 +742,38 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
 // Per-lane tables live in shared memory, interleaved so that lane l only ever touches bank l:
 // 128 words of packed u16 next-states + 64 words of (deltaNbBits | (deltaFindState + 512) << 21).
 constexpr int CHAIN_NT = 96;
-constexpr uint32_t CHAIN_SMEM_WORDS_PER_LANE = 128 + 64;   // 256 x u16 state table + 64 x u32 symbol transforms
+constexpr uint32_t CHAIN_SMEM_WORDS_PER_LANE = 64 + 56;   // 256 x u8 next-state offsets + 56 x u32 symbol transforms
 constexpr uint32_t CHAIN_SMEM_BYTES = CHAIN_NT * CHAIN_SMEM_WORDS_PER_LANE * 4;
 // K3: one lane per (chunk, table) walks the tANS state chain from the last sequence to the first
 // (blockenc.go:757-803 restated as three independent recurrences) and stores, per sequence, the bits it emits:
 // stb[i] = value | nbBits << 12.  The recurrence is latency-bound, so the loop keeps the dependent path to
 // add/shift/add + one shared-memory load per step: codes arrive eight at a time (one 8-byte load, requested two
 // blocks ahead), their symbol transforms are fetched up front, results leave as one 16-byte store per 8 steps.
+// Per-lane tables are interleaved so lane l only touches bank l: next states are kept as u8 offsets from tableSize
+// (4 per word), 45 KB per CTA, so five CTAs fit an SM and a 16 384-chunk batch is a single wave.
 B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_t chunk0) {
     const unsigned tid = threadIdx.x, lane = tid & 31, which = tid >> 5;
     const uint32_t chunk = chunk0 + lane;
     const bool live = chunk < P.nchunks && P.work[chunk < P.nchunks ? chunk : 0].kind == 0;
     ChunkWork *W = P.work + (live ? chunk : 0);
     uint32_t *st32 = smem32 + which * 32 * CHAIN_SMEM_WORDS_PER_LANE;  // this warp's region
-    uint16_t *tState = reinterpret_cast<uint16_t *>(st32) + lane;      // element i of lane l at u16 index i * 32 + l
-    uint32_t *tSym = st32 + 128 * 32 + lane;                           // element i of lane l at word i * 32 + l
-    uint32_t nseq = 0, useRLE = 1, tableLog = 0;
+    uint8_t *tState = reinterpret_cast<uint8_t *>(st32 + lane);        // element i at byte (i >> 2) * 128 + (i & 3)
+    uint32_t *tSym = st32 + 64 * 32 + lane;                            // element i of lane l at word i * 32 + l
+#define TSTATE(i) tState[(((uint32_t)(i)) >> 2) * 128 + (((uint32_t)(i)) & 3)]
+    uint32_t nseq = 0, useRLE = 1, tableLog = 0, tableSize = 1;
     if (live) {
         const FseCTable *t = &W->tbl[which];
-        nseq = W->nseq; useRLE = t->useRLE; tableLog = t->tableLog;
+        nseq = W->nseq; useRLE = t->useRLE; tableLog = t->tableLog; tableSize = 1u << tableLog;
         if (!useRLE) {
             const uint32_t *sw = reinterpret_cast<const uint32_t *>(t->stateTable);
-            const uint32_t ts2 = (1u << tableLog) / 2;
-            for (uint32_t i = 0; i < ts2; i++) {
-                const uint32_t v = sw[i];
-                tState[(2 * i) * 32] = (uint16_t)v;
-                tState[(2 * i + 1) * 32] = (uint16_t)(v >> 16);
+            const uint32_t ts2 = tableSize / 2;
+            for (uint32_t i = 0; i < ts2; i += 2) {      // tableSize >= 32: four states per word
+                const uint32_t v0 = sw[i], v1 = sw[i + 1];
+                st32[(i >> 1) * 32 + lane] = ((v0 & 0xffff) - tableSize) | (((v0 >> 16) - tableSize) << 8) |
+                                             (((v1 & 0xffff) - tableSize) << 16) | (((v1 >> 16) - tableSize) << 24);
             }
             const uint32_t sl = t->symbolLen;
-            for (uint32_t i = 0; i < 64; i++)
+            for (uint32_t i = 0; i < 56; i++)
                 tSym[i * 32] = (i < sl) ? (t->deltaNbBits[i] | ((uint32_t)((int32_t)t->deltaFindState[i] + 512) << 21)) : 0u;
         }
     }
@@ -780,12 +783,12 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
     uint32_t state = 0;
     const bool run = live && !useRLE && nseq >= 1;
     if (run) {
-        const uint32_t e = tSym[(codes[nseq - 1] & 63u) * 32];
+        const uint32_t e = tSym[(codes[nseq - 1] < 56u ? codes[nseq - 1] : 0u) * 32];
         const uint32_t dnb = e & 0x1fffffu;
         const int32_t dfs = (int32_t)(e >> 21) - 512;
         const uint32_t nbBitsOut = (dnb + (1u << 15)) >> 16;
         const int32_t im = (int32_t)((nbBitsOut << 16) - dnb);
-        state = tState[((im >> nbBitsOut) + dfs) * 32];
+        state = tableSize + TSTATE((im >> nbBitsOut) + dfs);
     }
     // sequences nseq-2 .. 0 in blocks of eight (block k = sequences 8k .. 8k+7), top block first
     const int32_t top = run ? (int32_t)nseq - 2 : -1;
@@ -803,7 +806,8 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
             uint32_t e[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const uint32_t code = (((j < 4) ? cwA.x : cwA.y) >> (8 * (j & 3))) & 63u;
+                uint32_t code = (((j < 4) ? cwA.x : cwA.y) >> (8 * (j & 3))) & 63u;
+                if (code >= 56u) code = 0;     // bytes past the last sequence are not codes
                 e[j] = tSym[code * 32];
             }
             uint32_t o[4] = {0, 0, 0, 0};
@@ -812,7 +816,7 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
                 if (8 * k + pos <= top) {
                     const uint32_t nb = (state + (e[pos] & 0x1fffffu)) >> 16;
                     o[pos >> 1] |= ((state & ((1u << nb) - 1)) | (nb << 12)) << (16 * (pos & 1));
-                    state = tState[((int32_t)(state >> nb) + (int32_t)(e[pos] >> 21) - 512) * 32];
+                    state = tableSize + TSTATE((int32_t)(state >> nb) + (int32_t)(e[pos] >> 21) - 512);
                 }
             }
             *reinterpret_cast<uint4 *>(stb + 8 * k) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -823,6 +827,7 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
         if (useRLE) { for (uint32_t i = 0; i + 1 < nseq; i++) stb[i] = 0; state = 0; }
         W->finalState[which] = state;
     }
+#undef TSTATE
 }
 
 // ------------------------------------------------------------------------------------------------ K4
