@@ -21,7 +21,7 @@ enum { HUF0_ERR_INCOMPRESSIBLE = -1, HUF0_ERR_USE_RLE = -2, HUF0_ERR_TOO_BIG = -
 
 struct Huf0Shared {
     HufWork hw;
-    uint16_t lcol[4 * 256 * 32];   // private counter per (symbol, lane) for 4 counting warps
+    uint32_t whist[(HUF0_NT / 32) * 256];
     uint32_t flag;
 };
 constexpr uint32_t HUF0_SMEM_BYTES = ((sizeof(Huf0Shared) + 15) / 16) * 16;
@@ -47,44 +47,7 @@ B2C_DEV void huf0_compress_block(Huf0Shared *sh, const Huf0Params &P, uint32_t c
         if (tid == 0) P.out_sizes[chunk] = HUF0_ERR_TOO_BIG;
         return;
     }
-    // countSimple (compress.go:351): warps 0..3 count with one private u16 counter per (symbol, lane) -- no atomics,
-    // no conflicts; a lane sees at most 262143 / 128 + 1 symbols, so the counters cannot overflow.
-    {
-        const unsigned lane = tid & 31, w = tid >> 5;
-        for (uint32_t i = tid; i < 4 * 256 * 32 / 2; i += HUF0_NT) reinterpret_cast<uint32_t *>(sh->lcol)[i] = 0;
-        __syncthreads();
-        if (w < 4) {
-            uint16_t *hcol = sh->lcol + w * 256 * 32 + lane;
-            const bool al = (reinterpret_cast<uintptr_t>(in) & 3) == 0;
-            const uint32_t nw = al ? n / 4 : 0;
-            const uint32_t *in32 = reinterpret_cast<const uint32_t *>(in);
-            for (uint32_t i = w * 32 + lane; i < nw; i += 4 * 32) {
-                const uint32_t v = in32[i];
-                const uint32_t s0 = v & 0xff, s1 = (v >> 8) & 0xff, s2 = (v >> 16) & 0xff, s3 = v >> 24;
-                uint32_t i0 = 1, i1 = 1, i2 = 1, i3 = 1;   // duplicates folded into the first occurrence
-                if (s1 == s0) { i0 += i1; i1 = 0; }
-                if (s2 == s0) { i0 += i2; i2 = 0; } else if (s2 == s1) { i1 += i2; i2 = 0; }
-                if (s3 == s0) { i0 += i3; i3 = 0; } else if (s3 == s1) { i1 += i3; i3 = 0; } else if (s3 == s2) { i2 += i3; i3 = 0; }
-                const uint32_t c0 = hcol[s0 * 32], c1 = hcol[s1 * 32], c2 = hcol[s2 * 32], c3 = hcol[s3 * 32];
-                hcol[s0 * 32] = (uint16_t)(c0 + i0);
-                if (i1) hcol[s1 * 32] = (uint16_t)(c1 + i1);
-                if (i2) hcol[s2 * 32] = (uint16_t)(c2 + i2);
-                if (i3) hcol[s3 * 32] = (uint16_t)(c3 + i3);
-            }
-            for (uint32_t i = nw * 4 + w * 32 + lane; i < n; i += 4 * 32) hcol[(uint32_t)in[i] * 32]++;
-        }
-        __syncthreads();
-        if (tid < 256) {
-            uint32_t c = 0;
-            for (int k = 0; k < 4; k++) {
-                const uint32_t *row = reinterpret_cast<const uint32_t *>(sh->lcol + (k * 256 + tid) * 32);
-#pragma unroll
-                for (int j = 0; j < 16; j++) { const uint32_t v = row[j]; c += (v & 0xffff) + (v >> 16); }
-            }
-            hw->count[tid] = c;
-        }
-        __syncthreads();
-    }
+    huf_histogram(in, n, sh->whist, hw, tid, HUF0_NT, 0);   // countSimple (compress.go:351), all 32 warps
     if (tid == 0) { hw->status = HUF_INCOMPRESSIBLE; hw->tableDescLen = 0; hw->tableLog = 0; }
     __syncthreads();
     huf_build_table(hw, n, tid, HUF0_NT, 0);         // sets hw->status (compress.go:66-80 early outs included)

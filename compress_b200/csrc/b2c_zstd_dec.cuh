@@ -392,7 +392,7 @@ B2C_DEV int dec_huf_read_table(DecWarp *dw, const uint8_t *in, uint32_t n, uint3
 // one Huffman stream, one lane: exactly `count` symbols, exact consumption (huff0/decompress_generic.go).
 // Symbols are produced four at a time and leave as one aligned 32-bit store; an over-read shows up as pos > total at
 // the end (bits below the start of the stream read as zero), so the loop itself needs no per-symbol end test.
-B2C_DEV int dec_huf_stream(const uint16_t *dt, uint32_t tl, const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t count) {
+__device__ __noinline__ int dec_huf_stream(const uint16_t *dt, uint32_t tl, const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t count) {
     BrB br;
     if (br.init(src, n)) return -1;
     uint32_t i = 0;
