@@ -70,3 +70,29 @@ def test_huf_roundtrip_config4(codec):
     torch.cuda.synchronize()
     assert bool((osz == bs).all())
     assert torch.equal(out[:, :bs], src[:, :bs])
+
+
+def test_huf_reference_error_table(codec, oracle_lib):
+    # huff0/compress_test.go:20-52: expected error class of Compress1X / Compress4X per input
+    from test_reference_tables import HUF_TABLE, huf_inputs, _cls
+    inputs = huf_inputs()
+    names = list(inputs)
+    for four in (False, True):
+        got = codec.compress_blocks([inputs[n] for n in names], four)
+        for n, (out, code) in zip(names, got):
+            assert _cls(code) == HUF_TABLE[n][1 if four else 0], (n, four, code)
+            assert (out, code) == orc_compress(inputs[n], four), n
+
+
+def test_zstd_large_zeros_gpu():
+    # zstd/testdata/large.zip (TestNewDecoderLarge): 100 KiB and 10 MiB of zeros
+    import os
+    import zipfile
+    from compress_b200 import zstd
+    dec = zstd.Decoder()
+    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_large.zip"))
+    for nm in zf.namelist():
+        if nm.endswith(".zst"):
+            size = int(zf.read(nm + ".size"))
+            assert dec.DecodeAll(zf.read(nm), size_hint=size + 8) == bytes(size), nm
+    dec.close()
