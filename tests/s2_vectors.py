@@ -37,3 +37,29 @@ DECODE_TABLE = [
 
 INVALID_VARINT = [b"\xff", b"\xff\xff\xff\xff\xff\xff\xff\xff\xff\xff\x00", b"\x80\x80\x80\x80\x10",
                   b"\x84\x80\x80\x80\x80\x80\x80\x00" + b"\x00" * 7 + b"\x30"]
+
+
+def decode_copy4_case():
+    """s2/s2_test.go:472-500 TestDecodeCopy4: (input, want)."""
+    dots = b"." * 65536
+    inp = b"\x89\x80\x04" + b"\x0cpqrs" + b"\xf4\xff\xff" + dots + b"\x13\x04\x00\x01\x00"
+    return inp, b"pqrs" + dots + b"pqrs."
+
+
+def decode_length_offset_cases():
+    """s2/s2_test.go:502-597 TestDecodeLengthOffset: literal + copy(length, offset) + literal, 18 x 18 x 19 cases."""
+    prefix, suffix = b"abcdefghijklmnopqr", b"ABCDEFGHIJKLMNOPQR"
+    out = []
+    for length in range(1, 19):
+        for offset in range(1, 19):
+            for suffix_len in range(0, 19):
+                total = len(prefix) + length + suffix_len
+                inp = bytes([total]) + bytes([4 * (len(prefix) - 1)]) + prefix + bytes([2 + 4 * (length - 1), offset, 0])
+                if suffix_len:
+                    inp += bytes([4 * (suffix_len - 1)]) + suffix[:suffix_len]
+                want = bytearray(prefix)
+                for _ in range(length):
+                    want.append(want[-offset])
+                want += suffix[:suffix_len]
+                out.append((inp, bytes(want)))
+    return out

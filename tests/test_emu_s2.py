@@ -78,3 +78,17 @@ def test_emu_s2_decode(emu_lib, oracle_lib):
     # too small destination / truncated input
     outs, _, _, _ = emu_s2_decode(emu_lib, [comp[24], comp[24][:-3]], [100, 65536])
     assert outs[0] == -4 and outs[1] == -5
+
+
+def test_s2_decode_copy4_and_length_offset(emu_lib, oracle_lib):
+    # s2/s2_test.go:472-597 TestDecodeCopy4, TestDecodeLengthOffset (output and no write past the decoded length)
+    from s2_vectors import decode_copy4_case, decode_length_offset_cases
+    cases = [decode_copy4_case()] + decode_length_offset_cases()
+    for inp, want in cases[:200] + cases[::37]:
+        n, got = orc_decode(inp, len(want))
+        assert n == len(want) and got == want
+    outs, res, dst, dst_off = emu_s2_decode(emu_lib, [c[0] for c in cases], [len(c[1]) + 40 for c in cases])
+    for i, ((inp, want), r, got) in enumerate(zip(cases, outs, res)):
+        assert r == len(want) and got == want, i
+        tail = dst[int(dst_off[i]) + len(want):int(dst_off[i]) + len(want) + 40]
+        assert (tail == 0x5A).all(), i
