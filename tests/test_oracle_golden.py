@@ -157,3 +157,19 @@ def test_huff0_error_classes(oracle_lib):
     pz = cnt[cnt > 0] / len(tw)
     shannon = -(pz * np.log2(pz)).sum() * len(tw) / 8
     assert shannon <= r < len(tw) * 0.7
+
+
+def test_xxh64_kats(oracle_lib):
+    # zstd/internal/xxhash/xxhash_test.go:17-27 (TestAll) and the content digests the encoder tests expect
+    # (zstd/encoder_test.go:543-563: Twain, HTML)
+    L = H.oracle()
+    L.orc_xxh64.restype = ctypes.c_uint64
+    L.orc_xxh64.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint64]
+    kats = [(b"", 0xef46db3751d8e999), (b"a", 0xd24ec4f1a98c6e5b), (b"as", 0x1c330fb2d66be179), (b"asd", 0x631c37ce72a97393),
+            (b"asdf", 0x415872f599cea71e),
+            (b"Call me Ishmael. Some years ago--never mind how long precisely-", 0x02a2e85470d6fd96)]
+    for data, want in kats:
+        assert L.orc_xxh64(data, len(data), 0) == want, data
+    tw, ht = H.golden("twain.txt"), H.golden("html.txt")
+    assert L.orc_xxh64(tw, len(tw), 0) == 0x121f127079371fc6
+    assert L.orc_xxh64(ht, len(ht), 0) == 0x35a95c37209ec337
