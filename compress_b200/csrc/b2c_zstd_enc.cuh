@@ -423,6 +423,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         }
         if (cnt) lastE = nextEmit;
     }
+    B2C_PHASE(6);
     cntA[tid] = (uint8_t)cnt;
     capA[tid] = (uint8_t)((cnt != 0) && capped);
     __syncthreads();
@@ -455,6 +456,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     // ---------------------------------------------------------------- P3: merge (trim overlaps), global layout
     uint32_t dummyTotal;
     const uint32_t R = group_scan_excl_max(lastE, sh->ws, 0, ENC_NT, tid, &dummyTotal);   // everything before R is taken
+    B2C_PHASE(8);
     uint32_t kept = 0, sumLen = 0, keptE = 0, lastOff = 0;
     for (uint32_t j = 0; j < cnt; j++) {
         const uint2 r = REC(j, tid);
@@ -465,6 +467,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         REC(kept, tid) = make_uint2(s2 | (l2 << 16), r.y);
         kept++; sumLen += l2; keptE = e0; lastOff = r.y;
     }
+    B2C_PHASE(9);
     keptEndA[tid] = keptE;
     lastOffA[tid] = (uint16_t)lastOff;
     uint32_t packedTotal, keyTotal;
@@ -473,6 +476,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     __syncthreads();
     // nearest earlier thread that kept something: gives the end of the previous sequence and its offset
     const uint32_t keyEx = group_scan_excl_max(kept ? tid + 1 : 0u, sh->ws, 0, ENC_NT, tid, &keyTotal);
+    B2C_PHASE(10);
     const uint32_t nseq = packedTotal >> 17, nlit = n - (packedTotal & 0x1ffffu);
     const uint32_t lastEnd = keyTotal ? keptEndA[keyTotal - 1] : 0u;      // end of the last sequence of the chunk
     if constexpr (MODE != LZ_MODE_ZSTD) {
@@ -583,7 +587,12 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
             const uint32_t ll = s0 - prevE;
             const uint32_t lpos = prevE - mrun;          // literal index = source position - match bytes before it
-            for (uint32_t k = 0; k < ll; k++) lit[lpos + k] = src[prevE + k];
+            {   // literal run: bytes up to the next 4-byte boundary of the destination, then whole words
+                uint32_t k = 0;
+                while (k < ll && ((lpos + k) & 3)) { lit[lpos + k] = src[prevE + k]; k++; }
+                for (; k + 4 <= ll; k += 4) *reinterpret_cast<uint32_t *>(lit + lpos + k) = ld32u(src, prevE + k);
+                for (; k < ll; k++) lit[lpos + k] = src[prevE + k];
+            }
             // repeat code 1 (= offset of the previous sequence, valid with litLen > 0; seqdec.go:463-500)
             const bool isrep = (gi > 0) && (d0 == pOff) && (ll > 0);
             const uint32_t ofv = isrep ? 1u : d0 + 3;
@@ -593,6 +602,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             W->codes[TBL_ML][gi] = (uint8_t)seq_ml_code(l0 - 3);
             prevE = s0 + l0; mrun += l0; pOff = d0; gi++;
         }
+        B2C_PHASE(11);
         const uint32_t tl = n - lastEnd;
         for (uint32_t k = tid; k < tl; k += ENC_NT) lit[nlit - tl + k] = src[lastEnd + k];
     }
@@ -609,38 +619,44 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
 
     // ---------------------------------------------------------------- P5: histograms (src is dead from here on)
     if (kind == 0) {
-        // literal histogram: warps 0..3, one private u16 counter per (symbol, lane) -- conflict-free, no atomics;
-        // four literals per load, the four counter updates of a word are made independent by merging equal symbols.
-        // meanwhile warps 4..31 count the sequence codes with ballots (lane l owns codes with low 5 bits == l) and
+        // literal histogram: warps 0..7, one private u8 counter per (symbol, lane) -- no atomics, no races.  A lane
+        // sees at most nlit / 256 < 253 literals (nlit <= n - n/64 - 16 here), so a counter cannot wrap.  Four
+        // literals per load; equal symbols inside a word are merged so the four updates are independent.
+        // Meanwhile warps 8..31 count the sequence codes with ballots (lane l owns codes with low 5 bits == l) and
         // copy the literals out.
-        uint16_t *lcol = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_L);       // [4][256][32] u16 = 64 KiB
-        uint32_t *shist2 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_SRC);   // [28][192] code counters (src is dead)
-        for (uint32_t i = tid; i < 4 * 256 * 32 / 2; i += ENC_NT) reinterpret_cast<uint32_t *>(lcol)[i] = 0;
+        constexpr int LH_WARPS = 8;
+        uint8_t *lcol = smem + ENC_SMEM_L;                                      // [8][256][32] u8 = 64 KiB
+        uint32_t *shist2 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_SRC);   // [24][192] code counters (src is dead)
+        for (uint32_t i = tid; i < LH_WARPS * 256 * 32 / 4; i += ENC_NT) reinterpret_cast<uint32_t *>(lcol)[i] = 0;
         __syncthreads();
-        if (w < 4) {
-            uint16_t *hcol = lcol + w * 256 * 32 + lane;
+        B2C_PHASE(12);
+        if (w < LH_WARPS) {
+            uint8_t *hcol = lcol + w * 256 * 32 + lane;
             const uint32_t nl4 = (nlit + 3) / 4;
             const uint32_t *lit32 = reinterpret_cast<const uint32_t *>(lit);
-            for (uint32_t i = w * 32 + lane; i < nl4; i += 4 * 32) {
-                const uint32_t v = lit32[i];
+            uint32_t i = w * 32 + lane;
+            uint32_t v = (i < nl4) ? lit32[i] : 0;
+            while (i < nl4) {
+                const uint32_t inext = i + LH_WARPS * 32;
+                const uint32_t vnext = (inext < nl4) ? lit32[inext] : 0;     // next word requested before this one is used
                 const uint32_t nv = (4 * i + 4 <= nlit) ? 4u : nlit - 4 * i;
                 const uint32_t s0 = v & 0xff, s1 = (v >> 8) & 0xff, s2 = (v >> 16) & 0xff, s3 = v >> 24;
-                // increments with duplicates folded into the first occurrence
                 uint32_t i0 = 1, i1 = nv > 1, i2 = nv > 2, i3 = nv > 3;
                 if (s1 == s0) { i0 += i1; i1 = 0; }
                 if (s2 == s0) { i0 += i2; i2 = 0; } else if (s2 == s1) { i1 += i2; i2 = 0; }
                 if (s3 == s0) { i0 += i3; i3 = 0; } else if (s3 == s1) { i1 += i3; i3 = 0; } else if (s3 == s2) { i2 += i3; i3 = 0; }
                 const uint32_t c0 = hcol[s0 * 32], c1 = hcol[s1 * 32], c2 = hcol[s2 * 32], c3 = hcol[s3 * 32];
-                hcol[s0 * 32] = (uint16_t)(c0 + i0);
-                if (i1) hcol[s1 * 32] = (uint16_t)(c1 + i1);
-                if (i2) hcol[s2 * 32] = (uint16_t)(c2 + i2);
-                if (i3) hcol[s3 * 32] = (uint16_t)(c3 + i3);
+                hcol[s0 * 32] = (uint8_t)(c0 + i0);
+                if (i1) hcol[s1 * 32] = (uint8_t)(c1 + i1);
+                if (i2) hcol[s2 * 32] = (uint8_t)(c2 + i2);
+                if (i3) hcol[s3 * 32] = (uint8_t)(c3 + i3);
+                i = inext; v = vnext;
             }
         } else {
             uint32_t sc[3][2];
 #pragma unroll
             for (int c = 0; c < 3; c++) { sc[c][0] = 0; sc[c][1] = 0; }
-            for (uint32_t base = (w - 4) * 32; base < nseq; base += (ENC_NW - 4) * 32) {
+            for (uint32_t base = (w - LH_WARPS) * 32; base < nseq; base += (ENC_NW - LH_WARPS) * 32) {
                 const uint32_t i = base + lane;
                 const bool valid = i < nseq;
 #pragma unroll
@@ -648,35 +664,44 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             }
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                shist2[(w - 4) * 192 + c * 64 + lane] = sc[c][0];
-                shist2[(w - 4) * 192 + c * 64 + 32 + lane] = sc[c][1];
+                shist2[(w - LH_WARPS) * 192 + c * 64 + lane] = sc[c][0];
+                shist2[(w - LH_WARPS) * 192 + c * 64 + 32 + lane] = sc[c][1];
             }
             // literals to the work record (coalesced 16-byte stores)
             const uint4 *s4 = reinterpret_cast<const uint4 *>(lit);
             uint4 *d4 = reinterpret_cast<uint4 *>(W->lit);
             const uint32_t n16 = (nlit + 15) / 16;
-            for (uint32_t i = tid - 128; i < n16; i += ENC_NT - 128) d4[i] = s4[i];
+            for (uint32_t i = tid - LH_WARPS * 32; i < n16; i += ENC_NT - LH_WARPS * 32) d4[i] = s4[i];
         }
+        B2C_PHASE(13);
         __syncthreads();
+        B2C_PHASE(14);
         if (tid < 256) {
+            // 8 tables x 32 byte counters of symbol `tid`; word j of every row is taken in a rotated order so the 32
+            // threads of a warp (row stride 8 words) do not pile onto the same banks
             uint32_t c = 0;
-            for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int k = 0; k < LH_WARPS; k++) {
                 const uint32_t *row = reinterpret_cast<const uint32_t *>(lcol + (k * 256 + tid) * 32);
 #pragma unroll
-                for (int j = 0; j < 16; j++) { uint32_t v = row[j]; c += (v & 0xffff) + (v >> 16); }
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t v = row[(j + (tid >> 2)) & 7];
+                    c += (v & 0xff) + ((v >> 8) & 0xff) + ((v >> 16) & 0xff) + (v >> 24);
+                }
             }
             W->litHist[tid] = c;
         } else if (tid < 256 + 192) {
             uint32_t s = tid - 256, c = 0;
-            for (int k = 0; k < ENC_NW - 4; k++) c += shist2[k * 192 + s];
+            for (int k = 0; k < ENC_NW - LH_WARPS; k++) c += shist2[k * 192 + s];
             W->seqHist[s / 64][s % 64] = c;
-            shist2[s] = c;  // thread s only ever touches column s: row 0 now holds the totals
+            // highest used code of each table: the three groups of 64 threads are warp-aligned (2 warps each)
+            const unsigned nz = __ballot_sync(FULLMASK, c != 0);
+            if ((s & 31) == 0) shist2[24 * 192 + (s >> 5)] = nz;
         }
         __syncthreads();
         if (tid < 3) {
-            uint32_t mx = 0;
-            for (uint32_t s = 0; s < 64; s++) if (shist2[tid * 64 + s]) mx = s;
-            W->maxSym[tid] = mx;
+            const uint32_t lo = shist2[24 * 192 + 2 * tid], hi = shist2[24 * 192 + 2 * tid + 1];
+            W->maxSym[tid] = hi ? 32 + (31 - (uint32_t)__clz((int)hi)) : (lo ? 31 - (uint32_t)__clz((int)lo) : 0u);
         }
         if (P.dbg_hdr) {
             for (uint32_t i = tid; i < nseq && i < P.dbg_seq_cap; i += ENC_NT) {

@@ -38,5 +38,17 @@ def main():
             ", ".join("w%d=%.0f" % (w, wmean[w]) for w in top)))
 
 
+    # finer stamps (per-warp arrival, no barrier implied): mean over chunks and warps of the time between stamps
+    chain = [(2, 6, "per-thread scan (until the warp leaves the loop)"), (6, 3, "wait + long-match resolution"),
+             (3, 8, "prefix-max of match ends"), (8, 9, "trim loop"), (9, 10, "two block scans"),
+             (10, 11, "emit loop (literal gather, codes, stores)"), (11, 4, "tail literals + RLE test barriers"),
+             (4, 12, "zero counters + barrier"), (12, 13, "histograms + literal copy-out"), (13, 14, "barrier wait"),
+             (14, 5, "reduce + maxSym + end")]
+    print("-- detail (mean cycles per warp; stamps are arrival times) --")
+    for a, b, nm in chain:
+        d = (c[:, b, :] - c[:, a, :]).astype(np.float64)
+        print("%-52s mean %8.0f   max-warp mean %8.0f" % (nm, d.mean(), d.mean(axis=0).max()))
+
+
 if __name__ == "__main__":
     main()
