@@ -305,6 +305,9 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                     if (p + j < npos) E[enc_hash6(lo, hi) >> (32 - ENC_EBITS)] = (uint16_t)(p + j);
                 }
             }
+            // keep the warps in step: a warp that falls behind would overwrite lower positions with higher ones, and
+            // every such slot costs a compare-and-swap in the fix-up pass
+            if ((k & 1) == 0) __syncthreads();
         }
         __syncthreads();
         // fix-up pass: every position checks its slot once; the (rare) losers of a write race take the slot with an
