@@ -581,11 +581,16 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     }
 
     // ---------------------------------------------------------------- P4: gather literals, sequences, codes
+    uint32_t seqCnt[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // this warp's code counts: lane l holds codes l and 32 + l
     if (kind == 0) {
         uint32_t prevE = keyEx ? keptEndA[keyEx - 1] : 0u;
         uint32_t pOff = keyEx ? (uint32_t)lastOffA[keyEx - 1] : 0u;
         uint32_t gi = packedEx >> 17, mrun = packedEx & 0x1ffffu;
-        for (uint32_t j = 0; j < kept; j++) {
+        const uint32_t keptMax = warp_max(kept);
+        for (uint32_t j = 0; j < keptMax; j++) {
+            const bool have = j < kept;
+            uint32_t cLLv = 0, cOFv = 0, cMLv = 0;
+            if (have) {
             const uint2 r = REC(j, tid);
             const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
             const uint32_t ll = s0 - prevE;
@@ -600,10 +605,16 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             const bool isrep = (gi > 0) && (d0 == pOff) && (ll > 0);
             const uint32_t ofv = isrep ? 1u : d0 + 3;
             W->seqLL[gi] = (uint16_t)ll; W->seqML[gi] = (uint16_t)(l0 - 3); W->seqOF[gi] = ofv;
-            W->codes[TBL_LL][gi] = (uint8_t)seq_ll_code(ll);
-            W->codes[TBL_OF][gi] = (uint8_t)highbit32(ofv);
-            W->codes[TBL_ML][gi] = (uint8_t)seq_ml_code(l0 - 3);
+            cLLv = seq_ll_code(ll); cOFv = highbit32(ofv); cMLv = seq_ml_code(l0 - 3);
+            W->codes[TBL_LL][gi] = (uint8_t)cLLv;
+            W->codes[TBL_OF][gi] = (uint8_t)cOFv;
+            W->codes[TBL_ML][gi] = (uint8_t)cMLv;
             prevE = s0 + l0; mrun += l0; pOff = d0; gi++;
+            }
+            // code histograms, ballot style: lane l owns the codes whose low 5 bits equal l
+            warp_hist_acc<6>(cLLv, have, seqCnt[TBL_LL], lane);
+            warp_hist_acc<6>(cOFv, have, seqCnt[TBL_OF], lane);
+            warp_hist_acc<6>(cMLv, have, seqCnt[TBL_ML], lane);
         }
         B2C_PHASE(11);
         const uint32_t tl = n - lastEnd;
@@ -622,19 +633,21 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
 
     // ---------------------------------------------------------------- P5: histograms (src is dead from here on)
     if (kind == 0) {
-        // literal histogram: warps 0..7, one private u8 counter per (symbol, lane) -- no atomics, no races.  A lane
-        // sees at most nlit / 256 < 253 literals (nlit <= n - n/64 - 16 here), so a counter cannot wrap.  Four
-        // literals per load; equal symbols inside a word are merged so the four updates are independent.
-        // Meanwhile warps 8..31 count the sequence codes with ballots (lane l owns codes with low 5 bits == l) and
-        // copy the literals out.
-        constexpr int LH_WARPS = 8;
-        uint8_t *lcol = smem + ENC_SMEM_L;                                      // [8][256][32] u8 = 64 KiB
-        uint32_t *shist2 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_SRC);   // [24][192] code counters (src is dead)
-        for (uint32_t i = tid; i < LH_WARPS * 256 * 32 / 4; i += ENC_NT) reinterpret_cast<uint32_t *>(lcol)[i] = 0;
+        // literal histogram: warps 0..15, one private u8 counter per (symbol, lane) -- no atomics, no races.  A lane
+        // sees at most nlit / 512 + 4 literals, so a counter cannot wrap.  Four literals per load; equal symbols inside
+        // a word are merged so the four updates are independent.  Warps 16..31 copy the literals out meanwhile.
+        // (The sequence-code counts were taken in the emit loop and wait in registers.)
+        constexpr int LH_WARPS = 16;
+        uint8_t *lcolA = smem + ENC_SMEM_L;        // tables 0..7  [8][256][32] u8
+        uint8_t *lcolB = smem + ENC_SMEM_SRC;      // tables 8..15 (src is dead)
+        for (uint32_t i = tid; i < 8 * 256 * 32 / 4; i += ENC_NT) {
+            reinterpret_cast<uint32_t *>(lcolA)[i] = 0;
+            reinterpret_cast<uint32_t *>(lcolB)[i] = 0;
+        }
         __syncthreads();
         B2C_PHASE(12);
         if (w < LH_WARPS) {
-            uint8_t *hcol = lcol + w * 256 * 32 + lane;
+            uint8_t *hcol = (w < 8 ? lcolA + w * 256 * 32 : lcolB + (w - 8) * 256 * 32) + lane;
             const uint32_t nl4 = (nlit + 3) / 4;
             const uint32_t *lit32 = reinterpret_cast<const uint32_t *>(lit);
             uint32_t i = w * 32 + lane;
@@ -656,20 +669,6 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                 i = inext; v = vnext;
             }
         } else {
-            uint32_t sc[3][2];
-#pragma unroll
-            for (int c = 0; c < 3; c++) { sc[c][0] = 0; sc[c][1] = 0; }
-            for (uint32_t base = (w - LH_WARPS) * 32; base < nseq; base += (ENC_NW - LH_WARPS) * 32) {
-                const uint32_t i = base + lane;
-                const bool valid = i < nseq;
-#pragma unroll
-                for (int c = 0; c < 3; c++) warp_hist_acc<6>(valid ? (uint32_t)W->codes[c][i] : 0u, valid, sc[c], lane);
-            }
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                shist2[(w - LH_WARPS) * 192 + c * 64 + lane] = sc[c][0];
-                shist2[(w - LH_WARPS) * 192 + c * 64 + 32 + lane] = sc[c][1];
-            }
             // literals to the work record (coalesced 16-byte stores)
             const uint4 *s4 = reinterpret_cast<const uint4 *>(lit);
             uint4 *d4 = reinterpret_cast<uint4 *>(W->lit);
@@ -680,12 +679,13 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         __syncthreads();
         B2C_PHASE(14);
         if (tid < 256) {
-            // 8 tables x 32 byte counters of symbol `tid`; word j of every row is taken in a rotated order so the 32
+            // 16 tables x 32 byte counters of symbol `tid`; word j of every row is taken in a rotated order so the 32
             // threads of a warp (row stride 8 words) do not pile onto the same banks
             uint32_t c = 0;
 #pragma unroll
             for (int k = 0; k < LH_WARPS; k++) {
-                const uint32_t *row = reinterpret_cast<const uint32_t *>(lcol + (k * 256 + tid) * 32);
+                const uint8_t *tb = (k < 8) ? lcolA + k * 256 * 32 : lcolB + (k - 8) * 256 * 32;
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(tb + tid * 32);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const uint32_t v = row[(j + (tid >> 2)) & 7];
@@ -693,17 +693,26 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                 }
             }
             W->litHist[tid] = c;
-        } else if (tid < 256 + 192) {
-            uint32_t s = tid - 256, c = 0;
-            for (int k = 0; k < ENC_NW - LH_WARPS; k++) c += shist2[k * 192 + s];
-            W->seqHist[s / 64][s % 64] = c;
+        }
+        __syncthreads();      // the literal tables are dead: their first rows take the per-warp code counts
+        uint32_t *shist2 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L);   // [32][192]
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            shist2[w * 192 + c * 64 + lane] = seqCnt[c][0];
+            shist2[w * 192 + c * 64 + 32 + lane] = seqCnt[c][1];
+        }
+        __syncthreads();
+        if (tid < 192) {
+            uint32_t c = 0;
+            for (int k = 0; k < ENC_NW; k++) c += shist2[k * 192 + tid];
+            W->seqHist[tid / 64][tid % 64] = c;
             // highest used code of each table: the three groups of 64 threads are warp-aligned (2 warps each)
             const unsigned nz = __ballot_sync(FULLMASK, c != 0);
-            if ((s & 31) == 0) shist2[24 * 192 + (s >> 5)] = nz;
+            if ((tid & 31) == 0) shist2[ENC_NW * 192 + (tid >> 5)] = nz;
         }
         __syncthreads();
         if (tid < 3) {
-            const uint32_t lo = shist2[24 * 192 + 2 * tid], hi = shist2[24 * 192 + 2 * tid + 1];
+            const uint32_t lo = shist2[ENC_NW * 192 + 2 * tid], hi = shist2[ENC_NW * 192 + 2 * tid + 1];
             W->maxSym[tid] = hi ? 32 + (31 - (uint32_t)__clz((int)hi)) : (lo ? 31 - (uint32_t)__clz((int)lo) : 0u);
         }
         if (P.dbg_hdr) {
