@@ -586,11 +586,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         uint32_t prevE = keyEx ? keptEndA[keyEx - 1] : 0u;
         uint32_t pOff = keyEx ? (uint32_t)lastOffA[keyEx - 1] : 0u;
         uint32_t gi = packedEx >> 17, mrun = packedEx & 0x1ffffu;
-        const uint32_t keptMax = warp_max(kept);
-        for (uint32_t j = 0; j < keptMax; j++) {
-            const bool have = j < kept;
-            uint32_t cLLv = 0, cOFv = 0, cMLv = 0;
-            if (have) {
+        for (uint32_t j = 0; j < kept; j++) {
             const uint2 r = REC(j, tid);
             const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
             const uint32_t ll = s0 - prevE;
@@ -605,16 +601,10 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             const bool isrep = (gi > 0) && (d0 == pOff) && (ll > 0);
             const uint32_t ofv = isrep ? 1u : d0 + 3;
             W->seqLL[gi] = (uint16_t)ll; W->seqML[gi] = (uint16_t)(l0 - 3); W->seqOF[gi] = ofv;
-            cLLv = seq_ll_code(ll); cOFv = highbit32(ofv); cMLv = seq_ml_code(l0 - 3);
-            W->codes[TBL_LL][gi] = (uint8_t)cLLv;
-            W->codes[TBL_OF][gi] = (uint8_t)cOFv;
-            W->codes[TBL_ML][gi] = (uint8_t)cMLv;
+            W->codes[TBL_LL][gi] = (uint8_t)seq_ll_code(ll);
+            W->codes[TBL_OF][gi] = (uint8_t)highbit32(ofv);
+            W->codes[TBL_ML][gi] = (uint8_t)seq_ml_code(l0 - 3);
             prevE = s0 + l0; mrun += l0; pOff = d0; gi++;
-            }
-            // code histograms, ballot style: lane l owns the codes whose low 5 bits equal l
-            warp_hist_acc<6>(cLLv, have, seqCnt[TBL_LL], lane);
-            warp_hist_acc<6>(cOFv, have, seqCnt[TBL_OF], lane);
-            warp_hist_acc<6>(cMLv, have, seqCnt[TBL_ML], lane);
         }
         B2C_PHASE(11);
         const uint32_t tl = n - lastEnd;
@@ -635,8 +625,8 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     if (kind == 0) {
         // literal histogram: warps 0..15, one private u8 counter per (symbol, lane) -- no atomics, no races.  A lane
         // sees at most nlit / 512 + 4 literals, so a counter cannot wrap.  Four literals per load; equal symbols inside
-        // a word are merged so the four updates are independent.  Warps 16..31 copy the literals out meanwhile.
-        // (The sequence-code counts were taken in the emit loop and wait in registers.)
+        // a word are merged so the four updates are independent.  Warps 16..31 count the sequence codes and copy the
+        // literals out meanwhile.
         constexpr int LH_WARPS = 16;
         uint8_t *lcolA = smem + ENC_SMEM_L;        // tables 0..7  [8][256][32] u8
         uint8_t *lcolB = smem + ENC_SMEM_SRC;      // tables 8..15 (src is dead)
@@ -669,6 +659,13 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                 i = inext; v = vnext;
             }
         } else {
+            // sequence-code counts, ballot style (lane l owns the codes whose low 5 bits equal l), kept in registers
+            for (uint32_t base = (w - LH_WARPS) * 32; base < nseq; base += (ENC_NW - LH_WARPS) * 32) {
+                const uint32_t i = base + lane;
+                const bool valid = i < nseq;
+#pragma unroll
+                for (int c = 0; c < 3; c++) warp_hist_acc<6>(valid ? (uint32_t)W->codes[c][i] : 0u, valid, seqCnt[c], lane);
+            }
             // literals to the work record (coalesced 16-byte stores)
             const uint4 *s4 = reinterpret_cast<const uint4 *>(lit);
             uint4 *d4 = reinterpret_cast<uint4 *>(W->lit);
