@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libb200comp.so")
+LIB_PATH = os.environ.get("B2C_LIB") or os.path.join(_HERE, "_lib", "libb200comp.so")   # B2C_LIB: tuning builds
 
 
 class B2CError(RuntimeError):

@@ -39,6 +39,12 @@ constexpr int ENC_NW = ENC_NT / 32;       // 32 parsing warps
 constexpr int ENC_EBITS = 15;             // earliest-occurrence table: 32 Ki x u16
 constexpr uint32_t ENC_LANE_BYTES = 68;   // bytes parsed by one thread (17 words: lanes start in distinct banks)
 constexpr uint32_t ENC_MAXREC = 17;       // matches a thread can start inside its 68 bytes (min match 4)
+#ifndef ENC_PROBES_PER_VOTE
+#define ENC_PROBES_PER_VOTE 8   // probe steps between two looks at the warp state
+#endif
+#ifndef ENC_EXTEND_BATCH
+#define ENC_EXTEND_BATCH 6      // lanes holding a match before the warp runs an extend-and-emit step
+#endif
 constexpr uint32_t ENC_EXT_CAP = 256;     // per-thread forward extension limit; longer matches are finished by warp 0
 constexpr uint32_t ENC_MAX_CHUNK = 1u << 16;
 constexpr uint32_t ENC_SRC_BYTES = ENC_MAX_CHUNK + 128;   // chunk + zero padding
@@ -379,7 +385,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         for (;;) {
             // four probe steps between two looks at the warp state (the votes are pure overhead for the scan)
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < ENC_PROBES_PER_VOTE; u++) {
                 if (scanning) {
                     const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
                     cand = E[enc_hash6(c_lo, c_hi) >> (32 - ENC_EBITS)];
@@ -394,7 +400,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             const unsigned wm = __ballot_sync(FULLMASK, waiting);
             const unsigned sm = __ballot_sync(FULLMASK, scanning);
             if ((wm | sm) == 0) break;
-            if (__popc(wm) >= 8 || sm == 0) {
+            if (__popc(wm) >= ENC_EXTEND_BATCH || sm == 0) {
                 if (waiting) {
                     const uint32_t lim = (p + ENC_EXT_CAP < n) ? p + ENC_EXT_CAP : n;
                     // forward: 4 bytes per step from two unaligned streams (aligned word loads + funnel shifts)
