@@ -39,6 +39,9 @@ constexpr int ENC_NW = ENC_NT / 32;       // 32 parsing warps
 constexpr int ENC_EBITS = 15;             // earliest-occurrence table: 32 Ki x u16
 constexpr uint32_t ENC_LANE_BYTES = 68;   // bytes parsed by one thread (17 words: lanes start in distinct banks)
 constexpr uint32_t ENC_MAXREC = 17;       // matches a thread can start inside its 68 bytes (min match 4)
+#ifndef ENC_EBUILD_SYNC_MASK
+#define ENC_EBUILD_SYNC_MASK 1  // barrier every (mask + 1) iterations of the table build's first round
+#endif
 #ifndef ENC_PROBES_PER_VOTE
 #define ENC_PROBES_PER_VOTE 8   // probe steps between two looks at the warp state
 #endif
@@ -313,7 +316,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             }
             // keep the warps in step: a warp that falls behind would overwrite lower positions with higher ones, and
             // every such slot costs a compare-and-swap in the fix-up pass
-            if ((k & 1) == 0) __syncthreads();
+            if ((k & ENC_EBUILD_SYNC_MASK) == 0) __syncthreads();
         }
         __syncthreads();
         // fix-up pass: every position checks its slot once; the (rare) losers of a write race take the slot with an
