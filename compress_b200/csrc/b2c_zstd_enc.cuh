@@ -383,28 +383,28 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         const uint32_t e = (b + ENC_LANE_BYTES < n) ? b + ENC_LANE_BYTES : n;
         const uint32_t pend = (tid < nlanes) ? (e < npos ? e : npos) : 0u;   // probe positions need 8 readable bytes
         uint32_t p = b, nextEmit = b, cand = 0;
-        bool scanning = p < pend, waiting = false;
-        uint64_t cv = scanning ? ld64u(src, p) : 0ull;
+        uint32_t mode = (p < pend) ? 1u : 0u;      // 1 = probing, 2 = holding a match, 0 = done
+        uint64_t cv = mode ? ld64u(src, p) : 0ull;
         for (;;) {
             // four probe steps between two looks at the warp state (the votes are pure overhead for the scan)
 #pragma unroll
             for (int u = 0; u < ENC_PROBES_PER_VOTE; u++) {
-                if (scanning) {
+                if (mode == 1) {
                     const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
                     cand = E[enc_hash6(c_lo, c_hi) >> (32 - ENC_EBITS)];
-                    if (cand < p && ld32u(src, cand) == c_lo) { waiting = true; scanning = false; }
+                    if (cand < p && ld32u(src, cand) == c_lo) mode = 2;
                     else {
                         p++;
                         cv = (cv >> 8) | ((uint64_t)src[p + 7] << 56);
-                        scanning = p < pend;
+                        if (p >= pend) mode = 0;
                     }
                 }
             }
-            const unsigned wm = __ballot_sync(FULLMASK, waiting);
-            const unsigned sm = __ballot_sync(FULLMASK, scanning);
+            const unsigned wm = __ballot_sync(FULLMASK, mode == 2);
+            const unsigned sm = __ballot_sync(FULLMASK, mode == 1);
             if ((wm | sm) == 0) break;
             if (__popc(wm) >= ENC_EXTEND_BATCH || sm == 0) {
-                if (waiting) {
+                if (mode == 2) {
                     const uint32_t lim = (p + ENC_EXT_CAP < n) ? p + ENC_EXT_CAP : n;
                     // forward: 4 bytes per step from two unaligned streams (aligned word loads + funnel shifts)
                     uint32_t len = 4;
@@ -427,9 +427,8 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                     cnt++;
                     p = s + len;
                     nextEmit = p;
-                    waiting = false;
-                    scanning = p < pend;
-                    if (scanning) cv = ld64u(src, p);
+                    mode = (p < pend) ? 1u : 0u;
+                    if (mode) cv = ld64u(src, p);
                 }
             }
         }
