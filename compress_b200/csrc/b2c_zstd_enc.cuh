@@ -635,12 +635,15 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         // sees at most nlit / 512 + 4 literals, so a counter cannot wrap.  Four literals per load; equal symbols inside
         // a word are merged so the four updates are independent.  Warps 16..31 count the sequence codes and copy the
         // literals out meanwhile.
-        constexpr int LH_WARPS = 16;
+#ifndef ENC_LH_WARPS
+#define ENC_LH_WARPS 8
+#endif
+        constexpr int LH_WARPS = ENC_LH_WARPS;   // literal counting warps (8..16); the rest count codes and copy literals out
         uint8_t *lcolA = smem + ENC_SMEM_L;        // tables 0..7  [8][256][32] u8
         uint8_t *lcolB = smem + ENC_SMEM_SRC;      // tables 8..15 (src is dead)
         for (uint32_t i = tid; i < 8 * 256 * 32 / 4; i += ENC_NT) {
             reinterpret_cast<uint32_t *>(lcolA)[i] = 0;
-            reinterpret_cast<uint32_t *>(lcolB)[i] = 0;
+            if (LH_WARPS > 8 && i < (LH_WARPS - 8) * 256 * 32 / 4) reinterpret_cast<uint32_t *>(lcolB)[i] = 0;
         }
         __syncthreads();
         B2C_PHASE(12);
@@ -668,11 +671,24 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             }
         } else {
             // sequence-code counts, ballot style (lane l owns the codes whose low 5 bits equal l), kept in registers
-            for (uint32_t base = (w - LH_WARPS) * 32; base < nseq; base += (ENC_NW - LH_WARPS) * 32) {
-                const uint32_t i = base + lane;
-                const bool valid = i < nseq;
+            // (codes come back from L2: four rounds of loads are put in flight before the first one is used)
+            constexpr uint32_t STEP = (ENC_NW - LH_WARPS) * 32;
+            for (uint32_t base = (w - LH_WARPS) * 32; base < nseq; base += 4 * STEP) {
+                uint32_t cv3[4][3];
 #pragma unroll
-                for (int c = 0; c < 3; c++) warp_hist_acc<6>(valid ? (uint32_t)W->codes[c][i] : 0u, valid, seqCnt[c], lane);
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = base + u * STEP + lane;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) cv3[u][c] = (i < nseq) ? (uint32_t)W->codes[c][i] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool valid = base + u * STEP + lane < nseq;
+                    if (base + u * STEP < nseq) {      // warp-uniform
+#pragma unroll
+                        for (int c = 0; c < 3; c++) warp_hist_acc<6>(cv3[u][c], valid, seqCnt[c], lane);
+                    }
+                }
             }
             // literals to the work record (coalesced 16-byte stores)
             const uint4 *s4 = reinterpret_cast<const uint4 *>(lit);
