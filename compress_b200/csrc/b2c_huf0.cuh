@@ -82,7 +82,7 @@ B2C_DEV int64_t huf0_decompress_block(DecWarp *dw, const uint8_t *src, uint32_t 
     uint32_t tl = 0;
     const int used = dec_huf_read_table(dw, src, n, &tl, lane);
     if (used < 0) return HUF0_ERR_CORRUPT;
-    const int e = dec_huf_streams(dw->hufDt, tl, src + used, n - (uint32_t)used, dst, dstSize, four, lane);
+    const int e = dec_huf_streams<true>(dw->hufDt, tl, src + used, n - (uint32_t)used, dst, dstSize, four, lane);
     if (__any_sync(FULLMASK, e != 0)) return HUF0_ERR_CORRUPT;
     return (int64_t)dstSize;
 }
