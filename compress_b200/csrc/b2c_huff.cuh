@@ -252,6 +252,35 @@ B2C_DEV void huf_bt_stats(HufWork *hw, uint32_t n, unsigned tid) {
 // huffSort: rank = #symbols ordered before me (count desc, symbol asc); zero counts included
 B2C_DEV void huf_bt_sort(HufWork *hw, unsigned tid, unsigned nthreads) {
     uint32_t symbolLen = hw->symbolLen;
+    if (nthreads == 32) {
+        // one warp: bitonic sort of the 256 keys count << 8 | (255 - symbol), descending, in place in ncount[1..256]
+        // (symbols >= symbolLen have count 0 and the smallest keys, so the first symbolLen slots are the ranking)
+        uint32_t *K = hw->ncount + 1;
+        for (unsigned s = tid; s < 256; s += 32) K[s] = (hw->count[s] << 8) | (255u - s);
+        __syncwarp();
+        for (unsigned k = 2; k <= 256; k <<= 1) {
+            for (unsigned j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+                for (unsigned m = 0; m < 4; m++) {
+                    const unsigned t = tid + 32 * m;                       // pair index 0..127
+                    const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const unsigned q = i | j;
+                    const uint32_t a = K[i], b = K[q];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) { K[i] = b; K[q] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        for (unsigned r = tid; r < symbolLen; r += 32) {
+            const uint32_t key = K[r];
+            hw->nsym[1 + r] = (uint8_t)(255u - (key & 255u));
+            hw->nparent[1 + r] = 0; hw->nbits[1 + r] = 0;
+            K[r] = key >> 8;
+        }
+        for (unsigned s = tid; s < 256; s += 32) hw->ctBits[s] = 0;
+        return;
+    }
     for (unsigned s = tid; s < symbolLen; s += nthreads) {
         uint32_t c = hw->count[s];
         uint32_t r = 0;
@@ -320,6 +349,25 @@ B2C_DEV void huf_bt_bits(HufWork *hw, unsigned tid, unsigned nthreads) {
 // canonical values: symbol order within each length (compress.go:552-564)
 B2C_DEV void huf_bt_vals(HufWork *hw, unsigned tid, unsigned nthreads) {
     uint32_t symbolLen = hw->symbolLen;
+    if (nthreads == 32) {
+        // one warp: running count per code length, a ballot per length and 32 symbols
+        uint32_t run[HUF_TABLELOG_MAX + 1];
+#pragma unroll
+        for (int b = 0; b <= HUF_TABLELOG_MAX; b++) run[b] = 0;
+        for (unsigned s0 = 0; s0 < symbolLen; s0 += 32) {
+            const unsigned s = s0 + tid;
+            const uint32_t mb = (s < symbolLen) ? hw->ctBits[s] : 0u;
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 1; b <= HUF_TABLELOG_MAX; b++) {
+                const unsigned m = __ballot_sync(FULLMASK, mb == (uint32_t)b);
+                if (mb == (uint32_t)b) v = hw->scan[b] + run[b] + (uint32_t)__popc(m & ((1u << tid) - 1));
+                run[b] += (uint32_t)__popc(m);
+            }
+            if (s < symbolLen) hw->ctVal[s] = (uint16_t)v;
+        }
+        return;
+    }
     for (unsigned s = tid; s < symbolLen; s += nthreads) {
         uint32_t b = hw->ctBits[s];
         uint32_t v = 0;

@@ -37,9 +37,14 @@ def test_no_device_fails_loudly():
         pytest.skip("GPU present")
     assert _lib.lib.b2c_device_count() == 0
     assert not _lib.lib.b2c_ctx_create(0, 16)
-    from compress_b200 import zstd
-    with pytest.raises(_lib.B2CError):
-        zstd.Encoder()
+    from compress_b200 import zstd, s2, huff0
+    for ctor in (zstd.Encoder, zstd.Decoder, s2.Codec, huff0.Codec):
+        with pytest.raises(_lib.B2CError):
+            ctor()
+    # the entry points themselves refuse to run without a context (no silent CPU path)
+    assert _lib.lib.b2c_zstd_encode_device(None, 1, 3, None, 0, None, 0, None, 0, None, 1, None) == -100
+    assert _lib.lib.b2c_s2_decode_device(None, None, 0, None, None, None, 0, None, 0, None, 1, None) == -100
+    assert _lib.lib.b2c_huf_compress_device(None, 1, None, 0, None, 0, None, 0, None, 1, None) == -100
 
 
 def test_bound_matches_reference_formula():
@@ -49,3 +54,16 @@ def test_bound_matches_reference_formula():
     L = H.oracle()
     for n in [0, 1, 255, 256, 1000, 65535, 65536]:
         assert _lib.lib.b2c_zstd_bound(n, 1) == L.orc_zstd_max_encoded_size(n, 1, 1)
+
+
+def test_s2_bound_matches_reference_formula():
+    # s2.MaxEncodedLen (s2/encode.go:389-418) vs the oracle's restatement
+    import ctypes as c
+    import helpers as H
+    from compress_b200 import _lib
+    L = H.oracle()
+    L.orc_s2_max_encoded_len.restype = c.c_int64
+    L.orc_s2_max_encoded_len.argtypes = [c.c_int64]
+    for n in [0, 1, 59, 60, 61, 255, 256, 257, 65535, 65536, 1 << 24, (1 << 32) - 11]:
+        assert _lib.lib.b2c_s2_bound(n) == L.orc_s2_max_encoded_len(n), n
+    assert _lib.lib.b2c_s2_bound((1 << 32) - 5) == 0 and L.orc_s2_max_encoded_len((1 << 32) - 5) == -1
