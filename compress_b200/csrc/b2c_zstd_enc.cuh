@@ -77,9 +77,10 @@ struct alignas(16) ChunkWork {
     uint8_t ncount[3][96];
     FseCTable tbl[3];                      // the table each chain uses (new, predefined copy, or RLE)
     alignas(16) uint8_t lit[ENC_MAX_CHUNK + 64];
-    alignas(16) uint32_t seqLM[ENC_MAXSEQ];   // litLen | (matchLen - 3) << 16
+    uint16_t seqLL[ENC_MAXSEQ];
+    uint16_t seqML[ENC_MAXSEQ];
     uint32_t seqOF[ENC_MAXSEQ];
-    alignas(16) uint32_t codes4[ENC_MAXSEQ];  // llCode | ofCode << 8 | mlCode << 16 (byte TBL_x of the word)
+    alignas(16) uint8_t codes[3][ENC_MAXSEQ];
     alignas(16) uint16_t stb[3][ENC_MAXSEQ];
 };
 
@@ -607,9 +608,10 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             // repeat code 1 (= offset of the previous sequence, valid with litLen > 0; seqdec.go:463-500)
             const bool isrep = (gi > 0) && (d0 == pOff) && (ll > 0);
             const uint32_t ofv = isrep ? 1u : d0 + 3;
-            // three 4-byte stores per sequence (neighbouring threads write neighbouring words)
-            W->seqLM[gi] = ll | ((l0 - 3) << 16); W->seqOF[gi] = ofv;
-            W->codes4[gi] = (seq_ll_code(ll) << (8 * TBL_LL)) | (highbit32(ofv) << (8 * TBL_OF)) | (seq_ml_code(l0 - 3) << (8 * TBL_ML));
+            W->seqLL[gi] = (uint16_t)ll; W->seqML[gi] = (uint16_t)(l0 - 3); W->seqOF[gi] = ofv;
+            W->codes[TBL_LL][gi] = (uint8_t)seq_ll_code(ll);
+            W->codes[TBL_OF][gi] = (uint8_t)highbit32(ofv);
+            W->codes[TBL_ML][gi] = (uint8_t)seq_ml_code(l0 - 3);
             prevE = s0 + l0; mrun += l0; pOff = d0; gi++;
         }
         B2C_PHASE(11);
@@ -620,8 +622,8 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     __syncthreads();
     // single-sequence RLE block test (blockenc.go:484-493); nlit <= 1
     if (kind == 0 && nseq == 1 && nlit <= 1 && tid == 0) {
-        uint32_t ll0 = W->seqLM[0] & 0xffff, of0 = W->seqOF[0];
-        if (ll0 == nlit && of0 - 3 == 1) { sh->kind = 2; sh->rleLen = (W->seqLM[0] >> 16) + 3 + ll0; }
+        uint32_t ll0 = W->seqLL[0], of0 = W->seqOF[0];
+        if (ll0 == nlit && of0 - 3 == 1) { sh->kind = 2; sh->rleLen = (uint32_t)W->seqML[0] + 3 + ll0; }
     }
     __syncthreads();
     kind = sh->kind;
@@ -676,9 +678,8 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const uint32_t i = base + u * STEP + lane;
-                    const uint32_t cw4 = (i < nseq) ? W->codes4[i] : 0u;
 #pragma unroll
-                    for (int c = 0; c < 3; c++) cv3[u][c] = (cw4 >> (8 * c)) & 0xff;
+                    for (int c = 0; c < 3; c++) cv3[u][c] = (i < nseq) ? (uint32_t)W->codes[c][i] : 0u;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -738,7 +739,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         if (P.dbg_hdr) {
             for (uint32_t i = tid; i < nseq && i < P.dbg_seq_cap; i += ENC_NT) {
                 uint32_t *d = P.dbg_seqs + ((uint64_t)chunk * P.dbg_seq_cap + i) * 3;
-                d[0] = W->seqLM[i] & 0xffff; d[1] = W->seqLM[i] >> 16; d[2] = W->seqOF[i];
+                d[0] = W->seqLL[i]; d[1] = W->seqML[i]; d[2] = W->seqOF[i];
             }
             for (uint32_t i = tid; i < nlit; i += ENC_NT) P.dbg_lits[(uint64_t)chunk * 65536 + i] = lit[i];
         }
@@ -781,7 +782,7 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
             for (uint32_t s = lane; s < 64; s += 32) sw->hist[which][s] = W->seqHist[which][s];
             if (lane == 0) sw->maxSym[which] = W->maxSym[which];
             __syncwarp();
-            seq_build_table(sw, which, nseq, (W->codes4[0] >> (8 * which)) & 0xff, lane);
+            seq_build_table(sw, which, nseq, W->codes[which][0], lane);
             __syncwarp();
             // publish the table this chain will use
             const FseCTable *t = seq_table(sw, which);
@@ -808,7 +809,7 @@ constexpr uint32_t CHAIN_SMEM_BYTES = CHAIN_NT * CHAIN_SMEM_WORDS_PER_LANE * 4;
 // K3: one lane per (chunk, table) walks the tANS state chain from the last sequence to the first
 // (blockenc.go:757-803 restated as three independent recurrences) and stores, per sequence, the bits it emits:
 // stb[i] = value | nbBits << 12.  The recurrence is latency-bound, so the loop keeps the dependent path to
-// add/shift/add + one shared-memory load per step: codes arrive eight at a time (two 16-byte loads, requested two
+// add/shift/add + one shared-memory load per step: codes arrive eight at a time (one 8-byte load, requested two
 // blocks ahead), their symbol transforms are fetched up front, results leave as one 16-byte store per 8 steps.
 // Per-lane tables are interleaved so lane l only touches bank l: next states are kept as u8 offsets from tableSize
 // (4 per word), 45 KB per CTA, so five CTAs fit an SM and a 16 384-chunk batch is a single wave.
@@ -839,14 +840,12 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
         }
     }
     __syncwarp();
-    const uint32_t *codes4 = W->codes4;
-    const uint32_t csh = 8 * which;                                 // this table's byte of the code word
+    const uint8_t *codes = W->codes[which];
     uint16_t *stb = W->stb[which];
     uint32_t state = 0;
     const bool run = live && !useRLE && nseq >= 1;
     if (run) {
-        const uint32_t c0 = (codes4[nseq - 1] >> csh) & 0xff;
-        const uint32_t e = tSym[(c0 < 56u ? c0 : 0u) * 32];
+        const uint32_t e = tSym[(codes[nseq - 1] < 56u ? codes[nseq - 1] : 0u) * 32];
         const uint32_t dnb = e & 0x1fffffu;
         const int32_t dfs = (int32_t)(e >> 21) - 512;
         const uint32_t nbBitsOut = (dnb + (1u << 15)) >> 16;
@@ -857,22 +856,20 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
     const int32_t top = run ? (int32_t)nseq - 2 : -1;
     const int32_t blk = top >> 3;                                  // -1 when there is nothing to do
     const uint32_t nblk = warp_max((uint32_t)(blk + 1));
-    const uint4 *c16 = reinterpret_cast<const uint4 *>(codes4);     // block k = c16[2k], c16[2k + 1]
-    const uint4 z4 = make_uint4(0, 0, 0, 0);
-    uint4 cwA0 = z4, cwA1 = z4, cwB0 = z4, cwB1 = z4;
-    if (blk >= 0) { cwA0 = c16[2 * blk]; cwA1 = c16[2 * blk + 1]; }
-    if (blk >= 1) { cwB0 = c16[2 * blk - 2]; cwB1 = c16[2 * blk - 1]; }
+    const uint2 *c8 = reinterpret_cast<const uint2 *>(codes);
+    uint2 cwA = make_uint2(0, 0), cwB = make_uint2(0, 0);
+    if (blk >= 0) cwA = c8[blk];
+    if (blk >= 1) cwB = c8[blk - 1];
     for (uint32_t it = 0; it < nblk; it++) {
         const int32_t k = blk - (int32_t)it;
         if (k >= 0) {
-            uint4 cwC0 = z4, cwC1 = z4;
-            if (k >= 2) { cwC0 = c16[2 * k - 4]; cwC1 = c16[2 * k - 3]; }
-            const uint32_t cw[8] = {cwA0.x, cwA0.y, cwA0.z, cwA0.w, cwA1.x, cwA1.y, cwA1.z, cwA1.w};
+            uint2 cwC = make_uint2(0, 0);
+            if (k >= 2) cwC = c8[k - 2];
             uint32_t e[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                uint32_t code = (cw[j] >> csh) & 63u;
-                if (code >= 56u) code = 0;     // words past the last sequence are not codes
+                uint32_t code = (((j < 4) ? cwA.x : cwA.y) >> (8 * (j & 3))) & 63u;
+                if (code >= 56u) code = 0;     // bytes past the last sequence are not codes
                 e[j] = tSym[code * 32];
             }
             uint32_t o[4] = {0, 0, 0, 0};
@@ -885,7 +882,7 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
                 }
             }
             *reinterpret_cast<uint4 *>(stb + 8 * k) = make_uint4(o[0], o[1], o[2], o[3]);
-            cwA0 = cwB0; cwA1 = cwB1; cwB0 = cwC0; cwB1 = cwC1;
+            cwA = cwB; cwB = cwC;
         }
     }
     if (live) {
@@ -1005,7 +1002,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         const uint32_t bsOff = tblOff + W->ncountLen[0] + W->ncountLen[1] + W->ncountLen[2];
 
         // ------------------------------------------------------------ sequence bitstream sizes
-        const uint32_t *codes4 = W->codes4;
+        const uint8_t *cLL = W->codes[TBL_LL], *cOF = W->codes[TBL_OF], *cML = W->codes[TBL_ML];
         const uint16_t *stbLL = W->stb[TBL_LL], *stbOF = W->stb[TBL_OF], *stbML = W->stb[TBL_ML];
         const uint32_t per = (nseq + PACK_NT - 1) / PACK_NT;
         uint32_t tA = tid * per, tB = tA + per;
@@ -1014,8 +1011,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         uint32_t mybits = 0;
         for (uint32_t t = tA; t < tB; t++) {
             uint32_t idx = nseq - 1 - t;
-            const uint32_t c4 = B2C_LDG(codes4 + idx);
-            const uint32_t cl = c4 & 0xff, co = (c4 >> 8) & 0xff, cm = (c4 >> 16) & 0xff;
+            uint32_t cl = B2C_LDG(cLL + idx), co = B2C_LDG(cOF + idx), cm = B2C_LDG(cML + idx);
             mybits += seq_ll_bits(cl) + seq_ml_bits(cm) + co;
             if (t) mybits += (uint32_t)(B2C_LDG(stbLL + idx) >> 12) + (uint32_t)(B2C_LDG(stbOF + idx) >> 12) + (uint32_t)(B2C_LDG(stbML + idx) >> 12);
         }
@@ -1045,10 +1041,8 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
                 br.init(reinterpret_cast<uint32_t *>(stage), bsOff * 8 + exBits);
                 for (uint32_t t = tA; t < tB; t++) {
                     uint32_t idx = nseq - 1 - t;
-                    const uint32_t c4 = B2C_LDG(codes4 + idx);
-                    const uint32_t cl = c4 & 0xff, co = (c4 >> 8) & 0xff, cm = (c4 >> 16) & 0xff;
-                    const uint32_t vLM = B2C_LDG(W->seqLM + idx), vOF = B2C_LDG(W->seqOF + idx);
-                    const uint32_t vLL = vLM & 0xffff, vML = vLM >> 16;
+                    uint32_t cl = B2C_LDG(cLL + idx), co = B2C_LDG(cOF + idx), cm = B2C_LDG(cML + idx);
+                    const uint32_t vLL = B2C_LDG(W->seqLL + idx), vML = B2C_LDG(W->seqML + idx), vOF = B2C_LDG(W->seqOF + idx);
                     if (t) {
                         uint32_t so = B2C_LDG(stbOF + idx), sm = B2C_LDG(stbML + idx), sl = B2C_LDG(stbLL + idx);
                         br.add(so & 0xfff, so >> 12);
