@@ -298,7 +298,7 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     P.dbg_cycles = dbg_cycles;
     unsigned sms = (unsigned)ctx->sm_count;
     unsigned g1 = sms < nchunks ? sms : nchunks;
-    unsigned g2 = sms * 16 < nchunks ? sms * 16 : nchunks;
+    unsigned g2 = sms * 8 < nchunks ? sms * 8 : nchunks;
     cudaEvent_t *pe = nullptr;
     if (ctx->prof) {
         while (ctx->pev.size() < ctx->pev_used + 6) {
@@ -318,7 +318,7 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     PEV(1);
     b2c_zstd_parse_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
     PEV(2);
-    b2c_zstd_tables_kernel<<<g2, TABLES_NT, 0, st>>>(P);
+    b2c_zstd_tables_kernel<<<g2, 128, 0, st>>>(P);
     PEV(3);
     b2c_zstd_chains_kernel<<<(nchunks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, st>>>(P);
     PEV(4);

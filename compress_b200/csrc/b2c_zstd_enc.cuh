@@ -753,7 +753,6 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
 // ------------------------------------------------------------------------------------------------ K2
 // One 128-thread CTA per chunk.  Warp 0 builds the Huffman table cooperatively (rank sort with 32 lanes, the
 // serial tree / setMaxHeight / table serialisation on lane 0); lane 0 of warps 1..3 builds one FSE table each.
-constexpr int TABLES_NT = 64;   // K2 block: warp 0 builds the Huffman table, warp 1 the three FSE tables
 struct TablesShared {
     HufWork hw;
     SeqWork sw;
@@ -776,25 +775,22 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
         }
         if (lane == 0) { W->hufStatus = (uint32_t)hw->status; W->hufTableLog = hw->tableLog; W->tableDescLen = hw->tableDescLen; }
     } else {
-        // warp 1: the three FSE tables one after the other (together about as long as the Huffman build of warp 0)
+        const int which = (int)w - 1;
         SeqWork *sw = &ts->sw;
-        for (int which = 0; which < 3; which++) {
-            for (uint32_t s = lane; s < 64; s += 32) sw->hist[which][s] = W->seqHist[which][s];
-            if (lane == 0) sw->maxSym[which] = W->maxSym[which];
-            __syncwarp();
-            seq_build_table(sw, which, nseq, W->codes[which][0], lane);
-            __syncwarp();
-            // publish the table this chain will use
-            const FseCTable *t = seq_table(sw, which);
-            const uint32_t *s32 = reinterpret_cast<const uint32_t *>(t);
-            uint32_t *d32 = reinterpret_cast<uint32_t *>(&W->tbl[which]);
-            for (uint32_t i = lane; i < sizeof(FseCTable) / 4; i += 32) d32[i] = s32[i];
-            for (uint32_t i = lane; i < sw->ncountLen[which] && i < 96; i += 32) W->ncount[which][i] = sw->ncount[which][i];
-            if (lane == 0) {
-                W->mode[which] = sw->mode[which]; W->ncountLen[which] = sw->ncountLen[which];
-                if (sw->ncountLen[which] == SEQ_TABLE_ERR) { W->ncountLen[which] = 0; W->kind = 1; }  // internal error: store raw
-            }
-            __syncwarp();
+        for (uint32_t s = lane; s < 64; s += 32) sw->hist[which][s] = W->seqHist[which][s];
+        if (lane == 0) sw->maxSym[which] = W->maxSym[which];
+        __syncwarp();
+        seq_build_table(sw, which, nseq, W->codes[which][0], lane);
+        __syncwarp();
+        // publish the table this chain will use
+        const FseCTable *t = seq_table(sw, which);
+        const uint32_t *s32 = reinterpret_cast<const uint32_t *>(t);
+        uint32_t *d32 = reinterpret_cast<uint32_t *>(&W->tbl[which]);
+        for (uint32_t i = lane; i < sizeof(FseCTable) / 4; i += 32) d32[i] = s32[i];
+        for (uint32_t i = lane; i < sw->ncountLen[which] && i < 96; i += 32) W->ncount[which][i] = sw->ncount[which][i];
+        if (lane == 0) {
+            W->mode[which] = sw->mode[which]; W->ncountLen[which] = sw->ncountLen[which];
+            if (sw->ncountLen[which] == SEQ_TABLE_ERR) { W->ncountLen[which] = 0; W->kind = 1; }  // internal error: store raw
         }
     }
 }
@@ -1243,7 +1239,7 @@ extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_zstd_parse_kernel(Zs
     uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
     for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_ZSTD>(smem, P, c, scratch);
 }
-extern "C" __global__ void __launch_bounds__(TABLES_NT) b2c_zstd_tables_kernel(ZstdEncParams P) {
+extern "C" __global__ void __launch_bounds__(128) b2c_zstd_tables_kernel(ZstdEncParams P) {
     __shared__ TablesShared ts;
     if (threadIdx.x < 3) seq_build_predef(&ts.sw, (int)threadIdx.x);
     __syncthreads();
