@@ -73,14 +73,10 @@ struct BrB {
     const uint8_t *in; uint32_t len; uint32_t total; uint32_t pos;
     uint64_t bits; uint32_t avail; int32_t nextByte;     // stream bytes below nextByte are not in `bits` yet
     uint32_t ahead;                                      // the 32 bits below nextByte, requested one refill early
-    B2C_DEV uint32_t load32(int32_t idx) const {
-        if (idx >= 0 && (uint32_t)idx + 8 <= len) {
-            const uintptr_t a = reinterpret_cast<uintptr_t>(in + idx);
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-            const uint32_t sh = (uint32_t)(a & 3) * 8;
-            const uint32_t w0 = w[0];
-            return sh ? __funnelshift_r(w0, w[1], sh) : w0;
-        }
+    // word-aligned view of the stream for the refills: in + nextByte keeps its alignment (nextByte moves by 4), so
+    // every refill needs one new aligned word and a fixed funnel shift
+    const uint32_t *wp; uint32_t wsh, whi;               // wp = aligned word holding byte nextByte; whi = *wp
+    B2C_DEV uint32_t load32_slow(int32_t idx) const {    // bytes outside [0, len) read as zero
         uint32_t v = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -89,24 +85,41 @@ struct BrB {
         }
         return v;
     }
+    // the 32 bits just below nextByte; moves the word view down by one word
+    B2C_DEV uint32_t fetch_below() {
+        uint32_t v;
+        if (nextByte >= 4) {
+            const uint32_t lo = wp[-1];
+            v = wsh ? __funnelshift_r(lo, whi, wsh) : lo;
+            whi = lo;
+        } else {
+            v = load32_slow(nextByte - 4);
+        }
+        wp -= 1;
+        return v;
+    }
     B2C_DEV int init(const uint8_t *p, uint32_t n) {
-        in = p; len = n; total = 0; pos = 0; bits = 0; avail = 0; nextByte = 0; ahead = 0;
+        in = p; len = n; total = 0; pos = 0; bits = 0; avail = 0; nextByte = 0; ahead = 0; wp = nullptr; wsh = 0; whi = 0;
         if (n < 1) return -1;
         const uint8_t v = p[n - 1];
         if (v == 0) return -1;
         total = 8 * (n - 1) + highbit32(v);
         const int32_t cbyte = (int32_t)((total + 7) >> 3) - 8;        // window = the 8 bytes ending at the top payload byte
-        const uint64_t win = (uint64_t)load32(cbyte) | ((uint64_t)load32(cbyte + 4) << 32);
+        const uint64_t win = (uint64_t)load32_slow(cbyte) | ((uint64_t)load32_slow(cbyte + 4) << 32);
         const uint32_t k = (uint32_t)((int32_t)total - 8 * cbyte);    // payload bits inside the window: 57..64
         bits = win << (64 - k);
         avail = k; nextByte = cbyte;
-        ahead = load32(cbyte - 4);
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p) + (uintptr_t)(intptr_t)cbyte;   // may lie below p for tiny streams
+        wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        wsh = (uint32_t)(a & 3) * 8;
+        whi = (cbyte >= 4) ? *wp : 0u;                   // only used by the fast path (nextByte >= 4)
+        ahead = fetch_below();
         return 0;
     }
     B2C_DEV void refill32() {     // requires avail <= 32
         bits |= (uint64_t)ahead << (32 - avail);
         avail += 32; nextByte -= 4;
-        ahead = load32(nextByte - 4);
+        ahead = fetch_below();
     }
     // next n bits, 1 <= n <= 32, without consuming them
     B2C_DEV uint32_t peek(uint32_t n) {
