@@ -70,7 +70,7 @@ struct ZstdDecParams {
 // dry, from two aligned word loads (byte loads with zero fill at the two ends of the buffer).  All 32-bit arithmetic:
 // a stream is at most one compressed block (128 KiB).
 struct BrB {
-    const uint8_t *in; uint32_t len; uint32_t total; uint32_t pos;
+    const uint8_t *in; uint32_t len; uint32_t total; uint32_t fed;   // fed = bits moved into the window so far
     uint64_t bits; uint32_t avail; int32_t nextByte;     // stream bytes below nextByte are not in `bits` yet
     uint32_t ahead;                                      // the 32 bits below nextByte, requested one refill early
     // word-aligned view of the stream for the refills: in + nextByte keeps its alignment (nextByte moves by 4), so
@@ -99,7 +99,7 @@ struct BrB {
         return v;
     }
     B2C_DEV int init(const uint8_t *p, uint32_t n) {
-        in = p; len = n; total = 0; pos = 0; bits = 0; avail = 0; nextByte = 0; ahead = 0; wp = nullptr; wsh = 0; whi = 0;
+        in = p; len = n; total = 0; fed = 0; bits = 0; avail = 0; nextByte = 0; ahead = 0; wp = nullptr; wsh = 0; whi = 0;
         if (n < 1) return -1;
         const uint8_t v = p[n - 1];
         if (v == 0) return -1;
@@ -108,7 +108,7 @@ struct BrB {
         const uint64_t win = (uint64_t)load32_slow(cbyte) | ((uint64_t)load32_slow(cbyte + 4) << 32);
         const uint32_t k = (uint32_t)((int32_t)total - 8 * cbyte);    // payload bits inside the window: 57..64
         bits = win << (64 - k);
-        avail = k; nextByte = cbyte;
+        avail = k; fed = k; nextByte = cbyte;
         const uintptr_t a = reinterpret_cast<uintptr_t>(p) + (uintptr_t)(intptr_t)cbyte;   // may lie below p for tiny streams
         wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         wsh = (uint32_t)(a & 3) * 8;
@@ -118,23 +118,23 @@ struct BrB {
     }
     B2C_DEV void refill32() {     // requires avail <= 32
         bits |= (uint64_t)ahead << (32 - avail);
-        avail += 32; nextByte -= 4;
+        avail += 32; fed += 32; nextByte -= 4;
         ahead = fetch_below();
     }
-    // next n bits, 1 <= n <= 32, without consuming them
+    B2C_DEV uint32_t pos() const { return fed - avail; }          // bits consumed
+    // next n bits, 0 <= n <= 32, without consuming them
     B2C_DEV uint32_t peek(uint32_t n) {
         if (avail < n) refill32();
-        return (uint32_t)(bits >> (64 - n));
+        return (uint32_t)((bits >> 1) >> (63 - n));
     }
     // consume n bits; n <= the n of the preceding peek
-    B2C_DEV void skip(uint32_t n) { bits <<= n; avail -= n; pos += n; }
+    B2C_DEV void skip(uint32_t n) { bits <<= n; avail -= n; }
     B2C_DEV uint32_t read(uint32_t n) {
-        if (n == 0) return 0;
         const uint32_t v = peek(n);
         skip(n);
         return v;
     }
-    B2C_DEV bool finished() const { return pos >= total; }
+    B2C_DEV bool finished() const { return pos() >= total; }
 };
 
 // forward LSB-first bit fetch with zero fill (readNCount)
@@ -331,7 +331,7 @@ B2C_DEV int dec_fse_weights(DecWarp *dw, const uint8_t *in, uint32_t n, unsigned
 #undef WGET
     __syncwarp();
     if (rc) return -1;
-    if (br.pos > br.total) return -1;
+    if (br.pos() > br.total) return -1;
     return (int)o;
 }
 
@@ -442,7 +442,7 @@ __device__ __noinline__ int dec_huf_stream(const uint16_t *dt, uint32_t tl, cons
         dst[i] = (uint8_t)s0;
     }
 #undef HUF_ONE
-    return br.pos == br.total ? 0 : -1;
+    return br.pos() == br.total ? 0 : -1;
 }
 
 // Decompress1X / Decompress4X body after the table (huff0/decompress.go:234-, :622-): 4 streams on 4 lanes.
@@ -677,7 +677,7 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const DecCta *dc, const uint8_t *
                         uint32_t myLL = 0, myML = 0, myMO = 0;
                         bool myOver = false;
                         for (uint32_t j = 0; j < want; j++) {
-                            if (br.pos > br.total) { if (lane == j) myOver = true; cnt = j + 1; break; }
+                            if (br.pos() > br.total) { if (lane == j) myOver = true; cnt = j + 1; break; }
                             int64_t ll = llS.baseline, ml = mlS.baseline, mo = ofS.baseline;
                             const uint32_t moB = (ofS.bits >> 8) & 0xff;
                             mo += br.read(moB);
@@ -784,7 +784,7 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const DecCta *dc, const uint8_t *
                     if (o + rest > outCap) DFAIL(DEC_ERR_DST);
                     for (uint32_t k = lane; k < rest; k += 32) out[o + k] = literals[litPos + k];
                     o += rest;
-                    if (br.pos != br.total) DFAIL(DEC_ERR_CORRUPT);
+                    if (br.pos() != br.total) DFAIL(DEC_ERR_CORRUPT);
                 }
                 __syncwarp();
             }
