@@ -419,6 +419,17 @@ __device__ __noinline__ int dec_huf_stream(const uint16_t *dt, uint32_t tl, cons
         (out) = (uint32_t)(e_ >> 8);                                                                   \
     } while (0)
     if (!WORDS) {
+        // two symbols per end test and refill test (2 * tl <= 22 bits; a refill leaves at least 32)
+        for (; i + 2 <= count; i += 2) {
+            if (br.finished()) return -1;
+            if (br.avail < 2 * tl) br.refill32();
+            const uint16_t e0 = dt[(uint32_t)(br.bits >> (64 - tl))];
+            br.skip(e0 & 0xff);
+            const uint16_t e1 = dt[(uint32_t)(br.bits >> (64 - tl))];
+            br.skip(e1 & 0xff);
+            dst[i] = (uint8_t)(e0 >> 8);
+            dst[i + 1] = (uint8_t)(e1 >> 8);
+        }
         for (; i < count; i++) {
             if (br.finished()) return -1;
             uint32_t s0; HUF_ONE(s0);
