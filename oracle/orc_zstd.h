@@ -59,7 +59,7 @@ int orc_blockenc_encode(orc_blockenc *b, const uint8_t *org, size_t orgLen, int 
 void orc_enc_fast_nohist(orc_blockenc *b, const uint8_t *src, size_t n);   /* enc_fast.go:294 */
 void orc_enc_dfast_nohist(orc_blockenc *b, const uint8_t *src, size_t n);  /* enc_dfast.go:372 */
 
-/* Encoder.EncodeAll (zstd/encoder.go:722-839). level: 1 fastest, 2 default. returns size or negative. */
+/* Encoder.EncodeAll (zstd/encoder.go:722-839). level: 1 fastest, 2 default, 3 better. returns size or negative. */
 int64_t orc_zstd_encode_all(const uint8_t *src, size_t n, int level, int crc, uint8_t *dst, size_t cap);
 size_t orc_zstd_max_encoded_size(size_t n, int level, int crc); /* MaxEncodedSize, encoder.go:843 */
 

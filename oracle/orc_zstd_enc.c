@@ -783,6 +783,8 @@ static int32_t window_size_for(int64_t size, int32_t maxMatchOff) { /* fastBase.
 
 void orc_dfast_encode_all_blocks(orc_blockenc *blk, const uint8_t *src, size_t n, size_t blockSize,
                                  uint8_t *dst, size_t cap, size_t *pos, int *err);
+void orc_better_encode_all_blocks(orc_blockenc *blk, const uint8_t *src, size_t n, size_t blockSize,
+                                  uint8_t *dst, size_t cap, size_t *pos, int *err);
 
 static int64_t encode_all_impl(orc_zstd_cctx *cc, const uint8_t *src, size_t n, int level, int crc, uint8_t *dst, size_t cap);
 
@@ -823,7 +825,7 @@ ORC_API int64_t orc_zstd_bench_chunks(orc_zstd_cctx *cc, const uint8_t *src, siz
 
 static int64_t encode_all_impl(orc_zstd_cctx *cc, const uint8_t *src, size_t n, int level, int crc, uint8_t *dst, size_t cap) {
     init_predef();
-    if (level != 1 && level != 2) return ORC_ERR_UNSUPPORTED;
+    if (level < 1 || level > 3) return ORC_ERR_UNSUPPORTED; /* SpeedFastest, SpeedDefault, SpeedBetterCompression */
     const size_t blockSize = (level == 1) ? (1u << 16) : ORC_ZSTD_MAX_BLOCK; /* encoder_options.go:41,248-252 */
     const int32_t windowSize = (level == 1) ? (4 << 20) : (8 << 20);
     size_t pos = 0;
@@ -840,6 +842,8 @@ static int64_t encode_all_impl(orc_zstd_cctx *cc, const uint8_t *src, size_t n, 
     int err = 0;
     if (level == 2) {
         orc_dfast_encode_all_blocks(blk, src, n, blockSize, dst, cap, &pos, &err);
+    } else if (level == 3) {
+        orc_better_encode_all_blocks(blk, src, n, blockSize, dst, cap, &pos, &err);
     } else if (n <= blockSize) {
         orc_blockenc_reset(blk);
         blk->last = 1;
