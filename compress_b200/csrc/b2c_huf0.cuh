@@ -57,7 +57,7 @@ B2C_DEV void huf0_compress_block(Huf0Shared *sh, const Huf0Params &P, uint32_t c
     else if (four && n < 12) result = HUF0_ERR_INCOMPRESSIBLE;          // compress4X (compress.go:270)
     if (result == 0) {
         HufEncState st;
-        const uint32_t total = huf_enc_sizes(hw, in, n, four ? 1 : 0, tid, HUF0_NT, 0, &st);
+        const uint32_t total = huf_enc_sizes(hw, sh->whist, in, n, four ? 1 : 0, tid, HUF0_NT, 0, &st);   // whist is free again: reused as the packed code table
         bool bad = total >= n;                                          // wantSize = len(in) (WantLogLess 0)
         if (four) for (int k = 0; k < 4; k++) bad = bad || hw->streamBytes[k] > 65535;   // jump table limit (:288)
         if (bad) result = HUF0_ERR_INCOMPRESSIBLE;
@@ -67,7 +67,7 @@ B2C_DEV void huf0_compress_block(Huf0Shared *sh, const Huf0Params &P, uint32_t c
             uint32_t *o32 = reinterpret_cast<uint32_t *>(out);
             for (uint32_t i = tid; i < (total + 3) / 4; i += HUF0_NT) o32[i] = 0;
             __syncthreads();
-            huf_enc_pack(hw, in, four ? 1 : 0, out, 0, tid, HUF0_NT, 0, &st);
+            huf_enc_pack(hw, sh->whist, in, four ? 1 : 0, out, 0, tid, HUF0_NT, 0, &st);
             result = (int64_t)total;
         }
     }

@@ -470,15 +470,28 @@ struct HufEncState {
     uint32_t t;       // thread index inside the stream group
 };
 // returns payload bytes = table desc + (jump table) + streams
-B2C_DEV uint32_t huf_enc_sizes(HufWork *hw, const uint8_t *lit, uint32_t n, int four, unsigned tid,
+// pk: 256 words of caller-provided shared scratch; filled here with (code | nbits << 16) for huf_enc_pack.
+B2C_DEV uint32_t huf_enc_sizes(HufWork *hw, uint32_t *pk, const uint8_t *lit, uint32_t n, int four, unsigned tid,
                                unsigned nthreads, int bar_id, HufEncState *st) {
 #define HSYNC() do { group_sync(bar_id, (int)nthreads); } while (0)
     int nstreams = four ? 4 : 1;
     HufSeg sg = huf_thread_seg(n, nstreams, tid, nthreads);
     unsigned per = nthreads / (unsigned)nstreams;
     unsigned t = tid % per;
+    for (unsigned s = tid; s < 256; s += nthreads) pk[s] = (uint32_t)hw->ctVal[s] | ((uint32_t)hw->ctBits[s] << 16);
     uint32_t mybits = 0;
-    for (uint32_t r = sg.r0; r < sg.r1; r++) mybits += hw->ctBits[lit[sg.segStart + sg.segLen - 1 - r]];
+    {
+        // my symbols are the bytes [a, b) of lit; the sum does not depend on the order: aligned words in the middle
+        const uint8_t *cb = hw->ctBits;
+        uint32_t i = sg.segStart + sg.segLen - sg.r1;
+        const uint32_t b = sg.segStart + sg.segLen - sg.r0;
+        while (i < b && (reinterpret_cast<uintptr_t>(lit + i) & 3)) mybits += cb[lit[i++]];
+        for (; i + 4 <= b; i += 4) {
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(lit + i);
+            mybits += (uint32_t)cb[w & 255] + cb[(w >> 8) & 255] + cb[(w >> 16) & 255] + cb[w >> 24];
+        }
+        while (i < b) mybits += cb[lit[i++]];
+    }
     uint32_t total;
     uint32_t ex = group_scan_excl(mybits, hw->scan, bar_id, (int)nthreads, tid, &total);
     if (t == 0) hw->streamBits[sg.stream] = ex;  // temporarily: the stream's base in the global scan
@@ -499,16 +512,30 @@ B2C_DEV uint32_t huf_enc_sizes(HufWork *hw, const uint8_t *lit, uint32_t n, int 
     return totalBytes;
 }
 // stageBase: 4-byte aligned, zero-initialised words; payload starts at byte offset byteOff.
-B2C_DEV void huf_enc_pack(HufWork *hw, const uint8_t *lit, int four, uint8_t *stageBase, uint32_t byteOff,
-                          unsigned tid, unsigned nthreads, int bar_id, const HufEncState *st) {
+// pk: the table huf_enc_sizes filled (a barrier lies between the two calls).
+B2C_DEV void huf_enc_pack(HufWork *hw, const uint32_t *pk, const uint8_t *lit, int four, uint8_t *stageBase,
+                          uint32_t byteOff, unsigned tid, unsigned nthreads, int bar_id, const HufEncState *st) {
 #define HSYNC() do { group_sync(bar_id, (int)nthreads); } while (0)
     const HufSeg &sg = st->sg;
     {
         BitRun br;
         br.init(reinterpret_cast<uint32_t *>(stageBase), (byteOff + st->soff) * 8 + st->myoff);
-        for (uint32_t r = sg.r0; r < sg.r1; r++) {
-            uint32_t sym = lit[sg.segStart + sg.segLen - 1 - r];
-            br.add(hw->ctVal[sym], hw->ctBits[sym]);
+        // bytes [a, b) of lit, emitted from b-1 down to a; codes are <= 11 bits, so two go into one add
+        const uint32_t a = sg.segStart + sg.segLen - sg.r1;
+        uint32_t i = sg.segStart + sg.segLen - sg.r0;
+        while (i > a && (reinterpret_cast<uintptr_t>(lit + i) & 3)) {
+            const uint32_t e = pk[lit[--i]];
+            br.add(e & 0xffffu, e >> 16);
+        }
+        for (; i >= a + 4; i -= 4) {
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(lit + i - 4);
+            const uint32_t e3 = pk[w >> 24], e2 = pk[(w >> 16) & 255], e1 = pk[(w >> 8) & 255], e0 = pk[w & 255];
+            br.add((e3 & 0xffffu) | ((e2 & 0xffffu) << (e3 >> 16)), (e3 >> 16) + (e2 >> 16));
+            br.add((e1 & 0xffffu) | ((e0 & 0xffffu) << (e1 >> 16)), (e1 >> 16) + (e0 >> 16));
+        }
+        while (i > a) {
+            const uint32_t e = pk[lit[--i]];
+            br.add(e & 0xffffu, e >> 16);
         }
         // end mark: added by the thread that owns the last symbol (or thread 0 of an empty stream)
         bool last = (sg.segLen == 0) ? (st->t == 0) : (sg.r1 == sg.segLen && sg.r0 < sg.r1);

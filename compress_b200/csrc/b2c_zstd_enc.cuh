@@ -55,7 +55,17 @@ constexpr uint32_t ENC_E_BYTES = (1u << ENC_EBITS) * 2;
 constexpr uint32_t ENC_SREC = 7;           // match records per thread kept in shared memory (the rest spill to HBM)
 constexpr uint32_t ENC_L_BYTES = 64 * 1024;   // 7 records + 8 bytes of merge state per thread; later the literal counters
 constexpr uint32_t ENC_MAXSEQ = 16384 + 64;
-constexpr int PACK_NT = 512;              // K4 threads per CTA
+#ifndef PACK_THREADS
+#define PACK_THREADS 512
+#endif
+#ifndef PACK_SEQ_UNROLL
+#define PACK_SEQ_UNROLL 1
+#endif
+#ifndef PACK_MIN_CTAS
+#define PACK_MIN_CTAS 1
+#endif
+constexpr int PACK_UNROLL = PACK_SEQ_UNROLL;   // unroll factor of the two per-sequence loops
+constexpr int PACK_NT = PACK_THREADS;     // K4 threads per CTA (a multiple of 128: four Huffman streams)
 constexpr uint32_t ENC_SCRATCH_BYTES = (ENC_MAXREC - ENC_SREC) * ENC_NT * 8;  // per-CTA spilled match records [k][thread]
 
 enum { ENC_FLAG_CRC = 1, ENC_FLAG_FRAME = 2 };
@@ -95,6 +105,7 @@ struct ZstdEncParams {
     int64_t *out_sizes;           // bytes written per chunk, negative = error
     uint32_t nchunks;
     uint32_t flags;
+    uint32_t chunk0;              // K1/K2 only: this launch covers chunks [chunk0, chunk0 + nchunks) (sub-batches)
     uint8_t *scratch;             // gridDim.x(K1) * ENC_SCRATCH_BYTES
     ChunkWork *work;              // [nchunks]
     // optional debug dump (tests): per chunk {nseq, nlit, kind, litMode} + seq triples + literals
@@ -892,10 +903,14 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
 struct PackShared {
     HufWork hw;               // only ctVal/ctBits/tableDesc*/scan/stream* are used here
     uint32_t scan[40];
+    uint32_t pk[256];         // Huffman codes as (code | nbits << 16)
     uint32_t litMode, lhSize, litPayload, pos;
 };
 constexpr uint32_t PACK_STAGE_BYTES = ENC_MAX_CHUNK + 128;
-constexpr uint32_t PACK_LIT_SMEM = 40 * 1024;   // literals are staged in shared memory when they fit
+#ifndef PACK_LIT_SMEM_BYTES
+#define PACK_LIT_SMEM_BYTES (40 * 1024)
+#endif
+constexpr uint32_t PACK_LIT_SMEM = PACK_LIT_SMEM_BYTES;   // literals are staged in shared memory when they fit
 constexpr uint32_t PACK_SMEM_SH = PACK_STAGE_BYTES + PACK_LIT_SMEM;
 constexpr uint32_t PACK_SMEM_BYTES = PACK_SMEM_SH + ((sizeof(PackShared) + 15) / 16) * 16;
 
@@ -960,7 +975,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         HufEncState hst;
         uint32_t payload = 0;
         const bool hufOK = hw->status == HUF_OK;
-        if (hufOK) payload = huf_enc_sizes(hw, lit, nlit, four ? 1 : 0, tid, PACK_NT, 0, &hst);
+        if (hufOK) payload = huf_enc_sizes(hw, ps->pk, lit, nlit, four ? 1 : 0, tid, PACK_NT, 0, &hst);
         if (tid == 0) {
             // huff0 compress(): out >= wantSize => ErrIncompressible (compress.go:155-158, WantLogLess 4)
             uint32_t mode = 2;
@@ -1005,6 +1020,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         if (tA > nseq) tA = nseq;
         if (tB > nseq) tB = nseq;
         uint32_t mybits = 0;
+#pragma unroll PACK_UNROLL
         for (uint32_t t = tA; t < tB; t++) {
             uint32_t idx = nseq - 1 - t;
             uint32_t cl = B2C_LDG(cLL + idx), co = B2C_LDG(cOF + idx), cm = B2C_LDG(cML + idx);
@@ -1025,7 +1041,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
             for (uint32_t i = tid; i < zw; i += PACK_NT) reinterpret_cast<uint32_t *>(stage)[i] = 0;
             __syncthreads();
             if (litMode == 2) {
-                huf_enc_pack(hw, lit, four ? 1 : 0, stage, litOff, tid, PACK_NT, 0, &hst);
+                huf_enc_pack(hw, ps->pk, lit, four ? 1 : 0, stage, litOff, tid, PACK_NT, 0, &hst);
             } else if (litMode == 0) {
                 for (uint32_t i = tid; i < nlit; i += PACK_NT) stage[litOff + i] = lit[i];
             } else if (tid == 0) {
@@ -1035,19 +1051,20 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
             {
                 BitRun br;
                 br.init(reinterpret_cast<uint32_t *>(stage), bsOff * 8 + exBits);
+#pragma unroll PACK_UNROLL
                 for (uint32_t t = tA; t < tB; t++) {
                     uint32_t idx = nseq - 1 - t;
                     uint32_t cl = B2C_LDG(cLL + idx), co = B2C_LDG(cOF + idx), cm = B2C_LDG(cML + idx);
                     const uint32_t vLL = B2C_LDG(W->seqLL + idx), vML = B2C_LDG(W->seqML + idx), vOF = B2C_LDG(W->seqOF + idx);
                     if (t) {
+                        // three state flushes (<= 9 bits each) in one append: OF, ML, LL (blockenc.go:757-790)
                         uint32_t so = B2C_LDG(stbOF + idx), sm = B2C_LDG(stbML + idx), sl = B2C_LDG(stbLL + idx);
-                        br.add(so & 0xfff, so >> 12);
-                        br.add(sm & 0xfff, sm >> 12);
-                        br.add(sl & 0xfff, sl >> 12);
+                        const uint32_t no = so >> 12, nm = sm >> 12;
+                        br.add((so & 0xfff) | ((sm & 0xfff) << no) | ((sl & 0xfff) << (no + nm)), no + nm + (sl >> 12));
                     }
+                    // extra bits: LL and ML (<= 16 bits each) together, then OF
                     uint32_t lb = seq_ll_bits(cl), mb = seq_ml_bits(cm);
-                    br.add(vLL & ((1u << lb) - 1), lb);
-                    br.add(vML & ((1u << mb) - 1), mb);
+                    br.add((vLL & ((1u << lb) - 1)) | ((vML & ((1u << mb) - 1)) << lb), lb + mb);
                     br.add(vOF & ((1u << co) - 1), co);
                 }
                 if (tB == nseq && tA < tB) {
@@ -1237,13 +1254,13 @@ extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_snappy_encode_kernel
 extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_zstd_parse_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_ZSTD>(smem, P, c, scratch);
+    for (uint32_t c = P.chunk0 + blockIdx.x; c < P.chunk0 + P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_ZSTD>(smem, P, c, scratch);
 }
 extern "C" __global__ void __launch_bounds__(128) b2c_zstd_tables_kernel(ZstdEncParams P) {
     __shared__ TablesShared ts;
     if (threadIdx.x < 3) seq_build_predef(&ts.sw, (int)threadIdx.x);
     __syncthreads();
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) {
+    for (uint32_t c = P.chunk0 + blockIdx.x; c < P.chunk0 + P.nchunks; c += gridDim.x) {
         zstd_tables_chunk(&ts, P, c);
         __syncthreads();
     }
@@ -1252,7 +1269,7 @@ extern "C" __global__ void __launch_bounds__(CHAIN_NT) b2c_zstd_chains_kernel(Zs
     extern __shared__ __align__(1024) uint8_t smem[];
     zstd_chains_block(reinterpret_cast<uint32_t *>(smem), P, blockIdx.x * 32);
 }
-extern "C" __global__ void __launch_bounds__(PACK_NT) b2c_zstd_pack_kernel(ZstdEncParams P) {
+extern "C" __global__ void __launch_bounds__(PACK_NT, PACK_MIN_CTAS) b2c_zstd_pack_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     zstd_pack_chunk(smem, P, blockIdx.x);
 }
