@@ -55,6 +55,9 @@ constexpr uint32_t ENC_E_BYTES = (1u << ENC_EBITS) * 2;
 constexpr uint32_t ENC_SREC = 7;           // match records per thread kept in shared memory (the rest spill to HBM)
 constexpr uint32_t ENC_L_BYTES = 64 * 1024;   // 7 records + 8 bytes of merge state per thread; later the literal counters
 constexpr uint32_t ENC_MAXSEQ = 16384 + 64;
+#ifndef TABLES_FREE_RUNNING
+#define TABLES_FREE_RUNNING 0   // 1: the four warps of a K2 CTA (Huffman, LL, OF, ML) walk their chunk lists without a per-chunk barrier
+#endif
 #ifndef PACK_THREADS
 #define PACK_THREADS 512
 #endif
@@ -1262,7 +1265,9 @@ extern "C" __global__ void __launch_bounds__(128) b2c_zstd_tables_kernel(ZstdEnc
     __syncthreads();
     for (uint32_t c = P.chunk0 + blockIdx.x; c < P.chunk0 + P.nchunks; c += gridDim.x) {
         zstd_tables_chunk(&ts, P, c);
+#if !TABLES_FREE_RUNNING
         __syncthreads();
+#endif
     }
 }
 extern "C" __global__ void __launch_bounds__(CHAIN_NT) b2c_zstd_chains_kernel(ZstdEncParams P) {

@@ -90,3 +90,29 @@ def test_reference_corpus_fixture(level):
         if len(data) == 0:
             continue
         _roundtrip(data, level=level)
+
+
+def _lz_like(rng, n):
+    """Bytes built from random literals and copies of earlier data at random distances (short and far)."""
+    out = bytearray(rng.integers(0, 64, size=64, dtype=np.uint8).tobytes())
+    while len(out) < n:
+        k = int(rng.integers(0, 4))
+        if k == 0:
+            out += rng.integers(0, 256, size=int(rng.integers(1, 40)), dtype=np.uint8).tobytes()
+        else:
+            dist = int(rng.integers(1, min(len(out), 1 << int(rng.integers(1, 18))) + 1))
+            ln = int(rng.integers(3, 300 if k == 3 else 24))
+            start = len(out) - dist
+            for i in range(ln):                    # overlapping copies allowed, as in the format
+                out.append(out[start + i])
+    return bytes(out[:n])
+
+
+@pytest.mark.parametrize("level", [1, 2, 3])
+@pytest.mark.parametrize("seed", range(6))
+def test_random_lz_structured_inputs(level, seed):
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    n = int(rng.integers(1, 400_000))
+    data = _lz_like(rng, n)
+    enc = _roundtrip(data, level=level, crc=bool(seed & 1))
+    assert len(enc) <= len(data) + 3 * (n // (64 << 10) + 1) + 18

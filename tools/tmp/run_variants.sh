@@ -7,6 +7,9 @@ for ov in 0 1 2; do
   echo "== overlap $ov"
   B2C_OVERLAP=$ov B2C_LIB=$PWD/variants/ov.so timeout 300 python tools/kernel_times.py 2>&1 | tail -4
 done
+echo "== free-running tables, overlap 0 / 2"
+B2C_OVERLAP=0 B2C_LIB=$PWD/variants/fr.so timeout 300 python tools/kernel_times.py 2>&1 | tail -4
+B2C_OVERLAP=2 B2C_LIB=$PWD/variants/fr.so timeout 300 python tools/kernel_times.py 2>&1 | tail -4
 echo "== overlap 2, 8 sub-batches"
 B2C_OVERLAP=2 B2C_LIB=$PWD/variants/ov8.so timeout 300 python tools/kernel_times.py 2>&1 | tail -4
 B2C_OVERLAP=2 B2C_LIB=$PWD/variants/ov.so timeout 600 python -m pytest tests/test_zstd_gpu.py -x -q -m gpu 2>&1 | tail -3
