@@ -18,6 +18,9 @@
 #ifndef ENC_SUB_BATCHES
 #define ENC_SUB_BATCHES 4        // overlap mode 2: parse sub-batches per encode call (<= 8)
 #endif
+#ifndef TABLES_SIDE_CTAS_PER_SM
+#define TABLES_SIDE_CTAS_PER_SM 1   // overlap mode 2: grid of a tables launch that runs beside the next parse (one CTA fits per SM)
+#endif
 #ifndef TABLES_CTAS_PER_SM
 #define TABLES_CTAS_PER_SM 8   // K2: resident CTAs per SM (19 KB static shared memory, 56 registers x 128 threads each)
 #endif
@@ -376,7 +379,9 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
     }
-    if (crc) LAUNCH(0, xs, b2c_zstd_xxh_kernel<<<(4 * nchunks + 127) / 128, 128, 0, xs>>>(P));
+    // serial order: xxh64 first.  Forked: it is issued right after the first parse launch, so that the parse CTAs take
+    // their SMs first and the xxh64 CTAs fill what is left (registers for two of them per SM).
+    if (crc && !fork) LAUNCH(0, st, b2c_zstd_xxh_kernel<<<(4 * nchunks + 127) / 128, 128, 0, st>>>(P));
     const uint32_t per = nb > 1 ? ((nchunks + nb - 1) / nb + sms - 1) / sms * sms : nchunks;   // whole rounds of the SMs
     for (unsigned b = 0; b < nb; b++) {
         const uint32_t first = b * per;
@@ -387,10 +392,12 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
         Pb.chunk0 = first; Pb.nchunks = count;
         const unsigned g1 = sms < count ? sms : count;
         LAUNCH(1, st, b2c_zstd_parse_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(Pb));
+        if (b == 0 && crc && fork) LAUNCH(0, xs, b2c_zstd_xxh_kernel<<<(4 * nchunks + 127) / 128, 128, 0, xs>>>(P));
         if (!lastb) {
             CK(cudaEventRecord(ctx->ev_k1[b], st));
             CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_k1[b], 0));
-            LAUNCH(2, ctx->aux, b2c_zstd_tables_kernel<<<g1, 128, 0, ctx->aux>>>(Pb));
+            const unsigned gs = sms * TABLES_SIDE_CTAS_PER_SM < count ? sms * TABLES_SIDE_CTAS_PER_SM : count;
+            LAUNCH(2, ctx->aux, b2c_zstd_tables_kernel<<<gs, 128, 0, ctx->aux>>>(Pb));
         } else {
             const unsigned g2 = sms * TABLES_CTAS_PER_SM < count ? sms * TABLES_CTAS_PER_SM : count;
             LAUNCH(2, st, b2c_zstd_tables_kernel<<<g2, 128, 0, st>>>(Pb));
