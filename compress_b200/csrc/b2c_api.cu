@@ -12,15 +12,6 @@
 #include "b2c_s2_dec.cuh"
 #include "b2c_huf0.cuh"
 
-#ifndef B2C_OVERLAP_DEFAULT
-#define B2C_OVERLAP_DEFAULT 0
-#endif
-#ifndef ENC_SUB_BATCHES
-#define ENC_SUB_BATCHES 4        // overlap mode 2: parse sub-batches per encode call (<= 8)
-#endif
-#ifndef TABLES_SIDE_CTAS_PER_SM
-#define TABLES_SIDE_CTAS_PER_SM 1   // overlap mode 2: grid of a tables launch that runs beside the next parse (one CTA fits per SM)
-#endif
 #ifndef TABLES_CTAS_PER_SM
 #define TABLES_CTAS_PER_SM 8   // K2: resident CTAs per SM (19 KB static shared memory, 56 registers x 128 threads each)
 #endif
@@ -60,17 +51,10 @@ struct b2c_ctx {
     uint8_t *d_dec_lit = nullptr; size_t dec_lit_cap = 0;
     uint8_t *d_dec_in = nullptr, *d_dec_out = nullptr; size_t dec_in_cap = 0, dec_out_cap = 0;
     uint8_t *d_dec_meta = nullptr; size_t dec_meta_cap = 0;
-    // optional per-kernel timing of the encode pipeline (b2c_profile_*): one (start, end) event pair per launch
+    // optional per-kernel timing of the encode pipeline (b2c_profile_*): 6 events per encode call
     bool prof = false;
-    std::vector<cudaEvent_t> pev;        // event pool
+    std::vector<cudaEvent_t> pev;
     size_t pev_used = 0;
-    struct ProfRec { int kernel; size_t a, b; };
-    std::vector<ProfRec> precs;
-    uint32_t prof_calls = 0;
-    // encode pipeline overlap (see launch_encode): side stream + fork/join events
-    int overlap = 0;                     // 0 serial, 1 xxh64 beside the parse, 2 also tables of sub-batch b beside parse b+1
-    cudaStream_t aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k1[8] = {nullptr};
     uint64_t launches = 0;
     char err[256] = {0};
 };
@@ -179,19 +163,6 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)PACK_SMEM_BYTES) == cudaSuccess;
-    // the small kernels that may share an SM with a parse CTA take the same (maximum) shared-memory carve-out
-    ok = ok && cudaFuncSetAttribute(b2c_zstd_tables_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(b2c_zstd_xxh_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
-    for (int k = 0; k < 8; k++) ok = ok && cudaEventCreateWithFlags(&ctx->ev_k1[k], cudaEventDisableTiming) == cudaSuccess;
-    {
-        const char *ov = getenv("B2C_OVERLAP");   // tuning override; the default is B2C_OVERLAP_DEFAULT
-        ctx->overlap = ov ? atoi(ov) : B2C_OVERLAP_DEFAULT;
-    }
     if (ok && max_chunks) {
         ok = ok && cudaMallocHost(&ctx->h_in, max_chunks * (size_t)ENC_MAX_CHUNK) == cudaSuccess;
         ok = ok && cudaMallocHost(&ctx->h_out, max_chunks * (size_t)kSlot) == cudaSuccess;
@@ -233,10 +204,6 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     cudaFree(ctx->d_in2); cudaFree(ctx->d_out2); cudaFree(ctx->d_packed2); cudaFree(ctx->d_sizes2);
     cudaFree(ctx->d_offsets2); cudaFree(ctx->d_src_sizes2); cudaFreeHost(ctx->h_sizes2); cudaFreeHost(ctx->h_src_sizes2);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    for (int k = 0; k < 8; k++) if (ctx->ev_k1[k]) cudaEventDestroy(ctx->ev_k1[k]);
-    if (ctx->aux) cudaStreamDestroy(ctx->aux);
     for (int k = 0; k < 2; k++) {
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
         if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
@@ -273,27 +240,23 @@ int b2c_profile_enable(b2c_ctx *ctx, int on) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     ctx->prof = on != 0;
     ctx->pev_used = 0;
-    ctx->precs.clear();
-    ctx->prof_calls = 0;
     return B2C_OK;
 }
-// ms[k] = summed duration of the launches of kernel k (0 xxh64, 1 parse, 2 tables, 3 chains, 4 pack) over the encode
-// calls issued since b2c_profile_enable(ctx, 1); *ncalls = number of encode calls.  Synchronises the device.
-// With the overlapped pipeline the durations of kernels that ran side by side add up to more than the step time.
+// ms[k] = summed duration of kernel k (0 xxh64, 1 parse, 2 tables, 3 chains, 4 pack) over the encode calls issued
+// since b2c_profile_enable(ctx, 1); *ncalls = number of encode calls.  Synchronises the device.
 int b2c_profile_read(b2c_ctx *ctx, double *ms, uint32_t *ncalls) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
     for (int k = 0; k < 5; k++) ms[k] = 0.0;
-    for (const b2c_ctx::ProfRec &r : ctx->precs) {
-        float t = 0.f;
-        CK(cudaEventElapsedTime(&t, ctx->pev[r.a], ctx->pev[r.b]));
-        ms[r.kernel] += (double)t;
-    }
-    if (ncalls) *ncalls = ctx->prof_calls;
+    for (size_t c = 0; c + 6 <= ctx->pev_used; c += 6)
+        for (int k = 0; k < 5; k++) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, ctx->pev[c + k], ctx->pev[c + k + 1]));
+            ms[k] += (double)t;
+        }
+    if (ncalls) *ncalls = (uint32_t)(ctx->pev_used / 6);
     ctx->pev_used = 0;
-    ctx->precs.clear();
-    ctx->prof_calls = 0;
     return B2C_OK;
 }
 
@@ -337,79 +300,36 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     P.work = ctx->d_work[slot];
     P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_cap;
     P.dbg_cycles = dbg_cycles;
-    const unsigned sms = (unsigned)ctx->sm_count;
-    // per-launch profiling: an event pair around every kernel, on the stream it is launched on
-    auto pev_get = [&](size_t *idx) -> int {
-        if (ctx->pev_used == ctx->pev.size()) {
+    unsigned sms = (unsigned)ctx->sm_count;
+    unsigned g1 = sms < nchunks ? sms : nchunks;
+    unsigned g2 = sms * TABLES_CTAS_PER_SM < nchunks ? sms * TABLES_CTAS_PER_SM : nchunks;
+    cudaEvent_t *pe = nullptr;
+    if (ctx->prof) {
+        while (ctx->pev.size() < ctx->pev_used + 6) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
             ctx->pev.push_back(e);
         }
-        *idx = ctx->pev_used++;
-        return B2C_OK;
-    };
-#define LAUNCH(kidx, stream_, ...)                                                                      \
-    do {                                                                                                \
-        size_t ea_ = 0, eb_ = 0;                                                                        \
-        if (ctx->prof) {                                                                                \
-            int rc_ = pev_get(&ea_); if (rc_) return rc_;                                               \
-            rc_ = pev_get(&eb_); if (rc_) return rc_;                                                   \
-            CK(cudaEventRecord(ctx->pev[ea_], stream_));                                                \
-        }                                                                                               \
-        __VA_ARGS__;                                                                                    \
-        ctx->launches += 1;                                                                             \
-        if (ctx->prof) {                                                                                \
-            CK(cudaEventRecord(ctx->pev[eb_], stream_));                                                \
-            ctx->precs.push_back({kidx, ea_, eb_});                                                     \
-        }                                                                                               \
-    } while (0)
-    if (ctx->prof) ctx->prof_calls++;
-
-    // Overlap.  A parse CTA (1024 threads, 197 KB of shared memory, 56 registers per thread) fills an SM's thread and
-    // shared-memory budget only partly in time: it is latency bound.  Two of the small kernels fit beside it
-    // (xxh64: no shared memory; tables: 19 KB, 128 threads), so they are issued on a side stream:
-    //   mode >= 1: xxh64 of the whole batch runs beside the parse (it only reads the source);
-    //   mode 2   : the batch is parsed in sub-batches and tables(b) runs beside parse(b + 1), one CTA per SM.
-    const bool crc = (flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC);
-    const bool fork = ctx->overlap >= 1 && !dbg_cycles && nchunks >= 2 * sms;
-    unsigned nb = 1;
-    if (fork && ctx->overlap >= 2 && nchunks >= 16 * sms) nb = ENC_SUB_BATCHES;
-    cudaStream_t xs = fork ? ctx->aux : st;
-    if (fork) {
-        CK(cudaEventRecord(ctx->ev_fork, st));
-        CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        pe = ctx->pev.data() + ctx->pev_used;
+        ctx->pev_used += 6;
     }
-    // serial order: xxh64 first.  Forked: it is issued right after the first parse launch, so that the parse CTAs take
-    // their SMs first and the xxh64 CTAs fill what is left (registers for two of them per SM).
-    if (crc && !fork) LAUNCH(0, st, b2c_zstd_xxh_kernel<<<(4 * nchunks + 127) / 128, 128, 0, st>>>(P));
-    const uint32_t per = nb > 1 ? ((nchunks + nb - 1) / nb + sms - 1) / sms * sms : nchunks;   // whole rounds of the SMs
-    for (unsigned b = 0; b < nb; b++) {
-        const uint32_t first = b * per;
-        if (first >= nchunks) break;
-        const uint32_t count = (nchunks - first < per) ? nchunks - first : per;
-        const bool lastb = first + count == nchunks;
-        ZstdEncParams Pb = P;
-        Pb.chunk0 = first; Pb.nchunks = count;
-        const unsigned g1 = sms < count ? sms : count;
-        LAUNCH(1, st, b2c_zstd_parse_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(Pb));
-        if (b == 0 && crc && fork) LAUNCH(0, xs, b2c_zstd_xxh_kernel<<<(4 * nchunks + 127) / 128, 128, 0, xs>>>(P));
-        if (!lastb) {
-            CK(cudaEventRecord(ctx->ev_k1[b], st));
-            CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_k1[b], 0));
-            const unsigned gs = sms * TABLES_SIDE_CTAS_PER_SM < count ? sms * TABLES_SIDE_CTAS_PER_SM : count;
-            LAUNCH(2, ctx->aux, b2c_zstd_tables_kernel<<<gs, 128, 0, ctx->aux>>>(Pb));
-        } else {
-            const unsigned g2 = sms * TABLES_CTAS_PER_SM < count ? sms * TABLES_CTAS_PER_SM : count;
-            LAUNCH(2, st, b2c_zstd_tables_kernel<<<g2, 128, 0, st>>>(Pb));
-        }
+#define PEV(k) do { if (pe) cudaEventRecord(pe[k], st); } while (0)
+    PEV(0);
+    if ((flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC)) {
+        b2c_zstd_xxh_kernel<<<(4 * nchunks + 127) / 128, 128, 0, st>>>(P);
+        ctx->launches += 1;
     }
-    if (fork) {
-        CK(cudaEventRecord(ctx->ev_join, ctx->aux));
-        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-    }
-    LAUNCH(3, st, b2c_zstd_chains_kernel<<<(nchunks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, st>>>(P));
-    LAUNCH(4, st, b2c_zstd_pack_kernel<<<nchunks, PACK_NT, PACK_SMEM_BYTES, st>>>(P));
-#undef LAUNCH
+    PEV(1);
+    b2c_zstd_parse_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+    PEV(2);
+    b2c_zstd_tables_kernel<<<g2, TABLES_NT, 0, st>>>(P);
+    PEV(3);
+    b2c_zstd_chains_kernel<<<(nchunks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, st>>>(P);
+    PEV(4);
+    b2c_zstd_pack_kernel<<<nchunks, PACK_NT, PACK_SMEM_BYTES, st>>>(P);
+    PEV(5);
+#undef PEV
+    ctx->launches += 4;
     CK(cudaGetLastError());
     return B2C_OK;
 }

@@ -255,14 +255,18 @@ B2C_DEV void huf_bt_sort(HufWork *hw, unsigned tid, unsigned nthreads) {
     if (nthreads == 32) {
         // one warp: bitonic sort of the 256 keys count << 8 | (255 - symbol), descending, in place in ncount[1..256]
         // (symbols >= symbolLen have count 0 and the smallest keys, so the first symbolLen slots are the ranking)
+        // Only the first N = 2^ceil(log2(symbolLen)) symbols take part (>= 64): the rest have count 0 and keys below
+        // every participant's, so the first symbolLen slots come out the same as from the full 256-key sort.
         uint32_t *K = hw->ncount + 1;
-        for (unsigned s = tid; s < 256; s += 32) K[s] = (hw->count[s] << 8) | (255u - s);
+        unsigned N = 64;
+        while (N < symbolLen) N <<= 1;
+        for (unsigned s = tid; s < N; s += 32) K[s] = (hw->count[s] << 8) | (255u - s);
         __syncwarp();
-        for (unsigned k = 2; k <= 256; k <<= 1) {
+        const unsigned rounds = N >> 6;                                    // pairs per lane
+        for (unsigned k = 2; k <= N; k <<= 1) {
             for (unsigned j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-                for (unsigned m = 0; m < 4; m++) {
-                    const unsigned t = tid + 32 * m;                       // pair index 0..127
+                for (unsigned m = 0; m < rounds; m++) {
+                    const unsigned t = tid + 32 * m;                       // pair index 0..N/2-1
                     const unsigned i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                     const unsigned q = i | j;
                     const uint32_t a = K[i], b = K[q];
@@ -417,7 +421,8 @@ B2C_DEV void huf_bt_write(HufWork *hw) {
     }
 }
 // Convenience: whole build with barriers (all threads of the group call).
-B2C_DEV void huf_build_table(HufWork *hw, uint32_t n, unsigned tid, unsigned nthreads, int bar_id) {
+// Code lengths and code values only (stages A-C): ctBits / ctVal / tableLog / symbolLen; hw->status on the early outs.
+B2C_DEV void huf_build_codes(HufWork *hw, uint32_t n, unsigned tid, unsigned nthreads, int bar_id) {
 #define HSYNC() do { group_sync(bar_id, (int)nthreads); } while (0)
     huf_bt_stats(hw, n, tid);
     HSYNC();
@@ -430,11 +435,18 @@ B2C_DEV void huf_build_table(HufWork *hw, uint32_t n, unsigned tid, unsigned nth
     HSYNC();
     huf_bt_vals(hw, tid, nthreads);
     HSYNC();
-    if (tid == 0) huf_bt_write(hw);
-    HSYNC();
 #undef HSYNC
 }
+B2C_DEV void huf_build_table(HufWork *hw, uint32_t n, unsigned tid, unsigned nthreads, int bar_id) {
+    huf_build_codes(hw, n, tid, nthreads, bar_id);
+    if (hw->status != HUF_OK) return;
+    if (tid == 0) huf_bt_write(hw);
+    group_sync(bar_id, (int)nthreads);
+}
 
+#ifndef HUF_ENC_WORDS
+#define HUF_ENC_WORDS 1   // literal reads by aligned words (0: byte by byte; tuning comparison)
+#endif
 // ---------------------------------------------------------------- encode
 // Lengths pass: every thread owns a contiguous run of symbols (in reverse order) of one of
 // `nstreams` (1 or 4) segments; returns per-thread bit count; segment geometry in out params.
@@ -486,7 +498,7 @@ B2C_DEV uint32_t huf_enc_sizes(HufWork *hw, uint32_t *pk, const uint8_t *lit, ui
         uint32_t i = sg.segStart + sg.segLen - sg.r1;
         const uint32_t b = sg.segStart + sg.segLen - sg.r0;
         while (i < b && (reinterpret_cast<uintptr_t>(lit + i) & 3)) mybits += cb[lit[i++]];
-        for (; i + 4 <= b; i += 4) {
+        for (; HUF_ENC_WORDS && i + 4 <= b; i += 4) {
             const uint32_t w = *reinterpret_cast<const uint32_t *>(lit + i);
             mybits += (uint32_t)cb[w & 255] + cb[(w >> 8) & 255] + cb[(w >> 16) & 255] + cb[w >> 24];
         }
@@ -527,7 +539,7 @@ B2C_DEV void huf_enc_pack(HufWork *hw, const uint32_t *pk, const uint8_t *lit, i
             const uint32_t e = pk[lit[--i]];
             br.add(e & 0xffffu, e >> 16);
         }
-        for (; i >= a + 4; i -= 4) {
+        for (; HUF_ENC_WORDS && i >= a + 4; i -= 4) {
             const uint32_t w = *reinterpret_cast<const uint32_t *>(lit + i - 4);
             const uint32_t e3 = pk[w >> 24], e2 = pk[(w >> 16) & 255], e1 = pk[(w >> 8) & 255], e0 = pk[w & 255];
             br.add((e3 & 0xffffu) | ((e2 & 0xffffu) << (e3 >> 16)), (e3 >> 16) + (e2 >> 16));

@@ -42,6 +42,12 @@ constexpr uint32_t ENC_MAXREC = 17;       // matches a thread can start inside i
 #ifndef ENC_EBUILD_SYNC_MASK
 #define ENC_EBUILD_SYNC_MASK 1  // barrier every (mask + 1) iterations of the table build's first round
 #endif
+#ifndef ENC_EBUILD_FUSED
+#define ENC_EBUILD_FUSED 0   // 1: table build with the race check folded into the store sweeps (one hash per position)
+#endif
+#ifndef ENC_EBUILD_GROUPS
+#define ENC_EBUILD_GROUPS 2
+#endif
 #ifndef ENC_PROBES_PER_VOTE
 #define ENC_PROBES_PER_VOTE 8   // probe steps between two looks at the warp state
 #endif
@@ -55,17 +61,20 @@ constexpr uint32_t ENC_E_BYTES = (1u << ENC_EBITS) * 2;
 constexpr uint32_t ENC_SREC = 7;           // match records per thread kept in shared memory (the rest spill to HBM)
 constexpr uint32_t ENC_L_BYTES = 64 * 1024;   // 7 records + 8 bytes of merge state per thread; later the literal counters
 constexpr uint32_t ENC_MAXSEQ = 16384 + 64;
-#ifndef TABLES_FREE_RUNNING
-#define TABLES_FREE_RUNNING 0   // 1: the four warps of a K2 CTA (Huffman, LL, OF, ML) walk their chunk lists without a per-chunk barrier
-#endif
 #ifndef PACK_THREADS
 #define PACK_THREADS 512
 #endif
 #ifndef PACK_SEQ_UNROLL
 #define PACK_SEQ_UNROLL 1
 #endif
+#ifndef PACK_SEQ_COMBINE
+#define PACK_SEQ_COMBINE 1   // 1: state bits of the three chains in one append, LL+ML extra bits in one
+#endif
+#ifndef PACK_BITS_LUT
+#define PACK_BITS_LUT 1      // extra-bit counts from a 2 x 64 byte shared-memory table instead of compare chains
+#endif
 #ifndef PACK_MIN_CTAS
-#define PACK_MIN_CTAS 1
+#define PACK_MIN_CTAS 2   // two CTAs per SM: caps the kernel at 64 registers per thread
 #endif
 constexpr int PACK_UNROLL = PACK_SEQ_UNROLL;   // unroll factor of the two per-sequence loops
 constexpr int PACK_NT = PACK_THREADS;     // K4 threads per CTA (a multiple of 128: four Huffman streams)
@@ -108,7 +117,6 @@ struct ZstdEncParams {
     int64_t *out_sizes;           // bytes written per chunk, negative = error
     uint32_t nchunks;
     uint32_t flags;
-    uint32_t chunk0;              // K1/K2 only: this launch covers chunks [chunk0, chunk0 + nchunks) (sub-batches)
     uint8_t *scratch;             // gridDim.x(K1) * ENC_SCRATCH_BYTES
     ChunkWork *work;              // [nchunks]
     // optional debug dump (tests): per chunk {nseq, nlit, kind, litMode} + seq triples + literals
@@ -312,6 +320,73 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     // ---------------------------------------------------------------- P1: earliest-occurrence table
     // Each thread owns groups of 4 consecutive positions (three aligned word loads serve four hashes).
     const uint32_t npos = (n >= 8) ? n - 7 : 0;  // positions with 8 readable bytes
+#if ENC_EBUILD_FUSED
+    {
+        // Descending sweeps of plain stores (low positions land last) with the race check folded in: a thread keeps the
+        // hashes of the positions it stored in the previous sweep and, after the barrier that completes that sweep,
+        // looks at its slots once; the rare loser of a same-sweep write race (a higher position landed later) takes the
+        // slot with a compare-and-swap minimum on the containing 32-bit word.  Stores of the next sweep may run
+        // beside those repairs: they carry lower positions, so whichever order they land in, the minimum survives.
+        const uint32_t ngroups = (npos + 3) / 4;
+        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
+        uint32_t *E32 = reinterpret_cast<uint32_t *>(E);
+        constexpr int G = ENC_EBUILD_GROUPS;                       // groups of 4 positions per thread and sweep
+        const int32_t sweeps = (int32_t)((ngroups + G * ENC_NT - 1) / (G * ENC_NT));
+        uint32_t hp[G][2];                                         // four 15-bit hashes per group, two per word
+        uint32_t pp[G];                                            // first position of the group, or ~0u
+#pragma unroll
+        for (int u = 0; u < G; u++) pp[u] = 0xffffffffu;
+        for (int32_t k = sweeps - 1; k >= -1; k--) {
+#pragma unroll
+            for (int u = 0; u < G; u++) {
+                if (pp[u] != 0xffffffffu) {
+                    uint32_t hj[4] = {hp[u][0] & 0xffffu, hp[u][0] >> 16, hp[u][1] & 0xffffu, hp[u][1] >> 16};
+                    uint32_t e[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) e[j] = E[hj[j]];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t pj = pp[u] + j;
+                        if (pj < npos && e[j] > pj) {
+                            const uint32_t widx = hj[j] >> 1, shft = (hj[j] & 1) * 16;
+                            uint32_t old = E32[widx];
+                            for (;;) {
+                                const uint32_t curv = (old >> shft) & 0xffffu;
+                                if (curv <= pj) break;
+                                const uint32_t nv = (old & ~(0xffffu << shft)) | (pj << shft);
+                                const uint32_t prev = atomicCAS(&E32[widx], old, nv);
+                                if (prev == old) break;
+                                old = prev;
+                            }
+                        }
+                    }
+                    pp[u] = 0xffffffffu;
+                }
+            }
+            if (k >= 0) {
+#pragma unroll
+                for (int u = G - 1; u >= 0; u--) {
+                    const uint32_t g = ((uint32_t)k * G + (uint32_t)u) * ENC_NT + tid;
+                    if (g < ngroups) {
+                        const uint32_t w0 = srcw[g], w1 = srcw[g + 1], w2 = srcw[g + 2];
+                        const uint32_t p = 4 * g;
+                        uint32_t hj[4];
+#pragma unroll
+                        for (int j = 3; j >= 0; j--) {
+                            const uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
+                            const uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
+                            hj[j] = enc_hash6(lo, hi) >> (32 - ENC_EBITS);
+                            if (p + j < npos) E[hj[j]] = (uint16_t)(p + j);
+                        }
+                        hp[u][0] = hj[0] | (hj[1] << 16); hp[u][1] = hj[2] | (hj[3] << 16);
+                        pp[u] = p;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+#else
     {
         const uint32_t ngroups = (npos + 3) / 4;
         const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
@@ -369,6 +444,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         }
         __syncthreads();
     }
+#endif
     B2C_PHASE(2);
 
     // ---------------------------------------------------------------- P2: parse, one thread per 68-byte range
@@ -767,20 +843,48 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
 // ------------------------------------------------------------------------------------------------ K2
 // One 128-thread CTA per chunk.  Warp 0 builds the Huffman table cooperatively (rank sort with 32 lanes, the
 // serial tree / setMaxHeight / table serialisation on lane 0); lane 0 of warps 1..3 builds one FSE table each.
+#ifndef TABLES_MIN_CTAS
+#define TABLES_MIN_CTAS 8      // resident K2 CTAs per SM the register allocation is held to
+#endif
+#ifndef TABLES_DIAG
+#define TABLES_DIAG 0            // 1 / 2: timing probes that leave out the Huffman warp / the FSE warps (output degrades to raw)
+#endif
+#ifndef TABLES_PIPELINED
+#define TABLES_PIPELINED 0   // 1: a fifth warp serialises the Huffman table of the previous chunk (see zstd_tables_loop)
+#endif
+constexpr int TABLES_NT = TABLES_PIPELINED ? 160 : 128;
 struct TablesShared {
     HufWork hw;
     SeqWork sw;
+#if TABLES_PIPELINED
+    HufWork hwB;              // code lengths of the previous chunk, handed to warp 4 for cTable.write
+    uint32_t jobChunk;        // that chunk, or TABLES_NO_JOB
+#endif
 };
+constexpr uint32_t TABLES_NO_JOB = 0xffffffffu;
 B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_t chunk) {
     const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     ChunkWork *W = P.work + chunk;
     if (W->kind != 0) return;
     const uint32_t nseq = W->nseq, nlit = W->nlit;
+#if TABLES_DIAG == 1
+    if (w == 0) { if (lane == 0) { W->hufStatus = HUF_INCOMPRESSIBLE; W->tableDescLen = 0; } return; }   // timing probe: FSE warps only
+#elif TABLES_DIAG == 2
+    if (w != 0) return;                                                                                    // timing probe: Huffman warp only
+#endif
     if (w == 0) {
         HufWork *hw = &ts->hw;
         for (uint32_t s = lane; s < 256; s += 32) hw->count[s] = W->litHist[s];
         if (lane == 0) { hw->status = HUF_INCOMPRESSIBLE; hw->tableDescLen = 0; hw->tableLog = 0; }
         __syncwarp();
+#if TABLES_PIPELINED
+        // codes only; the table description (weights, their FSE compression) is written one iteration later by warp 4
+        if (nlit > 16) huf_build_codes(hw, nlit, lane, 32, -1);
+        __syncwarp();
+        if (hw->status == HUF_OK)
+            for (uint32_t s = lane; s < 256; s += 32) { W->ctVal[s] = hw->ctVal[s]; W->ctBits[s] = hw->ctBits[s]; }
+        if (lane == 0) W->hufTableLog = hw->tableLog;
+#else
         if (nlit > 16) huf_build_table(hw, nlit, lane, 32, -1);
         __syncwarp();
         if (hw->status == HUF_OK) {
@@ -788,6 +892,7 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
             for (uint32_t i = lane; i < hw->tableDescLen; i += 32) W->tableDesc[i] = hw->tableDesc[i];
         }
         if (lane == 0) { W->hufStatus = (uint32_t)hw->status; W->hufTableLog = hw->tableLog; W->tableDescLen = hw->tableDescLen; }
+#endif
     } else {
         const int which = (int)w - 1;
         SeqWork *sw = &ts->sw;
@@ -807,6 +912,62 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
             if (sw->ncountLen[which] == SEQ_TABLE_ERR) { W->ncountLen[which] = 0; W->kind = 1; }  // internal error: store raw
         }
     }
+}
+
+// The chunk loop of a K2 CTA (chunks first, first + stride, ...).
+// Pipelined form: building the Huffman CODES of a chunk (sort, tree, lengths, values) and DESCRIBING the table
+// (weights, their FSE compression: cTable.write) are both serial and of similar length, and the second only needs the
+// code lengths.  Warp 0 therefore hands the lengths of chunk i to warp 4 and goes on with chunk i + 1; the Huffman
+// path per chunk is half as long while the three FSE warps still have slack.
+B2C_DEV void zstd_tables_loop(TablesShared *ts, const ZstdEncParams &P, uint32_t first, uint32_t stride) {
+#if TABLES_PIPELINED
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) ts->jobChunk = TABLES_NO_JOB;
+    __syncthreads();
+    for (uint32_t c = first;; c += stride) {
+        const bool have = c < P.nchunks;
+        const uint32_t job = ts->jobChunk;
+        if (!have && job == TABLES_NO_JOB) break;
+        if (w < 4) {
+            if (have) zstd_tables_chunk(ts, P, c);
+        } else if (job != TABLES_NO_JOB) {
+            HufWork *hb = &ts->hwB;
+            ChunkWork *W = P.work + job;
+            if (hb->status == HUF_OK) {
+                if (lane == 0) huf_bt_write(hb);
+                __syncwarp();
+                if (hb->status == HUF_OK)
+                    for (uint32_t i = lane; i < hb->tableDescLen; i += 32) W->tableDesc[i] = hb->tableDesc[i];
+            }
+            if (lane == 0) { W->hufStatus = (uint32_t)hb->status; W->tableDescLen = hb->tableDescLen; }
+        }
+        __syncthreads();
+        // hand-off: warp 4 is done with the previous job, warp 0 with this chunk's code lengths
+        if (w == 0) {
+            const bool valid = have && P.work[c].kind == 0;
+            if (valid) {
+                const HufWork *hw = &ts->hw;
+                HufWork *hb = &ts->hwB;
+                for (uint32_t s4 = lane; s4 < 64; s4 += 32)
+                    reinterpret_cast<uint32_t *>(hb->ctBits)[s4] = reinterpret_cast<const uint32_t *>(hw->ctBits)[s4];
+                if (lane == 0) {
+                    hb->symbolLen = hw->symbolLen; hb->tableLog = hw->tableLog; hb->status = hw->status;
+                    hb->tableDescLen = 0;
+                }
+            }
+            if (lane == 0) ts->jobChunk = valid ? c : TABLES_NO_JOB;
+        }
+        __syncthreads();
+    }
+#else
+    for (uint32_t c = first; c < P.nchunks; c += stride) {
+        zstd_tables_chunk(ts, P, c);
+        __syncthreads();
+#if TABLES_DIAG == 2
+        if (threadIdx.x == 32) P.work[c].kind = 1;   // no FSE tables were built: store the chunk raw
+#endif
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -904,11 +1065,20 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
 
 // ------------------------------------------------------------------------------------------------ K4
 struct PackShared {
-    HufWork hw;               // only ctVal/ctBits/tableDesc*/scan/stream* are used here
+    HufWork hw;               // only ctVal/ctBits/tableDesc*/scan/stream* hold their usual content here; two unused
+                              // members are reused (two CTAs must fit an SM, there is no kilobyte to spare):
+                              //   hw.count[256] = Huffman codes as (code | nbits << 16)               (PACK_PK)
+                              //   hw.nsym[0..127] = extra-bit counts per LL / ML code, seqenc.go:61-97  (PACK_LLB / PACK_MLB)
     uint32_t scan[40];
-    uint32_t pk[256];         // Huffman codes as (code | nbits << 16)
     uint32_t litMode, lhSize, litPayload, pos;
 };
+#if PACK_BITS_LUT
+#define PACK_LLB(c) ((uint32_t)ps->hw.nsym[(c) & 63])
+#define PACK_MLB(c) ((uint32_t)ps->hw.nsym[64 + ((c) & 63)])
+#else
+#define PACK_LLB(c) seq_ll_bits(c)
+#define PACK_MLB(c) seq_ml_bits(c)
+#endif
 constexpr uint32_t PACK_STAGE_BYTES = ENC_MAX_CHUNK + 128;
 #ifndef PACK_LIT_SMEM_BYTES
 #define PACK_LIT_SMEM_BYTES (40 * 1024)
@@ -916,6 +1086,7 @@ constexpr uint32_t PACK_STAGE_BYTES = ENC_MAX_CHUNK + 128;
 constexpr uint32_t PACK_LIT_SMEM = PACK_LIT_SMEM_BYTES;   // literals are staged in shared memory when they fit
 constexpr uint32_t PACK_SMEM_SH = PACK_STAGE_BYTES + PACK_LIT_SMEM;
 constexpr uint32_t PACK_SMEM_BYTES = PACK_SMEM_SH + ((sizeof(PackShared) + 15) / 16) * 16;
+static_assert(PACK_LIT_SMEM != 40 * 1024 || 2 * (PACK_SMEM_BYTES + 1024) <= 228 * 1024, "two K4 CTAs must fit one SM");
 
 B2C_DEV uint32_t frame_header_bytes(uint32_t n) {
     if (n == 0) return 6;
@@ -969,6 +1140,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         }
         HufWork *hw = &ps->hw;
         // Huffman table into shared memory
+        if (tid < 64) { ps->hw.nsym[tid] = (uint8_t)seq_ll_bits(tid); ps->hw.nsym[64 + tid] = (uint8_t)seq_ml_bits(tid); }
         for (uint32_t s = tid; s < 256; s += PACK_NT) { hw->ctVal[s] = W->ctVal[s]; hw->ctBits[s] = W->ctBits[s]; }
         for (uint32_t i = tid; i < W->tableDescLen; i += PACK_NT) hw->tableDesc[i] = W->tableDesc[i];
         if (tid == 0) { hw->tableDescLen = W->tableDescLen; hw->status = (int32_t)W->hufStatus; }
@@ -978,7 +1150,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         HufEncState hst;
         uint32_t payload = 0;
         const bool hufOK = hw->status == HUF_OK;
-        if (hufOK) payload = huf_enc_sizes(hw, ps->pk, lit, nlit, four ? 1 : 0, tid, PACK_NT, 0, &hst);
+        if (hufOK) payload = huf_enc_sizes(hw, ps->hw.count, lit, nlit, four ? 1 : 0, tid, PACK_NT, 0, &hst);
         if (tid == 0) {
             // huff0 compress(): out >= wantSize => ErrIncompressible (compress.go:155-158, WantLogLess 4)
             uint32_t mode = 2;
@@ -1027,7 +1199,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         for (uint32_t t = tA; t < tB; t++) {
             uint32_t idx = nseq - 1 - t;
             uint32_t cl = B2C_LDG(cLL + idx), co = B2C_LDG(cOF + idx), cm = B2C_LDG(cML + idx);
-            mybits += seq_ll_bits(cl) + seq_ml_bits(cm) + co;
+            mybits += PACK_LLB(cl) + PACK_MLB(cm) + co;
             if (t) mybits += (uint32_t)(B2C_LDG(stbLL + idx) >> 12) + (uint32_t)(B2C_LDG(stbOF + idx) >> 12) + (uint32_t)(B2C_LDG(stbML + idx) >> 12);
         }
         uint32_t totalBits;
@@ -1044,7 +1216,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
             for (uint32_t i = tid; i < zw; i += PACK_NT) reinterpret_cast<uint32_t *>(stage)[i] = 0;
             __syncthreads();
             if (litMode == 2) {
-                huf_enc_pack(hw, ps->pk, lit, four ? 1 : 0, stage, litOff, tid, PACK_NT, 0, &hst);
+                huf_enc_pack(hw, ps->hw.count, lit, four ? 1 : 0, stage, litOff, tid, PACK_NT, 0, &hst);
             } else if (litMode == 0) {
                 for (uint32_t i = tid; i < nlit; i += PACK_NT) stage[litOff + i] = lit[i];
             } else if (tid == 0) {
@@ -1059,6 +1231,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
                     uint32_t idx = nseq - 1 - t;
                     uint32_t cl = B2C_LDG(cLL + idx), co = B2C_LDG(cOF + idx), cm = B2C_LDG(cML + idx);
                     const uint32_t vLL = B2C_LDG(W->seqLL + idx), vML = B2C_LDG(W->seqML + idx), vOF = B2C_LDG(W->seqOF + idx);
+#if PACK_SEQ_COMBINE
                     if (t) {
                         // three state flushes (<= 9 bits each) in one append: OF, ML, LL (blockenc.go:757-790)
                         uint32_t so = B2C_LDG(stbOF + idx), sm = B2C_LDG(stbML + idx), sl = B2C_LDG(stbLL + idx);
@@ -1066,9 +1239,21 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
                         br.add((so & 0xfff) | ((sm & 0xfff) << no) | ((sl & 0xfff) << (no + nm)), no + nm + (sl >> 12));
                     }
                     // extra bits: LL and ML (<= 16 bits each) together, then OF
-                    uint32_t lb = seq_ll_bits(cl), mb = seq_ml_bits(cm);
+                    uint32_t lb = PACK_LLB(cl), mb = PACK_MLB(cm);
                     br.add((vLL & ((1u << lb) - 1)) | ((vML & ((1u << mb) - 1)) << lb), lb + mb);
                     br.add(vOF & ((1u << co) - 1), co);
+#else
+                    if (t) {
+                        uint32_t so = B2C_LDG(stbOF + idx), sm = B2C_LDG(stbML + idx), sl = B2C_LDG(stbLL + idx);
+                        br.add(so & 0xfff, so >> 12);
+                        br.add(sm & 0xfff, sm >> 12);
+                        br.add(sl & 0xfff, sl >> 12);
+                    }
+                    uint32_t lb = PACK_LLB(cl), mb = PACK_MLB(cm);
+                    br.add(vLL & ((1u << lb) - 1), lb);
+                    br.add(vML & ((1u << mb) - 1), mb);
+                    br.add(vOF & ((1u << co) - 1), co);
+#endif
                 }
                 if (tB == nseq && tA < tB) {
                     // final states: ml, of, ll (blockenc.go:804-806) + end mark
@@ -1257,18 +1442,13 @@ extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_snappy_encode_kernel
 extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_zstd_parse_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
-    for (uint32_t c = P.chunk0 + blockIdx.x; c < P.chunk0 + P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_ZSTD>(smem, P, c, scratch);
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_ZSTD>(smem, P, c, scratch);
 }
-extern "C" __global__ void __launch_bounds__(128) b2c_zstd_tables_kernel(ZstdEncParams P) {
+extern "C" __global__ void __launch_bounds__(TABLES_NT, TABLES_MIN_CTAS) b2c_zstd_tables_kernel(ZstdEncParams P) {
     __shared__ TablesShared ts;
     if (threadIdx.x < 3) seq_build_predef(&ts.sw, (int)threadIdx.x);
     __syncthreads();
-    for (uint32_t c = P.chunk0 + blockIdx.x; c < P.chunk0 + P.nchunks; c += gridDim.x) {
-        zstd_tables_chunk(&ts, P, c);
-#if !TABLES_FREE_RUNNING
-        __syncthreads();
-#endif
-    }
+    zstd_tables_loop(&ts, P, blockIdx.x, gridDim.x);
 }
 extern "C" __global__ void __launch_bounds__(CHAIN_NT) b2c_zstd_chains_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];

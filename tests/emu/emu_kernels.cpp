@@ -39,10 +39,10 @@ int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, 
     });
     // K2 tables
     static TablesShared ts;
-    emu::launch(1, 128, 0, [&]() {
+    emu::launch(1, TABLES_NT, 0, [&]() {
         if (threadIdx.x < 3) seq_build_predef(&ts.sw, (int)threadIdx.x);
         __syncthreads();
-        for (uint32_t c = 0; c < P.nchunks; c++) { zstd_tables_chunk(&ts, P, c); __syncthreads(); }
+        zstd_tables_loop(&ts, P, 0, 1);
     });
     // K3 chains
     emu::launch((nchunks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, [&]() {
