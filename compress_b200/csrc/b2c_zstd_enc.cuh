@@ -42,12 +42,6 @@ constexpr uint32_t ENC_MAXREC = 17;       // matches a thread can start inside i
 #ifndef ENC_EBUILD_SYNC_MASK
 #define ENC_EBUILD_SYNC_MASK 1  // barrier every (mask + 1) iterations of the table build's first round
 #endif
-#ifndef ENC_EBUILD_FUSED
-#define ENC_EBUILD_FUSED 0   // 1: table build with the race check folded into the store sweeps (one hash per position)
-#endif
-#ifndef ENC_EBUILD_GROUPS
-#define ENC_EBUILD_GROUPS 2
-#endif
 #ifndef ENC_PROBES_PER_VOTE
 #define ENC_PROBES_PER_VOTE 8   // probe steps between two looks at the warp state
 #endif
@@ -320,73 +314,6 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     // ---------------------------------------------------------------- P1: earliest-occurrence table
     // Each thread owns groups of 4 consecutive positions (three aligned word loads serve four hashes).
     const uint32_t npos = (n >= 8) ? n - 7 : 0;  // positions with 8 readable bytes
-#if ENC_EBUILD_FUSED
-    {
-        // Descending sweeps of plain stores (low positions land last) with the race check folded in: a thread keeps the
-        // hashes of the positions it stored in the previous sweep and, after the barrier that completes that sweep,
-        // looks at its slots once; the rare loser of a same-sweep write race (a higher position landed later) takes the
-        // slot with a compare-and-swap minimum on the containing 32-bit word.  Stores of the next sweep may run
-        // beside those repairs: they carry lower positions, so whichever order they land in, the minimum survives.
-        const uint32_t ngroups = (npos + 3) / 4;
-        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
-        uint32_t *E32 = reinterpret_cast<uint32_t *>(E);
-        constexpr int G = ENC_EBUILD_GROUPS;                       // groups of 4 positions per thread and sweep
-        const int32_t sweeps = (int32_t)((ngroups + G * ENC_NT - 1) / (G * ENC_NT));
-        uint32_t hp[G][2];                                         // four 15-bit hashes per group, two per word
-        uint32_t pp[G];                                            // first position of the group, or ~0u
-#pragma unroll
-        for (int u = 0; u < G; u++) pp[u] = 0xffffffffu;
-        for (int32_t k = sweeps - 1; k >= -1; k--) {
-#pragma unroll
-            for (int u = 0; u < G; u++) {
-                if (pp[u] != 0xffffffffu) {
-                    uint32_t hj[4] = {hp[u][0] & 0xffffu, hp[u][0] >> 16, hp[u][1] & 0xffffu, hp[u][1] >> 16};
-                    uint32_t e[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) e[j] = E[hj[j]];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t pj = pp[u] + j;
-                        if (pj < npos && e[j] > pj) {
-                            const uint32_t widx = hj[j] >> 1, shft = (hj[j] & 1) * 16;
-                            uint32_t old = E32[widx];
-                            for (;;) {
-                                const uint32_t curv = (old >> shft) & 0xffffu;
-                                if (curv <= pj) break;
-                                const uint32_t nv = (old & ~(0xffffu << shft)) | (pj << shft);
-                                const uint32_t prev = atomicCAS(&E32[widx], old, nv);
-                                if (prev == old) break;
-                                old = prev;
-                            }
-                        }
-                    }
-                    pp[u] = 0xffffffffu;
-                }
-            }
-            if (k >= 0) {
-#pragma unroll
-                for (int u = G - 1; u >= 0; u--) {
-                    const uint32_t g = ((uint32_t)k * G + (uint32_t)u) * ENC_NT + tid;
-                    if (g < ngroups) {
-                        const uint32_t w0 = srcw[g], w1 = srcw[g + 1], w2 = srcw[g + 2];
-                        const uint32_t p = 4 * g;
-                        uint32_t hj[4];
-#pragma unroll
-                        for (int j = 3; j >= 0; j--) {
-                            const uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
-                            const uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
-                            hj[j] = enc_hash6(lo, hi) >> (32 - ENC_EBITS);
-                            if (p + j < npos) E[hj[j]] = (uint16_t)(p + j);
-                        }
-                        hp[u][0] = hj[0] | (hj[1] << 16); hp[u][1] = hj[2] | (hj[3] << 16);
-                        pp[u] = p;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-#else
     {
         const uint32_t ngroups = (npos + 3) / 4;
         const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
@@ -444,7 +371,6 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         }
         __syncthreads();
     }
-#endif
     B2C_PHASE(2);
 
     // ---------------------------------------------------------------- P2: parse, one thread per 68-byte range
@@ -846,45 +772,21 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
 #ifndef TABLES_MIN_CTAS
 #define TABLES_MIN_CTAS 8      // resident K2 CTAs per SM the register allocation is held to
 #endif
-#ifndef TABLES_DIAG
-#define TABLES_DIAG 0            // 1 / 2: timing probes that leave out the Huffman warp / the FSE warps (output degrades to raw)
-#endif
-#ifndef TABLES_PIPELINED
-#define TABLES_PIPELINED 0   // 1: a fifth warp serialises the Huffman table of the previous chunk (see zstd_tables_loop)
-#endif
-constexpr int TABLES_NT = TABLES_PIPELINED ? 160 : 128;
+constexpr int TABLES_NT = 128;
 struct TablesShared {
     HufWork hw;
     SeqWork sw;
-#if TABLES_PIPELINED
-    HufWork hwB;              // code lengths of the previous chunk, handed to warp 4 for cTable.write
-    uint32_t jobChunk;        // that chunk, or TABLES_NO_JOB
-#endif
 };
-constexpr uint32_t TABLES_NO_JOB = 0xffffffffu;
 B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_t chunk) {
     const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     ChunkWork *W = P.work + chunk;
     if (W->kind != 0) return;
     const uint32_t nseq = W->nseq, nlit = W->nlit;
-#if TABLES_DIAG == 1
-    if (w == 0) { if (lane == 0) { W->hufStatus = HUF_INCOMPRESSIBLE; W->tableDescLen = 0; } return; }   // timing probe: FSE warps only
-#elif TABLES_DIAG == 2
-    if (w != 0) return;                                                                                    // timing probe: Huffman warp only
-#endif
     if (w == 0) {
         HufWork *hw = &ts->hw;
         for (uint32_t s = lane; s < 256; s += 32) hw->count[s] = W->litHist[s];
         if (lane == 0) { hw->status = HUF_INCOMPRESSIBLE; hw->tableDescLen = 0; hw->tableLog = 0; }
         __syncwarp();
-#if TABLES_PIPELINED
-        // codes only; the table description (weights, their FSE compression) is written one iteration later by warp 4
-        if (nlit > 16) huf_build_codes(hw, nlit, lane, 32, -1);
-        __syncwarp();
-        if (hw->status == HUF_OK)
-            for (uint32_t s = lane; s < 256; s += 32) { W->ctVal[s] = hw->ctVal[s]; W->ctBits[s] = hw->ctBits[s]; }
-        if (lane == 0) W->hufTableLog = hw->tableLog;
-#else
         if (nlit > 16) huf_build_table(hw, nlit, lane, 32, -1);
         __syncwarp();
         if (hw->status == HUF_OK) {
@@ -892,7 +794,6 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
             for (uint32_t i = lane; i < hw->tableDescLen; i += 32) W->tableDesc[i] = hw->tableDesc[i];
         }
         if (lane == 0) { W->hufStatus = (uint32_t)hw->status; W->hufTableLog = hw->tableLog; W->tableDescLen = hw->tableDescLen; }
-#endif
     } else {
         const int which = (int)w - 1;
         SeqWork *sw = &ts->sw;
@@ -914,60 +815,15 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
     }
 }
 
-// The chunk loop of a K2 CTA (chunks first, first + stride, ...).
-// Pipelined form: building the Huffman CODES of a chunk (sort, tree, lengths, values) and DESCRIBING the table
-// (weights, their FSE compression: cTable.write) are both serial and of similar length, and the second only needs the
-// code lengths.  Warp 0 therefore hands the lengths of chunk i to warp 4 and goes on with chunk i + 1; the Huffman
-// path per chunk is half as long while the three FSE warps still have slack.
+// The chunk loop of a K2 CTA (chunks first, first + stride, ...).  K2 is bound by instruction issue, not by latency:
+// its serial stretches run with one active lane, and at 8 CTAs per SM the schedulers are about half busy.  Splitting
+// the Huffman work over two warps (codes / table description, pipelined over consecutive chunks) was measured and
+// changed nothing; what helps is fewer warp instructions (e.g. the sort over 2^ceil(log2(symbolLen)) keys).
 B2C_DEV void zstd_tables_loop(TablesShared *ts, const ZstdEncParams &P, uint32_t first, uint32_t stride) {
-#if TABLES_PIPELINED
-    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) ts->jobChunk = TABLES_NO_JOB;
-    __syncthreads();
-    for (uint32_t c = first;; c += stride) {
-        const bool have = c < P.nchunks;
-        const uint32_t job = ts->jobChunk;
-        if (!have && job == TABLES_NO_JOB) break;
-        if (w < 4) {
-            if (have) zstd_tables_chunk(ts, P, c);
-        } else if (job != TABLES_NO_JOB) {
-            HufWork *hb = &ts->hwB;
-            ChunkWork *W = P.work + job;
-            if (hb->status == HUF_OK) {
-                if (lane == 0) huf_bt_write(hb);
-                __syncwarp();
-                if (hb->status == HUF_OK)
-                    for (uint32_t i = lane; i < hb->tableDescLen; i += 32) W->tableDesc[i] = hb->tableDesc[i];
-            }
-            if (lane == 0) { W->hufStatus = (uint32_t)hb->status; W->tableDescLen = hb->tableDescLen; }
-        }
-        __syncthreads();
-        // hand-off: warp 4 is done with the previous job, warp 0 with this chunk's code lengths
-        if (w == 0) {
-            const bool valid = have && P.work[c].kind == 0;
-            if (valid) {
-                const HufWork *hw = &ts->hw;
-                HufWork *hb = &ts->hwB;
-                for (uint32_t s4 = lane; s4 < 64; s4 += 32)
-                    reinterpret_cast<uint32_t *>(hb->ctBits)[s4] = reinterpret_cast<const uint32_t *>(hw->ctBits)[s4];
-                if (lane == 0) {
-                    hb->symbolLen = hw->symbolLen; hb->tableLog = hw->tableLog; hb->status = hw->status;
-                    hb->tableDescLen = 0;
-                }
-            }
-            if (lane == 0) ts->jobChunk = valid ? c : TABLES_NO_JOB;
-        }
-        __syncthreads();
-    }
-#else
     for (uint32_t c = first; c < P.nchunks; c += stride) {
         zstd_tables_chunk(ts, P, c);
         __syncthreads();
-#if TABLES_DIAG == 2
-        if (threadIdx.x == 32) P.work[c].kind = 1;   // no FSE tables were built: store the chunk raw
-#endif
     }
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------ K3
