@@ -12,8 +12,13 @@ import subprocess
 import sys
 
 
+KFILTER = []   # ["--kernel-name", "regex:..."] when the report holds several kernels (B2C_NCU_KERNEL=<regex>)
+if os.environ.get("B2C_NCU_KERNEL"):
+    KFILTER = ["--kernel-name", "regex:" + os.environ["B2C_NCU_KERNEL"]]
+
+
 def ncu(rep, *args):
-    return subprocess.run(["ncu", "-i", rep, *args, "--csv"], capture_output=True, text=True).stdout
+    return subprocess.run(["ncu", "-i", rep, *KFILTER, *args, "--csv"], capture_output=True, text=True).stdout
 
 
 def main():
