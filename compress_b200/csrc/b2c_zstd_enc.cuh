@@ -42,6 +42,9 @@ constexpr uint32_t ENC_MAXREC = 17;       // matches a thread can start inside i
 #ifndef ENC_EBUILD_SYNC_MASK
 #define ENC_EBUILD_SYNC_MASK 1  // barrier every (mask + 1) iterations of the table build's first round
 #endif
+#ifndef ENC_SCAN_BITMAP
+#define ENC_SCAN_BITMAP 1     // 1: dense candidate pass + per-thread walk over a bitmap; 0: per-thread probe loop
+#endif
 #ifndef ENC_PROBES_PER_VOTE
 #define ENC_PROBES_PER_VOTE 8   // probe steps between two looks at the warp state
 #endif
@@ -193,7 +196,9 @@ struct ParseShared {
 constexpr uint32_t ENC_SMEM_SRC = 0;
 constexpr uint32_t ENC_SMEM_E = ENC_SMEM_SRC + ENC_SRC_BYTES;
 constexpr uint32_t ENC_SMEM_L = ENC_SMEM_E + ENC_E_BYTES;
-constexpr uint32_t ENC_SMEM_SH = ENC_SMEM_L + ENC_L_BYTES;
+constexpr uint32_t ENC_BM_BYTES = ENC_MAX_CHUNK / 8 + 16;   // one bit per position: "an earlier occurrence verifies here"
+constexpr uint32_t ENC_SMEM_BM = ENC_SMEM_L + ENC_L_BYTES;
+constexpr uint32_t ENC_SMEM_SH = ENC_SMEM_BM + (ENC_SCAN_BITMAP ? ENC_BM_BYTES : 0);
 constexpr uint32_t ENC_SMEM_BYTES = ENC_SMEM_SH + ((sizeof(ParseShared) + 15) / 16) * 16;
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -389,6 +394,83 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     const uint32_t nlanes = (n + ENC_LANE_BYTES - 1) / ENC_LANE_BYTES;
     uint32_t cnt = 0, lastE = 0;
     bool capped = false;
+#if ENC_SCAN_BITMAP
+    // The greedy scan of a thread asks the same question at every position it visits: "is E[hash(p)] below p and do
+    // four bytes match there?".  The answer does not depend on the scan, so it is computed for ALL positions in one
+    // dense pass (every lane busy, three aligned word loads serve four positions) and kept as one bit per position;
+    // the per-thread loop then jumps from set bit to set bit inside its range instead of probing byte by byte with
+    // most of the warp idle.  The visited positions, and so the parse, are exactly those of the probe loop.
+    uint32_t *bm = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_BM);
+    {
+        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
+        const uint32_t ngroups = (npos + 3) / 4;
+        const uint32_t gEnd = (ngroups + 7) & ~7u;                 // whole bitmap words (8 groups of 4 positions)
+        for (uint32_t g = tid; g < ((gEnd + 31) & ~31u); g += ENC_NT) {
+            uint32_t nib = 0;
+            if (g < ngroups) {
+                const uint32_t w0 = srcw[g], w1 = srcw[g + 1], w2 = srcw[g + 2];
+                const uint32_t p = 4 * g;
+                uint32_t cand[4], lo4[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    lo4[j] = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
+                    const uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
+                    cand[j] = E[enc_hash6(lo4[j], hi) >> (32 - ENC_EBITS)];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (p + j < npos && cand[j] < p + j && ld32u(src, cand[j]) == lo4[j]) nib |= 1u << j;
+            }
+            uint32_t word = nib << (4 * (lane & 7));
+            word |= __shfl_xor_sync(FULLMASK, word, 1);
+            word |= __shfl_xor_sync(FULLMASK, word, 2);
+            word |= __shfl_xor_sync(FULLMASK, word, 4);
+            if ((lane & 7) == 0 && g < gEnd) bm[g >> 3] = word;
+        }
+        __syncthreads();
+    }
+    {
+        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
+        const uint32_t b = tid * ENC_LANE_BYTES;
+        const uint32_t e = (b + ENC_LANE_BYTES < n) ? b + ENC_LANE_BYTES : n;
+        const uint32_t pend = (tid < nlanes) ? (e < npos ? e : npos) : 0u;   // candidate positions need 8 readable bytes
+        uint32_t p = b, nextEmit = b;
+        while (p < pend) {
+            // next set bit in [p, pend)
+            uint32_t wi = p >> 5;
+            uint32_t wv = bm[wi] & (0xffffffffu << (p & 31));
+            while (wv == 0 && (wi + 1) * 32 < pend) wv = bm[++wi];
+            if (wv == 0) break;
+            p = wi * 32 + (uint32_t)(__ffs((int)wv) - 1);
+            if (p >= pend) break;
+            const uint64_t cv = ld64u(src, p);
+            const uint32_t cand = E[enc_hash6((uint32_t)cv, (uint32_t)(cv >> 32)) >> (32 - ENC_EBITS)];
+            const uint32_t lim = (p + ENC_EXT_CAP < n) ? p + ENC_EXT_CAP : n;
+            // forward: 4 bytes per step from two unaligned streams (aligned word loads + funnel shifts)
+            uint32_t len = 4;
+            {
+                uint32_t ia = (p + 4) >> 2, ib = (cand + 4) >> 2;
+                const uint32_t sha = ((p + 4) & 3) * 8, shb = ((cand + 4) & 3) * 8;
+                uint32_t wa0 = srcw[ia], wb0 = srcw[ib];
+                while (p + len < lim) {
+                    const uint32_t wa1 = srcw[++ia], wb1 = srcw[++ib];
+                    const uint32_t x = __funnelshift_r(wa0, wa1, sha) ^ __funnelshift_r(wb0, wb1, shb);
+                    if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                    len += 4; wa0 = wa1; wb0 = wb1;
+                }
+            }
+            capped = false;
+            if (p + len >= lim) { len = lim - p; capped = lim < n; }
+            uint32_t s = p, t = cand;
+            while (s > nextEmit && t > 0 && src[s - 1] == src[t - 1]) { s--; t--; len++; }
+            REC(cnt, tid) = make_uint2(s | (len << 16), p - cand);
+            cnt++;
+            p = s + len;
+            nextEmit = p;
+        }
+        if (cnt) lastE = nextEmit;
+    }
+#else
     {
         // The loop alternates two kinds of steps so that each runs with many active lanes: a probe step for the lanes
         // that are scanning, and -- once enough lanes of the warp hold an unverified-length match (or nobody is left
@@ -450,6 +532,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         }
         if (cnt) lastE = nextEmit;
     }
+#endif
     B2C_PHASE(6);
     cntA[tid] = (uint8_t)cnt;
     capA[tid] = (uint8_t)((cnt != 0) && capped);
