@@ -10,13 +10,13 @@
 // B200-first design: a pipeline of five kernels on one stream, each shaped after the parallelism its
 // stage really has, with a per-chunk work record (ChunkWork) in HBM/L2 between them:
 //   K1 parse    one CTA per chunk (persistent grid = #SMs, 1024 threads).  The chunk is staged into shared
-//               memory with one TMA bulk copy.  32 warps each parse a 2 KiB sub-range 32 positions per
-//               step: every lane hashes its position, probes a private per-warp table (most recent
-//               occurrence in the sub-range) and a CTA-wide table of the EARLIEST occurrence of each hash
-//               in the chunk (built by a race-free min-reduction, so candidates always precede the
-//               position and the output is deterministic), compares 8 bytes in shared memory, and the warp
-//               selects matches greedily with ballot/ffs.  Then literals are gathered, sequences
-//               compacted, codes and histograms computed with all threads.
+//               memory with one TMA bulk copy.  A CTA-wide table keeps the EARLIEST position of every 6-byte
+//               hash (exact minimum, so candidates always precede the position and the result does not
+//               depend on scheduling); one dense pass marks, one bit per position, where that earliest
+//               occurrence verifies over 4 bytes; then every thread runs the reference's greedy loop over
+//               its own 68-byte range, jumping from marked position to marked position (extend forwards /
+//               backwards, emit, skip).  Overlaps between neighbouring threads are trimmed by block-wide
+//               scans, literals are gathered, codes and histograms computed with all threads.
 //   K2 tables   one 4-warp CTA per chunk: the Huffman table (reference tie-breaking) and the three FSE
 //               tables are tiny serial problems -- thousands of them run side by side.
 //   K3 chains   one LANE per (chunk, tANS chain): the reference's serial state walk, 32 chunks per warp.
