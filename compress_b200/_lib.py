@@ -43,7 +43,7 @@ def _load():
         c.c_void_p, c.c_uint32, c.c_void_p]
     lib.b2c_zstd_encode_device_debug.restype = c.c_int
     lib.b2c_zstd_encode_device_debug.argtypes = [
-        c.c_void_p, c.c_int, c.c_void_p, c.c_size_t, c.c_void_p, c.c_uint32, c.c_void_p, c.c_size_t, c.c_void_p,
+        c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_size_t, c.c_void_p, c.c_uint32, c.c_void_p, c.c_size_t, c.c_void_p,
         c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p]
     lib.b2c_zstd_encode_chunks.restype = c.c_int
     lib.b2c_zstd_encode_chunks.argtypes = [

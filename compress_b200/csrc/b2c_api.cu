@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../include/b2c.h"
 #include "b2c_zstd_enc.cuh"
+#include "b2c_lz.cuh"
 #include "b2c_zstd_dec.cuh"
 #include "b2c_s2_dec.cuh"
 #include "b2c_huf0.cuh"
@@ -22,9 +23,15 @@ struct b2c_ctx {
     int device = 0;
     int sm_count = 0;
     size_t max_chunks = 0;
-    uint8_t *d_scratch = nullptr;       // sm_count * ENC_SCRATCH_BYTES (two sets: one per pipeline slot)
+    uint8_t *d_scratch = nullptr;       // per-CTA parse scratch (two sets: one per pipeline slot)
+    size_t scratch_slot = 0;            // bytes of one set
     ChunkWork *d_work[2] = {nullptr, nullptr};   // per-chunk work records, grown on demand
-    size_t work_cap[2] = {0, 0};
+    uint8_t *d_pool[2] = {nullptr, nullptr};     // per-chunk work pool slabs (literals, sequences, codes, state bits)
+    size_t work_cap[2] = {0, 0};        // chunks the records hold
+    size_t pool_cap[2] = {0, 0};        // bytes
+    int parse_r1 = 0;                   // B2C_PARSE=r1: level 1 runs the round-1 parse kernel (A/B measurements)
+    cudaEvent_t ev_busy = nullptr;      // last launch that used the context's scratch / work buffers
+    cudaStream_t busy_stream = nullptr; bool busy_valid = false;
     // host-buffer path staging (slot 0 of the pipeline doubles as the pointer-table path's buffers)
     uint8_t *h_in = nullptr;            // pinned, max_chunks * 64 KiB
     uint8_t *h_out = nullptr;           // pinned, max_chunks * slot
@@ -145,7 +152,24 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return nullptr; }
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = true;
-    ok = ok && cudaMalloc(&ctx->d_scratch, 2 * (size_t)ctx->sm_count * ENC_SCRATCH_BYTES) == cudaSuccess;
+    {
+        size_t a = (size_t)ctx->sm_count * ENC_SCRATCH_BYTES;
+        size_t b = (size_t)ctx->sm_count * LzCfg<1>::MIN_CTAS * LzLayout<1>::SCRATCH_BYTES;
+        size_t c = (size_t)ctx->sm_count * LzCfg<2>::MIN_CTAS * LzLayout<2>::SCRATCH_BYTES;
+        ctx->scratch_slot = ((a > b ? (a > c ? a : c) : (b > c ? b : c)) + 255) & ~(size_t)255;
+        const char *pe = getenv("B2C_PARSE");
+        ctx->parse_r1 = (pe && strcmp(pe, "r1") == 0) ? 1 : 0;
+    }
+    ok = ok && cudaMalloc(&ctx->d_scratch, 2 * ctx->scratch_slot) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_busy, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_parse1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)LzLayout<1>::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_parse2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)LzLayout<2>::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)HIST_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_pack128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)PackCfg<131072>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)ENC_SMEM_BYTES) == cudaSuccess;
@@ -198,7 +222,8 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_dec_lit); cudaFree(ctx->d_dec_in); cudaFree(ctx->d_dec_out); cudaFree(ctx->d_dec_meta);
-    cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
+    cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_pool[0]); cudaFree(ctx->d_pool[1]);
+    if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
     cudaFree(ctx->d_sizes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_src_sizes);
     cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_sizes); cudaFreeHost(ctx->h_src_sizes);
     cudaFree(ctx->d_in2); cudaFree(ctx->d_out2); cudaFree(ctx->d_packed2); cudaFree(ctx->d_sizes2);
@@ -242,20 +267,20 @@ int b2c_profile_enable(b2c_ctx *ctx, int on) {
     ctx->pev_used = 0;
     return B2C_OK;
 }
-// ms[k] = summed duration of kernel k (0 xxh64, 1 parse, 2 tables, 3 chains, 4 pack) over the encode calls issued
+// ms[k] = summed duration of kernel k (0 xxh64, 1 parse, 2 histograms, 3 tables, 4 chains, 5 pack) over the encode launches issued
 // since b2c_profile_enable(ctx, 1); *ncalls = number of encode calls.  Synchronises the device.
 int b2c_profile_read(b2c_ctx *ctx, double *ms, uint32_t *ncalls) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
-    for (int k = 0; k < 5; k++) ms[k] = 0.0;
-    for (size_t c = 0; c + 6 <= ctx->pev_used; c += 6)
-        for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < 6; k++) ms[k] = 0.0;
+    for (size_t c = 0; c + 7 <= ctx->pev_used; c += 7)
+        for (int k = 0; k < 6; k++) {
             float t = 0.f;
             CK(cudaEventElapsedTime(&t, ctx->pev[c + k], ctx->pev[c + k + 1]));
             ms[k] += (double)t;
         }
-    if (ncalls) *ncalls = (uint32_t)(ctx->pev_used / 6);
+    if (ncalls) *ncalls = (uint32_t)(ctx->pev_used / 7);
     ctx->pev_used = 0;
     return B2C_OK;
 }
@@ -273,65 +298,123 @@ size_t b2c_zstd_bound(size_t size, int level) {
     return fh + 3 * blocks + size;
 }
 
+static uint32_t level_block(int level) { return level == B2C_LEVEL_FASTEST ? (1u << 16) : (128u << 10); }
+static bool level_ok(int level) { return level == B2C_LEVEL_FASTEST || level == B2C_LEVEL_DEFAULT; }
+static size_t level_slot(int level) { return (size_t)level_block(level) + 512; }   // >= MaxEncodedSize(block), 16-byte multiple
+
+// Calls that use the context's scratch / work buffers are ordered among themselves even when they are issued on
+// different streams: the next one waits for the event the previous one recorded.
+static int ctx_order_begin(b2c_ctx *ctx, cudaStream_t st) {
+    if (ctx->busy_valid && ctx->busy_stream != st) CK(cudaStreamWaitEvent(st, ctx->ev_busy, 0));
+    return B2C_OK;
+}
+static int ctx_order_end(b2c_ctx *ctx, cudaStream_t st) {
+    CK(cudaEventRecord(ctx->ev_busy, st));
+    ctx->busy_stream = st; ctx->busy_valid = true;
+    return B2C_OK;
+}
+
+// One encode launch = the six kernels over at most `sub` chunks at a time (the work records and the work pool are
+// sized for `sub` chunks, so a device-resident call of any size needs a bounded amount of scratch).
 static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
                          const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
                          int64_t *d_out_sizes, uint32_t nchunks, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
                          uint8_t *dbg_lits, uint32_t dbg_cap, cudaStream_t st, unsigned long long *dbg_cycles = nullptr,
                          int slot = 0) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
-    if (level != B2C_LEVEL_FASTEST) return B2C_ERR_UNSUPPORTED;
+    if (!level_ok(level)) return B2C_ERR_UNSUPPORTED;
     if (nchunks == 0) return B2C_OK;
     if (dst_stride > 0xffffffffull) return B2C_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    if (ctx->work_cap[slot] < nchunks) {
-        // grow the per-chunk work records (kernels of earlier calls on other streams may still use the old one)
+    const uint32_t blockmax = level_block(level);
+    const uint64_t pstride = wk_pool_stride(blockmax);
+    const uint32_t subMax = blockmax > 65536 ? 2048u : 4096u;
+    const uint32_t sub = nchunks < subMax ? nchunks : subMax;
+    if (ctx->work_cap[slot] < sub || ctx->pool_cap[slot] < (size_t)sub * pstride) {
+        // grow the per-chunk work records / pool (kernels of earlier calls on other streams may still use the old ones)
         CK(cudaDeviceSynchronize());
-        if (ctx->d_work[slot]) CK(cudaFree(ctx->d_work[slot]));
-        ctx->d_work[slot] = nullptr; ctx->work_cap[slot] = 0;
-        CK(cudaMalloc(&ctx->d_work[slot], (size_t)nchunks * sizeof(ChunkWork)));
-        ctx->work_cap[slot] = nchunks;
-    }
-    ZstdEncParams P;
-    memset(&P, 0, sizeof(P));
-    P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_sizes = d_sizes; P.src_size_all = size_all;
-    P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
-    P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.flags = (uint32_t)flags;
-    P.scratch = ctx->d_scratch + (size_t)slot * ctx->sm_count * ENC_SCRATCH_BYTES;
-    P.work = ctx->d_work[slot];
-    P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_cap;
-    P.dbg_cycles = dbg_cycles;
-    unsigned sms = (unsigned)ctx->sm_count;
-    unsigned g1 = sms < nchunks ? sms : nchunks;
-    unsigned g2 = sms * TABLES_CTAS_PER_SM < nchunks ? sms * TABLES_CTAS_PER_SM : nchunks;
-    cudaEvent_t *pe = nullptr;
-    if (ctx->prof) {
-        while (ctx->pev.size() < ctx->pev_used + 6) {
-            cudaEvent_t e;
-            CK(cudaEventCreate(&e));
-            ctx->pev.push_back(e);
+        if (ctx->work_cap[slot] < sub) {
+            if (ctx->d_work[slot]) CK(cudaFree(ctx->d_work[slot]));
+            ctx->d_work[slot] = nullptr; ctx->work_cap[slot] = 0;
+            CK(cudaMalloc(&ctx->d_work[slot], (size_t)sub * sizeof(ChunkWork)));
+            ctx->work_cap[slot] = sub;
         }
-        pe = ctx->pev.data() + ctx->pev_used;
-        ctx->pev_used += 6;
+        if (ctx->pool_cap[slot] < (size_t)sub * pstride) {
+            if (ctx->d_pool[slot]) CK(cudaFree(ctx->d_pool[slot]));
+            ctx->d_pool[slot] = nullptr; ctx->pool_cap[slot] = 0;
+            CK(cudaMalloc(&ctx->d_pool[slot], (size_t)sub * pstride));
+            ctx->pool_cap[slot] = (size_t)sub * pstride;
+        }
     }
+    { int r = ctx_order_begin(ctx, st); if (r) return r; }
+    const unsigned sms = (unsigned)ctx->sm_count;
+    const bool r1 = ctx->parse_r1 && level == B2C_LEVEL_FASTEST;
+    for (uint32_t c0 = 0; c0 < nchunks; c0 += sub) {
+        const uint32_t m = (nchunks - c0 < sub) ? nchunks - c0 : sub;
+        ZstdEncParams P;
+        memset(&P, 0, sizeof(P));
+        P.src_base = (const uint8_t *)d_src + (size_t)c0 * src_stride; P.src_stride = src_stride;
+        P.src_sizes = d_sizes ? d_sizes + c0 : nullptr; P.src_size_all = size_all;
+        P.dst_base = (uint8_t *)d_dst + (size_t)c0 * dst_stride; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
+        P.out_sizes = d_out_sizes + c0; P.nchunks = m; P.flags = (uint32_t)flags;
+        P.scratch = ctx->d_scratch + (size_t)slot * ctx->scratch_slot;
+        P.work = ctx->d_work[slot];
+        P.pool = ctx->d_pool[slot]; P.pool_stride = pstride; P.maxseq = wk_maxseq(blockmax); P.blockmax = blockmax;
+        P.big = blockmax > 65536 ? 1u : 0u; P.level = (uint32_t)level;
+        if (dbg_hdr) {
+            P.dbg_hdr = dbg_hdr + (size_t)c0 * 4; P.dbg_seqs = dbg_seqs + (size_t)c0 * dbg_cap * 3;
+            P.dbg_lits = dbg_lits + (size_t)c0 * blockmax; P.dbg_seq_cap = dbg_cap;
+        }
+        P.dbg_cycles = dbg_cycles ? dbg_cycles + (size_t)c0 * 16 * 32 : nullptr;
+        cudaEvent_t *pe = nullptr;
+        if (ctx->prof) {
+            while (ctx->pev.size() < ctx->pev_used + 7) {
+                cudaEvent_t e;
+                CK(cudaEventCreate(&e));
+                ctx->pev.push_back(e);
+            }
+            pe = ctx->pev.data() + ctx->pev_used;
+            ctx->pev_used += 7;
+        }
 #define PEV(k) do { if (pe) cudaEventRecord(pe[k], st); } while (0)
-    PEV(0);
-    if ((flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC)) {
-        b2c_zstd_xxh_kernel<<<(4 * nchunks + 127) / 128, 128, 0, st>>>(P);
-        ctx->launches += 1;
-    }
-    PEV(1);
-    b2c_zstd_parse_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
-    PEV(2);
-    b2c_zstd_tables_kernel<<<g2, TABLES_NT, 0, st>>>(P);
-    PEV(3);
-    b2c_zstd_chains_kernel<<<(nchunks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, st>>>(P);
-    PEV(4);
-    b2c_zstd_pack_kernel<<<nchunks, PACK_NT, PACK_SMEM_BYTES, st>>>(P);
-    PEV(5);
+        PEV(0);
+        if ((flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC)) {
+            b2c_zstd_xxh_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(P);
+            ctx->launches += 1;
+        }
+        PEV(1);
+        if (r1) {
+            const unsigned g1 = sms < m ? sms : m;
+            b2c_zstd_parse_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+            PEV(2);
+            ctx->launches += 1;
+        } else {
+            if (level == B2C_LEVEL_FASTEST) {
+                const unsigned cap = sms * LzCfg<1>::MIN_CTAS, g1 = cap < m ? cap : m;
+                b2c_lz_parse1_kernel<<<g1, LzCfg<1>::NT, LzLayout<1>::SMEM_BYTES, st>>>(P);
+            } else {
+                const unsigned cap = sms * LzCfg<2>::MIN_CTAS, g1 = cap < m ? cap : m;
+                b2c_lz_parse2_kernel<<<g1, LzCfg<2>::NT, LzLayout<2>::SMEM_BYTES, st>>>(P);
+            }
+            PEV(2);
+            const unsigned gh = sms * 7 < m ? sms * 7 : m;
+            b2c_zstd_hist_kernel<<<gh, HIST_NT, HIST_SMEM_BYTES, st>>>(P);
+            ctx->launches += 2;
+        }
+        PEV(3);
+        const unsigned g2 = sms * TABLES_CTAS_PER_SM < m ? sms * TABLES_CTAS_PER_SM : m;
+        b2c_zstd_tables_kernel<<<g2, TABLES_NT, 0, st>>>(P);
+        PEV(4);
+        b2c_zstd_chains_kernel<<<(m + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, st>>>(P);
+        PEV(5);
+        if (blockmax > 65536) b2c_zstd_pack128_kernel<<<m, PACK_NT, PackCfg<131072>::SMEM_BYTES, st>>>(P);
+        else b2c_zstd_pack_kernel<<<m, PACK_NT, PACK_SMEM_BYTES, st>>>(P);
+        PEV(6);
 #undef PEV
-    ctx->launches += 4;
-    CK(cudaGetLastError());
-    return B2C_OK;
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+    }
+    return ctx_order_end(ctx, st);
 }
 
 int b2c_zstd_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
@@ -341,11 +424,11 @@ int b2c_zstd_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src
                          nchunks, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
-int b2c_zstd_encode_device_debug(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride,
+int b2c_zstd_encode_device_debug(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
                                  const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
                                  int64_t *d_out_sizes, uint32_t nchunks, uint32_t *d_dbg_hdr, uint32_t *d_dbg_seqs,
                                  uint8_t *d_dbg_lits, uint32_t dbg_seq_cap, void *stream) {
-    return launch_encode(ctx, B2C_LEVEL_FASTEST, flags, d_src, src_stride, d_sizes, size_all, d_dst, dst_stride,
+    return launch_encode(ctx, level, flags, d_src, src_stride, d_sizes, size_all, d_dst, dst_stride,
                          d_out_sizes, nchunks, d_dbg_hdr, d_dbg_seqs, d_dbg_lits, dbg_seq_cap, (cudaStream_t)stream);
 }
 
@@ -359,21 +442,24 @@ int b2c_zstd_encode_device_timed(b2c_ctx *ctx, int flags, const void *d_src, siz
 int b2c_zstd_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const *srcs, const size_t *src_sizes,
                            void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
-    if (level != B2C_LEVEL_FASTEST) return B2C_ERR_UNSUPPORTED;
+    if (!level_ok(level)) return B2C_ERR_UNSUPPORTED;
     if (!ctx->max_chunks) return B2C_ERR_ARG;
+    const size_t blk = level_block(level), slotB = level_slot(level);
+    const size_t mcap = ctx->max_chunks * (size_t)ENC_MAX_CHUNK / blk;   // the staging buffers hold max_chunks x 64 KiB
+    if (!mcap) return B2C_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    for (size_t base = 0; base < n; base += ctx->max_chunks) {
+    for (size_t base = 0; base < n; base += mcap) {
         size_t m = n - base;
-        if (m > ctx->max_chunks) m = ctx->max_chunks;
+        if (m > mcap) m = mcap;
         // contiguous equal-sized input needs no host-side staging copy
         bool contiguous = true;
         for (size_t i = 0; i < m; i++) {
-            if (src_sizes[base + i] > ENC_MAX_CHUNK) { contiguous = false; }
+            if (src_sizes[base + i] > blk) { contiguous = false; }
             if (i + 1 < m && ((const uint8_t *)srcs[base + i] + src_sizes[base + i] != (const uint8_t *)srcs[base + i + 1] ||
-                              src_sizes[base + i] != ENC_MAX_CHUNK))
+                              src_sizes[base + i] != blk))
                 contiguous = false;
-            ctx->h_src_sizes[i] = (uint32_t)(src_sizes[base + i] > ENC_MAX_CHUNK ? ENC_MAX_CHUNK + 1 : src_sizes[base + i]);
+            ctx->h_src_sizes[i] = (uint32_t)(src_sizes[base + i] > blk ? blk + 1 : src_sizes[base + i]);
         }
         size_t in_bytes = 0;
         for (size_t i = 0; i < m; i++) in_bytes += src_sizes[base + i];
@@ -381,17 +467,17 @@ int b2c_zstd_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const
             CK(cudaMemcpyAsync(ctx->d_in, srcs[base], in_bytes, cudaMemcpyHostToDevice, st));
         } else {
             for (size_t i = 0; i < m; i++) {
-                size_t sz = src_sizes[base + i] > ENC_MAX_CHUNK ? 0 : src_sizes[base + i];
-                memcpy(ctx->h_in + i * (size_t)ENC_MAX_CHUNK, srcs[base + i], sz);
+                size_t sz = src_sizes[base + i] > blk ? 0 : src_sizes[base + i];
+                memcpy(ctx->h_in + i * (size_t)blk, srcs[base + i], sz);
             }
-            CK(cudaMemcpyAsync(ctx->d_in, ctx->h_in, m * (size_t)ENC_MAX_CHUNK, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ctx->d_in, ctx->h_in, m * (size_t)blk, cudaMemcpyHostToDevice, st));
         }
         CK(cudaMemcpyAsync(ctx->d_src_sizes, ctx->h_src_sizes, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        int rc = launch_encode(ctx, level, flags, ctx->d_in, ENC_MAX_CHUNK, ctx->d_src_sizes, 0, ctx->d_out, kSlot,
+        int rc = launch_encode(ctx, level, flags, ctx->d_in, blk, ctx->d_src_sizes, 0, ctx->d_out, slotB,
                                ctx->d_sizes, (uint32_t)m, nullptr, nullptr, nullptr, 0, st);
         if (rc) return rc;
         b2c_scan_sizes_kernel<<<1, 1024, 0, st>>>(ctx->d_sizes, ctx->d_offsets, (uint32_t)m);
-        b2c_pack_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_out, kSlot, ctx->d_sizes, ctx->d_offsets, ctx->d_packed, (uint32_t)m);
+        b2c_pack_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->d_out, slotB, ctx->d_sizes, ctx->d_offsets, ctx->d_packed, (uint32_t)m);
         ctx->launches += 2;
         int64_t *h_sz = ctx->h_sizes;
         uint64_t *h_off = reinterpret_cast<uint64_t *>(ctx->h_sizes + m);
@@ -421,11 +507,13 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
                            uint32_t chunk_size, void *h_dst, size_t dst_cap, int64_t *sizes_out,
                            uint64_t *offsets_out, size_t *total_out) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
-    if (level != B2C_LEVEL_FASTEST) return B2C_ERR_UNSUPPORTED;
-    if (!ctx->max_chunks || chunk_size == 0 || chunk_size > ENC_MAX_CHUNK) return B2C_ERR_ARG;
+    if (!level_ok(level)) return B2C_ERR_UNSUPPORTED;
+    const size_t blk = level_block(level), slotB = level_slot(level);
+    if (!ctx->max_chunks || chunk_size == 0 || chunk_size > blk) return B2C_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const size_t nchunks = src_bytes == 0 ? 1 : (src_bytes + chunk_size - 1) / chunk_size;
-    const size_t B = ctx->max_chunks;
+    const size_t B = ctx->max_chunks * (size_t)ENC_MAX_CHUNK / blk;   // the staging buffers hold max_chunks x 64 KiB
+    if (!B) return B2C_ERR_ARG;
     // Batch schedule: full batches, then a tail that halves down to about four chunks per SM.  The H2D stream is the
     // bottleneck of the pipeline, so the time after the last H2D copy (kernels + D2H of the last batch) is pure
     // overhead; a small last batch keeps it short.
@@ -504,11 +592,11 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
         // kernels: need the input; the packed-output slot is free once batch b-2's D2H copy is done
         CK(cudaStreamWaitEvent(st_c, ctx->ev_in[sl], 0));
         if (b >= 2) CK(cudaStreamWaitEvent(st_c, ctx->ev_out[sl], 0));
-        int r = launch_encode(ctx, level, flags, S.d_in, chunk_size, bss[b], chunk_size, S.d_out, kSlot, S.d_sizes,
+        int r = launch_encode(ctx, level, flags, S.d_in, chunk_size, bss[b], chunk_size, S.d_out, slotB, S.d_sizes,
                               (uint32_t)m, nullptr, nullptr, nullptr, 0, st_c, nullptr, sl);
         if (r) return r;
         b2c_scan_sizes_kernel<<<1, 1024, 0, st_c>>>(S.d_sizes, S.d_off, (uint32_t)m);
-        b2c_pack_kernel<<<ctx->sm_count * 4, 256, 0, st_c>>>(S.d_out, kSlot, S.d_sizes, S.d_off, S.d_packed, (uint32_t)m);
+        b2c_pack_kernel<<<ctx->sm_count * 4, 256, 0, st_c>>>(S.d_out, slotB, S.d_sizes, S.d_off, S.d_packed, (uint32_t)m);
         ctx->launches += 2;
         CK(cudaMemcpyAsync(S.h_sizes, S.d_sizes, m * sizeof(int64_t), cudaMemcpyDeviceToHost, st_c));
         CK(cudaMemcpyAsync(S.h_sizes + m, S.d_off, (m + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st_c));

@@ -1,0 +1,644 @@
+// compress_b200/csrc/b2c_lz.cuh -- the round-2 match finder for the zstd block encoders (levels 1 and 2), sm_100a.
+//
+// Replaces, for the GPU path, the reference's serial match finders
+//   zstd/enc_fast.go:294-531   fastEncoder.EncodeNoHist        (level 1: one table, 6-byte hash, 64 KiB blocks)
+//   zstd/enc_dfast.go:372-675  doubleFastEncoder.EncodeNoHist  (level 2: long 8-byte + short 5-byte table, long match
+//                                                               preferred, lazy long check at s+1, 128 KiB blocks)
+// with one parallel parse whose output (literals + sequences) feeds the unchanged entropy stages K2..K4.
+//
+// Why a new table discipline.  Round 1 kept the EARLIEST position of every hash in a static table so that 1024 threads
+// could probe it at once; scoring parse variants with the oracle's entropy stage (tests/model/) showed that recency is
+// what the reference's "latest position" table buys: on 64 KiB text chunks a latest-position candidate is worth -6 %
+// output, on HTML -12 %.  A fully dynamic table is serial; what is built here is the parallel form that keeps most of
+// it: positions are inserted in TILES (4 per thread, in position order); a slot holds the earliest position of the
+// latest tile that touched it.  A position therefore sees (a) "far": the slot as the earlier tiles left it and (b) "near":
+// the earliest equal-hash position of its own tile, when that lies before it.  Per tile: probe (far) | barrier | plain
+// stores | barrier | losers of a store race fix the slot with atomicMin (exact minimum, so the result never depends
+// on scheduling) | barrier | probe (near).  Slots are 32-bit: position << 14 | 14 hash bits, so a candidate is
+// accepted by its tag and the dense pass never reads the input at the candidate (random shared-memory reads are what
+// bounded the round-1 kernel: about 3.4 bank-conflict cycles per warp access, five accesses per position there, four
+// here for a much better parse).  The chunk itself is streamed from global memory during the dense pass (coalesced,
+// prefetched one tile ahead) and only afterwards staged into the dead table's shared memory by one TMA bulk copy for
+// the random accesses of the walk.
+//
+// After the dense pass every thread runs the greedy scan over its own 128-byte range (set bit -> candidate distance
+// from a per-CTA scratch array -> extend forwards/backwards -> emit -> skip), neighbours are merged by a prefix
+// maximum of match ends (as in round 1), sequences and codes are written, and the literals are produced by a
+// warp-cooperative stream compaction of the staged chunk under a one-bit-per-position literal mask (coalesced byte
+// stores; no 64 KiB literal staging buffer, which is what lets two CTAs share an SM).  The literal and code histograms
+// moved to their own kernel (b2c_zstd_hist_kernel).
+#pragma once
+#include "b2c_zstd_enc.cuh"
+
+namespace b2c {
+
+constexpr uint32_t LZ_RANGE = 128;          // bytes walked by one thread
+constexpr uint32_t LZ_MAXREC = LZ_RANGE / 4;   // matches a thread can start inside its range (min match 4)
+constexpr uint32_t LZ_TAGBITS = 14;
+constexpr uint32_t LZ_TAGMASK = (1u << LZ_TAGBITS) - 1;
+constexpr uint32_t LZ_EMPTY = 0xffffffffu;
+constexpr uint32_t LZ_EXT_CAP = 256;        // per-thread forward extension limit; longer matches are finished by warp 0
+
+template <int LV> struct LzCfg;
+template <> struct LzCfg<1> {
+    static constexpr int NT = 512;
+    static constexpr uint32_t BLOCK = 65536;
+    static constexpr bool LONG = false;
+    static constexpr uint32_t TBITS = 14;
+    static constexpr uint32_t SREC = 6;       // match records per thread kept in shared memory
+    static constexpr int MIN_CTAS = 2;
+};
+template <> struct LzCfg<2> {
+    static constexpr int NT = 1024;
+    static constexpr uint32_t BLOCK = 131072;
+    static constexpr bool LONG = true;
+    static constexpr uint32_t TBITS = 14;
+    static constexpr uint32_t SREC = 4;
+    static constexpr int MIN_CTAS = 1;
+};
+
+template <int LV> struct LzLayout {
+    using C = LzCfg<LV>;
+    static constexpr uint32_t NTAB = C::LONG ? 2 : 1;
+    static constexpr uint32_t TAB_BYTES = NTAB * (4u << C::TBITS);
+    static constexpr uint32_t SRC_BYTES = C::BLOCK + 128;
+    static constexpr uint32_t A_BYTES = TAB_BYTES > SRC_BYTES ? TAB_BYTES : SRC_BYTES;
+    static constexpr uint32_t BM_BYTES = C::BLOCK / 8 + 16;
+    static constexpr uint32_t SM_A = 0;
+    static constexpr uint32_t SM_BM = SM_A + A_BYTES;
+    static constexpr uint32_t SM_BML = SM_BM + BM_BYTES;
+    static constexpr uint32_t SM_REC = SM_BML + (C::LONG ? BM_BYTES : 0);
+    static constexpr uint32_t SM_ARR = SM_REC + C::SREC * C::NT * 8;            // keptEnd u32 | lastOff u32 | cnt u8 | cap u8
+    static constexpr uint32_t SM_SH = SM_ARR + C::NT * 10;
+    static constexpr uint32_t SMEM_BYTES = SM_SH + ((sizeof(ParseShared) + 2 * 80 * 4 + 15) / 16) * 16;
+    // per-CTA global scratch: candidate distances (u16 per position) + spilled match records [k][thread]
+    static constexpr uint32_t DIST_BYTES = C::BLOCK * 2;
+    static constexpr uint32_t SCRATCH_BYTES = DIST_BYTES + (LZ_MAXREC - C::SREC) * C::NT * 8;
+};
+static_assert(2 * (LzLayout<1>::SMEM_BYTES + 1024) <= 228 * 1024, "two level-1 parse CTAs must fit one SM");
+static_assert(LzLayout<2>::SMEM_BYTES <= 227 * 1024, "the level-2 parse CTA must fit one SM");
+
+// hashes: two 32-bit multiply-adds (the reference's hashLen is a 64-bit multiply, zstd/hash.go:27-33; table contents
+// are an implementation detail, only verified matches reach the output)
+B2C_DEV uint32_t lz_hash6(uint32_t lo, uint32_t hi) { return lo * 0x9E3779B1u + (hi & 0xffffu) * 0x85EBCA6Bu; }
+B2C_DEV uint32_t lz_hash5(uint32_t lo, uint32_t hi) { return lo * 0x9E3779B1u + (hi & 0xffu) * 0x85EBCA6Bu; }
+B2C_DEV uint32_t lz_hash8(uint32_t lo, uint32_t hi) { return lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu; }
+
+// exclusive scan of two values per thread (same conventions as group_scan_excl; ws: >= 80 words)
+B2C_DEV void group_scan_excl_pair(uint32_t a, uint32_t b, uint32_t *ws, int nthreads, unsigned tid, uint32_t *exA,
+                                  uint32_t *exB, uint32_t *totA, uint32_t *totB) {
+    const unsigned lane = tid & 31, w = tid >> 5;
+    const uint32_t ia = warp_scan_incl(a), ib = warp_scan_incl(b);
+    if (lane == 31) { ws[w] = ia; ws[40 + w] = ib; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = nthreads >> 5;
+        const uint32_t xa = (lane < (unsigned)nw) ? ws[lane] : 0, xb = (lane < (unsigned)nw) ? ws[40 + lane] : 0;
+        const uint32_t sa = warp_scan_incl(xa), sb = warp_scan_incl(xb);
+        ws[lane] = sa - xa; ws[40 + lane] = sb - xb;
+        if (lane == 31) { ws[32] = sa; ws[72] = sb; }
+    }
+    __syncthreads();
+    *exA = ws[w] + ia - a; *exB = ws[40 + w] + ib - b;
+    *totA = ws[32]; *totB = ws[72];
+}
+
+// match record: start (17 bits) | low 15 length bits; distance (16 bits) | high length bits
+B2C_DEV uint2 lz_rec(uint32_t s, uint32_t len, uint32_t d) { return make_uint2(s | ((len & 0x7fffu) << 17), d | ((len >> 15) << 16)); }
+B2C_DEV uint32_t lz_rec_s(const uint2 r) { return r.x & 0x1ffffu; }
+B2C_DEV uint32_t lz_rec_len(const uint2 r) { return (r.x >> 17) | ((r.y >> 16) << 15); }
+B2C_DEV uint32_t lz_rec_d(const uint2 r) { return r.y & 0xffffu; }
+
+template <int LV>
+B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk, uint8_t *scratch) {
+    using C = LzCfg<LV>;
+    using L = LzLayout<LV>;
+    constexpr int NT = C::NT;
+    constexpr uint32_t TSIZE = 1u << C::TBITS;
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t *TS = reinterpret_cast<uint32_t *>(smem + L::SM_A);
+    uint32_t *TL = TS + TSIZE;                                   // level 2 only
+    uint8_t *src = smem + L::SM_A;                               // after the dense pass
+    uint32_t *bm = reinterpret_cast<uint32_t *>(smem + L::SM_BM);   // any candidate; later the literal mask
+    uint32_t *bml = reinterpret_cast<uint32_t *>(smem + L::SM_BML); // long candidate (level 2)
+    ParseShared *sh = reinterpret_cast<ParseShared *>(smem + L::SM_SH);
+    uint32_t *ws2 = reinterpret_cast<uint32_t *>(smem + L::SM_SH + ((sizeof(ParseShared) + 15) / 16) * 16);
+    ChunkWork *W = P.work + chunk;
+    const WkLens wlen = wk_lens(P, chunk);
+    uint32_t *const wof = wk_of(P, chunk);
+    uint8_t *const wcodes = wk_codes(P, chunk, 0);
+    const uint32_t mseq = P.maxseq;
+    uint16_t *cd = reinterpret_cast<uint16_t *>(scratch);
+
+    const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
+    const uint32_t n = chunk_size(P, chunk);
+    if (n > C::BLOCK || n > P.blockmax) {
+        if (tid == 0) { W->n = n; W->kind = 3; }   // reported as B2C_ERR_TOO_BIG by the pack kernel
+        return;
+    }
+    B2C_PHASE(0);
+    // ---------------------------------------------------------------- P0: empty tables
+    for (uint32_t i = tid; i < L::NTAB * TSIZE; i += NT) TS[i] = LZ_EMPTY;
+    __syncthreads();
+
+    // ---------------------------------------------------------------- P1: dense pass, tile by tile
+    // aligned word k of the chunk's address range holds chunk bytes [4k - mis, 4k - mis + 4)
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(gsrc) & 3), msh = mis * 8;
+    const uint32_t *gw = reinterpret_cast<const uint32_t *>(gsrc - mis);
+    const uint32_t nraw = (n + mis + 3) >> 2;      // aligned words that contain chunk bytes
+#define LZ_RAW(k) (((k) < nraw) ? B2C_LDG(gw + (k)) : 0u)
+#define LZ_WORD(dst, wi)                                                                         \
+    do {                                                                                         \
+        const uint32_t k_ = (wi);                                                                \
+        const uint32_t a_ = LZ_RAW(k_);                                                          \
+        if (mis) { const uint32_t b_ = LZ_RAW(k_ + 1); (dst) = __funnelshift_r(a_, b_, msh); }   \
+        else (dst) = a_;                                                                         \
+    } while (0)
+    const uint32_t npos = (n >= 8) ? n - 7 : 0;    // positions with 8 readable bytes
+    const uint32_t ngroups = (npos + 3) / 4;
+    const uint32_t ntiles = (ngroups + NT - 1) / NT;
+    {
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        if (ntiles) { LZ_WORD(w0, tid); LZ_WORD(w1, tid + 1); LZ_WORD(w2, tid + 2); }
+        for (uint32_t k = 0; k < ntiles; k++) {
+            const uint32_t g = k * NT + tid, p0 = 4 * g;
+            uint32_t nw0 = 0, nw1 = 0, nw2 = 0;
+            if (k + 1 < ntiles) { LZ_WORD(nw0, g + NT); LZ_WORD(nw1, g + NT + 1); LZ_WORD(nw2, g + NT + 2); }
+            uint32_t es[4], is[4], fs[4];
+            uint32_t el[4], il[4], fl[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
+                const uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
+                const uint32_t h = C::LONG ? lz_hash5(lo, hi) : lz_hash6(lo, hi);
+                is[j] = h >> (32 - C::TBITS);
+                es[j] = ((p0 + j) << LZ_TAGBITS) | ((h >> 4) & LZ_TAGMASK);
+                fs[j] = TS[is[j]];                                             // far candidate: earlier tiles
+                if constexpr (C::LONG) {
+                    const uint32_t hl = lz_hash8(lo, hi);
+                    il[j] = hl >> (32 - C::TBITS);
+                    el[j] = ((p0 + j) << LZ_TAGBITS) | ((hl >> 4) & LZ_TAGMASK);
+                    fl[j] = TL[il[j]];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 3; j >= 0; j--)                                       // lowest position of the thread lands last
+                if (p0 + j < npos) {
+                    TS[is[j]] = es[j];
+                    if constexpr (C::LONG) TL[il[j]] = el[j];
+                }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (p0 + j < npos) {
+                    if (TS[is[j]] > es[j]) atomicMin(&TS[is[j]], es[j]);      // lost a store race: exact minimum
+                    if constexpr (C::LONG) { if (TL[il[j]] > el[j]) atomicMin(&TL[il[j]], el[j]); }
+                }
+            __syncthreads();
+            uint32_t nibA = 0, nibL = 0, dist[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t p = p0 + j;
+                uint32_t d = 0;
+                bool ok = false, okL = false;
+                if (p < npos) {
+                    if constexpr (C::LONG) {
+                        const uint32_t r = TL[il[j]];
+                        const bool nearOk = r < el[j] && ((r ^ el[j]) & LZ_TAGMASK) == 0;
+                        const bool farOk = fl[j] < el[j] && ((fl[j] ^ el[j]) & LZ_TAGMASK) == 0;
+                        const uint32_t dd = p - ((nearOk ? r : fl[j]) >> LZ_TAGBITS);
+                        if ((nearOk || farOk) && dd < 65536u) { okL = true; d = dd; }
+                    }
+                    if (!okL) {
+                        const uint32_t r = TS[is[j]];
+                        const bool nearOk = r < es[j] && ((r ^ es[j]) & LZ_TAGMASK) == 0;
+                        const bool farOk = fs[j] < es[j] && ((fs[j] ^ es[j]) & LZ_TAGMASK) == 0;
+                        const uint32_t dd = p - ((nearOk ? r : fs[j]) >> LZ_TAGBITS);
+                        if ((nearOk || farOk) && dd < 65536u) { ok = true; d = dd; }
+                    }
+                }
+                dist[j] = d;
+                if (ok || okL) nibA |= 1u << j;
+                if (okL) nibL |= 1u << j;
+            }
+            *reinterpret_cast<uint2 *>(cd + p0) = make_uint2(dist[0] | (dist[1] << 16), dist[2] | (dist[3] << 16));
+            {
+                uint32_t word = nibA << (4 * (lane & 7));
+                word |= __shfl_xor_sync(FULLMASK, word, 1);
+                word |= __shfl_xor_sync(FULLMASK, word, 2);
+                word |= __shfl_xor_sync(FULLMASK, word, 4);
+                if ((lane & 7) == 0) bm[g >> 3] = word;
+                if constexpr (C::LONG) {
+                    uint32_t wl = nibL << (4 * (lane & 7));
+                    wl |= __shfl_xor_sync(FULLMASK, wl, 1);
+                    wl |= __shfl_xor_sync(FULLMASK, wl, 2);
+                    wl |= __shfl_xor_sync(FULLMASK, wl, 4);
+                    if ((lane & 7) == 0) bml[g >> 3] = wl;
+                }
+            }
+            w0 = nw0; w1 = nw1; w2 = nw2;
+        }
+    }
+    __syncthreads();      // the tables are dead: their memory takes the chunk
+    B2C_PHASE(1);
+
+    // ---------------------------------------------------------------- P2: stage the chunk (TMA bulk copy when aligned)
+    {
+#ifndef B2C_EMU
+        const bool bulk = ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) && ((n & 15) == 0) && n > 0;
+        if (bulk) {
+            if (tid == 0) {
+                mbar_init(&sh->mbar, 1);
+                mbar_fence_init();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy table accesses before the async write
+                mbar_expect_tx(&sh->mbar, n);
+                tma_load_1d(src, gsrc, n, &sh->mbar);
+            }
+            __syncthreads();
+            mbar_wait(&sh->mbar, 0);
+        } else
+#endif
+        {
+            uint32_t *sw = reinterpret_cast<uint32_t *>(src);
+            for (uint32_t i = tid; i < (n + 3) / 4; i += NT) { uint32_t v; LZ_WORD(v, i); sw[i] = v; }
+        }
+        // bytes behind the chunk are read (never used) by unaligned 8-byte loads: keep them defined
+        for (uint32_t i = ((n + 3) & ~3u) / 4 + tid; i < ((n + 3) & ~3u) / 4 + 8; i += NT) reinterpret_cast<uint32_t *>(src)[i] = 0;
+        __syncthreads();
+#ifndef B2C_EMU
+        if (bulk && tid == 0) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh->mbar))); }
+#endif
+    }
+#undef LZ_WORD
+#undef LZ_RAW
+    B2C_PHASE(2);
+
+    // ---------------------------------------------------------------- P3: walk, one thread per 128-byte range
+    // Every thread runs the greedy scan over its own range: next marked position, candidate = position - stored distance,
+    // extend forwards / backwards, emit, skip past the match.  Threads never communicate (bitmaps, distances and the
+    // chunk are read-only here), so the parse does not depend on scheduling.  A match may run past the end of the
+    // range; the merge step trims whatever a later thread found inside it.
+    // record k of thread t (k < SREC in shared memory, the rest in the per-CTA scratch): see lz_rec()
+    uint2 *recS = reinterpret_cast<uint2 *>(smem + L::SM_REC);
+    uint2 *recG = reinterpret_cast<uint2 *>(scratch + L::DIST_BYTES);
+#define REC(k, t) (*(((k) < C::SREC) ? &recS[(k) * NT + (t)] : &recG[((k) - C::SREC) * NT + (t)]))
+    uint32_t *keptEndA = reinterpret_cast<uint32_t *>(smem + L::SM_ARR);
+    uint32_t *lastOffA = keptEndA + NT;
+    uint8_t *cntA = reinterpret_cast<uint8_t *>(lastOffA + NT);
+    uint8_t *capA = cntA + NT;
+    const uint32_t nlanes = (n + LZ_RANGE - 1) / LZ_RANGE;
+    const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
+    uint32_t cnt = 0, lastE = 0;
+    bool capped = false;
+    {
+        const uint32_t b = tid * LZ_RANGE;
+        const uint32_t e = (b + LZ_RANGE < n) ? b + LZ_RANGE : n;
+        const uint32_t pend = (tid < nlanes) ? (e < npos ? e : npos) : 0u;
+        uint32_t p = b, nextEmit = b;
+        while (p < pend) {
+            // next set bit in [p, pend)
+            uint32_t wi = p >> 5;
+            uint32_t wv = bm[wi] & (0xffffffffu << (p & 31));
+            while (wv == 0 && (wi + 1) * 32 < pend) wv = bm[++wi];
+            if (wv == 0) break;
+            p = wi * 32 + (uint32_t)(__ffs((int)wv) - 1);
+            if (p >= pend) break;
+            if constexpr (C::LONG) {
+                // doubleFastEncoder's preference (enc_dfast.go:202-239): a long match wins; a short match yields to a
+                // long match that starts one byte later
+                const bool isL = (bml[p >> 5] >> (p & 31)) & 1;
+                if (!isL && p + 1 < pend && ((bml[(p + 1) >> 5] >> ((p + 1) & 31)) & 1)) p = p + 1;
+            }
+            const uint32_t d = cd[p];
+            if (d == 0 || d > p) { p++; continue; }
+            const uint32_t cand = p - d;
+            const uint32_t lim = (p + LZ_EXT_CAP < n) ? p + LZ_EXT_CAP : n;
+            // forward: 4 bytes per step from two unaligned streams (aligned word loads + funnel shifts); the tag that
+            // accepted the candidate is a hash, so the comparison starts at the first byte
+            uint32_t len = 0;
+            {
+                uint32_t ia = p >> 2, ib = cand >> 2;
+                const uint32_t sha = (p & 3) * 8, shb = (cand & 3) * 8;
+                uint32_t wa0 = srcw[ia], wb0 = srcw[ib];
+                while (p + len < lim) {
+                    const uint32_t wa1 = srcw[++ia], wb1 = srcw[++ib];
+                    const uint32_t x = __funnelshift_r(wa0, wa1, sha) ^ __funnelshift_r(wb0, wb1, shb);
+                    if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                    len += 4; wa0 = wa1; wb0 = wb1;
+                }
+            }
+            bool cp = false;
+            if (p + len >= lim) { len = lim - p; cp = lim < n; }
+            if (len < 4) { p++; continue; }
+            capped = cp;
+            uint32_t s = p, t = cand;
+            while (s > nextEmit && t > 0 && src[s - 1] == src[t - 1]) { s--; t--; len++; }
+            REC(cnt, tid) = lz_rec(s, len, d);
+            cnt++;
+            p = s + len;
+            nextEmit = p;
+        }
+        if (cnt) lastE = nextEmit;
+    }
+    B2C_PHASE(6);
+    cntA[tid] = (uint8_t)cnt;
+    capA[tid] = (uint8_t)((cnt != 0) && capped);
+    __syncthreads();
+    // long matches: warp 0 walks the capped records in order and finishes them cooperatively (128 bytes per step);
+    // a capped record that already lies inside an earlier finished one is skipped, so a chunk of zeros costs one pass
+    if (w == 0) {
+        uint32_t covered = 0;
+        for (uint32_t base = 0; base < nlanes; base += 32) {
+            const uint32_t t = base + lane;
+            unsigned m = __ballot_sync(FULLMASK, t < nlanes && capA[t]);
+            while (m) {
+                const uint32_t tt = base + (uint32_t)(__ffs((int)m) - 1);
+                m &= m - 1;
+                const uint32_t kk = (uint32_t)cntA[tt] - 1;
+                const uint2 r = REC(kk, tt);
+                const uint32_t s0 = lz_rec_s(r), l0 = lz_rec_len(r), d0 = lz_rec_d(r);
+                const uint32_t e0 = s0 + l0;
+                if (e0 > covered) {
+                    const uint32_t ext = warp_match_len(src, e0, e0 - d0, n);
+                    if (lane == 0) REC(kk, tt) = lz_rec(s0, l0 + ext, d0);
+                    covered = e0 + ext;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (capped && cnt) { const uint2 r = REC(cnt - 1, tid); lastE = lz_rec_s(r) + lz_rec_len(r); }
+    B2C_PHASE(3);
+
+    // ---------------------------------------------------------------- P4: merge (trim overlaps), global layout
+    uint32_t dummyTotal;
+    const uint32_t R = group_scan_excl_max(lastE, sh->ws, 0, NT, tid, &dummyTotal);   // everything before R is taken
+    B2C_PHASE(8);
+    uint32_t kept = 0, sumLen = 0, keptE = 0, lastOff = 0;
+    for (uint32_t j = 0; j < cnt; j++) {
+        const uint2 r = REC(j, tid);
+        const uint32_t s0 = lz_rec_s(r), e0 = s0 + lz_rec_len(r);
+        if (e0 <= R) continue;
+        const uint32_t s2 = s0 > R ? s0 : R, l2 = e0 - s2;
+        if (l2 < 4) continue;
+        REC(kept, tid) = lz_rec(s2, l2, lz_rec_d(r));
+        kept++; sumLen += l2; keptE = e0; lastOff = lz_rec_d(r);
+    }
+    B2C_PHASE(9);
+    keptEndA[tid] = keptE;
+    lastOffA[tid] = lastOff;
+    uint32_t seqEx, lenEx, nseq, sumAll, keyTotal;
+    __syncthreads();   // sh->ws is reused by the next scan
+    group_scan_excl_pair(kept, sumLen, ws2, NT, tid, &seqEx, &lenEx, &nseq, &sumAll);
+    (void)lenEx;
+    // nearest earlier thread that kept something: gives the end of the previous sequence and its offset
+    const uint32_t keyEx = group_scan_excl_max(kept ? tid + 1 : 0u, sh->ws, 0, NT, tid, &keyTotal);
+    B2C_PHASE(10);
+    const uint32_t nlit = n - sumAll;
+    const uint32_t prevE0 = keyEx ? keptEndA[keyEx - 1] : 0u;          // end of the sequence before this thread's first
+    const uint32_t pOff0 = keyEx ? lastOffA[keyEx - 1] : 0u;
+    const uint32_t lastEnd = keyTotal ? keptEndA[keyTotal - 1] : 0u;  // end of the last sequence of the chunk
+    (void)lastEnd;
+
+    // blockEnc.encode early decisions (blockenc.go:481-503): no sequences => literals-only (raw) block; then the
+    // single-sequence RLE test; then `saved < 16` => raw
+    uint32_t kind = 0;
+    const int saved = (int)n - (int)nlit - (int)(n >> 6);
+    if (nseq == 0) kind = 1;
+    else if (nseq != 1 && saved < 16) kind = 1;
+    if (nseq > mseq) kind = 1;      // cannot happen (mseq >= BLOCK / 4); keeps the arrays safe
+
+    // ---------------------------------------------------------------- P5: sequences, codes, literal mask
+    uint32_t *mask = bm;     // one bit per position: 1 = literal.  Thread t owns the four words of its own range.
+    uint32_t myLit = 0;
+    if (kind == 0 || (P.dbg_hdr && nseq <= mseq)) {      // (the parity tests also want the sequences of blocks stored raw)
+        const uint32_t b = tid * LZ_RANGE;
+        const uint32_t e = (b + LZ_RANGE < n) ? b + LZ_RANGE : n;
+        uint32_t m4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t lo = b + 32 * k;
+            m4[k] = (lo >= n) ? 0u : (n - lo >= 32 ? 0xffffffffu : ((1u << (n - lo)) - 1));
+        }
+        // clear [x, y) (absolute positions, clipped to this thread's range) in m4
+#define LZ_CLEAR(x, y)                                                                                   \
+    do {                                                                                                 \
+        const uint32_t x_ = (x) > b ? (x) - b : 0u, y_ = ((y) < e ? (y) : e);                             \
+        if (y_ > b && x_ < y_ - b) {                                                                      \
+            const uint32_t yy_ = y_ - b;                                                                  \
+            _Pragma("unroll") for (int k_ = 0; k_ < 4; k_++) {                                            \
+                const uint32_t lo_ = 32u * k_;                                                            \
+                const uint32_t a_ = x_ > lo_ ? x_ - lo_ : 0u, c_ = yy_ > lo_ ? yy_ - lo_ : 0u;            \
+                if (a_ < 32 && c_ > a_) {                                                                 \
+                    const uint32_t hi_ = c_ >= 32 ? 0xffffffffu : ((1u << c_) - 1);                       \
+                    m4[k_] &= ~(hi_ & (0xffffffffu << a_));                                               \
+                }                                                                                         \
+            }                                                                                             \
+        }                                                                                                 \
+    } while (0)
+        // the part of this range covered by the last kept match of the earlier threads
+        LZ_CLEAR(b, prevE0);
+        uint32_t prevE = prevE0, pOff = pOff0, gi = seqEx;
+        for (uint32_t j = 0; j < kept; j++) {
+            const uint2 r = REC(j, tid);
+            const uint32_t s0 = lz_rec_s(r), l0 = lz_rec_len(r), d0 = lz_rec_d(r);
+            const uint32_t ll = s0 - prevE;
+            LZ_CLEAR(s0, s0 + l0);
+            // repeat code 1 (= offset of the previous sequence, valid with litLen > 0; seqdec.go:463-500)
+            const bool isrep = (gi > 0) && (d0 == pOff) && (ll > 0);
+            const uint32_t ofv = isrep ? 1u : d0 + 3;
+            wlen.put(gi, ll, l0 - 3); wof[gi] = ofv;
+            wcodes[TBL_LL * mseq + gi] = (uint8_t)seq_ll_code(ll);
+            wcodes[TBL_OF * mseq + gi] = (uint8_t)highbit32(ofv);
+            wcodes[TBL_ML * mseq + gi] = (uint8_t)seq_ml_code(l0 - 3);
+            prevE = s0 + l0; pOff = d0; gi++;
+        }
+#undef LZ_CLEAR
+#pragma unroll
+        for (int k = 0; k < 4; k++) { mask[4 * tid + k] = m4[k]; myLit += (uint32_t)__popc(m4[k]); }
+    }
+    B2C_PHASE(11);
+    if (tid == 0) { sh->kind = kind; sh->rleLen = 0; }
+    __syncthreads();
+    // single-sequence RLE block test (blockenc.go:484-493); nlit <= 1
+    if (kind == 0 && nseq == 1 && nlit <= 1 && tid == 0) {
+        const uint32_t ll0 = wlen.peek_ll(0), of0 = wof[0];
+        if (ll0 == nlit && of0 - 3 == 1) { sh->kind = 2; sh->rleLen = wlen.peek_ml(0) + 3 + ll0; }
+        else if (saved < 16) sh->kind = 1;
+    } else if (kind == 0 && nseq == 1 && saved < 16 && tid == 0) sh->kind = 1;
+    uint32_t litEx, litTotal;
+    litEx = group_scan_excl(myLit, sh->ws, 0, NT, tid, &litTotal);   // literal index of this thread's first literal
+    __syncthreads();
+    kind = sh->kind;
+    B2C_PHASE(4);
+
+    // ---------------------------------------------------------------- P6: literals by stream compaction
+    // Warp w compacts the 4 KiB its own lanes walked: per step the 128 bytes of one range (lane j: word j), the four mask
+    // bits of the word select the literal bytes, a warp scan gives their places, byte stores go out in order (a step
+    // writes at most 128 consecutive bytes).  The literal index of a byte is its rank under the mask, which is exactly
+    // the order blockEnc.literals has (every sequence's literals precede its match).
+    if (kind == 0) {
+        uint8_t *glit = wk_lit(P, chunk);
+        for (uint32_t i = 0; i < 32; i++) {
+            const uint32_t t = w * 32 + i;
+            if (t * LZ_RANGE >= n) break;
+            const uint32_t base = __shfl_sync(FULLMASK, litEx, (int)i);
+            const uint32_t mw = mask[4 * t + (lane >> 3)];
+            const uint32_t nib = (mw >> (4 * (lane & 7))) & 15u;
+            const uint32_t c = (uint32_t)__popc(nib);
+            const uint32_t incl = warp_scan_incl(c);
+            if (__shfl_sync(FULLMASK, incl, 31) == 0) continue;
+            const uint32_t v = srcw[32 * t + lane];
+            uint32_t packed = 0, k = 0;
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++)
+                if ((nib >> bb) & 1) { packed |= ((v >> (8 * bb)) & 0xffu) << (8 * k); k++; }
+            uint8_t *o = glit + base + (incl - c);
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++)
+                if ((uint32_t)bb < c) o[bb] = (uint8_t)(packed >> (8 * bb));
+        }
+    }
+#undef REC
+    if (tid == 0) { W->n = n; W->nseq = nseq; W->nlit = nlit; W->kind = kind; W->rleLen = sh->rleLen; }
+    __syncthreads();
+    B2C_PHASE(5);
+}
+
+// ------------------------------------------------------------------------------------------------ histograms
+// One 128-thread CTA per chunk: literal histogram (one private u8 counter per (symbol, lane) and warp -- no atomics, no
+// races; literals are counted in slices small enough that a counter cannot wrap) and the three sequence-code
+// histograms (ballot counts, lane l owns the codes whose low 5 bits equal l) with their highest used code.  Input:
+// the literals and codes the parse kernel left in the work pool.  (Round 1 did this inside the parse kernel, where it
+// pinned 64 KiB of shared memory; as a separate kernel it runs at seven CTAs per SM.)
+constexpr int HIST_NT = 128;
+constexpr int HIST_WARPS = HIST_NT / 32;
+constexpr uint32_t HIST_SLICE = 255u * HIST_NT;    // literals per slice: at most 255 per lane
+constexpr uint32_t HIST_SMEM_BYTES = HIST_WARPS * 256 * 32;
+B2C_DEV void zstd_hist_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    ChunkWork *W = P.work + chunk;
+    const uint32_t nlit = W->nlit, nseq = W->nseq;
+    const uint8_t *lit = wk_lit(P, chunk);
+    if (P.dbg_hdr && W->kind != 3) {
+        const WkLens wlen = wk_lens(P, chunk);
+        const uint32_t *wof = wk_of(P, chunk);
+        for (uint32_t i = tid; i < nseq && i < P.dbg_seq_cap && i < P.maxseq; i += HIST_NT) {
+            uint32_t *d = P.dbg_seqs + ((uint64_t)chunk * P.dbg_seq_cap + i) * 3;
+            d[0] = wlen.get_ll(i); d[1] = wlen.get_ml(i); d[2] = wof[i];
+        }
+        if (W->kind == 0)
+            for (uint32_t i = tid; i < nlit; i += HIST_NT) P.dbg_lits[(uint64_t)chunk * P.blockmax + i] = lit[i];
+    }
+    if (W->kind != 0) return;
+    uint32_t acc0 = 0, acc1 = 0;                       // symbols tid and tid + 128
+    uint8_t *hcol = smem + w * 256 * 32 + lane;
+    for (uint32_t s0 = 0; s0 < nlit; s0 += HIST_SLICE) {
+        const uint32_t s1 = (s0 + HIST_SLICE < nlit) ? s0 + HIST_SLICE : nlit;
+        for (uint32_t i = tid; i < HIST_SMEM_BYTES / 4; i += HIST_NT) reinterpret_cast<uint32_t *>(smem)[i] = 0;
+        __syncthreads();
+        {
+            const uint32_t w0 = s0 / 4, nl4 = (s1 + 3) / 4;       // HIST_SLICE is a multiple of 4
+            const uint32_t *lit32 = reinterpret_cast<const uint32_t *>(lit);
+            uint32_t i = w0 + tid;
+            uint32_t v = (i < nl4) ? B2C_LDG(lit32 + i) : 0;
+            while (i < nl4) {
+                const uint32_t inext = i + HIST_NT;
+                const uint32_t vnext = (inext < nl4) ? B2C_LDG(lit32 + inext) : 0;   // next word requested before this one is used
+                const uint32_t nv = (4 * i + 4 <= s1) ? 4u : s1 - 4 * i;
+                const uint32_t a0 = v & 0xff, a1 = (v >> 8) & 0xff, a2 = (v >> 16) & 0xff, a3 = v >> 24;
+                uint32_t i0 = 1, i1 = nv > 1, i2 = nv > 2, i3 = nv > 3;
+                if (a1 == a0) { i0 += i1; i1 = 0; }
+                if (a2 == a0) { i0 += i2; i2 = 0; } else if (a2 == a1) { i1 += i2; i2 = 0; }
+                if (a3 == a0) { i0 += i3; i3 = 0; } else if (a3 == a1) { i1 += i3; i3 = 0; } else if (a3 == a2) { i2 += i3; i3 = 0; }
+                const uint32_t c0 = hcol[a0 * 32], c1 = hcol[a1 * 32], c2 = hcol[a2 * 32], c3 = hcol[a3 * 32];
+                hcol[a0 * 32] = (uint8_t)(c0 + i0);
+                if (i1) hcol[a1 * 32] = (uint8_t)(c1 + i1);
+                if (i2) hcol[a2 * 32] = (uint8_t)(c2 + i2);
+                if (i3) hcol[a3 * 32] = (uint8_t)(c3 + i3);
+                i = inext; v = vnext;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint32_t sym = tid + 128 * half;
+            uint32_t c = 0;
+#pragma unroll
+            for (int k = 0; k < HIST_WARPS; k++) {
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(smem + k * 256 * 32 + sym * 32);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t v = row[(j + (tid >> 2)) & 7];     // rotated: the 32 threads of a warp spread over the banks
+                    c += (v & 0xff) + ((v >> 8) & 0xff) + ((v >> 16) & 0xff) + (v >> 24);
+                }
+            }
+            if (half == 0) acc0 += c; else acc1 += c;
+        }
+        __syncthreads();
+    }
+    W->litHist[tid] = acc0;
+    W->litHist[tid + 128] = acc1;
+    // sequence-code counts
+    uint32_t seqCnt[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    const uint8_t *codes = wk_codes(P, chunk, 0);
+    const uint32_t mseq = P.maxseq;
+    for (uint32_t base = w * 32; base < nseq; base += 4 * HIST_NT) {
+        uint32_t cv3[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t i = base + u * HIST_NT + lane;
+#pragma unroll
+            for (int c = 0; c < 3; c++) cv3[u][c] = (i < nseq) ? (uint32_t)B2C_LDG(codes + c * mseq + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const bool valid = base + u * HIST_NT + lane < nseq;
+            if (base + u * HIST_NT < nseq) {      // warp-uniform
+#pragma unroll
+                for (int c = 0; c < 3; c++) warp_hist_acc<6>(cv3[u][c], valid, seqCnt[c], lane);
+            }
+        }
+    }
+    uint32_t *shist = reinterpret_cast<uint32_t *>(smem);      // [HIST_WARPS][192] + 6 words
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        shist[w * 192 + c * 64 + lane] = seqCnt[c][0];
+        shist[w * 192 + c * 64 + 32 + lane] = seqCnt[c][1];
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < 192; i += HIST_NT) {
+        uint32_t c = 0;
+        for (int k = 0; k < HIST_WARPS; k++) c += shist[k * 192 + i];
+        W->seqHist[i / 64][i % 64] = c;
+        // highest used code of each table: index groups of 32 are warp-aligned
+        const unsigned nz = __ballot_sync(FULLMASK, c != 0);
+        if ((i & 31) == 0) shist[HIST_WARPS * 192 + (i >> 5)] = nz;
+    }
+    __syncthreads();
+    if (tid < 3) {
+        const uint32_t lo = shist[HIST_WARPS * 192 + 2 * tid], hi = shist[HIST_WARPS * 192 + 2 * tid + 1];
+        W->maxSym[tid] = hi ? 32 + (31 - (uint32_t)__clz((int)hi)) : (lo ? 31 - (uint32_t)__clz((int)lo) : 0u);
+    }
+    __syncthreads();
+}
+
+#ifndef B2C_EMU
+extern "C" __global__ void __launch_bounds__(LzCfg<1>::NT, LzCfg<1>::MIN_CTAS) b2c_lz_parse1_kernel(ZstdEncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<1>::SCRATCH_BYTES;
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<1>(smem, P, c, scratch);
+}
+extern "C" __global__ void __launch_bounds__(LzCfg<2>::NT, LzCfg<2>::MIN_CTAS) b2c_lz_parse2_kernel(ZstdEncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<2>::SCRATCH_BYTES;
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<2>(smem, P, c, scratch);
+}
+extern "C" __global__ void __launch_bounds__(HIST_NT) b2c_zstd_hist_kernel(ZstdEncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_hist_chunk(smem, P, c);
+}
+#endif
+
+}  // namespace b2c

@@ -79,7 +79,9 @@ constexpr uint32_t ENC_SCRATCH_BYTES = (ENC_MAXREC - ENC_SREC) * ENC_NT * 8;  //
 
 enum { ENC_FLAG_CRC = 1, ENC_FLAG_FRAME = 2 };
 
-// Per-chunk work record handed from kernel to kernel (global memory, L2 resident for the active chunks).
+// Per-chunk work record handed from kernel to kernel (global memory, L2 resident for the active chunks): a small
+// header (this struct) plus one slab of the work pool holding the arrays whose size depends on the block size
+// (literals, per-sequence values, codes, state bits; layout below, sized by the host per level).
 struct alignas(16) ChunkWork {
     uint32_t n, nseq, nlit, kind;          // kind: 0 compressed candidate, 1 raw block, 2 RLE block, 3 too big
     uint32_t rleLen, hufStatus, hufTableLog, tableDescLen;
@@ -95,12 +97,6 @@ struct alignas(16) ChunkWork {
     uint8_t tableDesc[320];
     uint8_t ncount[3][96];
     FseCTable tbl[3];                      // the table each chain uses (new, predefined copy, or RLE)
-    alignas(16) uint8_t lit[ENC_MAX_CHUNK + 64];
-    uint16_t seqLL[ENC_MAXSEQ];
-    uint16_t seqML[ENC_MAXSEQ];
-    uint32_t seqOF[ENC_MAXSEQ];
-    alignas(16) uint8_t codes[3][ENC_MAXSEQ];
-    alignas(16) uint16_t stb[3][ENC_MAXSEQ];
 };
 
 struct ZstdEncParams {
@@ -114,8 +110,15 @@ struct ZstdEncParams {
     int64_t *out_sizes;           // bytes written per chunk, negative = error
     uint32_t nchunks;
     uint32_t flags;
-    uint8_t *scratch;             // gridDim.x(K1) * ENC_SCRATCH_BYTES
+    uint8_t *scratch;             // gridDim.x(K1) * ENC_SCRATCH_BYTES (round-1 parse) / per-CTA parse scratch (lz parse)
     ChunkWork *work;              // [nchunks]
+    uint8_t *pool;                // [nchunks] slabs of pool_stride bytes: lit | seqOF | seqLL | seqML | codes[3] | stb[3]
+    uint64_t pool_stride;
+    uint32_t maxseq;              // capacity of the per-sequence arrays (multiple of 16)
+    uint32_t blockmax;            // largest block this launch accepts (65536 or 131072)
+    uint32_t big;                 // 1: litLen / matchLen arrays are u32 (blocks > 64 KiB), 0: u16
+    uint32_t level;               // 1 fastest, 2 default
+    uint32_t chunk0;              // sub-batch offset: kernels work on chunks [chunk0, chunk0 + nchunks) of the call
     // optional debug dump (tests): per chunk {nseq, nlit, kind, litMode} + seq triples + literals
     uint32_t *dbg_hdr;            // [nchunks][4]
     uint32_t *dbg_seqs;           // [nchunks][dbg_seq_cap][3]
@@ -137,6 +140,48 @@ struct ZstdEncParams {
 #endif
 
 B2C_DEV uint32_t chunk_size(const ZstdEncParams &P, uint32_t c) { return P.src_sizes ? P.src_sizes[c] : P.src_size_all; }
+
+// ---- work pool layout (one slab per chunk) ----
+B2C_DEV uint32_t wk_off_lit() { return 0; }
+B2C_DEV uint32_t wk_off_of(const ZstdEncParams &P) { return (P.blockmax + 64 + 15) & ~15u; }
+B2C_DEV uint32_t wk_off_ll(const ZstdEncParams &P) { return wk_off_of(P) + 4 * P.maxseq; }
+B2C_DEV uint32_t wk_off_ml(const ZstdEncParams &P) { return wk_off_ll(P) + (P.big ? 4u : 2u) * P.maxseq; }
+B2C_DEV uint32_t wk_off_codes(const ZstdEncParams &P) { return wk_off_ml(P) + (P.big ? 4u : 2u) * P.maxseq; }
+B2C_DEV uint32_t wk_off_stb(const ZstdEncParams &P) { return wk_off_codes(P) + 3 * P.maxseq; }
+B2C_DEV uint8_t *wk_slab(const ZstdEncParams &P, uint32_t chunk) { return P.pool + (uint64_t)chunk * P.pool_stride; }
+B2C_DEV uint8_t *wk_lit(const ZstdEncParams &P, uint32_t chunk) { return wk_slab(P, chunk); }
+B2C_DEV uint32_t *wk_of(const ZstdEncParams &P, uint32_t chunk) { return reinterpret_cast<uint32_t *>(wk_slab(P, chunk) + wk_off_of(P)); }
+B2C_DEV uint8_t *wk_codes(const ZstdEncParams &P, uint32_t chunk, int c) { return wk_slab(P, chunk) + wk_off_codes(P) + (uint32_t)c * P.maxseq; }
+B2C_DEV uint16_t *wk_stb(const ZstdEncParams &P, uint32_t chunk, int c) {
+    return reinterpret_cast<uint16_t *>(wk_slab(P, chunk) + wk_off_stb(P)) + (uint32_t)c * P.maxseq;
+}
+// host side of the layout: slab bytes for a block size (maxseq = blockmax / 4 + 64: a match is at least 4 bytes)
+static inline uint32_t wk_maxseq(uint32_t blockmax) { return blockmax / 4 + 64; }
+static inline uint64_t wk_pool_stride(uint32_t blockmax) {
+    const uint64_t ms = wk_maxseq(blockmax), lenb = blockmax > 65536 ? 4 : 2;
+    return (((uint64_t)blockmax + 64 + 15) & ~15ull) + 4 * ms + 2 * lenb * ms + 3 * ms + 6 * ms;
+}
+// litLen / matchLen-3 of sequence i (u16 arrays for blocks <= 64 KiB, u32 above)
+struct WkLens {
+    uint8_t *ll, *ml;
+    uint32_t big;
+    B2C_DEV void put(uint32_t i, uint32_t vll, uint32_t vml) const {
+        if (big) { reinterpret_cast<uint32_t *>(ll)[i] = vll; reinterpret_cast<uint32_t *>(ml)[i] = vml; }
+        else { reinterpret_cast<uint16_t *>(ll)[i] = (uint16_t)vll; reinterpret_cast<uint16_t *>(ml)[i] = (uint16_t)vml; }
+    }
+    // plain loads: for values written earlier in the SAME kernel (the read-only path is not coherent with them)
+    B2C_DEV uint32_t peek_ll(uint32_t i) const { return big ? reinterpret_cast<const uint32_t *>(ll)[i] : (uint32_t)reinterpret_cast<const uint16_t *>(ll)[i]; }
+    B2C_DEV uint32_t peek_ml(uint32_t i) const { return big ? reinterpret_cast<const uint32_t *>(ml)[i] : (uint32_t)reinterpret_cast<const uint16_t *>(ml)[i]; }
+    B2C_DEV uint32_t get_ll(uint32_t i) const {
+        return big ? B2C_LDG(reinterpret_cast<const uint32_t *>(ll) + i) : (uint32_t)B2C_LDG(reinterpret_cast<const uint16_t *>(ll) + i);
+    }
+    B2C_DEV uint32_t get_ml(uint32_t i) const {
+        return big ? B2C_LDG(reinterpret_cast<const uint32_t *>(ml) + i) : (uint32_t)B2C_LDG(reinterpret_cast<const uint16_t *>(ml) + i);
+    }
+};
+B2C_DEV WkLens wk_lens(const ZstdEncParams &P, uint32_t chunk) {
+    WkLens w; w.ll = wk_slab(P, chunk) + wk_off_ll(P); w.ml = wk_slab(P, chunk) + wk_off_ml(P); w.big = P.big; return w;
+}
 
 // 6-byte multiplicative hash: two 32-bit multiply-adds (the reference's hashLen(u, bits, 6), zstd/hash.go:27,
 // is a 64-bit multiply = ~8 integer instructions per position on the SM; table contents are an
@@ -271,6 +316,10 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     ParseShared *sh = reinterpret_cast<ParseShared *>(smem + ENC_SMEM_SH);
     uint8_t *lit = smem + ENC_SMEM_E;                                      // after the parse
     ChunkWork *W = (MODE == LZ_MODE_ZSTD) ? P.work + chunk : nullptr;
+    const WkLens wlen = (MODE == LZ_MODE_ZSTD) ? wk_lens(P, chunk) : WkLens{nullptr, nullptr, 0};
+    uint32_t *const wof = (MODE == LZ_MODE_ZSTD) ? wk_of(P, chunk) : nullptr;
+    uint8_t *const wcodes = (MODE == LZ_MODE_ZSTD) ? wk_codes(P, chunk, 0) : nullptr;
+    const uint32_t mseq = P.maxseq;
 
     const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
     const uint32_t n = chunk_size(P, chunk);
@@ -680,12 +729,11 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         return;
     }
     uint32_t kind = 0;
-    // blockEnc.encode early decisions (blockenc.go:481-503)
+    // blockEnc.encode early decisions (blockenc.go:481-503): no sequences => literals-only (raw) block; then the
+    // single-sequence RLE test (needs the sequence, so it runs after the gather); then `saved < 16` => raw
+    const int saved = (int)n - (int)nlit - (int)(n >> 6);
     if (nseq == 0) kind = 1;  // encodeLits(..., rawAllLits=true) => raw block
-    else {
-        int saved = (int)n - (int)nlit - (int)(n >> 6);
-        if (saved < 16) kind = 1;
-    }
+    else if (nseq != 1 && saved < 16) kind = 1;
 
     // ---------------------------------------------------------------- P4: gather literals, sequences, codes
     uint32_t seqCnt[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // this warp's code counts: lane l holds codes l and 32 + l
@@ -707,10 +755,10 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             // repeat code 1 (= offset of the previous sequence, valid with litLen > 0; seqdec.go:463-500)
             const bool isrep = (gi > 0) && (d0 == pOff) && (ll > 0);
             const uint32_t ofv = isrep ? 1u : d0 + 3;
-            W->seqLL[gi] = (uint16_t)ll; W->seqML[gi] = (uint16_t)(l0 - 3); W->seqOF[gi] = ofv;
-            W->codes[TBL_LL][gi] = (uint8_t)seq_ll_code(ll);
-            W->codes[TBL_OF][gi] = (uint8_t)highbit32(ofv);
-            W->codes[TBL_ML][gi] = (uint8_t)seq_ml_code(l0 - 3);
+            wlen.put(gi, ll, l0 - 3); wof[gi] = ofv;
+            wcodes[TBL_LL * mseq + gi] = (uint8_t)seq_ll_code(ll);
+            wcodes[TBL_OF * mseq + gi] = (uint8_t)highbit32(ofv);
+            wcodes[TBL_ML * mseq + gi] = (uint8_t)seq_ml_code(l0 - 3);
             prevE = s0 + l0; mrun += l0; pOff = d0; gi++;
         }
         B2C_PHASE(11);
@@ -721,9 +769,10 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
     __syncthreads();
     // single-sequence RLE block test (blockenc.go:484-493); nlit <= 1
     if (kind == 0 && nseq == 1 && nlit <= 1 && tid == 0) {
-        uint32_t ll0 = W->seqLL[0], of0 = W->seqOF[0];
-        if (ll0 == nlit && of0 - 3 == 1) { sh->kind = 2; sh->rleLen = (uint32_t)W->seqML[0] + 3 + ll0; }
+        uint32_t ll0 = wlen.peek_ll(0), of0 = wof[0];
+        if (ll0 == nlit && of0 - 3 == 1) { sh->kind = 2; sh->rleLen = wlen.peek_ml(0) + 3 + ll0; }
     }
+    if (kind == 0 && nseq == 1 && saved < 16 && tid == 0 && sh->kind == 0) sh->kind = 1;
     __syncthreads();
     kind = sh->kind;
     B2C_PHASE(4);
@@ -778,7 +827,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
                 for (int u = 0; u < 4; u++) {
                     const uint32_t i = base + u * STEP + lane;
 #pragma unroll
-                    for (int c = 0; c < 3; c++) cv3[u][c] = (i < nseq) ? (uint32_t)W->codes[c][i] : 0u;
+                    for (int c = 0; c < 3; c++) cv3[u][c] = (i < nseq) ? (uint32_t)wcodes[c * mseq + i] : 0u;
                 }
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -791,7 +840,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
             }
             // literals to the work record (coalesced 16-byte stores)
             const uint4 *s4 = reinterpret_cast<const uint4 *>(lit);
-            uint4 *d4 = reinterpret_cast<uint4 *>(W->lit);
+            uint4 *d4 = reinterpret_cast<uint4 *>(wk_lit(P, chunk));
             const uint32_t n16 = (nlit + 15) / 16;
             for (uint32_t i = tid - LH_WARPS * 32; i < n16; i += ENC_NT - LH_WARPS * 32) d4[i] = s4[i];
         }
@@ -838,7 +887,7 @@ B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t ch
         if (P.dbg_hdr) {
             for (uint32_t i = tid; i < nseq && i < P.dbg_seq_cap; i += ENC_NT) {
                 uint32_t *d = P.dbg_seqs + ((uint64_t)chunk * P.dbg_seq_cap + i) * 3;
-                d[0] = W->seqLL[i]; d[1] = W->seqML[i]; d[2] = W->seqOF[i];
+                d[0] = wlen.peek_ll(i); d[1] = wlen.peek_ml(i); d[2] = wof[i];
             }
             for (uint32_t i = tid; i < nlit; i += ENC_NT) P.dbg_lits[(uint64_t)chunk * 65536 + i] = lit[i];
         }
@@ -883,7 +932,7 @@ B2C_DEV void zstd_tables_chunk(TablesShared *ts, const ZstdEncParams &P, uint32_
         for (uint32_t s = lane; s < 64; s += 32) sw->hist[which][s] = W->seqHist[which][s];
         if (lane == 0) sw->maxSym[which] = W->maxSym[which];
         __syncwarp();
-        seq_build_table(sw, which, nseq, W->codes[which][0], lane);
+        seq_build_table(sw, which, nseq, wk_codes(P, chunk, which)[0], lane);
         __syncwarp();
         // publish the table this chain will use
         const FseCTable *t = seq_table(sw, which);
@@ -950,8 +999,8 @@ B2C_DEV void zstd_chains_block(uint32_t *smem32, const ZstdEncParams &P, uint32_
         }
     }
     __syncwarp();
-    const uint8_t *codes = W->codes[which];
-    uint16_t *stb = W->stb[which];
+    const uint8_t *codes = wk_codes(P, live ? chunk : 0, (int)which);
+    uint16_t *stb = wk_stb(P, live ? chunk : 0, (int)which);
     uint32_t state = 0;
     const bool run = live && !useRLE && nseq >= 1;
     if (run) {
@@ -1018,14 +1067,20 @@ struct PackShared {
 #define PACK_LLB(c) seq_ll_bits(c)
 #define PACK_MLB(c) seq_ml_bits(c)
 #endif
-constexpr uint32_t PACK_STAGE_BYTES = ENC_MAX_CHUNK + 128;
 #ifndef PACK_LIT_SMEM_BYTES
 #define PACK_LIT_SMEM_BYTES (40 * 1024)
 #endif
-constexpr uint32_t PACK_LIT_SMEM = PACK_LIT_SMEM_BYTES;   // literals are staged in shared memory when they fit
-constexpr uint32_t PACK_SMEM_SH = PACK_STAGE_BYTES + PACK_LIT_SMEM;
-constexpr uint32_t PACK_SMEM_BYTES = PACK_SMEM_SH + ((sizeof(PackShared) + 15) / 16) * 16;
-static_assert(PACK_LIT_SMEM != 40 * 1024 || 2 * (PACK_SMEM_BYTES + 1024) <= 228 * 1024, "two K4 CTAs must fit one SM");
+// K4 shared-memory plan per block size: the staging buffer holds the whole output, literals are staged when they fit.
+// 64 KiB blocks: 64 K + 40 K -> two CTAs per SM; 128 KiB blocks (level 2): 128 K + 64 K -> one CTA per SM.
+template <uint32_t BLOCK> struct PackCfg {
+    static constexpr uint32_t STAGE_BYTES = BLOCK + 128;
+    static constexpr uint32_t LIT_SMEM = (BLOCK <= 65536) ? (uint32_t)PACK_LIT_SMEM_BYTES : 64u * 1024u;
+    static constexpr uint32_t SMEM_SH = STAGE_BYTES + LIT_SMEM;
+    static constexpr uint32_t SMEM_BYTES = SMEM_SH + ((sizeof(PackShared) + 15) / 16) * 16;
+};
+constexpr uint32_t PACK_SMEM_BYTES = PackCfg<65536>::SMEM_BYTES;
+static_assert(PACK_LIT_SMEM_BYTES != 40 * 1024 || 2 * (PACK_SMEM_BYTES + 1024) <= 228 * 1024, "two K4 CTAs must fit one SM");
+static_assert(PackCfg<131072>::SMEM_BYTES <= 227 * 1024, "the 128 KiB K4 CTA must fit one SM");
 
 B2C_DEV uint32_t frame_header_bytes(uint32_t n) {
     if (n == 0) return 6;
@@ -1053,10 +1108,13 @@ B2C_DEV uint32_t write_frame_header(uint8_t *o8, uint32_t n, bool crc) {
     return o;
 }
 
+template <uint32_t BLOCK>
 B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk) {
+    constexpr uint32_t PACK_STAGE_BYTES = PackCfg<BLOCK>::STAGE_BYTES;
+    constexpr uint32_t PACK_LIT_SMEM = PackCfg<BLOCK>::LIT_SMEM;
     const unsigned tid = threadIdx.x;
     uint8_t *stage = smem;
-    PackShared *ps = reinterpret_cast<PackShared *>(smem + PACK_SMEM_SH);
+    PackShared *ps = reinterpret_cast<PackShared *>(smem + PackCfg<BLOCK>::SMEM_SH);
     ChunkWork *W = P.work + chunk;
     const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
     uint8_t *gdst = P.dst_base + (uint64_t)chunk * P.dst_stride;
@@ -1069,10 +1127,10 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
     const uint32_t fh = frame ? frame_header_bytes(n) : 0;
 
     if (kind == 0) {
-        const uint8_t *lit = W->lit;
+        const uint8_t *lit = wk_lit(P, chunk);
         if (nlit <= PACK_LIT_SMEM) {
             uint8_t *ls = smem + PACK_STAGE_BYTES;
-            const uint4 *g4 = reinterpret_cast<const uint4 *>(W->lit);
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(lit);
             uint4 *s4 = reinterpret_cast<uint4 *>(ls);
             for (uint32_t i = tid; i < (nlit + 15) / 16; i += PACK_NT) s4[i] = g4[i];
             lit = ls;
@@ -1127,8 +1185,10 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         const uint32_t bsOff = tblOff + W->ncountLen[0] + W->ncountLen[1] + W->ncountLen[2];
 
         // ------------------------------------------------------------ sequence bitstream sizes
-        const uint8_t *cLL = W->codes[TBL_LL], *cOF = W->codes[TBL_OF], *cML = W->codes[TBL_ML];
-        const uint16_t *stbLL = W->stb[TBL_LL], *stbOF = W->stb[TBL_OF], *stbML = W->stb[TBL_ML];
+        const uint8_t *cLL = wk_codes(P, chunk, TBL_LL), *cOF = wk_codes(P, chunk, TBL_OF), *cML = wk_codes(P, chunk, TBL_ML);
+        const uint16_t *stbLL = wk_stb(P, chunk, TBL_LL), *stbOF = wk_stb(P, chunk, TBL_OF), *stbML = wk_stb(P, chunk, TBL_ML);
+        const WkLens wlen = wk_lens(P, chunk);
+        const uint32_t *wof = wk_of(P, chunk);
         const uint32_t per = (nseq + PACK_NT - 1) / PACK_NT;
         uint32_t tA = tid * per, tB = tA + per;
         if (tA > nseq) tA = nseq;
@@ -1169,7 +1229,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
                 for (uint32_t t = tA; t < tB; t++) {
                     uint32_t idx = nseq - 1 - t;
                     uint32_t cl = B2C_LDG(cLL + idx), co = B2C_LDG(cOF + idx), cm = B2C_LDG(cML + idx);
-                    const uint32_t vLL = B2C_LDG(W->seqLL + idx), vML = B2C_LDG(W->seqML + idx), vOF = B2C_LDG(W->seqOF + idx);
+                    const uint32_t vLL = wlen.get_ll(idx), vML = wlen.get_ml(idx), vOF = B2C_LDG(wof + idx);
 #if PACK_SEQ_COMBINE
                     if (t) {
                         // three state flushes (<= 9 bits each) in one append: OF, ML, LL (blockenc.go:757-790)
@@ -1299,7 +1359,7 @@ B2C_DEV void zstd_xxh_quad(const ZstdEncParams &P, uint32_t chunk, unsigned q /*
     const uint32_t n = live ? chunk_size(P, chunk) : 0;
     const bool aligned = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
     uint64_t v = (q == 0) ? P1 + P2 : (q == 1) ? P2 : (q == 2) ? 0ull : (0ull - P1);
-    uint32_t stripes = (n <= ENC_MAX_CHUNK) ? n / 32 : 0;
+    uint32_t stripes = (n <= P.blockmax) ? n / 32 : 0;
     uint32_t i = 0;
     if (aligned) {
         // sixteen stripes per batch: the loads are independent of the accumulator, so they are all in flight while
@@ -1327,7 +1387,7 @@ B2C_DEV void zstd_xxh_quad(const ZstdEncParams &P, uint32_t chunk, unsigned q /*
     }
     uint64_t v1 = __shfl_sync(FULLMASK, v, quadBaseLane), v2 = __shfl_sync(FULLMASK, v, quadBaseLane + 1),
              v3 = __shfl_sync(FULLMASK, v, quadBaseLane + 2), v4 = __shfl_sync(FULLMASK, v, quadBaseLane + 3);
-    if (q != 0 || !live || n > ENC_MAX_CHUNK) return;
+    if (q != 0 || !live || n > P.blockmax) return;
     uint64_t h;
     uint32_t p = stripes * 32;
     if (n >= 32) {
@@ -1395,7 +1455,11 @@ extern "C" __global__ void __launch_bounds__(CHAIN_NT) b2c_zstd_chains_kernel(Zs
 }
 extern "C" __global__ void __launch_bounds__(PACK_NT, PACK_MIN_CTAS) b2c_zstd_pack_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    zstd_pack_chunk(smem, P, blockIdx.x);
+    zstd_pack_chunk<65536>(smem, P, blockIdx.x);
+}
+extern "C" __global__ void __launch_bounds__(PACK_NT, 1) b2c_zstd_pack128_kernel(ZstdEncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    zstd_pack_chunk<131072>(smem, P, blockIdx.x);
 }
 extern "C" __global__ void __launch_bounds__(128) b2c_zstd_xxh_kernel(ZstdEncParams P) {
     unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;

@@ -19,6 +19,7 @@ SpeedFastest = 1
 SpeedDefault = 2
 CHUNK = 1 << 16           # SpeedFastest block size, zstd/encoder_options.go:248-252
 SLOT = CHUNK + 512        # per-chunk output slot (>= MaxEncodedSize(CHUNK))
+BLOCK = {SpeedFastest: 1 << 16, SpeedDefault: 128 << 10}   # zstd/encoder_options.go:41,248-252
 FLAG_CRC = 1
 FLAG_FRAME = 2
 
@@ -26,17 +27,19 @@ FLAG_FRAME = 2
 class Encoder:
     """zstd.Encoder for independent chunks on one B200.
 
-    EncodeAll(src) splits src into 64 KiB chunks, each encoded as one complete zstd frame (the
-    reference's EncodeAll emits a single multi-block frame with cross-block history; concatenated
-    frames decode to the same bytes, zstd/encoder.go:719).
+    EncodeAll(src) splits src into chunks of the level's block size (64 KiB at SpeedFastest, 128 KiB at
+    SpeedDefault), each encoded as one complete zstd frame (the reference's EncodeAll emits a single multi-block
+    frame with cross-block history; concatenated frames decode to the same bytes, zstd/encoder.go:719).
     """
 
     def __init__(self, level=SpeedFastest, crc=True, device=0, max_chunks=4096):
         if not torch.cuda.is_available() or lib.b2c_device_count() == 0:
             raise B2CError("no CUDA device: compress_b200 has no CPU fallback")
-        if level != SpeedFastest:
-            raise B2CError("only SpeedFastest is implemented on the GPU path so far")
+        if level not in BLOCK:
+            raise B2CError("levels on the GPU path: SpeedFastest, SpeedDefault")
         self.level = level
+        self.block = BLOCK[level]
+        self.slot = self.block + 512
         self.flags = (FLAG_CRC if crc else 0) | FLAG_FRAME
         self.device = device
         self.max_chunks = max_chunks
@@ -63,15 +66,15 @@ class Encoder:
     def sm_count(self):
         return int(lib.b2c_sm_count(self._ctx))
 
-    KERNELS = ("b2c_zstd_xxh_kernel", "b2c_zstd_parse_kernel", "b2c_zstd_tables_kernel", "b2c_zstd_chains_kernel",
-               "b2c_zstd_pack_kernel")
+    KERNELS = ("b2c_zstd_xxh_kernel", "b2c_lz_parse_kernel", "b2c_zstd_hist_kernel", "b2c_zstd_tables_kernel",
+               "b2c_zstd_chains_kernel", "b2c_zstd_pack_kernel")
 
     def profile(self, on=True):
         check(lib.b2c_profile_enable(self._ctx, 1 if on else 0), self._ctx)
 
     def profile_read(self):
         """-> ({kernel name: summed ms}, encode calls) since profile(True); synchronises the device."""
-        ms = (ctypes.c_double * 5)()
+        ms = (ctypes.c_double * 6)()
         nc = ctypes.c_uint32(0)
         check(lib.b2c_profile_read(self._ctx, ms, ctypes.byref(nc)), self._ctx)
         return {k: float(ms[i]) for i, k in enumerate(self.KERNELS)}, int(nc.value)
@@ -80,11 +83,13 @@ class Encoder:
         return int(lib.b2c_zstd_bound(size, self.level))
 
     # ---- device-resident batch -------------------------------------------------------------
-    def encode_device(self, src, sizes=None, chunk=CHUNK, dst=None, out_sizes=None, flags=None):
-        """src: uint8 CUDA tensor holding nchunks chunks at stride `chunk` bytes.
+    def encode_device(self, src, sizes=None, chunk=None, dst=None, out_sizes=None, flags=None):
+        """src: uint8 CUDA tensor holding nchunks chunks at stride `chunk` bytes (default: the level's block size).
         sizes: optional uint32 CUDA tensor (per-chunk sizes); default all `chunk` bytes.
-        Returns (dst [nchunks, SLOT] uint8, out_sizes [nchunks] int64), both on the device. Async."""
+        Returns (dst [nchunks, slot] uint8, out_sizes [nchunks] int64), both on the device. Async."""
         assert src.is_cuda and src.dtype == torch.uint8
+        chunk = self.block if chunk is None else chunk
+        SLOT = self.slot
         nchunks = src.numel() // chunk if sizes is None else sizes.numel()
         if dst is None:
             dst = torch.empty((nchunks, SLOT), dtype=torch.uint8, device=src.device)
@@ -98,18 +103,21 @@ class Encoder:
         check(rc, self._ctx)
         return dst, out_sizes
 
-    def encode_device_debug(self, src, sizes=None, chunk=CHUNK, flags=None, seq_cap=20000):
+    def encode_device_debug(self, src, sizes=None, chunk=None, flags=None, seq_cap=None):
         """Like encode_device but also returns the parse (sequence triples + literals) per chunk."""
+        chunk = self.block if chunk is None else chunk
+        SLOT = self.slot
+        seq_cap = self.block // 4 + 64 if seq_cap is None else seq_cap
         nchunks = src.numel() // chunk if sizes is None else sizes.numel()
         dev = src.device
         dst = torch.empty((nchunks, SLOT), dtype=torch.uint8, device=dev)
         out_sizes = torch.empty((nchunks,), dtype=torch.int64, device=dev)
         hdr = torch.zeros((nchunks, 4), dtype=torch.int32, device=dev)
         seqs = torch.zeros((nchunks, seq_cap, 3), dtype=torch.int32, device=dev)
-        lits = torch.zeros((nchunks, 65536), dtype=torch.uint8, device=dev)
+        lits = torch.zeros((nchunks, self.block), dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.b2c_zstd_encode_device_debug(
-            self._ctx, self.flags if flags is None else flags, src.data_ptr(), chunk,
+            self._ctx, self.level, self.flags if flags is None else flags, src.data_ptr(), chunk,
             None if sizes is None else sizes.data_ptr(), chunk, dst.data_ptr(), SLOT, out_sizes.data_ptr(), nchunks,
             hdr.data_ptr(), seqs.data_ptr(), lits.data_ptr(), seq_cap, ctypes.c_void_p(stream))
         check(rc, self._ctx)
@@ -117,7 +125,7 @@ class Encoder:
 
     # ---- host buffers (what the cgo shim calls) -----------------------------------------------
     def encode_chunks(self, chunks):
-        """chunks: list of bytes-like (each <= 64 KiB).  Returns list of encoded frames (bytes)."""
+        """chunks: list of bytes-like (each at most the level's block size).  Returns list of encoded frames (bytes)."""
         n = len(chunks)
         if n == 0:
             return []
@@ -137,7 +145,7 @@ class Encoder:
             out.append(outs[i][: res[i]].tobytes())
         return out
 
-    def encode_packed(self, src, dst=None, chunk=CHUNK):
+    def encode_packed(self, src, dst=None, chunk=None):
         """src: contiguous host buffer (bytes / numpy / CPU torch tensor, ideally pinned).  Returns
         (dst uint8 tensor (pinned), total, sizes int64 ndarray, offsets uint64 ndarray): dst[:total] is the
         concatenation of one frame per `chunk` bytes of src."""
@@ -147,6 +155,7 @@ class Encoder:
         else:
             arr = np.frombuffer(src, dtype=np.uint8)
             sptr, nbytes = arr.ctypes.data, arr.size
+        chunk = self.block if chunk is None else chunk
         nchunks = max(1, (nbytes + chunk - 1) // chunk)
         cap = nbytes + nchunks * 32 + 64
         if dst is None:

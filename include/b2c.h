@@ -60,7 +60,8 @@ enum { B2C_HUF_1X = 0, B2C_HUF_4X = 1 };
 /* huff0 results besides byte counts: the package's sentinel errors (huff0/huff0.go:30-42) */
 enum { B2C_HUF_ERR_INCOMPRESSIBLE = -1, B2C_HUF_ERR_USE_RLE = -2 };   /* ErrTooBig = B2C_ERR_TOO_BIG */
 
-/* zstd levels (zstd.EncoderLevel, zstd/encoder_options.go) */
+/* zstd levels (zstd.EncoderLevel, zstd/encoder_options.go:163-190): SpeedFastest = 64 KiB blocks, one hash table
+ * (zstd/enc_fast.go); SpeedDefault = 128 KiB blocks, long + short table with a lazy step (zstd/enc_dfast.go) */
 enum { B2C_LEVEL_FASTEST = 1, B2C_LEVEL_DEFAULT = 2 };
 
 typedef struct b2c_ctx b2c_ctx;
@@ -77,7 +78,8 @@ B2C_API uint64_t b2c_launch_count(b2c_ctx *ctx);
 
 /* Per-kernel timing of the encode pipeline with CUDA events recorded on the launching stream (bench.py's
  * roofline).  b2c_profile_enable(ctx, 1) starts collecting; b2c_profile_read synchronises the device and returns in
- * ms[0..4] the summed durations of {xxh64, parse, tables, chains, pack} over the *ncalls encode calls since. */
+ * ms[0..5] the summed durations of {xxh64, parse, histograms, tables, chains, pack} over the *ncalls encode launches
+ * since (a device-resident call larger than the work pool is several launches). */
 B2C_API int b2c_profile_enable(b2c_ctx *ctx, int on);
 B2C_API int b2c_profile_read(b2c_ctx *ctx, double *ms, uint32_t *ncalls);
 
@@ -115,9 +117,9 @@ B2C_API int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const voi
                                    uint64_t *offsets_out, size_t *total_out);
 
 /* Debug/parity hook used by tests: encode device-resident chunks and also dump, per chunk,
- * {nseq, nlit, kind, litMode}, the (litLen, matchLen-3, offset) triples and the literal bytes, so the
- * entropy stage can be compared byte-for-byte with the oracle's blockEnc.encode. */
-B2C_API int b2c_zstd_encode_device_debug(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride,
+ * {nseq, nlit, kind, litMode}, the (litLen, matchLen-3, offset) triples and the literal bytes (rows of the level's
+ * block size), so the entropy stage can be compared byte-for-byte with the oracle's blockEnc.encode. */
+B2C_API int b2c_zstd_encode_device_debug(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
                                          const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
                                          int64_t *d_out_sizes, uint32_t nchunks, uint32_t *d_dbg_hdr,
                                          uint32_t *d_dbg_seqs, uint8_t *d_dbg_lits, uint32_t dbg_seq_cap, void *stream);

@@ -5,7 +5,7 @@ import helpers as H
 from emu_util import frame_header_len
 
 
-def check_frames(chunks, frames, hdr=None, seqs=None, lits=None, crc=True, label=""):
+def check_frames(chunks, frames, hdr=None, seqs=None, lits=None, crc=True, label="", level=1, check_raw=True):
     """Every frame must (1) decode to its chunk with the oracle's restatement of the reference decoder
     and with libzstd, (2) respect MaxEncodedSize, and -- when the parse dump is given -- (3) carry a block
     that is byte-identical to the oracle's blockEnc.encode for the same literals + sequences."""
@@ -14,7 +14,7 @@ def check_frames(chunks, frames, hdr=None, seqs=None, lits=None, crc=True, label
     for i, c in enumerate(chunks):
         enc = frames[i]
         assert len(enc) > 0, f"{label} chunk {i}: empty output"
-        assert len(enc) <= L.orc_zstd_max_encoded_size(len(c), 1, 1), f"{label} chunk {i}: exceeds MaxEncodedSize"
+        assert len(enc) <= L.orc_zstd_max_encoded_size(len(c), level, 1), f"{label} chunk {i}: exceeds MaxEncodedSize"
         r, dec = H.oracle_decode(enc, len(c) + 64)
         assert r == len(c) and dec == c, f"{label} chunk {i}: oracle decode mismatch (r={r})"
         z = H.libzstd_decode(enc, len(c))
@@ -22,9 +22,15 @@ def check_frames(chunks, frames, hdr=None, seqs=None, lits=None, crc=True, label
         tot += len(enc)
         if hdr is not None:
             nseq, nlit, kind, _ = [int(x) for x in hdr[i]]
-            if kind == 0 and nseq > 0:
+            if nseq > 0 and (kind == 0 or check_raw):
+                # kind 0 = compressed candidate, 1 = raw fallback, 2 = RLE: in every case the block must be what the
+                # oracle's blockEnc.encode makes of the same literals + sequences (raw / RLE decisions included)
                 tri = np.asarray(seqs[i][:nseq]).astype(np.uint32)
-                lb = bytes(np.asarray(lits[i][:nlit]).astype(np.uint8))
+                if kind == 0:
+                    lb = bytes(np.asarray(lits[i][:nlit]).astype(np.uint8))
+                else:
+                    lb = _lits_from_seqs(tri, c)       # raw / RLE blocks: the kernel does not produce the literals
+                    assert len(lb) == nlit, f"{label} chunk {i}: literal count {nlit} vs sequences {len(lb)}"
                 # the sequences must reproduce the chunk (independent of the entropy stage)
                 assert _replay(tri, lb, len(c)) == c, f"{label} chunk {i}: sequences do not reproduce the input"
                 rb, ob = H.oracle_encode_block(c, lb, tri, 1)
@@ -32,8 +38,19 @@ def check_frames(chunks, frames, hdr=None, seqs=None, lits=None, crc=True, label
                 blk = enc[fh:len(enc) - (4 if crc else 0)]
                 assert rb == len(blk) and ob == blk, (
                     f"{label} chunk {i}: entropy stage differs from oracle blockEnc.encode "
-                    f"(oracle {rb} B, gpu {len(blk)} B, first diff {_first_diff(ob, blk)})")
+                    f"(kind {kind}, oracle {rb} B, gpu {len(blk)} B, first diff {_first_diff(ob, blk)})")
     return tot
+
+
+def _lits_from_seqs(tri, c):
+    """Literal bytes implied by (litLen, matchLen-3, offset) triples over the chunk c."""
+    out = bytearray()
+    pos = 0
+    for ll, ml3, _ in tri:
+        out += c[pos:pos + int(ll)]
+        pos += int(ll) + int(ml3) + 3
+    out += c[pos:]
+    return bytes(out)
 
 
 def _first_diff(a, b):

@@ -20,19 +20,5 @@ def oracle_lib():
 
 @pytest.fixture(scope="session")
 def emu_lib():
-    import ctypes
     import helpers
-    helpers.build_emu()
-    E = ctypes.CDLL(helpers.EMU_SO)
-    c = ctypes
-    E.emu_zstd_encode.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p,
-                                  c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32]
-    E.emu_zstd_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
-                                  c.c_void_p]
-    E.emu_s2_encode.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
-    E.emu_s2_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
-                                c.c_void_p]
-    E.emu_huf_compress.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
-    E.emu_huf_decompress.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p,
-                                     c.c_void_p, c.c_int]
-    return E
+    return helpers.emu()

@@ -2,10 +2,12 @@
 // SIMT emulator and exposes C entry points for pytest.  TEST INFRASTRUCTURE ONLY (see simt_emu.h).
 #include "simt_emu.h"
 #include "../../compress_b200/csrc/b2c_zstd_enc.cuh"
+#include "../../compress_b200/csrc/b2c_lz.cuh"
 #include "../../compress_b200/csrc/b2c_zstd_dec.cuh"
 #include "../../compress_b200/csrc/b2c_s2_dec.cuh"
 #include "../../compress_b200/csrc/b2c_huf0.cuh"
 #include <vector>
+#include <algorithm>
 #include <cstdlib>
 
 using namespace b2c;
@@ -14,19 +16,27 @@ extern "C" {
 
 void emu_set_lane_order(int desc) { emu::lane_order_desc = desc; }
 
-// Encode nchunks chunks laid out contiguously (chunk i = src + i*stride, size sizes[i]) with the same five
-// kernels the device runs.  dst slots of dst_stride bytes.  Optional debug dumps (may be null).
-int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
-                    uint64_t dst_stride, int64_t *out_sizes, uint32_t flags, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
-                    uint8_t *dbg_lits, uint32_t dbg_seq_cap) {
-    std::vector<uint8_t> scratch(ENC_SCRATCH_BYTES, 0xCD);
+// Encode nchunks chunks laid out contiguously (chunk i = src + i*stride, size sizes[i]) with the same kernels the
+// device runs.  level 1 / 2; parse 0 = tile-ordered parse (b2c_lz.cuh, the product path), 1 = the round-1 parse
+// (level 1 only).  dst slots of dst_stride bytes.  Optional debug dumps (may be null; dbg_lits rows of blockmax bytes).
+int emu_zstd_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
+                       uint64_t dst_stride, int64_t *out_sizes, uint32_t flags, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
+                       uint8_t *dbg_lits, uint32_t dbg_seq_cap, int level, int parse) {
+    const uint32_t blockmax = level >= 2 ? 131072u : 65536u;
+    if (parse == 1 && level != 1) return -1;
+    std::vector<uint8_t> scratch(std::max<size_t>(ENC_SCRATCH_BYTES, std::max(LzLayout<1>::SCRATCH_BYTES, LzLayout<2>::SCRATCH_BYTES)), 0xCD);
     ChunkWork *work = (ChunkWork *)aligned_alloc(16, sizeof(ChunkWork) * (size_t)nchunks);
     memset(work, 0xCD, sizeof(ChunkWork) * (size_t)nchunks);
+    const uint64_t pstride = wk_pool_stride(blockmax);
+    uint8_t *pool = (uint8_t *)aligned_alloc(16, pstride * (size_t)nchunks);
+    memset(pool, 0xCD, pstride * (size_t)nchunks);
     ZstdEncParams P;
     memset(&P, 0, sizeof(P));
     P.src_base = src; P.src_stride = stride; P.src_sizes = sizes; P.src_size_all = 0;
     P.dst_base = dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
     P.out_sizes = out_sizes; P.nchunks = nchunks; P.flags = flags; P.scratch = scratch.data(); P.work = work;
+    P.pool = pool; P.pool_stride = pstride; P.maxseq = wk_maxseq(blockmax); P.blockmax = blockmax;
+    P.big = blockmax > 65536; P.level = (uint32_t)level;
     P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_seq_cap;
     // K5 xxh64
     emu::launch((4 * nchunks + 127) / 128, 128, 0, [&]() {
@@ -34,9 +44,23 @@ int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, 
         zstd_xxh_quad(P, gt >> 2, gt & 3, (threadIdx.x & 31) & ~3u);
     });
     // K1 parse
-    emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
-        for (uint32_t c = 0; c < P.nchunks; c++) zstd_parse_chunk<LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
-    });
+    if (parse == 1) {
+        emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < P.nchunks; c++) zstd_parse_chunk<LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
+        });
+    } else {
+        if (level >= 2)
+            emu::launch(1, LzCfg<2>::NT, LzLayout<2>::SMEM_BYTES, [&]() {
+                for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<2>(emu::dyn_smem, P, c, P.scratch);
+            });
+        else
+            emu::launch(1, LzCfg<1>::NT, LzLayout<1>::SMEM_BYTES, [&]() {
+                for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<1>(emu::dyn_smem, P, c, P.scratch);
+            });
+        emu::launch(1, HIST_NT, HIST_SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < P.nchunks; c++) zstd_hist_chunk(emu::dyn_smem, P, c);
+        });
+    }
     // K2 tables
     static TablesShared ts;
     emu::launch(1, TABLES_NT, 0, [&]() {
@@ -49,9 +73,19 @@ int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, 
         zstd_chains_block(reinterpret_cast<uint32_t *>(emu::dyn_smem), P, blockIdx.x * 32);
     });
     // K4 pack
-    emu::launch(nchunks, PACK_NT, PACK_SMEM_BYTES, [&]() { zstd_pack_chunk(emu::dyn_smem, P, blockIdx.x); });
+    if (blockmax > 65536)
+        emu::launch(nchunks, PACK_NT, PackCfg<131072>::SMEM_BYTES, [&]() { zstd_pack_chunk<131072>(emu::dyn_smem, P, blockIdx.x); });
+    else
+        emu::launch(nchunks, PACK_NT, PACK_SMEM_BYTES, [&]() { zstd_pack_chunk<65536>(emu::dyn_smem, P, blockIdx.x); });
     free(work);
+    free(pool);
     return 0;
+}
+int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
+                    uint64_t dst_stride, int64_t *out_sizes, uint32_t flags, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
+                    uint8_t *dbg_lits, uint32_t dbg_seq_cap) {
+    return emu_zstd_encode_lv(src, stride, sizes, nchunks, dst, dst_stride, out_sizes, flags, dbg_hdr, dbg_seqs, dbg_lits,
+                              dbg_seq_cap, 1, 0);
 }
 
 // Decode n inputs (input i = src + src_off[i], src_sizes[i] bytes) into dst + dst_off[i] (capacity dst_caps[i]).
@@ -133,6 +167,7 @@ int emu_huf_decompress(const uint8_t *src, uint64_t stride, const uint32_t *size
 }
 
 uint32_t emu_enc_smem_bytes() { return ENC_SMEM_BYTES; }
+uint32_t emu_lz_smem_bytes(int level) { return level >= 2 ? LzLayout<2>::SMEM_BYTES : LzLayout<1>::SMEM_BYTES; }
 uint32_t emu_pack_smem_bytes() { return PACK_SMEM_BYTES; }
 uint64_t emu_chunkwork_bytes() { return sizeof(ChunkWork); }
 }

@@ -2,23 +2,28 @@
 import numpy as np
 
 
-def emu_encode(E, chunks, flags=3, desc=0, seq_cap=20000):
+def emu_encode(E, chunks, flags=3, desc=0, seq_cap=None, level=1, parse=0):
+    """level 1 / 2; parse 0 = the tile-ordered parse (product path), 1 = the round-1 parse (level 1 only)."""
     E.emu_set_lane_order(desc)
     n = len(chunks)
-    stride = 65536
+    stride = 65536 if level == 1 else 131072
+    if seq_cap is None:
+        seq_cap = stride // 4 + 64
     src = np.zeros(n * stride + 64, dtype=np.uint8)
     sizes = np.zeros(n, dtype=np.uint32)
     for i, c in enumerate(chunks):
-        src[i * stride:i * stride + len(c)] = np.frombuffer(c, dtype=np.uint8)
+        m = min(len(c), stride)
+        src[i * stride:i * stride + m] = np.frombuffer(c, dtype=np.uint8)[:m]
         sizes[i] = len(c)
-    dstride = 65536 + 512
+    dstride = stride + 512
     dst = np.zeros(n * dstride, dtype=np.uint8)
     outs = np.zeros(n, dtype=np.int64)
     hdr = np.zeros((n, 4), dtype=np.uint32)
     seqs = np.zeros((n, seq_cap, 3), dtype=np.uint32)
-    lits = np.zeros((n, 65536), dtype=np.uint8)
-    E.emu_zstd_encode(src.ctypes.data, stride, sizes.ctypes.data, n, dst.ctypes.data, dstride, outs.ctypes.data, flags,
-                      hdr.ctypes.data, seqs.ctypes.data, lits.ctypes.data, seq_cap)
+    lits = np.zeros((n, stride), dtype=np.uint8)
+    rc = E.emu_zstd_encode_lv(src.ctypes.data, stride, sizes.ctypes.data, n, dst.ctypes.data, dstride, outs.ctypes.data,
+                              flags, hdr.ctypes.data, seqs.ctypes.data, lits.ctypes.data, seq_cap, level, parse)
+    assert rc == 0
     frames = [bytes(dst[i * dstride:i * dstride + max(int(outs[i]), 0)]) for i in range(n)]
     return frames, outs, hdr, seqs, lits
 

@@ -25,6 +25,32 @@ def build_emu():
     return EMU_SO
 
 
+_emu = None
+
+
+def emu():
+    """ctypes handle of the SIMT-emulated kernels (tests/emu; built on demand) with argument types set."""
+    global _emu
+    if _emu is not None:
+        return _emu
+    build_emu()
+    E = ctypes.CDLL(EMU_SO)
+    c = ctypes
+    E.emu_zstd_encode.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p,
+                                  c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32]
+    E.emu_zstd_encode_lv.argtypes = E.emu_zstd_encode.argtypes + [c.c_int, c.c_int]
+    E.emu_zstd_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
+                                  c.c_void_p]
+    E.emu_s2_encode.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
+    E.emu_s2_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
+                                c.c_void_p]
+    E.emu_huf_compress.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
+    E.emu_huf_decompress.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p,
+                                     c.c_void_p, c.c_int]
+    _emu = E
+    return E
+
+
 _oracle = None
 
 

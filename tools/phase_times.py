@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Per-phase cycle breakdown of the zstd encode kernel (clock64 stamps of thread 0 of each CTA)."""
-import ctypes, os, sys
+"""Per-phase cycle breakdown of the level-1 parse kernel (b2c_lz_parse1_kernel; with B2C_PARSE=r1 the round-1 kernel):
+lane 0 of every warp stamps clock64 at the phase boundaries (B2C_PHASE), dumped through b2c_zstd_encode_device_timed."""
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
@@ -8,8 +9,12 @@ import helpers as H
 from compress_b200 import zstd
 from compress_b200._lib import lib, check
 
-NAMES = ["load", "Ebuild", "parse", "layout+gather", "hist", "huf stats/sort", "tree+fse tables", "bits",
-         "vals+write+chains", "lit sizes", "seq sizes", "zero+lit pack", "seq pack", "headers", "writeback"]
+# stamp order inside lz_parse_chunk and what lies between two consecutive stamps
+ORDER = [0, 1, 2, 6, 3, 8, 9, 10, 11, 4, 5]
+NAMES = ["dense pass (tiles: probe | store | fix | probe)", "stage chunk into shared memory (TMA)", "walk (per-thread greedy scan)",
+         "long matches (warp 0) + barriers", "prefix-max of match ends", "trim loop", "two block scans",
+         "emit loop (sequences, codes, literal mask)", "RLE test + literal scan", "literal compaction + header"]
+
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 8
@@ -23,31 +28,21 @@ def main():
                                               outs.data_ptr(), n, cyc.data_ptr(), None)
         check(rc, enc._ctx)
         torch.cuda.synchronize()
-    c = cyc.cpu().numpy().astype(np.int64)       # [n, 16, 32] arrival of warp w at the barrier before stamp k
-    rel = c[:, :6, :].max(axis=2)                  # release time of each barrier (K1 has stamps 0..5)
-    tot = rel[:, 5] - c[:, 0, :].min(axis=1)
-    print("K1 parse kernel: chunks", n, "mean cycles/chunk %.0f" % tot.mean(), "min", tot.min(), "max", tot.max())
-    names = ["load", "Ebuild", "parse", "layout+gather+rle", "hist+writeout"]
-    for k in range(5):
-        dur = rel[:, k + 1] - rel[:, k]
-        work = c[:, k + 1, :] - rel[:, k][:, None]          # per-warp busy time in this phase
-        wmean = work.mean(axis=0)
-        top = np.argsort(-wmean)[:3]
-        print("%-26s %9.0f %5.1f%%   busy: mean %7.0f  slowest warps %s" % (
-            names[k], dur.mean(), 100 * dur.mean() / tot.mean(), work.mean(),
-            ", ".join("w%d=%.0f" % (w, wmean[w]) for w in top)))
-
-
-    # finer stamps (per-warp arrival, no barrier implied): mean over chunks and warps of the time between stamps
-    chain = [(2, 6, "per-thread scan (until the warp leaves the loop)"), (6, 3, "wait + long-match resolution"),
-             (3, 8, "prefix-max of match ends"), (8, 9, "trim loop"), (9, 10, "two block scans"),
-             (10, 11, "emit loop (literal gather, codes, stores)"), (11, 4, "tail literals + RLE test barriers"),
-             (4, 12, "zero counters + barrier"), (12, 13, "histograms + literal copy-out"), (13, 14, "barrier wait"),
-             (14, 5, "reduce + maxSym + end")]
-    print("-- detail (mean cycles per warp; stamps are arrival times) --")
-    for a, b, nm in chain:
-        d = (c[:, b, :] - c[:, a, :]).astype(np.float64)
-        print("%-52s mean %8.0f   max-warp mean %8.0f" % (nm, d.mean(), d.mean(axis=0).max()))
+    c = cyc.cpu().numpy().astype(np.int64)       # [n, 16, 32]: arrival of warp w at stamp k (0 where the warp does not exist)
+    nw = int((c[0, 0] != 0).sum())
+    c = c[:, :, :nw]
+    if os.environ.get("B2C_PARSE") == "r1":
+        order = [0, 1, 2, 6, 3, 8, 9, 10, 11, 4, 12, 13, 14, 5]
+        names = ["load", "table build", "candidate pass + walk", "long matches", "prefix max", "trim", "scans", "emit + gather",
+                 "tail + RLE", "zero counters", "histograms + copy-out", "barrier", "reduce + end"]
+    else:
+        order, names = ORDER, NAMES
+    tot = c[:, order[-1], :].max(axis=1) - c[:, order[0], :].min(axis=1)
+    print("parse kernel: chunks %d, warps/CTA %d, mean cycles/chunk %.0f (min %d, max %d)" % (n, nw, tot.mean(), tot.min(), tot.max()))
+    for a, b, nm in zip(order[:-1], order[1:], names):
+        d = (c[:, b, :] - c[:, a, :]).astype(np.float64)          # per-warp time between the two stamps
+        rel = c[:, b, :].max(axis=1) - c[:, a, :].max(axis=1)     # between the slowest warps (~ barrier release to release)
+        print("%-52s slowest-warp %8.0f (%4.1f%%)   mean-warp %8.0f" % (nm, rel.mean(), 100 * rel.mean() / tot.mean(), d.mean()))
 
 
 if __name__ == "__main__":
