@@ -116,6 +116,10 @@ typedef struct {
     uint8_t *litBuf;
 } frame_state;
 
+/* Test_seqdec_decoder hook (zstd/seqdec_test.go:199-302): when set, decode_sequences stores (mo, ml, ll) per sequence
+ * here instead of executing the sequences -- sequenceDecs.decode (seqdec.go:119) vs decodeSync/execute. */
+static int64_t *seqDump = NULL;
+
 /* sequence section + execution; out = frame output start, *outLen = bytes so far */
 static int decode_sequences(frame_state *fs, const uint8_t *in, size_t inLen, int nSeqs, const uint8_t *literals,
                             size_t nLit, uint8_t *out, size_t *outLen, size_t outCap) {
@@ -158,6 +162,14 @@ static int decode_sequences(frame_state *fs, const uint8_t *in, size_t inLen, in
             }
         }
         if ((size_t)ll > nLit - litPos) return ORC_ERR_CORRUPT;       /* "unexpected literal count" */
+        if (seqDump) {   /* decode only (seqdec.go:119-218): same value rules, no output */
+            int64_t *d = seqDump + 3 * (size_t)(nSeqs - 1 - i);
+            d[0] = mo; d[1] = ml; d[2] = ll;
+            litPos += (size_t)ll;
+            if (ml > ORC_ZSTD_MAX_MATCHLEN) return ORC_ERR_CORRUPT;
+            if (mo == 0 && ml > 0) return ORC_ERR_CORRUPT;
+            goto next_state;
+        }
         size_t size = (size_t)ll + (size_t)ml + o;
         if (size - startSize > maxBlockSize) return ORC_ERR_CORRUPT;  /* "output bigger than max block size" */
         if (ml > ORC_ZSTD_MAX_MATCHLEN) return ORC_ERR_CORRUPT;       /* "match len bigger than max allowed" */
@@ -171,6 +183,7 @@ static int decode_sequences(frame_state *fs, const uint8_t *in, size_t inLen, in
             for (int64_t k = 0; k < ml; k++) out[o + k] = from[k]; /* overlap-safe byte copy */
             o += (size_t)ml;
         }
+    next_state:
         if (i == 0) break;
         /* state update, seqdec.go:405-424: LL bits first, then ML, then OF */
         {
@@ -183,6 +196,7 @@ static int decode_sequences(frame_state *fs, const uint8_t *in, size_t inLen, in
             ofS = ofT->dt[(ofS.newState + bo) & ((1 << MAX_TABLELOG_DEC) - 1)];
         }
     }
+    if (seqDump) return (br.pos != br.total) ? ORC_ERR_CORRUPT : 0;
     size_t rest = nLit - litPos;
     if (rest + o - startSize > maxBlockSize) return ORC_ERR_CORRUPT;
     if (o + rest > outCap) return ORC_ERR_DST_SMALL;
@@ -331,6 +345,96 @@ static int decode_compressed_block(frame_state *fs, const uint8_t *in, size_t le
         }
     }
     return decode_sequences(fs, in, len, nSeqs, literals, litRegenSize, out, outLen, outCap);
+}
+
+/* Header.Decode (zstd/decodeheader.go:94-229): fields of the frame header and of the first block header.
+ * out[0..14] = SingleSegment, WindowSize(lo), WindowSize(hi), DictionaryID, HasFCS, FCS(lo), FCS(hi), Skippable,
+ * SkippableID, SkippableSize, HeaderSize, FirstBlock.OK, Last, Compressed | HasCheckSum << 1, DecompressedSize,
+ * out[15] = CompressedSize.  Returns 0, or ORC_ERR_* (unexpected EOF / magic mismatch / reserved bit). */
+ORC_API int orc_zstd_header_decode(const uint8_t *in, size_t n, uint32_t *out) {
+    memset(out, 0, 16 * sizeof(uint32_t));
+    if (n < 4) return ORC_ERR_CORRUPT;                                  /* io.ErrUnexpectedEOF, :96-98 */
+    uint32_t hs = 4;
+    const uint8_t *b = in; in += 4; n -= 4;
+    if (!(b[0] == 0x28 && b[1] == 0xB5 && b[2] == 0x2F && b[3] == 0xFD)) {
+        if (!(b[1] == 0x2A && b[2] == 0x4D && b[3] == 0x18) || (b[0] & 0xf0) != 0x50) return ORC_ERR_MAGIC;  /* :102-104 */
+        if (n < 4) return ORC_ERR_CORRUPT;
+        out[7] = 1; out[8] = b[0] & 0xf; out[9] = (uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16) | ((uint32_t)in[3] << 24);
+        out[10] = hs + 4;
+        return 0;
+    }
+    if (n < 1) return ORC_ERR_CORRUPT;
+    uint8_t fhd = in[0]; in++; n--; hs++;
+    const int single = (fhd & (1 << 5)) != 0;
+    out[0] = single;
+    const uint32_t hasCrc = (fhd & (1 << 2)) != 0;
+    if (fhd & (1 << 3)) return ORC_ERR_CORRUPT;                         /* "reserved bit set on frame header", :124-126 */
+    if (!single) {                                                      /* :128-142 */
+        if (n < 1) return ORC_ERR_CORRUPT;
+        uint8_t wd = in[0]; in++; n--; hs++;
+        unsigned windowLog = 10 + (wd >> 3);
+        uint64_t windowBase = 1ull << windowLog;
+        uint64_t ws = windowBase + (windowBase / 8) * (uint64_t)(wd & 7);
+        out[1] = (uint32_t)ws; out[2] = (uint32_t)(ws >> 32);
+    }
+    unsigned size = fhd & 3;                                            /* dictionary id, :144-164 */
+    if (size) {
+        if (size == 3) size = 4;
+        if (n < size) return ORC_ERR_CORRUPT;
+        uint32_t id = 0;
+        for (unsigned k = 0; k < size; k++) id |= (uint32_t)in[k] << (8 * k);
+        out[3] = id; in += size; n -= size; hs += size;
+    }
+    unsigned fcsSize = 0, v = fhd >> 6;                                 /* :167-176 */
+    if (v == 0) { if (single) fcsSize = 1; } else fcsSize = 1u << v;
+    if (fcsSize) {
+        out[4] = 1;
+        if (n < fcsSize) return ORC_ERR_CORRUPT;
+        uint64_t fcs = 0;
+        for (unsigned k = 0; k < fcsSize; k++) fcs |= (uint64_t)in[k] << (8 * k);
+        if (fcsSize == 2) fcs += 256;
+        out[5] = (uint32_t)fcs; out[6] = (uint32_t)(fcs >> 32);
+        in += fcsSize; n -= fcsSize; hs += fcsSize;
+    }
+    out[10] = hs;
+    out[13] = hasCrc << 1;
+    if (n < 3) return 0;                                                /* :203-205: no room for a block header */
+    uint32_t bh = (uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16);
+    const uint32_t last = bh & 1, bt = (bh >> 1) & 3, cSize = bh >> 3;
+    out[12] = last;                                                     /* FirstBlock.Last is set before the type switch, :208 */
+    if (bt == 3) return 0;                                              /* blockTypeReserved */
+    if (bt == 1) { out[13] |= 1; out[14] = cSize; out[15] = 1; }        /* RLE */
+    else if (bt == 2) { out[13] |= 1; out[15] = cSize; }                /* compressed */
+    else { out[14] = cSize; out[15] = cSize; }                          /* raw */
+    out[11] = 1;
+    return 0;
+}
+
+/* The reference's sequence-decoder golden test (zstd/seqdec_test.go:199-302, testdata/seqs.zip <-> seqs-want.zip):
+ * three ready-made decoding tables (512 decSymbol words each: LL, ML, OF -- the order readDecoders reads them), the
+ * bitstream, nSeqs, the incoming repeat offsets; outputs (mo, ml, ll) per sequence and the final repeat offsets. */
+ORC_API int orc_zstd_seqdec_golden(const uint64_t *dtLL, unsigned tlLL, const uint64_t *dtML, unsigned tlML,
+                                   const uint64_t *dtOF, unsigned tlOF, const uint8_t *bits, size_t nbytes, int nSeqs,
+                                   int64_t *prev3, uint64_t windowSize, size_t nLit, int64_t *out3) {
+    init_tables();
+    frame_state *fs = (frame_state *)calloc(1, sizeof(frame_state));
+    const uint64_t *src[3] = {dtLL, dtOF, dtML};
+    const unsigned tl[3] = {tlLL, tlOF, tlML};
+    for (int t = 0; t < 3; t++) {
+        if (tl[t] > MAX_TABLELOG_DEC) { free(fs); return ORC_ERR_CORRUPT; }
+        memcpy(fs->tables[t].dt, src[t], sizeof(fs->tables[t].dt));   /* decSymbol: nbBits | addBits << 8 | newState << 16 | baseline << 32 */
+        fs->tables[t].actualTableLog = tl[t]; fs->tables[t].valid = 1;
+        fs->cur[t] = &fs->tables[t];
+    }
+    for (int k = 0; k < 3; k++) fs->recent[k] = prev3[k];
+    fs->windowSize = windowSize;
+    size_t outLen = 0;
+    seqDump = out3;
+    int r = decode_sequences(fs, bits, nbytes, nSeqs, NULL, nLit, NULL, &outLen, 0);
+    seqDump = NULL;
+    for (int k = 0; k < 3; k++) prev3[k] = fs->recent[k];
+    free(fs);
+    return r;
 }
 
 ORC_API int64_t orc_zstd_decode_all(const uint8_t *src, size_t n, uint8_t *dst, size_t cap) {

@@ -5,7 +5,11 @@ text corpora the reference's tests use -- never source code.  The GPU box has no
 everything the -m gpu tests, smoke() and bench.py need lives here.
 
   zstd_good.zip / zstd_bad.zip   zstd/testdata/good.zip, bad.zip (TestNewDecoderGood/Bad, decoder_test.go:393-455)
-  zstd_decoder_subset.zip        the smaller pairs of zstd/testdata/decoder.zip (TestNewDecoder, :201-216)
+  zstd_decoder.zip               zstd/testdata/decoder.zip, all 94 pairs (TestNewDecoder, :201-216)
+  zstd_comp_crashers.zip         zstd/testdata/comp-crashers.zip: 1657 inputs that once broke an encoder (TestEncoderRegression, encoder_test.go:218)
+  zstd_seqs.zip / _want.zip      sequence-decoder golden vectors (Test_seqdec_decoder, seqdec_test.go:199-302)
+  zstd_headers.zip / -want.json.zst  frame-header golden vectors (TestHeader_Decode, decodeheader_test.go)
+  s2_enc_regressions.zip         s2/testdata/enc_regressions.zip (TestEncoderRegression, s2/s2_test.go:2133)
   twain.txt, html.txt, e.txt     testdata/* corpora used by the encoder round-trip tests
   s2_twain.txt(.rawsnappy)       s2/testdata golden Snappy block (TestDecodeGoldenInput, s2_test.go:599)
   huff0_inputs.zip               inputs of huff0's compress tests whose error class is tabulated (huff0/compress_test.go:20-52)
@@ -27,21 +31,13 @@ def main():
     shutil.copy(f"{REF}/testdata/e.txt", f"{HERE}/e.txt")
     shutil.copy(f"{REF}/s2/testdata/Mark.Twain-Tom.Sawyer.txt", f"{HERE}/s2_twain.txt")
     shutil.copy(f"{REF}/s2/testdata/Mark.Twain-Tom.Sawyer.txt.rawsnappy", f"{HERE}/s2_twain.txt.rawsnappy")
-    zf = zipfile.ZipFile(f"{REF}/zstd/testdata/decoder.zip")
-    pairs = []
-    for nm in zf.namelist():
-        if nm.endswith(".zst") and nm[:-4] in zf.namelist():
-            pairs.append((zf.getinfo(nm).file_size + zf.getinfo(nm[:-4]).compress_size, nm))
-    pairs.sort()
-    out = zipfile.ZipFile(f"{HERE}/zstd_decoder_subset.zip", "w", zipfile.ZIP_DEFLATED, compresslevel=9)
-    total = 0
-    for sz, nm in pairs:
-        if total + sz > 700_000:
-            break
-        out.writestr(nm, zf.read(nm))
-        out.writestr(nm[:-4], zf.read(nm[:-4]))
-        total += sz
-    out.close()
+    shutil.copy(f"{REF}/zstd/testdata/decoder.zip", f"{HERE}/zstd_decoder.zip")
+    shutil.copy(f"{REF}/zstd/testdata/comp-crashers.zip", f"{HERE}/zstd_comp_crashers.zip")
+    shutil.copy(f"{REF}/zstd/testdata/seqs.zip", f"{HERE}/zstd_seqs.zip")
+    shutil.copy(f"{REF}/zstd/testdata/seqs-want.zip", f"{HERE}/zstd_seqs_want.zip")
+    shutil.copy(f"{REF}/zstd/testdata/headers.zip", f"{HERE}/zstd_headers.zip")
+    shutil.copy(f"{REF}/zstd/testdata/headers-want.json.zst", f"{HERE}/zstd_headers-want.json.zst")
+    shutil.copy(f"{REF}/s2/testdata/enc_regressions.zip", f"{HERE}/s2_enc_regressions.zip")
     hz = zipfile.ZipFile(f"{HERE}/huff0_inputs.zip", "w", zipfile.ZIP_DEFLATED, compresslevel=9)
     for nm in ("gettysburg.txt", "sharnd.out", "crash1.bin", "crash2.bin", "crash3.bin", "endzerobits.bin", "endnonzero.bin",
                "case1.bin", "case2.bin", "case3.bin", "pngdata.bin", "normcount2.bin"):

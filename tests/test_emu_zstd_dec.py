@@ -19,8 +19,8 @@ def _pairs(zf):
 
 def test_emu_decoder_zip_subset(emu_lib):
     # zstd/decoder_test.go:201-216 TestNewDecoder
-    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_decoder_subset.zip"))
-    items = list(_pairs(zf))
+    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_decoder.zip"))
+    items = sorted(_pairs(zf), key=lambda it: len(it[2]))[:24]      # the emulator is slow: the 24 smallest pairs
     for desc in (0, 1):
         outs, res = emu_decode(emu_lib, [c for _, c, _ in items], [len(w) + 64 for _, _, w in items], desc)
         for (nm, _, want), r, got in zip(items, outs, res):

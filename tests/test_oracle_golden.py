@@ -21,26 +21,87 @@ def _pairs(zf):
             yield nm, zf.read(nm), zf.read(nm[:-4])
 
 
-def test_decoder_zip_subset(oracle_lib):
-    # zstd/decoder_test.go:201-216 TestNewDecoder: every zN.zst must decode to zN
-    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_decoder_subset.zip"))
-    n = 0
-    for nm, comp, want in _pairs(zf):
-        r, got = H.oracle_decode(comp, len(want) + 1024)
-        assert r == len(want) and got == want, nm
-        n += 1
-    assert n >= 20
-
-
-@pytest.mark.skipif(not os.path.exists(REF), reason="reference mount not present")
 def test_decoder_zip_full(oracle_lib):
-    zf = zipfile.ZipFile(os.path.join(REF, "decoder.zip"))
+    # zstd/decoder_test.go:201-216 TestNewDecoder: every zN.zst must decode to zN (all 94 pairs of decoder.zip)
+    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_decoder.zip"))
     n = 0
     for nm, comp, want in _pairs(zf):
         r, got = H.oracle_decode(comp, len(want) + 1024)
         assert r == len(want) and got == want, nm
         n += 1
     assert n == 94
+
+
+def test_seqdec_golden(oracle_lib):
+    """Test_seqdec_decoder (zstd/seqdec_test.go:199-302): ready-made decoding tables + bitstream -> (matchOffset,
+    matchLength, litLength) per sequence and the final repeat offsets, compared with the reference's seqs-want.zip."""
+    c = ctypes
+    L = oracle_lib
+    L.orc_zstd_seqdec_golden.restype = c.c_int
+    L.orc_zstd_seqdec_golden.argtypes = [c.c_void_p, c.c_uint, c.c_void_p, c.c_uint, c.c_void_p, c.c_uint, c.c_char_p,
+                                         c.c_size_t, c.c_int, c.c_void_p, c.c_uint64, c.c_size_t, c.c_void_p]
+    zs = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_seqs.zip"))
+    zw = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_seqs_want.zip"))
+    import re
+    n_files = 0
+    for nm in zs.namelist():
+        m = re.fullmatch(r"n-(\d+)-lits-(\d+)-prev-(\d+)-(\d+)-(\d+)-win-(\d+)\.blk", nm)
+        assert m, nm
+        nseq, nlit, p0, p1, p2, win = map(int, m.groups())
+        d = zs.read(nm)
+        off, tabs = 0, []
+        for _ in range(3):      # readDecoders: litLengths, matchLengths, offsets (fse_decoder.go:186-207 layout)
+            dt = np.frombuffer(d, dtype="<u8", count=512, offset=off).copy()
+            symlen, tl, maxbits = struct.unpack_from("<HBB", d, off + 4096)
+            tabs.append((dt, tl))
+            off += 4096 + 4 + 512 + 512 + 1
+        bits = d[off:]
+        prev = np.array([p0, p1, p2], dtype=np.int64)
+        out = np.zeros((nseq, 3), dtype=np.int64)
+        r = L.orc_zstd_seqdec_golden(tabs[0][0].ctypes.data, tabs[0][1], tabs[1][0].ctypes.data, tabs[1][1],
+                                     tabs[2][0].ctypes.data, tabs[2][1], bits, len(bits), nseq, prev.ctypes.data, win, nlit,
+                                     out.ctypes.data)
+        assert r == 0, (nm, r)
+        rows = [tuple(map(int, ln.split(","))) for ln in zw.read(nm).decode().split()]
+        assert tuple(prev) == rows[0], (nm, tuple(prev), rows[0])
+        want = np.array(rows[1:], dtype=np.int64)
+        assert want.shape == out.shape and (want == out).all(), nm
+        n_files += 1
+    assert n_files == 14
+
+
+def test_header_decode_golden(oracle_lib):
+    """TestHeader_Decode (zstd/decodeheader_test.go): every entry of headers.zip parses to exactly the Header in
+    headers-want.json.zst, or fails when the reference has no entry for it."""
+    import json
+    c = ctypes
+    L = oracle_lib
+    L.orc_zstd_header_decode.restype = c.c_int
+    L.orc_zstd_header_decode.argtypes = [c.c_char_p, c.c_size_t, c.c_void_p]
+    jz = open(os.path.join(H.GOLDEN, "zstd_headers-want.json.zst"), "rb").read()
+    golden = json.loads(H.libzstd_decode(jz, 32 << 20))
+    zh = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_headers.zip"))
+    out = np.zeros(16, dtype=np.uint32)
+    ok = bad = 0
+    for nm in zh.namelist():
+        b = zh.read(nm)
+        r = L.orc_zstd_header_decode(b, len(b), out.ctypes.data)
+        want = golden.get(nm)
+        if r != 0:
+            assert want is None, (nm, r)
+            bad += 1
+            continue
+        assert want is not None, nm
+        o = [int(x) for x in out]
+        got = {"SingleSegment": bool(o[0]), "WindowSize": o[1] | (o[2] << 32), "DictionaryID": o[3], "HasFCS": bool(o[4]),
+               "FrameContentSize": o[5] | (o[6] << 32), "Skippable": bool(o[7]), "SkippableID": o[8], "SkippableSize": o[9],
+               "HeaderSize": o[10],
+               "FirstBlock": {"OK": bool(o[11]), "Last": bool(o[12]), "Compressed": bool(o[13] & 1), "DecompressedSize": o[14],
+                              "CompressedSize": o[15]},
+               "HasCheckSum": bool(o[13] & 2)}
+        assert got == want, (nm, got, want)
+        ok += 1
+    assert ok == len(golden) and ok + bad == len(zh.namelist())
 
 
 def test_good_zip(oracle_lib):

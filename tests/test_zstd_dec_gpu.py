@@ -27,9 +27,10 @@ def _pairs(zf):
             yield nm, zf.read(nm), zf.read(nm[:-4])
 
 
-def test_decoder_zip_subset(dec):
-    # zstd/decoder_test.go:201-216 TestNewDecoder
-    items = list(_pairs(zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_decoder_subset.zip"))))
+def test_decoder_zip_full(dec):
+    # zstd/decoder_test.go:201-216 TestNewDecoder: all 94 pairs of the reference's decoder.zip
+    items = list(_pairs(zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_decoder.zip"))))
+    assert len(items) == 94
     outs, codes = dec.decode_chunks([c for _, c, _ in items], [len(w) + 64 for _, _, w in items])
     for (nm, _, want), got, code in zip(items, outs, codes):
         assert code == len(want) and got == want, (nm, code)
