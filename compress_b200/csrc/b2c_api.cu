@@ -328,7 +328,7 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     CK(cudaSetDevice(ctx->device));
     const uint32_t blockmax = level_block(level);
     const uint64_t pstride = wk_pool_stride(blockmax);
-    const uint32_t subMax = blockmax > 65536 ? 2048u : 4096u;
+    const uint32_t subMax = blockmax > 65536 ? 4096u : 8192u;   // work pool: 2.8 GB (64 KiB blocks) / 3.4 GB (128 KiB blocks)
     const uint32_t sub = nchunks < subMax ? nchunks : subMax;
     if (ctx->work_cap[slot] < sub || ctx->pool_cap[slot] < (size_t)sub * pstride) {
         // grow the per-chunk work records / pool (kernels of earlier calls on other streams may still use the old ones)

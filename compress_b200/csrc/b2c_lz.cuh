@@ -109,6 +109,88 @@ B2C_DEV uint32_t lz_rec_s(const uint2 r) { return r.x & 0x1ffffu; }
 B2C_DEV uint32_t lz_rec_len(const uint2 r) { return (r.x >> 17) | ((r.y >> 16) << 15); }
 B2C_DEV uint32_t lz_rec_d(const uint2 r) { return r.y & 0xffffu; }
 
+// One tile of the dense pass for the four positions 4g .. 4g+3 of this thread (words w0..w2 hold their 11 bytes).
+// GUARD: the tile reaches past the last hashable position (only the last tile of a chunk).
+// A slot is position << 14 | tag, so for a slot r and this position's entry e the difference t = e - r is
+// (distance << 14) exactly when the tags agree and r lies before e: "t & (sign | tag bits) == 0" is the whole
+// acceptance test and t >> 14 the candidate's distance (an empty slot, all ones, can only pass with a distance beyond
+// the position, which the walk rejects).
+template <int LV, bool GUARD>
+B2C_DEV void lz_dense_tile(uint32_t *TS, uint32_t *TL, uint32_t *bm, uint32_t *bml, uint16_t *cd, uint32_t g, uint32_t npos,
+                           uint32_t w0, uint32_t w1, uint32_t w2, unsigned lane) {
+    using C = LzCfg<LV>;
+    constexpr uint32_t BAD = 0x80000000u | LZ_TAGMASK | (C::BLOCK > 65536 ? 0x40000000u : 0u);   // wrong tag, not earlier, or >= 64 KiB away
+    const uint32_t p0 = 4 * g;
+    uint32_t es[4], is[4], fs[4];
+    uint32_t el[4], il[4], fl[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
+        const uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
+        const uint32_t h = C::LONG ? lz_hash5(lo, hi) : lz_hash6(lo, hi);
+        is[j] = h >> (32 - C::TBITS);
+        es[j] = ((p0 + j) << LZ_TAGBITS) | ((h >> 4) & LZ_TAGMASK);
+        fs[j] = TS[is[j]];                                             // far candidate: the slot as earlier tiles left it
+        if constexpr (C::LONG) {
+            const uint32_t hl = lz_hash8(lo, hi);
+            il[j] = hl >> (32 - C::TBITS);
+            el[j] = ((p0 + j) << LZ_TAGBITS) | ((hl >> 4) & LZ_TAGMASK);
+            fl[j] = TL[il[j]];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 3; j >= 0; j--)                                       // the thread's lowest position lands last
+        if (!GUARD || p0 + j < npos) {
+            TS[is[j]] = es[j];
+            if constexpr (C::LONG) TL[il[j]] = el[j];
+        }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (!GUARD || p0 + j < npos) {
+            if (TS[is[j]] > es[j]) atomicMin(&TS[is[j]], es[j]);      // lost a store race: exact minimum of the tile
+            if constexpr (C::LONG) { if (TL[il[j]] > el[j]) atomicMin(&TL[il[j]], el[j]); }
+        }
+    __syncthreads();
+    uint32_t nibA = 0, nibL = 0, dist[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t d = 0;
+        bool ok = false, okL = false;
+        if (!GUARD || p0 + j < npos) {
+            if constexpr (C::LONG) {
+                const uint32_t tn = el[j] - TL[il[j]], tf = el[j] - fl[j];
+                const bool nearOk = (tn & BAD) == 0 && tn != 0;           // near: the tile's earliest equal-hash position, if before this one
+                okL = nearOk || (tf & BAD) == 0;
+                if (okL) d = (nearOk ? tn : tf) >> LZ_TAGBITS;
+            }
+            if (!okL) {
+                const uint32_t tn = es[j] - TS[is[j]], tf = es[j] - fs[j];
+                const bool nearOk = (tn & BAD) == 0 && tn != 0;
+                ok = nearOk || (tf & BAD) == 0;
+                if (ok) d = (nearOk ? tn : tf) >> LZ_TAGBITS;
+            }
+        }
+        dist[j] = d;
+        if (ok || okL) nibA |= 1u << j;
+        if (okL) nibL |= 1u << j;
+    }
+    *reinterpret_cast<uint2 *>(cd + p0) = make_uint2(dist[0] | (dist[1] << 16), dist[2] | (dist[3] << 16));
+    uint32_t word = nibA << (4 * (lane & 7));
+    word |= __shfl_xor_sync(FULLMASK, word, 1);
+    word |= __shfl_xor_sync(FULLMASK, word, 2);
+    word |= __shfl_xor_sync(FULLMASK, word, 4);
+    if ((lane & 7) == 0) bm[g >> 3] = word;
+    if constexpr (C::LONG) {
+        uint32_t wl = nibL << (4 * (lane & 7));
+        wl |= __shfl_xor_sync(FULLMASK, wl, 1);
+        wl |= __shfl_xor_sync(FULLMASK, wl, 2);
+        wl |= __shfl_xor_sync(FULLMASK, wl, 4);
+        if ((lane & 7) == 0) bml[g >> 3] = wl;
+    }
+}
+
 template <int LV>
 B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk, uint8_t *scratch) {
     using C = LzCfg<LV>;
@@ -161,82 +243,16 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
         uint32_t w0 = 0, w1 = 0, w2 = 0;
         if (ntiles) { LZ_WORD(w0, tid); LZ_WORD(w1, tid + 1); LZ_WORD(w2, tid + 2); }
         for (uint32_t k = 0; k < ntiles; k++) {
-            const uint32_t g = k * NT + tid, p0 = 4 * g;
+            const uint32_t g = k * NT + tid;
+            // the next tile's three words are requested before this tile's barriers; whole tiles of an aligned chunk
+            // take the unguarded forms (block-uniform tests)
             uint32_t nw0 = 0, nw1 = 0, nw2 = 0;
-            if (k + 1 < ntiles) { LZ_WORD(nw0, g + NT); LZ_WORD(nw1, g + NT + 1); LZ_WORD(nw2, g + NT + 2); }
-            uint32_t es[4], is[4], fs[4];
-            uint32_t el[4], il[4], fl[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
-                const uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
-                const uint32_t h = C::LONG ? lz_hash5(lo, hi) : lz_hash6(lo, hi);
-                is[j] = h >> (32 - C::TBITS);
-                es[j] = ((p0 + j) << LZ_TAGBITS) | ((h >> 4) & LZ_TAGMASK);
-                fs[j] = TS[is[j]];                                             // far candidate: earlier tiles
-                if constexpr (C::LONG) {
-                    const uint32_t hl = lz_hash8(lo, hi);
-                    il[j] = hl >> (32 - C::TBITS);
-                    el[j] = ((p0 + j) << LZ_TAGBITS) | ((hl >> 4) & LZ_TAGMASK);
-                    fl[j] = TL[il[j]];
-                }
+            if (k + 1 < ntiles) {
+                if (mis == 0 && (k + 2) * NT + 2 < nraw) { nw0 = B2C_LDG(gw + g + NT); nw1 = B2C_LDG(gw + g + NT + 1); nw2 = B2C_LDG(gw + g + NT + 2); }
+                else { LZ_WORD(nw0, g + NT); LZ_WORD(nw1, g + NT + 1); LZ_WORD(nw2, g + NT + 2); }
             }
-            __syncthreads();
-#pragma unroll
-            for (int j = 3; j >= 0; j--)                                       // lowest position of the thread lands last
-                if (p0 + j < npos) {
-                    TS[is[j]] = es[j];
-                    if constexpr (C::LONG) TL[il[j]] = el[j];
-                }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (p0 + j < npos) {
-                    if (TS[is[j]] > es[j]) atomicMin(&TS[is[j]], es[j]);      // lost a store race: exact minimum
-                    if constexpr (C::LONG) { if (TL[il[j]] > el[j]) atomicMin(&TL[il[j]], el[j]); }
-                }
-            __syncthreads();
-            uint32_t nibA = 0, nibL = 0, dist[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t p = p0 + j;
-                uint32_t d = 0;
-                bool ok = false, okL = false;
-                if (p < npos) {
-                    if constexpr (C::LONG) {
-                        const uint32_t r = TL[il[j]];
-                        const bool nearOk = r < el[j] && ((r ^ el[j]) & LZ_TAGMASK) == 0;
-                        const bool farOk = fl[j] < el[j] && ((fl[j] ^ el[j]) & LZ_TAGMASK) == 0;
-                        const uint32_t dd = p - ((nearOk ? r : fl[j]) >> LZ_TAGBITS);
-                        if ((nearOk || farOk) && dd < 65536u) { okL = true; d = dd; }
-                    }
-                    if (!okL) {
-                        const uint32_t r = TS[is[j]];
-                        const bool nearOk = r < es[j] && ((r ^ es[j]) & LZ_TAGMASK) == 0;
-                        const bool farOk = fs[j] < es[j] && ((fs[j] ^ es[j]) & LZ_TAGMASK) == 0;
-                        const uint32_t dd = p - ((nearOk ? r : fs[j]) >> LZ_TAGBITS);
-                        if ((nearOk || farOk) && dd < 65536u) { ok = true; d = dd; }
-                    }
-                }
-                dist[j] = d;
-                if (ok || okL) nibA |= 1u << j;
-                if (okL) nibL |= 1u << j;
-            }
-            *reinterpret_cast<uint2 *>(cd + p0) = make_uint2(dist[0] | (dist[1] << 16), dist[2] | (dist[3] << 16));
-            {
-                uint32_t word = nibA << (4 * (lane & 7));
-                word |= __shfl_xor_sync(FULLMASK, word, 1);
-                word |= __shfl_xor_sync(FULLMASK, word, 2);
-                word |= __shfl_xor_sync(FULLMASK, word, 4);
-                if ((lane & 7) == 0) bm[g >> 3] = word;
-                if constexpr (C::LONG) {
-                    uint32_t wl = nibL << (4 * (lane & 7));
-                    wl |= __shfl_xor_sync(FULLMASK, wl, 1);
-                    wl |= __shfl_xor_sync(FULLMASK, wl, 2);
-                    wl |= __shfl_xor_sync(FULLMASK, wl, 4);
-                    if ((lane & 7) == 0) bml[g >> 3] = wl;
-                }
-            }
+            if (4 * (k + 1) * NT <= npos) lz_dense_tile<LV, false>(TS, TL, bm, bml, cd, g, npos, w0, w1, w2, lane);
+            else lz_dense_tile<LV, true>(TS, TL, bm, bml, cd, g, npos, w0, w1, w2, lane);
             w0 = nw0; w1 = nw1; w2 = nw2;
         }
     }
@@ -479,25 +495,49 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     // writes at most 128 consecutive bytes).  The literal index of a byte is its rank under the mask, which is exactly
     // the order blockEnc.literals has (every sequence's literals precede its match).
     if (kind == 0) {
+        // per-warp staging (the match records are dead): literal bytes are collected in shared memory at the same
+        // 16-byte phase as their destination and leave as 16-byte vectors; only the ragged ends use byte stores
+        constexpr uint32_t STG = (C::SREC * NT * 8) / (NT / 32);        // bytes of staging per warp
+        uint8_t *stg = smem + L::SM_REC + w * STG;
         uint8_t *glit = wk_lit(P, chunk);
-        for (uint32_t i = 0; i < 32; i++) {
+        uint32_t gpos = __shfl_sync(FULLMASK, litEx, 0);                // literal index of staging byte `ph`
+        uint32_t ph = (uint32_t)((reinterpret_cast<uintptr_t>(glit) + gpos) & 15), fill = 0;
+        for (uint32_t i = 0; i <= 32; i++) {
             const uint32_t t = w * 32 + i;
-            if (t * LZ_RANGE >= n) break;
-            const uint32_t base = __shfl_sync(FULLMASK, litEx, (int)i);
+            const bool last = (i == 32) || (t * LZ_RANGE >= n);
+            if (last || ph + fill + 128 > STG) {
+                // flush [gpos, gpos + fill): head bytes up to the first 16-byte boundary, vectors, tail bytes
+                __syncwarp();
+                uint8_t *gd = glit + gpos;
+                const uint32_t head = fill < ((16 - ph) & 15) ? fill : ((16 - ph) & 15);
+                if (lane < head) gd[lane] = stg[ph + lane];
+                const uint32_t nvec = (fill - head) / 16;
+                const uint4 *sv = reinterpret_cast<const uint4 *>(stg + ph + head);
+                uint4 *gv = reinterpret_cast<uint4 *>(gd + head);
+                for (uint32_t v = lane; v < nvec; v += 32) gv[v] = sv[v];
+                const uint32_t done = head + nvec * 16;
+                if (lane < fill - done) gd[done + lane] = stg[ph + done + lane];
+                __syncwarp();
+                gpos += fill; fill = 0;
+                ph = (uint32_t)((reinterpret_cast<uintptr_t>(glit) + gpos) & 15);
+            }
+            if (last) break;
             const uint32_t mw = mask[4 * t + (lane >> 3)];
             const uint32_t nib = (mw >> (4 * (lane & 7))) & 15u;
             const uint32_t c = (uint32_t)__popc(nib);
             const uint32_t incl = warp_scan_incl(c);
-            if (__shfl_sync(FULLMASK, incl, 31) == 0) continue;
+            const uint32_t tot = __shfl_sync(FULLMASK, incl, 31);
+            if (tot == 0) continue;
             const uint32_t v = srcw[32 * t + lane];
             uint32_t packed = 0, k = 0;
 #pragma unroll
             for (int bb = 0; bb < 4; bb++)
                 if ((nib >> bb) & 1) { packed |= ((v >> (8 * bb)) & 0xffu) << (8 * k); k++; }
-            uint8_t *o = glit + base + (incl - c);
+            uint8_t *o = stg + ph + fill + (incl - c);
 #pragma unroll
             for (int bb = 0; bb < 4; bb++)
                 if ((uint32_t)bb < c) o[bb] = (uint8_t)(packed >> (8 * bb));
+            fill += tot;
         }
     }
 #undef REC
@@ -580,45 +620,61 @@ B2C_DEV void zstd_hist_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
     }
     W->litHist[tid] = acc0;
     W->litHist[tid + 128] = acc1;
-    // sequence-code counts
-    uint32_t seqCnt[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    // sequence-code counts: the same private byte counters, one 64-row table per code stream and warp
+    uint32_t cacc = 0, acc1c = 0;                       // code bins tid and tid + 128 (bin = table * 64 + code)
     const uint8_t *codes = wk_codes(P, chunk, 0);
     const uint32_t mseq = P.maxseq;
-    for (uint32_t base = w * 32; base < nseq; base += 4 * HIST_NT) {
-        uint32_t cv3[4][3];
+    for (uint32_t s0 = 0; s0 < nseq; s0 += HIST_SLICE) {
+        const uint32_t s1 = (s0 + HIST_SLICE < nseq) ? s0 + HIST_SLICE : nseq;
+        for (uint32_t i = tid; i < HIST_SMEM_BYTES / 4; i += HIST_NT) reinterpret_cast<uint32_t *>(smem)[i] = 0;
+        __syncthreads();
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t i = base + u * HIST_NT + lane;
-#pragma unroll
-            for (int c = 0; c < 3; c++) cv3[u][c] = (i < nseq) ? (uint32_t)B2C_LDG(codes + c * mseq + i) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const bool valid = base + u * HIST_NT + lane < nseq;
-            if (base + u * HIST_NT < nseq) {      // warp-uniform
-#pragma unroll
-                for (int c = 0; c < 3; c++) warp_hist_acc<6>(cv3[u][c], valid, seqCnt[c], lane);
+        for (int c = 0; c < 3; c++) {
+            uint8_t *ccol = smem + w * 256 * 32 + c * 64 * 32 + lane;
+            const uint32_t w0 = s0 / 4, nl4 = (s1 + 3) / 4;
+            const uint32_t *c32 = reinterpret_cast<const uint32_t *>(codes + (uint32_t)c * mseq);   // maxseq is a multiple of 16
+            for (uint32_t i = w0 + tid; i < nl4; i += HIST_NT) {
+                const uint32_t v = B2C_LDG(c32 + i);
+                const uint32_t nv = (4 * i + 4 <= s1) ? 4u : s1 - 4 * i;
+                const uint32_t a0 = v & 63, a1 = (v >> 8) & 63, a2 = (v >> 16) & 63, a3 = (v >> 24) & 63;
+                uint32_t i0 = 1, i1 = nv > 1, i2 = nv > 2, i3 = nv > 3;
+                if (a1 == a0) { i0 += i1; i1 = 0; }
+                if (a2 == a0) { i0 += i2; i2 = 0; } else if (a2 == a1) { i1 += i2; i2 = 0; }
+                if (a3 == a0) { i0 += i3; i3 = 0; } else if (a3 == a1) { i1 += i3; i3 = 0; } else if (a3 == a2) { i2 += i3; i3 = 0; }
+                const uint32_t c0 = ccol[a0 * 32], c1 = ccol[a1 * 32], c2 = ccol[a2 * 32], c3 = ccol[a3 * 32];
+                ccol[a0 * 32] = (uint8_t)(c0 + i0);
+                if (i1) ccol[a1 * 32] = (uint8_t)(c1 + i1);
+                if (i2) ccol[a2 * 32] = (uint8_t)(c2 + i2);
+                if (i3) ccol[a3 * 32] = (uint8_t)(c3 + i3);
             }
         }
-    }
-    uint32_t *shist = reinterpret_cast<uint32_t *>(smem);      // [HIST_WARPS][192] + 6 words
+        __syncthreads();
+        for (uint32_t i = tid; i < 192; i += HIST_NT) {     // (HIST_NT = 128: two rounds; the accumulator is per (round, thread))
+            uint32_t c = 0;
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        shist[w * 192 + c * 64 + lane] = seqCnt[c][0];
-        shist[w * 192 + c * 64 + 32 + lane] = seqCnt[c][1];
+            for (int k = 0; k < HIST_WARPS; k++) {
+                const uint32_t *row = reinterpret_cast<const uint32_t *>(smem + k * 256 * 32 + i * 32);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    const uint32_t v = row[(jj + (tid >> 2)) & 7];
+                    c += (v & 0xff) + ((v >> 8) & 0xff) + ((v >> 16) & 0xff) + (v >> 24);
+                }
+            }
+            if (i < HIST_NT) cacc += c; else acc1c += c;
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    uint32_t *shist = reinterpret_cast<uint32_t *>(smem);      // 6 ballot words
     for (uint32_t i = tid; i < 192; i += HIST_NT) {
-        uint32_t c = 0;
-        for (int k = 0; k < HIST_WARPS; k++) c += shist[k * 192 + i];
+        const uint32_t c = (i < HIST_NT) ? cacc : acc1c;
         W->seqHist[i / 64][i % 64] = c;
         // highest used code of each table: index groups of 32 are warp-aligned
         const unsigned nz = __ballot_sync(FULLMASK, c != 0);
-        if ((i & 31) == 0) shist[HIST_WARPS * 192 + (i >> 5)] = nz;
+        if ((i & 31) == 0) shist[i >> 5] = nz;
     }
     __syncthreads();
     if (tid < 3) {
-        const uint32_t lo = shist[HIST_WARPS * 192 + 2 * tid], hi = shist[HIST_WARPS * 192 + 2 * tid + 1];
+        const uint32_t lo = shist[2 * tid], hi = shist[2 * tid + 1];
         W->maxSym[tid] = hi ? 32 + (31 - (uint32_t)__clz((int)hi)) : (lo ? 31 - (uint32_t)__clz((int)lo) : 0u);
     }
     __syncthreads();
