@@ -6,6 +6,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <deque>
+#include <chrono>
+#include <atomic>
 #include "../../include/b2c.h"
 #include "b2c_zstd_enc.cuh"
 #include "b2c_lz.cuh"
@@ -51,6 +57,7 @@ struct b2c_ctx {
     uint32_t *d_src_sizes2 = nullptr, *h_src_sizes2 = nullptr;
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream3 = nullptr;
+    uint8_t *h_in2 = nullptr, *h_out2 = nullptr;   // second pinned staging pair: pageable callers of b2c_zstd_encode_packed (lazy)
     cudaEvent_t ev[2] = {nullptr, nullptr};       // compute of the batch in slot s finished
     cudaEvent_t ev_in[2] = {nullptr, nullptr};    // H2D of slot s finished
     cudaEvent_t ev_out[2] = {nullptr, nullptr};   // D2H of slot s finished
@@ -225,7 +232,7 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_pool[0]); cudaFree(ctx->d_pool[1]);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
     cudaFree(ctx->d_sizes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_src_sizes);
-    cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_sizes); cudaFreeHost(ctx->h_src_sizes);
+    cudaFreeHost(ctx->h_in); cudaFreeHost(ctx->h_out); cudaFreeHost(ctx->h_in2); cudaFreeHost(ctx->h_out2); cudaFreeHost(ctx->h_sizes); cudaFreeHost(ctx->h_src_sizes);
     cudaFree(ctx->d_in2); cudaFree(ctx->d_out2); cudaFree(ctx->d_packed2); cudaFree(ctx->d_sizes2);
     cudaFree(ctx->d_offsets2); cudaFree(ctx->d_src_sizes2); cudaFreeHost(ctx->h_sizes2); cudaFreeHost(ctx->h_src_sizes2);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
@@ -498,14 +505,42 @@ int b2c_zstd_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const
 }
 
 
+
+// ---- host-side helpers of the host-buffer calls ---------------------------------------------------------------
+// A Go caller's slices are ordinary (pageable) memory: a cudaMemcpyAsync from them is staged by the driver through a
+// small pinned window and blocks.  The packed call therefore stages pageable buffers itself: several host threads copy
+// into / out of the context's pinned buffers while the copy engines and kernels work on the neighbouring batches.
+static bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    const size_t kMin = 4u << 20;
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = hw ? (hw < 8 ? hw : 8) : 4;
+    if (bytes < 2 * kMin || nt < 2) { memcpy(dst, src, bytes); return; }
+    if ((size_t)nt * kMin > bytes) nt = (unsigned)(bytes / kMin);
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) {
+        const size_t lo = (size_t)t * per;
+        if (lo >= bytes) break;
+        const size_t len = (lo + per <= bytes && t + 1 < nt) ? per : bytes - lo;
+        th.emplace_back([=]() { memcpy((uint8_t *)dst + lo, (const uint8_t *)src + lo, len); });
+    }
+    memcpy(dst, src, per < bytes ? per : bytes);
+    for (auto &x : th) x.join();
+}
+
 // Contiguous host input -> packed host output (concatenated frames).  Three streams (H2D, kernels, D2H) and two
 // buffer slots: the H2D copy of batch b+1 and the D2H copy of batch b-1 overlap the kernels of batch b.  This is the
 // shape of a large EncodeAll / of a WithConcurrentBlocks job (zstd/enc_jobs.go): the caller gets one valid zstd
 // stream plus the per-chunk frame table.  h_src / h_dst should be pinned (cudaHostRegister / torch pin_memory)
 // for full PCIe rate; pageable memory works but is staged by the driver.
-int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src, size_t src_bytes,
-                           uint32_t chunk_size, void *h_dst, size_t dst_cap, int64_t *sizes_out,
-                           uint64_t *offsets_out, size_t *total_out) {
+static int encode_packed_impl(b2c_ctx *ctx, int level, int flags, const void *h_src, size_t src_bytes,
+                              uint32_t chunk_size, void *h_dst, size_t dst_cap, int64_t *sizes_out,
+                              uint64_t *offsets_out, size_t *total_out) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     if (!level_ok(level)) return B2C_ERR_UNSUPPORTED;
     const size_t blk = level_block(level), slotB = level_slot(level);
@@ -533,6 +568,23 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
     }
     const size_t nb = bcount.size();
     cudaStream_t st_c = ctx->stream, st_in = ctx->stream2, st_out = ctx->stream3;
+    // pageable caller memory is staged through the context's pinned buffers (see parallel_memcpy above)
+    const bool stage_in = src_bytes > 0 && !host_ptr_is_pinned(h_src);
+    const bool stage_out = !host_ptr_is_pinned(h_dst);
+    if ((stage_in && !ctx->h_in2) || (stage_out && !ctx->h_out2)) {
+        if (!ctx->h_in2) CK(cudaMallocHost(&ctx->h_in2, ctx->max_chunks * (size_t)ENC_MAX_CHUNK));
+        if (!ctx->h_out2) CK(cudaMallocHost(&ctx->h_out2, ctx->max_chunks * (size_t)kSlot));
+    }
+    uint8_t *stg_in[2] = {ctx->h_in, ctx->h_in2}, *stg_out[2] = {ctx->h_out, ctx->h_out2};
+    struct Pending { bool live; uint64_t pos, bytes; } pend[2] = {{false, 0, 0}, {false, 0, 0}};
+    // a staged D2H copy of slot sl has landed in pinned memory: hand it to the caller's buffer
+    auto drain = [&](int sl) -> int {
+        if (!pend[sl].live) return B2C_OK;
+        if (cudaEventSynchronize(ctx->ev_out[sl]) != cudaSuccess) return B2C_ERR_CUDA;
+        parallel_memcpy((uint8_t *)h_dst + pend[sl].pos, stg_out[sl], pend[sl].bytes);
+        pend[sl].live = false;
+        return B2C_OK;
+    };
     struct Slot { uint8_t *d_in, *d_out, *d_packed; int64_t *d_sizes, *h_sizes; uint64_t *d_off;
                   uint32_t *d_ss, *h_ss; } slot[2] = {
         {ctx->d_in, ctx->d_out, ctx->d_packed, ctx->d_sizes, ctx->h_sizes, ctx->d_offsets, ctx->d_src_sizes, ctx->h_src_sizes},
@@ -549,9 +601,14 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
         const uint64_t *h_off = reinterpret_cast<const uint64_t *>(S.h_sizes + m);
         uint64_t total = h_off[m];
         if (out_pos + total > dst_cap) return B2C_ERR_DST_SMALL;
-        if (cudaMemcpyAsync((uint8_t *)h_dst + out_pos, S.d_packed, total, cudaMemcpyDeviceToHost, st_out) != cudaSuccess)
+        if (stage_out) {
+            { int rd = drain(sl); if (rd) return rd; }            // the slot's pinned buffer still holds batch b-2
+            if (cudaMemcpyAsync(stg_out[sl], S.d_packed, total, cudaMemcpyDeviceToHost, st_out) != cudaSuccess) return B2C_ERR_CUDA;
+            pend[sl].live = true; pend[sl].pos = out_pos; pend[sl].bytes = total;
+        } else if (cudaMemcpyAsync((uint8_t *)h_dst + out_pos, S.d_packed, total, cudaMemcpyDeviceToHost, st_out) != cudaSuccess)
             return B2C_ERR_CUDA;
         if (cudaEventRecord(ctx->ev_out[sl], st_out) != cudaSuccess) return B2C_ERR_CUDA;
+        if (stage_out) { int rd = drain(sl ^ 1); if (rd) return rd; }   // batch b-1's bytes have had a whole batch to arrive
         for (size_t i = 0; i < m; i++) {
             sizes_out[c0 + i] = h_sz[i];
             if (offsets_out) offsets_out[c0 + i] = out_pos + h_off[i];
@@ -569,7 +626,13 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
         size_t off = c0 * (size_t)chunk_size;
         size_t bytes = (off + m * (size_t)chunk_size <= src_bytes) ? m * (size_t)chunk_size : src_bytes - off;
         if (b >= 2) CK(cudaStreamWaitEvent(st_in, ctx->ev[sl], 0));
-        if (bytes) CK(cudaMemcpyAsync(S.d_in, (const uint8_t *)h_src + off, bytes, cudaMemcpyHostToDevice, st_in));
+        const uint8_t *from = (const uint8_t *)h_src + off;
+        if (stage_in && bytes) {
+            if (b >= 2) CK(cudaEventSynchronize(ctx->ev_in[sl]));      // the H2D copy of batch b-2 has left the pinned buffer
+            parallel_memcpy(stg_in[sl], from, bytes);
+            from = stg_in[sl];
+        }
+        if (bytes) CK(cudaMemcpyAsync(S.d_in, from, bytes, cudaMemcpyHostToDevice, st_in));
         if (bytes != m * (size_t)chunk_size) {  // ragged last chunk (or empty input): explicit sizes
             for (size_t i = 0; i < m; i++) {
                 size_t o = i * (size_t)chunk_size;
@@ -608,7 +671,23 @@ int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src
     CK(cudaStreamSynchronize(st_in));
     CK(cudaStreamSynchronize(st_c));
     CK(cudaStreamSynchronize(st_out));
+    { int rd = drain(0); if (rd) return rd; }
+    { int rd = drain(1); if (rd) return rd; }
     if (total_out) *total_out = out_pos;
+    return rc;
+}
+
+int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src, size_t src_bytes,
+                           uint32_t chunk_size, void *h_dst, size_t dst_cap, int64_t *sizes_out,
+                           uint64_t *offsets_out, size_t *total_out) {
+    const int rc = encode_packed_impl(ctx, level, flags, h_src, src_bytes, chunk_size, h_dst, dst_cap, sizes_out, offsets_out,
+                                      total_out);
+    if (rc != B2C_OK && ctx && ctx->stream) {
+        // an error return must not leave copies in flight that read h_src / write h_dst, nor the slots mid-pipeline
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream3);
+    }
     return rc;
 }
 
@@ -863,6 +942,125 @@ int b2c_huf_decompress_device(b2c_ctx *ctx, int flags, const void *d_src, size_t
     b2c_huf_decompress_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, (cudaStream_t)stream>>>(P);
     ctx->launches += 1;
     CK(cudaGetLastError());
+    return B2C_OK;
+}
+
+// ---- coalescing queue ---------------------------------------------------------------------------------------------
+// The reference's seams are one block per call from many goroutines at once: zstd.Encoder.EncodeAll "can be called
+// concurrently" (zstd/encoder.go:717-729), s2.WriterCustomEncoder's hook runs on one goroutine per block
+// (s2/writer.go:1052-1064, call sites :455-461), Decoder.DecodeAll likewise.  A GPU wants batches.  b2c_queue is the
+// piece of the shim that turns the former into the latter: callers block in b2c_queue_*; one dispatcher thread owns
+// the context, collects what is pending (lingering a few microseconds for stragglers), issues ONE *_chunks call per
+// kind of request and wakes the callers with their results.  Caller memory is only touched during the call.
+struct b2c_req {
+    int op, level, flags;                 // op: 0 zstd encode, 1 s2 encode, 2 zstd decode, 3 s2 decode
+    const void *src; size_t n; void *dst; size_t cap;
+    int64_t result; bool done;
+};
+struct b2c_queue {
+    b2c_ctx *ctx = nullptr;
+    size_t max_batch = 0;
+    unsigned linger_us = 0;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<b2c_req *> pending;
+    bool stop = false;
+    std::thread worker;
+    std::atomic<uint64_t> calls{0}, batches{0};
+};
+
+static void queue_run_batch(b2c_queue *q, std::vector<b2c_req *> &grp) {
+    const size_t m = grp.size();
+    std::vector<const void *> srcs(m);
+    std::vector<void *> dsts(m);
+    std::vector<size_t> ssz(m), dcap(m);
+    std::vector<int64_t> res(m, 0);
+    for (size_t i = 0; i < m; i++) { srcs[i] = grp[i]->src; ssz[i] = grp[i]->n; dsts[i] = grp[i]->dst; dcap[i] = grp[i]->cap; }
+    const b2c_req *r0 = grp[0];
+    int rc;
+    switch (r0->op) {
+    case 0: rc = b2c_zstd_encode_chunks(q->ctx, r0->level, r0->flags, srcs.data(), ssz.data(), dsts.data(), dcap.data(), res.data(), m); break;
+    case 1: rc = b2c_s2_encode_chunks(q->ctx, r0->level, r0->flags, srcs.data(), ssz.data(), dsts.data(), dcap.data(), res.data(), m); break;
+    case 2: rc = b2c_zstd_decode_chunks(q->ctx, srcs.data(), ssz.data(), dsts.data(), dcap.data(), res.data(), m); break;
+    default: rc = b2c_s2_decode_chunks(q->ctx, srcs.data(), ssz.data(), dsts.data(), dcap.data(), res.data(), m); break;
+    }
+    for (size_t i = 0; i < m; i++) grp[i]->result = rc ? (int64_t)rc : res[i];
+    q->batches++;
+}
+
+static void queue_worker(b2c_queue *q) {
+    cudaSetDevice(q->ctx->device);
+    std::unique_lock<std::mutex> lk(q->mu);
+    for (;;) {
+        q->cv_work.wait(lk, [&] { return q->stop || !q->pending.empty(); });
+        if (q->pending.empty()) { if (q->stop) return; continue; }
+        if (q->linger_us && q->pending.size() < q->max_batch && !q->stop)   // give concurrent callers a moment to arrive
+            q->cv_work.wait_for(lk, std::chrono::microseconds(q->linger_us), [&] { return q->stop || q->pending.size() >= q->max_batch; });
+        std::vector<b2c_req *> take;
+        while (!q->pending.empty() && take.size() < q->max_batch) { take.push_back(q->pending.front()); q->pending.pop_front(); }
+        lk.unlock();
+        // one device batch per kind of request, in arrival order of the kinds
+        std::vector<char> used(take.size(), 0);
+        for (size_t i = 0; i < take.size(); i++) {
+            if (used[i]) continue;
+            std::vector<b2c_req *> grp;
+            for (size_t j = i; j < take.size(); j++)
+                if (!used[j] && take[j]->op == take[i]->op && take[j]->level == take[i]->level && take[j]->flags == take[i]->flags) {
+                    grp.push_back(take[j]); used[j] = 1;
+                }
+            queue_run_batch(q, grp);
+        }
+        lk.lock();
+        for (b2c_req *r : take) r->done = true;
+        q->cv_done.notify_all();
+    }
+}
+
+static int64_t queue_call(b2c_queue *q, int op, int level, int flags, const void *src, size_t n, void *dst, size_t cap) {
+    if (!q) return B2C_ERR_NO_DEVICE;
+    b2c_req r{op, level, flags, src, n, dst, cap, 0, false};
+    std::unique_lock<std::mutex> lk(q->mu);
+    if (q->stop) return B2C_ERR_ARG;
+    q->pending.push_back(&r);
+    q->calls++;
+    q->cv_work.notify_one();
+    q->cv_done.wait(lk, [&] { return r.done; });
+    return r.result;
+}
+
+b2c_queue *b2c_queue_create(int device, size_t max_batch, unsigned linger_us) {
+    if (max_batch == 0) max_batch = 1024;
+    b2c_ctx *ctx = b2c_ctx_create(device, max_batch);
+    if (!ctx) return nullptr;
+    b2c_queue *q = new b2c_queue();
+    q->ctx = ctx; q->max_batch = max_batch; q->linger_us = linger_us;
+    q->worker = std::thread(queue_worker, q);
+    return q;
+}
+void b2c_queue_destroy(b2c_queue *q) {
+    if (!q) return;
+    { std::lock_guard<std::mutex> lk(q->mu); q->stop = true; }
+    q->cv_work.notify_all();
+    if (q->worker.joinable()) q->worker.join();
+    b2c_ctx_destroy(q->ctx);
+    delete q;
+}
+int64_t b2c_queue_zstd_encode(b2c_queue *q, int level, int flags, const void *src, size_t n, void *dst, size_t cap) {
+    return queue_call(q, 0, level, flags, src, n, dst, cap);
+}
+int64_t b2c_queue_s2_encode(b2c_queue *q, int level, int flags, const void *src, size_t n, void *dst, size_t cap) {
+    return queue_call(q, 1, level, flags, src, n, dst, cap);
+}
+int64_t b2c_queue_zstd_decode(b2c_queue *q, const void *src, size_t n, void *dst, size_t cap) {
+    return queue_call(q, 2, 0, 0, src, n, dst, cap);
+}
+int64_t b2c_queue_s2_decode(b2c_queue *q, const void *src, size_t n, void *dst, size_t cap) {
+    return queue_call(q, 3, 0, 0, src, n, dst, cap);
+}
+int b2c_queue_stats(b2c_queue *q, uint64_t *calls, uint64_t *batches) {
+    if (!q) return B2C_ERR_NO_DEVICE;
+    if (calls) *calls = q->calls.load();
+    if (batches) *batches = q->batches.load();
     return B2C_OK;
 }
 

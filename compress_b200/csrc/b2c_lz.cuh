@@ -45,7 +45,7 @@ template <> struct LzCfg<1> {
     static constexpr uint32_t BLOCK = 65536;
     static constexpr bool LONG = false;
     static constexpr uint32_t TBITS = 14;
-    static constexpr uint32_t SREC = 6;       // match records per thread kept in shared memory
+    static constexpr uint32_t KREC = 16;      // match records (4 bytes each) per thread kept in shared memory
     static constexpr int MIN_CTAS = 2;
 };
 template <> struct LzCfg<2> {
@@ -53,7 +53,7 @@ template <> struct LzCfg<2> {
     static constexpr uint32_t BLOCK = 131072;
     static constexpr bool LONG = true;
     static constexpr uint32_t TBITS = 14;
-    static constexpr uint32_t SREC = 4;
+    static constexpr uint32_t KREC = 8;
     static constexpr int MIN_CTAS = 1;
 };
 
@@ -68,12 +68,13 @@ template <int LV> struct LzLayout {
     static constexpr uint32_t SM_BM = SM_A + A_BYTES;
     static constexpr uint32_t SM_BML = SM_BM + BM_BYTES;
     static constexpr uint32_t SM_REC = SM_BML + (C::LONG ? BM_BYTES : 0);
-    static constexpr uint32_t SM_ARR = SM_REC + C::SREC * C::NT * 8;            // keptEnd u32 | lastOff u32 | cnt u8 | cap u8
-    static constexpr uint32_t SM_SH = SM_ARR + C::NT * 10;
+    static constexpr uint32_t REC_BYTES = C::KREC * C::NT * 4;
+    static constexpr uint32_t SM_ARR = SM_REC + REC_BYTES;                      // keptEnd u32 | lastOff u32 | longLen u32 | cnt u8 | cap u8
+    static constexpr uint32_t SM_SH = SM_ARR + C::NT * 14;
     static constexpr uint32_t SMEM_BYTES = SM_SH + ((sizeof(ParseShared) + 2 * 80 * 4 + 15) / 16) * 16;
     // per-CTA global scratch: candidate distances (u16 per position) + spilled match records [k][thread]
     static constexpr uint32_t DIST_BYTES = C::BLOCK * 2;
-    static constexpr uint32_t SCRATCH_BYTES = DIST_BYTES + (LZ_MAXREC - C::SREC) * C::NT * 8;
+    static constexpr uint32_t SCRATCH_BYTES = DIST_BYTES + (LZ_MAXREC - C::KREC) * C::NT * 4;
 };
 static_assert(2 * (LzLayout<1>::SMEM_BYTES + 1024) <= 228 * 1024, "two level-1 parse CTAs must fit one SM");
 static_assert(LzLayout<2>::SMEM_BYTES <= 227 * 1024, "the level-2 parse CTA must fit one SM");
@@ -103,11 +104,14 @@ B2C_DEV void group_scan_excl_pair(uint32_t a, uint32_t b, uint32_t *ws, int nthr
     *totA = ws[32]; *totB = ws[72];
 }
 
-// match record: start (17 bits) | low 15 length bits; distance (16 bits) | high length bits
-B2C_DEV uint2 lz_rec(uint32_t s, uint32_t len, uint32_t d) { return make_uint2(s | ((len & 0x7fffu) << 17), d | ((len >> 15) << 16)); }
-B2C_DEV uint32_t lz_rec_s(const uint2 r) { return r.x & 0x1ffffu; }
-B2C_DEV uint32_t lz_rec_len(const uint2 r) { return (r.x >> 17) | ((r.y >> 16) << 15); }
-B2C_DEV uint32_t lz_rec_d(const uint2 r) { return r.y & 0xffffu; }
+// match record of a thread (4 bytes, never rewritten): start - range start (7 bits) | length << 7 (9 bits: the walk caps
+// a match at 256 bytes forwards and 127 backwards) | distance << 16.  A match that warp 0 finished keeps its walked
+// length here and its full length in longLen[thread].  Trimming against earlier threads is applied when a record is
+// read (it only needs the thread's R), so the records are written once.
+B2C_DEV uint32_t lz_rec(uint32_t rel, uint32_t len, uint32_t d) { return rel | (len << 7) | (d << 16); }
+B2C_DEV uint32_t lz_rec_rel(uint32_t r) { return r & 127u; }
+B2C_DEV uint32_t lz_rec_len(uint32_t r) { return (r >> 7) & 511u; }
+B2C_DEV uint32_t lz_rec_d(uint32_t r) { return r >> 16; }
 
 // One tile of the dense pass for the four positions 4g .. 4g+3 of this thread (words w0..w2 hold their 11 bytes).
 // GUARD: the tile reaches past the last hashable position (only the last tile of a chunk).
@@ -295,21 +299,22 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     // extend forwards / backwards, emit, skip past the match.  Threads never communicate (bitmaps, distances and the
     // chunk are read-only here), so the parse does not depend on scheduling.  A match may run past the end of the
     // range; the merge step trims whatever a later thread found inside it.
-    // record k of thread t (k < SREC in shared memory, the rest in the per-CTA scratch): see lz_rec()
-    uint2 *recS = reinterpret_cast<uint2 *>(smem + L::SM_REC);
-    uint2 *recG = reinterpret_cast<uint2 *>(scratch + L::DIST_BYTES);
-#define REC(k, t) (*(((k) < C::SREC) ? &recS[(k) * NT + (t)] : &recG[((k) - C::SREC) * NT + (t)]))
+    // record k of thread t (k < KREC in shared memory, the rest in the per-CTA scratch): see lz_rec()
+    uint32_t *recS = reinterpret_cast<uint32_t *>(smem + L::SM_REC);
+    uint32_t *recG = reinterpret_cast<uint32_t *>(scratch + L::DIST_BYTES);
+#define REC(k, t) (*(((k) < C::KREC) ? &recS[(k) * NT + (t)] : &recG[((k) - C::KREC) * NT + (t)]))
     uint32_t *keptEndA = reinterpret_cast<uint32_t *>(smem + L::SM_ARR);
     uint32_t *lastOffA = keptEndA + NT;
-    uint8_t *cntA = reinterpret_cast<uint8_t *>(lastOffA + NT);
+    uint32_t *longLen = lastOffA + NT;          // full length of a thread's last record when warp 0 finished it, else 0
+    uint8_t *cntA = reinterpret_cast<uint8_t *>(longLen + NT);
     uint8_t *capA = cntA + NT;
     const uint32_t nlanes = (n + LZ_RANGE - 1) / LZ_RANGE;
     const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
+    const uint32_t b = tid * LZ_RANGE;                                   // this thread's range [b, e)
+    const uint32_t e = (b + LZ_RANGE < n) ? b + LZ_RANGE : n;
     uint32_t cnt = 0, lastE = 0;
     bool capped = false;
     {
-        const uint32_t b = tid * LZ_RANGE;
-        const uint32_t e = (b + LZ_RANGE < n) ? b + LZ_RANGE : n;
         const uint32_t pend = (tid < nlanes) ? (e < npos ? e : npos) : 0u;
         uint32_t p = b, nextEmit = b;
         while (p < pend) {
@@ -350,7 +355,7 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
             capped = cp;
             uint32_t s = p, t = cand;
             while (s > nextEmit && t > 0 && src[s - 1] == src[t - 1]) { s--; t--; len++; }
-            REC(cnt, tid) = lz_rec(s, len, d);
+            REC(cnt, tid) = lz_rec(s - b, len, d);
             cnt++;
             p = s + len;
             nextEmit = p;
@@ -360,6 +365,7 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     B2C_PHASE(6);
     cntA[tid] = (uint8_t)cnt;
     capA[tid] = (uint8_t)((cnt != 0) && capped);
+    longLen[tid] = 0;
     __syncthreads();
     // long matches: warp 0 walks the capped records in order and finishes them cooperatively (128 bytes per step);
     // a capped record that already lies inside an earlier finished one is skipped, so a chunk of zeros costs one pass
@@ -371,34 +377,36 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
             while (m) {
                 const uint32_t tt = base + (uint32_t)(__ffs((int)m) - 1);
                 m &= m - 1;
-                const uint32_t kk = (uint32_t)cntA[tt] - 1;
-                const uint2 r = REC(kk, tt);
-                const uint32_t s0 = lz_rec_s(r), l0 = lz_rec_len(r), d0 = lz_rec_d(r);
+                const uint32_t r = REC((uint32_t)cntA[tt] - 1, tt);
+                const uint32_t s0 = tt * LZ_RANGE + lz_rec_rel(r), l0 = lz_rec_len(r), d0 = lz_rec_d(r);
                 const uint32_t e0 = s0 + l0;
                 if (e0 > covered) {
                     const uint32_t ext = warp_match_len(src, e0, e0 - d0, n);
-                    if (lane == 0) REC(kk, tt) = lz_rec(s0, l0 + ext, d0);
+                    if (lane == 0) longLen[tt] = l0 + ext;
                     covered = e0 + ext;
                 }
             }
         }
     }
     __syncthreads();
-    if (capped && cnt) { const uint2 r = REC(cnt - 1, tid); lastE = lz_rec_s(r) + lz_rec_len(r); }
+    const uint32_t myLong = longLen[tid];
+    if (myLong) lastE = b + lz_rec_rel(REC(cnt - 1, tid)) + myLong;
     B2C_PHASE(3);
 
     // ---------------------------------------------------------------- P4: merge (trim overlaps), global layout
     uint32_t dummyTotal;
     const uint32_t R = group_scan_excl_max(lastE, sh->ws, 0, NT, tid, &dummyTotal);   // everything before R is taken
     B2C_PHASE(8);
-    uint32_t kept = 0, sumLen = 0, keptE = 0, lastOff = 0;
+    // A record survives when at least 4 of its bytes lie behind R; the dropped ones are a prefix of the thread's records
+    // (records are ordered and disjoint), so the kept ones are firstKept .. cnt-1, the first of them possibly trimmed.
+    uint32_t kept = 0, firstKept = cnt, sumLen = 0, keptE = 0, lastOff = 0;
     for (uint32_t j = 0; j < cnt; j++) {
-        const uint2 r = REC(j, tid);
-        const uint32_t s0 = lz_rec_s(r), e0 = s0 + lz_rec_len(r);
+        const uint32_t r = REC(j, tid);
+        const uint32_t s0 = b + lz_rec_rel(r), e0 = s0 + ((j + 1 == cnt && myLong) ? myLong : lz_rec_len(r));
         if (e0 <= R) continue;
         const uint32_t s2 = s0 > R ? s0 : R, l2 = e0 - s2;
         if (l2 < 4) continue;
-        REC(kept, tid) = lz_rec(s2, l2, lz_rec_d(r));
+        if (kept == 0) firstKept = j;
         kept++; sumLen += l2; keptE = e0; lastOff = lz_rec_d(r);
     }
     B2C_PHASE(9);
@@ -414,8 +422,6 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     const uint32_t nlit = n - sumAll;
     const uint32_t prevE0 = keyEx ? keptEndA[keyEx - 1] : 0u;          // end of the sequence before this thread's first
     const uint32_t pOff0 = keyEx ? lastOffA[keyEx - 1] : 0u;
-    const uint32_t lastEnd = keyTotal ? keptEndA[keyTotal - 1] : 0u;  // end of the last sequence of the chunk
-    (void)lastEnd;
 
     // blockEnc.encode early decisions (blockenc.go:481-503): no sequences => literals-only (raw) block; then the
     // single-sequence RLE test; then `saved < 16` => raw
@@ -425,12 +431,11 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     else if (nseq != 1 && saved < 16) kind = 1;
     if (nseq > mseq) kind = 1;      // cannot happen (mseq >= BLOCK / 4); keeps the arrays safe
 
-    // ---------------------------------------------------------------- P5: sequences, codes, literal mask
+    // ---------------------------------------------------------------- P5: literal mask, sequences, codes
     uint32_t *mask = bm;     // one bit per position: 1 = literal.  Thread t owns the four words of its own range.
     uint32_t myLit = 0;
     if (kind == 0 || (P.dbg_hdr && nseq <= mseq)) {      // (the parity tests also want the sequences of blocks stored raw)
-        const uint32_t b = tid * LZ_RANGE;
-        const uint32_t e = (b + LZ_RANGE < n) ? b + LZ_RANGE : n;
+        // -- per thread: the four mask words of the own range
         uint32_t m4[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
@@ -453,26 +458,61 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
             }                                                                                             \
         }                                                                                                 \
     } while (0)
-        // the part of this range covered by the last kept match of the earlier threads
-        LZ_CLEAR(b, prevE0);
-        uint32_t prevE = prevE0, pOff = pOff0, gi = seqEx;
-        for (uint32_t j = 0; j < kept; j++) {
-            const uint2 r = REC(j, tid);
-            const uint32_t s0 = lz_rec_s(r), l0 = lz_rec_len(r), d0 = lz_rec_d(r);
-            const uint32_t ll = s0 - prevE;
-            LZ_CLEAR(s0, s0 + l0);
-            // repeat code 1 (= offset of the previous sequence, valid with litLen > 0; seqdec.go:463-500)
-            const bool isrep = (gi > 0) && (d0 == pOff) && (ll > 0);
-            const uint32_t ofv = isrep ? 1u : d0 + 3;
-            wlen.put(gi, ll, l0 - 3); wof[gi] = ofv;
-            wcodes[TBL_LL * mseq + gi] = (uint8_t)seq_ll_code(ll);
-            wcodes[TBL_OF * mseq + gi] = (uint8_t)highbit32(ofv);
-            wcodes[TBL_ML * mseq + gi] = (uint8_t)seq_ml_code(l0 - 3);
-            prevE = s0 + l0; pOff = d0; gi++;
+        LZ_CLEAR(b, prevE0);              // the part of this range covered by the last kept match of the earlier threads
+        for (uint32_t j = firstKept; j < cnt; j++) {
+            const uint32_t r = REC(j, tid);
+            const uint32_t s0 = b + lz_rec_rel(r), e0 = s0 + ((j + 1 == cnt && myLong) ? myLong : lz_rec_len(r));
+            LZ_CLEAR(s0 > R ? s0 : R, e0);
         }
 #undef LZ_CLEAR
 #pragma unroll
         for (int k = 0; k < 4; k++) { mask[4 * tid + k] = m4[k]; myLit += (uint32_t)__popc(m4[k]); }
+
+        // -- per warp: the kept records of the 32 lanes, flattened, 32 sequences per step, so that every store of the
+        //    step is one coalesced access (lane l handles flat index f + l; its owner lane is found by a binary search
+        //    over the lanes' exclusive counts; the previous sequence's end and offset come from the neighbouring lane)
+        {
+            const uint32_t incl = warp_scan_incl(kept), excl = incl - kept;
+            const uint32_t total = __shfl_sync(FULLMASK, incl, 31);
+            const uint32_t gbase = __shfl_sync(FULLMASK, seqEx, 0);
+            uint32_t carryE = __shfl_sync(FULLMASK, prevE0, 0), carryD = __shfl_sync(FULLMASK, pOff0, 0);
+            for (uint32_t f0 = 0; f0 < total; f0 += 32) {
+                const uint32_t f = f0 + lane;
+                const bool live = f < total;
+                uint32_t o = 0;                        // owner: the largest lane whose exclusive count is <= f
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1) {
+                    const uint32_t c = o + st;
+                    const uint32_t v = __shfl_sync(FULLMASK, excl, (int)(c & 31));
+                    if (c < 32 && v <= f) o = c;
+                }
+                const uint32_t oExcl = __shfl_sync(FULLMASK, excl, (int)o), oFirst = __shfl_sync(FULLMASK, firstKept, (int)o);
+                const uint32_t oCnt = __shfl_sync(FULLMASK, cnt, (int)o), oLong = __shfl_sync(FULLMASK, myLong, (int)o);
+                const uint32_t oR = __shfl_sync(FULLMASK, R, (int)o);
+                uint32_t s2 = 0, e0 = 0, d0 = 0;
+                if (live) {
+                    const uint32_t ot = (tid & ~31u) + o, j = oFirst + (f - oExcl);
+                    const uint32_t r = REC(j, ot);
+                    const uint32_t s0 = ot * LZ_RANGE + lz_rec_rel(r);
+                    e0 = s0 + ((j + 1 == oCnt && oLong) ? oLong : lz_rec_len(r));
+                    s2 = s0 > oR ? s0 : oR;
+                    d0 = lz_rec_d(r);
+                }
+                uint32_t pe = __shfl_up_sync(FULLMASK, e0, 1), pd = __shfl_up_sync(FULLMASK, d0, 1);
+                if (lane == 0) { pe = carryE; pd = carryD; }
+                if (live) {
+                    const uint32_t gi = gbase + f, ll = s2 - pe, l2 = e0 - s2;
+                    // repeat code 1 (= offset of the previous sequence, valid with litLen > 0; seqdec.go:463-500)
+                    const bool isrep = (gi > 0) && (d0 == pd) && (ll > 0);
+                    const uint32_t ofv = isrep ? 1u : d0 + 3;
+                    wlen.put(gi, ll, l2 - 3); wof[gi] = ofv;
+                    wcodes[TBL_LL * mseq + gi] = (uint8_t)seq_ll_code(ll);
+                    wcodes[TBL_OF * mseq + gi] = (uint8_t)highbit32(ofv);
+                    wcodes[TBL_ML * mseq + gi] = (uint8_t)seq_ml_code(l2 - 3);
+                }
+                carryE = __shfl_sync(FULLMASK, e0, 31); carryD = __shfl_sync(FULLMASK, d0, 31);
+            }
+        }
     }
     B2C_PHASE(11);
     if (tid == 0) { sh->kind = kind; sh->rleLen = 0; }
@@ -497,7 +537,7 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     if (kind == 0) {
         // per-warp staging (the match records are dead): literal bytes are collected in shared memory at the same
         // 16-byte phase as their destination and leave as 16-byte vectors; only the ragged ends use byte stores
-        constexpr uint32_t STG = (C::SREC * NT * 8) / (NT / 32);        // bytes of staging per warp
+        constexpr uint32_t STG = L::REC_BYTES / (NT / 32);               // bytes of staging per warp
         uint8_t *stg = smem + L::SM_REC + w * STG;
         uint8_t *glit = wk_lit(P, chunk);
         uint32_t gpos = __shfl_sync(FULLMASK, litEx, 0);                // literal index of staging byte `ph`

@@ -31,3 +31,50 @@ def max_over_ranks(values, device="cpu"):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return [float(x) for x in t]
+
+
+# ---- host placement: one process per GPU, bound to the GPU's NUMA node -----------------------------------------
+def _parse_cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus += list(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def gpu_numa_node(pci_bus_id, sysfs="/sys"):
+    """NUMA node of a GPU from its PCI address ("0000:1b:00.0"); None when the platform does not say (-1 / missing)."""
+    import os
+    bdf = pci_bus_id.lower()
+    if len(bdf.split(":")[0]) == 8:          # nvidia-smi style 00000000:1B:00.0
+        bdf = bdf[4:]
+    try:
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")).read())
+    except (OSError, ValueError):
+        return None
+    return node if node >= 0 else None
+
+
+def bind_to_gpu_numa(pci_bus_id, sysfs="/sys"):
+    """Restrict this process (and the pinned buffers it allocates from now on: first touch) to the CPUs of the
+    GPU's NUMA node, intersected with the CPUs it is allowed to use.  The end-to-end path is bound by host-memory
+    traffic of the H2D/D2H copies; with 8 ranks on a two-socket box an unbound rank copies across the socket link.
+    Returns the node, or None when nothing was changed."""
+    import os
+    node = gpu_numa_node(pci_bus_id, sysfs)
+    if node is None or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        cpus = set(_parse_cpulist(open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)).read()))
+    except OSError:
+        return None
+    allowed = cpus & set(os.sched_getaffinity(0))
+    if not allowed:
+        return None
+    os.sched_setaffinity(0, allowed)
+    return node

@@ -272,3 +272,58 @@ class Decoder:
             dst += outs[0]
             return dst
         return outs[0]
+
+
+# ---- coalescing queue (the shim's batching of concurrent one-block calls) ----------------------------------------
+class Queue:
+    """Thread-safe, blocking per-block calls batched onto one GPU by a dispatcher thread inside libb200comp.so
+    (include/b2c.h, b2c_queue_*): what a cgo shim puts behind concurrent ``Encoder.EncodeAll`` calls
+    (zstd/encoder.go:717-729), ``Decoder.DecodeAll`` calls and s2's ``WriterCustomEncoder`` hook
+    (s2/writer.go:1052-1064).  ctypes releases the GIL during the call, so Python threads exercise real concurrency."""
+
+    def __init__(self, device=0, max_batch=1024, linger_us=200):
+        if not torch.cuda.is_available() or lib.b2c_device_count() == 0:
+            raise B2CError("no CUDA device: compress_b200 has no CPU fallback")
+        self._q = lib.b2c_queue_create(device, max_batch, linger_us)
+        if not self._q:
+            raise B2CError("b2c_queue_create failed")
+
+    def close(self):
+        if self._q:
+            lib.b2c_queue_destroy(self._q)
+            self._q = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        calls, batches = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        check(lib.b2c_queue_stats(self._q, ctypes.byref(calls), ctypes.byref(batches)))
+        return int(calls.value), int(batches.value)
+
+    def _call(self, fn, args, src, cap):
+        src = bytes(src)
+        out = ctypes.create_string_buffer(max(cap, 1))
+        r = fn(self._q, *args, src, len(src), out, cap)
+        if r < 0:
+            raise ZstdError(r)
+        return out.raw[:r]
+
+    def EncodeAll(self, src, level=SpeedFastest, crc=True):
+        """One block (at most the level's block size) -> one frame; blocks until the batch it joined has run."""
+        flags = (FLAG_CRC if crc else 0) | FLAG_FRAME
+        return self._call(lib.b2c_queue_zstd_encode, (level, flags), src, int(lib.b2c_zstd_bound(len(src), level)) + 16)
+
+    def DecodeAll(self, src, max_size=1 << 20):
+        return self._call(lib.b2c_queue_zstd_decode, (), src, max_size)
+
+    def S2Encode(self, src, snappy=False):
+        """The WriterCustomEncoder contract on one block: the encoded block (this mirror keeps the uvarint length)."""
+        cap = int(lib.b2c_s2_bound(len(src)))
+        return self._call(lib.b2c_queue_s2_encode, (1, 1 if snappy else 0), src, cap)
+
+    def S2Decode(self, src, max_size=1 << 20):
+        return self._call(lib.b2c_queue_s2_decode, (), src, max_size)

@@ -110,7 +110,9 @@ B2C_API int b2c_zstd_encode_chunks(b2c_ctx *ctx, int level, int flags, const voi
  * Contiguous host input -> packed host output: src is cut into chunk_size pieces (<= 64 KiB at level 1), each
  * encoded as one frame, frames written back to back into h_dst (a valid zstd stream: concatenated frames,
  * zstd/encoder.go:719).  sizes_out[i] / offsets_out[i] describe frame i; *total_out is the stream length.
- * Double-buffered: H2D, kernels and D2H of consecutive batches overlap.  Synchronous.
+ * Double-buffered: H2D, kernels and D2H of consecutive batches overlap.  Synchronous.  h_src / h_dst may be pinned
+ * (copied directly at PCIe rate) or ordinary pageable memory such as a Go slice (then the library stages them through
+ * its own pinned buffers with several host threads; no cudaHostRegister by the caller is needed).
  */
 B2C_API int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const void *h_src, size_t src_bytes,
                                    uint32_t chunk_size, void *h_dst, size_t dst_cap, int64_t *sizes_out,
@@ -183,6 +185,24 @@ B2C_API int b2c_huf_compress_device(b2c_ctx *ctx, int flags, const void *d_src, 
 B2C_API int b2c_huf_decompress_device(b2c_ctx *ctx, int flags, const void *d_src, size_t src_stride,
                                       const uint32_t *d_src_sizes, void *d_dst, size_t dst_stride,
                                       const uint32_t *d_dst_sizes, int64_t *d_out_sizes, uint32_t nchunks, void *stream);
+
+/*
+ * Coalescing queue: the shim's answer to the reference's one-block-per-call seams.  zstd.Encoder.EncodeAll may be
+ * called concurrently (zstd/encoder.go:717-729), s2.WriterCustomEncoder's hook runs on one goroutine per block
+ * (s2/writer.go:1052-1064, :455-461) and so do Decoder.DecodeAll / s2.Decode.  Every b2c_queue_* call blocks like the
+ * function it replaces; a dispatcher thread owned by the queue gathers the calls that are pending (waiting up to
+ * linger_us for more, at most max_batch per dispatch), issues one batched device call per kind of request and returns
+ * each caller its byte count or negative error.  Thread-safe; src/dst are ordinary host memory, valid for the call.
+ * Inputs larger than the level's block size are refused with B2C_ERR_TOO_BIG (use b2c_zstd_encode_packed for those).
+ */
+typedef struct b2c_queue b2c_queue;
+B2C_API b2c_queue *b2c_queue_create(int device, size_t max_batch, unsigned linger_us);
+B2C_API void b2c_queue_destroy(b2c_queue *q);
+B2C_API int64_t b2c_queue_zstd_encode(b2c_queue *q, int level, int flags, const void *src, size_t n, void *dst, size_t cap);
+B2C_API int64_t b2c_queue_zstd_decode(b2c_queue *q, const void *src, size_t n, void *dst, size_t cap);
+B2C_API int64_t b2c_queue_s2_encode(b2c_queue *q, int level, int flags, const void *src, size_t n, void *dst, size_t cap);
+B2C_API int64_t b2c_queue_s2_decode(b2c_queue *q, const void *src, size_t n, void *dst, size_t cap);
+B2C_API int b2c_queue_stats(b2c_queue *q, uint64_t *calls, uint64_t *batches);
 
 #ifdef __cplusplus
 }

@@ -197,9 +197,34 @@ ORC_API void orc_enc_dfast_nohist(orc_blockenc *b, const uint8_t *src, size_t n)
  * checksum are written by the caller (orc_zstd_enc.c).  The whole input is the history buffer: for inputs
  * below window + block size the reference never slides e.hist, and beyond that the window test keeps the
  * result the same. */
+/* Pooled encoder state (zstd/encoder.go:90-99 keeps encoders in a pool; Reset does not clear the tables but bumps
+ * e.cur past every stored offset: fastBase.resetBase, enc_base.go:168-199). */
+void *orc_dfast_state_new(void) { return df_state_new(8 << 20); }
+void orc_dfast_state_free(void *st) { free(st); }
+void orc_dfast_state_reset(void *st, int32_t lastLen) {
+    df_state *e = (df_state *)st;
+    if (e->cur >= (1 << 30) - e->maxMatchOff - lastLen) {   /* bufferReset guard: start over with cleared tables */
+        memset(e->shortTab, 0, sizeof(e->shortTab));
+        memset(e->longTab, 0, sizeof(e->longTab));
+        e->cur = e->maxMatchOff;
+    } else {
+        e->cur += e->maxMatchOff + lastLen;
+    }
+}
+
+void orc_dfast_encode_all_blocks_st(void *st, orc_blockenc *blk, const uint8_t *src, size_t n, size_t blockSize,
+                                    uint8_t *dst, size_t cap, size_t *pos, int *err);
+
 void orc_dfast_encode_all_blocks(orc_blockenc *blk, const uint8_t *src, size_t n, size_t blockSize,
                                  uint8_t *dst, size_t cap, size_t *pos, int *err) {
     df_state *e = df_state_new(8 << 20);
+    orc_dfast_encode_all_blocks_st(e, blk, src, n, blockSize, dst, cap, pos, err);
+    free(e);
+}
+
+void orc_dfast_encode_all_blocks_st(void *st, orc_blockenc *blk, const uint8_t *src, size_t n, size_t blockSize,
+                                    uint8_t *dst, size_t cap, size_t *pos, int *err) {
+    df_state *e = (df_state *)st;
     *err = 0;
     if (n <= blockSize) {
         orc_blockenc_reset(blk);
@@ -218,5 +243,4 @@ void orc_dfast_encode_all_blocks(orc_blockenc *blk, const uint8_t *src, size_t n
             off += todo;
         }
     }
-    free(e);
 }

@@ -725,10 +725,18 @@ ORC_API void orc_enc_fast_nohist(orc_blockenc *b, const uint8_t *src, size_t n) 
 
 /* Reusable encoder (one per host thread), the shape of the reference's pooled encoders
  * (zstd/encoder.go:90-99,722-729): no allocation and no table clearing per EncodeAll call. */
+void *orc_dfast_state_new(void);
+void orc_dfast_state_free(void *st);
+void orc_dfast_state_reset(void *st, int32_t lastLen);
+void orc_dfast_encode_all_blocks_st(void *st, orc_blockenc *blk, const uint8_t *src, size_t n, size_t blockSize,
+                                    uint8_t *dst, size_t cap, size_t *pos, int *err);
+
 typedef struct {
     orc_blockenc *blk;
     fast_state *fast;
     int32_t lastLen;
+    void *dfast;          /* pooled level-2 state, created on first use */
+    int32_t dfastLastLen;
 } orc_zstd_cctx;
 
 ORC_API orc_zstd_cctx *orc_zstd_cctx_new(void) {
@@ -742,7 +750,7 @@ ORC_API orc_zstd_cctx *orc_zstd_cctx_new(void) {
 }
 ORC_API void orc_zstd_cctx_free(orc_zstd_cctx *c) {
     if (!c) return;
-    orc_blockenc_free(c->blk); free(c->fast); free(c);
+    orc_blockenc_free(c->blk); free(c->fast); if (c->dfast) orc_dfast_state_free(c->dfast); free(c);
 }
 
 /* ----------------------------------------------------------------- frames */
@@ -794,7 +802,7 @@ ORC_API int64_t orc_zstd_encode_all(const uint8_t *src, size_t n, int level, int
 /* EncodeAll on a reused encoder (level 1 only reuses state; other levels fall back to fresh state) */
 ORC_API int64_t orc_zstd_encode_all_ctx(orc_zstd_cctx *cc, const uint8_t *src, size_t n, int level, int crc,
                                         uint8_t *dst, size_t cap) {
-    return encode_all_impl(level == 1 ? cc : NULL, src, n, level, crc, dst, cap);
+    return encode_all_impl(level <= 2 ? cc : NULL, src, n, level, crc, dst, cap);
 }
 
 /* Benchmark helper (bench.py cpu_baseline / --impl reference): one EncodeAll per `chunk` bytes of src on a
@@ -841,7 +849,14 @@ static int64_t encode_all_impl(orc_zstd_cctx *cc, const uint8_t *src, size_t n, 
     if (cc) { orc_blockenc_reset(blk); orc_blockenc_init_new_encode(blk); }
     int err = 0;
     if (level == 2) {
-        orc_dfast_encode_all_blocks(blk, src, n, blockSize, dst, cap, &pos, &err);
+        if (cc) {
+            if (!cc->dfast) cc->dfast = orc_dfast_state_new();
+            else orc_dfast_state_reset(cc->dfast, cc->dfastLastLen);
+            cc->dfastLastLen = (int32_t)n;
+            orc_dfast_encode_all_blocks_st(cc->dfast, blk, src, n, blockSize, dst, cap, &pos, &err);
+        } else {
+            orc_dfast_encode_all_blocks(blk, src, n, blockSize, dst, cap, &pos, &err);
+        }
     } else if (level == 3) {
         orc_better_encode_all_blocks(blk, src, n, blockSize, dst, cap, &pos, &err);
     } else if (n <= blockSize) {

@@ -70,3 +70,28 @@ def test_chunk_range_covers_everything():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_numa_binding_helpers(tmp_path):
+    """bind_to_gpu_numa reads the GPU's NUMA node and that node's CPU list from sysfs (a fake tree here)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("b2c_shard", os.path.join(ROOT, "compress_b200", "shard.py"))
+    shard = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shard)
+    assert shard._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    mine = sorted(os.sched_getaffinity(0))
+    (node / "cpulist").write_text(",".join(str(c) for c in mine[:1]) + "\n")
+    assert shard.gpu_numa_node("00000000:1B:00.0", str(tmp_path)) == 1
+    before = os.sched_getaffinity(0)
+    try:
+        assert shard.bind_to_gpu_numa("0000:1b:00.0", str(tmp_path)) == 1
+        assert os.sched_getaffinity(0) == {mine[0]}
+    finally:
+        os.sched_setaffinity(0, before)
+    (dev / "numa_node").write_text("-1\n")
+    assert shard.bind_to_gpu_numa("0000:1b:00.0", str(tmp_path)) is None
