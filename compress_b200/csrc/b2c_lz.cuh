@@ -37,6 +37,9 @@ constexpr uint32_t LZ_MAXREC = LZ_RANGE / 4;   // matches a thread can start ins
 constexpr uint32_t LZ_TAGBITS = 14;
 constexpr uint32_t LZ_TAGMASK = (1u << LZ_TAGBITS) - 1;
 constexpr uint32_t LZ_EMPTY = 0xffffffffu;
+#ifndef LZ_INS_STRIDE
+#define LZ_INS_STRIDE 1     // 2: only even positions are inserted into the tables (every position is still probed)
+#endif
 constexpr uint32_t LZ_EXT_CAP = 256;        // per-thread forward extension limit; longer matches are finished by warp 0
 
 template <int LV> struct LzCfg;
@@ -133,26 +136,26 @@ B2C_DEV void lz_dense_tile(uint32_t *TS, uint32_t *TL, uint32_t *bm, uint32_t *b
         const uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
         const uint32_t h = C::LONG ? lz_hash5(lo, hi) : lz_hash6(lo, hi);
         is[j] = h >> (32 - C::TBITS);
-        es[j] = ((p0 + j) << LZ_TAGBITS) | ((h >> 4) & LZ_TAGMASK);
+        es[j] = ((p0 + j) << LZ_TAGBITS) | (h & LZ_TAGMASK);          // tag: the hash's low bits (index: its high bits)
         fs[j] = TS[is[j]];                                             // far candidate: the slot as earlier tiles left it
         if constexpr (C::LONG) {
             const uint32_t hl = lz_hash8(lo, hi);
             il[j] = hl >> (32 - C::TBITS);
-            el[j] = ((p0 + j) << LZ_TAGBITS) | ((hl >> 4) & LZ_TAGMASK);
+            el[j] = ((p0 + j) << LZ_TAGBITS) | (hl & LZ_TAGMASK);
             fl[j] = TL[il[j]];
         }
     }
     __syncthreads();
 #pragma unroll
     for (int j = 3; j >= 0; j--)                                       // the thread's lowest position lands last
-        if (!GUARD || p0 + j < npos) {
+        if ((LZ_INS_STRIDE == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
             TS[is[j]] = es[j];
             if constexpr (C::LONG) TL[il[j]] = el[j];
         }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        if (!GUARD || p0 + j < npos) {
+        if ((LZ_INS_STRIDE == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
             if (TS[is[j]] > es[j]) atomicMin(&TS[is[j]], es[j]);      // lost a store race: exact minimum of the tile
             if constexpr (C::LONG) { if (TL[il[j]] > el[j]) atomicMin(&TL[il[j]], el[j]); }
         }
@@ -209,6 +212,7 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     uint32_t *bml = reinterpret_cast<uint32_t *>(smem + L::SM_BML); // long candidate (level 2)
     ParseShared *sh = reinterpret_cast<ParseShared *>(smem + L::SM_SH);
     uint32_t *ws2 = reinterpret_cast<uint32_t *>(smem + L::SM_SH + ((sizeof(ParseShared) + 15) / 16) * 16);
+    uint16_t *plut = reinterpret_cast<uint16_t *>(ws2 + 96);   // byte-permute selector per 4-bit mask: the set bytes, in order
     ChunkWork *W = P.work + chunk;
     const WkLens wlen = wk_lens(P, chunk);
     uint32_t *const wof = wk_of(P, chunk);
@@ -225,6 +229,12 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     B2C_PHASE(0);
     // ---------------------------------------------------------------- P0: empty tables
     for (uint32_t i = tid; i < L::NTAB * TSIZE; i += NT) TS[i] = LZ_EMPTY;
+    if (tid < 16) {
+        uint32_t sel = 0, k = 0;
+        for (uint32_t bb = 0; bb < 4; bb++)
+            if ((tid >> bb) & 1) { sel |= bb << (4 * k); k++; }
+        plut[tid] = (uint16_t)sel;
+    }
     __syncthreads();
 
     // ---------------------------------------------------------------- P1: dense pass, tile by tile
@@ -542,10 +552,12 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
         uint8_t *glit = wk_lit(P, chunk);
         uint32_t gpos = __shfl_sync(FULLMASK, litEx, 0);                // literal index of staging byte `ph`
         uint32_t ph = (uint32_t)((reinterpret_cast<uintptr_t>(glit) + gpos) & 15), fill = 0;
-        for (uint32_t i = 0; i <= 32; i++) {
-            const uint32_t t = w * 32 + i;
-            const bool last = (i == 32) || (t * LZ_RANGE >= n);
-            if (last || ph + fill + 128 > STG) {
+        const uint32_t nr = (w * 32 * LZ_RANGE >= n) ? 0u : ((n - w * 32 * LZ_RANGE + LZ_RANGE - 1) / LZ_RANGE < 32 ? (n - w * 32 * LZ_RANGE + LZ_RANGE - 1) / LZ_RANGE : 32u);
+        // four ranges (512 bytes) per step: one warp scan serves all four (the four counts travel in the bytes of one word,
+        // each at most 128); the literal bytes of a word are gathered with one byte permute (selector table by mask nibble)
+        for (uint32_t i0 = 0;; i0 += 4) {
+            const bool last = i0 >= nr;
+            if (last || ph + fill + 512 > STG) {
                 // flush [gpos, gpos + fill): head bytes up to the first 16-byte boundary, vectors, tail bytes
                 __syncwarp();
                 uint8_t *gd = glit + gpos;
@@ -562,22 +574,33 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
                 ph = (uint32_t)((reinterpret_cast<uintptr_t>(glit) + gpos) & 15);
             }
             if (last) break;
-            const uint32_t mw = mask[4 * t + (lane >> 3)];
-            const uint32_t nib = (mw >> (4 * (lane & 7))) & 15u;
-            const uint32_t c = (uint32_t)__popc(nib);
-            const uint32_t incl = warp_scan_incl(c);
-            const uint32_t tot = __shfl_sync(FULLMASK, incl, 31);
-            if (tot == 0) continue;
-            const uint32_t v = srcw[32 * t + lane];
-            uint32_t packed = 0, k = 0;
+            uint32_t nib[4], pc = 0;
 #pragma unroll
-            for (int bb = 0; bb < 4; bb++)
-                if ((nib >> bb) & 1) { packed |= ((v >> (8 * bb)) & 0xffu) << (8 * k); k++; }
-            uint8_t *o = stg + ph + fill + (incl - c);
+            for (int q = 0; q < 4; q++) {
+                const uint32_t t = w * 32 + i0 + q;
+                const uint32_t mw = (i0 + q < nr) ? mask[4 * t + (lane >> 3)] : 0u;
+                nib[q] = (mw >> (4 * (lane & 7))) & 15u;
+                pc |= (uint32_t)__popc(nib[q]) << (8 * q);
+            }
+            const uint32_t incl = warp_scan_incl(pc);
+            const uint32_t tots = __shfl_sync(FULLMASK, incl, 31);
+            if (tots == 0) continue;
+            uint32_t rbase = ph + fill;
 #pragma unroll
-            for (int bb = 0; bb < 4; bb++)
-                if ((uint32_t)bb < c) o[bb] = (uint8_t)(packed >> (8 * bb));
-            fill += tot;
+            for (int q = 0; q < 4; q++) {
+                const uint32_t c = (pc >> (8 * q)) & 0xffu;
+                if (c) {
+                    const uint32_t v = srcw[32 * (w * 32 + i0 + q) + lane];
+                    const uint32_t packed = __byte_perm(v, 0u, (uint32_t)plut[nib[q]]);
+                    uint8_t *o = stg + rbase + ((incl >> (8 * q)) & 0xffu) - c;
+                    o[0] = (uint8_t)packed;
+                    if (c > 1) o[1] = (uint8_t)(packed >> 8);
+                    if (c > 2) o[2] = (uint8_t)(packed >> 16);
+                    if (c > 3) o[3] = (uint8_t)(packed >> 24);
+                }
+                rbase += (tots >> (8 * q)) & 0xffu;
+            }
+            fill = rbase - ph;
         }
     }
 #undef REC
@@ -594,8 +617,43 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
 // pinned 64 KiB of shared memory; as a separate kernel it runs at seven CTAs per SM.)
 constexpr int HIST_NT = 128;
 constexpr int HIST_WARPS = HIST_NT / 32;
-constexpr uint32_t HIST_SLICE = 255u * HIST_NT;    // literals per slice: at most 255 per lane
+constexpr uint32_t HIST_SLICE = 15u * 16u * HIST_NT; // bytes per slice: a lane takes 16-byte pieces, at most 15 of them (240 <= 255)
 constexpr uint32_t HIST_SMEM_BYTES = HIST_WARPS * 256 * 32;
+// Private-counter byte histogram of stream[s0, s1) (s0 a multiple of 16, stream 16-byte aligned): every lane owns one
+// byte counter per symbol (col[sym * 32]), reads 16 bytes per step with the next step's load already in flight, and merges
+// equal symbols inside a word so that the four updates of a word are independent.  At most 255 symbols per lane and call.
+template <uint32_t SYMMASK>
+B2C_DEV void hist_count_stream(const uint8_t *stream, uint32_t s0, uint32_t s1, uint8_t *col, unsigned tid) {
+    const uint4 *s16 = reinterpret_cast<const uint4 *>(stream);
+    const uint32_t n16 = (s1 + 15) / 16;
+    uint32_t i = s0 / 16 + tid;
+    uint4 v = (i < n16) ? B2C_LDG(s16 + i) : make_uint4(0, 0, 0, 0);
+    while (i < n16) {
+        const uint32_t inext = i + HIST_NT;
+        const uint4 vnext = (inext < n16) ? B2C_LDG(s16 + inext) : make_uint4(0, 0, 0, 0);   // requested before this one is used
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t pos = 16 * i + 4 * k;
+            if (pos < s1) {
+                const uint32_t nv = (pos + 4 <= s1) ? 4u : s1 - pos;
+                const uint32_t x = wv[k];
+                const uint32_t a0 = x & SYMMASK, a1 = (x >> 8) & SYMMASK, a2 = (x >> 16) & SYMMASK, a3 = (x >> 24) & SYMMASK;
+                uint32_t i0 = 1, i1 = nv > 1, i2 = nv > 2, i3 = nv > 3;
+                if (a1 == a0) { i0 += i1; i1 = 0; }
+                if (a2 == a0) { i0 += i2; i2 = 0; } else if (a2 == a1) { i1 += i2; i2 = 0; }
+                if (a3 == a0) { i0 += i3; i3 = 0; } else if (a3 == a1) { i1 += i3; i3 = 0; } else if (a3 == a2) { i2 += i3; i3 = 0; }
+                const uint32_t c0 = col[a0 * 32], c1 = col[a1 * 32], c2 = col[a2 * 32], c3 = col[a3 * 32];
+                col[a0 * 32] = (uint8_t)(c0 + i0);
+                if (i1) col[a1 * 32] = (uint8_t)(c1 + i1);
+                if (i2) col[a2 * 32] = (uint8_t)(c2 + i2);
+                if (i3) col[a3 * 32] = (uint8_t)(c3 + i3);
+            }
+        }
+        i = inext; v = vnext;
+    }
+}
+
 B2C_DEV void zstd_hist_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk) {
     const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     ChunkWork *W = P.work + chunk;
@@ -618,28 +676,7 @@ B2C_DEV void zstd_hist_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         const uint32_t s1 = (s0 + HIST_SLICE < nlit) ? s0 + HIST_SLICE : nlit;
         for (uint32_t i = tid; i < HIST_SMEM_BYTES / 4; i += HIST_NT) reinterpret_cast<uint32_t *>(smem)[i] = 0;
         __syncthreads();
-        {
-            const uint32_t w0 = s0 / 4, nl4 = (s1 + 3) / 4;       // HIST_SLICE is a multiple of 4
-            const uint32_t *lit32 = reinterpret_cast<const uint32_t *>(lit);
-            uint32_t i = w0 + tid;
-            uint32_t v = (i < nl4) ? B2C_LDG(lit32 + i) : 0;
-            while (i < nl4) {
-                const uint32_t inext = i + HIST_NT;
-                const uint32_t vnext = (inext < nl4) ? B2C_LDG(lit32 + inext) : 0;   // next word requested before this one is used
-                const uint32_t nv = (4 * i + 4 <= s1) ? 4u : s1 - 4 * i;
-                const uint32_t a0 = v & 0xff, a1 = (v >> 8) & 0xff, a2 = (v >> 16) & 0xff, a3 = v >> 24;
-                uint32_t i0 = 1, i1 = nv > 1, i2 = nv > 2, i3 = nv > 3;
-                if (a1 == a0) { i0 += i1; i1 = 0; }
-                if (a2 == a0) { i0 += i2; i2 = 0; } else if (a2 == a1) { i1 += i2; i2 = 0; }
-                if (a3 == a0) { i0 += i3; i3 = 0; } else if (a3 == a1) { i1 += i3; i3 = 0; } else if (a3 == a2) { i2 += i3; i3 = 0; }
-                const uint32_t c0 = hcol[a0 * 32], c1 = hcol[a1 * 32], c2 = hcol[a2 * 32], c3 = hcol[a3 * 32];
-                hcol[a0 * 32] = (uint8_t)(c0 + i0);
-                if (i1) hcol[a1 * 32] = (uint8_t)(c1 + i1);
-                if (i2) hcol[a2 * 32] = (uint8_t)(c2 + i2);
-                if (i3) hcol[a3 * 32] = (uint8_t)(c3 + i3);
-                i = inext; v = vnext;
-            }
-        }
+        hist_count_stream<255>(lit, s0, s1, hcol, tid);
         __syncthreads();
 #pragma unroll
         for (int half = 0; half < 2; half++) {
@@ -671,22 +708,7 @@ B2C_DEV void zstd_hist_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             uint8_t *ccol = smem + w * 256 * 32 + c * 64 * 32 + lane;
-            const uint32_t w0 = s0 / 4, nl4 = (s1 + 3) / 4;
-            const uint32_t *c32 = reinterpret_cast<const uint32_t *>(codes + (uint32_t)c * mseq);   // maxseq is a multiple of 16
-            for (uint32_t i = w0 + tid; i < nl4; i += HIST_NT) {
-                const uint32_t v = B2C_LDG(c32 + i);
-                const uint32_t nv = (4 * i + 4 <= s1) ? 4u : s1 - 4 * i;
-                const uint32_t a0 = v & 63, a1 = (v >> 8) & 63, a2 = (v >> 16) & 63, a3 = (v >> 24) & 63;
-                uint32_t i0 = 1, i1 = nv > 1, i2 = nv > 2, i3 = nv > 3;
-                if (a1 == a0) { i0 += i1; i1 = 0; }
-                if (a2 == a0) { i0 += i2; i2 = 0; } else if (a2 == a1) { i1 += i2; i2 = 0; }
-                if (a3 == a0) { i0 += i3; i3 = 0; } else if (a3 == a1) { i1 += i3; i3 = 0; } else if (a3 == a2) { i2 += i3; i3 = 0; }
-                const uint32_t c0 = ccol[a0 * 32], c1 = ccol[a1 * 32], c2 = ccol[a2 * 32], c3 = ccol[a3 * 32];
-                ccol[a0 * 32] = (uint8_t)(c0 + i0);
-                if (i1) ccol[a1 * 32] = (uint8_t)(c1 + i1);
-                if (i2) ccol[a2 * 32] = (uint8_t)(c2 + i2);
-                if (i3) ccol[a3 * 32] = (uint8_t)(c3 + i3);
-            }
+            hist_count_stream<63>(codes + (uint32_t)c * mseq, s0, s1, ccol, tid);      // maxseq is a multiple of 16
         }
         __syncthreads();
         for (uint32_t i = tid; i < 192; i += HIST_NT) {     // (HIST_NT = 128: two rounds; the accumulator is per (round, thread))
