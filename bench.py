@@ -276,14 +276,15 @@ def main():
         s2sz = torch.empty((n,), dtype=torch.int64, device=dev)
         dout = torch.empty((n, CHUNK), dtype=torch.uint8, device=dev)
         dres = torch.empty((n,), dtype=torch.int64, device=dev)
-        for name, snappy in (("s2", False), ("snappy", True)):
+        for name, snappy, better in (("s2", False, False), ("snappy", True, False), ("s2_better", False, True),
+                                     ("snappy_better", True, True)):
             for _ in range(2):
-                s2c.encode_device(src, snappy=snappy, dst=s2dst, out_sizes=s2sz)
+                s2c.encode_device(src, snappy=snappy, better=better, dst=s2dst, out_sizes=s2sz)
             torch.cuda.synchronize()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             for _ in range(3):
-                s2c.encode_device(src, snappy=snappy, dst=s2dst, out_sizes=s2sz)
+                s2c.encode_device(src, snappy=snappy, better=better, dst=s2dst, out_sizes=s2sz)
             a1.record()
             torch.cuda.synchronize()
             ems = a0.elapsed_time(a1) / 3

@@ -163,6 +163,10 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
         size_t a = (size_t)ctx->sm_count * ENC_SCRATCH_BYTES;
         size_t b = (size_t)ctx->sm_count * LzCfg<1>::MIN_CTAS * LzLayout<1>::SCRATCH_BYTES;
         size_t c = (size_t)ctx->sm_count * LzCfg<2>::MIN_CTAS * LzLayout<2>::SCRATCH_BYTES;
+        size_t d3 = (size_t)ctx->sm_count * LzCfg<3>::MIN_CTAS * LzLayout<3>::SCRATCH_BYTES;
+        size_t d4 = (size_t)ctx->sm_count * LzCfg<4>::MIN_CTAS * LzLayout<4>::SCRATCH_BYTES;
+        if (d3 > a) a = d3;
+        if (d4 > a) a = d4;
         ctx->scratch_slot = ((a > b ? (a > c ? a : c) : (b > c ? b : c)) + 255) & ~(size_t)255;
         const char *pe = getenv("B2C_PARSE");
         ctx->parse_r1 = (pe && strcmp(pe, "r1") == 0) ? 1 : 0;
@@ -173,6 +177,10 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)LzLayout<1>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_lz_parse2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)LzLayout<2>::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_s2_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzLayout<3>::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_snappy_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzLayout<3>::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_s2_better_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzLayout<4>::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_snappy_better_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzLayout<4>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)HIST_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_pack128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -791,24 +799,36 @@ int b2c_s2_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, 
                          const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
                          int64_t *d_out_sizes, uint32_t nchunks, void *stream) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
-    if (level != B2C_S2_FAST) return B2C_ERR_UNSUPPORTED;
+    if (level != B2C_S2_FAST && level != B2C_S2_BETTER) return B2C_ERR_UNSUPPORTED;
     if (nchunks == 0) return B2C_OK;
     if (dst_stride > 0xffffffffull) return B2C_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    { int r = ctx_order_begin(ctx, st); if (r) return r; }
     ZstdEncParams P;
     memset(&P, 0, sizeof(P));
     P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_sizes = d_sizes; P.src_size_all = size_all;
     P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
-    P.out_sizes = d_out_sizes; P.nchunks = nchunks;
+    P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.blockmax = ENC_MAX_CHUNK;
     P.scratch = ctx->d_scratch;
-    unsigned sms = (unsigned)ctx->sm_count;
-    unsigned g1 = sms < nchunks ? sms : nchunks;
-    if (flags & B2C_S2_SNAPPY) b2c_snappy_encode_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
-    else b2c_s2_encode_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+    const unsigned sms = (unsigned)ctx->sm_count;
+    const bool snappy = (flags & B2C_S2_SNAPPY) != 0;
+    if (ctx->parse_r1 && level == B2C_S2_FAST) {
+        const unsigned g1 = sms < nchunks ? sms : nchunks;
+        if (snappy) b2c_snappy_encode_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+        else b2c_s2_encode_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
+    } else if (level == B2C_S2_FAST) {
+        const unsigned cap = sms * LzCfg<3>::MIN_CTAS, g1 = cap < nchunks ? cap : nchunks;
+        if (snappy) b2c_lz_snappy_fast_kernel<<<g1, LzCfg<3>::NT, LzLayout<3>::SMEM_BYTES, st>>>(P);
+        else b2c_lz_s2_fast_kernel<<<g1, LzCfg<3>::NT, LzLayout<3>::SMEM_BYTES, st>>>(P);
+    } else {
+        const unsigned cap = sms * LzCfg<4>::MIN_CTAS, g1 = cap < nchunks ? cap : nchunks;
+        if (snappy) b2c_lz_snappy_better_kernel<<<g1, LzCfg<4>::NT, LzLayout<4>::SMEM_BYTES, st>>>(P);
+        else b2c_lz_s2_better_kernel<<<g1, LzCfg<4>::NT, LzLayout<4>::SMEM_BYTES, st>>>(P);
+    }
     ctx->launches += 1;
     CK(cudaGetLastError());
-    return B2C_OK;
+    return ctx_order_end(ctx, st);
 }
 
 int b2c_s2_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, const uint64_t *d_src_offsets,
@@ -833,7 +853,7 @@ int b2c_s2_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, con
 
 // Host-buffer batches for the block API (s2.Encode / s2.EncodeSnappy / s2.Decode per element).  Inputs are packed
 // back to back on the device, outputs land in per-element slots; one kernel per call.
-static int s2_host_batch(b2c_ctx *ctx, bool encode, int flags, const void *const *srcs, const size_t *src_sizes,
+static int s2_host_batch(b2c_ctx *ctx, bool encode, int level, int flags, const void *const *srcs, const size_t *src_sizes,
                          void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     if (n == 0) return B2C_OK;
@@ -866,7 +886,7 @@ static int s2_host_batch(b2c_ctx *ctx, bool encode, int flags, const void *const
     uint32_t *d_ss = reinterpret_cast<uint32_t *>(dm + 3 * n);
     int64_t *d_res = reinterpret_cast<int64_t *>(dm + 2 * n);
     if (encode)
-        rc = b2c_s2_encode_device(ctx, B2C_S2_FAST, flags, ctx->d_dec_in, ENC_MAX_CHUNK, d_ss, 0, ctx->d_dec_out, kSlot, d_res,
+        rc = b2c_s2_encode_device(ctx, level, flags, ctx->d_dec_in, ENC_MAX_CHUNK, d_ss, 0, ctx->d_dec_out, kSlot, d_res,
                                   (uint32_t)n, st);
     else {
         S2DecParams P;
@@ -895,12 +915,12 @@ static int s2_host_batch(b2c_ctx *ctx, bool encode, int flags, const void *const
 
 int b2c_s2_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const *srcs, const size_t *src_sizes,
                          void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n) {
-    if (level != B2C_S2_FAST) return ctx ? B2C_ERR_UNSUPPORTED : B2C_ERR_NO_DEVICE;
-    return s2_host_batch(ctx, true, flags, srcs, src_sizes, dsts, dst_caps, sizes_out, n);
+    if (level != B2C_S2_FAST && level != B2C_S2_BETTER) return ctx ? B2C_ERR_UNSUPPORTED : B2C_ERR_NO_DEVICE;
+    return s2_host_batch(ctx, true, level, flags, srcs, src_sizes, dsts, dst_caps, sizes_out, n);
 }
 int b2c_s2_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
                          const size_t *dst_caps, int64_t *sizes_out, size_t n) {
-    return s2_host_batch(ctx, false, 0, srcs, src_sizes, dsts, dst_caps, sizes_out, n);
+    return s2_host_batch(ctx, false, 0, 0, srcs, src_sizes, dsts, dst_caps, sizes_out, n);
 }
 
 

@@ -17,7 +17,7 @@ namespace b2c {
 constexpr int HUF0_NT = 1024;
 constexpr uint32_t HUF0_BLOCK_MAX = (1u << 18) - 1;   // huff0.BlockSizeMax (huff0/huff0.go:27)
 enum { HUF0_FLAG_4X = 1 };
-enum { HUF0_ERR_INCOMPRESSIBLE = -1, HUF0_ERR_USE_RLE = -2, HUF0_ERR_TOO_BIG = -3, HUF0_ERR_DST = -4, HUF0_ERR_CORRUPT = -5 };
+enum { HUF0_ERR_INCOMPRESSIBLE = -1, HUF0_ERR_USE_RLE = -2, HUF0_ERR_TOO_BIG = -3, HUF0_ERR_DST = -4, HUF0_ERR_CORRUPT = -5, HUF0_ERR_UNSUPPORTED = -11 };
 
 struct Huf0Shared {
     HufWork hw;
@@ -81,6 +81,7 @@ B2C_DEV int64_t huf0_decompress_block(DecWarp *dw, const uint8_t *src, uint32_t 
     if (dstSize > HUF0_BLOCK_MAX) return HUF0_ERR_TOO_BIG;             // MaxDecodedSize default = BlockSizeMax
     uint32_t tl = 0;
     const int used = dec_huf_read_table(dw, src, n, &tl, lane);
+    if (used == -2) return HUF0_ERR_UNSUPPORTED;     // weight table description beyond this decoder's limits (fse tableLog > 9)
     if (used < 0) return HUF0_ERR_CORRUPT;
     const int e = dec_huf_streams<true>(dw->hufDt, tl, src + used, n - (uint32_t)used, dst, dstSize, four, lane);
     if (__any_sync(FULLMASK, e != 0)) return HUF0_ERR_CORRUPT;
@@ -100,9 +101,11 @@ extern "C" __global__ void __launch_bounds__(DEC_WARPS * 32) b2c_huf_decompress_
     const uint32_t totalWarps = gridDim.x * DEC_WARPS;
     for (uint32_t c = blockIdx.x * DEC_WARPS + w; c < P.nchunks; c += totalWarps) {
         __syncwarp();
-        const int64_t r = huf0_decompress_block(dw, P.src_base + (uint64_t)c * P.src_stride, P.src_sizes[c],
-                                                P.dst_base + (uint64_t)c * P.dst_stride,
-                                                P.dst_sizes ? P.dst_sizes[c] : P.dst_cap, (P.flags & HUF0_FLAG_4X) != 0, lane);
+        const uint32_t want = P.dst_sizes ? P.dst_sizes[c] : P.dst_cap;
+        // the exact decoded size must fit the block's slot (it is the caller's number, not the stream's)
+        const int64_t r = (P.dst_stride && want > P.dst_stride && want <= HUF0_BLOCK_MAX) ? (int64_t)HUF0_ERR_DST
+                          : huf0_decompress_block(dw, P.src_base + (uint64_t)c * P.src_stride, P.src_sizes[c],
+                                                  P.dst_base + (uint64_t)c * P.dst_stride, want, (P.flags & HUF0_FLAG_4X) != 0, lane);
         __syncwarp();
         if (lane == 0) P.out_sizes[c] = r;
     }

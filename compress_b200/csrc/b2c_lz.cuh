@@ -37,16 +37,22 @@ constexpr uint32_t LZ_MAXREC = LZ_RANGE / 4;   // matches a thread can start ins
 constexpr uint32_t LZ_TAGBITS = 14;
 constexpr uint32_t LZ_TAGMASK = (1u << LZ_TAGBITS) - 1;
 constexpr uint32_t LZ_EMPTY = 0xffffffffu;
+#ifndef LZ_PPT1
+#define LZ_PPT1 8           // positions per thread and tile of the single-table configurations (4 or 8)
+#endif
 #ifndef LZ_INS_STRIDE
 #define LZ_INS_STRIDE 1     // 2: only even positions are inserted into the tables (every position is still probed)
 #endif
 constexpr uint32_t LZ_EXT_CAP = 256;        // per-thread forward extension limit; longer matches are finished by warp 0
 
 template <int LV> struct LzCfg;
+enum { LZ_ZSTD1 = 1, LZ_ZSTD2 = 2, LZ_S2FAST = 3, LZ_S2BETTER = 4 };
 template <> struct LzCfg<1> {
     static constexpr int NT = 512;
     static constexpr uint32_t BLOCK = 65536;
     static constexpr bool LONG = false;
+    static constexpr int SMLS = 6, LMLS = 8;   // bytes hashed for the short / long table
+    static constexpr int PPT = LZ_PPT1;        // positions per thread and tile (tile = NT * PPT positions)
     static constexpr uint32_t TBITS = 14;
     static constexpr uint32_t KREC = 16;      // match records (4 bytes each) per thread kept in shared memory
     static constexpr int MIN_CTAS = 2;
@@ -55,9 +61,34 @@ template <> struct LzCfg<2> {
     static constexpr int NT = 1024;
     static constexpr uint32_t BLOCK = 131072;
     static constexpr bool LONG = true;
+    static constexpr int SMLS = 5, LMLS = 8;
+    static constexpr int PPT = 4;
     static constexpr uint32_t TBITS = 14;
     static constexpr uint32_t KREC = 8;
     static constexpr int MIN_CTAS = 1;
+};
+
+// S2 block encoders (s2/encode_all.go:72 encodeBlockGo: one table, 4-byte minimum match; s2/encode_better.go:485
+// encodeBlockBetterGo64K: long 7-byte + short 4-byte table, long preferred, lazy step): 64 KiB blocks, two CTAs per SM
+template <> struct LzCfg<3> {
+    static constexpr int NT = 512;
+    static constexpr uint32_t BLOCK = 65536;
+    static constexpr bool LONG = false;
+    static constexpr int SMLS = 4, LMLS = 8;
+    static constexpr int PPT = LZ_PPT1;
+    static constexpr uint32_t TBITS = 14;
+    static constexpr uint32_t KREC = 16;
+    static constexpr int MIN_CTAS = 2;
+};
+template <> struct LzCfg<4> {
+    static constexpr int NT = 512;
+    static constexpr uint32_t BLOCK = 65536;
+    static constexpr bool LONG = true;
+    static constexpr int SMLS = 4, LMLS = 7;
+    static constexpr int PPT = 4;
+    static constexpr uint32_t TBITS = 13;
+    static constexpr uint32_t KREC = 12;      // (the second bitmap takes the room of four records per thread)
+    static constexpr int MIN_CTAS = 2;
 };
 
 template <int LV> struct LzLayout {
@@ -73,6 +104,9 @@ template <int LV> struct LzLayout {
     static constexpr uint32_t SM_REC = SM_BML + (C::LONG ? BM_BYTES : 0);
     static constexpr uint32_t REC_BYTES = C::KREC * C::NT * 4;
     static constexpr uint32_t SM_ARR = SM_REC + REC_BYTES;                      // keptEnd u32 | lastOff u32 | longLen u32 | cnt u8 | cap u8
+    // S2 modes: per-warp output windows in the candidate bitmaps (dead after the walk); a thread's piece is < 400 bytes
+    static constexpr uint32_t SM_STG = SM_BM;
+    static constexpr uint32_t STG_S2 = ((BM_BYTES * (C::LONG ? 2u : 1u)) / (C::NT / 32)) & ~15u;
     static constexpr uint32_t SM_SH = SM_ARR + C::NT * 14;
     static constexpr uint32_t SMEM_BYTES = SM_SH + ((sizeof(ParseShared) + 2 * 80 * 4 + 15) / 16) * 16;
     // per-CTA global scratch: candidate distances (u16 per position) + spilled match records [k][thread]
@@ -81,12 +115,19 @@ template <int LV> struct LzLayout {
 };
 static_assert(2 * (LzLayout<1>::SMEM_BYTES + 1024) <= 228 * 1024, "two level-1 parse CTAs must fit one SM");
 static_assert(LzLayout<2>::SMEM_BYTES <= 227 * 1024, "the level-2 parse CTA must fit one SM");
+static_assert(2 * (LzLayout<3>::SMEM_BYTES + 1024) <= 228 * 1024 && 2 * (LzLayout<4>::SMEM_BYTES + 1024) <= 228 * 1024, "two S2 parse CTAs must fit one SM");
 
 // hashes: two 32-bit multiply-adds (the reference's hashLen is a 64-bit multiply, zstd/hash.go:27-33; table contents
 // are an implementation detail, only verified matches reach the output)
-B2C_DEV uint32_t lz_hash6(uint32_t lo, uint32_t hi) { return lo * 0x9E3779B1u + (hi & 0xffffu) * 0x85EBCA6Bu; }
-B2C_DEV uint32_t lz_hash5(uint32_t lo, uint32_t hi) { return lo * 0x9E3779B1u + (hi & 0xffu) * 0x85EBCA6Bu; }
-B2C_DEV uint32_t lz_hash8(uint32_t lo, uint32_t hi) { return lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu; }
+template <int MLS> B2C_DEV uint32_t lz_hash_short(uint32_t lo, uint32_t hi) {
+    if constexpr (MLS == 4) return lo * 0x9E3779B1u;
+    else if constexpr (MLS == 5) return lo * 0x9E3779B1u + (hi & 0xffu) * 0x85EBCA6Bu;
+    else return lo * 0x9E3779B1u + (hi & 0xffffu) * 0x85EBCA6Bu;
+}
+template <int MLS> B2C_DEV uint32_t lz_hash_long(uint32_t lo, uint32_t hi) {
+    if constexpr (MLS == 7) return lo * 0xC2B2AE3Du + (hi & 0xffffffu) * 0x27D4EB2Fu;
+    else return lo * 0xC2B2AE3Du + hi * 0x27D4EB2Fu;
+}
 
 // exclusive scan of two values per thread (same conventions as group_scan_excl; ws: >= 80 words)
 B2C_DEV void group_scan_excl_pair(uint32_t a, uint32_t b, uint32_t *ws, int nthreads, unsigned tid, uint32_t *exA,
@@ -124,81 +165,110 @@ B2C_DEV uint32_t lz_rec_d(uint32_t r) { return r >> 16; }
 // the position, which the walk rejects).
 template <int LV, bool GUARD>
 B2C_DEV void lz_dense_tile(uint32_t *TS, uint32_t *TL, uint32_t *bm, uint32_t *bml, uint16_t *cd, uint32_t g, uint32_t npos,
-                           uint32_t w0, uint32_t w1, uint32_t w2, unsigned lane) {
+                           const uint32_t (&wv)[LzCfg<LV>::PPT / 4 + 2], unsigned lane) {
     using C = LzCfg<LV>;
+    constexpr int PPT = C::PPT;
     constexpr uint32_t BAD = 0x80000000u | LZ_TAGMASK | (C::BLOCK > 65536 ? 0x40000000u : 0u);   // wrong tag, not earlier, or >= 64 KiB away
-    const uint32_t p0 = 4 * g;
-    uint32_t es[4], is[4], fs[4];
-    uint32_t el[4], il[4], fl[4];
+    const uint32_t p0 = PPT * g;
+    uint32_t hs[PPT], fs[PPT];                  // short table: hash (index = high bits, tag = low bits) and far slot content
+    uint32_t hl[C::LONG ? PPT : 1], fl[C::LONG ? PPT : 1];
+#define LZ_IDX(h) ((h) >> (32 - C::TBITS))
+#define LZ_ENT(h, j) (((p0 + (j)) << LZ_TAGBITS) | ((h) & LZ_TAGMASK))
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
-        const uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
-        const uint32_t h = C::LONG ? lz_hash5(lo, hi) : lz_hash6(lo, hi);
-        is[j] = h >> (32 - C::TBITS);
-        es[j] = ((p0 + j) << LZ_TAGBITS) | (h & LZ_TAGMASK);          // tag: the hash's low bits (index: its high bits)
-        fs[j] = TS[is[j]];                                             // far candidate: the slot as earlier tiles left it
+    for (int j = 0; j < PPT; j++) {
+        const uint32_t a = wv[j >> 2], bb = wv[(j >> 2) + 1], c = wv[(j >> 2) + 2];
+        const uint32_t lo = (j & 3) ? __funnelshift_r(a, bb, 8 * (j & 3)) : a;
+        const uint32_t hi = (j & 3) ? __funnelshift_r(bb, c, 8 * (j & 3)) : bb;
+        hs[j] = lz_hash_short<C::SMLS>(lo, hi);
+        fs[j] = TS[LZ_IDX(hs[j])];                                     // far candidate: the slot as earlier tiles left it
         if constexpr (C::LONG) {
-            const uint32_t hl = lz_hash8(lo, hi);
-            il[j] = hl >> (32 - C::TBITS);
-            el[j] = ((p0 + j) << LZ_TAGBITS) | (hl & LZ_TAGMASK);
-            fl[j] = TL[il[j]];
+            hl[j] = lz_hash_long<C::LMLS>(lo, hi);
+            fl[j] = TL[LZ_IDX(hl[j])];
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 3; j >= 0; j--)                                       // the thread's lowest position lands last
+    for (int j = PPT - 1; j >= 0; j--)                                 // the thread's lowest position lands last
         if ((LZ_INS_STRIDE == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
-            TS[is[j]] = es[j];
-            if constexpr (C::LONG) TL[il[j]] = el[j];
+            TS[LZ_IDX(hs[j])] = LZ_ENT(hs[j], j);
+            if constexpr (C::LONG) TL[LZ_IDX(hl[j])] = LZ_ENT(hl[j], j);
         }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int j = 0; j < PPT; j++)
         if ((LZ_INS_STRIDE == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
-            if (TS[is[j]] > es[j]) atomicMin(&TS[is[j]], es[j]);      // lost a store race: exact minimum of the tile
-            if constexpr (C::LONG) { if (TL[il[j]] > el[j]) atomicMin(&TL[il[j]], el[j]); }
+            if (TS[LZ_IDX(hs[j])] > LZ_ENT(hs[j], j)) atomicMin(&TS[LZ_IDX(hs[j])], LZ_ENT(hs[j], j));   // lost a store race: exact minimum of the tile
+            if constexpr (C::LONG) { if (TL[LZ_IDX(hl[j])] > LZ_ENT(hl[j], j)) atomicMin(&TL[LZ_IDX(hl[j])], LZ_ENT(hl[j], j)); }
         }
     __syncthreads();
-    uint32_t nibA = 0, nibL = 0, dist[4];
+    uint32_t bitsA = 0, bitsL = 0, dist[PPT];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < PPT; j++) {
         uint32_t d = 0;
         bool ok = false, okL = false;
         if (!GUARD || p0 + j < npos) {
             if constexpr (C::LONG) {
-                const uint32_t tn = el[j] - TL[il[j]], tf = el[j] - fl[j];
+                const uint32_t e = LZ_ENT(hl[j], j);
+                const uint32_t tn = e - TL[LZ_IDX(hl[j])], tf = e - fl[j];
                 const bool nearOk = (tn & BAD) == 0 && tn != 0;           // near: the tile's earliest equal-hash position, if before this one
                 okL = nearOk || (tf & BAD) == 0;
                 if (okL) d = (nearOk ? tn : tf) >> LZ_TAGBITS;
             }
             if (!okL) {
-                const uint32_t tn = es[j] - TS[is[j]], tf = es[j] - fs[j];
+                const uint32_t e = LZ_ENT(hs[j], j);
+                const uint32_t tn = e - TS[LZ_IDX(hs[j])], tf = e - fs[j];
                 const bool nearOk = (tn & BAD) == 0 && tn != 0;
                 ok = nearOk || (tf & BAD) == 0;
                 if (ok) d = (nearOk ? tn : tf) >> LZ_TAGBITS;
             }
         }
         dist[j] = d;
-        if (ok || okL) nibA |= 1u << j;
-        if (okL) nibL |= 1u << j;
+        if (ok || okL) bitsA |= 1u << j;
+        if (okL) bitsL |= 1u << j;
     }
-    *reinterpret_cast<uint2 *>(cd + p0) = make_uint2(dist[0] | (dist[1] << 16), dist[2] | (dist[3] << 16));
-    uint32_t word = nibA << (4 * (lane & 7));
-    word |= __shfl_xor_sync(FULLMASK, word, 1);
-    word |= __shfl_xor_sync(FULLMASK, word, 2);
-    word |= __shfl_xor_sync(FULLMASK, word, 4);
-    if ((lane & 7) == 0) bm[g >> 3] = word;
-    if constexpr (C::LONG) {
-        uint32_t wl = nibL << (4 * (lane & 7));
-        wl |= __shfl_xor_sync(FULLMASK, wl, 1);
-        wl |= __shfl_xor_sync(FULLMASK, wl, 2);
-        wl |= __shfl_xor_sync(FULLMASK, wl, 4);
-        if ((lane & 7) == 0) bml[g >> 3] = wl;
+#undef LZ_IDX
+#undef LZ_ENT
+    if constexpr (PPT == 8) {
+        *reinterpret_cast<uint4 *>(cd + p0) = make_uint4(dist[0] | (dist[1] << 16), dist[2] | (dist[3] << 16),
+                                                          dist[4] | (dist[5] << 16), dist[6] | (dist[7] << 16));
+        // one byte per thread, one bitmap word per four threads
+        uint32_t word = bitsA << (8 * (lane & 3));
+        word |= __shfl_xor_sync(FULLMASK, word, 1);
+        word |= __shfl_xor_sync(FULLMASK, word, 2);
+        if ((lane & 3) == 0) bm[g >> 2] = word;
+    } else {
+        *reinterpret_cast<uint2 *>(cd + p0) = make_uint2(dist[0] | (dist[1] << 16), dist[2] | (dist[3] << 16));
+        uint32_t word = bitsA << (4 * (lane & 7));
+        word |= __shfl_xor_sync(FULLMASK, word, 1);
+        word |= __shfl_xor_sync(FULLMASK, word, 2);
+        word |= __shfl_xor_sync(FULLMASK, word, 4);
+        if ((lane & 7) == 0) bm[g >> 3] = word;
+        if constexpr (C::LONG) {
+            uint32_t wl = bitsL << (4 * (lane & 7));
+            wl |= __shfl_xor_sync(FULLMASK, wl, 1);
+            wl |= __shfl_xor_sync(FULLMASK, wl, 2);
+            wl |= __shfl_xor_sync(FULLMASK, wl, 4);
+            if ((lane & 7) == 0) bml[g >> 3] = wl;
+        }
     }
 }
 
-template <int LV>
+// One warp writes staging bytes [ph, ph + fill) to gd[0, fill): the staging offset has the destination's 16-byte phase, so
+// the middle leaves as 16-byte vectors and only the ragged ends use byte stores.
+B2C_DEV void lz_warp_flush(const uint8_t *stg, uint32_t ph, uint32_t fill, uint8_t *gd, unsigned lane) {
+    __syncwarp();
+    const uint32_t head = fill < ((16 - ph) & 15) ? fill : ((16 - ph) & 15);
+    if (lane < head) gd[lane] = stg[ph + lane];
+    const uint32_t nvec = (fill - head) / 16;
+    const uint4 *sv = reinterpret_cast<const uint4 *>(stg + ph + head);
+    uint4 *gv = reinterpret_cast<uint4 *>(gd + head);
+    for (uint32_t v = lane; v < nvec; v += 32) gv[v] = sv[v];
+    const uint32_t done = head + nvec * 16;
+    if (lane < fill - done) gd[done + lane] = stg[ph + done + lane];
+    __syncwarp();
+}
+
+template <int LV, int MODE>
 B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk, uint8_t *scratch) {
     using C = LzCfg<LV>;
     using L = LzLayout<LV>;
@@ -213,17 +283,21 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     ParseShared *sh = reinterpret_cast<ParseShared *>(smem + L::SM_SH);
     uint32_t *ws2 = reinterpret_cast<uint32_t *>(smem + L::SM_SH + ((sizeof(ParseShared) + 15) / 16) * 16);
     uint16_t *plut = reinterpret_cast<uint16_t *>(ws2 + 96);   // byte-permute selector per 4-bit mask: the set bytes, in order
-    ChunkWork *W = P.work + chunk;
-    const WkLens wlen = wk_lens(P, chunk);
-    uint32_t *const wof = wk_of(P, chunk);
-    uint8_t *const wcodes = wk_codes(P, chunk, 0);
-    const uint32_t mseq = P.maxseq;
+    constexpr bool ZSTD = (MODE == LZ_MODE_ZSTD);
+    ChunkWork *W = ZSTD ? P.work + chunk : nullptr;
+    const WkLens wlen = ZSTD ? wk_lens(P, chunk) : WkLens{nullptr, nullptr, 0};
+    uint32_t *const wof = ZSTD ? wk_of(P, chunk) : nullptr;
+    uint8_t *const wcodes = ZSTD ? wk_codes(P, chunk, 0) : nullptr;
+    const uint32_t mseq = ZSTD ? P.maxseq : 0xffffffffu;
     uint16_t *cd = reinterpret_cast<uint16_t *>(scratch);
 
     const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
     const uint32_t n = chunk_size(P, chunk);
-    if (n > C::BLOCK || n > P.blockmax) {
-        if (tid == 0) { W->n = n; W->kind = 3; }   // reported as B2C_ERR_TOO_BIG by the pack kernel
+    if (n > C::BLOCK || (ZSTD && n > P.blockmax)) {
+        if (tid == 0) {
+            if constexpr (ZSTD) { W->n = n; W->kind = 3; }   // reported as B2C_ERR_TOO_BIG by the pack kernel
+            else P.out_sizes[chunk] = -3;
+        }
         return;
     }
     B2C_PHASE(0);
@@ -251,23 +325,35 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
         else (dst) = a_;                                                                         \
     } while (0)
     const uint32_t npos = (n >= 8) ? n - 7 : 0;    // positions with 8 readable bytes
-    const uint32_t ngroups = (npos + 3) / 4;
+    constexpr int PPT = C::PPT, NWRD = PPT / 4 + 2, WPT = PPT / 4;       // a thread's PPT positions read NWRD words, WPT of them its own
+    static_assert(!C::LONG || PPT == 4, "the two-table configurations keep four positions per thread");
+    const uint32_t ngroups = (npos + PPT - 1) / PPT;
     const uint32_t ntiles = (ngroups + NT - 1) / NT;
     {
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
-        if (ntiles) { LZ_WORD(w0, tid); LZ_WORD(w1, tid + 1); LZ_WORD(w2, tid + 2); }
+        uint32_t wv[NWRD], nwv[NWRD];
+#pragma unroll
+        for (int q = 0; q < NWRD; q++) { wv[q] = 0; nwv[q] = 0; }
+        if (ntiles) {
+#pragma unroll
+            for (int q = 0; q < NWRD; q++) LZ_WORD(wv[q], WPT * tid + q);
+        }
         for (uint32_t k = 0; k < ntiles; k++) {
             const uint32_t g = k * NT + tid;
-            // the next tile's three words are requested before this tile's barriers; whole tiles of an aligned chunk
-            // take the unguarded forms (block-uniform tests)
-            uint32_t nw0 = 0, nw1 = 0, nw2 = 0;
+            // the next tile's words are requested before this tile's barriers; whole tiles of an aligned chunk take the
+            // unguarded forms (block-uniform tests)
             if (k + 1 < ntiles) {
-                if (mis == 0 && (k + 2) * NT + 2 < nraw) { nw0 = B2C_LDG(gw + g + NT); nw1 = B2C_LDG(gw + g + NT + 1); nw2 = B2C_LDG(gw + g + NT + 2); }
-                else { LZ_WORD(nw0, g + NT); LZ_WORD(nw1, g + NT + 1); LZ_WORD(nw2, g + NT + 2); }
+                if (mis == 0 && WPT * (k + 2) * NT + 2 < nraw) {
+#pragma unroll
+                    for (int q = 0; q < NWRD; q++) nwv[q] = B2C_LDG(gw + WPT * (g + NT) + q);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NWRD; q++) LZ_WORD(nwv[q], WPT * (g + NT) + q);
+                }
             }
-            if (4 * (k + 1) * NT <= npos) lz_dense_tile<LV, false>(TS, TL, bm, bml, cd, g, npos, w0, w1, w2, lane);
-            else lz_dense_tile<LV, true>(TS, TL, bm, bml, cd, g, npos, w0, w1, w2, lane);
-            w0 = nw0; w1 = nw1; w2 = nw2;
+            if (PPT * (k + 1) * NT <= npos) lz_dense_tile<LV, false>(TS, TL, bm, bml, cd, g, npos, wv, lane);
+            else lz_dense_tile<LV, true>(TS, TL, bm, bml, cd, g, npos, wv, lane);
+#pragma unroll
+            for (int q = 0; q < NWRD; q++) wv[q] = nwv[q];
         }
     }
     __syncthreads();      // the tables are dead: their memory takes the chunk
@@ -433,6 +519,125 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     const uint32_t prevE0 = keyEx ? keptEndA[keyEx - 1] : 0u;          // end of the sequence before this thread's first
     const uint32_t pOff0 = keyEx ? lastOffA[keyEx - 1] : 0u;
 
+    if constexpr (!ZSTD) {
+        // -------------------------------------------------------------- S2 / Snappy emission (s2/encode_go.go:80-289)
+        // Sizes per thread -> block scan -> every thread writes its literal runs and copy / repeat tags into its warp's
+        // staging window (the lanes of a warp produce one contiguous piece of the block, in lane order), windows leave
+        // as 16-byte vectors.  A repeat tag is used whenever the offset equals the previous copy's.
+        constexpr bool SNAPPY = (MODE == LZ_MODE_SNAPPY);
+        const uint32_t hdrLen = n < 128 ? 1u : (n < 16384 ? 2u : 3u);       // uvarint(n), n <= 65536
+        const bool firstThread = (seqEx == 0);                               // no sequence before this thread's
+        uint32_t mySize = 0;
+        {
+            uint32_t pe = prevE0, po = pOff0;
+            bool fst = firstThread;
+            for (uint32_t j = firstKept; j < cnt; j++) {
+                const uint32_t r = REC(j, tid);
+                const uint32_t s0 = b + lz_rec_rel(r), e0 = s0 + ((j + 1 == cnt && myLong) ? myLong : lz_rec_len(r));
+                const uint32_t s2 = s0 > R ? s0 : R, l2 = e0 - s2, d0 = lz_rec_d(r), ll = s2 - pe;
+                mySize += s2_lit_hdr_size(ll) + ll;
+                if (SNAPPY) mySize += snappy_copy_size(d0, l2);
+                else mySize += (!fst && d0 == po) ? s2_repeat_size(d0, l2) : s2_copy_size(d0, l2);
+                pe = e0; po = d0; fst = false;
+            }
+        }
+        uint32_t bodyNoTail;
+        __syncthreads();
+        const uint32_t myOff = group_scan_excl(mySize, sh->ws, 0, NT, tid, &bodyNoTail);
+        const uint32_t lastEnd = keyTotal ? keptEndA[keyTotal - 1] : 0u;      // end of the last sequence of the block
+        const uint32_t tl = n - lastEnd;
+        const uint32_t body = bodyNoTail + s2_lit_hdr_size(tl) + tl;
+        uint8_t *gdst = P.dst_base + (uint64_t)chunk * P.dst_stride;
+        // encodeBlock's "not compressible" rule (s2/encode_all.go:88: dstLimit), blocks below minNonLiteralBlockSize
+        // (s2/encode.go:375) and the empty input are stored as one literal
+        const bool store = (n < 32) || (nseq == 0) || (body > n - (n >> 5) - 5);
+        const uint32_t total = hdrLen + (store ? s2_lit_hdr_size(n) + n : body);
+        if (total > P.dst_cap) {
+            if (tid == 0) P.out_sizes[chunk] = -4;
+        } else {
+            if (tid == 0) {
+                uint32_t o = 0, v = n;
+                while (v >= 0x80) { gdst[o++] = (uint8_t)(v | 0x80); v >>= 7; }
+                gdst[o++] = (uint8_t)v;
+                if (store) s2_put_lit_hdr(gdst + o, n);
+                else s2_put_lit_hdr(gdst + hdrLen + bodyNoTail, tl);
+                P.out_sizes[chunk] = (int64_t)total;
+            }
+            if (store) {
+                const uint32_t o0 = hdrLen + s2_lit_hdr_size(n);
+                for (uint32_t i = tid; i < n; i += NT) gdst[o0 + i] = src[i];
+            } else {
+                // (the match records are still being read, so the windows live in the candidate bitmaps, which are dead)
+                static_assert(L::STG_S2 >= 96 + 128 + 32 * 6 + 16, "a thread's piece (without a long leading run) must fit a window");
+                uint8_t *stg = smem + L::SM_STG + w * L::STG_S2;
+                uint8_t *gbody = gdst + hdrLen;
+                // A thread's piece starts with the literals since the previous sequence, which may be long (everything the
+                // earlier threads left unmatched).  A leading run of more than 96 bytes does not go through the window:
+                // when its thread is next, the warp copies it from the staged chunk straight to the destination.
+                uint32_t bigLL = 0;
+                if (kept) {
+                    const uint32_t r = REC(firstKept, tid);
+                    const uint32_t s0 = b + lz_rec_rel(r);
+                    const uint32_t ll0 = (s0 > R ? s0 : R) - prevE0;
+                    if (ll0 > 96) bigLL = ll0;
+                }
+                uint32_t curOff = myOff, curSize = mySize;     // what is left of this thread's piece
+                bool bigPending = bigLL != 0;
+                uint32_t doneLanes = 0;
+                while (doneLanes < 32) {
+                    if (__shfl_sync(FULLMASK, (int)bigPending, (int)doneLanes)) {
+                        const uint32_t ll = __shfl_sync(FULLMASK, bigLL, (int)doneLanes);
+                        const uint32_t from = __shfl_sync(FULLMASK, prevE0, (int)doneLanes);
+                        const uint32_t at = __shfl_sync(FULLMASK, curOff, (int)doneLanes);
+                        const uint32_t hb = s2_lit_hdr_size(ll);
+                        if (lane == doneLanes) { s2_put_lit_hdr(gbody + at, ll); bigPending = false; curOff += hb + ll; curSize -= hb + ll; }
+                        for (uint32_t k = lane; k < ll; k += 32) gbody[at + hb + k] = src[from + k];
+                        continue;
+                    }
+                    const uint32_t winStart = __shfl_sync(FULLMASK, curOff, (int)doneLanes);
+                    const uint32_t ph = (uint32_t)((reinterpret_cast<uintptr_t>(gbody) + winStart) & 15);
+                    const bool fits = lane >= doneLanes && !bigPending && (curOff + curSize - winStart + ph <= L::STG_S2);
+                    const unsigned fm = __ballot_sync(FULLMASK, fits) >> doneLanes;
+                    uint32_t take = (fm == 0xffffffffu >> doneLanes) ? 32 - doneLanes : (uint32_t)(__ffs((int)~fm) - 1);
+                    // (without its leading run an S2 piece is at most 96 + 128 literal bytes and 32 x (1 + 5) tag bytes: it fits.
+                    // A Snappy piece with a very long match -- 3 bytes per 60 -- may not: that thread writes to the
+                    // destination directly)
+                    const bool direct = (take == 0);
+                    if (direct) take = 1;
+                    if (lane >= doneLanes && lane < doneLanes + take && curSize) {
+                        uint8_t *d = direct ? gbody + curOff : stg + ph + (curOff - winStart);
+                        uint32_t pe = prevE0, po = pOff0;
+                        bool fst = firstThread;
+                        for (uint32_t j = firstKept; j < cnt; j++) {
+                            const uint32_t r = REC(j, tid);
+                            const uint32_t s0 = b + lz_rec_rel(r), e0 = s0 + ((j + 1 == cnt && myLong) ? myLong : lz_rec_len(r));
+                            const uint32_t s2 = s0 > R ? s0 : R, l2 = e0 - s2, d0 = lz_rec_d(r), ll = s2 - pe;
+                            if (!(j == firstKept && bigLL)) {          // (a long leading run has been written already)
+                                d += s2_put_lit_hdr(d, ll);
+                                for (uint32_t k = 0; k < ll; k++) d[k] = src[pe + k];
+                                d += ll;
+                            }
+                            if (SNAPPY) d += snappy_put_copy(d, d0, l2);
+                            else d += (!fst && d0 == po) ? s2_put_repeat(d, d0, l2) : s2_put_copy(d, d0, l2);
+                            pe = e0; po = d0; fst = false;
+                        }
+                    }
+                    const uint32_t lastLane = doneLanes + take - 1;
+                    const uint32_t winEnd = __shfl_sync(FULLMASK, curOff + curSize, (int)lastLane);
+                    if (!direct) lz_warp_flush(stg, ph, winEnd - winStart, gbody + winStart, lane);
+                    doneLanes += take;
+                }
+                // trailing literals: straight from the staged chunk
+                const uint32_t th = s2_lit_hdr_size(tl);
+                uint8_t *dt = gbody + bodyNoTail + th;
+                for (uint32_t k = tid; k < tl; k += NT) dt[k] = src[lastEnd + k];
+            }
+        }
+        __syncthreads();
+        B2C_PHASE(4);
+        B2C_PHASE(5);
+        return;
+    } else {
     // blockEnc.encode early decisions (blockenc.go:481-503): no sequences => literals-only (raw) block; then the
     // single-sequence RLE test; then `saved < 16` => raw
     uint32_t kind = 0;
@@ -558,18 +763,7 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
         for (uint32_t i0 = 0;; i0 += 4) {
             const bool last = i0 >= nr;
             if (last || ph + fill + 512 > STG) {
-                // flush [gpos, gpos + fill): head bytes up to the first 16-byte boundary, vectors, tail bytes
-                __syncwarp();
-                uint8_t *gd = glit + gpos;
-                const uint32_t head = fill < ((16 - ph) & 15) ? fill : ((16 - ph) & 15);
-                if (lane < head) gd[lane] = stg[ph + lane];
-                const uint32_t nvec = (fill - head) / 16;
-                const uint4 *sv = reinterpret_cast<const uint4 *>(stg + ph + head);
-                uint4 *gv = reinterpret_cast<uint4 *>(gd + head);
-                for (uint32_t v = lane; v < nvec; v += 32) gv[v] = sv[v];
-                const uint32_t done = head + nvec * 16;
-                if (lane < fill - done) gd[done + lane] = stg[ph + done + lane];
-                __syncwarp();
+                lz_warp_flush(stg, ph, fill, glit + gpos, lane);
                 gpos += fill; fill = 0;
                 ph = (uint32_t)((reinterpret_cast<uintptr_t>(glit) + gpos) & 15);
             }
@@ -607,6 +801,7 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     if (tid == 0) { W->n = n; W->nseq = nseq; W->nlit = nlit; W->kind = kind; W->rleLen = sh->rleLen; }
     __syncthreads();
     B2C_PHASE(5);
+    }   // zstd mode
 }
 
 // ------------------------------------------------------------------------------------------------ histograms
@@ -746,13 +941,25 @@ B2C_DEV void zstd_hist_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
 extern "C" __global__ void __launch_bounds__(LzCfg<1>::NT, LzCfg<1>::MIN_CTAS) b2c_lz_parse1_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<1>::SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<1>(smem, P, c, scratch);
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<1, LZ_MODE_ZSTD>(smem, P, c, scratch);
 }
 extern "C" __global__ void __launch_bounds__(LzCfg<2>::NT, LzCfg<2>::MIN_CTAS) b2c_lz_parse2_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<2>::SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<2>(smem, P, c, scratch);
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<2, LZ_MODE_ZSTD>(smem, P, c, scratch);
 }
+// S2 / Snappy block encoders: the same parse, tag-stream emission instead of the entropy stages (one kernel per block batch)
+#define B2C_LZ_S2_KERNEL(name, LV, MODE)                                                                                   \
+    extern "C" __global__ void __launch_bounds__(LzCfg<LV>::NT, LzCfg<LV>::MIN_CTAS) name(ZstdEncParams P) {               \
+        extern __shared__ __align__(1024) uint8_t smem[];                                                                  \
+        uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<LV>::SCRATCH_BYTES;                                 \
+        for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<LV, MODE>(smem, P, c, scratch);        \
+    }
+B2C_LZ_S2_KERNEL(b2c_lz_s2_fast_kernel, 3, LZ_MODE_S2)
+B2C_LZ_S2_KERNEL(b2c_lz_snappy_fast_kernel, 3, LZ_MODE_SNAPPY)
+B2C_LZ_S2_KERNEL(b2c_lz_s2_better_kernel, 4, LZ_MODE_S2)
+B2C_LZ_S2_KERNEL(b2c_lz_snappy_better_kernel, 4, LZ_MODE_SNAPPY)
+#undef B2C_LZ_S2_KERNEL
 extern "C" __global__ void __launch_bounds__(HIST_NT) b2c_zstd_hist_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_hist_chunk(smem, P, c);

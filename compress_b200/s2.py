@@ -1,6 +1,7 @@
 """Host-side mirror of the reference's S2 block interface for the accelerated path.
 
-Names follow klauspost/compress/s2: ``Encode`` (s2/encode.go:29), ``EncodeSnappy`` (:204), ``Decode``
+Names follow klauspost/compress/s2: ``Encode`` (s2/encode.go:29), ``EncodeBetter`` (:117), ``EncodeSnappy`` (:204),
+``EncodeSnappyBetter`` (:248), ``Decode``
 (s2/decode.go:58), ``MaxEncodedLen`` (s2/encode.go:389), ``ErrCorrupt`` / ``ErrTooLarge`` (s2/decode.go:17-26).
 The work is done by libb200comp.so through the C ABI in include/b2c.h; blocks are at most 64 KiB (the
 ``WriterBlockSize`` the GPU path is built for), larger inputs raise ``ErrTooLarge``.
@@ -15,6 +16,7 @@ from ._lib import lib, check, B2CError
 BLOCK = 1 << 16
 SLOT = BLOCK + 512
 FAST = 1
+BETTER = 2
 FLAG_SNAPPY = 1
 
 
@@ -57,7 +59,7 @@ class Codec:
         return int(lib.b2c_launch_count(self._ctx))
 
     # ---- device-resident batches --------------------------------------------------------------
-    def encode_device(self, src, sizes=None, block=BLOCK, snappy=False, dst=None, out_sizes=None):
+    def encode_device(self, src, sizes=None, block=BLOCK, snappy=False, dst=None, out_sizes=None, better=False):
         """src: uint8 CUDA tensor, block i at i*block.  Returns (dst [n, SLOT], out_sizes int64).  Async."""
         assert src.is_cuda and src.dtype == torch.uint8
         n = src.numel() // block if sizes is None else sizes.numel()
@@ -66,7 +68,7 @@ class Codec:
         if out_sizes is None:
             out_sizes = torch.empty((n,), dtype=torch.int64, device=src.device)
         stream = torch.cuda.current_stream(src.device).cuda_stream
-        check(lib.b2c_s2_encode_device(self._ctx, FAST, FLAG_SNAPPY if snappy else 0, src.data_ptr(), block,
+        check(lib.b2c_s2_encode_device(self._ctx, BETTER if better else FAST, FLAG_SNAPPY if snappy else 0, src.data_ptr(), block,
                                        None if sizes is None else sizes.data_ptr(), block, dst.data_ptr(), SLOT,
                                        out_sizes.data_ptr(), n, ctypes.c_void_p(stream)), self._ctx)
         return dst, out_sizes
@@ -97,10 +99,10 @@ class Codec:
         codes = [int(r) for r in res]
         return [outs[i][:codes[i]].tobytes() if codes[i] >= 0 else None for i in range(n)], codes
 
-    def encode_blocks(self, blocks, snappy=False):
+    def encode_blocks(self, blocks, snappy=False, better=False):
         if not blocks:
             return []
-        outs, codes = self._host(lib.b2c_s2_encode_chunks, blocks, [MaxEncodedLen(len(b)) + 16 for b in blocks], FAST,
+        outs, codes = self._host(lib.b2c_s2_encode_chunks, blocks, [MaxEncodedLen(len(b)) + 16 for b in blocks], BETTER if better else FAST,
                                  FLAG_SNAPPY if snappy else 0)
         for c in codes:
             if c == -3:
@@ -117,6 +119,14 @@ class Codec:
     def Encode(self, src):
         """s2.Encode(nil, src) for one block (s2/encode.go:29)."""
         return self.encode_blocks([src])[0]
+
+    def EncodeBetter(self, src):
+        """s2.EncodeBetter(nil, src) (s2/encode.go:117): the two-table match finder."""
+        return self.encode_blocks([src], better=True)[0]
+
+    def EncodeSnappyBetter(self, src):
+        """s2.EncodeSnappyBetter(nil, src) (s2/encode.go:248)."""
+        return self.encode_blocks([src], snappy=True, better=True)[0]
 
     def EncodeSnappy(self, src):
         """s2.EncodeSnappy(nil, src) (s2/encode.go:204): output any Snappy decoder accepts."""

@@ -50,9 +50,11 @@ enum {
     B2C_ZSTD_FRAME = 2   /* emit one complete frame per chunk (EncodeAll); otherwise bare blocks */
 };
 
-/* S2 block encoder: level and flags.  B2C_S2_FAST = s2.Encode's match finder class (s2/encode.go:29);
- * B2C_S2_SNAPPY selects Snappy-compatible output (s2.EncodeSnappy, s2/encode.go:204: no repeat tags, copies <= 64). */
-enum { B2C_S2_FAST = 1 };
+/* S2 block encoder: level and flags.  B2C_S2_FAST = s2.Encode's match finder class (s2/encode.go:29, encodeBlockGo),
+ * B2C_S2_BETTER = s2.EncodeBetter's (s2/encode.go:117, encodeBlockBetterGo64K in s2/encode_better.go:485: long 7-byte +
+ * short 4-byte table, long preferred, lazy step).  B2C_S2_SNAPPY selects Snappy-compatible output (s2.EncodeSnappy /
+ * EncodeSnappyBetter, s2/encode.go:204,248: no repeat tags, copies <= 64). */
+enum { B2C_S2_FAST = 1, B2C_S2_BETTER = 2 };
 enum { B2C_S2_SNAPPY = 1 };
 
 /* huff0: number of streams (huff0.Compress4X / Compress1X, huff0/compress.go:27,14) */

@@ -51,11 +51,11 @@ int emu_zstd_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *size
     } else {
         if (level >= 2)
             emu::launch(1, LzCfg<2>::NT, LzLayout<2>::SMEM_BYTES, [&]() {
-                for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<2>(emu::dyn_smem, P, c, P.scratch);
+                for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<2, LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
             });
         else
             emu::launch(1, LzCfg<1>::NT, LzLayout<1>::SMEM_BYTES, [&]() {
-                for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<1>(emu::dyn_smem, P, c, P.scratch);
+                for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<1, LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
             });
         emu::launch(1, HIST_NT, HIST_SMEM_BYTES, [&]() {
             for (uint32_t c = 0; c < P.nchunks; c++) zstd_hist_chunk(emu::dyn_smem, P, c);
@@ -106,21 +106,43 @@ int emu_zstd_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t 
 }
 
 // S2 (snappy = 0) / Snappy-compatible (snappy = 1) block encode of nchunks chunks (chunk i = src + i*stride).
-int emu_s2_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
-                  uint64_t dst_stride, int64_t *out_sizes, int snappy) {
-    std::vector<uint8_t> scratch(ENC_SCRATCH_BYTES, 0xCD);
+// better: 0 = s2.Encode's class, 1 = s2.EncodeBetter's; parse 0 = tile-ordered parse (product), 1 = round-1 kernel (fast only)
+int emu_s2_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
+                     uint64_t dst_stride, int64_t *out_sizes, int snappy, int better, int parse) {
+    if (parse == 1 && better) return -1;
+    std::vector<uint8_t> scratch(std::max<size_t>(ENC_SCRATCH_BYTES, std::max(LzLayout<3>::SCRATCH_BYTES, LzLayout<4>::SCRATCH_BYTES)), 0xCD);
     ZstdEncParams P;
     memset(&P, 0, sizeof(P));
     P.src_base = src; P.src_stride = stride; P.src_sizes = sizes;
     P.dst_base = dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
-    P.out_sizes = out_sizes; P.nchunks = nchunks; P.scratch = scratch.data();
-    emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
-        for (uint32_t c = 0; c < P.nchunks; c++) {
-            if (snappy) zstd_parse_chunk<LZ_MODE_SNAPPY>(emu::dyn_smem, P, c, P.scratch);
-            else zstd_parse_chunk<LZ_MODE_S2>(emu::dyn_smem, P, c, P.scratch);
-        }
-    });
+    P.out_sizes = out_sizes; P.nchunks = nchunks; P.scratch = scratch.data(); P.blockmax = 65536;
+    if (parse == 1) {
+        emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < P.nchunks; c++) {
+                if (snappy) zstd_parse_chunk<LZ_MODE_SNAPPY>(emu::dyn_smem, P, c, P.scratch);
+                else zstd_parse_chunk<LZ_MODE_S2>(emu::dyn_smem, P, c, P.scratch);
+            }
+        });
+    } else if (better) {
+        emu::launch(1, LzCfg<4>::NT, LzLayout<4>::SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < P.nchunks; c++) {
+                if (snappy) lz_parse_chunk<4, LZ_MODE_SNAPPY>(emu::dyn_smem, P, c, P.scratch);
+                else lz_parse_chunk<4, LZ_MODE_S2>(emu::dyn_smem, P, c, P.scratch);
+            }
+        });
+    } else {
+        emu::launch(1, LzCfg<3>::NT, LzLayout<3>::SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < P.nchunks; c++) {
+                if (snappy) lz_parse_chunk<3, LZ_MODE_SNAPPY>(emu::dyn_smem, P, c, P.scratch);
+                else lz_parse_chunk<3, LZ_MODE_S2>(emu::dyn_smem, P, c, P.scratch);
+            }
+        });
+    }
     return 0;
+}
+int emu_s2_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
+                  uint64_t dst_stride, int64_t *out_sizes, int snappy) {
+    return emu_s2_encode_lv(src, stride, sizes, nchunks, dst, dst_stride, out_sizes, snappy, 0, 0);
 }
 
 int emu_s2_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t *src_sizes, uint32_t n, uint8_t *dst,

@@ -64,7 +64,7 @@ def emu_decode(E, inputs, caps, desc=0):
     return outs, res
 
 
-def emu_s2_encode(E, blocks, snappy=False, desc=0):
+def emu_s2_encode(E, blocks, snappy=False, desc=0, better=False, parse=0):
     E.emu_set_lane_order(desc)
     n = len(blocks)
     stride = 65536
@@ -76,8 +76,9 @@ def emu_s2_encode(E, blocks, snappy=False, desc=0):
     dstride = 65536 + 512
     dst = np.zeros(n * dstride, dtype=np.uint8)
     outs = np.zeros(n, dtype=np.int64)
-    E.emu_s2_encode(src.ctypes.data, stride, sizes.ctypes.data, n, dst.ctypes.data, dstride, outs.ctypes.data,
-                    1 if snappy else 0)
+    rc = E.emu_s2_encode_lv(src.ctypes.data, stride, sizes.ctypes.data, n, dst.ctypes.data, dstride, outs.ctypes.data,
+                            1 if snappy else 0, 1 if better else 0, parse)
+    assert rc == 0
     return [bytes(dst[i * dstride:i * dstride + max(int(outs[i]), 0)]) for i in range(n)], outs
 
 

@@ -42,6 +42,7 @@ def emu():
     E.emu_zstd_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
                                   c.c_void_p]
     E.emu_s2_encode.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
+    E.emu_s2_encode_lv.argtypes = E.emu_s2_encode.argtypes + [c.c_int, c.c_int]
     E.emu_s2_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
                                 c.c_void_p]
     E.emu_huf_compress.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]

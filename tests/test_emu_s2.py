@@ -43,13 +43,42 @@ def test_emu_s2_encode_roundtrip(emu_lib, oracle_lib):
     assert len(enc[0]) == 65536 + 3 + 3 and enc[1] == bytes([15, 14 << 2]) + blocks[2]
 
 
+def test_emu_s2_better_and_ratios(emu_lib, oracle_lib):
+    """s2.EncodeBetter / EncodeSnappyBetter class: blocks decode with the oracle's s2Decode in
+    both lane orders, and per corpus the size is within +5 % of the reference algorithm of the same class
+    (all corpora, not one chunk); the fast class is checked the same way against s2.Encode."""
+    blocks = _blocks()
+    L = _L()
+    for snappy in (False, True):
+        a, outs = emu_s2_encode(emu_lib, blocks, snappy=snappy, better=True, desc=0)
+        b2, _ = emu_s2_encode(emu_lib, blocks, snappy=snappy, better=True, desc=1)
+        assert a == b2
+        for i, (blk, c, r) in enumerate(zip(blocks, a, outs)):
+            assert r == len(c) > 0 and r <= L.orc_s2_max_encoded_len(len(blk)), (i, r)
+            n, got = orc_decode(c, len(blk))
+            assert n == len(blk) and got == blk, (snappy, i)
+    tw = H.golden("twain.txt")
+    corp = {"twain": [tw[i:i + 65536] for i in range(0, 3 * 65536, 65536)], "html": [H.golden("html.txt")],
+            "e": [H.golden("e.txt")[:65536]], "synth": [H.synth_text(65536, 3)]}
+    for name, chunks in corp.items():
+        for better, mode in ((False, 0), (True, 1)):
+            ours = sum(len(x) for x in emu_s2_encode(emu_lib, chunks, better=better)[0])
+            ref = sum(len(orc_encode(c, mode)) for c in chunks)
+            assert ours <= 1.05 * ref, (name, better, ours, ref)
+        # Snappy-compatible output of both classes against the oracle's EncodeSnappy (it has one Snappy match finder class)
+        ours = sum(len(x) for x in emu_s2_encode(emu_lib, chunks, snappy=True)[0])
+        ref = sum(len(orc_encode(c, 2)) for c in chunks)
+        assert ours <= 1.05 * ref, (name, "snappy", ours, ref)
+
+
 def test_emu_snappy_output_is_snappy(emu_lib):
     pa = pytest.importorskip("pyarrow")
     codec = pa.Codec("snappy")
     blocks = [b for b in _blocks() if len(b)]
-    enc, _ = emu_s2_encode(emu_lib, blocks, snappy=True)
-    for i, (b, c) in enumerate(zip(blocks, enc)):
-        assert codec.decompress(c, decompressed_size=len(b)).to_pybytes() == b, i
+    for better in (False, True):
+        enc, _ = emu_s2_encode(emu_lib, blocks, snappy=True, better=better)
+        for i, (b, c) in enumerate(zip(blocks, enc)):
+            assert codec.decompress(c, decompressed_size=len(b)).to_pybytes() == b, (better, i)
 
 
 def test_emu_s2_decode(emu_lib, oracle_lib):

@@ -73,11 +73,12 @@ def test_emu_zstd_comp_crashers_small(emu_lib, level):
 def test_emu_s2_enc_regressions_small(emu_lib):
     from emu_util import emu_s2_encode
     blocks = _blocks_of([e for e in _entries("s2_enc_regressions.zip") if len(e[1]) <= 65536 + 13], 65536)
-    for snappy in (False, True):
-        enc, _ = emu_s2_encode(emu_lib, blocks, snappy=snappy)
-        for b, e in zip(blocks, enc):
-            n, dec = orc_s2_decode(e, len(b))
-            assert n == len(b) and dec == b
+    for better in (False, True):
+        for snappy in (False, True):
+            enc, _ = emu_s2_encode(emu_lib, blocks, snappy=snappy, better=better)
+            for b, e in zip(blocks, enc):
+                n, dec = orc_s2_decode(e, len(b))
+                assert n == len(b) and dec == b
 
 
 @pytest.mark.gpu
@@ -108,12 +109,13 @@ def test_gpu_s2_enc_regressions():
     pc = pa.Codec("snappy")
     codec = s2.Codec()
     blocks = _blocks_of(_entries("s2_enc_regressions.zip"), 65536)
-    for snappy in (False, True):
-        enc = codec.encode_blocks(blocks, snappy=snappy)
-        for b, e in zip(blocks, enc):
-            assert 0 < len(e) <= s2.MaxEncodedLen(len(b))
-            n, dec = orc_s2_decode(e, len(b))
-            assert n == len(b) and dec == b
-            if snappy and len(b):
-                assert pc.decompress(e, decompressed_size=len(b)).to_pybytes() == b
+    for better in (False, True):
+        for snappy in (False, True):
+            enc = codec.encode_blocks(blocks, snappy=snappy, better=better)
+            for b, e in zip(blocks, enc):
+                assert 0 < len(e) <= s2.MaxEncodedLen(len(b))
+                n, dec = orc_s2_decode(e, len(b))
+                assert n == len(b) and dec == b
+                if snappy and len(b):
+                    assert pc.decompress(e, decompressed_size=len(b)).to_pybytes() == b
     codec.close()

@@ -23,12 +23,13 @@ def test_s2_encode_blocks(codec, oracle_lib):
     from compress_b200 import s2
     blocks = _blocks()
     L = _L()
-    for snappy in (False, True):
-        enc = codec.encode_blocks(blocks, snappy=snappy)
-        for i, (b, c) in enumerate(zip(blocks, enc)):
-            assert 0 < len(c) <= L.orc_s2_max_encoded_len(len(b)) == s2.MaxEncodedLen(len(b)), i
-            n, got = orc_decode(c, len(b))
-            assert n == len(b) and got == b, (snappy, i)
+    for better in (False, True):
+        for snappy in (False, True):
+            enc = codec.encode_blocks(blocks, snappy=snappy, better=better)
+            for i, (b, c) in enumerate(zip(blocks, enc)):
+                assert 0 < len(c) <= L.orc_s2_max_encoded_len(len(b)) == s2.MaxEncodedLen(len(b)), i
+                n, got = orc_decode(c, len(b))
+                assert n == len(b) and got == b, (better, snappy, i)
     with pytest.raises(s2.ErrTooLarge):
         codec.Encode(bytes(65537))
     assert s2.MaxEncodedLen(0) == 1 and s2.MaxEncodedLen(0xffffffff) == -1
@@ -37,18 +38,33 @@ def test_s2_encode_blocks(codec, oracle_lib):
 def test_s2_gpu_matches_emulator(codec, emu_lib):
     from emu_util import emu_s2_encode
     blocks = _blocks()
-    for snappy in (False, True):
-        emu, _ = emu_s2_encode(emu_lib, blocks, snappy=snappy)
-        assert codec.encode_blocks(blocks, snappy=snappy) == emu
+    for better in (False, True):
+        for snappy in (False, True):
+            emu, _ = emu_s2_encode(emu_lib, blocks, snappy=snappy, better=better)
+            assert codec.encode_blocks(blocks, snappy=snappy, better=better) == emu
+
+
+def test_s2_ratio_per_corpus(codec, oracle_lib):
+    """Per corpus, each class is within +5 % of the reference algorithm of the same class (s2.Encode / EncodeBetter /
+    EncodeSnappy restated in the oracle) -- BASELINE config 3 "+Better" included."""
+    tw = H.golden("twain.txt")
+    corp = {"twain": [tw[i:i + 65536] for i in range(0, len(tw), 65536)], "html": [H.golden("html.txt")],
+            "e": [H.golden("e.txt")[:65536], H.golden("e.txt")[65536:]], "synth": H.synth_chunks("text", 8, seed=5)}
+    for name, chunks in corp.items():
+        for better, snappy, mode in ((False, False, 0), (True, False, 1), (False, True, 2), (True, True, 2)):
+            ours = sum(len(x) for x in codec.encode_blocks(chunks, snappy=snappy, better=better))
+            ref = sum(len(orc_encode(c, mode)) for c in chunks)
+            assert ours <= 1.05 * ref, (name, better, snappy, ours, ref)
 
 
 def test_snappy_interop(codec):
     pa = pytest.importorskip("pyarrow")
     pc = pa.Codec("snappy")
     blocks = [b for b in _blocks() if len(b)]
-    enc = codec.encode_blocks(blocks, snappy=True)
-    for b, c in zip(blocks, enc):
-        assert pc.decompress(c, decompressed_size=len(b)).to_pybytes() == b
+    for better in (False, True):
+        enc = codec.encode_blocks(blocks, snappy=True, better=better)
+        for b, c in zip(blocks, enc):
+            assert pc.decompress(c, decompressed_size=len(b)).to_pybytes() == b
     # blocks written by an independent Snappy encoder decode on the GPU
     comp = [pc.compress(b).to_pybytes() for b in blocks]
     outs, codes = codec.decode_blocks(comp, [len(b) for b in blocks])
@@ -82,8 +98,8 @@ def test_s2_roundtrip_device_256mib(codec):
     src = H.synth_text_torch(n * 65536, "cuda")
     src[10 * 65536:11 * 65536] = 0
     src[11 * 65536:12 * 65536] = torch.randint(0, 256, (65536,), dtype=torch.uint8, device="cuda")
-    for snappy in (False, True):
-        enc, sizes = codec.encode_device(src, snappy=snappy)
+    for snappy, better in ((False, False), (True, False), (False, True), (True, True)):
+        enc, sizes = codec.encode_device(src, snappy=snappy, better=better)
         torch.cuda.synchronize()
         assert int(sizes.min()) > 0
         out, osz = codec.decode_device(enc, sizes.to(torch.int32), src_stride=enc.stride(0))
