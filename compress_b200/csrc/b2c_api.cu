@@ -740,7 +740,64 @@ int b2c_zstd_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, c
     return launch_decode(ctx, P, (cudaStream_t)stream);
 }
 
-// Host-buffer batch decode: inputs are packed back to back, copied H2D, decoded, outputs copied back.
+// Host pre-scan of a zstd stream (no decompression): the frames it is made of, each with its byte range and -- when the
+// header carries one -- its Frame_Content_Size.  Header layout as in frameDec.reset (zstd/framedec.go:65-270) /
+// Header.Decode (zstd/decodeheader.go:94-229); frame length = header + block headers' sizes (blockdec.go:128-160) +
+// checksum.  Returns false when the stream cannot be walked (truncated, bad magic, reserved block type): the caller then
+// hands the whole input to one decoder warp, which reports the error the reference reports.
+struct FrameSpan { size_t off, len; uint64_t fcs; bool has_fcs, skippable; };
+static bool scan_frames(const uint8_t *p, size_t n, std::vector<FrameSpan> &out) {
+    size_t pos = 0;
+    while (pos < n) {
+        if (n - pos < 4) return false;
+        const uint32_t magic = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24);
+        if ((magic & 0xfffffff0u) == 0x184D2A50u) {          // skippable frame: magic, 4-byte size, payload
+            if (n - pos < 8) return false;
+            const uint64_t sz = (uint32_t)p[pos + 4] | ((uint32_t)p[pos + 5] << 8) | ((uint32_t)p[pos + 6] << 16) | ((uint64_t)p[pos + 7] << 24);
+            if (n - pos - 8 < sz) return false;
+            out.push_back({pos, (size_t)(8 + sz), 0, true, true});
+            pos += 8 + sz;
+            continue;
+        }
+        if (magic != 0xFD2FB528u) return false;
+        size_t q = pos + 4;
+        if (q >= n) return false;
+        const uint8_t fhd = p[q++];
+        if (fhd & 8) return false;
+        const bool single = (fhd & 32) != 0, crc = (fhd & 4) != 0;
+        if (!single) { if (q >= n) return false; q++; }
+        const unsigned did = fhd & 3, didLen = did == 3 ? 4 : did;
+        if (n - q < didLen) return false;
+        q += didLen;
+        unsigned fcsLen = 0;
+        if ((fhd >> 6) == 0) fcsLen = single ? 1 : 0; else fcsLen = 1u << (fhd >> 6);
+        if (n - q < fcsLen) return false;
+        uint64_t fcs = 0;
+        for (unsigned k = 0; k < fcsLen; k++) fcs |= (uint64_t)p[q + k] << (8 * k);
+        if (fcsLen == 2) fcs += 256;
+        q += fcsLen;
+        for (;;) {                                          // blocks
+            if (n - q < 3) return false;
+            const uint32_t bh = (uint32_t)p[q] | ((uint32_t)p[q + 1] << 8) | ((uint32_t)p[q + 2] << 16);
+            q += 3;
+            const uint32_t bt = (bh >> 1) & 3, bs = bh >> 3;
+            if (bt == 3) return false;
+            const size_t body = bt == 1 ? 1 : bs;
+            if (n - q < body) return false;
+            q += body;
+            if (bh & 1) break;
+        }
+        if (crc) { if (n - q < 4) return false; q += 4; }
+        out.push_back({pos, q - pos, fcs, fcsLen != 0, false});
+        pos = q;
+    }
+    return true;
+}
+
+// Host-buffer batch decode: inputs are packed back to back, copied H2D, decoded, outputs copied back.  A stream whose
+// frames all declare their content size (what every encoder here and the reference's EncodeAll write) is cut into its
+// frames: every frame gets its own decoder warp and the device output buffer is sized from the declared sizes instead
+// of the caller's cap (DecodeAll of a large EncodeAll output is thousands of independent frames, not one serial stream).
 int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
                            const size_t *dst_caps, int64_t *sizes_out, size_t n) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
@@ -748,37 +805,83 @@ int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *
     if (n > 0xffffffffull) return B2C_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    // meta: src_off[n] u64 | dst_off[n] u64 | out_sizes[n] i64 | src_sizes[n] u32 | dst_caps[n] u32
-    std::vector<uint64_t> meta(3 * n + n);
-    uint64_t *so = meta.data(), *dof = so + n;
-    uint32_t *ss = reinterpret_cast<uint32_t *>(meta.data() + 3 * n), *dc = ss + n;
+    // work items: one per frame (split inputs) or one per input (everything else)
+    struct Item { size_t input; size_t src_off_in_input; uint32_t src_len; uint64_t dst_off_in_input; uint32_t cap; };
+    std::vector<Item> items;
+    std::vector<size_t> first_item(n + 1, 0);
+    std::vector<uint64_t> in_base(n), out_base(n), out_len(n);
+    std::vector<char> split(n, 0);
     uint64_t inb = 0, outb = 0;
+    std::vector<FrameSpan> fr;
     for (size_t i = 0; i < n; i++) {
         if (src_sizes[i] > 0xffffffffull) return B2C_ERR_ARG;
-        so[i] = inb; dof[i] = outb;
-        ss[i] = (uint32_t)src_sizes[i];
-        dc[i] = (uint32_t)(dst_caps[i] > 0xffffffffull ? 0xffffffffull : dst_caps[i]);
+        first_item[i] = items.size();
+        const uint64_t cap = dst_caps[i] > 0xffffffffull ? 0xffffffffull : dst_caps[i];
+        fr.clear();
+        bool ok = src_sizes[i] > 0 && scan_frames((const uint8_t *)srcs[i], src_sizes[i], fr) && !fr.empty();
+        uint64_t total = 0;
+        if (ok)
+            for (const FrameSpan &f : fr) {
+                if (!f.skippable && (!f.has_fcs || f.fcs > 0xffffffffull)) { ok = false; break; }
+                total += f.skippable ? 0 : f.fcs;
+            }
+        if (ok && total > cap) ok = false;               // the serial path reports the reference's "too large" error
+        in_base[i] = inb; out_base[i] = outb;
+        if (ok) {
+            split[i] = 1;
+            uint64_t o = 0;
+            for (const FrameSpan &f : fr) {
+                if (f.skippable) continue;
+                items.push_back({i, f.off, (uint32_t)f.len, o, (uint32_t)f.fcs});
+                o += f.fcs;
+            }
+            out_len[i] = total;
+        } else {
+            items.push_back({i, 0, (uint32_t)src_sizes[i], 0, (uint32_t)cap});
+            out_len[i] = cap;
+        }
         inb += (src_sizes[i] + 15) & ~(size_t)15;
-        outb += ((size_t)dc[i] + 15) & ~(size_t)15;
+        outb += (out_len[i] + 15) & ~(uint64_t)15;
+    }
+    first_item[n] = items.size();
+    const size_t m = items.size();
+    if (m > 0xffffffffull) return B2C_ERR_ARG;
+    // meta: src_off[m] u64 | dst_off[m] u64 | out_sizes[m] i64 | src_sizes[m] u32 | dst_caps[m] u32
+    std::vector<uint64_t> meta(3 * m + m);
+    uint64_t *so = meta.data(), *dof = so + m;
+    uint32_t *ss = reinterpret_cast<uint32_t *>(meta.data() + 3 * m), *dc = ss + m;
+    for (size_t k = 0; k < m; k++) {
+        so[k] = in_base[items[k].input] + items[k].src_off_in_input;
+        dof[k] = out_base[items[k].input] + items[k].dst_off_in_input;
+        ss[k] = items[k].src_len; dc[k] = items[k].cap;
     }
     int rc;
     if ((rc = grow(ctx, &ctx->d_dec_in, &ctx->dec_in_cap, inb + 64))) return rc;
     if ((rc = grow(ctx, &ctx->d_dec_out, &ctx->dec_out_cap, outb + 64))) return rc;
     if ((rc = grow(ctx, &ctx->d_dec_meta, &ctx->dec_meta_cap, meta.size() * 8))) return rc;
     for (size_t i = 0; i < n; i++)
-        if (src_sizes[i]) CK(cudaMemcpyAsync(ctx->d_dec_in + so[i], srcs[i], src_sizes[i], cudaMemcpyHostToDevice, st));
+        if (src_sizes[i]) CK(cudaMemcpyAsync(ctx->d_dec_in + in_base[i], srcs[i], src_sizes[i], cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_dec_meta, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, st));
     ZstdDecParams P;
     memset(&P, 0, sizeof(P));
     uint64_t *dm = reinterpret_cast<uint64_t *>(ctx->d_dec_meta);
-    P.src_base = ctx->d_dec_in; P.src_offsets = dm; P.src_sizes = reinterpret_cast<uint32_t *>(dm + 3 * n);
-    P.dst_base = ctx->d_dec_out; P.dst_offsets = dm + n; P.dst_caps = P.src_sizes + n;
-    P.out_sizes = reinterpret_cast<int64_t *>(dm + 2 * n); P.nchunks = (uint32_t)n;
+    P.src_base = ctx->d_dec_in; P.src_offsets = dm; P.src_sizes = reinterpret_cast<uint32_t *>(dm + 3 * m);
+    P.dst_base = ctx->d_dec_out; P.dst_offsets = dm + m; P.dst_caps = P.src_sizes + m;
+    P.out_sizes = reinterpret_cast<int64_t *>(dm + 2 * m); P.nchunks = (uint32_t)m;
     if ((rc = launch_decode(ctx, P, st))) return rc;
-    CK(cudaMemcpyAsync(sizes_out, P.out_sizes, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    std::vector<int64_t> res(m);
+    CK(cudaMemcpyAsync(res.data(), P.out_sizes, m * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (size_t i = 0; i < n; i++)
-        if (sizes_out[i] > 0) CK(cudaMemcpyAsync(dsts[i], ctx->d_dec_out + dof[i], (size_t)sizes_out[i], cudaMemcpyDeviceToHost, st));
+    for (size_t i = 0; i < n; i++) {
+        int64_t total = 0;
+        for (size_t k = first_item[i]; k < first_item[i + 1]; k++) {
+            if (res[k] < 0) { total = res[k]; break; }                       // the first failing frame decides
+            if (split[i] && (uint64_t)res[k] != items[k].cap) { total = B2C_ERR_SIZE; break; }   // declared size not met
+            total += res[k];
+        }
+        sizes_out[i] = total;
+        if (total > 0) CK(cudaMemcpyAsync(dsts[i], ctx->d_dec_out + out_base[i], (size_t)total, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     return B2C_OK;
 }

@@ -112,3 +112,36 @@ def test_roundtrip_device_256mib(dec):
     assert bool((osz2 < 0).all())
     assert bool((out2[:, 1024:] == 0x5A).all())
     e.close()
+
+
+def test_decode_all_splits_frames(dec, oracle_lib):
+    """DecodeAll of a stream of many frames (what EncodeAll of a large input is): the host pre-scan hands every frame to
+    its own warp and sizes the device buffer from the declared content sizes; results equal the oracle's, including
+    skippable frames in between, an empty frame, a frame without a content size (serial fallback) and a corrupt frame."""
+    from compress_b200 import zstd
+    enc = zstd.Encoder(max_chunks=256)
+    data = H.synth_text(40 * 65536 + 1234, seed=21)
+    stream = enc.EncodeAll(data)                       # 41 frames
+    assert dec.DecodeAll(stream, size_hint=len(data) + 64) == data
+    skip = bytes([0x5A, 0x2A, 0x4D, 0x18, 5, 0, 0, 0]) + b"hello"
+    empty = enc.EncodeAll(b"")
+    mixed = skip + stream[:0] + empty + stream + skip
+    assert dec.DecodeAll(mixed, size_hint=len(data) + 64) == data
+    # too small a destination: the reference's "decoder size exceeded" class, not a partial result
+    with pytest.raises(zstd.ZstdError):
+        dec.DecodeAll(stream, size_hint=len(data) - 1)
+    # a libzstd streaming-style frame without content size in the middle: whole input goes to one warp, same bytes
+    import ctypes
+    Z = H.libzstd()
+    raw = data[:200000]
+    r, of = H.oracle_encode(raw, level=1)
+    nofcs = bytearray(of)
+    outs, codes = dec.decode_chunks([stream + bytes(of)], [len(data) + len(raw) + 64])
+    assert codes[0] == len(data) + len(raw) and outs[0] == data + raw
+    # corrupt one frame in the middle: the first failing frame decides, as in a serial decode
+    bad = bytearray(stream)
+    bad[len(stream) // 2] ^= 0x55
+    outs, codes = dec.decode_chunks([bytes(bad)], [len(data) + 64])
+    ro, _ = H.oracle_decode(bytes(bad), len(data) + 64)
+    assert codes[0] < 0 and ro < 0
+    enc.close()
