@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 LEVELS = {1: {"chunk": 65536, "nchunks": 16384, "name": "SpeedFastest"},
-          2: {"chunk": 131072, "nchunks": 8192, "name": "SpeedDefault"}}
+          2: {"chunk": 131072, "nchunks": 8192, "name": "SpeedDefault"},
+          3: {"chunk": 131072, "nchunks": 8192, "name": "SpeedBetterCompression"}}
 DATA_SEED = 1000
 
 
@@ -147,7 +148,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--level", type=int, default=1, choices=[1, 2])
+    ap.add_argument("--level", type=int, default=1, choices=[1, 2, 3])
     ap.add_argument("--nchunks", type=int, default=0, help="chunks per GPU (default: 1 GiB worth)")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="chunks per e2e step (default: all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -167,6 +167,8 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
         size_t d4 = (size_t)ctx->sm_count * LzCfg<4>::MIN_CTAS * LzLayout<4>::SCRATCH_BYTES;
         if (d3 > a) a = d3;
         if (d4 > a) a = d4;
+        size_t d5 = (size_t)ctx->sm_count * LzCfg<5>::MIN_CTAS * LzLayout<5>::SCRATCH_BYTES;
+        if (d5 > a) a = d5;
         ctx->scratch_slot = ((a > b ? (a > c ? a : c) : (b > c ? b : c)) + 255) & ~(size_t)255;
         const char *pe = getenv("B2C_PARSE");
         ctx->parse_r1 = (pe && strcmp(pe, "r1") == 0) ? 1 : 0;
@@ -177,6 +179,8 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)LzLayout<1>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_lz_parse2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)LzLayout<2>::SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_parse3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)LzLayout<5>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_lz_s2_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzLayout<3>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_lz_snappy_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzLayout<3>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_lz_s2_better_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LzLayout<4>::SMEM_BYTES) == cudaSuccess;
@@ -314,7 +318,7 @@ size_t b2c_zstd_bound(size_t size, int level) {
 }
 
 static uint32_t level_block(int level) { return level == B2C_LEVEL_FASTEST ? (1u << 16) : (128u << 10); }
-static bool level_ok(int level) { return level == B2C_LEVEL_FASTEST || level == B2C_LEVEL_DEFAULT; }
+static bool level_ok(int level) { return level == B2C_LEVEL_FASTEST || level == B2C_LEVEL_DEFAULT || level == B2C_LEVEL_BETTER; }
 static size_t level_slot(int level) { return (size_t)level_block(level) + 512; }   // >= MaxEncodedSize(block), 16-byte multiple
 
 // Calls that use the context's scratch / work buffers are ordered among themselves even when they are issued on
@@ -407,9 +411,12 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
             if (level == B2C_LEVEL_FASTEST) {
                 const unsigned cap = sms * LzCfg<1>::MIN_CTAS, g1 = cap < m ? cap : m;
                 b2c_lz_parse1_kernel<<<g1, LzCfg<1>::NT, LzLayout<1>::SMEM_BYTES, st>>>(P);
-            } else {
+            } else if (level == B2C_LEVEL_DEFAULT) {
                 const unsigned cap = sms * LzCfg<2>::MIN_CTAS, g1 = cap < m ? cap : m;
                 b2c_lz_parse2_kernel<<<g1, LzCfg<2>::NT, LzLayout<2>::SMEM_BYTES, st>>>(P);
+            } else {
+                const unsigned cap = sms * LzCfg<5>::MIN_CTAS, g1 = cap < m ? cap : m;
+                b2c_lz_parse3_kernel<<<g1, LzCfg<5>::NT, LzLayout<5>::SMEM_BYTES, st>>>(P);
             }
             PEV(2);
             const unsigned gh = sms * 7 < m ? sms * 7 : m;

@@ -46,7 +46,7 @@ constexpr uint32_t LZ_EMPTY = 0xffffffffu;
 constexpr uint32_t LZ_EXT_CAP = 256;        // per-thread forward extension limit; longer matches are finished by warp 0
 
 template <int LV> struct LzCfg;
-enum { LZ_ZSTD1 = 1, LZ_ZSTD2 = 2, LZ_S2FAST = 3, LZ_S2BETTER = 4 };
+enum { LZ_ZSTD1 = 1, LZ_ZSTD2 = 2, LZ_S2FAST = 3, LZ_S2BETTER = 4, LZ_ZSTD3 = 5 };
 template <> struct LzCfg<1> {
     static constexpr int NT = 512;
     static constexpr uint32_t BLOCK = 65536;
@@ -63,6 +63,21 @@ template <> struct LzCfg<2> {
     static constexpr bool LONG = true;
     static constexpr int SMLS = 5, LMLS = 8;
     static constexpr int PPT = 4;
+    static constexpr uint32_t TBITS = 14;
+    static constexpr uint32_t KREC = 8;
+    static constexpr int MIN_CTAS = 1;
+};
+
+// zstd level 3 (SpeedBetterCompression, zstd/enc_better.go:56-568): the level-2 shape with the finest tile order this
+// kernel offers -- one position per thread and tile, so a position's "near" candidate comes from the previous 1024
+// positions at most and its "far" candidate from everything before: the closest this parse gets to the reference's
+// always-current tables (its chained long table, :298-347, is replaced by the near / far pair of every slot).
+template <> struct LzCfg<5> {
+    static constexpr int NT = 1024;
+    static constexpr uint32_t BLOCK = 131072;
+    static constexpr bool LONG = true;
+    static constexpr int SMLS = 5, LMLS = 8;
+    static constexpr int PPT = 1;
     static constexpr uint32_t TBITS = 14;
     static constexpr uint32_t KREC = 8;
     static constexpr int MIN_CTAS = 1;
@@ -114,7 +129,7 @@ template <int LV> struct LzLayout {
     static constexpr uint32_t SCRATCH_BYTES = DIST_BYTES + (LZ_MAXREC - C::KREC) * C::NT * 4;
 };
 static_assert(2 * (LzLayout<1>::SMEM_BYTES + 1024) <= 228 * 1024, "two level-1 parse CTAs must fit one SM");
-static_assert(LzLayout<2>::SMEM_BYTES <= 227 * 1024, "the level-2 parse CTA must fit one SM");
+static_assert(LzLayout<2>::SMEM_BYTES <= 227 * 1024 && LzLayout<5>::SMEM_BYTES <= 227 * 1024, "the level-2 / level-3 parse CTA must fit one SM");
 static_assert(2 * (LzLayout<3>::SMEM_BYTES + 1024) <= 228 * 1024 && 2 * (LzLayout<4>::SMEM_BYTES + 1024) <= 228 * 1024, "two S2 parse CTAs must fit one SM");
 
 // hashes: two 32-bit multiply-adds (the reference's hashLen is a 64-bit multiply, zstd/hash.go:27-33; table contents
@@ -165,7 +180,7 @@ B2C_DEV uint32_t lz_rec_d(uint32_t r) { return r >> 16; }
 // the position, which the walk rejects).
 template <int LV, bool GUARD>
 B2C_DEV void lz_dense_tile(uint32_t *TS, uint32_t *TL, uint32_t *bm, uint32_t *bml, uint16_t *cd, uint32_t g, uint32_t npos,
-                           const uint32_t (&wv)[LzCfg<LV>::PPT / 4 + 2], unsigned lane) {
+                           const uint32_t (&wv)[LzCfg<LV>::PPT < 4 ? 3 : LzCfg<LV>::PPT / 4 + 2], unsigned lane) {
     using C = LzCfg<LV>;
     constexpr int PPT = C::PPT;
     constexpr uint32_t BAD = 0x80000000u | LZ_TAGMASK | (C::BLOCK > 65536 ? 0x40000000u : 0u);   // wrong tag, not earlier, or >= 64 KiB away
@@ -176,9 +191,17 @@ B2C_DEV void lz_dense_tile(uint32_t *TS, uint32_t *TL, uint32_t *bm, uint32_t *b
 #define LZ_ENT(h, j) (((p0 + (j)) << LZ_TAGBITS) | ((h) & LZ_TAGMASK))
 #pragma unroll
     for (int j = 0; j < PPT; j++) {
-        const uint32_t a = wv[j >> 2], bb = wv[(j >> 2) + 1], c = wv[(j >> 2) + 2];
-        const uint32_t lo = (j & 3) ? __funnelshift_r(a, bb, 8 * (j & 3)) : a;
-        const uint32_t hi = (j & 3) ? __funnelshift_r(bb, c, 8 * (j & 3)) : bb;
+        uint32_t lo, hi;
+        if constexpr (PPT < 4) {        // the thread's first position is not word aligned: byte offset (PPT * g) & 3, + j
+            const uint32_t bo = ((PPT * g) & 3u) + j;          // 0 .. 4
+            const uint32_t sh = (bo & 3u) * 8;
+            const uint32_t a = bo >= 4 ? wv[1] : wv[0], bb = bo >= 4 ? wv[2] : wv[1], c = bo >= 4 ? 0u : wv[2];
+            lo = __funnelshift_r(a, bb, sh); hi = __funnelshift_r(bb, c, sh);
+        } else {
+            const uint32_t a = wv[j >> 2], bb = wv[(j >> 2) + 1], c = wv[(j >> 2) + 2];
+            lo = (j & 3) ? __funnelshift_r(a, bb, 8 * (j & 3)) : a;
+            hi = (j & 3) ? __funnelshift_r(bb, c, 8 * (j & 3)) : bb;
+        }
         hs[j] = lz_hash_short<C::SMLS>(lo, hi);
         fs[j] = TS[LZ_IDX(hs[j])];                                     // far candidate: the slot as earlier tiles left it
         if constexpr (C::LONG) {
@@ -236,6 +259,20 @@ B2C_DEV void lz_dense_tile(uint32_t *TS, uint32_t *TL, uint32_t *bm, uint32_t *b
         word |= __shfl_xor_sync(FULLMASK, word, 1);
         word |= __shfl_xor_sync(FULLMASK, word, 2);
         if ((lane & 3) == 0) bm[g >> 2] = word;
+    } else if constexpr (PPT == 1) {
+        cd[p0] = (uint16_t)dist[0];
+        const unsigned wa = __ballot_sync(FULLMASK, bitsA & 1u);
+        if (lane == 0) bm[g >> 5] = wa;
+        if constexpr (C::LONG) {
+            const unsigned wl = __ballot_sync(FULLMASK, bitsL & 1u);
+            if (lane == 0) bml[g >> 5] = wl;
+        }
+    } else if constexpr (PPT == 2) {
+        *reinterpret_cast<uint32_t *>(cd + p0) = dist[0] | (dist[1] << 16);
+        uint32_t word = bitsA << (2 * (lane & 15)), wl = bitsL << (2 * (lane & 15));
+#pragma unroll
+        for (int x = 1; x < 16; x <<= 1) { word |= __shfl_xor_sync(FULLMASK, word, x); wl |= __shfl_xor_sync(FULLMASK, wl, x); }
+        if ((lane & 15) == 0) { bm[g >> 4] = word; if constexpr (C::LONG) bml[g >> 4] = wl; }
     } else {
         *reinterpret_cast<uint2 *>(cd + p0) = make_uint2(dist[0] | (dist[1] << 16), dist[2] | (dist[3] << 16));
         uint32_t word = bitsA << (4 * (lane & 7));
@@ -325,8 +362,9 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
         else (dst) = a_;                                                                         \
     } while (0)
     const uint32_t npos = (n >= 8) ? n - 7 : 0;    // positions with 8 readable bytes
-    constexpr int PPT = C::PPT, NWRD = PPT / 4 + 2, WPT = PPT / 4;       // a thread's PPT positions read NWRD words, WPT of them its own
-    static_assert(!C::LONG || PPT == 4, "the two-table configurations keep four positions per thread");
+    constexpr int PPT = C::PPT, NWRD = PPT < 4 ? 3 : PPT / 4 + 2;      // a thread's PPT positions read NWRD words from word (PPT * g) / 4 on
+    static_assert(!C::LONG || PPT <= 4, "the two-table configurations keep at most four positions per thread");
+#define LZ_WI(gg) ((uint32_t)(PPT * (gg)) >> 2)
     const uint32_t ngroups = (npos + PPT - 1) / PPT;
     const uint32_t ntiles = (ngroups + NT - 1) / NT;
     {
@@ -335,19 +373,19 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
         for (int q = 0; q < NWRD; q++) { wv[q] = 0; nwv[q] = 0; }
         if (ntiles) {
 #pragma unroll
-            for (int q = 0; q < NWRD; q++) LZ_WORD(wv[q], WPT * tid + q);
+            for (int q = 0; q < NWRD; q++) LZ_WORD(wv[q], LZ_WI(tid) + q);
         }
         for (uint32_t k = 0; k < ntiles; k++) {
             const uint32_t g = k * NT + tid;
             // the next tile's words are requested before this tile's barriers; whole tiles of an aligned chunk take the
             // unguarded forms (block-uniform tests)
             if (k + 1 < ntiles) {
-                if (mis == 0 && WPT * (k + 2) * NT + 2 < nraw) {
+                if (mis == 0 && LZ_WI((k + 2) * NT) + 3 < nraw) {
 #pragma unroll
-                    for (int q = 0; q < NWRD; q++) nwv[q] = B2C_LDG(gw + WPT * (g + NT) + q);
+                    for (int q = 0; q < NWRD; q++) nwv[q] = B2C_LDG(gw + LZ_WI(g + NT) + q);
                 } else {
 #pragma unroll
-                    for (int q = 0; q < NWRD; q++) LZ_WORD(nwv[q], WPT * (g + NT) + q);
+                    for (int q = 0; q < NWRD; q++) LZ_WORD(nwv[q], LZ_WI(g + NT) + q);
                 }
             }
             if (PPT * (k + 1) * NT <= npos) lz_dense_tile<LV, false>(TS, TL, bm, bml, cd, g, npos, wv, lane);
@@ -388,6 +426,7 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     }
 #undef LZ_WORD
 #undef LZ_RAW
+#undef LZ_WI
     B2C_PHASE(2);
 
     // ---------------------------------------------------------------- P3: walk, one thread per 128-byte range
@@ -947,6 +986,11 @@ extern "C" __global__ void __launch_bounds__(LzCfg<2>::NT, LzCfg<2>::MIN_CTAS) b
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<2>::SCRATCH_BYTES;
     for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<2, LZ_MODE_ZSTD>(smem, P, c, scratch);
+}
+extern "C" __global__ void __launch_bounds__(LzCfg<5>::NT, LzCfg<5>::MIN_CTAS) b2c_lz_parse3_kernel(ZstdEncParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<5>::SCRATCH_BYTES;
+    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<5, LZ_MODE_ZSTD>(smem, P, c, scratch);
 }
 // S2 / Snappy block encoders: the same parse, tag-stream emission instead of the entropy stages (one kernel per block batch)
 #define B2C_LZ_S2_KERNEL(name, LV, MODE)                                                                                   \

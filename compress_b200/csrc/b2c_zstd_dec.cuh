@@ -71,11 +71,14 @@ struct ZstdDecParams {
 // a stream is at most one compressed block (128 KiB).
 struct BrB {
     const uint8_t *in; uint32_t len; uint32_t total; uint32_t fed;   // fed = bits moved into the window so far
-    uint64_t bits; uint32_t avail; int32_t nextByte;     // stream bytes below nextByte are not in `bits` yet
-    uint32_t ahead;                                      // the 32 bits below nextByte, requested one refill early
-    // word-aligned view of the stream for the refills: in + nextByte keeps its alignment (nextByte moves by 4), so
-    // every refill needs one new aligned word and a fixed funnel shift
-    const uint32_t *wp; uint32_t wsh, whi;               // wp = aligned word holding byte nextByte; whi = *wp
+    uint64_t bits; uint32_t avail;
+    // look-ahead queue: the 128 bits below the window, requested four refills early (an L2 round trip lasts several
+    // refills of a Huffman / sequence walk, so one word of look-ahead left the walk waiting on memory)
+    uint32_t ahead, ahead1, ahead2, ahead3;
+    int32_t fb;                                          // stream bytes below fb have not been requested yet
+    // word-aligned view of the stream for the fetches: in + fb keeps its alignment (fb moves by 4), so every fetch needs
+    // one new aligned word and a fixed funnel shift
+    const uint32_t *wp; uint32_t wsh, whi;               // wp = aligned word holding byte fb; whi = *wp
     B2C_DEV uint32_t load32_slow(int32_t idx) const {    // bytes outside [0, len) read as zero
         uint32_t v = 0;
 #pragma unroll
@@ -85,21 +88,21 @@ struct BrB {
         }
         return v;
     }
-    // the 32 bits just below nextByte; moves the word view down by one word
+    // the 32 bits just below fb; moves the word view down by one word
     B2C_DEV uint32_t fetch_below() {
         uint32_t v;
-        if (nextByte >= 4) {
+        if (fb >= 4) {
             const uint32_t lo = wp[-1];
             v = wsh ? __funnelshift_r(lo, whi, wsh) : lo;
             whi = lo;
         } else {
-            v = load32_slow(nextByte - 4);
+            v = (fb > -4) ? load32_slow(fb - 4) : 0u;     // below the start of the stream: zeros
         }
-        wp -= 1;
+        wp -= 1; fb -= 4;
         return v;
     }
     B2C_DEV int init(const uint8_t *p, uint32_t n) {
-        in = p; len = n; total = 0; fed = 0; bits = 0; avail = 0; nextByte = 0; ahead = 0; wp = nullptr; wsh = 0; whi = 0;
+        in = p; len = n; total = 0; fed = 0; bits = 0; avail = 0; fb = 0; ahead = ahead1 = ahead2 = ahead3 = 0; wp = nullptr; wsh = 0; whi = 0;
         if (n < 1) return -1;
         const uint8_t v = p[n - 1];
         if (v == 0) return -1;
@@ -108,18 +111,19 @@ struct BrB {
         const uint64_t win = (uint64_t)load32_slow(cbyte) | ((uint64_t)load32_slow(cbyte + 4) << 32);
         const uint32_t k = (uint32_t)((int32_t)total - 8 * cbyte);    // payload bits inside the window: 57..64
         bits = win << (64 - k);
-        avail = k; fed = k; nextByte = cbyte;
+        avail = k; fed = k; fb = cbyte;
         const uintptr_t a = reinterpret_cast<uintptr_t>(p) + (uintptr_t)(intptr_t)cbyte;   // may lie below p for tiny streams
         wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         wsh = (uint32_t)(a & 3) * 8;
-        whi = (cbyte >= 4) ? *wp : 0u;                   // only used by the fast path (nextByte >= 4)
-        ahead = fetch_below();
+        whi = (cbyte >= 4) ? *wp : 0u;                   // only used by the fast path (fb >= 4)
+        ahead = fetch_below(); ahead1 = fetch_below(); ahead2 = fetch_below(); ahead3 = fetch_below();
         return 0;
     }
     B2C_DEV void refill32() {     // requires avail <= 32
         bits |= (uint64_t)ahead << (32 - avail);
-        avail += 32; fed += 32; nextByte -= 4;
-        ahead = fetch_below();
+        avail += 32; fed += 32;
+        ahead = ahead1; ahead1 = ahead2; ahead2 = ahead3;
+        ahead3 = fetch_below();
     }
     B2C_DEV uint32_t pos() const { return fed - avail; }          // bits consumed
     // next n bits, 0 <= n <= 32, without consuming them
@@ -738,14 +742,31 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const DecCta *dc, const uint8_t *
                         }
                         const unsigned bad = __ballot_sync(FULLMASK, err != 0);
                         if (bad) DFAIL(__shfl_sync(FULLMASK, err, __ffs((int)bad) - 1));
-                        // ---- literal runs: short ones by their lane, long ones by the warp
-                        const bool longLit = mine && myLL >= 96;
-                        if (mine && !longLit) for (uint32_t k = 0; k < myLL; k++) out[myOut + k] = literals[myLit + k];
-                        for (unsigned m = __ballot_sync(FULLMASK, longLit); m; m &= m - 1) {
-                            const int f = __ffs((int)m) - 1;
-                            const uint64_t fo = __shfl_sync(FULLMASK, myOut, f);
-                            const uint32_t fl = __shfl_sync(FULLMASK, myLit, f), fn = __shfl_sync(FULLMASK, myLL, f);
-                            for (uint32_t k = lane; k < fn; k += 32) out[fo + k] = literals[fl + k];
+                        // ---- literal runs of the batch: their source bytes are one contiguous piece of the literal buffer, so
+                        // the warp copies it with coalesced loads; every byte finds its sequence by a binary search over the
+                        // lanes' inclusive literal counts (a per-lane byte loop left 31 lanes waiting on one L2 round trip
+                        // per byte)
+                        {
+                            const uint32_t totLit = __shfl_sync(FULLMASK, llIncl, 31);
+                            const uint32_t myOutLo = (uint32_t)myOut, myOutHi = (uint32_t)(myOut >> 32);
+                            for (uint32_t k0 = 0; k0 < totLit; k0 += 32) {
+                                const uint32_t k = k0 + lane;
+                                uint32_t owner = 0;                       // first lane whose inclusive count exceeds k
+#pragma unroll
+                                for (int st = 16; st > 0; st >>= 1) {
+                                    const uint32_t c = owner + st - 1;
+                                    const uint32_t v = __shfl_sync(FULLMASK, llIncl, (int)(c & 31));
+                                    if (c < 32 && v <= k) owner += st;
+                                }
+                                const uint32_t oIncl = __shfl_sync(FULLMASK, llIncl, (int)(owner & 31));
+                                const uint32_t oLL = __shfl_sync(FULLMASK, myLL, (int)(owner & 31));
+                                const uint32_t oLo = __shfl_sync(FULLMASK, myOutLo, (int)(owner & 31));
+                                const uint32_t oHi = __shfl_sync(FULLMASK, myOutHi, (int)(owner & 31));
+                                if (k < totLit) {
+                                    const uint64_t ob = ((uint64_t)oHi << 32) | oLo;
+                                    out[ob + (k - (oIncl - oLL))] = literals[litPos + k];
+                                }
+                            }
                         }
                         __syncwarp();
                         // ---- matches in waves
@@ -766,7 +787,17 @@ B2C_DEV int64_t zstd_decode_input(DecWarp *dw, const DecCta *dc, const uint8_t *
                             const bool longM = ready && myML >= 96;
                             if (ready && !longM) {
                                 const uint8_t *from = out + myDst - myMO;
-                                for (uint32_t k = 0; k < myML; k++) out[myDst + k] = from[k];
+                                uint32_t k = 0;
+                                if (myMO >= 8) {        // the next eight source bytes are final: eight loads in flight per round trip
+                                    for (; k + 8 <= myML; k += 8) {
+                                        uint8_t t8[8];
+#pragma unroll
+                                        for (int q = 0; q < 8; q++) t8[q] = from[k + q];
+#pragma unroll
+                                        for (int q = 0; q < 8; q++) out[myDst + k + q] = t8[q];
+                                    }
+                                }
+                                for (; k < myML; k++) out[myDst + k] = from[k];
                             }
                             for (unsigned m = __ballot_sync(FULLMASK, longM); m; m &= m - 1) {
                                 const int f = __ffs((int)m) - 1;

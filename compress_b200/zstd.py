@@ -17,9 +17,10 @@ from ._lib import lib, check, B2CError
 
 SpeedFastest = 1
 SpeedDefault = 2
+SpeedBetterCompression = 3
 CHUNK = 1 << 16           # SpeedFastest block size, zstd/encoder_options.go:248-252
 SLOT = CHUNK + 512        # per-chunk output slot (>= MaxEncodedSize(CHUNK))
-BLOCK = {SpeedFastest: 1 << 16, SpeedDefault: 128 << 10}   # zstd/encoder_options.go:41,248-252
+BLOCK = {SpeedFastest: 1 << 16, SpeedDefault: 128 << 10, SpeedBetterCompression: 128 << 10}   # zstd/encoder_options.go:41,248-252
 FLAG_CRC = 1
 FLAG_FRAME = 2
 
@@ -36,7 +37,7 @@ class Encoder:
         if not torch.cuda.is_available() or lib.b2c_device_count() == 0:
             raise B2CError("no CUDA device: compress_b200 has no CPU fallback")
         if level not in BLOCK:
-            raise B2CError("levels on the GPU path: SpeedFastest, SpeedDefault")
+            raise B2CError("levels on the GPU path: SpeedFastest, SpeedDefault, SpeedBetterCompression")
         self.level = level
         self.block = BLOCK[level]
         self.slot = self.block + 512

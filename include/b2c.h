@@ -64,7 +64,7 @@ enum { B2C_HUF_ERR_INCOMPRESSIBLE = -1, B2C_HUF_ERR_USE_RLE = -2 };   /* ErrTooB
 
 /* zstd levels (zstd.EncoderLevel, zstd/encoder_options.go:163-190): SpeedFastest = 64 KiB blocks, one hash table
  * (zstd/enc_fast.go); SpeedDefault = 128 KiB blocks, long + short table with a lazy step (zstd/enc_dfast.go) */
-enum { B2C_LEVEL_FASTEST = 1, B2C_LEVEL_DEFAULT = 2 };
+enum { B2C_LEVEL_FASTEST = 1, B2C_LEVEL_DEFAULT = 2, B2C_LEVEL_BETTER = 3 };   /* 3: SpeedBetterCompression (zstd/enc_better.go), 128 KiB blocks */
 
 typedef struct b2c_ctx b2c_ctx;
 

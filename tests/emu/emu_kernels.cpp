@@ -24,7 +24,7 @@ int emu_zstd_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *size
                        uint8_t *dbg_lits, uint32_t dbg_seq_cap, int level, int parse) {
     const uint32_t blockmax = level >= 2 ? 131072u : 65536u;
     if (parse == 1 && level != 1) return -1;
-    std::vector<uint8_t> scratch(std::max<size_t>(ENC_SCRATCH_BYTES, std::max(LzLayout<1>::SCRATCH_BYTES, LzLayout<2>::SCRATCH_BYTES)), 0xCD);
+    std::vector<uint8_t> scratch(std::max<size_t>(ENC_SCRATCH_BYTES, std::max(LzLayout<1>::SCRATCH_BYTES, std::max(LzLayout<2>::SCRATCH_BYTES, LzLayout<5>::SCRATCH_BYTES))), 0xCD);
     ChunkWork *work = (ChunkWork *)aligned_alloc(16, sizeof(ChunkWork) * (size_t)nchunks);
     memset(work, 0xCD, sizeof(ChunkWork) * (size_t)nchunks);
     const uint64_t pstride = wk_pool_stride(blockmax);
@@ -49,7 +49,11 @@ int emu_zstd_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *size
             for (uint32_t c = 0; c < P.nchunks; c++) zstd_parse_chunk<LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
         });
     } else {
-        if (level >= 2)
+        if (level >= 3)
+            emu::launch(1, LzCfg<5>::NT, LzLayout<5>::SMEM_BYTES, [&]() {
+                for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<5, LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
+            });
+        else if (level >= 2)
             emu::launch(1, LzCfg<2>::NT, LzLayout<2>::SMEM_BYTES, [&]() {
                 for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<2, LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
             });

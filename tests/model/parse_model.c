@@ -27,6 +27,7 @@ typedef struct {
     uint32_t tile;         /* dyn only: >0 = a position only sees insertions from earlier tiles of this many positions */
     uint32_t local;        /* tile only: 1 = plus the latest equal-hash position inside the same aligned 32-position group */
     uint32_t lag;          /* dyn only: candidates are at least this far back (exact latest otherwise) */
+    uint32_t both;         /* 1 = the walk extends the near and the far candidate and keeps the longer match */
     uint32_t dyn;          /* 1 = candidate = latest earlier position with the same hash (upper bound: a dynamic table) */
 } pm_cfg;
 
@@ -61,9 +62,10 @@ int pm_parse(const uint8_t *src, uint32_t n, const pm_cfg *c, uint32_t *triples,
             if (EL[hl] == 0xffffffffu || (c->latest && p < H)) EL[hl] = p;
         }
     }
-    uint32_t *PS = NULL, *PL = NULL;
+    uint32_t *PS = NULL, *PL = NULL, *FS = NULL, *FLg = NULL;   /* F*: far candidates kept beside the near ones (both=1) */
     if (c->dyn) {
-        PS = malloc(4 * (npos + 1)); PL = malloc(4 * (npos + 1));
+        PS = malloc(4 * (npos + 1)); PL = malloc(4 * (npos + 1)); FS = malloc(4 * (npos + 1)); FLg = malloc(4 * (npos + 1));
+        memset(FS, 0xff, 4 * (npos + 1)); memset(FLg, 0xff, 4 * (npos + 1));
         memset(ES, 0xff, sizeof(uint32_t) << c->shortBits);
         if (EL) memset(EL, 0xff, sizeof(uint32_t) << c->longBits);
         const uint32_t TL = c->tile ? c->tile : 1;
@@ -73,6 +75,7 @@ int pm_parse(const uint8_t *src, uint32_t n, const pm_cfg *c, uint32_t *triples,
                 uint64_t v = rd64(src + p);
                 PS[p] = ES[hashN(v, c->shortMls, c->shortBits)];
                 if (EL) PL[p] = EL[hashN(v, c->longMls, c->longBits)];
+                FS[p] = PS[p]; if (EL) FLg[p] = PL[p];
                 if (c->local) {   /* nearest earlier position of the same 32-group with the same hash */
                     for (uint32_t q = p; q-- > (p & ~31u);) {
                         uint64_t vq = rd64(src + q);
@@ -150,6 +153,17 @@ int pm_parse(const uint8_t *src, uint32_t n, const pm_cfg *c, uint32_t *triples,
             if (cand == 0xffffffffu) { p++; continue; }
             uint32_t len = 4;
             while (p + len < N && src[p + len] == src[cand + len]) len++;
+            if (c->both && c->dyn) {
+                uint32_t alts[2] = {FS[p], EL ? FLg[p] : 0xffffffffu};
+                for (int a = 0; a < 2; a++) {
+                    uint32_t q = alts[a];
+                    if (q == 0xffffffffu || q >= p || q == cand || rd32(src + q) != (uint32_t)v) continue;
+                    if (c->maxDist && p - q > c->maxDist) continue;
+                    uint32_t l2 = 4;
+                    while (p + l2 < N && src[p + l2] == src[q + l2]) l2++;
+                    if (l2 > len + 1) { len = l2; cand = q; }
+                }
+            }
             uint32_t s = p, t = cand;
             while (s > nextEmit && t > 0 && src[s - 1] == src[t - 1]) { s--; t--; len++; }
             recs[nrec].s = s; recs[nrec].len = len; recs[nrec].dist = p - cand; nrec++;
@@ -210,6 +224,6 @@ int pm_parse(const uint8_t *src, uint32_t n, const pm_cfg *c, uint32_t *triples,
     }
     memcpy(lits + nl, src + prevE, N - prevE); nl += N - prevE;
     *nlit_out = nl;
-    free(PS); free(PL); free(ES); free(EL); free(recs); free(rfirst); free(kept);
+    free(PS); free(PL); free(FS); free(FLg); free(ES); free(EL); free(recs); free(rfirst); free(kept);
     return (int)nk;
 }

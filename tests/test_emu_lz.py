@@ -1,6 +1,6 @@
 """The tile-ordered parse (compress_b200/csrc/b2c_lz.cuh: zstd levels 1 and 2) under the SIMT emulator.
 
-SURVEY section 8 rows a-2 (fastEncoder), a-3 (doubleFastEncoder), a-5/a-6: the GPU match finders are a different,
+SURVEY section 8 rows a-2 (fastEncoder), a-3 (doubleFastEncoder), a-4 (betterFastEncoder), a-5/a-6: the GPU match finders are a different,
 deterministic, parallel parse, so parity is layered: the entropy stage is byte-identical to the
 oracle's blockEnc.encode for the same parse (raw / RLE decisions included), every frame decodes with the pinned
 decoder oracle and libzstd, sizes respect MaxEncodedSize, output size is within +3 % of the reference algorithm at the
@@ -23,7 +23,7 @@ def _edge(block):
             b"abcd" * 5000, b"0123456789" * 300, tw[:block - 1], tw[:block - 15], bytes(block)]
 
 
-@pytest.mark.parametrize("level", [1, 2])
+@pytest.mark.parametrize("level", [1, 2, 3])
 def test_lz_edge_cases(emu_lib, level):
     chunks = _edge(65536 if level == 1 else 131072)
     frames, outs, hdr, seqs, lits = emu_encode(emu_lib, chunks, level=level)
@@ -31,7 +31,7 @@ def test_lz_edge_cases(emu_lib, level):
     check_frames(chunks, frames, hdr, seqs, lits, label="lz-edge-L%d" % level, level=level)
 
 
-@pytest.mark.parametrize("level", [1, 2])
+@pytest.mark.parametrize("level", [1, 2, 3])
 def test_lz_corpora_ratio(emu_lib, level):
     """Ratio tolerance against the reference algorithm (oracle restatement) at the same level and chunking: <= +3 %
     per corpus -- Twain, HTML, e.txt, synthetic text (no corpus is excluded)."""
@@ -47,7 +47,7 @@ def test_lz_corpora_ratio(emu_lib, level):
         assert got <= ref * 1.03, (name, level, got, ref)
 
 
-@pytest.mark.parametrize("level", [1, 2])
+@pytest.mark.parametrize("level", [1, 2, 3])
 def test_lz_deterministic_lane_order(emu_lib, level):
     tw = H.golden("twain.txt")
     chunks = [tw[200000:200000 + 20000], b"xyz" * 3000, H.synth_text(30000, 11), bytes(5000) + tw[:3000] + bytes(70)]

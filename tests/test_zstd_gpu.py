@@ -26,9 +26,17 @@ def enc2():
     e.close()
 
 
-@pytest.fixture(params=[1, 2])
-def lv_enc(request, enc, enc2):
-    return enc if request.param == 1 else enc2
+@pytest.fixture(scope="module")
+def enc3():
+    from compress_b200 import zstd
+    e = zstd.Encoder(level=zstd.SpeedBetterCompression, max_chunks=2048)
+    yield e
+    e.close()
+
+
+@pytest.fixture(params=[1, 2, 3])
+def lv_enc(request, enc, enc2, enc3):
+    return {1: enc, 2: enc2, 3: enc3}[request.param]
 
 
 def _to_device(chunks, stride=65536):
