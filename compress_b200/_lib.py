@@ -91,6 +91,11 @@ def _load():
     lib.b2c_huf_decompress_device.argtypes = [
         c.c_void_p, c.c_int, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_void_p,
         c.c_uint32, c.c_void_p]
+    for nm in ("b2c_huf_compress_chunks", "b2c_huf_decompress_chunks"):
+        getattr(lib, nm).restype = c.c_int
+        getattr(lib, nm).argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
+    lib.b2c_huf_read_table.restype = c.c_int
+    lib.b2c_huf_read_table.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
     lib.b2c_queue_create.restype = c.c_void_p
     lib.b2c_queue_create.argtypes = [c.c_int, c.c_size_t, c.c_uint]
     lib.b2c_queue_destroy.argtypes = [c.c_void_p]
@@ -115,6 +120,7 @@ EXPORTED_SYMBOLS = [
     "b2c_zstd_decode_device", "b2c_zstd_decode_chunks", "b2c_profile_enable", "b2c_profile_read",
     "b2c_huf_compress_device", "b2c_huf_decompress_device",
     "b2c_s2_bound", "b2c_s2_encode_device", "b2c_s2_decode_device", "b2c_s2_encode_chunks", "b2c_s2_decode_chunks",
+    "b2c_huf_compress_chunks", "b2c_huf_decompress_chunks", "b2c_huf_read_table",
     "b2c_queue_create", "b2c_queue_destroy", "b2c_queue_zstd_encode", "b2c_queue_zstd_decode", "b2c_queue_s2_encode",
     "b2c_queue_s2_decode", "b2c_queue_stats",
 ]

@@ -198,6 +198,8 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)HUF0_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_huf_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_huf_read_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_s2_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)ENC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_snappy_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1073,6 +1075,82 @@ int b2c_huf_decompress_device(b2c_ctx *ctx, int flags, const void *d_src, size_t
     ctx->launches += 1;
     CK(cudaGetLastError());
     return B2C_OK;
+}
+
+// Host-buffer batches for the standalone huff0 calls (huff0.Compress4X / Compress1X, Decoder.Decompress4X / 1X, ReadTable
+// per element): inputs are packed into equal slots on the device, one kernel per call, results copied back.
+//   op 0: compress (dst_caps = capacities), op 1: decompress (dst_caps = EXACT decoded sizes), op 2: read table
+//   (dsts[i] receives the 260-byte row described in include/b2c.h)
+static int huf_host_batch(b2c_ctx *ctx, int op, int flags, const void *const *srcs, const size_t *src_sizes,
+                          void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (n == 0) return B2C_OK;
+    if (n > 0xffffffffull) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t maxIn = 16, maxOut = 16;
+    for (size_t i = 0; i < n; i++) {
+        if (src_sizes[i] > 0x7fffffffull) return B2C_ERR_ARG;
+        if (src_sizes[i] > maxIn) maxIn = src_sizes[i];
+        const size_t want = op == 2 ? 260 : (op == 0 ? (dst_caps[i] < src_sizes[i] ? dst_caps[i] : src_sizes[i]) : dst_caps[i]);
+        if (want > maxOut) maxOut = want;
+    }
+    if (op == 1 && maxOut > 262144) maxOut = 262144;      // larger exact sizes are refused by the kernel (ErrTooBig class)
+    const size_t inStride = (maxIn + 15) & ~(size_t)15, outStride = (maxOut + 15) & ~(size_t)15;
+    // meta: out_sizes[n] i64 | src_sizes[n] u32 | dst_sizes[n] u32
+    std::vector<uint64_t> meta(2 * n);
+    uint32_t *ss = reinterpret_cast<uint32_t *>(meta.data() + n), *ds = ss + n;
+    for (size_t i = 0; i < n; i++) { ss[i] = (uint32_t)src_sizes[i]; ds[i] = (uint32_t)(dst_caps[i] > 0xffffffffull ? 0xffffffffull : dst_caps[i]); }
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_dec_in, &ctx->dec_in_cap, n * inStride + 256))) return rc;
+    if ((rc = grow(ctx, &ctx->d_dec_out, &ctx->dec_out_cap, n * outStride + 256))) return rc;
+    if ((rc = grow(ctx, &ctx->d_dec_meta, &ctx->dec_meta_cap, meta.size() * 8))) return rc;
+    for (size_t i = 0; i < n; i++)
+        if (src_sizes[i]) CK(cudaMemcpyAsync(ctx->d_dec_in + i * inStride, srcs[i], src_sizes[i], cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_dec_meta, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, st));
+    uint64_t *dm = reinterpret_cast<uint64_t *>(ctx->d_dec_meta);
+    int64_t *d_res = reinterpret_cast<int64_t *>(dm);
+    uint32_t *d_ss = reinterpret_cast<uint32_t *>(dm + n), *d_ds = d_ss + n;
+    if (op == 0)
+        rc = b2c_huf_compress_device(ctx, flags, ctx->d_dec_in, inStride, d_ss, 0, ctx->d_dec_out, outStride, d_res, (uint32_t)n, st);
+    else if (op == 1)
+        rc = b2c_huf_decompress_device(ctx, flags, ctx->d_dec_in, inStride, d_ss, ctx->d_dec_out, outStride, d_ds, d_res, (uint32_t)n, st);
+    else {
+        Huf0Params P;
+        memset(&P, 0, sizeof(P));
+        P.src_base = ctx->d_dec_in; P.src_stride = inStride; P.src_sizes = d_ss;
+        P.dst_base = ctx->d_dec_out; P.dst_stride = outStride; P.out_sizes = d_res; P.nchunks = (uint32_t)n;
+        const unsigned ctasPerSm = (227u * 1024u) / (DEC_SMEM_BYTES + 1024u);
+        unsigned grid = ((unsigned)n + DEC_WARPS - 1) / DEC_WARPS, maxGrid = (unsigned)ctx->sm_count * (ctasPerSm ? ctasPerSm : 1);
+        if (grid > maxGrid) grid = maxGrid;
+        b2c_huf_read_table_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, st>>>(P);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+        rc = B2C_OK;
+    }
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(sizes_out, d_res, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; i++) {
+        if (sizes_out[i] < 0) continue;
+        const size_t bytes = op == 2 ? 260 : (size_t)sizes_out[i];
+        if (op == 0 && bytes > dst_caps[i]) { sizes_out[i] = B2C_ERR_DST_SMALL; continue; }
+        if (bytes) CK(cudaMemcpyAsync(dsts[i], ctx->d_dec_out + i * outStride, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return B2C_OK;
+}
+int b2c_huf_compress_chunks(b2c_ctx *ctx, int flags, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
+                            const size_t *dst_caps, int64_t *sizes_out, size_t n) {
+    return huf_host_batch(ctx, 0, flags, srcs, src_sizes, dsts, dst_caps, sizes_out, n);
+}
+int b2c_huf_decompress_chunks(b2c_ctx *ctx, int flags, const void *const *srcs, const size_t *src_sizes, void *const *dsts,
+                              const size_t *dst_sizes, int64_t *sizes_out, size_t n) {
+    return huf_host_batch(ctx, 1, flags, srcs, src_sizes, dsts, dst_sizes, sizes_out, n);
+}
+int b2c_huf_read_table(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *rows, int64_t *sizes_out, size_t n) {
+    std::vector<size_t> caps(n, 260);
+    return huf_host_batch(ctx, 2, 0, srcs, src_sizes, rows, caps.data(), sizes_out, n);
 }
 
 // ---- coalescing queue ---------------------------------------------------------------------------------------------

@@ -88,7 +88,36 @@ B2C_DEV int64_t huf0_decompress_block(DecWarp *dw, const uint8_t *src, uint32_t 
     return (int64_t)dstSize;
 }
 
+// huff0.ReadTable (huff0/decompress.go:29-166) as a service: one warp per input.  Row i of `tables` (260 bytes) receives
+// [0] actualTableLog, [1] 0, [2..3] bytes the table description occupies (LE), [4..259] the code length of every symbol
+// (0 = not present); out_sizes[i] = the same byte count, or a negative error.
+B2C_DEV void huf0_read_table_block(DecWarp *dw, const uint8_t *src, uint32_t n, uint8_t *row, int64_t *res, unsigned lane) {
+    for (uint32_t i = lane; i < 260; i += 32) dw->weight[i] = 0;
+    __syncwarp();
+    uint32_t tl = 0;
+    const int used = dec_huf_read_table(dw, src, n, &tl, lane);
+    __syncwarp();
+    if (used < 0) { if (lane == 0) *res = (used == -2) ? HUF0_ERR_UNSUPPORTED : HUF0_ERR_CORRUPT; return; }
+    for (uint32_t sym = lane; sym < 256; sym += 32) {
+        const uint32_t wgt = dw->weight[sym];
+        row[4 + sym] = (uint8_t)(wgt ? tl + 1 - wgt : 0);
+    }
+    if (lane == 0) { row[0] = (uint8_t)tl; row[1] = 0; row[2] = (uint8_t)used; row[3] = (uint8_t)(used >> 8); *res = used; }
+}
+
 #ifndef B2C_EMU
+extern "C" __global__ void __launch_bounds__(DEC_WARPS * 32) b2c_huf_read_table_kernel(Huf0Params P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    DecWarp *dw = reinterpret_cast<DecWarp *>(smem + w * DEC_WARP_BYTES);
+    const uint32_t totalWarps = gridDim.x * DEC_WARPS;
+    for (uint32_t c = blockIdx.x * DEC_WARPS + w; c < P.nchunks; c += totalWarps) {
+        __syncwarp();
+        huf0_read_table_block(dw, P.src_base + (uint64_t)c * P.src_stride, P.src_sizes[c], P.dst_base + (uint64_t)c * P.dst_stride,
+                              P.out_sizes + c, lane);
+        __syncwarp();
+    }
+}
 extern "C" __global__ void __launch_bounds__(HUF0_NT, 1) b2c_huf_compress_kernel(Huf0Params P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     Huf0Shared *sh = reinterpret_cast<Huf0Shared *>(smem);

@@ -117,6 +117,44 @@ class Codec:
         dsth = dst.cpu().numpy()
         return [(dsth[i, :outs[i]].tobytes() if outs[i] >= 0 else None, int(outs[i])) for i in range(n)]
 
+    # ---- host-buffer C-ABI calls (what a cgo shim binds) ------------------------------------------------------
+    def _host(self, fn, blobs, caps, *pre):
+        n = len(blobs)
+        bufs = [np.frombuffer(bytes(b), dtype=np.uint8) if len(b) else np.zeros(0, dtype=np.uint8) for b in blobs]
+        outs = [np.empty(max(int(c), 1), dtype=np.uint8) for c in caps]
+        srcs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        ssz = (ctypes.c_size_t * n)(*[len(b) for b in blobs])
+        dsts = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+        res = (ctypes.c_int64 * n)()
+        if caps is not None and fn is not lib.b2c_huf_read_table:
+            dcap = (ctypes.c_size_t * n)(*[int(c) for c in caps])
+            check(fn(self._ctx, *pre, srcs, ssz, dsts, dcap, res, n), self._ctx)
+        else:
+            check(fn(self._ctx, srcs, ssz, dsts, res, n), self._ctx)
+        return outs, [int(r) for r in res]
+
+    def compress_chunks(self, blocks, four=True):
+        """b2c_huf_compress_chunks: -> list of (bytes or None, code)."""
+        if not blocks:
+            return []
+        outs, codes = self._host(lib.b2c_huf_compress_chunks, blocks, [len(b) + 16 for b in blocks], 1 if four else 0)
+        return [(outs[i][:codes[i]].tobytes() if codes[i] >= 0 else None, codes[i]) for i in range(len(blocks))]
+
+    def decompress_chunks(self, blocks, dst_sizes, four=True):
+        if not blocks:
+            return []
+        outs, codes = self._host(lib.b2c_huf_decompress_chunks, blocks, dst_sizes, 1 if four else 0)
+        return [(outs[i][:codes[i]].tobytes() if codes[i] >= 0 else None, codes[i]) for i in range(len(blocks))]
+
+    def ReadTable(self, data):
+        """huff0.ReadTable(in, nil) (huff0/decompress.go:29): -> (code length per symbol [256], tableLog, remaining input)."""
+        outs, codes = self._host(lib.b2c_huf_read_table, [data], [260])
+        if codes[0] < 0:
+            raise _ERR.get(codes[0], B2CError)(lib.b2c_strerror(codes[0]).decode())
+        row = outs[0]
+        used = int(row[2]) | (int(row[3]) << 8)
+        return [int(x) for x in row[4:260]], int(row[0]), bytes(data)[used:]
+
     def _one(self, res):
         out, code = res
         if code < 0:

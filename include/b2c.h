@@ -188,6 +188,19 @@ B2C_API int b2c_huf_decompress_device(b2c_ctx *ctx, int flags, const void *d_src
                                       const uint32_t *d_src_sizes, void *d_dst, size_t dst_stride,
                                       const uint32_t *d_dst_sizes, int64_t *d_out_sizes, uint32_t nchunks, void *stream);
 
+/* Host-buffer forms of the huff0 calls (the call a cgo shim makes): blocks[i] in ordinary host memory, results per
+ * element as above.  b2c_huf_decompress_chunks takes the EXACT decoded size of every block in dst_sizes (the dstSize
+ * argument of Decoder.Decompress4X, huff0/decompress_asm.go:27-31).  b2c_huf_read_table is huff0.ReadTable
+ * (huff0/decompress.go:29-166): rows[i] receives 260 bytes -- [0] actualTableLog, [1] 0, [2..3] the size of the table
+ * description in bytes (little endian; the streams start there), [4..259] the code length of every symbol (0 = absent) --
+ * and sizes_out[i] the same size, or a negative error. */
+B2C_API int b2c_huf_compress_chunks(b2c_ctx *ctx, int flags, const void *const *srcs, const size_t *src_sizes,
+                                    void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n);
+B2C_API int b2c_huf_decompress_chunks(b2c_ctx *ctx, int flags, const void *const *srcs, const size_t *src_sizes,
+                                      void *const *dsts, const size_t *dst_sizes, int64_t *sizes_out, size_t n);
+B2C_API int b2c_huf_read_table(b2c_ctx *ctx, const void *const *srcs, const size_t *src_sizes, void *const *rows,
+                               int64_t *sizes_out, size_t n);
+
 /*
  * Coalescing queue: the shim's answer to the reference's one-block-per-call seams.  zstd.Encoder.EncodeAll may be
  * called concurrently (zstd/encoder.go:717-729), s2.WriterCustomEncoder's hook runs on one goroutine per block

@@ -192,6 +192,20 @@ int emu_huf_decompress(const uint8_t *src, uint64_t stride, const uint32_t *size
     return 0;
 }
 
+// huff0.ReadTable rows (260 bytes each, layout of include/b2c.h) for n inputs at src + i*stride
+int emu_huf_read_table(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t n, uint8_t *rows, int64_t *out_sizes) {
+    emu::launch(1, DEC_WARPS * 32, DEC_SMEM_BYTES, [&]() {
+        const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        DecWarp *dw = reinterpret_cast<DecWarp *>(emu::dyn_smem + w * DEC_WARP_BYTES);
+        for (uint32_t c = w; c < n; c += DEC_WARPS) {
+            __syncwarp();
+            huf0_read_table_block(dw, src + (uint64_t)c * stride, sizes[c], rows + (uint64_t)c * 260, out_sizes + c, lane);
+            __syncwarp();
+        }
+    });
+    return 0;
+}
+
 uint32_t emu_enc_smem_bytes() { return ENC_SMEM_BYTES; }
 uint32_t emu_lz_smem_bytes(int level) { return level >= 2 ? LzLayout<2>::SMEM_BYTES : LzLayout<1>::SMEM_BYTES; }
 uint32_t emu_pack_smem_bytes() { return PACK_SMEM_BYTES; }

@@ -48,6 +48,7 @@ def emu():
     E.emu_huf_compress.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
     E.emu_huf_decompress.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p,
                                      c.c_void_p, c.c_int]
+    E.emu_huf_read_table.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p]
     _emu = E
     return E
 

@@ -82,3 +82,47 @@ def test_emu_huf_decompress(emu_lib, oracle_lib):
             if code >= 0:
                 assert g == wout
         assert bad[0][1] == -5 and bad[3][1] == -5 and bad[4][1] == -5
+
+
+def test_emu_read_table_matches_oracle(emu_lib, oracle_lib):
+    """huff0.ReadTable (huff0/decompress.go:29-166): bytes consumed, table log and the code length of every symbol equal
+    the oracle's for table descriptions produced by the compressor (raw 4-bit weights and FSE-compressed weights)."""
+    import ctypes
+    import numpy as np
+    from emu_util import emu_huf_compress
+    rng = np.random.default_rng(3)
+    blocks = [H.golden("twain.txt")[:50000], H.golden("e.txt")[:30000], bytes(rng.integers(0, 7, 20000, dtype=np.uint8)),
+              bytes(rng.integers(97, 123, 4000, dtype=np.uint8)), H.golden("html.txt")]
+    comp = [c for c, code in emu_huf_compress(emu_lib, blocks, four=True)]
+    assert all(c is not None for c in comp)
+    n = len(comp)
+    stride = max(len(c) for c in comp) + 16
+    src = np.zeros((n, stride), dtype=np.uint8)
+    for i, c in enumerate(comp):
+        src[i, :len(c)] = np.frombuffer(c, dtype=np.uint8)
+    sizes = np.array([len(c) for c in comp], dtype=np.uint32)
+    rows = np.zeros((n, 260), dtype=np.uint8)
+    outs = np.zeros(n, dtype=np.int64)
+    emu_lib.emu_huf_read_table(src.ctypes.data, stride, sizes.ctypes.data, n, rows.ctypes.data, outs.ctypes.data)
+
+    class DT(ctypes.Structure):
+        _fields_ = [("dt", ctypes.c_uint16 * 2048), ("actualTableLog", ctypes.c_uint), ("loaded", ctypes.c_int)]
+    L = oracle_lib
+    L.orc_huf_read_table.restype = ctypes.c_int64
+    L.orc_huf_read_table.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+    for i, c in enumerate(comp):
+        d = DT()
+        used = L.orc_huf_read_table(ctypes.byref(d), c, len(c))
+        assert used > 0 and outs[i] == used == int(rows[i, 2]) | (int(rows[i, 3]) << 8)
+        assert rows[i, 0] == d.actualTableLog
+        want = [0] * 256
+        for e in d.dt[: 1 << d.actualTableLog]:
+            want[e >> 8] = e & 0xff
+        assert list(rows[i, 4:260]) == want, i
+    # truncated description -> corrupt
+    bad = comp[0][:3]
+    src[0, :] = 0
+    src[0, :3] = np.frombuffer(bad, dtype=np.uint8)
+    sizes[0] = 3
+    emu_lib.emu_huf_read_table(src.ctypes.data, stride, sizes.ctypes.data, 1, rows.ctypes.data, outs.ctypes.data)
+    assert outs[0] == -5

@@ -96,3 +96,39 @@ def test_zstd_large_zeros_gpu():
             size = int(zf.read(nm + ".size"))
             assert dec.DecodeAll(zf.read(nm), size_hint=size + 8) == bytes(size), nm
     dec.close()
+
+
+def test_huf_host_buffer_calls_and_read_table(oracle_lib):
+    """b2c_huf_compress_chunks / b2c_huf_decompress_chunks / b2c_huf_read_table (the calls a cgo shim binds for
+    huff0.Compress4X, Decoder.Decompress4X and huff0.ReadTable) against the device-resident path and the oracle."""
+    import ctypes
+    from compress_b200 import huff0
+    hc = huff0.Codec()
+    rng = np.random.default_rng(9)
+    blocks = [H.golden("twain.txt")[:100000], H.golden("e.txt")[:262143], bytes(rng.integers(0, 5, 50000, dtype=np.uint8)),
+              H.golden("html.txt"), bytes(rng.integers(0, 256, 4000, dtype=np.uint8)), bytes(1000)]
+    for four in (True, False):
+        a = hc.compress_chunks(blocks, four)
+        b = hc.compress_blocks(blocks, four)
+        assert a == b
+        good = [(blk, c) for blk, (c, code) in zip(blocks, a) if code > 0]
+        back = hc.decompress_chunks([c for _, c in good], [len(blk) for blk, _ in good], four)
+        assert [x[0] for x in back] == [blk for blk, _ in good]
+    comp = hc.Compress4X(blocks[0])
+
+    class DT(ctypes.Structure):
+        _fields_ = [("dt", ctypes.c_uint16 * 2048), ("actualTableLog", ctypes.c_uint), ("loaded", ctypes.c_int)]
+    L = oracle_lib
+    L.orc_huf_read_table.restype = ctypes.c_int64
+    L.orc_huf_read_table.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+    d = DT()
+    used = L.orc_huf_read_table(ctypes.byref(d), comp, len(comp))
+    nbits, tlog, rest = hc.ReadTable(comp)
+    assert tlog == d.actualTableLog and rest == comp[used:]
+    want = [0] * 256
+    for e in d.dt[: 1 << d.actualTableLog]:
+        want[e >> 8] = e & 0xff
+    assert nbits == want
+    with pytest.raises(huff0.ErrCorrupt):
+        hc.ReadTable(comp[:2])
+    hc.close()
