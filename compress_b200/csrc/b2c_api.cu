@@ -884,7 +884,12 @@ int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *
     for (size_t i = 0; i < n; i++) {
         int64_t total = 0;
         for (size_t k = first_item[i]; k < first_item[i + 1]; k++) {
-            if (res[k] < 0) { total = res[k]; break; }                       // the first failing frame decides
+            if (res[k] < 0) {                                                // the first failing frame decides
+                // a split frame's capacity is its declared content size: running out of it means the frame is larger
+                // than declared, which the reference reports as ErrFrameSizeExceeded (framedec.go:330-412)
+                total = (split[i] && res[k] == B2C_ERR_DST_SMALL) ? (int64_t)B2C_ERR_SIZE : res[k];
+                break;
+            }
             if (split[i] && (uint64_t)res[k] != items[k].cap) { total = B2C_ERR_SIZE; break; }   // declared size not met
             total += res[k];
         }

@@ -40,9 +40,9 @@ constexpr uint32_t LZ_EMPTY = 0xffffffffu;
 #ifndef LZ_PPT1
 #define LZ_PPT1 8           // positions per thread and tile of the single-table configurations (4 or 8)
 #endif
-#ifndef LZ_INS_STRIDE
-#define LZ_INS_STRIDE 1     // 2: only even positions are inserted into the tables (every position is still probed)
-#endif
+#ifndef LZ_INS_FAST
+#define LZ_INS_FAST 2       // insertion stride of the "fastest" classes (zstd level 1, S2 fast): 2 = only even positions enter
+#endif                      // the table (every position is still probed): one random access per position less, about +2 % output
 constexpr uint32_t LZ_EXT_CAP = 256;        // per-thread forward extension limit; longer matches are finished by warp 0
 
 template <int LV> struct LzCfg;
@@ -53,6 +53,7 @@ template <> struct LzCfg<1> {
     static constexpr bool LONG = false;
     static constexpr int SMLS = 6, LMLS = 8;   // bytes hashed for the short / long table
     static constexpr int PPT = LZ_PPT1;        // positions per thread and tile (tile = NT * PPT positions)
+    static constexpr int INS = LZ_INS_FAST;    // insertion stride
     static constexpr uint32_t TBITS = 14;
     static constexpr uint32_t KREC = 16;      // match records (4 bytes each) per thread kept in shared memory
     static constexpr int MIN_CTAS = 2;
@@ -63,6 +64,7 @@ template <> struct LzCfg<2> {
     static constexpr bool LONG = true;
     static constexpr int SMLS = 5, LMLS = 8;
     static constexpr int PPT = 4;
+    static constexpr int INS = 1;
     static constexpr uint32_t TBITS = 14;
     static constexpr uint32_t KREC = 8;
     static constexpr int MIN_CTAS = 1;
@@ -78,6 +80,7 @@ template <> struct LzCfg<5> {
     static constexpr bool LONG = true;
     static constexpr int SMLS = 5, LMLS = 8;
     static constexpr int PPT = 1;
+    static constexpr int INS = 1;
     static constexpr uint32_t TBITS = 14;
     static constexpr uint32_t KREC = 8;
     static constexpr int MIN_CTAS = 1;
@@ -91,6 +94,7 @@ template <> struct LzCfg<3> {
     static constexpr bool LONG = false;
     static constexpr int SMLS = 4, LMLS = 8;
     static constexpr int PPT = LZ_PPT1;
+    static constexpr int INS = LZ_INS_FAST;
     static constexpr uint32_t TBITS = 14;
     static constexpr uint32_t KREC = 16;
     static constexpr int MIN_CTAS = 2;
@@ -101,6 +105,7 @@ template <> struct LzCfg<4> {
     static constexpr bool LONG = true;
     static constexpr int SMLS = 4, LMLS = 7;
     static constexpr int PPT = 4;
+    static constexpr int INS = 1;
     static constexpr uint32_t TBITS = 13;
     static constexpr uint32_t KREC = 12;      // (the second bitmap takes the room of four records per thread)
     static constexpr int MIN_CTAS = 2;
@@ -212,14 +217,14 @@ B2C_DEV void lz_dense_tile(uint32_t *TS, uint32_t *TL, uint32_t *bm, uint32_t *b
     __syncthreads();
 #pragma unroll
     for (int j = PPT - 1; j >= 0; j--)                                 // the thread's lowest position lands last
-        if ((LZ_INS_STRIDE == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
+        if ((C::INS == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
             TS[LZ_IDX(hs[j])] = LZ_ENT(hs[j], j);
             if constexpr (C::LONG) TL[LZ_IDX(hl[j])] = LZ_ENT(hl[j], j);
         }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < PPT; j++)
-        if ((LZ_INS_STRIDE == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
+        if ((C::INS == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
             if (TS[LZ_IDX(hs[j])] > LZ_ENT(hs[j], j)) atomicMin(&TS[LZ_IDX(hs[j])], LZ_ENT(hs[j], j));   // lost a store race: exact minimum of the tile
             if constexpr (C::LONG) { if (TL[LZ_IDX(hl[j])] > LZ_ENT(hl[j], j)) atomicMin(&TL[LZ_IDX(hl[j])], LZ_ENT(hl[j], j)); }
         }

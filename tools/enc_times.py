@@ -37,8 +37,45 @@ ms, calls = enc.profile_read()
 tot = e0.elapsed_time(e1) / steps
 o = outs.cpu()
 assert int(o.min()) > 0
-print("level %d  parse %s  %d x %d KiB" % (level, os.environ.get("B2C_PARSE", "lz"), n, CH >> 10))
+from compress_b200 import _lib
+print("level %d  parse %s  %d x %d KiB   lib md5 %s" % (level, os.environ.get("B2C_PARSE", "lz"), n, CH >> 10,
+                                                    hashlib.md5(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:10]))
 print("  step %.3f ms = %.1f GB/s; ratio %.4f; sizes sha1 %s" % (
     tot, n * CH / tot / 1e6, float(o.sum()) / (n * CH), hashlib.sha1(o.numpy().tobytes()).hexdigest()[:12]))
 print("  per step: " + "  ".join("%s %.3f" % (k.replace("b2c_zstd_", "").replace("b2c_", "").replace("_kernel", ""), v / steps)
                                  for k, v in ms.items()) + "   (%d launches of the pipeline per step)" % (calls // steps))
+
+if "--decode" in sys.argv:
+    dec = zstd.Decoder()
+    dsz = outs.to(torch.int32)
+    dout = torch.empty((n, CH), dtype=torch.uint8, device=dev)
+    dres = torch.empty((n,), dtype=torch.int64, device=dev)
+    for _ in range(2):
+        dec.decode_device(dst, dsz, src_stride=enc.slot, dst=dout, dst_cap=CH, out_sizes=dres)
+    torch.cuda.synchronize()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(3):
+        dec.decode_device(dst, dsz, src_stride=enc.slot, dst=dout, dst_cap=CH, out_sizes=dres)
+    d1.record()
+    torch.cuda.synchronize()
+    ms = d0.elapsed_time(d1) / 3
+    assert bool((dres == CH).all()) and torch.equal(dout.view(-1), src)
+    print("  decode %.3f ms = %.1f GB/s (output bytes)" % (ms, n * CH / ms / 1e6))
+if "--s2" in sys.argv and level == 1:
+    from compress_b200 import s2 as s2mod
+    c = s2mod.Codec()
+    sd = torch.empty((n, s2mod.SLOT), dtype=torch.uint8, device=dev)
+    ss = torch.empty((n,), dtype=torch.int64, device=dev)
+    for name, snappy, better in (("s2", False, False), ("s2-better", False, True), ("snappy", True, False)):
+        for _ in range(2):
+            c.encode_device(src, snappy=snappy, better=better, dst=sd, out_sizes=ss)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(3):
+            c.encode_device(src, snappy=snappy, better=better, dst=sd, out_sizes=ss)
+        a1.record()
+        torch.cuda.synchronize()
+        ms = a0.elapsed_time(a1) / 3
+        print("  %-10s %.3f ms = %.1f GB/s; ratio %.4f" % (name, ms, n * CH / ms / 1e6, float(ss.sum()) / (n * CH)))
