@@ -65,6 +65,7 @@ struct b2c_ctx {
     uint8_t *d_dec_lit = nullptr; size_t dec_lit_cap = 0;
     uint8_t *d_dec_in = nullptr, *d_dec_out = nullptr; size_t dec_in_cap = 0, dec_out_cap = 0;
     uint8_t *d_dec_meta = nullptr; size_t dec_meta_cap = 0;
+    uint8_t *h_stg_in = nullptr, *h_stg_out = nullptr; size_t h_stg_in_cap = 0, h_stg_out_cap = 0;   // pinned staging of the pointer-table calls
     // optional per-kernel timing of the encode pipeline (b2c_profile_*): 6 events per encode call
     bool prof = false;
     std::vector<cudaEvent_t> pev;
@@ -242,6 +243,7 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
 void b2c_ctx_destroy(b2c_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaFreeHost(ctx->h_stg_in); cudaFreeHost(ctx->h_stg_out);
     cudaFree(ctx->d_dec_lit); cudaFree(ctx->d_dec_in); cudaFree(ctx->d_dec_out); cudaFree(ctx->d_dec_meta);
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_pool[0]); cudaFree(ctx->d_pool[1]);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
@@ -720,6 +722,56 @@ static int grow(b2c_ctx *ctx, uint8_t **p, size_t *cap, size_t need) {
     return B2C_OK;
 }
 
+static int grow_host(b2c_ctx *ctx, uint8_t **p, size_t *cap, size_t need) {
+    if (*cap >= need) return B2C_OK;
+    if (*p) CK(cudaFreeHost(*p));
+    *p = nullptr; *cap = 0;
+    need += need / 4;
+    CK(cudaMallocHost(p, need));
+    *cap = need;
+    return B2C_OK;
+}
+// Pointer-table calls: n separately allocated host pieces <-> one packed device range.  Thousands of small
+// cudaMemcpyAsync calls cost more than the bytes they move (and block on pageable memory), so the pieces are gathered
+// into / scattered from one pinned staging buffer and cross the bus as ONE copy each way.  offs[i] = offset of piece i in
+// the device range `d_base[0, total)`.
+static const size_t kStageLimit = (size_t)1 << 30;
+static int gather_h2d(b2c_ctx *ctx, const void *const *srcs, const size_t *sizes, const uint64_t *offs, size_t n, uint8_t *d_base,
+                      size_t total, cudaStream_t st) {
+    if (total == 0) return B2C_OK;
+    if (total > kStageLimit) {
+        for (size_t i = 0; i < n; i++)
+            if (sizes[i]) CK(cudaMemcpyAsync(d_base + offs[i], srcs[i], sizes[i], cudaMemcpyHostToDevice, st));
+        return B2C_OK;
+    }
+    int rc = grow_host(ctx, &ctx->h_stg_in, &ctx->h_stg_in_cap, total);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++)
+        if (sizes[i]) memcpy(ctx->h_stg_in + offs[i], srcs[i], sizes[i]);
+    CK(cudaMemcpyAsync(d_base, ctx->h_stg_in, total, cudaMemcpyHostToDevice, st));
+    return B2C_OK;
+}
+// results: piece i = d_base[offs[i], offs[i] + lens[i]) -> dsts[i]; synchronises the stream
+static int scatter_d2h(b2c_ctx *ctx, void *const *dsts, const size_t *lens, const uint64_t *offs, size_t n, const uint8_t *d_base,
+                       size_t range, cudaStream_t st) {
+    size_t useful = 0;
+    for (size_t i = 0; i < n; i++) useful += lens[i];
+    if (useful == 0) { CK(cudaStreamSynchronize(st)); return B2C_OK; }
+    if (range > kStageLimit || useful * 2 < range) {          // sparse or huge: copy the pieces
+        for (size_t i = 0; i < n; i++)
+            if (lens[i]) CK(cudaMemcpyAsync(dsts[i], d_base + offs[i], lens[i], cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return B2C_OK;
+    }
+    int rc = grow_host(ctx, &ctx->h_stg_out, &ctx->h_stg_out_cap, range);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_stg_out, d_base, range, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; i++)
+        if (lens[i]) memcpy(dsts[i], ctx->h_stg_out + offs[i], lens[i]);
+    return B2C_OK;
+}
+
 static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st) {
     if (P.nchunks == 0) return B2C_OK;
     const unsigned ctasPerSm = (227u * 1024u) / (DEC_SMEM_BYTES + 1024u);
@@ -868,8 +920,7 @@ int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *
     if ((rc = grow(ctx, &ctx->d_dec_in, &ctx->dec_in_cap, inb + 64))) return rc;
     if ((rc = grow(ctx, &ctx->d_dec_out, &ctx->dec_out_cap, outb + 64))) return rc;
     if ((rc = grow(ctx, &ctx->d_dec_meta, &ctx->dec_meta_cap, meta.size() * 8))) return rc;
-    for (size_t i = 0; i < n; i++)
-        if (src_sizes[i]) CK(cudaMemcpyAsync(ctx->d_dec_in + in_base[i], srcs[i], src_sizes[i], cudaMemcpyHostToDevice, st));
+    if ((rc = gather_h2d(ctx, srcs, src_sizes, in_base.data(), n, ctx->d_dec_in, (size_t)inb, st))) return rc;
     CK(cudaMemcpyAsync(ctx->d_dec_meta, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, st));
     ZstdDecParams P;
     memset(&P, 0, sizeof(P));
@@ -894,9 +945,13 @@ int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *
             total += res[k];
         }
         sizes_out[i] = total;
-        if (total > 0) CK(cudaMemcpyAsync(dsts[i], ctx->d_dec_out + out_base[i], (size_t)total, cudaMemcpyDeviceToHost, st));
+        out_len[i] = total > 0 ? (uint64_t)total : 0;
     }
-    CK(cudaStreamSynchronize(st));
+    {
+        std::vector<size_t> lens(n);
+        for (size_t i = 0; i < n; i++) lens[i] = (size_t)out_len[i];
+        if ((rc = scatter_d2h(ctx, dsts, lens.data(), out_base.data(), n, ctx->d_dec_out, (size_t)outb, st))) return rc;
+    }
     return B2C_OK;
 }
 
@@ -994,9 +1049,13 @@ static int s2_host_batch(b2c_ctx *ctx, bool encode, int level, int flags, const 
     if ((rc = grow(ctx, &ctx->d_dec_in, &ctx->dec_in_cap, inb + 256))) return rc;
     if ((rc = grow(ctx, &ctx->d_dec_out, &ctx->dec_out_cap, outb + 256))) return rc;
     if ((rc = grow(ctx, &ctx->d_dec_meta, &ctx->dec_meta_cap, meta.size() * 8))) return rc;
-    for (size_t i = 0; i < n; i++) {
-        if (encode && src_sizes[i] > ENC_MAX_CHUNK) { ss[i] = ENC_MAX_CHUNK + 1; continue; }   // reported as too big
-        if (src_sizes[i]) CK(cudaMemcpyAsync(ctx->d_dec_in + so[i], srcs[i], src_sizes[i], cudaMemcpyHostToDevice, st));
+    {
+        std::vector<size_t> lens(n);
+        for (size_t i = 0; i < n; i++) {
+            lens[i] = src_sizes[i];
+            if (encode && src_sizes[i] > ENC_MAX_CHUNK) { ss[i] = ENC_MAX_CHUNK + 1; lens[i] = 0; }   // reported as too big
+        }
+        if ((rc = gather_h2d(ctx, srcs, lens.data(), so, n, ctx->d_dec_in, (size_t)inb, st))) return rc;
     }
     CK(cudaMemcpyAsync(ctx->d_dec_meta, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, st));
     uint64_t *dm = reinterpret_cast<uint64_t *>(ctx->d_dec_meta);
@@ -1021,12 +1080,14 @@ static int s2_host_batch(b2c_ctx *ctx, bool encode, int level, int flags, const 
     if (rc) return rc;
     CK(cudaMemcpyAsync(sizes_out, d_res, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    for (size_t i = 0; i < n; i++) {
-        if (sizes_out[i] > 0 && (size_t)sizes_out[i] > dst_caps[i]) { sizes_out[i] = B2C_ERR_DST_SMALL; continue; }
-        if (sizes_out[i] > 0)
-            CK(cudaMemcpyAsync(dsts[i], ctx->d_dec_out + dof[i], (size_t)sizes_out[i], cudaMemcpyDeviceToHost, st));
+    {
+        std::vector<size_t> lens(n, 0);
+        for (size_t i = 0; i < n; i++) {
+            if (sizes_out[i] > 0 && (size_t)sizes_out[i] > dst_caps[i]) { sizes_out[i] = B2C_ERR_DST_SMALL; continue; }
+            if (sizes_out[i] > 0) lens[i] = (size_t)sizes_out[i];
+        }
+        if ((rc = scatter_d2h(ctx, dsts, lens.data(), dof, n, ctx->d_dec_out, (size_t)outb, st))) return rc;
     }
-    CK(cudaStreamSynchronize(st));
     return B2C_OK;
 }
 

@@ -222,12 +222,23 @@ B2C_DEV void lz_dense_tile(uint32_t *TS, uint32_t *TL, uint32_t *bm, uint32_t *b
             if constexpr (C::LONG) TL[LZ_IDX(hl[j])] = LZ_ENT(hl[j], j);
         }
     __syncthreads();
+    {
+        // all slots are read before the first fix: the loads overlap (an atomic between two loads would order them), and a
+        // stale value can only cause a redundant atomicMin
+        uint32_t cs[PPT], cl[C::LONG ? PPT : 1];
 #pragma unroll
-    for (int j = 0; j < PPT; j++)
-        if ((C::INS == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
-            if (TS[LZ_IDX(hs[j])] > LZ_ENT(hs[j], j)) atomicMin(&TS[LZ_IDX(hs[j])], LZ_ENT(hs[j], j));   // lost a store race: exact minimum of the tile
-            if constexpr (C::LONG) { if (TL[LZ_IDX(hl[j])] > LZ_ENT(hl[j], j)) atomicMin(&TL[LZ_IDX(hl[j])], LZ_ENT(hl[j], j)); }
-        }
+        for (int j = 0; j < PPT; j++)
+            if (C::INS == 1 || (j & 1) == 0) {
+                cs[j] = TS[LZ_IDX(hs[j])];
+                if constexpr (C::LONG) cl[j] = TL[LZ_IDX(hl[j])];
+            }
+#pragma unroll
+        for (int j = 0; j < PPT; j++)
+            if ((C::INS == 1 || (j & 1) == 0) && (!GUARD || p0 + j < npos)) {
+                if (cs[j] > LZ_ENT(hs[j], j)) atomicMin(&TS[LZ_IDX(hs[j])], LZ_ENT(hs[j], j));   // lost a store race: exact minimum of the tile
+                if constexpr (C::LONG) { if (cl[j] > LZ_ENT(hl[j], j)) atomicMin(&TL[LZ_IDX(hl[j])], LZ_ENT(hl[j], j)); }
+            }
+    }
     __syncthreads();
     uint32_t bitsA = 0, bitsL = 0, dist[PPT];
 #pragma unroll
