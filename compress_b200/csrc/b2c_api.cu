@@ -35,7 +35,6 @@ struct b2c_ctx {
     uint8_t *d_pool[2] = {nullptr, nullptr};     // per-chunk work pool slabs (literals, sequences, codes, state bits)
     size_t work_cap[2] = {0, 0};        // chunks the records hold
     size_t pool_cap[2] = {0, 0};        // bytes
-    int parse_r1 = 0;                   // B2C_PARSE=r1: level 1 runs the round-1 parse kernel (A/B measurements)
     cudaEvent_t ev_busy = nullptr;      // last launch that used the context's scratch / work buffers
     cudaStream_t busy_stream = nullptr; bool busy_valid = false;
     // host-buffer path staging (slot 0 of the pipeline doubles as the pointer-table path's buffers)
@@ -161,7 +160,7 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = true;
     {
-        size_t a = (size_t)ctx->sm_count * ENC_SCRATCH_BYTES;
+        size_t a = 0;
         size_t b = (size_t)ctx->sm_count * LzCfg<1>::MIN_CTAS * LzLayout<1>::SCRATCH_BYTES;
         size_t c = (size_t)ctx->sm_count * LzCfg<2>::MIN_CTAS * LzLayout<2>::SCRATCH_BYTES;
         size_t d3 = (size_t)ctx->sm_count * LzCfg<3>::MIN_CTAS * LzLayout<3>::SCRATCH_BYTES;
@@ -171,8 +170,6 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
         size_t d5 = (size_t)ctx->sm_count * LzCfg<5>::MIN_CTAS * LzLayout<5>::SCRATCH_BYTES;
         if (d5 > a) a = d5;
         ctx->scratch_slot = ((a > b ? (a > c ? a : c) : (b > c ? b : c)) + 255) & ~(size_t)255;
-        const char *pe = getenv("B2C_PARSE");
-        ctx->parse_r1 = (pe && strcmp(pe, "r1") == 0) ? 1 : 0;
     }
     ok = ok && cudaMalloc(&ctx->d_scratch, 2 * ctx->scratch_slot) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_busy, cudaEventDisableTiming) == cudaSuccess;
@@ -191,8 +188,6 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
     ok = ok && cudaFuncSetAttribute(b2c_zstd_pack128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)PackCfg<131072>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(b2c_zstd_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)ENC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)CHAIN_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_huf_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -201,10 +196,6 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_huf_read_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(b2c_s2_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)ENC_SMEM_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(b2c_snappy_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)ENC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -371,7 +362,6 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     }
     { int r = ctx_order_begin(ctx, st); if (r) return r; }
     const unsigned sms = (unsigned)ctx->sm_count;
-    const bool r1 = ctx->parse_r1 && level == B2C_LEVEL_FASTEST;
     for (uint32_t c0 = 0; c0 < nchunks; c0 += sub) {
         const uint32_t m = (nchunks - c0 < sub) ? nchunks - c0 : sub;
         ZstdEncParams P;
@@ -406,12 +396,7 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
             ctx->launches += 1;
         }
         PEV(1);
-        if (r1) {
-            const unsigned g1 = sms < m ? sms : m;
-            b2c_zstd_parse_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
-            PEV(2);
-            ctx->launches += 1;
-        } else {
+        {
             if (level == B2C_LEVEL_FASTEST) {
                 const unsigned cap = sms * LzCfg<1>::MIN_CTAS, g1 = cap < m ? cap : m;
                 b2c_lz_parse1_kernel<<<g1, LzCfg<1>::NT, LzLayout<1>::SMEM_BYTES, st>>>(P);
@@ -985,11 +970,7 @@ int b2c_s2_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     P.scratch = ctx->d_scratch;
     const unsigned sms = (unsigned)ctx->sm_count;
     const bool snappy = (flags & B2C_S2_SNAPPY) != 0;
-    if (ctx->parse_r1 && level == B2C_S2_FAST) {
-        const unsigned g1 = sms < nchunks ? sms : nchunks;
-        if (snappy) b2c_snappy_encode_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
-        else b2c_s2_encode_kernel<<<g1, ENC_NT, ENC_SMEM_BYTES, st>>>(P);
-    } else if (level == B2C_S2_FAST) {
+    if (level == B2C_S2_FAST) {
         const unsigned cap = sms * LzCfg<3>::MIN_CTAS, g1 = cap < nchunks ? cap : nchunks;
         if (snappy) b2c_lz_snappy_fast_kernel<<<g1, LzCfg<3>::NT, LzLayout<3>::SMEM_BYTES, st>>>(P);
         else b2c_lz_s2_fast_kernel<<<g1, LzCfg<3>::NT, LzLayout<3>::SMEM_BYTES, st>>>(P);

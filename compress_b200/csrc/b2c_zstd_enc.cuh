@@ -1,22 +1,16 @@
-// compress_b200/csrc/b2c_zstd_enc.cuh -- zstd "SpeedFastest" chunk encoder for sm_100a.
+// compress_b200/csrc/b2c_zstd_enc.cuh -- zstd chunk encoder for sm_100a: entropy stages, framing, work records.
 //
-// Turns N independent <= 64 KiB chunks into N complete zstd frames (what one zstd.Encoder.EncodeAll call does
+// Turns N independent chunks (<= 64 KiB at level 1, <= 128 KiB at levels 2-3) into N complete zstd frames (what one zstd.Encoder.EncodeAll call does
 // per chunk, zstd/encoder.go:722-839) or bare blocks.  Replaces, for the GPU path, the reference's
 //   zstd/enc_fast.go:294-531  fastEncoder.EncodeNoHist      (match finding)
 //   zstd/blockenc.go:481-826  blockEnc.encode               (entropy stage, byte-identical here)
 //   zstd/frameenc.go:25-92    frameHeader.appendTo
 //   zstd/internal/xxhash      XXH64 frame checksum
 //
-// B200-first design: a pipeline of five kernels on one stream, each shaped after the parallelism its
-// stage really has, with a per-chunk work record (ChunkWork) in HBM/L2 between them:
-//   K1 parse    one CTA per chunk (persistent grid = #SMs, 1024 threads).  The chunk is staged into shared
-//               memory with one TMA bulk copy.  A CTA-wide table keeps the EARLIEST position of every 6-byte
-//               hash (exact minimum, so candidates always precede the position and the result does not
-//               depend on scheduling); one dense pass marks, one bit per position, where that earliest
-//               occurrence verifies over 4 bytes; then every thread runs the reference's greedy loop over
-//               its own 68-byte range, jumping from marked position to marked position (extend forwards /
-//               backwards, emit, skip).  Overlaps between neighbouring threads are trimmed by block-wide
-//               scans, literals are gathered, codes and histograms computed with all threads.
+// B200-first design: a pipeline of six kernels on one stream, each shaped after the parallelism its stage really has, with
+// a per-chunk work record (ChunkWork header + a slab of the work pool) in HBM/L2 between them:
+//   K1 parse    b2c_lz.cuh: the tile-ordered match finder (levels 1-3; also the S2 / Snappy block encoders)
+//   hist        b2c_lz.cuh: literal and sequence-code histograms
 //   K2 tables   one 4-warp CTA per chunk: the Huffman table (reference tie-breaking) and the three FSE
 //               tables are tiny serial problems -- thousands of them run side by side.
 //   K3 chains   one LANE per (chunk, tANS chain): the reference's serial state walk, 32 chunks per warp.
@@ -26,6 +20,7 @@
 //   K5 xxh64    four lanes per chunk (the four XXH64 accumulators).
 // The parse differs from the reference's serial greedy parse; the entropy stage is byte-identical to
 // blockEnc.encode for the same (literals, sequences) -- tests/check_util.py verifies both properties.
+// This file: work record and pool layout, S2 tag emitters, K2..K5.
 #pragma once
 #include "b2c_common.cuh"
 #include "b2c_fse.cuh"
@@ -34,30 +29,7 @@
 
 namespace b2c {
 
-constexpr int ENC_NT = 1024;              // K1 threads per CTA
-constexpr int ENC_NW = ENC_NT / 32;       // 32 parsing warps
-constexpr int ENC_EBITS = 15;             // earliest-occurrence table: 32 Ki x u16
-constexpr uint32_t ENC_LANE_BYTES = 68;   // bytes parsed by one thread (17 words: lanes start in distinct banks)
-constexpr uint32_t ENC_MAXREC = 17;       // matches a thread can start inside its 68 bytes (min match 4)
-#ifndef ENC_EBUILD_SYNC_MASK
-#define ENC_EBUILD_SYNC_MASK 1  // barrier every (mask + 1) iterations of the table build's first round
-#endif
-#ifndef ENC_SCAN_BITMAP
-#define ENC_SCAN_BITMAP 1     // 1: dense candidate pass + per-thread walk over a bitmap; 0: per-thread probe loop
-#endif
-#ifndef ENC_PROBES_PER_VOTE
-#define ENC_PROBES_PER_VOTE 8   // probe steps between two looks at the warp state
-#endif
-#ifndef ENC_EXTEND_BATCH
-#define ENC_EXTEND_BATCH 6      // lanes holding a match before the warp runs an extend-and-emit step
-#endif
-constexpr uint32_t ENC_EXT_CAP = 256;     // per-thread forward extension limit; longer matches are finished by warp 0
-constexpr uint32_t ENC_MAX_CHUNK = 1u << 16;
-constexpr uint32_t ENC_SRC_BYTES = ENC_MAX_CHUNK + 128;   // chunk + zero padding
-constexpr uint32_t ENC_E_BYTES = (1u << ENC_EBITS) * 2;
-constexpr uint32_t ENC_SREC = 7;           // match records per thread kept in shared memory (the rest spill to HBM)
-constexpr uint32_t ENC_L_BYTES = 64 * 1024;   // 7 records + 8 bytes of merge state per thread; later the literal counters
-constexpr uint32_t ENC_MAXSEQ = 16384 + 64;
+constexpr uint32_t ENC_MAX_CHUNK = 1u << 16;   // block size of zstd level 1 and of the S2 block encoders
 #ifndef PACK_THREADS
 #define PACK_THREADS 512
 #endif
@@ -75,7 +47,6 @@ constexpr uint32_t ENC_MAXSEQ = 16384 + 64;
 #endif
 constexpr int PACK_UNROLL = PACK_SEQ_UNROLL;   // unroll factor of the two per-sequence loops
 constexpr int PACK_NT = PACK_THREADS;     // K4 threads per CTA (a multiple of 128: four Huffman streams)
-constexpr uint32_t ENC_SCRATCH_BYTES = (ENC_MAXREC - ENC_SREC) * ENC_NT * 8;  // per-CTA spilled match records [k][thread]
 
 enum { ENC_FLAG_CRC = 1, ENC_FLAG_FRAME = 2 };
 
@@ -110,7 +81,7 @@ struct ZstdEncParams {
     int64_t *out_sizes;           // bytes written per chunk, negative = error
     uint32_t nchunks;
     uint32_t flags;
-    uint8_t *scratch;             // gridDim.x(K1) * ENC_SCRATCH_BYTES (round-1 parse) / per-CTA parse scratch (lz parse)
+    uint8_t *scratch;             // per-CTA parse scratch: gridDim.x(K1) * LzLayout<..>::SCRATCH_BYTES
     ChunkWork *work;              // [nchunks]
     uint8_t *pool;                // [nchunks] slabs of pool_stride bytes: lit | seqOF | seqLL | seqML | codes[3] | stb[3]
     uint64_t pool_stride;
@@ -214,38 +185,11 @@ B2C_DEV uint32_t warp_match_len(const uint8_t *src, uint32_t a, uint32_t b, uint
     }
 }
 
-// Ballot histogram step: every lane contributes one symbol (NBITS wide); lane l counts the symbols whose low 5 bits
-// equal l, split by the remaining high bits: cnt[k] += #symbols == (k << 5 | l).
-template <int NBITS>
-B2C_DEV void warp_hist_acc(uint32_t sym, bool valid, uint32_t *cnt, unsigned lane) {
-    unsigned b[NBITS];
-#pragma unroll
-    for (int j = 0; j < NBITS; j++) b[j] = __ballot_sync(FULLMASK, valid && ((sym >> j) & 1));
-    unsigned m = __ballot_sync(FULLMASK, valid);
-#pragma unroll
-    for (int j = 0; j < 5; j++) m &= ((lane >> j) & 1) ? b[j] : ~b[j];
-#pragma unroll
-    for (int k = 0; k < (1 << (NBITS - 5)); k++) {
-        unsigned mk = m;
-#pragma unroll
-        for (int j = 5; j < NBITS; j++) mk &= ((k >> (j - 5)) & 1) ? b[j] : ~b[j];
-        cnt[k] += (uint32_t)__popc(mk);
-    }
-}
-
 struct ParseShared {
     uint32_t ws[40];        // block scan scratch
     uint32_t nseq, nlit, kind, rleLen;
     uint64_t mbar;
 };
-constexpr uint32_t ENC_SMEM_SRC = 0;
-constexpr uint32_t ENC_SMEM_E = ENC_SMEM_SRC + ENC_SRC_BYTES;
-constexpr uint32_t ENC_SMEM_L = ENC_SMEM_E + ENC_E_BYTES;
-constexpr uint32_t ENC_BM_BYTES = ENC_MAX_CHUNK / 8 + 16;   // one bit per position: "an earlier occurrence verifies here"
-constexpr uint32_t ENC_SMEM_BM = ENC_SMEM_L + ENC_L_BYTES;
-constexpr uint32_t ENC_SMEM_SH = ENC_SMEM_BM + (ENC_SCAN_BITMAP ? ENC_BM_BYTES : 0);
-constexpr uint32_t ENC_SMEM_BYTES = ENC_SMEM_SH + ((sizeof(ParseShared) + 15) / 16) * 16;
-
 // ------------------------------------------------------------------------------------------------ K1
 // ---- S2 / Snappy byte-tag emitters for offsets < 65536 (s2/encode_go.go:80-289; byte layouts pinned by the KATs of
 // s2/s2_test.go:827-942).  *_size give the bytes the matching put would write.
@@ -304,598 +248,6 @@ B2C_DEV uint32_t snappy_put_copy(uint8_t *d, uint32_t off, uint32_t len) {   // 
     if (len >= 12 || off >= 2048) { d[o + 2] = (uint8_t)(off >> 8); d[o + 1] = (uint8_t)off; d[o] = (uint8_t)((len - 1) << 2 | 2); return o + 3; }
     d[o + 1] = (uint8_t)off; d[o] = (uint8_t)((off >> 8) << 5 | (len - 4) << 2 | 1);
     return o + 2;
-}
-
-// MODE: LZ_MODE_ZSTD -> fills the ChunkWork record for K2..K4; LZ_MODE_S2 / LZ_MODE_SNAPPY -> writes the finished
-// S2 block (uvarint length + tag stream, s2/encode.go:29-60) straight to the destination slot.
-template <int MODE>
-B2C_DEV void zstd_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chunk, uint8_t *scratch) {
-    const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    uint8_t *src = smem + ENC_SMEM_SRC;
-    uint16_t *E = reinterpret_cast<uint16_t *>(smem + ENC_SMEM_E);
-    ParseShared *sh = reinterpret_cast<ParseShared *>(smem + ENC_SMEM_SH);
-    uint8_t *lit = smem + ENC_SMEM_E;                                      // after the parse
-    ChunkWork *W = (MODE == LZ_MODE_ZSTD) ? P.work + chunk : nullptr;
-    const WkLens wlen = (MODE == LZ_MODE_ZSTD) ? wk_lens(P, chunk) : WkLens{nullptr, nullptr, 0};
-    uint32_t *const wof = (MODE == LZ_MODE_ZSTD) ? wk_of(P, chunk) : nullptr;
-    uint8_t *const wcodes = (MODE == LZ_MODE_ZSTD) ? wk_codes(P, chunk, 0) : nullptr;
-    const uint32_t mseq = P.maxseq;
-
-    const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
-    const uint32_t n = chunk_size(P, chunk);
-    if (n > ENC_MAX_CHUNK) {
-        if (tid == 0) {
-            if constexpr (MODE == LZ_MODE_ZSTD) { W->n = n; W->kind = 3; }  // reported as B2C_ERR_TOO_BIG by the pack kernel
-            else P.out_sizes[chunk] = -3;
-        }
-        return;
-    }
-    B2C_PHASE(0);
-    // ---------------------------------------------------------------- P0: stage the chunk
-    {
-#ifndef B2C_EMU
-        bool bulk = ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) && ((n & 15) == 0) && n > 0;
-        if (bulk) {
-            if (tid == 0) {
-                mbar_init(&sh->mbar, 1);
-                mbar_fence_init();
-            }
-            __syncthreads();
-            if (tid == 0) {
-                // order the previous chunk's generic-proxy accesses to this buffer before the async-proxy write
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&sh->mbar, n);
-                tma_load_1d(src, gsrc, n, &sh->mbar);
-            }
-        } else
-#endif
-        {
-            for (uint32_t i = tid; i < n; i += ENC_NT) src[i] = gsrc[i];
-        }
-        // zero padding behind the chunk (unaligned 8-byte loads may look at up to n+11)
-        for (uint32_t i = n + tid; i < ((n + 128 + 15) & ~15u) && i < ENC_SRC_BYTES; i += ENC_NT) src[i] = 0;
-        for (uint32_t i = tid; i < (1u << ENC_EBITS) / 2; i += ENC_NT) reinterpret_cast<uint32_t *>(E)[i] = 0xffffffffu;
-#ifndef B2C_EMU
-        if (bulk) mbar_wait(&sh->mbar, 0);
-#endif
-        __syncthreads();
-#ifndef B2C_EMU
-        if (bulk && tid == 0) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&sh->mbar))); }
-#endif
-    }
-    B2C_PHASE(1);
-
-    // ---------------------------------------------------------------- P1: earliest-occurrence table
-    // Each thread owns groups of 4 consecutive positions (three aligned word loads serve four hashes).
-    const uint32_t npos = (n >= 8) ? n - 7 : 0;  // positions with 8 readable bytes
-    {
-        const uint32_t ngroups = (npos + 3) / 4;
-        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
-        // round 1: plain stores, highest positions first so low positions tend to land last
-        for (int32_t k = (int32_t)((ngroups + ENC_NT - 1) / ENC_NT) - 1; k >= 0; k--) {
-            uint32_t g = (uint32_t)k * ENC_NT + tid;
-            if (g < ngroups) {
-                uint32_t w0 = srcw[g], w1 = srcw[g + 1], w2 = srcw[g + 2];
-                uint32_t p = 4 * g;
-#pragma unroll
-                for (int j = 3; j >= 0; j--) {
-                    uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
-                    uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
-                    if (p + j < npos) E[enc_hash6(lo, hi) >> (32 - ENC_EBITS)] = (uint16_t)(p + j);
-                }
-            }
-            // keep the warps in step: a warp that falls behind would overwrite lower positions with higher ones, and
-            // every such slot costs a compare-and-swap in the fix-up pass
-            if ((k & ENC_EBUILD_SYNC_MASK) == 0) __syncthreads();
-        }
-        __syncthreads();
-        // fix-up pass: every position checks its slot once; the (rare) losers of a write race take the slot with an
-        // atomic compare-and-swap minimum on the containing 32-bit word, so the table is exactly the minimum.
-        {
-            uint32_t *E32 = reinterpret_cast<uint32_t *>(E);
-            for (uint32_t g = tid; g < ngroups; g += ENC_NT) {
-                uint32_t w0 = srcw[g], w1 = srcw[g + 1], w2 = srcw[g + 2];
-                uint32_t p = 4 * g;
-                uint32_t h[4], e[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint32_t lo = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
-                    uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
-                    h[j] = enc_hash6(lo, hi) >> (32 - ENC_EBITS);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++) e[j] = E[h[j]];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint32_t pj = p + j;
-                    if (pj < npos && e[j] > pj) {
-                        uint32_t widx = h[j] >> 1, shft = (h[j] & 1) * 16;
-                        uint32_t old = E32[widx];
-                        for (;;) {
-                            uint32_t curv = (old >> shft) & 0xffffu;
-                            if (curv <= pj) break;
-                            uint32_t nv = (old & ~(0xffffu << shft)) | (pj << shft);
-                            uint32_t prev = atomicCAS(&E32[widx], old, nv);
-                            if (prev == old) break;
-                            old = prev;
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-    B2C_PHASE(2);
-
-    // ---------------------------------------------------------------- P2: parse, one thread per 68-byte range
-    // Every thread runs the serial greedy scan of fastEncoder over its own range (probe E at each position, verify 4
-    // bytes, extend forwards/backwards, skip past the match).  Threads never communicate: E is read-only here, so the
-    // result does not depend on scheduling.  A match may run past the end of the thread's range; the merge step (P3)
-    // trims whatever a later thread found inside it.
-    // record k of thread t: x = start | len << 16, y = dist; k < ENC_SREC in shared memory, the rest in the HBM scratch
-    uint2 *recS = reinterpret_cast<uint2 *>(smem + ENC_SMEM_L);
-    uint2 *recG = reinterpret_cast<uint2 *>(scratch);
-#define REC(k, t) (*(((k) < ENC_SREC) ? &recS[(k) * ENC_NT + (t)] : &recG[((k) - ENC_SREC) * ENC_NT + (t)]))
-    uint32_t *keptEndA = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L + ENC_SREC * 8 * ENC_NT);   // [1024]
-    uint16_t *lastOffA = reinterpret_cast<uint16_t *>(keptEndA + ENC_NT);   // [1024]
-    uint8_t *cntA = reinterpret_cast<uint8_t *>(lastOffA + ENC_NT);         // [1024]
-    uint8_t *capA = cntA + ENC_NT;                                          // [1024]
-    const uint32_t nlanes = (n + ENC_LANE_BYTES - 1) / ENC_LANE_BYTES;
-    uint32_t cnt = 0, lastE = 0;
-    bool capped = false;
-#if ENC_SCAN_BITMAP
-    // The greedy scan of a thread asks the same question at every position it visits: "is E[hash(p)] below p and do
-    // four bytes match there?".  The answer does not depend on the scan, so it is computed for ALL positions in one
-    // dense pass (every lane busy, three aligned word loads serve four positions) and kept as one bit per position;
-    // the per-thread loop then jumps from set bit to set bit inside its range instead of probing byte by byte with
-    // most of the warp idle.  The visited positions, and so the parse, are exactly those of the probe loop.
-    uint32_t *bm = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_BM);
-    {
-        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
-        const uint32_t ngroups = (npos + 3) / 4;
-        const uint32_t gEnd = (ngroups + 7) & ~7u;                 // whole bitmap words (8 groups of 4 positions)
-        for (uint32_t g = tid; g < ((gEnd + 31) & ~31u); g += ENC_NT) {
-            uint32_t nib = 0;
-            if (g < ngroups) {
-                const uint32_t w0 = srcw[g], w1 = srcw[g + 1], w2 = srcw[g + 2];
-                const uint32_t p = 4 * g;
-                uint32_t cand[4], lo4[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    lo4[j] = j ? __funnelshift_r(w0, w1, 8 * j) : w0;
-                    const uint32_t hi = j ? __funnelshift_r(w1, w2, 8 * j) : w1;
-                    cand[j] = E[enc_hash6(lo4[j], hi) >> (32 - ENC_EBITS)];
-                }
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (p + j < npos && cand[j] < p + j && ld32u(src, cand[j]) == lo4[j]) nib |= 1u << j;
-            }
-            uint32_t word = nib << (4 * (lane & 7));
-            word |= __shfl_xor_sync(FULLMASK, word, 1);
-            word |= __shfl_xor_sync(FULLMASK, word, 2);
-            word |= __shfl_xor_sync(FULLMASK, word, 4);
-            if ((lane & 7) == 0 && g < gEnd) bm[g >> 3] = word;
-        }
-        __syncthreads();
-    }
-    {
-        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
-        const uint32_t b = tid * ENC_LANE_BYTES;
-        const uint32_t e = (b + ENC_LANE_BYTES < n) ? b + ENC_LANE_BYTES : n;
-        const uint32_t pend = (tid < nlanes) ? (e < npos ? e : npos) : 0u;   // candidate positions need 8 readable bytes
-        uint32_t p = b, nextEmit = b;
-        while (p < pend) {
-            // next set bit in [p, pend)
-            uint32_t wi = p >> 5;
-            uint32_t wv = bm[wi] & (0xffffffffu << (p & 31));
-            while (wv == 0 && (wi + 1) * 32 < pend) wv = bm[++wi];
-            if (wv == 0) break;
-            p = wi * 32 + (uint32_t)(__ffs((int)wv) - 1);
-            if (p >= pend) break;
-            const uint64_t cv = ld64u(src, p);
-            const uint32_t cand = E[enc_hash6((uint32_t)cv, (uint32_t)(cv >> 32)) >> (32 - ENC_EBITS)];
-            const uint32_t lim = (p + ENC_EXT_CAP < n) ? p + ENC_EXT_CAP : n;
-            // forward: 4 bytes per step from two unaligned streams (aligned word loads + funnel shifts)
-            uint32_t len = 4;
-            {
-                uint32_t ia = (p + 4) >> 2, ib = (cand + 4) >> 2;
-                const uint32_t sha = ((p + 4) & 3) * 8, shb = ((cand + 4) & 3) * 8;
-                uint32_t wa0 = srcw[ia], wb0 = srcw[ib];
-                while (p + len < lim) {
-                    const uint32_t wa1 = srcw[++ia], wb1 = srcw[++ib];
-                    const uint32_t x = __funnelshift_r(wa0, wa1, sha) ^ __funnelshift_r(wb0, wb1, shb);
-                    if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                    len += 4; wa0 = wa1; wb0 = wb1;
-                }
-            }
-            capped = false;
-            if (p + len >= lim) { len = lim - p; capped = lim < n; }
-            uint32_t s = p, t = cand;
-            while (s > nextEmit && t > 0 && src[s - 1] == src[t - 1]) { s--; t--; len++; }
-            REC(cnt, tid) = make_uint2(s | (len << 16), p - cand);
-            cnt++;
-            p = s + len;
-            nextEmit = p;
-        }
-        if (cnt) lastE = nextEmit;
-    }
-#else
-    {
-        // The loop alternates two kinds of steps so that each runs with many active lanes: a probe step for the lanes
-        // that are scanning, and -- once enough lanes of the warp hold an unverified-length match (or nobody is left
-        // scanning) -- an extend-and-emit step for those.  The per-thread sequence of operations is unchanged by the
-        // batching, so the parse does not depend on it.
-        const uint32_t *srcw = reinterpret_cast<const uint32_t *>(src);
-        const uint32_t b = tid * ENC_LANE_BYTES;
-        const uint32_t e = (b + ENC_LANE_BYTES < n) ? b + ENC_LANE_BYTES : n;
-        const uint32_t pend = (tid < nlanes) ? (e < npos ? e : npos) : 0u;   // probe positions need 8 readable bytes
-        uint32_t p = b, nextEmit = b, cand = 0;
-        uint32_t mode = (p < pend) ? 1u : 0u;      // 1 = probing, 2 = holding a match, 0 = done
-        uint64_t cv = mode ? ld64u(src, p) : 0ull;
-        for (;;) {
-            // four probe steps between two looks at the warp state (the votes are pure overhead for the scan)
-#pragma unroll
-            for (int u = 0; u < ENC_PROBES_PER_VOTE; u++) {
-                if (mode == 1) {
-                    const uint32_t c_lo = (uint32_t)cv, c_hi = (uint32_t)(cv >> 32);
-                    cand = E[enc_hash6(c_lo, c_hi) >> (32 - ENC_EBITS)];
-                    if (cand < p && ld32u(src, cand) == c_lo) mode = 2;
-                    else {
-                        p++;
-                        cv = (cv >> 8) | ((uint64_t)src[p + 7] << 56);
-                        if (p >= pend) mode = 0;
-                    }
-                }
-            }
-            const unsigned wm = __ballot_sync(FULLMASK, mode == 2);
-            const unsigned sm = __ballot_sync(FULLMASK, mode == 1);
-            if ((wm | sm) == 0) break;
-            if (__popc(wm) >= ENC_EXTEND_BATCH || sm == 0) {
-                if (mode == 2) {
-                    const uint32_t lim = (p + ENC_EXT_CAP < n) ? p + ENC_EXT_CAP : n;
-                    // forward: 4 bytes per step from two unaligned streams (aligned word loads + funnel shifts)
-                    uint32_t len = 4;
-                    {
-                        uint32_t ia = (p + 4) >> 2, ib = (cand + 4) >> 2;
-                        const uint32_t sha = ((p + 4) & 3) * 8, shb = ((cand + 4) & 3) * 8;
-                        uint32_t wa0 = srcw[ia], wb0 = srcw[ib];
-                        while (p + len < lim) {
-                            const uint32_t wa1 = srcw[++ia], wb1 = srcw[++ib];
-                            const uint32_t x = __funnelshift_r(wa0, wa1, sha) ^ __funnelshift_r(wb0, wb1, shb);
-                            if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                            len += 4; wa0 = wa1; wb0 = wb1;
-                        }
-                    }
-                    capped = false;
-                    if (p + len >= lim) { len = lim - p; capped = lim < n; }
-                    uint32_t s = p, t = cand;
-                    while (s > nextEmit && t > 0 && src[s - 1] == src[t - 1]) { s--; t--; len++; }
-                    REC(cnt, tid) = make_uint2(s | (len << 16), p - cand);
-                    cnt++;
-                    p = s + len;
-                    nextEmit = p;
-                    mode = (p < pend) ? 1u : 0u;
-                    if (mode) cv = ld64u(src, p);
-                }
-            }
-        }
-        if (cnt) lastE = nextEmit;
-    }
-#endif
-    B2C_PHASE(6);
-    cntA[tid] = (uint8_t)cnt;
-    capA[tid] = (uint8_t)((cnt != 0) && capped);
-    __syncthreads();
-    // long matches: warp 0 walks the capped records in order and finishes them cooperatively (128 bytes per step);
-    // a capped record that already lies inside an earlier finished one is skipped, so a chunk of zeros costs one pass
-    if (w == 0) {
-        uint32_t covered = 0;
-        for (uint32_t base = 0; base < nlanes; base += 32) {
-            const uint32_t t = base + lane;
-            unsigned m = __ballot_sync(FULLMASK, t < nlanes && capA[t]);
-            while (m) {
-                const uint32_t tt = base + (uint32_t)(__ffs((int)m) - 1);
-                m &= m - 1;
-                const uint32_t kk = (uint32_t)cntA[tt] - 1;
-                const uint2 r = REC(kk, tt);
-                const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
-                const uint32_t e0 = s0 + l0;
-                if (e0 > covered) {
-                    const uint32_t ext = warp_match_len(src, e0, e0 - d0, n);
-                    if (lane == 0) REC(kk, tt) = make_uint2(s0 | ((l0 + ext) << 16), d0);
-                    covered = e0 + ext;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (capped && cnt) { const uint2 r = REC(cnt - 1, tid); lastE = (r.x & 0xffff) + (r.x >> 16); }
-    B2C_PHASE(3);
-
-    // ---------------------------------------------------------------- P3: merge (trim overlaps), global layout
-    uint32_t dummyTotal;
-    const uint32_t R = group_scan_excl_max(lastE, sh->ws, 0, ENC_NT, tid, &dummyTotal);   // everything before R is taken
-    B2C_PHASE(8);
-    uint32_t kept = 0, sumLen = 0, keptE = 0, lastOff = 0;
-    for (uint32_t j = 0; j < cnt; j++) {
-        const uint2 r = REC(j, tid);
-        const uint32_t s0 = r.x & 0xffff, e0 = s0 + (r.x >> 16);
-        if (e0 <= R) continue;
-        const uint32_t s2 = s0 > R ? s0 : R, l2 = e0 - s2;
-        if (l2 < 4) continue;
-        REC(kept, tid) = make_uint2(s2 | (l2 << 16), r.y);
-        kept++; sumLen += l2; keptE = e0; lastOff = r.y;
-    }
-    B2C_PHASE(9);
-    keptEndA[tid] = keptE;
-    lastOffA[tid] = (uint16_t)lastOff;
-    uint32_t packedTotal, keyTotal;
-    __syncthreads();   // sh->ws is reused by the next scan
-    const uint32_t packedEx = group_scan_excl((kept << 17) | sumLen, sh->ws, 0, ENC_NT, tid, &packedTotal);
-    __syncthreads();
-    // nearest earlier thread that kept something: gives the end of the previous sequence and its offset
-    const uint32_t keyEx = group_scan_excl_max(kept ? tid + 1 : 0u, sh->ws, 0, ENC_NT, tid, &keyTotal);
-    B2C_PHASE(10);
-    const uint32_t nseq = packedTotal >> 17, nlit = n - (packedTotal & 0x1ffffu);
-    const uint32_t lastEnd = keyTotal ? keptEndA[keyTotal - 1] : 0u;      // end of the last sequence of the chunk
-    if constexpr (MODE != LZ_MODE_ZSTD) {
-        // -------------------------------------------------------------- S2 / Snappy emission
-        // sizes per thread -> block scan -> every thread writes its own literal runs and copy tags into the staging
-        // buffer (the hash-table region, dead by now) -> one coalesced copy to the destination slot.
-        constexpr bool SNAPPY = (MODE == LZ_MODE_SNAPPY);
-        uint8_t *out = smem + ENC_SMEM_E;
-        const uint32_t hdrLen = n < 128 ? 1u : (n < 16384 ? 2u : 3u);       // uvarint(n), n <= 65536
-        uint32_t prevE = keyEx ? keptEndA[keyEx - 1] : 0u;
-        uint32_t pOff = keyEx ? (uint32_t)lastOffA[keyEx - 1] : 0u;
-        const bool first = (packedEx >> 17) == 0;                            // no sequence before this thread's
-        uint32_t mySize = 0;
-        {
-            uint32_t pe = prevE, po = pOff;
-            bool fst = first;
-            for (uint32_t j = 0; j < kept; j++) {
-                const uint2 r = REC(j, tid);
-                const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
-                const uint32_t ll = s0 - pe;
-                mySize += s2_lit_hdr_size(ll) + ll;
-                if (SNAPPY) mySize += snappy_copy_size(d0, l0);
-                else mySize += (!fst && d0 == po) ? s2_repeat_size(d0, l0) : s2_copy_size(d0, l0);
-                pe = s0 + l0; po = d0; fst = false;
-            }
-        }
-        uint32_t bodyNoTail;
-        __syncthreads();
-        const uint32_t myOff = group_scan_excl(mySize, sh->ws, 0, ENC_NT, tid, &bodyNoTail);
-        const uint32_t tl = n - lastEnd;
-        const uint32_t body = bodyNoTail + s2_lit_hdr_size(tl) + tl;
-        uint8_t *gdst = P.dst_base + (uint64_t)chunk * P.dst_stride;
-        // encodeBlock's "not compressible" rule (s2/encode_all.go:88: dstLimit), blocks below minNonLiteralBlockSize
-        // (s2/encode.go:375) and the empty input are stored as one literal
-        const bool store = (n < 32) || (nseq == 0) || (body > n - (n >> 5) - 5);
-        const uint32_t total = hdrLen + (store ? s2_lit_hdr_size(n) + n : body);
-        if (total > P.dst_cap) {
-            if (tid == 0) P.out_sizes[chunk] = -4;
-        } else if (store) {
-            if (tid == 0) {
-                uint32_t o = 0, v = n;
-                while (v >= 0x80) { gdst[o++] = (uint8_t)(v | 0x80); v >>= 7; }
-                gdst[o++] = (uint8_t)v;
-                s2_put_lit_hdr(gdst + o, n);
-                P.out_sizes[chunk] = (int64_t)total;
-            }
-            const uint32_t o0 = hdrLen + s2_lit_hdr_size(n);
-            for (uint32_t i = tid; i < n; i += ENC_NT) gdst[o0 + i] = src[i];
-        } else {
-            if (tid == 0) {
-                uint32_t o = 0, v = n;
-                while (v >= 0x80) { out[o++] = (uint8_t)(v | 0x80); v >>= 7; }
-                out[o++] = (uint8_t)v;
-            }
-            uint8_t *d = out + hdrLen + myOff;
-            bool fst = first;
-            for (uint32_t j = 0; j < kept; j++) {
-                const uint2 r = REC(j, tid);
-                const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
-                const uint32_t ll = s0 - prevE;
-                d += s2_put_lit_hdr(d, ll);
-                for (uint32_t k = 0; k < ll; k++) d[k] = src[prevE + k];
-                d += ll;
-                if (SNAPPY) d += snappy_put_copy(d, d0, l0);
-                else d += (!fst && d0 == pOff) ? s2_put_repeat(d, d0, l0) : s2_put_copy(d, d0, l0);
-                prevE = s0 + l0; pOff = d0; fst = false;
-            }
-            {   // trailing literals: header by one thread, bytes by everybody
-                uint8_t *dt = out + hdrLen + bodyNoTail;
-                const uint32_t th = s2_lit_hdr_size(tl);
-                if (tid == 0) s2_put_lit_hdr(dt, tl);
-                for (uint32_t k = tid; k < tl; k += ENC_NT) dt[th + k] = src[lastEnd + k];
-            }
-            __syncthreads();
-            // write-back: bytes up to the first 16-byte boundary of the destination, then 16-byte stores
-            const uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(gdst) & 15)) & 15);
-            if (head == 0) {
-                const uint32_t n16 = total / 16;
-                const uint4 *s4 = reinterpret_cast<const uint4 *>(out);
-                uint4 *d4 = reinterpret_cast<uint4 *>(gdst);
-                for (uint32_t i = tid; i < n16; i += ENC_NT) d4[i] = s4[i];
-                for (uint32_t i = n16 * 16 + tid; i < total; i += ENC_NT) gdst[i] = out[i];
-            } else {
-                for (uint32_t i = tid; i < total; i += ENC_NT) gdst[i] = out[i];
-            }
-            if (tid == 0) P.out_sizes[chunk] = (int64_t)total;
-        }
-        __syncthreads();
-        B2C_PHASE(4);
-        B2C_PHASE(5);
-        return;
-    }
-    uint32_t kind = 0;
-    // blockEnc.encode early decisions (blockenc.go:481-503): no sequences => literals-only (raw) block; then the
-    // single-sequence RLE test (needs the sequence, so it runs after the gather); then `saved < 16` => raw
-    const int saved = (int)n - (int)nlit - (int)(n >> 6);
-    if (nseq == 0) kind = 1;  // encodeLits(..., rawAllLits=true) => raw block
-    else if (nseq != 1 && saved < 16) kind = 1;
-
-    // ---------------------------------------------------------------- P4: gather literals, sequences, codes
-    uint32_t seqCnt[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // this warp's code counts: lane l holds codes l and 32 + l
-    if (kind == 0) {
-        uint32_t prevE = keyEx ? keptEndA[keyEx - 1] : 0u;
-        uint32_t pOff = keyEx ? (uint32_t)lastOffA[keyEx - 1] : 0u;
-        uint32_t gi = packedEx >> 17, mrun = packedEx & 0x1ffffu;
-        for (uint32_t j = 0; j < kept; j++) {
-            const uint2 r = REC(j, tid);
-            const uint32_t s0 = r.x & 0xffff, l0 = r.x >> 16, d0 = r.y;
-            const uint32_t ll = s0 - prevE;
-            const uint32_t lpos = prevE - mrun;          // literal index = source position - match bytes before it
-            {   // literal run: bytes up to the next 4-byte boundary of the destination, then whole words
-                uint32_t k = 0;
-                while (k < ll && ((lpos + k) & 3)) { lit[lpos + k] = src[prevE + k]; k++; }
-                for (; k + 4 <= ll; k += 4) *reinterpret_cast<uint32_t *>(lit + lpos + k) = ld32u(src, prevE + k);
-                for (; k < ll; k++) lit[lpos + k] = src[prevE + k];
-            }
-            // repeat code 1 (= offset of the previous sequence, valid with litLen > 0; seqdec.go:463-500)
-            const bool isrep = (gi > 0) && (d0 == pOff) && (ll > 0);
-            const uint32_t ofv = isrep ? 1u : d0 + 3;
-            wlen.put(gi, ll, l0 - 3); wof[gi] = ofv;
-            wcodes[TBL_LL * mseq + gi] = (uint8_t)seq_ll_code(ll);
-            wcodes[TBL_OF * mseq + gi] = (uint8_t)highbit32(ofv);
-            wcodes[TBL_ML * mseq + gi] = (uint8_t)seq_ml_code(l0 - 3);
-            prevE = s0 + l0; mrun += l0; pOff = d0; gi++;
-        }
-        B2C_PHASE(11);
-        const uint32_t tl = n - lastEnd;
-        for (uint32_t k = tid; k < tl; k += ENC_NT) lit[nlit - tl + k] = src[lastEnd + k];
-    }
-    if (tid == 0) { sh->kind = kind; sh->rleLen = 0; }
-    __syncthreads();
-    // single-sequence RLE block test (blockenc.go:484-493); nlit <= 1
-    if (kind == 0 && nseq == 1 && nlit <= 1 && tid == 0) {
-        uint32_t ll0 = wlen.peek_ll(0), of0 = wof[0];
-        if (ll0 == nlit && of0 - 3 == 1) { sh->kind = 2; sh->rleLen = wlen.peek_ml(0) + 3 + ll0; }
-    }
-    if (kind == 0 && nseq == 1 && saved < 16 && tid == 0 && sh->kind == 0) sh->kind = 1;
-    __syncthreads();
-    kind = sh->kind;
-    B2C_PHASE(4);
-
-    // ---------------------------------------------------------------- P5: histograms (src is dead from here on)
-    if (kind == 0) {
-        // literal histogram: warps 0..15, one private u8 counter per (symbol, lane) -- no atomics, no races.  A lane
-        // sees at most nlit / 512 + 4 literals, so a counter cannot wrap.  Four literals per load; equal symbols inside
-        // a word are merged so the four updates are independent.  Warps 16..31 count the sequence codes and copy the
-        // literals out meanwhile.
-#ifndef ENC_LH_WARPS
-#define ENC_LH_WARPS 8
-#endif
-        constexpr int LH_WARPS = ENC_LH_WARPS;   // literal counting warps (8..16); the rest count codes and copy literals out
-        uint8_t *lcolA = smem + ENC_SMEM_L;        // tables 0..7  [8][256][32] u8
-        uint8_t *lcolB = smem + ENC_SMEM_SRC;      // tables 8..15 (src is dead)
-        for (uint32_t i = tid; i < 8 * 256 * 32 / 4; i += ENC_NT) {
-            reinterpret_cast<uint32_t *>(lcolA)[i] = 0;
-            if (LH_WARPS > 8 && i < (LH_WARPS - 8) * 256 * 32 / 4) reinterpret_cast<uint32_t *>(lcolB)[i] = 0;
-        }
-        __syncthreads();
-        B2C_PHASE(12);
-        if (w < LH_WARPS) {
-            uint8_t *hcol = (w < 8 ? lcolA + w * 256 * 32 : lcolB + (w - 8) * 256 * 32) + lane;
-            const uint32_t nl4 = (nlit + 3) / 4;
-            const uint32_t *lit32 = reinterpret_cast<const uint32_t *>(lit);
-            uint32_t i = w * 32 + lane;
-            uint32_t v = (i < nl4) ? lit32[i] : 0;
-            while (i < nl4) {
-                const uint32_t inext = i + LH_WARPS * 32;
-                const uint32_t vnext = (inext < nl4) ? lit32[inext] : 0;     // next word requested before this one is used
-                const uint32_t nv = (4 * i + 4 <= nlit) ? 4u : nlit - 4 * i;
-                const uint32_t s0 = v & 0xff, s1 = (v >> 8) & 0xff, s2 = (v >> 16) & 0xff, s3 = v >> 24;
-                uint32_t i0 = 1, i1 = nv > 1, i2 = nv > 2, i3 = nv > 3;
-                if (s1 == s0) { i0 += i1; i1 = 0; }
-                if (s2 == s0) { i0 += i2; i2 = 0; } else if (s2 == s1) { i1 += i2; i2 = 0; }
-                if (s3 == s0) { i0 += i3; i3 = 0; } else if (s3 == s1) { i1 += i3; i3 = 0; } else if (s3 == s2) { i2 += i3; i3 = 0; }
-                const uint32_t c0 = hcol[s0 * 32], c1 = hcol[s1 * 32], c2 = hcol[s2 * 32], c3 = hcol[s3 * 32];
-                hcol[s0 * 32] = (uint8_t)(c0 + i0);
-                if (i1) hcol[s1 * 32] = (uint8_t)(c1 + i1);
-                if (i2) hcol[s2 * 32] = (uint8_t)(c2 + i2);
-                if (i3) hcol[s3 * 32] = (uint8_t)(c3 + i3);
-                i = inext; v = vnext;
-            }
-        } else {
-            // sequence-code counts, ballot style (lane l owns the codes whose low 5 bits equal l), kept in registers
-            // (codes come back from L2: four rounds of loads are put in flight before the first one is used)
-            constexpr uint32_t STEP = (ENC_NW - LH_WARPS) * 32;
-            for (uint32_t base = (w - LH_WARPS) * 32; base < nseq; base += 4 * STEP) {
-                uint32_t cv3[4][3];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t i = base + u * STEP + lane;
-#pragma unroll
-                    for (int c = 0; c < 3; c++) cv3[u][c] = (i < nseq) ? (uint32_t)wcodes[c * mseq + i] : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const bool valid = base + u * STEP + lane < nseq;
-                    if (base + u * STEP < nseq) {      // warp-uniform
-#pragma unroll
-                        for (int c = 0; c < 3; c++) warp_hist_acc<6>(cv3[u][c], valid, seqCnt[c], lane);
-                    }
-                }
-            }
-            // literals to the work record (coalesced 16-byte stores)
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(lit);
-            uint4 *d4 = reinterpret_cast<uint4 *>(wk_lit(P, chunk));
-            const uint32_t n16 = (nlit + 15) / 16;
-            for (uint32_t i = tid - LH_WARPS * 32; i < n16; i += ENC_NT - LH_WARPS * 32) d4[i] = s4[i];
-        }
-        B2C_PHASE(13);
-        __syncthreads();
-        B2C_PHASE(14);
-        if (tid < 256) {
-            // 16 tables x 32 byte counters of symbol `tid`; word j of every row is taken in a rotated order so the 32
-            // threads of a warp (row stride 8 words) do not pile onto the same banks
-            uint32_t c = 0;
-#pragma unroll
-            for (int k = 0; k < LH_WARPS; k++) {
-                const uint8_t *tb = (k < 8) ? lcolA + k * 256 * 32 : lcolB + (k - 8) * 256 * 32;
-                const uint32_t *row = reinterpret_cast<const uint32_t *>(tb + tid * 32);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint32_t v = row[(j + (tid >> 2)) & 7];
-                    c += (v & 0xff) + ((v >> 8) & 0xff) + ((v >> 16) & 0xff) + (v >> 24);
-                }
-            }
-            W->litHist[tid] = c;
-        }
-        __syncthreads();      // the literal tables are dead: their first rows take the per-warp code counts
-        uint32_t *shist2 = reinterpret_cast<uint32_t *>(smem + ENC_SMEM_L);   // [32][192]
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            shist2[w * 192 + c * 64 + lane] = seqCnt[c][0];
-            shist2[w * 192 + c * 64 + 32 + lane] = seqCnt[c][1];
-        }
-        __syncthreads();
-        if (tid < 192) {
-            uint32_t c = 0;
-            for (int k = 0; k < ENC_NW; k++) c += shist2[k * 192 + tid];
-            W->seqHist[tid / 64][tid % 64] = c;
-            // highest used code of each table: the three groups of 64 threads are warp-aligned (2 warps each)
-            const unsigned nz = __ballot_sync(FULLMASK, c != 0);
-            if ((tid & 31) == 0) shist2[ENC_NW * 192 + (tid >> 5)] = nz;
-        }
-        __syncthreads();
-        if (tid < 3) {
-            const uint32_t lo = shist2[ENC_NW * 192 + 2 * tid], hi = shist2[ENC_NW * 192 + 2 * tid + 1];
-            W->maxSym[tid] = hi ? 32 + (31 - (uint32_t)__clz((int)hi)) : (lo ? 31 - (uint32_t)__clz((int)lo) : 0u);
-        }
-        if (P.dbg_hdr) {
-            for (uint32_t i = tid; i < nseq && i < P.dbg_seq_cap; i += ENC_NT) {
-                uint32_t *d = P.dbg_seqs + ((uint64_t)chunk * P.dbg_seq_cap + i) * 3;
-                d[0] = wlen.peek_ll(i); d[1] = wlen.peek_ml(i); d[2] = wof[i];
-            }
-            for (uint32_t i = tid; i < nlit; i += ENC_NT) P.dbg_lits[(uint64_t)chunk * 65536 + i] = lit[i];
-        }
-    }
-#undef REC
-    if (tid == 0) { W->n = n; W->nseq = nseq; W->nlit = nlit; W->kind = kind; W->rleLen = sh->rleLen; }
-    __syncthreads();
-    B2C_PHASE(5);
 }
 
 // ------------------------------------------------------------------------------------------------ K2
@@ -1427,22 +779,6 @@ B2C_DEV void zstd_xxh_quad(const ZstdEncParams &P, uint32_t chunk, unsigned q /*
 }
 
 #ifndef B2C_EMU
-// S2 / Snappy block encode: the same parse, tag-stream emission instead of the entropy stages (one kernel).
-extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_s2_encode_kernel(ZstdEncParams P) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_S2>(smem, P, c, scratch);
-}
-extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_snappy_encode_kernel(ZstdEncParams P) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_SNAPPY>(smem, P, c, scratch);
-}
-extern "C" __global__ void __launch_bounds__(ENC_NT, 1) b2c_zstd_parse_kernel(ZstdEncParams P) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * ENC_SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_parse_chunk<LZ_MODE_ZSTD>(smem, P, c, scratch);
-}
 extern "C" __global__ void __launch_bounds__(TABLES_NT, TABLES_MIN_CTAS) b2c_zstd_tables_kernel(ZstdEncParams P) {
     __shared__ TablesShared ts;
     if (threadIdx.x < 3) seq_build_predef(&ts.sw, (int)threadIdx.x);

@@ -17,14 +17,13 @@ extern "C" {
 void emu_set_lane_order(int desc) { emu::lane_order_desc = desc; }
 
 // Encode nchunks chunks laid out contiguously (chunk i = src + i*stride, size sizes[i]) with the same kernels the
-// device runs.  level 1 / 2; parse 0 = tile-ordered parse (b2c_lz.cuh, the product path), 1 = the round-1 parse
-// (level 1 only).  dst slots of dst_stride bytes.  Optional debug dumps (may be null; dbg_lits rows of blockmax bytes).
+// device runs.  level 1 / 2 / 3; parse must be 0 (kept in the signature for the test helpers).  dst slots of dst_stride bytes.  Optional debug dumps (may be null; dbg_lits rows of blockmax bytes).
 int emu_zstd_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
                        uint64_t dst_stride, int64_t *out_sizes, uint32_t flags, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
                        uint8_t *dbg_lits, uint32_t dbg_seq_cap, int level, int parse) {
     const uint32_t blockmax = level >= 2 ? 131072u : 65536u;
-    if (parse == 1 && level != 1) return -1;
-    std::vector<uint8_t> scratch(std::max<size_t>(ENC_SCRATCH_BYTES, std::max(LzLayout<1>::SCRATCH_BYTES, std::max(LzLayout<2>::SCRATCH_BYTES, LzLayout<5>::SCRATCH_BYTES))), 0xCD);
+    if (parse != 0) return -1;
+    std::vector<uint8_t> scratch(std::max<size_t>(16, std::max(LzLayout<1>::SCRATCH_BYTES, std::max(LzLayout<2>::SCRATCH_BYTES, LzLayout<5>::SCRATCH_BYTES))), 0xCD);
     ChunkWork *work = (ChunkWork *)aligned_alloc(16, sizeof(ChunkWork) * (size_t)nchunks);
     memset(work, 0xCD, sizeof(ChunkWork) * (size_t)nchunks);
     const uint64_t pstride = wk_pool_stride(blockmax);
@@ -44,11 +43,7 @@ int emu_zstd_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *size
         zstd_xxh_quad(P, gt >> 2, gt & 3, (threadIdx.x & 31) & ~3u);
     });
     // K1 parse
-    if (parse == 1) {
-        emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
-            for (uint32_t c = 0; c < P.nchunks; c++) zstd_parse_chunk<LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
-        });
-    } else {
+    {
         if (level >= 3)
             emu::launch(1, LzCfg<5>::NT, LzLayout<5>::SMEM_BYTES, [&]() {
                 for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<5, LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
@@ -110,24 +105,17 @@ int emu_zstd_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t 
 }
 
 // S2 (snappy = 0) / Snappy-compatible (snappy = 1) block encode of nchunks chunks (chunk i = src + i*stride).
-// better: 0 = s2.Encode's class, 1 = s2.EncodeBetter's; parse 0 = tile-ordered parse (product), 1 = round-1 kernel (fast only)
+// better: 0 = s2.Encode's class, 1 = s2.EncodeBetter's; parse must be 0
 int emu_s2_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
                      uint64_t dst_stride, int64_t *out_sizes, int snappy, int better, int parse) {
-    if (parse == 1 && better) return -1;
-    std::vector<uint8_t> scratch(std::max<size_t>(ENC_SCRATCH_BYTES, std::max(LzLayout<3>::SCRATCH_BYTES, LzLayout<4>::SCRATCH_BYTES)), 0xCD);
+    if (parse != 0) return -1;
+    std::vector<uint8_t> scratch(std::max<size_t>(16, std::max(LzLayout<3>::SCRATCH_BYTES, LzLayout<4>::SCRATCH_BYTES)), 0xCD);
     ZstdEncParams P;
     memset(&P, 0, sizeof(P));
     P.src_base = src; P.src_stride = stride; P.src_sizes = sizes;
     P.dst_base = dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
     P.out_sizes = out_sizes; P.nchunks = nchunks; P.scratch = scratch.data(); P.blockmax = 65536;
-    if (parse == 1) {
-        emu::launch(1, ENC_NT, ENC_SMEM_BYTES, [&]() {
-            for (uint32_t c = 0; c < P.nchunks; c++) {
-                if (snappy) zstd_parse_chunk<LZ_MODE_SNAPPY>(emu::dyn_smem, P, c, P.scratch);
-                else zstd_parse_chunk<LZ_MODE_S2>(emu::dyn_smem, P, c, P.scratch);
-            }
-        });
-    } else if (better) {
+    if (better) {
         emu::launch(1, LzCfg<4>::NT, LzLayout<4>::SMEM_BYTES, [&]() {
             for (uint32_t c = 0; c < P.nchunks; c++) {
                 if (snappy) lz_parse_chunk<4, LZ_MODE_SNAPPY>(emu::dyn_smem, P, c, P.scratch);
@@ -206,7 +194,6 @@ int emu_huf_read_table(const uint8_t *src, uint64_t stride, const uint32_t *size
     return 0;
 }
 
-uint32_t emu_enc_smem_bytes() { return ENC_SMEM_BYTES; }
 uint32_t emu_lz_smem_bytes(int level) { return level >= 2 ? LzLayout<2>::SMEM_BYTES : LzLayout<1>::SMEM_BYTES; }
 uint32_t emu_pack_smem_bytes() { return PACK_SMEM_BYTES; }
 uint64_t emu_chunkwork_bytes() { return sizeof(ChunkWork); }

@@ -12,11 +12,11 @@ M = ctypes.CDLL(SO)
 
 class Cfg(ctypes.Structure):
     _fields_ = [(k, ctypes.c_uint32) for k in
-                "rangeBytes shortBits shortMls longBits longMls insStride lazy repProbe repCodes joinCont minLong minShort maxDist hist latest tile local lag both dyn".split()]
+                "rangeBytes shortBits shortMls longBits longMls insStride lazy repProbe repCodes joinCont minLong minShort maxDist hist latest tile local lag probeStride both dyn".split()]
 
 def mk(**kw):
     d = dict(rangeBytes=68, shortBits=15, shortMls=6, longBits=0, longMls=8, insStride=1, lazy=0, repProbe=0,
-             repCodes=1, joinCont=0, minLong=4, minShort=4, maxDist=0, hist=0, latest=0, tile=0, local=0, lag=0, both=0, dyn=0)
+             repCodes=1, joinCont=0, minLong=4, minShort=4, maxDist=0, hist=0, latest=0, tile=0, local=0, lag=0, probeStride=0, both=0, dyn=0)
     d.update(kw)
     return Cfg(**d)
 

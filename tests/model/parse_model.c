@@ -27,6 +27,7 @@ typedef struct {
     uint32_t tile;         /* dyn only: >0 = a position only sees insertions from earlier tiles of this many positions */
     uint32_t local;        /* tile only: 1 = plus the latest equal-hash position inside the same aligned 32-position group */
     uint32_t lag;          /* dyn only: candidates are at least this far back (exact latest otherwise) */
+    uint32_t probeStride;  /* 2 = only even positions are probed (candidates exist at even positions only) */
     uint32_t both;         /* 1 = the walk extends the near and the far candidate and keeps the longer match */
     uint32_t dyn;          /* 1 = candidate = latest earlier position with the same hash (upper bound: a dynamic table) */
 } pm_cfg;
@@ -132,6 +133,7 @@ int pm_parse(const uint8_t *src, uint32_t n, const pm_cfg *c, uint32_t *triples,
         while (p < pend) {
             uint64_t v = rd64(src + p);
             uint32_t cand = 0xffffffffu;
+            if (c->probeStride == 2 && (p & 1)) { p++; continue; }
             if (repLeft && prevOff && p >= prevOff && rd32(src + p - prevOff) == (uint32_t)v) cand = p - prevOff;
             if (repLeft) repLeft--;
             if (cand == 0xffffffffu && EL) {

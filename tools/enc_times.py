@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel device times (ms per GiB of input) of the zstd encode pipeline at level 1 or 2, from the library's own
-CUDA-event profile.  usage: enc_times.py [level] [GiB]   (B2C_PARSE=r1 selects the round-1 parse kernel at level 1)"""
+CUDA-event profile.  usage: enc_times.py [level] [GiB]"""
 import hashlib
 import os
 import sys
@@ -38,7 +38,7 @@ tot = e0.elapsed_time(e1) / steps
 o = outs.cpu()
 assert int(o.min()) > 0
 from compress_b200 import _lib
-print("level %d  parse %s  %d x %d KiB   lib md5 %s" % (level, os.environ.get("B2C_PARSE", "lz"), n, CH >> 10,
+print("level %d  %d x %d KiB   lib md5 %s" % (level, n, CH >> 10,
                                                     hashlib.md5(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:10]))
 print("  step %.3f ms = %.1f GB/s; ratio %.4f; sizes sha1 %s" % (
     tot, n * CH / tot / 1e6, float(o.sum()) / (n * CH), hashlib.sha1(o.numpy().tobytes()).hexdigest()[:12]))

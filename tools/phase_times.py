@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Per-phase cycle breakdown of the level-1 parse kernel (b2c_lz_parse1_kernel; with B2C_PARSE=r1 the round-1 kernel):
+"""Per-phase cycle breakdown of the level-1 parse kernel (b2c_lz_parse1_kernel):
 lane 0 of every warp stamps clock64 at the phase boundaries (B2C_PHASE), dumped through b2c_zstd_encode_device_timed."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -31,12 +31,7 @@ def main():
     c = cyc.cpu().numpy().astype(np.int64)       # [n, 16, 32]: arrival of warp w at stamp k (0 where the warp does not exist)
     nw = int((c[0, 0] != 0).sum())
     c = c[:, :, :nw]
-    if os.environ.get("B2C_PARSE") == "r1":
-        order = [0, 1, 2, 6, 3, 8, 9, 10, 11, 4, 12, 13, 14, 5]
-        names = ["load", "table build", "candidate pass + walk", "long matches", "prefix max", "trim", "scans", "emit + gather",
-                 "tail + RLE", "zero counters", "histograms + copy-out", "barrier", "reduce + end"]
-    else:
-        order, names = ORDER, NAMES
+    order, names = ORDER, NAMES
     tot = c[:, order[-1], :].max(axis=1) - c[:, order[0], :].min(axis=1)
     print("parse kernel: chunks %d, warps/CTA %d, mean cycles/chunk %.0f (min %d, max %d)" % (n, nw, tot.mean(), tot.min(), tot.max()))
     for a, b, nm in zip(order[:-1], order[1:], names):
