@@ -16,6 +16,7 @@
 #include "b2c_zstd_enc.cuh"
 #include "b2c_lz.cuh"
 #include "b2c_zstd_dec.cuh"
+#include "b2c_zstd_dec_staged.cuh"
 #include "b2c_s2_dec.cuh"
 #include "b2c_huf0.cuh"
 
@@ -62,6 +63,11 @@ struct b2c_ctx {
     cudaEvent_t ev_out[2] = {nullptr, nullptr};   // D2H of slot s finished
     // decoder: per-warp literal scratch, host-path staging (grown on demand)
     uint8_t *d_dec_lit = nullptr; size_t dec_lit_cap = 0;
+    uint8_t *d_fd = nullptr; size_t fd_cap = 0;            // staged decoder: records | tables
+    uint8_t *d_fd_seq = nullptr; size_t fd_seq_cap = 0;    //   sequence records
+    uint8_t *d_fd_lit = nullptr; size_t fd_lit_cap = 0;    //   decoded literals
+    int dec_staged = 1;                                    // B2C_DEC=onewarp: one-warp decoder only (A/B measurements)
+    float dec_ms[5] = {0, 0, 0, 0, 0}; cudaEvent_t dec_ev[6] = {}; int dec_prof = 0;
     uint8_t *d_dec_in = nullptr, *d_dec_out = nullptr; size_t dec_in_cap = 0, dec_out_cap = 0;
     uint8_t *d_dec_meta = nullptr; size_t dec_meta_cap = 0;
     uint8_t *h_stg_in = nullptr, *h_stg_out = nullptr; size_t h_stg_in_cap = 0, h_stg_out_cap = 0;   // pinned staging of the pointer-table calls
@@ -198,6 +204,13 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_dec_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)DEC_SMEM_BYTES) == cudaSuccess;
+    for (int i = 0; i < 6; i++) ok = ok && cudaEventCreate(&ctx->dec_ev[i]) == cudaSuccess;
+    {
+        const char *de = getenv("B2C_DEC");
+        ctx->dec_staged = (de && strcmp(de, "onewarp") == 0) ? 0 : 1;
+    }
     ok = ok && cudaFuncSetAttribute(b2c_zstd_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)PACK_SMEM_BYTES) == cudaSuccess;
     if (ok && max_chunks) {
@@ -235,6 +248,7 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFreeHost(ctx->h_stg_in); cudaFreeHost(ctx->h_stg_out);
+    cudaFree(ctx->d_fd); cudaFree(ctx->d_fd_seq); cudaFree(ctx->d_fd_lit);
     cudaFree(ctx->d_dec_lit); cudaFree(ctx->d_dec_in); cudaFree(ctx->d_dec_out); cudaFree(ctx->d_dec_meta);
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_pool[0]); cudaFree(ctx->d_pool[1]);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
@@ -296,6 +310,20 @@ int b2c_profile_read(b2c_ctx *ctx, double *ms, uint32_t *ncalls) {
         }
     if (ncalls) *ncalls = (uint32_t)(ctx->pev_used / 7);
     ctx->pev_used = 0;
+    return B2C_OK;
+}
+
+// Decode-side counterpart: ms[0..4] = summed durations of {scan, sequences, execute, xxh64, one-warp decoder} over the
+// staged decode launches since b2c_decode_profile_enable(ctx, 1).  Enabled, every decode launch synchronises.
+int b2c_decode_profile_enable(b2c_ctx *ctx, int on) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    ctx->dec_prof = on != 0;
+    for (int i = 0; i < 5; i++) ctx->dec_ms[i] = 0.f;
+    return B2C_OK;
+}
+int b2c_decode_profile_read(b2c_ctx *ctx, double *ms) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    for (int i = 0; i < 5; i++) { ms[i] = (double)ctx->dec_ms[i]; ctx->dec_ms[i] = 0.f; }
     return B2C_OK;
 }
 
@@ -757,7 +785,11 @@ static int scatter_d2h(b2c_ctx *ctx, void *const *dsts, const size_t *lens, cons
     return B2C_OK;
 }
 
-static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st) {
+// lit_span: bytes of the output layout (literal areas mirror it: input c's area starts at c * lit_stride, or at
+// dst_offsets[c] when lit_stride is 0 -- the caller then guarantees non-overlapping, increasing offsets); 0 = unknown: the
+// one-warp decoder takes every input.
+static const uint64_t kStagedSpanLimit = 24ull << 30;
+static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st, uint64_t lit_span, uint64_t lit_stride) {
     if (P.nchunks == 0) return B2C_OK;
     const unsigned ctasPerSm = (227u * 1024u) / (DEC_SMEM_BYTES + 1024u);
     unsigned grid = (P.nchunks + DEC_WARPS - 1) / DEC_WARPS;
@@ -766,8 +798,38 @@ static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st) {
     int rc = grow(ctx, &ctx->d_dec_lit, &ctx->dec_lit_cap, (size_t)maxGrid * DEC_WARPS * DEC_LIT_SCRATCH);
     if (rc) return rc;
     P.lit_scratch = ctx->d_dec_lit;
+    const uint32_t n = P.nchunks;
+    const bool prof = ctx->dec_prof != 0;
+    const bool staged = ctx->dec_staged && lit_span > 0 && lit_span <= kStagedSpanLimit && (uint64_t)n * sizeof(FdChunk) < (1ull << 31);
+    if (staged) {
+        const size_t recBytes = (((size_t)n * sizeof(FdChunk)) + 255) & ~(size_t)255;
+        const size_t tabBytes = (size_t)n * FD_MAXB * FD_TAB_ENTRIES * sizeof(uint2);
+        if ((rc = grow(ctx, &ctx->d_fd, &ctx->fd_cap, recBytes + tabBytes))) return rc;
+        if ((rc = grow(ctx, &ctx->d_fd_seq, &ctx->fd_seq_cap, 8 * ((size_t)(lit_span / 3) + 2 * (size_t)n + 8)))) return rc;
+        if ((rc = grow(ctx, &ctx->d_fd_lit, &ctx->fd_lit_cap, (size_t)lit_span + 64))) return rc;
+        P.fd = reinterpret_cast<FdChunk *>(ctx->d_fd);
+        P.fd_tabs = reinterpret_cast<uint2 *>(ctx->d_fd + recBytes);
+        P.fd_seqs = reinterpret_cast<uint64_t *>(ctx->d_fd_seq);
+        P.fd_lits = ctx->d_fd_lit;
+        P.fd_lit_stride = lit_stride;
+        if (prof) cudaEventRecord(ctx->dec_ev[0], st);
+        b2c_zstd_dec_scan_kernel<<<grid, FD_SCAN_WARPS * 32, DEC_SMEM_BYTES, st>>>(P);
+        if (prof) cudaEventRecord(ctx->dec_ev[1], st);
+        b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+        if (prof) cudaEventRecord(ctx->dec_ev[2], st);
+        b2c_zstd_dec_exec_kernel<<<(n + FD_EXEC_WARPS - 1) / FD_EXEC_WARPS, FD_EXEC_WARPS * 32, 0, st>>>(P);
+        if (prof) cudaEventRecord(ctx->dec_ev[3], st);
+        b2c_zstd_dec_xxh_kernel<<<(unsigned)(((uint64_t)n * 4 + 127) / 128), 128, 0, st>>>(P);
+        if (prof) cudaEventRecord(ctx->dec_ev[4], st);
+        ctx->launches += 4;
+    }
     b2c_zstd_decode_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, st>>>(P);
     ctx->launches += 1;
+    if (prof && staged) {
+        cudaEventRecord(ctx->dec_ev[5], st);
+        cudaEventSynchronize(ctx->dec_ev[5]);
+        for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->dec_ev[i], ctx->dec_ev[i + 1]); ctx->dec_ms[i] += ms; }
+    }
     CK(cudaGetLastError());
     return B2C_OK;
 }
@@ -783,7 +845,8 @@ int b2c_zstd_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, c
     P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_offsets = d_src_offsets; P.src_sizes = d_src_sizes;
     P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_offsets = d_dst_offsets; P.dst_cap = dst_cap;
     P.out_sizes = d_out_sizes; P.nchunks = nchunks;
-    return launch_decode(ctx, P, (cudaStream_t)stream);
+    // literal areas: one of dst_cap bytes per input
+    return launch_decode(ctx, P, (cudaStream_t)stream, (uint64_t)nchunks * dst_cap, dst_cap);
 }
 
 // Host pre-scan of a zstd stream (no decompression): the frames it is made of, each with its byte range and -- when the
@@ -913,7 +976,7 @@ int b2c_zstd_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const size_t *
     P.src_base = ctx->d_dec_in; P.src_offsets = dm; P.src_sizes = reinterpret_cast<uint32_t *>(dm + 3 * m);
     P.dst_base = ctx->d_dec_out; P.dst_offsets = dm + m; P.dst_caps = P.src_sizes + m;
     P.out_sizes = reinterpret_cast<int64_t *>(dm + 2 * m); P.nchunks = (uint32_t)m;
-    if ((rc = launch_decode(ctx, P, st))) return rc;
+    if ((rc = launch_decode(ctx, P, st, outb, 0))) return rc;
     std::vector<int64_t> res(m);
     CK(cudaMemcpyAsync(res.data(), P.out_sizes, m * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

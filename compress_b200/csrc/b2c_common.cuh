@@ -179,6 +179,81 @@ struct BitRun {
     }
 };
 
+// XXH64 (zstd/internal/xxhash/xxhash.go:62-160) of src[0, n): four adjacent lanes (q = 0..3, the first of them lane
+// quadBaseLane of the warp) hold the four accumulators; all four must call (with n = 0 when they have no input); the
+// digest is returned on q == 0.
+B2C_DEV uint64_t xxh64_quad(const uint8_t *src, uint64_t n, unsigned q /*0..3*/, unsigned quadBaseLane) {
+    const uint64_t P1 = 11400714785074694791ull, P2 = 14029467366897019727ull, P3 = 1609587929392839161ull,
+                   P4 = 9650029242287828579ull, P5 = 2870177450012600261ull;
+    const bool aligned = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
+    uint64_t v = (q == 0) ? P1 + P2 : (q == 1) ? P2 : (q == 2) ? 0ull : (0ull - P1);
+    const uint64_t stripes = n / 32;
+    uint64_t i = 0;
+    if (aligned) {
+        // sixteen stripes per batch: the loads are independent of the accumulator, so they are all in flight while
+        // the (serial) multiply-rotate chain of the previous ones runs
+        const uint64_t *s8 = reinterpret_cast<const uint64_t *>(src) + q;
+        for (; i + 16 <= stripes; i += 16) {
+            uint64_t in[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) in[k] = s8[4 * (i + k)];
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                v += in[k] * P2;
+                v = (v << 31) | (v >> 33);
+                v *= P1;
+            }
+        }
+    }
+    for (; i < stripes; i++) {
+        uint64_t in;
+        if (aligned) in = reinterpret_cast<const uint64_t *>(src)[4 * i + q];
+        else { in = 0; for (int b = 0; b < 8; b++) in |= (uint64_t)src[32 * i + 8 * q + b] << (8 * b); }
+        v += in * P2;
+        v = (v << 31) | (v >> 33);
+        v *= P1;
+    }
+    uint64_t v1 = __shfl_sync(FULLMASK, v, quadBaseLane), v2 = __shfl_sync(FULLMASK, v, quadBaseLane + 1),
+             v3 = __shfl_sync(FULLMASK, v, quadBaseLane + 2), v4 = __shfl_sync(FULLMASK, v, quadBaseLane + 3);
+    if (q != 0) return 0;
+    uint64_t h;
+    uint64_t p = stripes * 32;
+    if (n >= 32) {
+        h = ((v1 << 1) | (v1 >> 63)) + ((v2 << 7) | (v2 >> 57)) + ((v3 << 12) | (v3 >> 52)) + ((v4 << 18) | (v4 >> 46));
+#define XMERGE(vv)                                                                                     \
+    do {                                                                                               \
+        uint64_t t_ = (vv) * P2; t_ = (t_ << 31) | (t_ >> 33); t_ *= P1;                               \
+        h ^= t_; h = h * P1 + P4;                                                                      \
+    } while (0)
+        XMERGE(v1); XMERGE(v2); XMERGE(v3); XMERGE(v4);
+#undef XMERGE
+    } else {
+        h = P5;
+    }
+    h += n;
+    while (p + 8 <= n) {
+        uint64_t k1 = 0;
+        for (int b = 0; b < 8; b++) k1 |= (uint64_t)src[p + b] << (8 * b);
+        k1 *= P2; k1 = (k1 << 31) | (k1 >> 33); k1 *= P1;
+        h ^= k1; h = ((h << 27) | (h >> 37)) * P1 + P4;
+        p += 8;
+    }
+    if (p + 4 <= n) {
+        uint32_t k4 = 0;
+        for (int b = 0; b < 4; b++) k4 |= (uint32_t)src[p + b] << (8 * b);
+        h ^= (uint64_t)k4 * P1;
+        h = ((h << 23) | (h >> 41)) * P2 + P3;
+        p += 4;
+    }
+    while (p < n) {
+        h ^= (uint64_t)src[p] * P5;
+        h = ((h << 11) | (h >> 53)) * P1;
+        p++;
+    }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
 #ifndef B2C_EMU
 // ---- 1-D TMA bulk copy global -> shared with mbarrier completion (UBLKCP) ----
 B2C_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

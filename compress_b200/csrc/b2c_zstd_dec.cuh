@@ -61,7 +61,15 @@ struct ZstdDecParams {
     int64_t *out_sizes;                                                        // decoded bytes or negative error
     uint32_t nchunks;
     uint8_t *lit_scratch;                                                      // [gridDim.x * DEC_WARPS][DEC_LIT_SCRATCH]
+    // staged path (b2c_zstd_dec_staged.cuh); fd == nullptr: every input goes through the one-warp decoder, else only the
+    // inputs the staged stages marked
+    struct FdChunk *fd;                                                        // [nchunks]
+    uint2 *fd_tabs;                                                            // [nchunks][FD_MAXB][FD_TAB_ENTRIES]
+    uint64_t *fd_seqs;                                                         // sequence records, fd_seq_off(c)
+    uint8_t *fd_lits;                                                          // decoded literals, fd_lit_off(c)
+    uint64_t fd_lit_stride;                                                    // literal area of input c at c * stride (0: dst_offsets[c])
 };
+B2C_DEV bool dec_staged_done(const ZstdDecParams &P, uint32_t c);               // b2c_zstd_dec_staged.cuh
 
 // ---- backward bit reader over global memory (zstd/bitreader.go semantics: exact consumption required).
 // The stream is a little-endian integer; `total` payload bits sit below the end mark; reads take bits from the top
@@ -911,6 +919,7 @@ B2C_DEV void zstd_decode_warp(uint8_t *smem, const ZstdDecParams &P, uint32_t wa
     __syncthreads();
     dec_build_predef(dw, lane);
     for (uint32_t c = warpGlobal; c < P.nchunks; c += totalWarps) {
+        if (P.fd && dec_staged_done(P, c)) continue;
         const uint8_t *src = P.src_base + (P.src_offsets ? P.src_offsets[c] : (uint64_t)c * P.src_stride);
         uint8_t *dst = P.dst_base + (P.dst_offsets ? P.dst_offsets[c] : (uint64_t)c * P.dst_stride);
         uint32_t cap = P.dst_caps ? P.dst_caps[c] : P.dst_cap;

@@ -198,7 +198,7 @@ ErrDecoderSizeExceeded = -4
 
 
 class Decoder:
-    """zstd.Decoder for batches of independent streams on one B200 (one warp per stream)."""
+    """zstd.Decoder for batches of independent streams on one B200 (staged kernels; a one-warp decoder for the rest)."""
 
     def __init__(self, device=0, max_decoded=64 << 20):
         if not torch.cuda.is_available() or lib.b2c_device_count() == 0:
@@ -223,6 +223,18 @@ class Decoder:
     @property
     def launches(self):
         return int(lib.b2c_launch_count(self._ctx))
+
+    DECODE_KERNELS = ("b2c_zstd_dec_scan_kernel", "b2c_zstd_dec_seq_kernel", "b2c_zstd_dec_exec_kernel",
+                      "b2c_zstd_dec_xxh_kernel", "b2c_zstd_decode_kernel")
+
+    def profile(self, on=True):
+        check(lib.b2c_decode_profile_enable(self._ctx, 1 if on else 0), self._ctx)
+
+    def profile_read(self):
+        """-> {kernel name: summed ms} of the decode launches since profile(True)."""
+        ms = (ctypes.c_double * 5)()
+        check(lib.b2c_decode_profile_read(self._ctx, ms), self._ctx)
+        return {k: float(ms[i]) for i, k in enumerate(self.DECODE_KERNELS)}
 
     def decode_device(self, src, src_sizes, src_offsets=None, src_stride=0, dst=None, dst_cap=CHUNK, dst_offsets=None,
                       out_sizes=None, dst_stride=None):

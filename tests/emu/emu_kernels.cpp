@@ -4,6 +4,7 @@
 #include "../../compress_b200/csrc/b2c_zstd_enc.cuh"
 #include "../../compress_b200/csrc/b2c_lz.cuh"
 #include "../../compress_b200/csrc/b2c_zstd_dec.cuh"
+#include "../../compress_b200/csrc/b2c_zstd_dec_staged.cuh"
 #include "../../compress_b200/csrc/b2c_s2_dec.cuh"
 #include "../../compress_b200/csrc/b2c_huf0.cuh"
 #include <vector>
@@ -88,8 +89,11 @@ int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, 
 }
 
 // Decode n inputs (input i = src + src_off[i], src_sizes[i] bytes) into dst + dst_off[i] (capacity dst_caps[i]).
-int emu_zstd_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t *src_sizes, uint32_t n, uint8_t *dst,
-                    const uint64_t *dst_off, const uint32_t *dst_caps, int64_t *out_sizes) {
+// mode 0: the device's launch sequence (staged kernels, then the one-warp decoder over the inputs they marked; dst_off
+// must be increasing with non-overlapping [dst_off[i], dst_off[i] + dst_caps[i]) ranges); mode 1: one-warp decoder only.
+// staged_out (optional, n entries): 1 where the staged kernels produced the result.
+int emu_zstd_decode_mode(const uint8_t *src, const uint64_t *src_off, const uint32_t *src_sizes, uint32_t n, uint8_t *dst,
+                         const uint64_t *dst_off, const uint32_t *dst_caps, int64_t *out_sizes, int mode, uint8_t *staged_out) {
     uint32_t grid = (n + DEC_WARPS - 1) / DEC_WARPS;
     if (grid > 2) grid = 2;
     std::vector<uint8_t> lit((size_t)grid * DEC_WARPS * DEC_LIT_SCRATCH, 0xCD);
@@ -98,10 +102,43 @@ int emu_zstd_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t 
     P.src_base = src; P.src_offsets = src_off; P.src_sizes = src_sizes;
     P.dst_base = dst; P.dst_offsets = dst_off; P.dst_caps = dst_caps;
     P.out_sizes = out_sizes; P.nchunks = n; P.lit_scratch = lit.data();
+    std::vector<FdChunk> fd;
+    std::vector<uint2> tabs;
+    std::vector<uint64_t> seqs;
+    std::vector<uint8_t> lits;
+    if (mode == 0 && n > 0) {
+        const uint64_t span = dst_off[n - 1] + dst_caps[n - 1];
+        fd.resize(n);
+        memset(fd.data(), 0xCD, sizeof(FdChunk) * (size_t)n);
+        tabs.assign((size_t)n * FD_MAXB * FD_TAB_ENTRIES, make_uint2(0xCDCDCDCDu, 0xCDCDCDCDu));
+        seqs.assign((size_t)(span / 3) + 2 * (size_t)n + 8, 0xCDCDCDCDCDCDCDCDull);
+        lits.assign((size_t)span + 64, 0xCD);
+        P.fd = fd.data(); P.fd_tabs = tabs.data(); P.fd_seqs = seqs.data(); P.fd_lits = lits.data(); P.fd_lit_stride = 0;
+        emu::launch(grid, FD_SCAN_WARPS * 32, DEC_SMEM_BYTES, [&]() {
+            fd_scan_warp(emu::dyn_smem, P, blockIdx.x * FD_SCAN_WARPS + (threadIdx.x >> 5), gridDim.x * FD_SCAN_WARPS);
+        });
+        emu::launch((n + 31) / 32, 32, 0, [&]() {
+            const uint32_t c = blockIdx.x * 32 + threadIdx.x;
+            if (c < P.nchunks) fd_seq_lane(P, c);
+        });
+        emu::launch((n + FD_EXEC_WARPS - 1) / FD_EXEC_WARPS, FD_EXEC_WARPS * 32, 0, [&]() {
+            const uint32_t c = blockIdx.x * FD_EXEC_WARPS + (threadIdx.x >> 5);
+            if (c < P.nchunks) fd_exec_input(P, c, threadIdx.x & 31);
+        });
+        emu::launch((unsigned)(((uint64_t)n * 4 + 127) / 128), 128, 0, [&]() {
+            const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+            fd_xxh_quad(P, gt >> 2, gt & 3, (threadIdx.x & 31) & ~3u);
+        });
+        if (staged_out) for (uint32_t i = 0; i < n; i++) staged_out[i] = fd[i].state == 0;
+    }
     emu::launch(grid, DEC_WARPS * 32, DEC_SMEM_BYTES, [&]() {
         zstd_decode_warp(emu::dyn_smem, P, blockIdx.x * DEC_WARPS + (threadIdx.x >> 5), gridDim.x * DEC_WARPS);
     });
     return 0;
+}
+int emu_zstd_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t *src_sizes, uint32_t n, uint8_t *dst,
+                    const uint64_t *dst_off, const uint32_t *dst_caps, int64_t *out_sizes) {
+    return emu_zstd_decode_mode(src, src_off, src_sizes, n, dst, dst_off, dst_caps, out_sizes, 0, nullptr);
 }
 
 // S2 (snappy = 0) / Snappy-compatible (snappy = 1) block encode of nchunks chunks (chunk i = src + i*stride).

@@ -39,8 +39,10 @@ def frame_header_len(n):
     return fh
 
 
-def emu_decode(E, inputs, caps, desc=0):
-    """Run the emulated decode kernel on a list of compressed byte strings; returns (sizes, outputs)."""
+def emu_decode(E, inputs, caps, desc=0, mode=0, staged=None):
+    """Run the emulated decode kernels on a list of compressed byte strings; returns (sizes, outputs).
+    mode 0: the device's launch sequence (staged kernels, then the one-warp decoder over what they marked); mode 1: the
+    one-warp decoder alone.  staged: optional list, filled with 1 / 0 per input (result produced by the staged kernels)."""
     E.emu_set_lane_order(desc)
     n = len(inputs)
     src_off = np.zeros(n, dtype=np.uint64)
@@ -58,8 +60,11 @@ def emu_decode(E, inputs, caps, desc=0):
         src[int(src_off[i]):int(src_off[i]) + len(b)] = np.frombuffer(b, dtype=np.uint8)
     dst = np.zeros(do + 64, dtype=np.uint8)
     outs = np.zeros(n, dtype=np.int64)
-    E.emu_zstd_decode(src.ctypes.data, src_off.ctypes.data, sizes.ctypes.data, n, dst.ctypes.data, dst_off.ctypes.data,
-                      capv.ctypes.data, outs.ctypes.data)
+    flags = np.zeros(max(n, 1), dtype=np.uint8)
+    E.emu_zstd_decode_mode(src.ctypes.data, src_off.ctypes.data, sizes.ctypes.data, n, dst.ctypes.data, dst_off.ctypes.data,
+                           capv.ctypes.data, outs.ctypes.data, mode, flags.ctypes.data)
+    if staged is not None:
+        staged[:] = [int(x) for x in flags[:n]]
     res = [bytes(dst[int(dst_off[i]):int(dst_off[i]) + max(int(outs[i]), 0)]) for i in range(n)]
     return outs, res
 

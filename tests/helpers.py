@@ -41,6 +41,7 @@ def emu():
     E.emu_zstd_encode_lv.argtypes = E.emu_zstd_encode.argtypes + [c.c_int, c.c_int]
     E.emu_zstd_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,
                                   c.c_void_p]
+    E.emu_zstd_decode_mode.argtypes = E.emu_zstd_decode.argtypes + [c.c_int, c.c_void_p]
     E.emu_s2_encode.argtypes = [c.c_void_p, c.c_uint64, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_int]
     E.emu_s2_encode_lv.argtypes = E.emu_s2_encode.argtypes + [c.c_int, c.c_int]
     E.emu_s2_decode.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p,

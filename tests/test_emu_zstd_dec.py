@@ -68,9 +68,15 @@ def test_emu_decode_encoder_output(emu_lib, oracle_lib):
     # concatenated frames with a skippable frame in between
     srcs.append(srcs[5][:5000] + srcs[6][:5000])
     comps.append(enc(srcs[5][:5000]) + b"\x50\x2a\x4d\x18\x03\x00\x00\x00xyz" + enc(srcs[6][:5000]))
-    outs, res = emu_decode(emu_lib, comps, [len(s) + 16 for s in srcs])
+    staged = []
+    outs, res = emu_decode(emu_lib, comps, [len(s) + 16 for s in srcs], staged=staged)
     for i, (s, r, got) in enumerate(zip(srcs, outs, res)):
         assert r == len(s) and got == s, i
+    # the staged kernels (b2c_zstd_dec_staged.cuh) take single frames of at most four blocks; the concatenated input and
+    # the longer frames are left to the one-warp decoder
+    assert staged[:5] == [1] * 5 and staged[6] == 1 and staged[7] == 1 and staged[10] == 0, staged
+    outs1, res1 = emu_decode(emu_lib, comps, [len(s) + 16 for s in srcs], mode=1)
+    assert list(outs1) == list(outs) and res1 == res
     # too-small destination and truncation are reported, not written past
     outs, _ = emu_decode(emu_lib, [comps[5], comps[5][:-5], comps[8][:1000]], [1000, 300000, 300000])
     assert all(o < 0 for o in outs)
@@ -79,6 +85,34 @@ def test_emu_decode_encoder_output(emu_lib, oracle_lib):
 def test_emu_decode_own_frames(emu_lib):
     chunks = H.synth_chunks("text", 3) + [H.golden("twain.txt")[:65536], bytes(65536), b"xy" * 100]
     frames, outs, *_ = emu_encode(emu_lib, chunks)
-    souts, res = emu_decode(emu_lib, frames, [65536] * len(frames))
+    staged = []
+    souts, res = emu_decode(emu_lib, frames, [65536] * len(frames), staged=staged)
     for c, r, got in zip(chunks, souts, res):
         assert r == len(c) and got == c
+    assert staged == [1] * len(frames)
+
+
+def test_emu_decode_staged_levels_and_marks(emu_lib):
+    # frames of every encoder level through the staged kernels (reversed lane order too); a flipped content checksum, a
+    # flipped payload bit and a short destination are marked by a staged stage and answered by the one-warp decoder
+    # exactly as it answers them alone
+    chunks = [H.golden("twain.txt")[:131072], H.synth_chunks("text", 1, size=131072)[0][:100000], bytes(131072),
+              H.golden("html.txt")[:70000]]
+    for level in (2, 3):
+        frames, outs, *_ = emu_encode(emu_lib, chunks, level=level)
+        for desc in (0, 1):
+            staged = []
+            souts, res = emu_decode(emu_lib, frames, [len(c) for c in chunks], desc=desc, staged=staged)
+            for c, r, got in zip(chunks, souts, res):
+                assert r == len(c) and got == c
+            assert staged == [1] * len(frames), (level, desc, staged)
+    f = frames[0]
+    bad_crc = f[:-1] + bytes([f[-1] ^ 1])
+    bad_bit = f[:len(f) // 2] + bytes([f[len(f) // 2] ^ 0x10]) + f[len(f) // 2 + 1:]
+    cases = [bad_crc, bad_bit, f, f[:-3]]
+    caps = [131072, 131072, 1000, 131072]
+    staged = []
+    outs0, _ = emu_decode(emu_lib, cases, caps, staged=staged)
+    outs1, _ = emu_decode(emu_lib, cases, caps, mode=1)
+    assert list(outs0) == list(outs1) and all(o < 0 for o in outs0), (outs0, outs1)
+    assert staged == [0, 0, 0, 0]

@@ -62,6 +62,12 @@ if "--decode" in sys.argv:
     ms = d0.elapsed_time(d1) / 3
     assert bool((dres == CH).all()) and torch.equal(dout.view(-1), src)
     print("  decode %.3f ms = %.1f GB/s (output bytes)" % (ms, n * CH / ms / 1e6))
+    dec.profile(True)
+    for _ in range(3):
+        dec.decode_device(dst, dsz, src_stride=enc.slot, dst=dout, dst_cap=CH, out_sizes=dres)
+    pm = dec.profile_read()
+    dec.profile(False)
+    print("  decode per step: " + "  ".join("%s %.3f" % (k.replace("b2c_zstd_", "").replace("_kernel", ""), v / 3) for k, v in pm.items()))
 if "--s2" in sys.argv and level == 1:
     from compress_b200 import s2 as s2mod
     c = s2mod.Codec()
