@@ -63,11 +63,12 @@ struct b2c_ctx {
     cudaEvent_t ev_out[2] = {nullptr, nullptr};   // D2H of slot s finished
     // decoder: per-warp literal scratch, host-path staging (grown on demand)
     uint8_t *d_dec_lit = nullptr; size_t dec_lit_cap = 0;
-    uint8_t *d_fd = nullptr; size_t fd_cap = 0;            // staged decoder: records | tables
+    uint8_t *d_fd = nullptr; size_t fd_cap = 0;            // staged decoder: records | FSE tables | Huffman tables
+    uint32_t *d_fd_const = nullptr;                          //   code maps + predefined tables
     uint8_t *d_fd_seq = nullptr; size_t fd_seq_cap = 0;    //   sequence records
     uint8_t *d_fd_lit = nullptr; size_t fd_lit_cap = 0;    //   decoded literals
     int dec_staged = 1;                                    // B2C_DEC=onewarp: one-warp decoder only (A/B measurements)
-    float dec_ms[5] = {0, 0, 0, 0, 0}; cudaEvent_t dec_ev[6] = {}; int dec_prof = 0;
+    float dec_ms[6] = {0, 0, 0, 0, 0, 0}; cudaEvent_t dec_ev[7] = {}; int dec_prof = 0;
     uint8_t *d_dec_in = nullptr, *d_dec_out = nullptr; size_t dec_in_cap = 0, dec_out_cap = 0;
     uint8_t *d_dec_meta = nullptr; size_t dec_meta_cap = 0;
     uint8_t *h_stg_in = nullptr, *h_stg_out = nullptr; size_t h_stg_in_cap = 0, h_stg_out_cap = 0;   // pinned staging of the pointer-table calls
@@ -204,9 +205,16 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(b2c_zstd_dec_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)DEC_SMEM_BYTES) == cudaSuccess;
-    for (int i = 0; i < 6; i++) ok = ok && cudaEventCreate(&ctx->dec_ev[i]) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_dec_lit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(FD_LIT_WARPS * FD_LIT_WARP_BYTES)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_dec_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)DEC_WARP_BYTES) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_fd_const, FD_CONST_ENTRIES * sizeof(uint32_t)) == cudaSuccess;
+    if (ok) {
+        b2c_zstd_dec_init_kernel<<<1, 32, DEC_WARP_BYTES>>>(ctx->d_fd_const);
+        ok = cudaDeviceSynchronize() == cudaSuccess;
+    }
+    for (int i = 0; i < 7; i++) ok = ok && cudaEventCreate(&ctx->dec_ev[i]) == cudaSuccess;
     {
         const char *de = getenv("B2C_DEC");
         ctx->dec_staged = (de && strcmp(de, "onewarp") == 0) ? 0 : 1;
@@ -248,7 +256,7 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFreeHost(ctx->h_stg_in); cudaFreeHost(ctx->h_stg_out);
-    cudaFree(ctx->d_fd); cudaFree(ctx->d_fd_seq); cudaFree(ctx->d_fd_lit);
+    cudaFree(ctx->d_fd); cudaFree(ctx->d_fd_const); cudaFree(ctx->d_fd_seq); cudaFree(ctx->d_fd_lit);
     cudaFree(ctx->d_dec_lit); cudaFree(ctx->d_dec_in); cudaFree(ctx->d_dec_out); cudaFree(ctx->d_dec_meta);
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_pool[0]); cudaFree(ctx->d_pool[1]);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
@@ -313,17 +321,17 @@ int b2c_profile_read(b2c_ctx *ctx, double *ms, uint32_t *ncalls) {
     return B2C_OK;
 }
 
-// Decode-side counterpart: ms[0..4] = summed durations of {scan, sequences, execute, xxh64, one-warp decoder} over the
+// Decode-side counterpart: ms[0..5] = summed durations of {scan, literals, sequences, execute, xxh64, one-warp decoder} over the
 // staged decode launches since b2c_decode_profile_enable(ctx, 1).  Enabled, every decode launch synchronises.
 int b2c_decode_profile_enable(b2c_ctx *ctx, int on) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     ctx->dec_prof = on != 0;
-    for (int i = 0; i < 5; i++) ctx->dec_ms[i] = 0.f;
+    for (int i = 0; i < 6; i++) ctx->dec_ms[i] = 0.f;
     return B2C_OK;
 }
 int b2c_decode_profile_read(b2c_ctx *ctx, double *ms) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
-    for (int i = 0; i < 5; i++) { ms[i] = (double)ctx->dec_ms[i]; ctx->dec_ms[i] = 0.f; }
+    for (int i = 0; i < 6; i++) { ms[i] = (double)ctx->dec_ms[i]; ctx->dec_ms[i] = 0.f; }
     return B2C_OK;
 }
 
@@ -800,35 +808,41 @@ static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st, uint64
     P.lit_scratch = ctx->d_dec_lit;
     const uint32_t n = P.nchunks;
     const bool prof = ctx->dec_prof != 0;
-    const bool staged = ctx->dec_staged && lit_span > 0 && lit_span <= kStagedSpanLimit && (uint64_t)n * sizeof(FdChunk) < (1ull << 31);
+    const bool staged = ctx->dec_staged && lit_span > 0 && lit_span <= kStagedSpanLimit && (uint64_t)n * FD_MAXB * FD_TAB_ENTRIES < (1ull << 31);
     if (staged) {
         const size_t recBytes = (((size_t)n * sizeof(FdChunk)) + 255) & ~(size_t)255;
-        const size_t tabBytes = (size_t)n * FD_MAXB * FD_TAB_ENTRIES * sizeof(uint2);
-        if ((rc = grow(ctx, &ctx->d_fd, &ctx->fd_cap, recBytes + tabBytes))) return rc;
+        const size_t tabBytes = (size_t)n * FD_MAXB * FD_TAB_ENTRIES * sizeof(uint32_t);
+        const size_t hufBytes = (size_t)n * FD_MAXB * 2048 * sizeof(uint16_t);
+        if ((rc = grow(ctx, &ctx->d_fd, &ctx->fd_cap, recBytes + tabBytes + hufBytes))) return rc;
         if ((rc = grow(ctx, &ctx->d_fd_seq, &ctx->fd_seq_cap, 8 * ((size_t)(lit_span / 3) + 2 * (size_t)n + 8)))) return rc;
         if ((rc = grow(ctx, &ctx->d_fd_lit, &ctx->fd_lit_cap, (size_t)lit_span + 64))) return rc;
         P.fd = reinterpret_cast<FdChunk *>(ctx->d_fd);
-        P.fd_tabs = reinterpret_cast<uint2 *>(ctx->d_fd + recBytes);
+        P.fd_tabs = reinterpret_cast<uint32_t *>(ctx->d_fd + recBytes);
+        P.fd_huf = reinterpret_cast<uint16_t *>(ctx->d_fd + recBytes + tabBytes);
+        P.fd_const = ctx->d_fd_const;
         P.fd_seqs = reinterpret_cast<uint64_t *>(ctx->d_fd_seq);
         P.fd_lits = ctx->d_fd_lit;
         P.fd_lit_stride = lit_stride;
+        const unsigned groups = (n + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
         if (prof) cudaEventRecord(ctx->dec_ev[0], st);
-        b2c_zstd_dec_scan_kernel<<<grid, FD_SCAN_WARPS * 32, DEC_SMEM_BYTES, st>>>(P);
+        b2c_zstd_dec_scan_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
         if (prof) cudaEventRecord(ctx->dec_ev[1], st);
-        b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+        b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, st>>>(P);
         if (prof) cudaEventRecord(ctx->dec_ev[2], st);
-        b2c_zstd_dec_exec_kernel<<<(n + FD_EXEC_WARPS - 1) / FD_EXEC_WARPS, FD_EXEC_WARPS * 32, 0, st>>>(P);
+        b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
         if (prof) cudaEventRecord(ctx->dec_ev[3], st);
-        b2c_zstd_dec_xxh_kernel<<<(unsigned)(((uint64_t)n * 4 + 127) / 128), 128, 0, st>>>(P);
+        b2c_zstd_dec_exec_kernel<<<(n + FD_EXEC_WARPS - 1) / FD_EXEC_WARPS, FD_EXEC_WARPS * 32, 0, st>>>(P);
         if (prof) cudaEventRecord(ctx->dec_ev[4], st);
-        ctx->launches += 4;
+        b2c_zstd_dec_xxh_kernel<<<(unsigned)(((uint64_t)n * 4 + 127) / 128), 128, 0, st>>>(P);
+        if (prof) cudaEventRecord(ctx->dec_ev[5], st);
+        ctx->launches += 5;
     }
     b2c_zstd_decode_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, st>>>(P);
     ctx->launches += 1;
     if (prof && staged) {
-        cudaEventRecord(ctx->dec_ev[5], st);
-        cudaEventSynchronize(ctx->dec_ev[5]);
-        for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->dec_ev[i], ctx->dec_ev[i + 1]); ctx->dec_ms[i] += ms; }
+        cudaEventRecord(ctx->dec_ev[6], st);
+        cudaEventSynchronize(ctx->dec_ev[6]);
+        for (int i = 0; i < 6; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->dec_ev[i], ctx->dec_ev[i + 1]); ctx->dec_ms[i] += ms; }
     }
     CK(cudaGetLastError());
     return B2C_OK;

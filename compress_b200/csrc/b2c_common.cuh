@@ -254,6 +254,23 @@ B2C_DEV uint64_t xxh64_quad(const uint8_t *src, uint64_t n, unsigned q /*0..3*/,
     return h;
 }
 
+// streaming (evict-first) 8-byte store: data another kernel reads once should not push reused lines out of L2
+B2C_DEV void st_stream64(uint64_t *p, uint64_t v) {
+#ifndef B2C_EMU
+    __stcs(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+#else
+    *p = v;
+#endif
+}
+// hint: bring the 128-byte line holding p into L1 (no-op under the emulator)
+B2C_DEV void prefetch_l1(const void *p) {
+#ifndef B2C_EMU
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 #ifndef B2C_EMU
 // ---- 1-D TMA bulk copy global -> shared with mbarrier completion (UBLKCP) ----
 B2C_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

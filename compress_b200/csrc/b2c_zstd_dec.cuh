@@ -64,7 +64,9 @@ struct ZstdDecParams {
     // staged path (b2c_zstd_dec_staged.cuh); fd == nullptr: every input goes through the one-warp decoder, else only the
     // inputs the staged stages marked
     struct FdChunk *fd;                                                        // [nchunks]
-    uint2 *fd_tabs;                                                            // [nchunks][FD_MAXB][FD_TAB_ENTRIES]
+    uint32_t *fd_tabs;                                                         // [nchunks][FD_MAXB][FD_TAB_ENTRIES] packed entries
+    uint16_t *fd_huf;                                                          // [nchunks][FD_MAXB][2048] Huffman decoding tables
+    const uint32_t *fd_const;                                                   // code maps + predefined tables (FD_CONST_*)
     uint64_t *fd_seqs;                                                         // sequence records, fd_seq_off(c)
     uint8_t *fd_lits;                                                          // decoded literals, fd_lit_off(c)
     uint64_t fd_lit_stride;                                                    // literal area of input c at c * stride (0: dst_offsets[c])
@@ -80,13 +82,14 @@ B2C_DEV bool dec_staged_done(const ZstdDecParams &P, uint32_t c);               
 struct BrB {
     const uint8_t *in; uint32_t len; uint32_t total; uint32_t fed;   // fed = bits moved into the window so far
     uint64_t bits; uint32_t avail;
-    // look-ahead queue: the 128 bits below the window, requested four refills early (an L2 round trip lasts several
-    // refills of a Huffman / sequence walk, so one word of look-ahead left the walk waiting on memory)
+    // look-ahead queue: the four aligned words below the window, requested four refills early (an L2 round trip lasts
+    // several refills of a Huffman / sequence walk).  The queue holds the words as loaded; the funnel shift that turns a
+    // word into stream bits happens when it is consumed, so nothing waits on a load at request time.
     uint32_t ahead, ahead1, ahead2, ahead3;
     int32_t fb;                                          // stream bytes below fb have not been requested yet
-    // word-aligned view of the stream for the fetches: in + fb keeps its alignment (fb moves by 4), so every fetch needs
-    // one new aligned word and a fixed funnel shift
-    const uint32_t *wp; uint32_t wsh, whi;               // wp = aligned word holding byte fb; whi = *wp
+    // word-aligned view of the stream: in + fb keeps its alignment (fb moves by 4), so every refill needs one new
+    // aligned word and a fixed funnel shift
+    const uint32_t *wp; uint32_t wsh, whi;               // wp = aligned word holding byte fb; whi = the word above `ahead`
     B2C_DEV uint32_t load32_slow(int32_t idx) const {    // bytes outside [0, len) read as zero
         uint32_t v = 0;
 #pragma unroll
@@ -96,16 +99,13 @@ struct BrB {
         }
         return v;
     }
-    // the 32 bits just below fb; moves the word view down by one word
+    // the aligned word below wp, bytes that lie before the start of the stream cleared; moves the word view down
     B2C_DEV uint32_t fetch_below() {
+        const int32_t sidx = fb - (int32_t)(wsh >> 3) - 4;    // stream index of that word's first byte
         uint32_t v;
-        if (fb >= 4) {
-            const uint32_t lo = wp[-1];
-            v = wsh ? __funnelshift_r(lo, whi, wsh) : lo;
-            whi = lo;
-        } else {
-            v = (fb > -4) ? load32_slow(fb - 4) : 0u;     // below the start of the stream: zeros
-        }
+        if (sidx >= 0) v = wp[-1];
+        else if (sidx <= -4) v = 0u;
+        else v = wp[-1] & (0xffffffffu << (8 * (uint32_t)(-sidx)));   // the word holding in[0]: safe to read
         wp -= 1; fb -= 4;
         return v;
     }
@@ -123,12 +123,17 @@ struct BrB {
         const uintptr_t a = reinterpret_cast<uintptr_t>(p) + (uintptr_t)(intptr_t)cbyte;   // may lie below p for tiny streams
         wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         wsh = (uint32_t)(a & 3) * 8;
-        whi = (cbyte >= 4) ? *wp : 0u;                   // only used by the fast path (fb >= 4)
+        // the word holding byte cbyte: only its bytes below cbyte are ever used, and only when they are stream bytes
+        whi = (cbyte >= 1 && wsh != 0) ? *wp : 0u;
+        if (cbyte >= 1 && wsh != 0 && (int32_t)(wsh >> 3) > cbyte) whi &= 0xffffffffu << (8 * ((wsh >> 3) - (uint32_t)cbyte));
         ahead = fetch_below(); ahead1 = fetch_below(); ahead2 = fetch_below(); ahead3 = fetch_below();
         return 0;
     }
     B2C_DEV void refill32() {     // requires avail <= 32
-        bits |= (uint64_t)ahead << (32 - avail);
+        const uint32_t lo = ahead;
+        const uint32_t v = wsh ? __funnelshift_r(lo, whi, wsh) : lo;
+        whi = lo;
+        bits |= (uint64_t)v << (32 - avail);
         avail += 32; fed += 32;
         ahead = ahead1; ahead1 = ahead2; ahead2 = ahead3;
         ahead3 = fetch_below();

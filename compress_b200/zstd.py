@@ -224,7 +224,7 @@ class Decoder:
     def launches(self):
         return int(lib.b2c_launch_count(self._ctx))
 
-    DECODE_KERNELS = ("b2c_zstd_dec_scan_kernel", "b2c_zstd_dec_seq_kernel", "b2c_zstd_dec_exec_kernel",
+    DECODE_KERNELS = ("b2c_zstd_dec_scan_kernel", "b2c_zstd_dec_lit_kernel", "b2c_zstd_dec_seq_kernel", "b2c_zstd_dec_exec_kernel",
                       "b2c_zstd_dec_xxh_kernel", "b2c_zstd_decode_kernel")
 
     def profile(self, on=True):
@@ -232,7 +232,7 @@ class Decoder:
 
     def profile_read(self):
         """-> {kernel name: summed ms} of the decode launches since profile(True)."""
-        ms = (ctypes.c_double * 5)()
+        ms = (ctypes.c_double * 6)()
         check(lib.b2c_decode_profile_read(self._ctx, ms), self._ctx)
         return {k: float(ms[i]) for i, k in enumerate(self.DECODE_KERNELS)}
 

@@ -84,7 +84,7 @@ B2C_API uint64_t b2c_launch_count(b2c_ctx *ctx);
  * since (a device-resident call larger than the work pool is several launches). */
 B2C_API int b2c_profile_enable(b2c_ctx *ctx, int on);
 B2C_API int b2c_profile_read(b2c_ctx *ctx, double *ms, uint32_t *ncalls);
-/* The same for zstd decode: ms[0..4] = {scan, sequences, execute, xxh64, one-warp decoder} summed over the decode
+/* The same for zstd decode: ms[0..5] = {scan, literals, sequences, execute, xxh64, one-warp decoder} summed over the decode
  * launches since b2c_decode_profile_enable(ctx, 1); while enabled every decode launch synchronises its stream. */
 B2C_API int b2c_decode_profile_enable(b2c_ctx *ctx, int on);
 B2C_API int b2c_decode_profile_read(b2c_ctx *ctx, double *ms);

@@ -103,20 +103,33 @@ int emu_zstd_decode_mode(const uint8_t *src, const uint64_t *src_off, const uint
     P.dst_base = dst; P.dst_offsets = dst_off; P.dst_caps = dst_caps;
     P.out_sizes = out_sizes; P.nchunks = n; P.lit_scratch = lit.data();
     std::vector<FdChunk> fd;
-    std::vector<uint2> tabs;
+    std::vector<uint32_t> tabs;
     std::vector<uint64_t> seqs;
     std::vector<uint8_t> lits;
+    std::vector<uint16_t> hufs;
     if (mode == 0 && n > 0) {
         const uint64_t span = dst_off[n - 1] + dst_caps[n - 1];
         fd.resize(n);
         memset(fd.data(), 0xCD, sizeof(FdChunk) * (size_t)n);
-        tabs.assign((size_t)n * FD_MAXB * FD_TAB_ENTRIES, make_uint2(0xCDCDCDCDu, 0xCDCDCDCDu));
+        tabs.assign((size_t)n * FD_MAXB * FD_TAB_ENTRIES, 0xCDCDCDCDu);
         seqs.assign((size_t)(span / 3) + 2 * (size_t)n + 8, 0xCDCDCDCDCDCDCDCDull);
         lits.assign((size_t)span + 64, 0xCD);
         P.fd = fd.data(); P.fd_tabs = tabs.data(); P.fd_seqs = seqs.data(); P.fd_lits = lits.data(); P.fd_lit_stride = 0;
-        emu::launch(grid, FD_SCAN_WARPS * 32, DEC_SMEM_BYTES, [&]() {
-            fd_scan_warp(emu::dyn_smem, P, blockIdx.x * FD_SCAN_WARPS + (threadIdx.x >> 5), gridDim.x * FD_SCAN_WARPS);
+        std::vector<uint32_t> fdc(FD_CONST_ENTRIES);
+        hufs.assign((size_t)n * FD_MAXB * 2048, 0xCDCD);
+        emu::launch(1, 32, DEC_WARP_BYTES, [&]() { fd_init_warp(emu::dyn_smem, fdc.data(), threadIdx.x); });
+        P.fd_huf = hufs.data(); P.fd_const = fdc.data();
+        emu::launch((n + 31) / 32, 32, 0, [&]() {
+            const uint32_t c = blockIdx.x * 32 + threadIdx.x;
+            if (c < P.nchunks) fd_scan_lane(P, c);
         });
+        {
+            const unsigned groups = (n + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
+            emu::launch((groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, [&]() {
+                const unsigned w = threadIdx.x >> 5;
+                fd_lit_warp(emu::dyn_smem + w * FD_LIT_WARP_BYTES, P, blockIdx.x * FD_LIT_WARPS + w, threadIdx.x & 31);
+            });
+        }
         emu::launch((n + 31) / 32, 32, 0, [&]() {
             const uint32_t c = blockIdx.x * 32 + threadIdx.x;
             if (c < P.nchunks) fd_seq_lane(P, c);
