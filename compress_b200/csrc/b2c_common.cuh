@@ -271,6 +271,45 @@ B2C_DEV void prefetch_l1(const void *p) {
 #endif
 }
 
+// read-only 32-bit load of data that is re-read all through a kernel while other data streams past it: an L2 cache
+// policy (createpolicy ... evict_last) keeps it resident.  pol = l2_keep_policy(), once per thread.
+B2C_DEV uint64_t l2_keep_policy() {
+#ifndef B2C_EMU
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+#else
+    return 0;
+#endif
+}
+B2C_DEV uint32_t ld_keep32(const uint32_t *p, uint64_t pol) {
+#ifndef B2C_EMU
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+#else
+    (void)pol;
+    return *p;
+#endif
+}
+// 32-bit load that is cached in L2 only: with most of the SM's memory configured as shared memory the few L1 lines
+// left cannot hold the lines of hundreds of independent streams, and allocating them serialises the misses
+B2C_DEV uint32_t ld_cg32(const uint32_t *p) {
+#ifndef B2C_EMU
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+// hint: bring the sector holding p into L2
+B2C_DEV void prefetch_l2(const void *p) {
+#ifndef B2C_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 #ifndef B2C_EMU
 // ---- 1-D TMA bulk copy global -> shared with mbarrier completion (UBLKCP) ----
 B2C_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -132,7 +132,7 @@ int emu_zstd_decode_mode(const uint8_t *src, const uint64_t *src_off, const uint
         }
         emu::launch((n + 31) / 32, 32, 0, [&]() {
             const uint32_t c = blockIdx.x * 32 + threadIdx.x;
-            if (c < P.nchunks) fd_seq_lane(P, c);
+            if (c < P.nchunks) fd_seq_lane(P, c, P.fd_const + FD_CONST_BASE, P.fd_const + FD_CONST_BASE + 128);
         });
         emu::launch((n + FD_EXEC_WARPS - 1) / FD_EXEC_WARPS, FD_EXEC_WARPS * 32, 0, [&]() {
             const uint32_t c = blockIdx.x * FD_EXEC_WARPS + (threadIdx.x >> 5);
