@@ -57,6 +57,8 @@ struct b2c_ctx {
     uint32_t *d_src_sizes2 = nullptr, *h_src_sizes2 = nullptr;
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream3 = nullptr;
+    cudaStream_t dec_aux = nullptr;                        // staged decode: the literal kernel runs beside the sequence walk
+    cudaEvent_t dec_fork = nullptr, dec_join = nullptr;
     uint8_t *h_in2 = nullptr, *h_out2 = nullptr;   // second pinned staging pair: pageable callers of b2c_zstd_encode_packed (lazy)
     cudaEvent_t ev[2] = {nullptr, nullptr};       // compute of the batch in slot s finished
     cudaEvent_t ev_in[2] = {nullptr, nullptr};    // H2D of slot s finished
@@ -215,6 +217,9 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
         ok = cudaDeviceSynchronize() == cudaSuccess;
     }
     for (int i = 0; i < 7; i++) ok = ok && cudaEventCreate(&ctx->dec_ev[i]) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->dec_aux, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->dec_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->dec_join, cudaEventDisableTiming) == cudaSuccess;
     {
         const char *de = getenv("B2C_DEC");
         ctx->dec_staged = (de && strcmp(de, "onewarp") == 0) ? 0 : 1;
@@ -270,6 +275,9 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
         if (ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
         if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
     }
+    if (ctx->dec_aux) cudaStreamDestroy(ctx->dec_aux);
+    if (ctx->dec_fork) cudaEventDestroy(ctx->dec_fork);
+    if (ctx->dec_join) cudaEventDestroy(ctx->dec_join);
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -806,6 +814,7 @@ static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st, uint64
     int rc = grow(ctx, &ctx->d_dec_lit, &ctx->dec_lit_cap, (size_t)maxGrid * DEC_WARPS * DEC_LIT_SCRATCH);
     if (rc) return rc;
     P.lit_scratch = ctx->d_dec_lit;
+    { int r = ctx_order_begin(ctx, st); if (r) return r; }    // the context's scratch is shared by all streams
     const uint32_t n = P.nchunks;
     const bool prof = ctx->dec_prof != 0;
     const bool staged = ctx->dec_staged && lit_span > 0 && lit_span <= kStagedSpanLimit && (uint64_t)n * FD_MAXB * FD_TAB_ENTRIES < (1ull << 31);
@@ -826,10 +835,21 @@ static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st, uint64
         const unsigned groups = (n + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
         if (prof) cudaEventRecord(ctx->dec_ev[0], st);
         b2c_zstd_dec_scan_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
-        if (prof) cudaEventRecord(ctx->dec_ev[1], st);
-        b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, st>>>(P);
-        if (prof) cudaEventRecord(ctx->dec_ev[2], st);
-        b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+        // the literal kernel and the sequence walk both depend on the scan only and both are bound by the latency of their
+        // serial walks, not by any unit: they run side by side (one after the other when per-kernel times are wanted)
+        if (prof) {
+            cudaEventRecord(ctx->dec_ev[1], st);
+            b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, st>>>(P);
+            cudaEventRecord(ctx->dec_ev[2], st);
+            b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+        } else {
+            CK(cudaEventRecord(ctx->dec_fork, st));
+            CK(cudaStreamWaitEvent(ctx->dec_aux, ctx->dec_fork, 0));
+            b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, ctx->dec_aux>>>(P);
+            CK(cudaEventRecord(ctx->dec_join, ctx->dec_aux));
+            b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+            CK(cudaStreamWaitEvent(st, ctx->dec_join, 0));
+        }
         if (prof) cudaEventRecord(ctx->dec_ev[3], st);
         b2c_zstd_dec_exec_kernel<<<(n + FD_EXEC_WARPS - 1) / FD_EXEC_WARPS, FD_EXEC_WARPS * 32, 0, st>>>(P);
         if (prof) cudaEventRecord(ctx->dec_ev[4], st);
@@ -845,7 +865,7 @@ static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st, uint64
         for (int i = 0; i < 6; i++) { float ms = 0; cudaEventElapsedTime(&ms, ctx->dec_ev[i], ctx->dec_ev[i + 1]); ctx->dec_ms[i] += ms; }
     }
     CK(cudaGetLastError());
-    return B2C_OK;
+    return ctx_order_end(ctx, st);
 }
 
 int b2c_zstd_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, const uint64_t *d_src_offsets,
