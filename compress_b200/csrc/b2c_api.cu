@@ -337,6 +337,22 @@ int b2c_decode_profile_enable(b2c_ctx *ctx, int on) {
     for (int i = 0; i < 6; i++) ctx->dec_ms[i] = 0.f;
     return B2C_OK;
 }
+// How many of the first nchunks inputs of the most recent decode launch were completed by the staged kernels (the others
+// went through the one-warp decoder).  Synchronises the device.  Test / diagnostics hook.
+int b2c_decode_staged_count(b2c_ctx *ctx, uint32_t nchunks, uint32_t *staged) {
+    if (!ctx || !staged) return B2C_ERR_ARG;
+    *staged = 0;
+    if (!ctx->d_fd || !ctx->dec_staged || nchunks == 0) return B2C_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    if ((size_t)nchunks * sizeof(FdChunk) > ctx->fd_cap) return B2C_ERR_ARG;
+    std::vector<uint32_t> st(nchunks);
+    CK(cudaMemcpy2D(st.data(), sizeof(uint32_t), ctx->d_fd, sizeof(FdChunk), sizeof(uint32_t), nchunks, cudaMemcpyDeviceToHost));
+    uint32_t k = 0;
+    for (uint32_t v : st) k += v == 0;
+    *staged = k;
+    return B2C_OK;
+}
 int b2c_decode_profile_read(b2c_ctx *ctx, double *ms) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     for (int i = 0; i < 6; i++) { ms[i] = (double)ctx->dec_ms[i]; ctx->dec_ms[i] = 0.f; }

@@ -236,6 +236,12 @@ class Decoder:
         check(lib.b2c_decode_profile_read(self._ctx, ms), self._ctx)
         return {k: float(ms[i]) for i, k in enumerate(self.DECODE_KERNELS)}
 
+    def staged_count(self, n):
+        """Of the first n inputs of the most recent decode launch: how many the staged kernels completed."""
+        k = ctypes.c_uint32(0)
+        check(lib.b2c_decode_staged_count(self._ctx, n, ctypes.byref(k)), self._ctx)
+        return int(k.value)
+
     def decode_device(self, src, src_sizes, src_offsets=None, src_stride=0, dst=None, dst_cap=CHUNK, dst_offsets=None,
                       out_sizes=None, dst_stride=None):
         """src: uint8 CUDA tensor; stream i is src[off_i : off_i + src_sizes[i]] with off_i = src_offsets[i]

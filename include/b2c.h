@@ -88,6 +88,9 @@ B2C_API int b2c_profile_read(b2c_ctx *ctx, double *ms, uint32_t *ncalls);
  * launches since b2c_decode_profile_enable(ctx, 1); while enabled every decode launch synchronises its stream. */
 B2C_API int b2c_decode_profile_enable(b2c_ctx *ctx, int on);
 B2C_API int b2c_decode_profile_read(b2c_ctx *ctx, double *ms);
+/* diagnostics: of the first nchunks inputs of the most recent decode launch, how many the staged kernels completed (the
+ * rest were decoded by the one-warp decoder).  Synchronises the device. */
+B2C_API int b2c_decode_staged_count(b2c_ctx *ctx, uint32_t nchunks, uint32_t *staged);
 
 /* Encoder.MaxEncodedSize for one chunk of n bytes (zstd/encoder.go:843-873) */
 B2C_API size_t b2c_zstd_bound(size_t n, int level);

@@ -1,4 +1,5 @@
-"""GPU parity tests for the zstd decoder (one warp per stream), through the C ABI (libb200comp.so).
+"""GPU parity tests for the zstd decoder (staged kernels + the one-warp decoder for what they mark), through the C ABI
+(libb200comp.so).
 Golden vectors are the reference's own (zstd/testdata/*.zip, committed under tests/golden/)."""
 import os
 import zipfile
@@ -104,6 +105,7 @@ def test_roundtrip_device_256mib(dec):
     torch.cuda.synchronize()
     assert bool((osz == 65536).all()), osz[osz != 65536][:10]
     assert torch.equal(out.view(-1), src)
+    assert dec.staged_count(n) == n                      # every one of these frames is the staged kernels' work
     # too small destination -> every stream reports an error, nothing is written past the capacity
     out2 = torch.full((n, 1024 + 64), 0x5A, dtype=torch.uint8, device="cuda")
     _, osz2 = dec.decode_device(frames, sizes.to(torch.int32), src_stride=frames.stride(0), dst=out2, dst_cap=1024,
@@ -111,7 +113,48 @@ def test_roundtrip_device_256mib(dec):
     torch.cuda.synchronize()
     assert bool((osz2 < 0).all())
     assert bool((out2[:, 1024:] == 0x5A).all())
+    assert dec.staged_count(n) == 0                      # ... and none of these: the one-warp decoder names the error
     e.close()
+
+
+def test_staged_and_onewarp_agree(dec, oracle_lib):
+    """Levels 2 and 3 (128 KiB blocks), damaged frames and frames the staged kernels do not take (two frames in one input,
+    more than four blocks): staged + one-warp results equal the one-warp decoder's alone (B2C_DEC=onewarp context)."""
+    import os
+    from compress_b200 import zstd
+    rng = np.random.default_rng(5)
+    base = H.synth_text(6 * 131072, seed=9)
+    comps, wants = [], []
+    for level in (zstd.SpeedDefault, zstd.SpeedBetterCompression):
+        e = zstd.Encoder(level=level, max_chunks=16)
+        for k in range(6):
+            c = base[k * 131072:(k + 1) * 131072 - 17 * k]
+            comps.append(e.EncodeAll(c)); wants.append(c)
+        e.close()
+    long_src = H.synth_text(700000, seed=3)
+    r, long_frame = H.oracle_encode(long_src, level=2)          # one frame, six blocks
+    comps.append(bytes(long_frame)); wants.append(long_src)
+    comps.append(comps[0] + comps[1]); wants.append(wants[0] + wants[1])
+    for k in range(12):                                          # damage
+        b = bytearray(comps[k])
+        pos = int(rng.integers(8, len(b)))
+        b[pos] ^= 1 << int(rng.integers(0, 8))
+        comps.append(bytes(b)); wants.append(None)
+    caps = [len(w) + 32 if w is not None else 131072 + 32 for w in wants]
+    outs, codes = dec.decode_chunks(comps, caps)
+    os.environ["B2C_DEC"] = "onewarp"
+    try:
+        d1 = zstd.Decoder()
+    finally:
+        del os.environ["B2C_DEC"]
+    outs1, codes1 = d1.decode_chunks(comps, caps)
+    d1.close()
+    assert list(codes) == list(codes1)
+    for w, o, o1, c in zip(wants, outs, outs1, codes):
+        if c >= 0:
+            assert o == o1
+        if w is not None:
+            assert c == len(w) and o == w
 
 
 def test_decode_all_splits_frames(dec, oracle_lib):
