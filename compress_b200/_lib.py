@@ -48,6 +48,15 @@ def _load():
     lib.b2c_zstd_encode_chunks.restype = c.c_int
     lib.b2c_zstd_encode_chunks.argtypes = [
         c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
+    lib.b2c_zstd_frame_bound.restype = c.c_size_t
+    lib.b2c_zstd_frame_bound.argtypes = [c.c_size_t, c.c_int]
+    lib.b2c_zstd_encode_frames_device.restype = c.c_int
+    lib.b2c_zstd_encode_frames_device.argtypes = [
+        c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p,
+        c.c_void_p, c.c_void_p]
+    lib.b2c_zstd_encode_frames.restype = c.c_int
+    lib.b2c_zstd_encode_frames.argtypes = [
+        c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
     lib.b2c_zstd_encode_packed.restype = c.c_int
     lib.b2c_zstd_encode_packed.argtypes = [
         c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_size_t, c.c_uint32, c.c_void_p, c.c_size_t, c.c_void_p,
@@ -129,6 +138,7 @@ EXPORTED_SYMBOLS = [
     "b2c_huf_compress_chunks", "b2c_huf_decompress_chunks", "b2c_huf_read_table",
     "b2c_queue_create", "b2c_queue_destroy", "b2c_queue_zstd_encode", "b2c_queue_zstd_decode", "b2c_queue_s2_encode",
     "b2c_queue_s2_decode", "b2c_queue_stats",
+    "b2c_zstd_frame_bound", "b2c_zstd_encode_frames_device", "b2c_zstd_encode_frames",
 ]
 
 

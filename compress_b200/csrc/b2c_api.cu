@@ -15,6 +15,7 @@
 #include "../../include/b2c.h"
 #include "b2c_zstd_enc.cuh"
 #include "b2c_lz.cuh"
+#include "b2c_frame.cuh"
 #include "b2c_zstd_dec.cuh"
 #include "b2c_zstd_dec_staged.cuh"
 #include "b2c_s2_dec.cuh"
@@ -58,6 +59,11 @@ struct b2c_ctx {
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream3 = nullptr;
     cudaStream_t dec_aux = nullptr;                        // staged decode: the literal kernel runs beside the sequence walk
+    cudaStream_t enc_aux[2] = {nullptr, nullptr};          // encode: XXH64 (registers only) runs beside the parse kernel
+    cudaEvent_t enc_fork[2] = {nullptr, nullptr}, enc_join[2] = {nullptr, nullptr};
+    uint8_t *d_fr = nullptr; size_t fr_cap = 0;            // frame mode: block / frame tables, block slots (grown on demand)
+    uint8_t *d_fr_io = nullptr; size_t fr_io_cap = 0;      // frame mode, host-buffer call: staged input | packed output | results
+    int enc_side = 1;                                      // B2C_ENC_SIDE=0: everything on the caller's stream (A/B measurements)
     cudaEvent_t dec_fork = nullptr, dec_join = nullptr;
     uint8_t *h_in2 = nullptr, *h_out2 = nullptr;   // second pinned staging pair: pageable callers of b2c_zstd_encode_packed (lazy)
     cudaEvent_t ev[2] = {nullptr, nullptr};       // compute of the batch in slot s finished
@@ -197,6 +203,16 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
     ok = ok && cudaFuncSetAttribute(b2c_zstd_pack128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)PackCfg<131072>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    // XXH64 runs beside the parse kernel: CTAs of two kernels share an SM only when both ask for the same shared-memory
+    // carveout, so the (shared-memory-free) XXH64 kernel asks for the parse kernel's
+    ok = ok && cudaFuncSetAttribute(b2c_zstd_xxh_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_parse1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_parse2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_lz_parse3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)CHAIN_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_huf_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -220,6 +236,15 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
     ok = ok && cudaStreamCreateWithFlags(&ctx->dec_aux, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->dec_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->dec_join, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 2; k++) {
+        ok = ok && cudaStreamCreateWithFlags(&ctx->enc_aux[k], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->enc_fork[k], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->enc_join[k], cudaEventDisableTiming) == cudaSuccess;
+    }
+    {
+        const char *es = getenv("B2C_ENC_SIDE");
+        ctx->enc_side = (es && strcmp(es, "0") == 0) ? 0 : 1;
+    }
     {
         const char *de = getenv("B2C_DEC");
         ctx->dec_staged = (de && strcmp(de, "onewarp") == 0) ? 0 : 1;
@@ -263,6 +288,7 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     cudaFreeHost(ctx->h_stg_in); cudaFreeHost(ctx->h_stg_out);
     cudaFree(ctx->d_fd); cudaFree(ctx->d_fd_const); cudaFree(ctx->d_fd_seq); cudaFree(ctx->d_fd_lit);
     cudaFree(ctx->d_dec_lit); cudaFree(ctx->d_dec_in); cudaFree(ctx->d_dec_out); cudaFree(ctx->d_dec_meta);
+    cudaFree(ctx->d_fr); cudaFree(ctx->d_fr_io);
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_pool[0]); cudaFree(ctx->d_pool[1]);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
     cudaFree(ctx->d_sizes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_src_sizes);
@@ -276,6 +302,11 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
         if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
     }
     if (ctx->dec_aux) cudaStreamDestroy(ctx->dec_aux);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->enc_aux[k]) cudaStreamDestroy(ctx->enc_aux[k]);
+        if (ctx->enc_fork[k]) cudaEventDestroy(ctx->enc_fork[k]);
+        if (ctx->enc_join[k]) cudaEventDestroy(ctx->enc_join[k]);
+    }
     if (ctx->dec_fork) cudaEventDestroy(ctx->dec_fork);
     if (ctx->dec_join) cudaEventDestroy(ctx->dec_join);
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
@@ -394,7 +425,7 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
                          const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
                          int64_t *d_out_sizes, uint32_t nchunks, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
                          uint8_t *dbg_lits, uint32_t dbg_cap, cudaStream_t st, unsigned long long *dbg_cycles = nullptr,
-                         int slot = 0) {
+                         int slot = 0, const EncBlockDesc *d_desc = nullptr) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     if (!level_ok(level)) return B2C_ERR_UNSUPPORTED;
     if (nchunks == 0) return B2C_OK;
@@ -426,7 +457,8 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
         const uint32_t m = (nchunks - c0 < sub) ? nchunks - c0 : sub;
         ZstdEncParams P;
         memset(&P, 0, sizeof(P));
-        P.src_base = (const uint8_t *)d_src + (size_t)c0 * src_stride; P.src_stride = src_stride;
+        P.src_base = d_desc ? (const uint8_t *)d_src : (const uint8_t *)d_src + (size_t)c0 * src_stride; P.src_stride = src_stride;
+        P.desc = d_desc ? d_desc + c0 : nullptr;
         P.src_sizes = d_sizes ? d_sizes + c0 : nullptr; P.src_size_all = size_all;
         P.dst_base = (uint8_t *)d_dst + (size_t)c0 * dst_stride; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
         P.out_sizes = d_out_sizes + c0; P.nchunks = m; P.flags = (uint32_t)flags;
@@ -451,8 +483,21 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
         }
 #define PEV(k) do { if (pe) cudaEventRecord(pe[k], st); } while (0)
         PEV(0);
+        // XXH64 needs registers only (32 x 128 threads, no shared memory) and is latency-bound: it runs on a side stream
+        // beside the parse kernel (whose two CTAs leave room for exactly that on an SM) and joins before the pack kernel.
+        // The per-kernel profile keeps everything on one stream.
+        const bool side = ctx->enc_side && !pe && !dbg_cycles;
+        bool joined = true;
         if ((flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC)) {
-            b2c_zstd_xxh_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(P);
+            if (side) {
+                CK(cudaEventRecord(ctx->enc_fork[slot], st));
+                CK(cudaStreamWaitEvent(ctx->enc_aux[slot], ctx->enc_fork[slot], 0));
+                b2c_zstd_xxh_kernel<<<(4 * m + 127) / 128, 128, 0, ctx->enc_aux[slot]>>>(P);
+                CK(cudaEventRecord(ctx->enc_join[slot], ctx->enc_aux[slot]));
+                joined = false;
+            } else {
+                b2c_zstd_xxh_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(P);
+            }
             ctx->launches += 1;
         }
         PEV(1);
@@ -478,6 +523,7 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
         PEV(4);
         b2c_zstd_chains_kernel<<<(m + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, st>>>(P);
         PEV(5);
+        if (!joined) CK(cudaStreamWaitEvent(st, ctx->enc_join[slot], 0));
         if (blockmax > 65536) b2c_zstd_pack128_kernel<<<m, PACK_NT, PackCfg<131072>::SMEM_BYTES, st>>>(P);
         else b2c_zstd_pack_kernel<<<m, PACK_NT, PACK_SMEM_BYTES, st>>>(P);
         PEV(6);
@@ -508,6 +554,159 @@ int b2c_zstd_encode_device_timed(b2c_ctx *ctx, int flags, const void *d_src, siz
                                  unsigned long long *d_cycles, void *stream) {
     return launch_encode(ctx, B2C_LEVEL_FASTEST, flags, d_src, src_stride, nullptr, size_all, d_dst, dst_stride,
                          d_out_sizes, nchunks, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream, d_cycles);
+}
+
+
+// ------------------------------------------------------------------------------------------------ frame mode
+// zstd.Encoder.EncodeAll of an input larger than one block (zstd/encoder.go:796-830): ONE frame per input -- header with
+// the content size, the blocks, the XXH64 of the whole content.  Every block is encoded by the same six-kernel pipeline
+// as an independent chunk, with two differences: the match finder sees the `hist` bytes before the block (previous
+// blocks of the same frame, already in memory), and the blocks are bare (no frame header / checksum of their own).
+// Blocks are entropy-coded independently (no repeat-mode tables between blocks, which would serialise a frame's
+// blocks; the reference's seqCoders.setPrev / compModeRepeat, zstd/seqenc.go:19-42, is a size optimisation only).
+// XXH64 of every frame's content: four lanes per frame (the digest is a serial chain over the whole input)
+__global__ void b2c_zstd_frame_xxh_kernel(const uint8_t *src, const FrameDesc *fr, uint64_t *xxh, uint32_t nframes) {
+    const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t f = gt >> 2;
+    const bool live = f < nframes && fr[f < nframes ? f : 0].crc;
+    const uint64_t h = xxh64_quad(src + (live ? fr[f].off : 0), live ? fr[f].size : 0, gt & 3, (threadIdx.x & 31) & ~3u);
+    if ((gt & 3) == 0 && live) xxh[f] = h;
+}
+// base[k + 1] = base[k] + bytes of sub-batch k (offsets[m] = total of the scan)
+__global__ void b2c_frame_base_kernel(uint64_t *base, uint32_t k, const uint64_t *offsets, uint32_t m) { base[k + 1] = base[k] + offsets[m]; }
+__global__ void b2c_frame_place_kernel(const uint8_t *slots, uint64_t slot_stride, const int64_t *sizes, const uint64_t *offsets,
+                                       const uint64_t *base, uint32_t k, const EncBlockDesc *desc, const FrameDesc *fr,
+                                       uint8_t *packed, uint64_t cap, uint64_t *pos, uint32_t c0, uint32_t m) {
+    for (uint32_t c = blockIdx.x; c < m; c += gridDim.x)
+        frame_place_block(slots, slot_stride, sizes, offsets, base[k], desc, fr, packed, cap, pos, c0, c, threadIdx.x, blockDim.x);
+}
+__global__ void b2c_frame_finish_kernel(const FrameDesc *fr, const uint64_t *pos, const int64_t *sizes_all, const uint64_t *xxh,
+                                        uint8_t *packed, uint64_t cap, uint64_t *out_offsets, int64_t *out_sizes, uint32_t nframes) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < nframes) frame_finish_one(fr, pos, sizes_all, xxh, packed, cap, out_offsets, out_sizes, f);
+}
+
+size_t b2c_zstd_frame_bound(size_t size, int level) {
+    if (!level_ok(level)) return 0;
+    const FrameGeom g = frame_geom(level);
+    const size_t blocks = size ? (size + g.block - 1) / g.block : 1;
+    return 14 + 4 + 3 * blocks + size;        // maxHeaderSize + checksum + one block header per block (raw blocks at worst)
+}
+
+// Device-resident frame mode.  Frame f = h_src_sizes[f] bytes at d_src + h_src_offsets[f] (host arrays: the block list is
+// planned on the host).  Frames are written back to back into d_dst (capacity dst_cap); d_dst_offsets[f] / d_out_sizes[f]
+// (device arrays) receive where frame f starts and its size (negative = error).  Asynchronous on `stream`.
+int b2c_zstd_encode_frames_device(b2c_ctx *ctx, int level, int flags, const void *d_src, const uint64_t *h_src_offsets,
+                                  const uint64_t *h_src_sizes, uint32_t nframes, void *d_dst, uint64_t dst_cap,
+                                  uint64_t *d_dst_offsets, int64_t *d_out_sizes, void *stream) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (!level_ok(level)) return B2C_ERR_UNSUPPORTED;
+    if (nframes == 0) return B2C_OK;
+    if (!h_src_offsets || !h_src_sizes || !d_dst_offsets || !d_out_sizes) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const FrameGeom g = frame_geom(level);
+    const bool crc = (flags & B2C_ZSTD_CRC) != 0;
+    // ---- plan: block list and frame table
+    std::vector<EncBlockDesc> blocks;
+    std::vector<FrameDesc> frames;
+    if (!frame_plan(level, crc, h_src_offsets, h_src_sizes, nframes, blocks, frames)) return B2C_ERR_ARG;
+    const uint32_t nblocks = (uint32_t)blocks.size();
+    const uint32_t subMax = level_block(level) > 65536 ? 4096u : 8192u;
+    const uint32_t sub = nblocks < subMax ? nblocks : subMax, nsub = (nblocks + sub - 1) / sub;
+    const size_t slotB = (size_t)g.block + 512;
+    // ---- device memory of the call: descriptors | frame table | per-block sizes, positions | scan offsets | bases | xxh | slots
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t oDesc = take(sizeof(EncBlockDesc) * nblocks), oFr = take(sizeof(FrameDesc) * nframes),
+                 oSizes = take(sizeof(int64_t) * nblocks), oPos = take(sizeof(uint64_t) * nblocks),
+                 oScan = take(sizeof(uint64_t) * ((size_t)sub + 1)), oBase = take(sizeof(uint64_t) * ((size_t)nsub + 1)),
+                 oXxh = take(sizeof(uint64_t) * nframes), oSlots = take(slotB * sub);
+    if (ctx->fr_cap < o) {
+        CK(cudaDeviceSynchronize());
+        if (ctx->d_fr) CK(cudaFree(ctx->d_fr));
+        ctx->d_fr = nullptr; ctx->fr_cap = 0;
+        CK(cudaMalloc(&ctx->d_fr, o));
+        ctx->fr_cap = o;
+    }
+    { int r = ctx_order_begin(ctx, st); if (r) return r; }   // (the frame buffers belong to the context like the work pool)
+    uint8_t *B = ctx->d_fr;
+    EncBlockDesc *d_desc = (EncBlockDesc *)(B + oDesc);
+    FrameDesc *d_frames = (FrameDesc *)(B + oFr);
+    int64_t *d_sizes = (int64_t *)(B + oSizes);
+    uint64_t *d_pos = (uint64_t *)(B + oPos), *d_scan = (uint64_t *)(B + oScan), *d_base = (uint64_t *)(B + oBase),
+             *d_xxh = (uint64_t *)(B + oXxh);
+    uint8_t *d_slots = B + oSlots;
+    // pageable host vectors: the copies complete before cudaMemcpyAsync returns (staged by the runtime)
+    CK(cudaMemcpyAsync(d_desc, blocks.data(), sizeof(EncBlockDesc) * nblocks, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_frames, frames.data(), sizeof(FrameDesc) * nframes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_base, 0, sizeof(uint64_t), st));
+    if (crc) {
+        b2c_zstd_frame_xxh_kernel<<<(4 * nframes + 127) / 128, 128, 0, st>>>((const uint8_t *)d_src, d_frames, d_xxh, nframes);
+        ctx->launches += 1;
+    }
+    for (uint32_t k = 0; k < nsub; k++) {
+        const uint32_t c0 = k * sub, m = (nblocks - c0 < sub) ? nblocks - c0 : sub;
+        int r = launch_encode(ctx, level, 0, d_src, 0, nullptr, 0, d_slots, slotB, d_sizes + c0, m, nullptr, nullptr, nullptr, 0,
+                              st, nullptr, 0, d_desc + c0);
+        if (r) return r;
+        b2c_scan_sizes_kernel<<<1, 1024, 0, st>>>(d_sizes + c0, d_scan, m);
+        b2c_frame_base_kernel<<<1, 1, 0, st>>>(d_base, k, d_scan, m);
+        b2c_frame_place_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, st>>>(d_slots, slotB, d_sizes + c0, d_scan, d_base, k, d_desc,
+                                                                              d_frames, (uint8_t *)d_dst, dst_cap, d_pos, c0, m);
+        ctx->launches += 3;
+    }
+    b2c_frame_finish_kernel<<<(nframes + 127) / 128, 128, 0, st>>>(d_frames, d_pos, d_sizes, d_xxh, (uint8_t *)d_dst, dst_cap,
+                                                                    d_dst_offsets, d_out_sizes, nframes);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return ctx_order_end(ctx, st);
+}
+
+// Host-buffer frame mode: what a cgo shim calls for EncodeAll(src) with len(src) > one block (any mix of sizes).
+// srcs[i] -> one frame in dsts[i] (capacity dst_caps[i] >= b2c_zstd_frame_bound); sizes_out[i] = frame bytes or a negative error.
+int b2c_zstd_encode_frames(b2c_ctx *ctx, int level, int flags, const void *const *srcs, const size_t *src_sizes,
+                           void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (!level_ok(level)) return B2C_ERR_UNSUPPORTED;
+    if (n == 0) return B2C_OK;
+    if (n > 0x7fffffffull) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::vector<uint64_t> offs(n), lens(n);
+    uint64_t tin = 0, tout = 0;
+    for (size_t i = 0; i < n; i++) {
+        offs[i] = tin; lens[i] = src_sizes[i];
+        tin += (src_sizes[i] + 15) & ~(uint64_t)15;          // frames start 16-byte aligned (bulk-copy staging of their blocks)
+        tout += b2c_zstd_frame_bound(src_sizes[i], level);
+    }
+    const size_t inB = tin + 64, outB = tout + 64, metaB = (sizeof(uint64_t) + sizeof(int64_t)) * n;
+    if (ctx->fr_io_cap < inB + outB + metaB + 512) {
+        CK(cudaDeviceSynchronize());
+        if (ctx->d_fr_io) CK(cudaFree(ctx->d_fr_io));
+        ctx->d_fr_io = nullptr; ctx->fr_io_cap = 0;
+        CK(cudaMalloc(&ctx->d_fr_io, inB + outB + metaB + 512));
+        ctx->fr_io_cap = inB + outB + metaB + 512;
+    }
+    uint8_t *d_in = ctx->d_fr_io, *d_out = d_in + ((inB + 255) & ~(size_t)255);
+    uint64_t *d_off = (uint64_t *)(d_out + ((outB + 255) & ~(size_t)255));
+    int64_t *d_sz = (int64_t *)(d_off + n);
+    for (size_t i = 0; i < n; i++)
+        if (src_sizes[i]) CK(cudaMemcpyAsync(d_in + offs[i], srcs[i], src_sizes[i], cudaMemcpyHostToDevice, st));
+    int r = b2c_zstd_encode_frames_device(ctx, level, flags, d_in, offs.data(), lens.data(), (uint32_t)n, d_out, outB, d_off, d_sz, st);
+    if (r) { cudaStreamSynchronize(st); return r; }
+    std::vector<uint64_t> ho(n);
+    std::vector<int64_t> hs(n);
+    CK(cudaMemcpyAsync(ho.data(), d_off, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hs.data(), d_sz, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; i++) {
+        if (hs[i] > 0 && (size_t)hs[i] > dst_caps[i]) hs[i] = B2C_ERR_DST_SMALL;
+        if (hs[i] > 0) CK(cudaMemcpyAsync(dsts[i], d_out + ho[i], (size_t)hs[i], cudaMemcpyDeviceToHost, st));
+        sizes_out[i] = hs[i];
+    }
+    CK(cudaStreamSynchronize(st));
+    return B2C_OK;
 }
 
 int b2c_zstd_encode_chunks(b2c_ctx *ctx, int level, int flags, const void *const *srcs, const size_t *src_sizes,

@@ -344,11 +344,17 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     const uint32_t mseq = ZSTD ? P.maxseq : 0xffffffffu;
     uint16_t *cd = reinterpret_cast<uint16_t *>(scratch);
 
-    const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
-    const uint32_t n = chunk_size(P, chunk);
+    // Frame mode: the block is parsed as the tail of a "virtual chunk" that starts `hist` bytes earlier (the end of the
+    // previous block(s) of the same frame, contiguous in memory).  The dense pass covers the whole virtual chunk, so the
+    // tables hold the history's positions when the block's own tiles are probed; the walk, the literals and the sequences
+    // cover only [hist, n).  This is fastBase.hist / addBlock (zstd/enc_base.go:57-199) without a table that survives
+    // between blocks: every block of a frame is parsed independently of the others.
+    const uint32_t hist = ZSTD ? chunk_hist(P, chunk) : 0u;
+    const uint8_t *gsrc = chunk_src(P, chunk) - hist;
+    const uint32_t n = chunk_size(P, chunk) + hist;
     if (n > C::BLOCK || (ZSTD && n > P.blockmax)) {
         if (tid == 0) {
-            if constexpr (ZSTD) { W->n = n; W->kind = 3; }   // reported as B2C_ERR_TOO_BIG by the pack kernel
+            if constexpr (ZSTD) { W->n = n - hist; W->kind = 3; }   // reported as B2C_ERR_TOO_BIG by the pack kernel
             else P.out_sizes[chunk] = -3;
         }
         return;
@@ -467,7 +473,7 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     bool capped = false;
     {
         const uint32_t pend = (tid < nlanes) ? (e < npos ? e : npos) : 0u;
-        uint32_t p = b, nextEmit = b;
+        uint32_t p = b > hist ? b : hist, nextEmit = p;            // (history is never walked, nor extended into backwards)
         while (p < pend) {
             // next set bit in [p, pend)
             uint32_t wi = p >> 5;
@@ -570,8 +576,8 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     // nearest earlier thread that kept something: gives the end of the previous sequence and its offset
     const uint32_t keyEx = group_scan_excl_max(kept ? tid + 1 : 0u, sh->ws, 0, NT, tid, &keyTotal);
     B2C_PHASE(10);
-    const uint32_t nlit = n - sumAll;
-    const uint32_t prevE0 = keyEx ? keptEndA[keyEx - 1] : 0u;          // end of the sequence before this thread's first
+    const uint32_t nlit = n - hist - sumAll;
+    const uint32_t prevE0 = keyEx ? keptEndA[keyEx - 1] : hist;        // end of the sequence before this thread's first
     const uint32_t pOff0 = keyEx ? lastOffA[keyEx - 1] : 0u;
 
     if constexpr (!ZSTD) {
@@ -696,7 +702,8 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
     // blockEnc.encode early decisions (blockenc.go:481-503): no sequences => literals-only (raw) block; then the
     // single-sequence RLE test; then `saved < 16` => raw
     uint32_t kind = 0;
-    const int saved = (int)n - (int)nlit - (int)(n >> 6);
+    const uint32_t nblk = n - hist;                                    // the block itself
+    const int saved = (int)nblk - (int)nlit - (int)(nblk >> 6);
     if (nseq == 0) kind = 1;
     else if (nseq != 1 && saved < 16) kind = 1;
     if (nseq > mseq) kind = 1;      // cannot happen (mseq >= BLOCK / 4); keeps the arrays safe
@@ -853,7 +860,7 @@ B2C_DEV void lz_parse_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chun
         }
     }
 #undef REC
-    if (tid == 0) { W->n = n; W->nseq = nseq; W->nlit = nlit; W->kind = kind; W->rleLen = sh->rleLen; }
+    if (tid == 0) { W->n = nblk; W->nseq = nseq; W->nlit = nlit; W->kind = kind; W->rleLen = sh->rleLen; }
     __syncthreads();
     B2C_PHASE(5);
     }   // zstd mode

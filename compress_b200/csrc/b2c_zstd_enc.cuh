@@ -70,7 +70,16 @@ struct alignas(16) ChunkWork {
     FseCTable tbl[3];                      // the table each chain uses (new, predefined copy, or RLE)
 };
 
+// Frame mode (b2c_zstd_encode_frames_*): chunk i is block `i` of the batch's block list -- `len` bytes at src_base + off,
+// preceded (in the same frame, contiguous in memory) by `hist` bytes the match finder may refer to (fastBase.hist /
+// addBlock, zstd/enc_base.go:57-199).  Bit 0 of flags: last block of its frame (blockHeader.setLast, blockenc.go:120).
+struct EncBlockDesc {
+    uint64_t off;
+    uint32_t len, hist, frame, flags;
+};
+
 struct ZstdEncParams {
+    const EncBlockDesc *desc;     // frame mode: block descriptors (then src_stride / src_sizes are unused); else nullptr
     const uint8_t *src_base;      // chunk i at src_base + i * src_stride
     uint64_t src_stride;
     const uint32_t *src_sizes;    // per-chunk sizes (<= 65536); nullptr => all chunks are src_size_all
@@ -110,7 +119,14 @@ struct ZstdEncParams {
     } while (0)
 #endif
 
-B2C_DEV uint32_t chunk_size(const ZstdEncParams &P, uint32_t c) { return P.src_sizes ? P.src_sizes[c] : P.src_size_all; }
+B2C_DEV uint32_t chunk_size(const ZstdEncParams &P, uint32_t c) {
+    return P.desc ? P.desc[c].len : (P.src_sizes ? P.src_sizes[c] : P.src_size_all);
+}
+B2C_DEV const uint8_t *chunk_src(const ZstdEncParams &P, uint32_t c) {
+    return P.desc ? P.src_base + P.desc[c].off : P.src_base + (uint64_t)c * P.src_stride;
+}
+B2C_DEV uint32_t chunk_hist(const ZstdEncParams &P, uint32_t c) { return P.desc ? P.desc[c].hist : 0u; }
+B2C_DEV uint32_t chunk_last(const ZstdEncParams &P, uint32_t c) { return P.desc ? (P.desc[c].flags & 1u) : 1u; }
 
 // ---- work pool layout (one slab per chunk) ----
 B2C_DEV uint32_t wk_off_lit() { return 0; }
@@ -468,9 +484,10 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
     uint8_t *stage = smem;
     PackShared *ps = reinterpret_cast<PackShared *>(smem + PackCfg<BLOCK>::SMEM_SH);
     ChunkWork *W = P.work + chunk;
-    const uint8_t *gsrc = P.src_base + (uint64_t)chunk * P.src_stride;
+    const uint8_t *gsrc = chunk_src(P, chunk);
     uint8_t *gdst = P.dst_base + (uint64_t)chunk * P.dst_stride;
     const uint32_t n = W->n;
+    const uint32_t lastBit = chunk_last(P, chunk);
     const bool frame = (P.flags & ENC_FLAG_FRAME) != 0;
     const bool crc = frame && (P.flags & ENC_FLAG_CRC) != 0;
     uint32_t kind = W->kind;
@@ -620,7 +637,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
             if (tid == 0) {
                 uint32_t o = 0;
                 if (frame) o = write_frame_header(stage, n, crc);
-                uint32_t bh = 1u | (2u << 1) | (blockBytes << 3);  // last block, compressed
+                uint32_t bh = lastBit | (2u << 1) | (blockBytes << 3);  // compressed block
                 stage[o++] = (uint8_t)bh; stage[o++] = (uint8_t)(bh >> 8); stage[o++] = (uint8_t)(bh >> 16);
                 // literals header (blockenc.go:153-238)
                 uint64_t lh;
@@ -679,7 +696,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
         if (tid == 0) {
             uint32_t o = 0;
             if (frame) o = write_frame_header(hdr, n, crc);
-            uint32_t bh = (kind == 2) ? (1u | (1u << 1) | (W->rleLen << 3)) : (1u | (0u << 1) | (n << 3));
+            uint32_t bh = (kind == 2) ? (lastBit | (1u << 1) | (W->rleLen << 3)) : (lastBit | (0u << 1) | (n << 3));
             hdr[o++] = (uint8_t)bh; hdr[o++] = (uint8_t)(bh >> 8); hdr[o++] = (uint8_t)(bh >> 16);
             ps->pos = o;
         }
@@ -705,7 +722,7 @@ B2C_DEV void zstd_pack_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
 // XXH64 of every chunk (xxh64_quad, b2c_common.cuh): four lanes per chunk hold the four accumulators.
 B2C_DEV void zstd_xxh_quad(const ZstdEncParams &P, uint32_t chunk, unsigned q /*0..3*/, unsigned quadBaseLane) {
     const bool live = chunk < P.nchunks;
-    const uint8_t *src = P.src_base + (uint64_t)(live ? chunk : 0) * P.src_stride;
+    const uint8_t *src = chunk_src(P, live ? chunk : 0);
     uint32_t n = live ? chunk_size(P, chunk) : 0;
     const bool ok = n <= P.blockmax;
     if (!ok) n = 0;

@@ -169,11 +169,62 @@ class Encoder:
         check(rc, self._ctx)
         return dst, int(total.value), sizes, offs
 
-    def EncodeAll(self, src, dst=None):
-        """EncodeAll will encode all input in src and append it to dst (zstd/encoder.go:715-729)."""
+    # ---- frame mode: one frame per input of any size (the multi-block branch of encodeAll, zstd/encoder.go:796-830) ----
+    def FrameBound(self, size):
+        return int(lib.b2c_zstd_frame_bound(size, self.level))
+
+    def encode_frames_device(self, src, offsets, sizes, dst=None):
+        """src: uint8 CUDA tensor; frame f = sizes[f] bytes at src[offsets[f]:] (host sequences of ints).  Every frame's
+        blocks see the bytes before them (history) and are encoded in parallel.  Returns (dst uint8 CUDA tensor,
+        frame_offsets uint64 CUDA tensor, frame_sizes int64 CUDA tensor): frame f is dst[off[f] : off[f] + size[f]].  Async."""
+        assert src.is_cuda and src.dtype == torch.uint8
+        n = len(sizes)
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        lens = np.ascontiguousarray(sizes, dtype=np.uint64)
+        if dst is None:
+            cap = sum(self.FrameBound(int(x)) for x in lens) + 64
+            dst = torch.empty(cap, dtype=torch.uint8, device=src.device)
+        foff = torch.empty(n, dtype=torch.uint64, device=src.device)
+        fsz = torch.empty(n, dtype=torch.int64, device=src.device)
+        stream = torch.cuda.current_stream(src.device).cuda_stream
+        rc = lib.b2c_zstd_encode_frames_device(self._ctx, self.level, self.flags & FLAG_CRC, src.data_ptr(), offs.ctypes.data,
+                                               lens.ctypes.data, n, dst.data_ptr(), dst.numel(), foff.data_ptr(),
+                                               fsz.data_ptr(), ctypes.c_void_p(stream))
+        check(rc, self._ctx)
+        return dst, foff, fsz
+
+    def encode_frames(self, inputs):
+        """inputs: list of bytes-like of any size.  Returns one zstd frame (bytes) per input: Encoder.EncodeAll applied to
+        each, all blocks of all inputs in one device batch."""
+        n = len(inputs)
+        if n == 0:
+            return []
+        bufs = [np.frombuffer(c, dtype=np.uint8) if len(c) else np.zeros(0, dtype=np.uint8) for c in inputs]
+        outs = [np.empty(self.FrameBound(len(c)) + 16, dtype=np.uint8) for c in inputs]
+        srcs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        ssz = (ctypes.c_size_t * n)(*[len(c) for c in inputs])
+        dsts = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+        dcap = (ctypes.c_size_t * n)(*[o.size for o in outs])
+        res = (ctypes.c_int64 * n)()
+        rc = lib.b2c_zstd_encode_frames(self._ctx, self.level, self.flags & FLAG_CRC, srcs, ssz, dsts, dcap, res, n)
+        check(rc, self._ctx)
+        out = []
+        for i in range(n):
+            if res[i] < 0:
+                raise B2CError(f"input {i}: {lib.b2c_strerror(int(res[i])).decode()}")
+            out.append(outs[i][: res[i]].tobytes())
+        return out
+
+    def EncodeAll(self, src, dst=None, single_frame=True):
+        """EncodeAll will encode all input in src and append it to dst (zstd/encoder.go:715-729).  As in the reference the
+        result is ONE frame (content size in the header, one checksum); single_frame=False gives round 1's stream of
+        independent one-block frames instead (a valid zstd stream of the same content, zstd/encoder.go:719)."""
         src = bytes(src)
-        buf, total, _, _ = self.encode_packed(src)
-        out = bytes(buf[:total].numpy())
+        if single_frame:
+            out = self.encode_frames([src])[0]
+        else:
+            buf, total, _, _ = self.encode_packed(src)
+            out = bytes(buf[:total].numpy())
         if dst is not None:
             dst += out
             return dst

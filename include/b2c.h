@@ -127,6 +127,26 @@ B2C_API int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const voi
                                    uint32_t chunk_size, void *h_dst, size_t dst_cap, int64_t *sizes_out,
                                    uint64_t *offsets_out, size_t *total_out);
 
+/*
+ * Frame mode: zstd.Encoder.EncodeAll for inputs of any size (zstd/encoder.go:722-840, the multi-block branch :796-830):
+ * ONE frame per input -- frame header with the content size (frameHeader.appendTo, zstd/frameenc.go:25-92), the blocks,
+ * the XXH64 of the whole content (B2C_ZSTD_CRC).  Blocks are 32 KiB at level 1 and 64 KiB at levels 2-3; the match
+ * finder of every block also sees the 32 / 64 KiB before it (the reference's history, fastBase.addBlock,
+ * zstd/enc_base.go:57-199), so match offsets reach back across blocks.  Blocks of a frame are encoded in parallel and
+ * entropy-coded independently (no repeat-mode tables).
+ * _device: frame f is h_src_sizes[f] bytes at d_src + h_src_offsets[f] (HOST arrays; 16-byte aligned offsets are
+ * fastest); frames are written back to back into d_dst; d_dst_offsets[f] / d_out_sizes[f] (DEVICE arrays) receive
+ * every frame's position and size (negative = error).  Asynchronous on `stream`.
+ * b2c_zstd_encode_frames: host pointers in and out, one frame per (srcs[i], dsts[i]); synchronous.
+ */
+B2C_API size_t b2c_zstd_frame_bound(size_t n, int level);
+B2C_API int b2c_zstd_encode_frames_device(b2c_ctx *ctx, int level, int flags, const void *d_src,
+                                          const uint64_t *h_src_offsets, const uint64_t *h_src_sizes, uint32_t nframes,
+                                          void *d_dst, uint64_t dst_cap, uint64_t *d_dst_offsets, int64_t *d_out_sizes,
+                                          void *stream);
+B2C_API int b2c_zstd_encode_frames(b2c_ctx *ctx, int level, int flags, const void *const *srcs, const size_t *src_sizes,
+                                   void *const *dsts, const size_t *dst_caps, int64_t *sizes_out, size_t n);
+
 /* Debug/parity hook used by tests: encode device-resident chunks and also dump, per chunk,
  * {nseq, nlit, kind, litMode}, the (litLen, matchLen-3, offset) triples and the literal bytes (rows of the level's
  * block size), so the entropy stage can be compared byte-for-byte with the oracle's blockEnc.encode. */

@@ -3,6 +3,7 @@
 #include "simt_emu.h"
 #include "../../compress_b200/csrc/b2c_zstd_enc.cuh"
 #include "../../compress_b200/csrc/b2c_lz.cuh"
+#include "../../compress_b200/csrc/b2c_frame.cuh"
 #include "../../compress_b200/csrc/b2c_zstd_dec.cuh"
 #include "../../compress_b200/csrc/b2c_zstd_dec_staged.cuh"
 #include "../../compress_b200/csrc/b2c_s2_dec.cuh"
@@ -81,6 +82,96 @@ int emu_zstd_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *size
     free(pool);
     return 0;
 }
+// Frame mode (b2c_zstd_encode_frames_device) with the device's kernels and launch order: frame f = sizes[f] bytes at
+// src + offs[f]; frames are written back to back into dst; out_offsets / out_sizes per frame.  Optional debug dumps per BLOCK
+// (rows of the level's virtual block size), n_blocks_out = number of blocks planned, blk_desc_out (optional, 4 u64 per
+// block: off, len, hist, flags).
+int emu_zstd_encode_frames(const uint8_t *src, const uint64_t *offs, const uint64_t *sizes, uint32_t nframes, uint8_t *dst,
+                           uint64_t dst_cap, uint64_t *out_offsets, int64_t *out_sizes, int crc, int level, uint32_t *dbg_hdr,
+                           uint32_t *dbg_seqs, uint8_t *dbg_lits, uint32_t dbg_seq_cap, uint32_t dbg_block_cap,
+                           uint32_t *n_blocks_out, uint64_t *blk_desc_out) {
+    std::vector<EncBlockDesc> blocks;
+    std::vector<FrameDesc> frames;
+    if (!frame_plan(level, crc != 0, offs, sizes, nframes, blocks, frames)) return -1;
+    const uint32_t nblocks = (uint32_t)blocks.size();
+    if (n_blocks_out) *n_blocks_out = nblocks;
+    if (blk_desc_out)
+        for (uint32_t i = 0; i < nblocks && i < dbg_block_cap; i++) {
+            blk_desc_out[4 * i] = blocks[i].off; blk_desc_out[4 * i + 1] = blocks[i].len;
+            blk_desc_out[4 * i + 2] = blocks[i].hist; blk_desc_out[4 * i + 3] = blocks[i].flags;
+        }
+    if (dbg_hdr && nblocks > dbg_block_cap) return -2;
+    const FrameGeom g = frame_geom(level);
+    const uint32_t blockmax = level >= 2 ? 131072u : 65536u;
+    const uint64_t slotB = (uint64_t)g.block + 512;
+    std::vector<uint8_t> slots((size_t)slotB * nblocks + 64, 0xCD);
+    std::vector<int64_t> bsizes(nblocks, 0);
+    std::vector<uint8_t> scratch(std::max<size_t>(16, std::max(LzLayout<1>::SCRATCH_BYTES, std::max(LzLayout<2>::SCRATCH_BYTES, LzLayout<5>::SCRATCH_BYTES))), 0xCD);
+    ChunkWork *work = (ChunkWork *)aligned_alloc(16, sizeof(ChunkWork) * (size_t)nblocks);
+    memset(work, 0xCD, sizeof(ChunkWork) * (size_t)nblocks);
+    const uint64_t pstride = wk_pool_stride(blockmax);
+    uint8_t *pool = (uint8_t *)aligned_alloc(16, pstride * (size_t)nblocks);
+    memset(pool, 0xCD, pstride * (size_t)nblocks);
+    ZstdEncParams P;
+    memset(&P, 0, sizeof(P));
+    P.desc = blocks.data(); P.src_base = src;
+    P.dst_base = slots.data(); P.dst_stride = slotB; P.dst_cap = (uint32_t)slotB;
+    P.out_sizes = bsizes.data(); P.nchunks = nblocks; P.flags = 0; P.scratch = scratch.data(); P.work = work;
+    P.pool = pool; P.pool_stride = pstride; P.maxseq = wk_maxseq(blockmax); P.blockmax = blockmax;
+    P.big = blockmax > 65536; P.level = (uint32_t)level;
+    P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_seq_cap;
+    std::vector<uint64_t> xxh(nframes, 0);
+    emu::launch((4 * nframes + 127) / 128, 128, 0, [&]() {
+        const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t f = gt >> 2;
+        const bool live = f < nframes && frames[f < nframes ? f : 0].crc;
+        const uint64_t h = xxh64_quad(src + (live ? frames[f].off : 0), live ? frames[f].size : 0, gt & 3, (threadIdx.x & 31) & ~3u);
+        if ((gt & 3) == 0 && live) xxh[f] = h;
+    });
+    if (level >= 3)
+        emu::launch(1, LzCfg<5>::NT, LzLayout<5>::SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<5, LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
+        });
+    else if (level >= 2)
+        emu::launch(1, LzCfg<2>::NT, LzLayout<2>::SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<2, LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
+        });
+    else
+        emu::launch(1, LzCfg<1>::NT, LzLayout<1>::SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < P.nchunks; c++) lz_parse_chunk<1, LZ_MODE_ZSTD>(emu::dyn_smem, P, c, P.scratch);
+        });
+    emu::launch(1, HIST_NT, HIST_SMEM_BYTES, [&]() {
+        for (uint32_t c = 0; c < P.nchunks; c++) zstd_hist_chunk(emu::dyn_smem, P, c);
+    });
+    static TablesShared ts;
+    emu::launch(1, TABLES_NT, 0, [&]() {
+        if (threadIdx.x < 3) seq_build_predef(&ts.sw, (int)threadIdx.x);
+        __syncthreads();
+        zstd_tables_loop(&ts, P, 0, 1);
+    });
+    emu::launch((nblocks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, [&]() {
+        zstd_chains_block(reinterpret_cast<uint32_t *>(emu::dyn_smem), P, blockIdx.x * 32);
+    });
+    if (blockmax > 65536)
+        emu::launch(nblocks, PACK_NT, PackCfg<131072>::SMEM_BYTES, [&]() { zstd_pack_chunk<131072>(emu::dyn_smem, P, blockIdx.x); });
+    else
+        emu::launch(nblocks, PACK_NT, PACK_SMEM_BYTES, [&]() { zstd_pack_chunk<65536>(emu::dyn_smem, P, blockIdx.x); });
+    // scan of the block sizes (b2c_scan_sizes_kernel), placement, completion
+    std::vector<uint64_t> scan(nblocks + 1, 0), pos(nblocks, 0);
+    for (uint32_t i = 0; i < nblocks; i++) scan[i + 1] = scan[i] + (bsizes[i] > 0 ? (uint64_t)bsizes[i] : 0);
+    emu::launch(nblocks, 256, 0, [&]() {
+        frame_place_block(slots.data(), slotB, bsizes.data(), scan.data(), 0, blocks.data(), frames.data(), dst, dst_cap,
+                          pos.data(), 0, blockIdx.x, threadIdx.x, blockDim.x);
+    });
+    emu::launch((nframes + 127) / 128, 128, 0, [&]() {
+        const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+        if (f < nframes) frame_finish_one(frames.data(), pos.data(), bsizes.data(), xxh.data(), dst, dst_cap, out_offsets, out_sizes, f);
+    });
+    free(work);
+    free(pool);
+    return 0;
+}
+
 int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
                     uint64_t dst_stride, int64_t *out_sizes, uint32_t flags, uint32_t *dbg_hdr, uint32_t *dbg_seqs,
                     uint8_t *dbg_lits, uint32_t dbg_seq_cap) {

@@ -140,3 +140,55 @@ def emu_huf_decompress(E, blocks, dst_sizes, four=True, desc=0):
     E.emu_huf_decompress(src.ctypes.data, stride, sizes.ctypes.data, n, dst.ctypes.data, dstride, ds.ctypes.data,
                          outs.ctypes.data, 1 if four else 0)
     return [(bytes(dst[i, :outs[i]]) if outs[i] >= 0 else None, int(outs[i])) for i in range(n)]
+
+
+def emu_encode_frames(E, inputs, level=1, crc=True, desc=0, dump=True):
+    """Frame mode under the emulator (b2c_zstd_encode_frames_device's launch sequence): one frame per input of any size.
+    Returns (frames, blocks): blocks = list of dicts per planned block (frame-relative order) with off / len / hist / last and,
+    when dump, the parse: nseq, nlit, kind, tri (n x 3), lits."""
+    import ctypes as c
+    E.emu_set_lane_order(desc)
+    E.emu_zstd_encode_frames.argtypes = [c.c_void_p] * 3 + [c.c_uint32, c.c_void_p, c.c_uint64, c.c_void_p, c.c_void_p, c.c_int,
+                                                            c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_uint32, c.c_uint32,
+                                                            c.c_void_p, c.c_void_p]
+    n = len(inputs)
+    offs = np.zeros(n, dtype=np.uint64)
+    sizes = np.array([len(x) for x in inputs], dtype=np.uint64)
+    tot = 0
+    for i, x in enumerate(inputs):
+        offs[i] = tot
+        tot += (len(x) + 15) & ~15
+    src = np.zeros(tot + 256, dtype=np.uint8)
+    for i, x in enumerate(inputs):
+        src[int(offs[i]):int(offs[i]) + len(x)] = np.frombuffer(x, dtype=np.uint8)
+    fblock = 32768 if level == 1 else 65536
+    vblock = 65536 if level == 1 else 131072
+    nblk_max = sum(max(1, (len(x) + fblock - 1) // fblock) for x in inputs)
+    cap = sum(len(x) + 3 * max(1, (len(x) + fblock - 1) // fblock) + 32 for x in inputs) + 64
+    dst = np.zeros(cap, dtype=np.uint8)
+    foff = np.zeros(n, dtype=np.uint64)
+    fsz = np.zeros(n, dtype=np.int64)
+    seq_cap = vblock // 4 + 64
+    hdr = np.zeros((nblk_max, 4), dtype=np.uint32)
+    seqs = np.zeros((nblk_max, seq_cap, 3), dtype=np.uint32) if dump else None
+    lits = np.zeros((nblk_max, vblock), dtype=np.uint8) if dump else None
+    nb = c.c_uint32(0)
+    bd = np.zeros((nblk_max, 4), dtype=np.uint64)
+    rc = E.emu_zstd_encode_frames(src.ctypes.data, offs.ctypes.data, sizes.ctypes.data, n, dst.ctypes.data, cap, foff.ctypes.data,
+                                  fsz.ctypes.data, 1 if crc else 0, level, hdr.ctypes.data if dump else None,
+                                  seqs.ctypes.data if dump else None, lits.ctypes.data if dump else None, seq_cap, nblk_max,
+                                  c.byref(nb), bd.ctypes.data)
+    assert rc == 0, rc
+    assert nb.value == nblk_max
+    frames = []
+    for i in range(n):
+        assert fsz[i] > 0, (i, fsz[i])
+        frames.append(bytes(dst[int(foff[i]):int(foff[i]) + int(fsz[i])]))
+    blocks = []
+    for b in range(nblk_max):
+        d = {"off": int(bd[b, 0]), "len": int(bd[b, 1]), "hist": int(bd[b, 2]), "last": int(bd[b, 3]) & 1}
+        if dump:
+            nseq, nlit, kind, _ = [int(v) for v in hdr[b]]
+            d.update(nseq=nseq, nlit=nlit, kind=kind, tri=seqs[b][:nseq].copy(), lits=bytes(lits[b][:nlit]) if kind == 0 else None)
+        blocks.append(d)
+    return frames, blocks, offs

@@ -85,3 +85,29 @@ if "--s2" in sys.argv and level == 1:
         torch.cuda.synchronize()
         ms = a0.elapsed_time(a1) / 3
         print("  %-10s %.3f ms = %.1f GB/s; ratio %.4f" % (name, ms, n * CH / ms / 1e6, float(ss.sum()) / (n * CH)))
+if "--frames" in sys.argv:
+    # frame mode: the same bytes as 1 MiB inputs, one frame each (blocks see their history)
+    fs = 1 << 20
+    nf = (n * CH) // fs
+    offs, lens = [i * fs for i in range(nf)], [fs] * nf
+    fdst = torch.empty(nf * (fs + 4096), dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        _, foff, fsz = enc.encode_frames_device(src, offs, lens, dst=fdst)
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(3):
+        _, foff, fsz = enc.encode_frames_device(src, offs, lens, dst=fdst)
+    f1.record()
+    torch.cuda.synchronize()
+    fms = f0.elapsed_time(f1) / 3
+    fz = fsz.cpu()
+    assert int(fz.min()) > 0
+    print("  frame mode (%d x 1 MiB frames) %.3f ms = %.1f GB/s; ratio %.4f" % (nf, fms, nf * fs / fms / 1e6, float(fz.sum()) / (nf * fs)))
+    enc.profile(True)
+    for _ in range(2):
+        enc.encode_frames_device(src, offs, lens, dst=fdst)
+    pm, pc = enc.profile_read()
+    enc.profile(False)
+    print("  frame mode per step: " + "  ".join("%s %.3f" % (k.replace("b2c_zstd_", "").replace("b2c_", "").replace("_kernel", ""), v / 2)
+                                                for k, v in pm.items()))
