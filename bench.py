@@ -275,6 +275,34 @@ def main():
         del dout
         dec.close()
 
+    if not args.no_secondary:
+        # ---- frame mode: the same bytes as 1 MiB inputs, ONE multi-block frame each (EncodeAll of a large
+        # input, zstd/encoder.go:796-830); blocks see the history before them
+        fs = 1 << 20
+        nf = in_bytes // fs
+        foffs, flens = [i * fs for i in range(nf)], [fs] * nf
+        fdst = torch.empty(nf * (fs + 4096), dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            _, foff, fsz = enc.encode_frames_device(src, foffs, flens, dst=fdst)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(3):
+            _, foff, fsz = enc.encode_frames_device(src, foffs, flens, dst=fdst)
+        f1.record()
+        torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1) / 3
+        fz, fo = fsz.cpu().numpy(), foff.cpu().numpy().astype(np.int64)
+        assert (fz > 0).all(), "frame mode error"
+        import helpers as _H
+        probe = bytes(fdst[int(fo[nf // 2]): int(fo[nf // 2]) + int(fz[nf // 2])].cpu().numpy())
+        assert _H.libzstd_decode(probe, fs) == bytes(src[(nf // 2) * fs:(nf // 2 + 1) * fs].cpu().numpy()), "frame mode decode mismatch"
+        side["frame_mode"] = {"value": nf * fs / (fms / 1e3) / 1e9, "unit": "GB/s (input, this rank)", "ms": fms, "frames": nf,
+                              "frame_bytes": fs, "ratio": float(fz.sum()) / (nf * fs),
+                              "note": "one multi-block frame per 1 MiB input (b2c_zstd_encode_frames_device); one frame checked "
+                                      "with libzstd"}
+        del fdst
+
     if not args.no_secondary and level == 1:
         # ---- BASELINE config 3: S2 / Snappy block encode + decode of the same chunks, device-resident
         from compress_b200 import s2 as s2mod

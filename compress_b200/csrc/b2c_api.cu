@@ -59,11 +59,10 @@ struct b2c_ctx {
     cudaStream_t stream2 = nullptr;
     cudaStream_t stream3 = nullptr;
     cudaStream_t dec_aux = nullptr;                        // staged decode: the literal kernel runs beside the sequence walk
-    cudaStream_t enc_aux[2] = {nullptr, nullptr};          // encode: XXH64 (registers only) runs beside the parse kernel
-    cudaEvent_t enc_fork[2] = {nullptr, nullptr}, enc_join[2] = {nullptr, nullptr};
     uint8_t *d_fr = nullptr; size_t fr_cap = 0;            // frame mode: block / frame tables, block slots (grown on demand)
     uint8_t *d_fr_io = nullptr; size_t fr_io_cap = 0;      // frame mode, host-buffer call: staged input | packed output | results
-    int enc_side = 1;                                      // B2C_ENC_SIDE=0: everything on the caller's stream (A/B measurements)
+    uint32_t *d_counters = nullptr; uint32_t counter_seq = 0;   // chunk counters of the persistent parse kernels (one per launch, rotating)
+    int enc_fused_xxh = 1;                                 // B2C_ENC_XXH=kernel: XXH64 as its own kernel (A/B measurements)
     cudaEvent_t dec_fork = nullptr, dec_join = nullptr;
     uint8_t *h_in2 = nullptr, *h_out2 = nullptr;   // second pinned staging pair: pageable callers of b2c_zstd_encode_packed (lazy)
     cudaEvent_t ev[2] = {nullptr, nullptr};       // compute of the batch in slot s finished
@@ -203,16 +202,6 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
     ok = ok && cudaFuncSetAttribute(b2c_zstd_pack128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)PackCfg<131072>::SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    // XXH64 runs beside the parse kernel: CTAs of two kernels share an SM only when both ask for the same shared-memory
-    // carveout, so the (shared-memory-free) XXH64 kernel asks for the parse kernel's
-    ok = ok && cudaFuncSetAttribute(b2c_zstd_xxh_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(b2c_lz_parse1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(b2c_lz_parse2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(b2c_lz_parse3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)CHAIN_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_huf_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -236,14 +225,10 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
     ok = ok && cudaStreamCreateWithFlags(&ctx->dec_aux, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->dec_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->dec_join, cudaEventDisableTiming) == cudaSuccess;
-    for (int k = 0; k < 2; k++) {
-        ok = ok && cudaStreamCreateWithFlags(&ctx->enc_aux[k], cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&ctx->enc_fork[k], cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&ctx->enc_join[k], cudaEventDisableTiming) == cudaSuccess;
-    }
+    ok = ok && cudaMalloc(&ctx->d_counters, 256 * sizeof(uint32_t)) == cudaSuccess;
     {
-        const char *es = getenv("B2C_ENC_SIDE");
-        ctx->enc_side = (es && strcmp(es, "0") == 0) ? 0 : 1;
+        const char *es = getenv("B2C_ENC_XXH");
+        ctx->enc_fused_xxh = (es && strcmp(es, "kernel") == 0) ? 0 : 1;
     }
     {
         const char *de = getenv("B2C_DEC");
@@ -288,7 +273,7 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     cudaFreeHost(ctx->h_stg_in); cudaFreeHost(ctx->h_stg_out);
     cudaFree(ctx->d_fd); cudaFree(ctx->d_fd_const); cudaFree(ctx->d_fd_seq); cudaFree(ctx->d_fd_lit);
     cudaFree(ctx->d_dec_lit); cudaFree(ctx->d_dec_in); cudaFree(ctx->d_dec_out); cudaFree(ctx->d_dec_meta);
-    cudaFree(ctx->d_fr); cudaFree(ctx->d_fr_io);
+    cudaFree(ctx->d_fr); cudaFree(ctx->d_fr_io); cudaFree(ctx->d_counters);
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_pool[0]); cudaFree(ctx->d_pool[1]);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
     cudaFree(ctx->d_sizes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_src_sizes);
@@ -302,11 +287,6 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
         if (ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
     }
     if (ctx->dec_aux) cudaStreamDestroy(ctx->dec_aux);
-    for (int k = 0; k < 2; k++) {
-        if (ctx->enc_aux[k]) cudaStreamDestroy(ctx->enc_aux[k]);
-        if (ctx->enc_fork[k]) cudaEventDestroy(ctx->enc_fork[k]);
-        if (ctx->enc_join[k]) cudaEventDestroy(ctx->enc_join[k]);
-    }
     if (ctx->dec_fork) cudaEventDestroy(ctx->dec_fork);
     if (ctx->dec_join) cudaEventDestroy(ctx->dec_join);
     if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
@@ -403,6 +383,14 @@ size_t b2c_zstd_bound(size_t size, int level) {
     return fh + 3 * blocks + size;
 }
 
+// a zeroed chunk counter for one launch of a persistent parse kernel (rotating: launches in flight never share one)
+static int next_counter(b2c_ctx *ctx, cudaStream_t st, uint32_t **out) {
+    uint32_t *c = ctx->d_counters + (ctx->counter_seq++ & 255u);
+    CK(cudaMemsetAsync(c, 0, sizeof(uint32_t), st));
+    *out = c;
+    return B2C_OK;
+}
+
 static uint32_t level_block(int level) { return level == B2C_LEVEL_FASTEST ? (1u << 16) : (128u << 10); }
 static bool level_ok(int level) { return level == B2C_LEVEL_FASTEST || level == B2C_LEVEL_DEFAULT || level == B2C_LEVEL_BETTER; }
 static size_t level_slot(int level) { return (size_t)level_block(level) + 512; }   // >= MaxEncodedSize(block), 16-byte multiple
@@ -483,23 +471,13 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
         }
 #define PEV(k) do { if (pe) cudaEventRecord(pe[k], st); } while (0)
         PEV(0);
-        // XXH64 needs registers only (32 x 128 threads, no shared memory) and is latency-bound: it runs on a side stream
-        // beside the parse kernel (whose two CTAs leave room for exactly that on an SM) and joins before the pack kernel.
-        // The per-kernel profile keeps everything on one stream.
-        const bool side = ctx->enc_side && !pe && !dbg_cycles;
-        bool joined = true;
-        if ((flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC)) {
-            if (side) {
-                CK(cudaEventRecord(ctx->enc_fork[slot], st));
-                CK(cudaStreamWaitEvent(ctx->enc_aux[slot], ctx->enc_fork[slot], 0));
-                b2c_zstd_xxh_kernel<<<(4 * m + 127) / 128, 128, 0, ctx->enc_aux[slot]>>>(P);
-                CK(cudaEventRecord(ctx->enc_join[slot], ctx->enc_aux[slot]));
-                joined = false;
-            } else {
-                b2c_zstd_xxh_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(P);
-            }
+        // XXH64 rides in the chains launch (four more warps per CTA); as its own kernel only for A/B measurements
+        const bool wantXxh = (flags & B2C_ZSTD_FRAME) && (flags & B2C_ZSTD_CRC);
+        if (wantXxh && !ctx->enc_fused_xxh) {
+            b2c_zstd_xxh_kernel<<<(4 * m + 127) / 128, 128, 0, st>>>(P);
             ctx->launches += 1;
         }
+        { int r = next_counter(ctx, st, &P.counter); if (r) return r; }
         PEV(1);
         {
             if (level == B2C_LEVEL_FASTEST) {
@@ -521,9 +499,8 @@ static int launch_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, 
         const unsigned g2 = sms * TABLES_CTAS_PER_SM < m ? sms * TABLES_CTAS_PER_SM : m;
         b2c_zstd_tables_kernel<<<g2, TABLES_NT, 0, st>>>(P);
         PEV(4);
-        b2c_zstd_chains_kernel<<<(m + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, st>>>(P);
+        b2c_zstd_chains_kernel<<<(m + 31) / 32, CHAIN_NT + ((wantXxh && ctx->enc_fused_xxh) ? CHAIN_XXH_NT : 0), CHAIN_SMEM_BYTES, st>>>(P);
         PEV(5);
-        if (!joined) CK(cudaStreamWaitEvent(st, ctx->enc_join[slot], 0));
         if (blockmax > 65536) b2c_zstd_pack128_kernel<<<m, PACK_NT, PackCfg<131072>::SMEM_BYTES, st>>>(P);
         else b2c_zstd_pack_kernel<<<m, PACK_NT, PACK_SMEM_BYTES, st>>>(P);
         PEV(6);
@@ -564,13 +541,15 @@ int b2c_zstd_encode_device_timed(b2c_ctx *ctx, int flags, const void *d_src, siz
 // blocks of the same frame, already in memory), and the blocks are bare (no frame header / checksum of their own).
 // Blocks are entropy-coded independently (no repeat-mode tables between blocks, which would serialise a frame's
 // blocks; the reference's seqCoders.setPrev / compModeRepeat, zstd/seqenc.go:19-42, is a size optimisation only).
-// XXH64 of every frame's content: four lanes per frame (the digest is a serial chain over the whole input)
-__global__ void b2c_zstd_frame_xxh_kernel(const uint8_t *src, const FrameDesc *fr, uint64_t *xxh, uint32_t nframes) {
-    const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t f = gt >> 2;
-    const bool live = f < nframes && fr[f < nframes ? f : 0].crc;
-    const uint64_t h = xxh64_quad(src + (live ? fr[f].off : 0), live ? fr[f].size : 0, gt & 3, (threadIdx.x & 31) & ~3u);
-    if ((gt & 3) == 0 && live) xxh[f] = h;
+// XXH64 of every frame's content: one warp per frame (xxh64_warp: the warp streams, four lanes hash)
+constexpr int FRAME_XXH_WARPS = 4;
+__global__ void __launch_bounds__(FRAME_XXH_WARPS * 32) b2c_zstd_frame_xxh_kernel(const uint8_t *src, const FrameDesc *fr, uint64_t *xxh, uint32_t nframes) {
+    __shared__ __align__(16) uint8_t stg[FRAME_XXH_WARPS][2 * XXH_TILE];
+    const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t f = blockIdx.x * FRAME_XXH_WARPS + w;
+    if (f >= nframes || !fr[f].crc) return;
+    const uint64_t h = xxh64_warp(src + fr[f].off, fr[f].size, stg[w], lane);
+    if (lane == 0) xxh[f] = h;
 }
 // base[k + 1] = base[k] + bytes of sub-batch k (offsets[m] = total of the scan)
 __global__ void b2c_frame_base_kernel(uint64_t *base, uint32_t k, const uint64_t *offsets, uint32_t m) { base[k + 1] = base[k] + offsets[m]; }
@@ -642,7 +621,8 @@ int b2c_zstd_encode_frames_device(b2c_ctx *ctx, int level, int flags, const void
     CK(cudaMemcpyAsync(d_frames, frames.data(), sizeof(FrameDesc) * nframes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_base, 0, sizeof(uint64_t), st));
     if (crc) {
-        b2c_zstd_frame_xxh_kernel<<<(4 * nframes + 127) / 128, 128, 0, st>>>((const uint8_t *)d_src, d_frames, d_xxh, nframes);
+        b2c_zstd_frame_xxh_kernel<<<(nframes + FRAME_XXH_WARPS - 1) / FRAME_XXH_WARPS, FRAME_XXH_WARPS * 32, 0, st>>>(
+            (const uint8_t *)d_src, d_frames, d_xxh, nframes);
         ctx->launches += 1;
     }
     for (uint32_t k = 0; k < nsub; k++) {
@@ -1280,6 +1260,7 @@ int b2c_s2_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
     P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.blockmax = ENC_MAX_CHUNK;
     P.scratch = ctx->d_scratch;
+    { int r = next_counter(ctx, st, &P.counter); if (r) return r; }
     const unsigned sms = (unsigned)ctx->sm_count;
     const bool snappy = (flags & B2C_S2_SNAPPY) != 0;
     if (level == B2C_S2_FAST) {
@@ -1546,7 +1527,25 @@ static void queue_run_batch(b2c_queue *q, std::vector<b2c_req *> &grp) {
     const b2c_req *r0 = grp[0];
     int rc;
     switch (r0->op) {
-    case 0: rc = b2c_zstd_encode_chunks(q->ctx, r0->level, r0->flags, srcs.data(), ssz.data(), dsts.data(), dcap.data(), res.data(), m); break;
+    case 0: {
+        // EncodeAll: inputs of at most one block are single-block frames (encode_chunks); larger ones go through frame mode
+        // (one multi-block frame each), both as one device batch
+        const size_t blk = level_ok(r0->level) ? level_block(r0->level) : 0;
+        std::vector<size_t> big, small;
+        for (size_t i = 0; i < m; i++) (ssz[i] > blk ? big : small).push_back(i);
+        rc = B2C_OK;
+        for (int pass = 0; pass < 2 && rc == B2C_OK; pass++) {
+            const std::vector<size_t> &ix = pass ? big : small;
+            if (ix.empty()) continue;
+            const size_t k = ix.size();
+            std::vector<const void *> s2(k); std::vector<void *> d2(k); std::vector<size_t> z2(k), c2(k); std::vector<int64_t> r2(k, 0);
+            for (size_t j = 0; j < k; j++) { s2[j] = srcs[ix[j]]; d2[j] = dsts[ix[j]]; z2[j] = ssz[ix[j]]; c2[j] = dcap[ix[j]]; }
+            rc = pass ? b2c_zstd_encode_frames(q->ctx, r0->level, r0->flags & B2C_ZSTD_CRC, s2.data(), z2.data(), d2.data(), c2.data(), r2.data(), k)
+                      : b2c_zstd_encode_chunks(q->ctx, r0->level, r0->flags, s2.data(), z2.data(), d2.data(), c2.data(), r2.data(), k);
+            for (size_t j = 0; j < k; j++) res[ix[j]] = r2[j];
+        }
+        break;
+    }
     case 1: rc = b2c_s2_encode_chunks(q->ctx, r0->level, r0->flags, srcs.data(), ssz.data(), dsts.data(), dcap.data(), res.data(), m); break;
     case 2: rc = b2c_zstd_decode_chunks(q->ctx, srcs.data(), ssz.data(), dsts.data(), dcap.data(), res.data(), m); break;
     default: rc = b2c_s2_decode_chunks(q->ctx, srcs.data(), ssz.data(), dsts.data(), dcap.data(), res.data(), m); break;

@@ -179,6 +179,48 @@ struct BitRun {
     }
 };
 
+// XXH64: merge of the four accumulators, the tail bytes and the avalanche (xxhash.go:101-160)
+B2C_DEV uint64_t xxh64_finish(uint64_t v1, uint64_t v2, uint64_t v3, uint64_t v4, const uint8_t *src, uint64_t n) {
+    const uint64_t P1 = 11400714785074694791ull, P2 = 14029467366897019727ull, P3 = 1609587929392839161ull,
+                   P4 = 9650029242287828579ull, P5 = 2870177450012600261ull;
+    uint64_t h;
+    uint64_t p = (n / 32) * 32;
+    if (n >= 32) {
+        h = ((v1 << 1) | (v1 >> 63)) + ((v2 << 7) | (v2 >> 57)) + ((v3 << 12) | (v3 >> 52)) + ((v4 << 18) | (v4 >> 46));
+#define XMERGE(vv)                                                                                     \
+    do {                                                                                               \
+        uint64_t t_ = (vv) * P2; t_ = (t_ << 31) | (t_ >> 33); t_ *= P1;                               \
+        h ^= t_; h = h * P1 + P4;                                                                      \
+    } while (0)
+        XMERGE(v1); XMERGE(v2); XMERGE(v3); XMERGE(v4);
+#undef XMERGE
+    } else {
+        h = P5;
+    }
+    h += n;
+    while (p + 8 <= n) {
+        uint64_t k1 = 0;
+        for (int b = 0; b < 8; b++) k1 |= (uint64_t)src[p + b] << (8 * b);
+        k1 *= P2; k1 = (k1 << 31) | (k1 >> 33); k1 *= P1;
+        h ^= k1; h = ((h << 27) | (h >> 37)) * P1 + P4;
+        p += 8;
+    }
+    if (p + 4 <= n) {
+        uint32_t k4 = 0;
+        for (int b = 0; b < 4; b++) k4 |= (uint32_t)src[p + b] << (8 * b);
+        h ^= (uint64_t)k4 * P1;
+        h = ((h << 23) | (h >> 41)) * P2 + P3;
+        p += 4;
+    }
+    while (p < n) {
+        h ^= (uint64_t)src[p] * P5;
+        h = ((h << 11) | (h >> 53)) * P1;
+        p++;
+    }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
+}
+
 // XXH64 (zstd/internal/xxhash/xxhash.go:62-160) of src[0, n): four adjacent lanes (q = 0..3, the first of them lane
 // quadBaseLane of the warp) hold the four accumulators; all four must call (with n = 0 when they have no input); the
 // digest is returned on q == 0.
@@ -216,42 +258,58 @@ B2C_DEV uint64_t xxh64_quad(const uint8_t *src, uint64_t n, unsigned q /*0..3*/,
     uint64_t v1 = __shfl_sync(FULLMASK, v, quadBaseLane), v2 = __shfl_sync(FULLMASK, v, quadBaseLane + 1),
              v3 = __shfl_sync(FULLMASK, v, quadBaseLane + 2), v4 = __shfl_sync(FULLMASK, v, quadBaseLane + 3);
     if (q != 0) return 0;
-    uint64_t h;
-    uint64_t p = stripes * 32;
-    if (n >= 32) {
-        h = ((v1 << 1) | (v1 >> 63)) + ((v2 << 7) | (v2 >> 57)) + ((v3 << 12) | (v3 >> 52)) + ((v4 << 18) | (v4 >> 46));
-#define XMERGE(vv)                                                                                     \
-    do {                                                                                               \
-        uint64_t t_ = (vv) * P2; t_ = (t_ << 31) | (t_ >> 33); t_ *= P1;                               \
-        h ^= t_; h = h * P1 + P4;                                                                      \
-    } while (0)
-        XMERGE(v1); XMERGE(v2); XMERGE(v3); XMERGE(v4);
-#undef XMERGE
-    } else {
-        h = P5;
+    return xxh64_finish(v1, v2, v3, v4, src, n);
+}
+
+// XXH64 of a long input by ONE WARP: all lanes stream the input (coalesced 16-byte loads, the next 2 KiB tile requested
+// while the current one is hashed) into a warp-private shared buffer, lanes 0-3 run the four accumulator chains over it.
+// The digest is a serial recurrence, so a lane-quad on its own waits out one memory round trip per handful of stripes;
+// here the loads of the whole warp are in flight instead.  stg: 2 x 2 KiB per warp, 16-byte aligned.  src 16-byte
+// aligned (else the quad form is used).  Result on lane 0.
+constexpr uint32_t XXH_TILE = 2048;
+B2C_DEV uint64_t xxh64_warp(const uint8_t *src, uint64_t n, uint8_t *stg, unsigned lane) {
+    const uint64_t P1 = 11400714785074694791ull, P2 = 14029467366897019727ull;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) != 0) return xxh64_quad(src, lane < 4 ? n : 0, lane & 3, lane & ~3u);
+    uint64_t v = (lane == 0) ? P1 + P2 : (lane == 1) ? P2 : (lane == 2) ? 0ull : (0ull - P1);
+    const uint64_t ntiles = n / XXH_TILE;
+    const uint4 *g = reinterpret_cast<const uint4 *>(src);
+    uint4 r[4];
+    if (ntiles) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] = B2C_LDG(g + k * 32 + lane);
     }
-    h += n;
-    while (p + 8 <= n) {
-        uint64_t k1 = 0;
-        for (int b = 0; b < 8; b++) k1 |= (uint64_t)src[p + b] << (8 * b);
-        k1 *= P2; k1 = (k1 << 31) | (k1 >> 33); k1 *= P1;
-        h ^= k1; h = ((h << 27) | (h >> 37)) * P1 + P4;
-        p += 8;
+    for (uint64_t t = 0; t < ntiles; t++) {
+        uint4 *sb = reinterpret_cast<uint4 *>(stg + (t & 1) * XXH_TILE);
+#pragma unroll
+        for (int k = 0; k < 4; k++) sb[k * 32 + lane] = r[k];
+        if (t + 1 < ntiles) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) r[k] = B2C_LDG(g + (t + 1) * (XXH_TILE / 16) + k * 32 + lane);
+        }
+        __syncwarp();
+        if (lane < 4) {
+            const uint64_t *s8 = reinterpret_cast<const uint64_t *>(sb) + lane;
+#pragma unroll 8
+            for (uint32_t i = 0; i < XXH_TILE / 32; i++) {
+                v += s8[4 * i] * P2;
+                v = (v << 31) | (v >> 33);
+                v *= P1;
+            }
+        }
+        __syncwarp();      // (the buffer written two tiles later is this one)
     }
-    if (p + 4 <= n) {
-        uint32_t k4 = 0;
-        for (int b = 0; b < 4; b++) k4 |= (uint32_t)src[p + b] << (8 * b);
-        h ^= (uint64_t)k4 * P1;
-        h = ((h << 23) | (h >> 41)) * P2 + P3;
-        p += 4;
-    }
-    while (p < n) {
-        h ^= (uint64_t)src[p] * P5;
-        h = ((h << 11) | (h >> 53)) * P1;
-        p++;
-    }
-    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
-    return h;
+    // the stripes behind the last whole tile: straight from memory
+    const uint64_t done = ntiles * XXH_TILE, stripes = n / 32;
+    if (lane < 4)
+        for (uint64_t i = done / 32; i < stripes; i++) {
+            v += reinterpret_cast<const uint64_t *>(src)[4 * i + lane] * P2;
+            v = (v << 31) | (v >> 33);
+            v *= P1;
+        }
+    const uint64_t v1 = __shfl_sync(FULLMASK, v, 0), v2 = __shfl_sync(FULLMASK, v, 1), v3 = __shfl_sync(FULLMASK, v, 2),
+                   v4 = __shfl_sync(FULLMASK, v, 3);
+    if (lane != 0) return 0;
+    return xxh64_finish(v1, v2, v3, v4, src, n);
 }
 
 // streaming (evict-first) 8-byte store: data another kernel reads once should not push reused lines out of L2

@@ -1000,33 +1000,35 @@ B2C_DEV void zstd_hist_chunk(uint8_t *smem, const ZstdEncParams &P, uint32_t chu
 }
 
 #ifndef B2C_EMU
-extern "C" __global__ void __launch_bounds__(LzCfg<1>::NT, LzCfg<1>::MIN_CTAS) b2c_lz_parse1_kernel(ZstdEncParams P) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<1>::SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<1, LZ_MODE_ZSTD>(smem, P, c, scratch);
+// The parse kernels are persistent (one CTA per resident slot); chunks are handed out through a global counter, so a CTA
+// that starts late (its SM was busy with another stream's kernel) or meets slow chunks simply takes fewer of them.  The
+// output of a chunk does not depend on the CTA that parses it (the per-CTA scratch holds nothing across chunks).
+template <int LV, int MODE> B2C_DEV void lz_parse_loop(uint8_t *smem, const ZstdEncParams &P) {
+    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<LV>::SCRATCH_BYTES;
+    ParseShared *sh = reinterpret_cast<ParseShared *>(smem + LzLayout<LV>::SM_SH);
+    for (;;) {
+        __syncthreads();                                     // the previous chunk's last reads of the shared record
+        if (threadIdx.x == 0) sh->nextChunk = atomicAdd(P.counter, 1u);
+        __syncthreads();
+        const uint32_t c = sh->nextChunk;
+        if (c >= P.nchunks) break;
+        lz_parse_chunk<LV, MODE>(smem, P, c, scratch);
+    }
 }
-extern "C" __global__ void __launch_bounds__(LzCfg<2>::NT, LzCfg<2>::MIN_CTAS) b2c_lz_parse2_kernel(ZstdEncParams P) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<2>::SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<2, LZ_MODE_ZSTD>(smem, P, c, scratch);
-}
-extern "C" __global__ void __launch_bounds__(LzCfg<5>::NT, LzCfg<5>::MIN_CTAS) b2c_lz_parse3_kernel(ZstdEncParams P) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<5>::SCRATCH_BYTES;
-    for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<5, LZ_MODE_ZSTD>(smem, P, c, scratch);
-}
-// S2 / Snappy block encoders: the same parse, tag-stream emission instead of the entropy stages (one kernel per block batch)
-#define B2C_LZ_S2_KERNEL(name, LV, MODE)                                                                                   \
+#define B2C_LZ_KERNEL(name, LV, MODE)                                                                                      \
     extern "C" __global__ void __launch_bounds__(LzCfg<LV>::NT, LzCfg<LV>::MIN_CTAS) name(ZstdEncParams P) {               \
         extern __shared__ __align__(1024) uint8_t smem[];                                                                  \
-        uint8_t *scratch = P.scratch + (uint64_t)blockIdx.x * LzLayout<LV>::SCRATCH_BYTES;                                 \
-        for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) lz_parse_chunk<LV, MODE>(smem, P, c, scratch);        \
+        lz_parse_loop<LV, MODE>(smem, P);                                                                                  \
     }
-B2C_LZ_S2_KERNEL(b2c_lz_s2_fast_kernel, 3, LZ_MODE_S2)
-B2C_LZ_S2_KERNEL(b2c_lz_snappy_fast_kernel, 3, LZ_MODE_SNAPPY)
-B2C_LZ_S2_KERNEL(b2c_lz_s2_better_kernel, 4, LZ_MODE_S2)
-B2C_LZ_S2_KERNEL(b2c_lz_snappy_better_kernel, 4, LZ_MODE_SNAPPY)
-#undef B2C_LZ_S2_KERNEL
+B2C_LZ_KERNEL(b2c_lz_parse1_kernel, 1, LZ_MODE_ZSTD)
+B2C_LZ_KERNEL(b2c_lz_parse2_kernel, 2, LZ_MODE_ZSTD)
+B2C_LZ_KERNEL(b2c_lz_parse3_kernel, 5, LZ_MODE_ZSTD)
+// S2 / Snappy block encoders: the same parse, tag-stream emission instead of the entropy stages (one kernel per block batch)
+B2C_LZ_KERNEL(b2c_lz_s2_fast_kernel, 3, LZ_MODE_S2)
+B2C_LZ_KERNEL(b2c_lz_snappy_fast_kernel, 3, LZ_MODE_SNAPPY)
+B2C_LZ_KERNEL(b2c_lz_s2_better_kernel, 4, LZ_MODE_S2)
+B2C_LZ_KERNEL(b2c_lz_snappy_better_kernel, 4, LZ_MODE_SNAPPY)
+#undef B2C_LZ_KERNEL
 extern "C" __global__ void __launch_bounds__(HIST_NT) b2c_zstd_hist_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     for (uint32_t c = blockIdx.x; c < P.nchunks; c += gridDim.x) zstd_hist_chunk(smem, P, c);

@@ -98,6 +98,7 @@ struct ZstdEncParams {
     uint32_t blockmax;            // largest block this launch accepts (65536 or 131072)
     uint32_t big;                 // 1: litLen / matchLen arrays are u32 (blocks > 64 KiB), 0: u16
     uint32_t level;               // 1 fastest, 2 default
+    uint32_t *counter;            // persistent parse kernels: next chunk to hand out (zeroed before the launch)
     uint32_t chunk0;              // sub-batch offset: kernels work on chunks [chunk0, chunk0 + nchunks) of the call
     // optional debug dump (tests): per chunk {nseq, nlit, kind, litMode} + seq triples + literals
     uint32_t *dbg_hdr;            // [nchunks][4]
@@ -203,7 +204,7 @@ B2C_DEV uint32_t warp_match_len(const uint8_t *src, uint32_t a, uint32_t b, uint
 
 struct ParseShared {
     uint32_t ws[40];        // block scan scratch
-    uint32_t nseq, nlit, kind, rleLen;
+    uint32_t nextChunk, pad0, kind, rleLen;   // nextChunk: the chunk this CTA takes next (dynamic schedule of the persistent kernels)
     uint64_t mbar;
 };
 // ------------------------------------------------------------------------------------------------ K1
@@ -331,6 +332,7 @@ B2C_DEV void zstd_tables_loop(TablesShared *ts, const ZstdEncParams &P, uint32_t
 // Per-lane tables live in shared memory, interleaved so that lane l only ever touches bank l:
 // 128 words of packed u16 next-states + 64 words of (deltaNbBits | (deltaFindState + 512) << 21).
 constexpr int CHAIN_NT = 96;
+constexpr int CHAIN_XXH_NT = 128;   // optional extra warps of a chains CTA: XXH64 of its 32 chunks, four lanes per chunk
 constexpr uint32_t CHAIN_SMEM_WORDS_PER_LANE = 64 + 56;   // 256 x u8 next-state offsets + 56 x u32 symbol transforms
 constexpr uint32_t CHAIN_SMEM_BYTES = CHAIN_NT * CHAIN_SMEM_WORDS_PER_LANE * 4;
 // K3: one lane per (chunk, table) walks the tANS state chain from the last sequence to the first
@@ -737,9 +739,17 @@ extern "C" __global__ void __launch_bounds__(TABLES_NT, TABLES_MIN_CTAS) b2c_zst
     __syncthreads();
     zstd_tables_loop(&ts, P, blockIdx.x, gridDim.x);
 }
-extern "C" __global__ void __launch_bounds__(CHAIN_NT) b2c_zstd_chains_kernel(ZstdEncParams P) {
+// K3 + K5 in one launch: the three chain warps of a CTA walk the tANS chains of 32 chunks; when the launch has
+// CHAIN_NT + CHAIN_XXH_NT threads, four more warps compute the XXH64 of the same 32 chunks (four lanes per chunk).  Both
+// are latency-bound serial recurrences that need few registers, so they hide behind each other (as its own kernel XXH64
+// cost 0.44 ms per GiB; a side stream beside the parse kernel did not overlap with it on the device).
+extern "C" __global__ void __launch_bounds__(CHAIN_NT + CHAIN_XXH_NT) b2c_zstd_chains_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    zstd_chains_block(reinterpret_cast<uint32_t *>(smem), P, blockIdx.x * 32);
+    if (threadIdx.x < CHAIN_NT) zstd_chains_block(reinterpret_cast<uint32_t *>(smem), P, blockIdx.x * 32);
+    else {
+        const unsigned t = threadIdx.x - CHAIN_NT;
+        zstd_xxh_quad(P, blockIdx.x * 32 + (t >> 2), t & 3, (t & 31) & ~3u);
+    }
 }
 extern "C" __global__ void __launch_bounds__(PACK_NT, PACK_MIN_CTAS) b2c_zstd_pack_kernel(ZstdEncParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];

@@ -383,9 +383,11 @@ class Queue:
         return out.raw[:r]
 
     def EncodeAll(self, src, level=SpeedFastest, crc=True):
-        """One block (at most the level's block size) -> one frame; blocks until the batch it joined has run."""
+        """EncodeAll for any input size -> one frame (single-block, or multi-block through frame mode); blocks until the
+        batch it joined has run."""
         flags = (FLAG_CRC if crc else 0) | FLAG_FRAME
-        return self._call(lib.b2c_queue_zstd_encode, (level, flags), src, int(lib.b2c_zstd_bound(len(src), level)) + 16)
+        cap = max(int(lib.b2c_zstd_bound(len(src), level)), int(lib.b2c_zstd_frame_bound(len(src), level))) + 16
+        return self._call(lib.b2c_queue_zstd_encode, (level, flags), src, cap)
 
     def DecodeAll(self, src, max_size=1 << 20):
         return self._call(lib.b2c_queue_zstd_decode, (), src, max_size)

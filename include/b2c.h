@@ -130,8 +130,8 @@ B2C_API int b2c_zstd_encode_packed(b2c_ctx *ctx, int level, int flags, const voi
 /*
  * Frame mode: zstd.Encoder.EncodeAll for inputs of any size (zstd/encoder.go:722-840, the multi-block branch :796-830):
  * ONE frame per input -- frame header with the content size (frameHeader.appendTo, zstd/frameenc.go:25-92), the blocks,
- * the XXH64 of the whole content (B2C_ZSTD_CRC).  Blocks are 32 KiB at level 1 and 64 KiB at levels 2-3; the match
- * finder of every block also sees the 32 / 64 KiB before it (the reference's history, fastBase.addBlock,
+ * the XXH64 of the whole content (B2C_ZSTD_CRC).  Blocks are 48 KiB at level 1 and 96 KiB at levels 2-3; the match
+ * finder of every block also sees the 16 / 32 KiB before it (the reference's history, fastBase.addBlock,
  * zstd/enc_base.go:57-199), so match offsets reach back across blocks.  Blocks of a frame are encoded in parallel and
  * entropy-coded independently (no repeat-mode tables).
  * _device: frame f is h_src_sizes[f] bytes at d_src + h_src_offsets[f] (HOST arrays; 16-byte aligned offsets are
@@ -235,7 +235,8 @@ B2C_API int b2c_huf_read_table(b2c_ctx *ctx, const void *const *srcs, const size
  * function it replaces; a dispatcher thread owned by the queue gathers the calls that are pending (waiting up to
  * linger_us for more, at most max_batch per dispatch), issues one batched device call per kind of request and returns
  * each caller its byte count or negative error.  Thread-safe; src/dst are ordinary host memory, valid for the call.
- * Inputs larger than the level's block size are refused with B2C_ERR_TOO_BIG (use b2c_zstd_encode_packed for those).
+ * b2c_queue_zstd_encode is EncodeAll for any input size: inputs of at most one block become single-block frames, larger
+ * ones one multi-block frame each (frame mode); S2 blocks larger than 64 KiB are refused with B2C_ERR_TOO_BIG.
  */
 typedef struct b2c_queue b2c_queue;
 B2C_API b2c_queue *b2c_queue_create(int device, size_t max_batch, unsigned linger_us);

@@ -39,11 +39,6 @@ int emu_zstd_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *size
     P.pool = pool; P.pool_stride = pstride; P.maxseq = wk_maxseq(blockmax); P.blockmax = blockmax;
     P.big = blockmax > 65536; P.level = (uint32_t)level;
     P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_seq_cap;
-    // K5 xxh64
-    emu::launch((4 * nchunks + 127) / 128, 128, 0, [&]() {
-        unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
-        zstd_xxh_quad(P, gt >> 2, gt & 3, (threadIdx.x & 31) & ~3u);
-    });
     // K1 parse
     {
         if (level >= 3)
@@ -69,9 +64,13 @@ int emu_zstd_encode_lv(const uint8_t *src, uint64_t stride, const uint32_t *size
         __syncthreads();
         zstd_tables_loop(&ts, P, 0, 1);
     });
-    // K3 chains
-    emu::launch((nchunks + 31) / 32, CHAIN_NT, CHAIN_SMEM_BYTES, [&]() {
-        zstd_chains_block(reinterpret_cast<uint32_t *>(emu::dyn_smem), P, blockIdx.x * 32);
+    // K3 chains + K5 xxh64 (four more warps per CTA)
+    emu::launch((nchunks + 31) / 32, CHAIN_NT + CHAIN_XXH_NT, CHAIN_SMEM_BYTES, [&]() {
+        if (threadIdx.x < CHAIN_NT) zstd_chains_block(reinterpret_cast<uint32_t *>(emu::dyn_smem), P, blockIdx.x * 32);
+        else {
+            const unsigned t = threadIdx.x - CHAIN_NT;
+            zstd_xxh_quad(P, blockIdx.x * 32 + (t >> 2), t & 3, (t & 31) & ~3u);
+        }
     });
     // K4 pack
     if (blockmax > 65536)
@@ -121,12 +120,12 @@ int emu_zstd_encode_frames(const uint8_t *src, const uint64_t *offs, const uint6
     P.big = blockmax > 65536; P.level = (uint32_t)level;
     P.dbg_hdr = dbg_hdr; P.dbg_seqs = dbg_seqs; P.dbg_lits = dbg_lits; P.dbg_seq_cap = dbg_seq_cap;
     std::vector<uint64_t> xxh(nframes, 0);
-    emu::launch((4 * nframes + 127) / 128, 128, 0, [&]() {
-        const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
-        const uint32_t f = gt >> 2;
-        const bool live = f < nframes && frames[f < nframes ? f : 0].crc;
-        const uint64_t h = xxh64_quad(src + (live ? frames[f].off : 0), live ? frames[f].size : 0, gt & 3, (threadIdx.x & 31) & ~3u);
-        if ((gt & 3) == 0 && live) xxh[f] = h;
+    emu::launch((nframes + 3) / 4, 128, 4 * 2 * XXH_TILE, [&]() {
+        const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const uint32_t f = blockIdx.x * 4 + w;
+        if (f >= nframes || !frames[f].crc) return;
+        const uint64_t h = xxh64_warp(src + frames[f].off, frames[f].size, emu::dyn_smem + w * 2 * XXH_TILE, lane);
+        if (lane == 0) xxh[f] = h;
     });
     if (level >= 3)
         emu::launch(1, LzCfg<5>::NT, LzLayout<5>::SMEM_BYTES, [&]() {

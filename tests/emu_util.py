@@ -142,7 +142,7 @@ def emu_huf_decompress(E, blocks, dst_sizes, four=True, desc=0):
     return [(bytes(dst[i, :outs[i]]) if outs[i] >= 0 else None, int(outs[i])) for i in range(n)]
 
 
-def emu_encode_frames(E, inputs, level=1, crc=True, desc=0, dump=True):
+def emu_encode_frames(E, inputs, level=1, crc=True, desc=0, dump=True, misalign=0):
     """Frame mode under the emulator (b2c_zstd_encode_frames_device's launch sequence): one frame per input of any size.
     Returns (frames, blocks): blocks = list of dicts per planned block (frame-relative order) with off / len / hist / last and,
     when dump, the parse: nseq, nlit, kind, tri (n x 3), lits."""
@@ -154,14 +154,14 @@ def emu_encode_frames(E, inputs, level=1, crc=True, desc=0, dump=True):
     n = len(inputs)
     offs = np.zeros(n, dtype=np.uint64)
     sizes = np.array([len(x) for x in inputs], dtype=np.uint64)
-    tot = 0
+    tot = misalign          # (frames normally start 16-byte aligned; misalign shifts all of them)
     for i, x in enumerate(inputs):
         offs[i] = tot
         tot += (len(x) + 15) & ~15
     src = np.zeros(tot + 256, dtype=np.uint8)
     for i, x in enumerate(inputs):
         src[int(offs[i]):int(offs[i]) + len(x)] = np.frombuffer(x, dtype=np.uint8)
-    fblock = 32768 if level == 1 else 65536
+    fblock = 49152 if level == 1 else 98304
     vblock = 65536 if level == 1 else 131072
     nblk_max = sum(max(1, (len(x) + fblock - 1) // fblock) for x in inputs)
     cap = sum(len(x) + 3 * max(1, (len(x) + fblock - 1) // fblock) + 32 for x in inputs) + 64

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 def test_frames_equal_emulator_and_decode(level):
     from compress_b200 import zstd
     tw = H.golden("twain.txt")
-    fblock = 32768 if level == 1 else 65536
+    fblock = 49152 if level == 1 else 98304
     inputs = [b"", b"a", tw[:200], tw[:1025], tw[:fblock], tw[:fblock + 1], tw[:3 * fblock + 777], bytes(2 * fblock + 5),
               b"abcd" * (fblock // 2), H.golden("html.txt"), H.golden("e.txt")[:70000], tw]
     enc = zstd.Encoder(level=level, max_chunks=64)

@@ -72,10 +72,11 @@ def test_queue_16_concurrent_callers():
                 assert n == len(blk) and dec == blk
                 if back is not None:
                     assert back == blk
-    # a block larger than the level's block size is refused, as documented
-    with pytest.raises(zstd.ZstdError) as ei:
-        q.EncodeAll(bytes(65537))
-    assert ei.value.code == -3
+    # an input larger than the level's block size becomes one multi-block frame (frame mode), as EncodeAll's does
+    big = tw[:200000]
+    f = q.EncodeAll(big)
+    assert f == enc.encode_frames([big])[0] and H.libzstd_decode(f, len(big)) == big
+    assert q.DecodeAll(f, max_size=len(big) + 64) == big
     q.close(); enc.close(); enc2.close()
 
 
