@@ -111,3 +111,22 @@ if "--frames" in sys.argv:
     enc.profile(False)
     print("  frame mode per step: " + "  ".join("%s %.3f" % (k.replace("b2c_zstd_", "").replace("b2c_", "").replace("_kernel", ""), v / 2)
                                                 for k, v in pm.items()))
+if "--frames-decode" in sys.argv:
+    # GPU decode of the multi-block frames (one-warp decoder: more than four blocks per frame)
+    dec = zstd.Decoder()
+    fo = foff.to(torch.int64)
+    fsz32 = fsz.to(torch.int32)
+    dout = torch.empty((nf, fs), dtype=torch.uint8, device=dev)
+    dres = torch.empty((nf,), dtype=torch.int64, device=dev)
+    for _ in range(2):
+        dec.decode_device(fdst, fsz32, src_offsets=foff, dst=dout, dst_cap=fs, out_sizes=dres)
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(2):
+        dec.decode_device(fdst, fsz32, src_offsets=foff, dst=dout, dst_cap=fs, out_sizes=dres)
+    g1.record()
+    torch.cuda.synchronize()
+    gms = g0.elapsed_time(g1) / 2
+    assert bool((dres == fs).all()) and torch.equal(dout.view(-1), src[: nf * fs])
+    print("  decode of the %d multi-block frames %.3f ms = %.1f GB/s (output bytes)" % (nf, gms, nf * fs / gms / 1e6))
