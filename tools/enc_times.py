@@ -13,6 +13,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import helpers as H
 from compress_b200 import zstd
 
+# --stream: run everything on a torch side stream instead of the (legacy) default stream
+if "--stream" in sys.argv:
+    _side = torch.cuda.Stream()
+    torch.cuda.set_stream(_side)
 level = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 gib = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 steps = 5
