@@ -48,6 +48,16 @@ def _load():
     lib.b2c_zstd_encode_chunks.restype = c.c_int
     lib.b2c_zstd_encode_chunks.argtypes = [
         c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
+    lib.b2c_s2_stream_bound.restype = c.c_size_t
+    lib.b2c_s2_stream_bound.argtypes = [c.c_size_t, c.c_size_t]
+    lib.b2c_s2_encode_stream_device.restype = c.c_int
+    lib.b2c_s2_encode_stream_device.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_uint64, c.c_uint32, c.c_void_p,
+                                                c.c_uint64, c.c_void_p, c.c_void_p, c.c_void_p]
+    lib.b2c_s2_encode_stream.restype = c.c_int
+    lib.b2c_s2_encode_stream.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_size_t, c.c_uint32, c.c_void_p, c.c_size_t,
+                                         c.c_void_p]
+    lib.b2c_s2_decode_stream.restype = c.c_int
+    lib.b2c_s2_decode_stream.argtypes = [c.c_void_p, c.c_void_p, c.c_size_t, c.c_void_p, c.c_size_t, c.c_void_p]
     lib.b2c_zstd_frame_bound.restype = c.c_size_t
     lib.b2c_zstd_frame_bound.argtypes = [c.c_size_t, c.c_int]
     lib.b2c_zstd_encode_frames_device.restype = c.c_int
@@ -139,6 +149,7 @@ EXPORTED_SYMBOLS = [
     "b2c_queue_create", "b2c_queue_destroy", "b2c_queue_zstd_encode", "b2c_queue_zstd_decode", "b2c_queue_s2_encode",
     "b2c_queue_s2_decode", "b2c_queue_stats",
     "b2c_zstd_frame_bound", "b2c_zstd_encode_frames_device", "b2c_zstd_encode_frames",
+    "b2c_s2_stream_bound", "b2c_s2_encode_stream_device", "b2c_s2_encode_stream", "b2c_s2_decode_stream",
 ]
 
 

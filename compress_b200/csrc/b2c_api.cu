@@ -19,6 +19,7 @@
 #include "b2c_zstd_dec.cuh"
 #include "b2c_zstd_dec_staged.cuh"
 #include "b2c_s2_dec.cuh"
+#include "b2c_s2_stream.cuh"
 #include "b2c_huf0.cuh"
 
 #ifndef TABLES_CTAS_PER_SM
@@ -61,6 +62,8 @@ struct b2c_ctx {
     cudaStream_t dec_aux = nullptr;                        // staged decode: the literal kernel runs beside the sequence walk
     uint8_t *d_fr = nullptr; size_t fr_cap = 0;            // frame mode: block / frame tables, block slots (grown on demand)
     uint8_t *d_fr_io = nullptr; size_t fr_io_cap = 0;      // frame mode, host-buffer call: staged input | packed output | results
+    uint8_t *d_s2s = nullptr; size_t s2s_cap = 0;          // S2 stream calls: block slots, sizes, checksums, scan, tables (grown on demand)
+    uint8_t *d_s2s_io = nullptr; size_t s2s_io_cap = 0;    //   host-buffer calls: staged input | output
     uint32_t *d_counters = nullptr; uint32_t counter_seq = 0;   // chunk counters of the persistent parse kernels (one per launch, rotating)
     int enc_fused_xxh = 1;                                 // B2C_ENC_XXH=kernel: XXH64 as its own kernel (A/B measurements)
     cudaEvent_t dec_fork = nullptr, dec_join = nullptr;
@@ -273,7 +276,7 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     cudaFreeHost(ctx->h_stg_in); cudaFreeHost(ctx->h_stg_out);
     cudaFree(ctx->d_fd); cudaFree(ctx->d_fd_const); cudaFree(ctx->d_fd_seq); cudaFree(ctx->d_fd_lit);
     cudaFree(ctx->d_dec_lit); cudaFree(ctx->d_dec_in); cudaFree(ctx->d_dec_out); cudaFree(ctx->d_dec_meta);
-    cudaFree(ctx->d_fr); cudaFree(ctx->d_fr_io); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_fr); cudaFree(ctx->d_fr_io); cudaFree(ctx->d_counters); cudaFree(ctx->d_s2s); cudaFree(ctx->d_s2s_io);
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_pool[0]); cudaFree(ctx->d_pool[1]);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
     cudaFree(ctx->d_sizes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_src_sizes);
@@ -564,6 +567,8 @@ __global__ void b2c_frame_finish_kernel(const FrameDesc *fr, const uint64_t *pos
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f < nframes) frame_finish_one(fr, pos, sizes_all, xxh, packed, cap, out_offsets, out_sizes, f);
 }
+
+__global__ void b2c_s2_stream_total_kernel(const uint64_t *base, uint32_t nsub, uint64_t *total) { *total = 10 + base[nsub]; }
 
 size_t b2c_zstd_frame_bound(size_t size, int level) {
     if (!level_ok(level)) return 0;
@@ -1244,19 +1249,19 @@ size_t b2c_s2_bound(size_t n) {
     return r > 0xffffffffull ? 0 : r;
 }
 
-int b2c_s2_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
-                         const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
-                         int64_t *d_out_sizes, uint32_t nchunks, void *stream) {
+static int launch_s2_encode(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
+                            const uint32_t *d_sizes, uint32_t size_all, uint64_t src_total, void *d_dst, size_t dst_stride,
+                            int64_t *d_out_sizes, uint32_t nchunks, cudaStream_t st) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     if (level != B2C_S2_FAST && level != B2C_S2_BETTER) return B2C_ERR_UNSUPPORTED;
     if (nchunks == 0) return B2C_OK;
     if (dst_stride > 0xffffffffull) return B2C_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
     { int r = ctx_order_begin(ctx, st); if (r) return r; }
     ZstdEncParams P;
     memset(&P, 0, sizeof(P));
     P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_sizes = d_sizes; P.src_size_all = size_all;
+    P.src_total = src_total;
     P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_cap = (uint32_t)dst_stride;
     P.out_sizes = d_out_sizes; P.nchunks = nchunks; P.blockmax = ENC_MAX_CHUNK;
     P.scratch = ctx->d_scratch;
@@ -1275,6 +1280,221 @@ int b2c_s2_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, 
     ctx->launches += 1;
     CK(cudaGetLastError());
     return ctx_order_end(ctx, st);
+}
+
+int b2c_s2_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, size_t src_stride,
+                         const uint32_t *d_sizes, uint32_t size_all, void *d_dst, size_t dst_stride,
+                         int64_t *d_out_sizes, uint32_t nchunks, void *stream) {
+    return launch_s2_encode(ctx, level, flags, d_src, src_stride, d_sizes, size_all, 0, d_dst, dst_stride, d_out_sizes, nchunks,
+                            (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ S2 / Snappy streams
+// s2.Writer.EncodeBuffer / s2.Reader for whole buffers (s2/writer.go:357-470, s2/reader.go:249-420): the framing format
+// around the block codecs -- stream identifier, one chunk per block with the masked CRC32-C of its uncompressed bytes.
+size_t b2c_s2_stream_bound(size_t n, size_t block) {
+    if (block == 0 || block > 65536) return 0;
+    const size_t nb = (n + block - 1) / block;
+    return 10 + nb * 8 + nb * (b2c_s2_bound(block) - block) + n;
+}
+
+// Device-resident: d_src[0, n) -> a complete stream in d_dst; *d_total (device, 8 bytes) = its length; *d_err (device, 4
+// bytes) = 0 or a negative error (B2C_ERR_DST_SMALL).  block <= 65536.  Asynchronous on `stream`.
+int b2c_s2_encode_stream_device(b2c_ctx *ctx, int level, int flags, const void *d_src, uint64_t n, uint32_t block, void *d_dst,
+                                uint64_t dst_cap, uint64_t *d_total, int32_t *d_err, void *stream) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (level != B2C_S2_FAST && level != B2C_S2_BETTER) return B2C_ERR_UNSUPPORTED;
+    if (block == 0 || block > 65536 || !d_total || !d_err) return B2C_ERR_ARG;
+    if (n / block >= 0x7fffffffull || dst_cap < 10) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t nblocks = (uint32_t)((n + block - 1) / block);
+    const uint32_t sub = nblocks < 4096 ? (nblocks ? nblocks : 1) : 4096u, nsub = (nblocks + sub - 1) / sub;
+    const size_t slotB = (b2c_s2_bound(block) + 15) & ~(size_t)15;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t oSlots = take(slotB * sub), oEnc = take(sizeof(int64_t) * sub), oPiece = take(sizeof(int64_t) * sub),
+                 oCrc = take(sizeof(uint32_t) * sub), oScan = take(sizeof(uint64_t) * ((size_t)sub + 1)),
+                 oBase = take(sizeof(uint64_t) * ((size_t)nsub + 1));
+    if (ctx->s2s_cap < o) {
+        CK(cudaDeviceSynchronize());
+        if (ctx->d_s2s) CK(cudaFree(ctx->d_s2s));
+        ctx->d_s2s = nullptr; ctx->s2s_cap = 0;
+        CK(cudaMalloc(&ctx->d_s2s, o));
+        ctx->s2s_cap = o;
+    }
+    { int r = ctx_order_begin(ctx, st); if (r) return r; }
+    uint8_t *B = ctx->d_s2s;
+    uint64_t *d_base = (uint64_t *)(B + oBase);
+    CK(cudaMemsetAsync(d_base, 0, sizeof(uint64_t), st));
+    CK(cudaMemsetAsync(d_err, 0, sizeof(int32_t), st));
+    const bool snappy = (flags & B2C_S2_SNAPPY) != 0;
+    if (nblocks == 0) {      // an empty input: the identifier alone
+        const char *magic = snappy ? "\xff\x06\x00\x00sNaPpY" : "\xff\x06\x00\x00S2sTwO";
+        CK(cudaMemcpyAsync(d_dst, magic, 10, cudaMemcpyHostToDevice, st));
+    }
+    for (uint32_t k = 0; k < nsub && nblocks; k++) {
+        const uint32_t c0 = k * sub, m = (nblocks - c0 < sub) ? nblocks - c0 : sub;
+        const uint8_t *srck = (const uint8_t *)d_src + (uint64_t)c0 * block;
+        int r = launch_s2_encode(ctx, level, flags, srck, block, nullptr, block, n - (uint64_t)c0 * block, B + oSlots, slotB,
+                                 (int64_t *)(B + oEnc), m, st);
+        if (r) return r;
+        S2StreamParams P;
+        memset(&P, 0, sizeof(P));
+        P.src = (const uint8_t *)d_src; P.total = n; P.block = block;
+        P.slots = B + oSlots; P.slot_stride = slotB; P.enc_sizes = (const int64_t *)(B + oEnc);
+        P.crc = (uint32_t *)(B + oCrc); P.piece = (int64_t *)(B + oPiece); P.offsets = (const uint64_t *)(B + oScan);
+        P.base = d_base; P.k = k; P.dst = (uint8_t *)d_dst; P.cap = dst_cap; P.c0 = c0; P.m = m; P.snappy = snappy ? 1u : 0u;
+        P.err = d_err;
+        b2c_s2_stream_crc_kernel<<<(unsigned)ctx->sm_count * 4, S2S_WARPS * 32, 0, st>>>(P);
+        b2c_scan_sizes_kernel<<<1, 1024, 0, st>>>(P.piece, (uint64_t *)(B + oScan), m);
+        b2c_s2_stream_place_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, st>>>(P);
+        b2c_frame_base_kernel<<<1, 1, 0, st>>>(d_base, k, (const uint64_t *)(B + oScan), m);
+        ctx->launches += 4;
+    }
+    // total = identifier + all pieces
+    b2c_s2_stream_total_kernel<<<1, 1, 0, st>>>(d_base, nsub * (nblocks ? 1u : 0u), d_total);
+    CK(cudaGetLastError());
+    return ctx_order_end(ctx, st);
+}
+
+// Host buffers: src[0, n) -> stream in dst (capacity cap >= b2c_s2_stream_bound); *out_len = stream bytes.  Synchronous.
+int b2c_s2_encode_stream(b2c_ctx *ctx, int level, int flags, const void *src, size_t n, uint32_t block, void *dst, size_t cap,
+                         size_t *out_len) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (!out_len || block == 0 || block > 65536) return B2C_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t bound = b2c_s2_stream_bound(n, block);
+    const size_t inB = (n + 255) & ~(size_t)255, outB = (bound + 255) & ~(size_t)255;
+    if (ctx->s2s_io_cap < inB + outB + 512) {
+        CK(cudaDeviceSynchronize());
+        if (ctx->d_s2s_io) CK(cudaFree(ctx->d_s2s_io));
+        ctx->d_s2s_io = nullptr; ctx->s2s_io_cap = 0;
+        CK(cudaMalloc(&ctx->d_s2s_io, inB + outB + 512));
+        ctx->s2s_io_cap = inB + outB + 512;
+    }
+    uint8_t *d_in = ctx->d_s2s_io, *d_out = d_in + inB;
+    uint64_t *d_total = (uint64_t *)(d_out + outB);
+    int32_t *d_err = (int32_t *)(d_total + 1);
+    if (n) CK(cudaMemcpyAsync(d_in, src, n, cudaMemcpyHostToDevice, st));
+    int r = b2c_s2_encode_stream_device(ctx, level, flags, d_in, n, block, d_out, bound, d_total, d_err, st);
+    if (r) { cudaStreamSynchronize(st); return r; }
+    uint64_t total = 0; int32_t err = 0;
+    CK(cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&err, d_err, sizeof(err), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (err) return err;
+    if (total > cap) return B2C_ERR_DST_SMALL;
+    CK(cudaMemcpy(dst, d_out, total, cudaMemcpyDeviceToHost));
+    *out_len = (size_t)total;
+    return B2C_OK;
+}
+
+// Host buffers: a complete S2 / Snappy stream -> its content (s2.Reader over a buffer).  The chunk headers are walked on the
+// host (4 bytes each, no data is touched there); the device decodes every block, copies uncompressed chunks and verifies
+// all checksums.  Errors are the reader's: B2C_ERR_CORRUPT (ErrCorrupt), B2C_ERR_CRC (ErrCRC), B2C_ERR_UNSUPPORTED
+// (reserved unskippable chunk), B2C_ERR_DST_SMALL.
+int b2c_s2_decode_stream(b2c_ctx *ctx, const void *src, size_t n, void *dst, size_t cap, size_t *out_len) {
+    if (!ctx) return B2C_ERR_NO_DEVICE;
+    if (!out_len) return B2C_ERR_ARG;
+    const uint8_t *s = (const uint8_t *)src;
+    std::vector<S2StreamBlock> blocks;
+    uint64_t o = 0, total = 0;
+    bool seen = false, snappyFrame = false;
+    const uint32_t maxBlock = 4u << 20;                      // s2/s2.go:87 maxBlockSize
+    while (o < n) {
+        if (o + 4 > n) return B2C_ERR_CORRUPT;               // io.ErrUnexpectedEOF
+        const uint32_t typ = s[o], ln = (uint32_t)s[o + 1] | (uint32_t)s[o + 2] << 8 | (uint32_t)s[o + 3] << 16;
+        o += 4;
+        if (!seen) { if (typ != 0xff) return B2C_ERR_CORRUPT; seen = true; }
+        if (typ == 0x00 || typ == 0x01) {
+            if (ln < 4 || o + ln > n) return B2C_ERR_CORRUPT;
+            S2StreamBlock b;
+            b.type = typ; b.crc = (uint32_t)s[o] | (uint32_t)s[o + 1] << 8 | (uint32_t)s[o + 2] << 16 | (uint32_t)s[o + 3] << 24;
+            b.src_off = o + 4; b.src_len = ln - 4; b.dst_off = total;
+            if (typ == 0x00) {
+                uint64_t v = 0; uint32_t k = 0, shift = 0;             // DecodedLen (s2/decode.go:36-49)
+                for (;;) {
+                    if (k >= b.src_len || k >= 10) return B2C_ERR_CORRUPT;
+                    const uint8_t by = s[b.src_off + k++];
+                    v |= (uint64_t)(by & 0x7f) << shift;
+                    if (by < 0x80) break;
+                    shift += 7;
+                }
+                if (k > 5 || v > 0xffffffffull) return B2C_ERR_CORRUPT;
+                if (v > maxBlock || (snappyFrame && v > 65536)) return B2C_ERR_CORRUPT;
+                b.dst_len = (uint32_t)v;
+            } else {
+                if (b.src_len > maxBlock || (snappyFrame && b.src_len > 65536)) return B2C_ERR_CORRUPT;
+                b.dst_len = b.src_len;
+            }
+            total += b.dst_len;
+            blocks.push_back(b);
+        } else if (typ == 0xff) {
+            if (ln != 6 || o + 6 > n) return B2C_ERR_CORRUPT;
+            if (memcmp(s + o, "S2sTwO", 6) == 0) snappyFrame = false;
+            else if (memcmp(s + o, "sNaPpY", 6) == 0) snappyFrame = true;
+            else return B2C_ERR_CORRUPT;
+        } else if (typ <= 0x7f) {
+            return B2C_ERR_UNSUPPORTED;                        // reserved unskippable chunk (s2/reader.go:386-391)
+        } else if (o + ln > n) {
+            return B2C_ERR_CORRUPT;                            // skippable chunk / padding cut short
+        }
+        o += ln;
+    }
+    if (total > cap) return B2C_ERR_DST_SMALL;
+    *out_len = (size_t)total;
+    const uint32_t nb = (uint32_t)blocks.size();
+    if (nb == 0) return B2C_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 255) & ~(size_t)255; return r; };
+    const size_t oIn = take(n), oOut = take(total + 16), oBlk = take(sizeof(S2StreamBlock) * nb), oSrcOff = take(8 * (size_t)nb),
+                 oDstOff = take(8 * (size_t)nb), oSrcSz = take(4 * (size_t)nb), oCaps = take(4 * (size_t)nb),
+                 oRes = take(8 * (size_t)nb), oStat = take(4 * (size_t)nb);
+    if (ctx->s2s_io_cap < off) {
+        CK(cudaDeviceSynchronize());
+        if (ctx->d_s2s_io) CK(cudaFree(ctx->d_s2s_io));
+        ctx->d_s2s_io = nullptr; ctx->s2s_io_cap = 0;
+        CK(cudaMalloc(&ctx->d_s2s_io, off));
+        ctx->s2s_io_cap = off;
+    }
+    uint8_t *B = ctx->d_s2s_io;
+    // compressed blocks go to the block decoder; an uncompressed chunk is handed to it as an empty job (size 0 in, cap 0)
+    std::vector<uint64_t> so(nb), dof(nb);
+    std::vector<uint32_t> ssz(nb), caps(nb);
+    for (uint32_t i = 0; i < nb; i++) {
+        so[i] = blocks[i].src_off; dof[i] = blocks[i].dst_off;
+        ssz[i] = blocks[i].type == 0 ? blocks[i].src_len : 0; caps[i] = blocks[i].type == 0 ? blocks[i].dst_len : 0;
+    }
+    CK(cudaMemcpyAsync(B + oIn, src, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B + oBlk, blocks.data(), sizeof(S2StreamBlock) * nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B + oSrcOff, so.data(), 8 * (size_t)nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B + oDstOff, dof.data(), 8 * (size_t)nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B + oSrcSz, ssz.data(), 4 * (size_t)nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(B + oCaps, caps.data(), 4 * (size_t)nb, cudaMemcpyHostToDevice, st));
+    S2DecParams P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = B + oIn; P.src_offsets = (const uint64_t *)(B + oSrcOff); P.src_sizes = (const uint32_t *)(B + oSrcSz);
+    P.dst_base = B + oOut; P.dst_offsets = (const uint64_t *)(B + oDstOff); P.dst_caps = (const uint32_t *)(B + oCaps);
+    P.out_sizes = (int64_t *)(B + oRes); P.nchunks = nb;
+    unsigned grid = (nb + S2DEC_WARPS - 1) / S2DEC_WARPS;
+    if (grid > (unsigned)ctx->sm_count * 16) grid = (unsigned)ctx->sm_count * 16;
+    b2c_s2_decode_kernel<<<grid, S2DEC_WARPS * 32, 0, st>>>(P);
+    unsigned g2 = (nb + S2S_WARPS - 1) / S2S_WARPS;
+    if (g2 > (unsigned)ctx->sm_count * 16) g2 = (unsigned)ctx->sm_count * 16;
+    b2c_s2_stream_verify_kernel<<<g2, S2S_WARPS * 32, 0, st>>>((const S2StreamBlock *)(B + oBlk), B + oIn, B + oOut,
+                                                                (const int64_t *)(B + oRes), (int32_t *)(B + oStat), nb);
+    ctx->launches += 2;
+    std::vector<int32_t> stat(nb);
+    CK(cudaMemcpyAsync(stat.data(), B + oStat, 4 * (size_t)nb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < nb; i++)
+        if (stat[i]) return stat[i] == -4 ? B2C_ERR_CORRUPT : stat[i];      // (a block longer than its declared length is corrupt)
+    CK(cudaMemcpy(dst, B + oOut, total, cudaMemcpyDeviceToHost));
+    return B2C_OK;
 }
 
 int b2c_s2_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, const uint64_t *d_src_offsets,

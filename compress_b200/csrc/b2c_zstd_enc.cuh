@@ -98,6 +98,7 @@ struct ZstdEncParams {
     uint32_t blockmax;            // largest block this launch accepts (65536 or 131072)
     uint32_t big;                 // 1: litLen / matchLen arrays are u32 (blocks > 64 KiB), 0: u16
     uint32_t level;               // 1 fastest, 2 default
+    uint64_t src_total;           // non-zero: the chunks tile one buffer of src_total bytes (the last chunk is shorter)
     uint32_t *counter;            // persistent parse kernels: next chunk to hand out (zeroed before the launch)
     uint32_t chunk0;              // sub-batch offset: kernels work on chunks [chunk0, chunk0 + nchunks) of the call
     // optional debug dump (tests): per chunk {nseq, nlit, kind, litMode} + seq triples + literals
@@ -121,7 +122,13 @@ struct ZstdEncParams {
 #endif
 
 B2C_DEV uint32_t chunk_size(const ZstdEncParams &P, uint32_t c) {
-    return P.desc ? P.desc[c].len : (P.src_sizes ? P.src_sizes[c] : P.src_size_all);
+    if (P.desc) return P.desc[c].len;
+    if (P.src_sizes) return P.src_sizes[c];
+    if (P.src_total) {
+        const uint64_t off = (uint64_t)c * P.src_stride;
+        return (uint32_t)(P.src_total - off < P.src_size_all ? P.src_total - off : P.src_size_all);
+    }
+    return P.src_size_all;
 }
 B2C_DEV const uint8_t *chunk_src(const ZstdEncParams &P, uint32_t c) {
     return P.desc ? P.src_base + P.desc[c].off : P.src_base + (uint64_t)c * P.src_stride;

@@ -24,6 +24,14 @@ class ErrCorrupt(B2CError):
     pass
 
 
+class ErrCRC(B2CError):
+    """s2.ErrCRC (s2/decode.go:20)"""
+
+
+class ErrUnsupported(B2CError):
+    """s2.ErrUnsupported (s2/decode.go:24)"""
+
+
 class ErrTooLarge(B2CError):
     pass
 
@@ -140,3 +148,47 @@ class Codec:
         if codes[0] < 0:
             raise ErrCorrupt("s2: corrupt input")
         return outs[0]
+
+    # ---- streams: the framing format (s2.Writer.EncodeBuffer / s2.Reader, s2/writer.go:357-470, s2/reader.go:249-420) ----
+    def EncodeStream(self, src, better=False, snappy=False, block_size=BLOCK):
+        """Writer.EncodeBuffer(src) + Close(): a complete S2 (or Snappy) stream -- identifier, one checksummed chunk per
+        block.  block_size <= 64 KiB (WriterBlockSize)."""
+        buf = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(0, dtype=np.uint8)
+        cap = int(lib.b2c_s2_stream_bound(len(src), block_size)) + 16
+        out = np.empty(cap, dtype=np.uint8)
+        n = ctypes.c_size_t(0)
+        rc = lib.b2c_s2_encode_stream(self._ctx, BETTER if better else FAST, FLAG_SNAPPY if snappy else 0, buf.ctypes.data, len(src),
+                                      block_size, out.ctypes.data, cap, ctypes.byref(n))
+        check(rc, self._ctx)
+        return out[: n.value].tobytes()
+
+    def encode_stream_device(self, src, better=False, snappy=False, block_size=BLOCK, dst=None):
+        """src: uint8 CUDA tensor.  Returns (dst uint8 CUDA tensor, total uint64 CUDA tensor [1], err int32 CUDA tensor [1]).  Async."""
+        assert src.is_cuda and src.dtype == torch.uint8
+        n = src.numel()
+        if dst is None:
+            dst = torch.empty(int(lib.b2c_s2_stream_bound(n, block_size)) + 16, dtype=torch.uint8, device=src.device)
+        total = torch.zeros(1, dtype=torch.uint64, device=src.device)
+        err = torch.zeros(1, dtype=torch.int32, device=src.device)
+        stream = torch.cuda.current_stream(src.device).cuda_stream
+        rc = lib.b2c_s2_encode_stream_device(self._ctx, BETTER if better else FAST, FLAG_SNAPPY if snappy else 0, src.data_ptr(), n,
+                                             block_size, dst.data_ptr(), dst.numel(), total.data_ptr(), err.data_ptr(),
+                                             ctypes.c_void_p(stream))
+        check(rc, self._ctx)
+        return dst, total, err
+
+    def DecodeStream(self, stream, max_size=None):
+        """io.ReadAll(s2.NewReader(stream)): the stream's content; raises the reader's errors (ErrCorrupt, ErrCRC, ...)."""
+        buf = np.frombuffer(stream, dtype=np.uint8) if len(stream) else np.zeros(0, dtype=np.uint8)
+        cap = max_size if max_size is not None else max(64, 64 * len(stream))
+        out = np.empty(cap, dtype=np.uint8)
+        n = ctypes.c_size_t(0)
+        rc = lib.b2c_s2_decode_stream(self._ctx, buf.ctypes.data, len(stream), out.ctypes.data, cap, ctypes.byref(n))
+        if rc == -5:
+            raise ErrCorrupt("s2: corrupt input")
+        if rc == -9:
+            raise ErrCRC("s2: corrupt input, crc mismatch")
+        if rc == -11:
+            raise ErrUnsupported("s2: unsupported input")
+        check(rc, self._ctx)
+        return out[: n.value].tobytes()

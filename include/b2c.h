@@ -201,6 +201,23 @@ B2C_API int b2c_s2_decode_chunks(b2c_ctx *ctx, const void *const *srcs, const si
                                  const size_t *dst_caps, int64_t *sizes_out, size_t n);
 
 /*
+ * S2 / Snappy STREAMS (the framing format: s2.Writer.EncodeBuffer, s2/writer.go:357-470, and s2.Reader over a buffer,
+ * s2/reader.go:249-420; constants and the masked CRC32-C: s2/s2.go:75-126).  A stream = the identifier chunk, then per
+ * block (<= 64 KiB here, WriterBlockSize) one chunk: type (0 compressed, 1 uncompressed), 24-bit length, checksum of the
+ * uncompressed bytes, payload.  level / flags as for the block encoders (B2C_S2_SNAPPY writes a Snappy stream).
+ * _encode_stream_device: device buffers, asynchronous; *d_total (device u64) = stream bytes, *d_err (device i32) = 0 or a
+ * negative error.  _encode_stream / _decode_stream: host buffers, synchronous.  The reader accepts what s2.Reader accepts
+ * (blocks up to 4 MiB, skippable and padding chunks, Snappy streams) and returns its errors: B2C_ERR_CORRUPT, B2C_ERR_CRC,
+ * B2C_ERR_UNSUPPORTED (reserved unskippable chunk), B2C_ERR_DST_SMALL.
+ */
+B2C_API size_t b2c_s2_stream_bound(size_t n, size_t block);
+B2C_API int b2c_s2_encode_stream_device(b2c_ctx *ctx, int level, int flags, const void *d_src, uint64_t n, uint32_t block,
+                                        void *d_dst, uint64_t dst_cap, uint64_t *d_total, int32_t *d_err, void *stream);
+B2C_API int b2c_s2_encode_stream(b2c_ctx *ctx, int level, int flags, const void *src, size_t n, uint32_t block, void *dst,
+                                 size_t cap, size_t *out_len);
+B2C_API int b2c_s2_decode_stream(b2c_ctx *ctx, const void *src, size_t n, void *dst, size_t cap, size_t *out_len);
+
+/*
  * Standalone huff0 blocks (huff0.Compress4X / Compress1X with a fresh Scratch, huff0/compress.go:14-141;
  * huff0.ReadTable + Decoder.Decompress4X / Decompress1X, huff0/decompress.go:29,234,622).  Block i (<= 262143
  * bytes) -> table description + (jump table +) streams, byte-identical to the reference's output;

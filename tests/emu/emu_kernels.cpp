@@ -7,6 +7,7 @@
 #include "../../compress_b200/csrc/b2c_zstd_dec.cuh"
 #include "../../compress_b200/csrc/b2c_zstd_dec_staged.cuh"
 #include "../../compress_b200/csrc/b2c_s2_dec.cuh"
+#include "../../compress_b200/csrc/b2c_s2_stream.cuh"
 #include "../../compress_b200/csrc/b2c_huf0.cuh"
 #include <vector>
 #include <algorithm>
@@ -169,6 +170,19 @@ int emu_zstd_encode_frames(const uint8_t *src, const uint64_t *offs, const uint6
     free(work);
     free(pool);
     return 0;
+}
+
+// masked CRC32-C of p[0, n) by the device's one-warp routine (the S2 stream checksum)
+uint32_t emu_s2_stream_crc(const uint8_t *p, uint32_t n) {
+    uint32_t out = 0;
+    emu::launch(1, 32, 1024, [&]() {
+        uint32_t *tab = reinterpret_cast<uint32_t *>(emu::dyn_smem);
+        crc32c_fill_table(tab, threadIdx.x, blockDim.x);
+        __syncthreads();
+        const uint32_t c = crc32c_warp(p, n, tab, threadIdx.x);
+        if (threadIdx.x == 0) out = crc_mask(c);
+    });
+    return out;
 }
 
 int emu_zstd_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t nchunks, uint8_t *dst,
