@@ -306,6 +306,7 @@ def main():
     if not args.no_secondary and level == 1:
         # ---- BASELINE config 3: S2 / Snappy block encode + decode of the same chunks, device-resident
         from compress_b200 import s2 as s2mod
+        from compress_b200 import _lib as _lib_mod
         s2c = s2mod.Codec(device=local_rank)
         s2res = {}
         s2dst = torch.empty((n, s2mod.SLOT), dtype=torch.uint8, device=dev)
@@ -340,6 +341,21 @@ def main():
                            "decode_gbs": in_bytes / (dms / 1e3) / 1e9, "decode_ms": dms,
                            "encode_roofline_frac": (in_bytes + s2out) / (ems / 1e3) / 1e9 / peak}
         del dout, s2dst
+        # the framing format around the same blocks (s2.Writer.EncodeBuffer): identifier + one checksummed chunk per block
+        sdst = torch.empty(int(_lib_mod.lib.b2c_s2_stream_bound(in_bytes, CHUNK)) + 16, dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            _, stot, serr = s2c.encode_stream_device(src, dst=sdst)
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(3):
+            _, stot, serr = s2c.encode_stream_device(src, dst=sdst)
+        a1.record()
+        torch.cuda.synchronize()
+        sms = a0.elapsed_time(a1) / 3
+        assert int(serr.item()) == 0
+        s2res["stream"] = {"encode_gbs": in_bytes / (sms / 1e3) / 1e9, "encode_ms": sms, "ratio": int(stot.cpu().numpy()[0]) / in_bytes,
+                           "note": "b2c_s2_encode_stream_device: blocks + CRC32-C + placement into one S2 stream"}
+        del sdst
         side["s2"] = s2res
 
         # ---- BASELINE config 4: standalone huff0 Compress4X / Decompress4X, 262143-byte blocks of the same text

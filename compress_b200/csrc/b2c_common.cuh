@@ -312,6 +312,17 @@ B2C_DEV uint64_t xxh64_warp(const uint8_t *src, uint64_t n, uint8_t *stg, unsign
     return xxh64_finish(v1, v2, v3, v4, src, n);
 }
 
+// Cooperative copy of sz bytes between arbitrarily aligned global addresses: bytes up to the destination's 16-byte boundary,
+// then 4-byte destination words assembled from aligned source words, then the tail.  All threads of the group call.
+B2C_DEV void coop_copy(uint8_t *d, const uint8_t *s, uint32_t sz, unsigned tid, unsigned nthreads) {
+    uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15);
+    if (head > sz) head = sz;
+    for (uint32_t i = tid; i < head; i += nthreads) d[i] = s[i];
+    const uint32_t body = (sz - head) & ~3u;
+    for (uint32_t i = tid * 4; i < body; i += nthreads * 4) *reinterpret_cast<uint32_t *>(d + head + i) = ld32u(s, head + i);
+    for (uint32_t i = head + body + tid; i < sz; i += nthreads) d[i] = s[i];
+}
+
 // streaming (evict-first) 8-byte store: data another kernel reads once should not push reused lines out of L2
 B2C_DEV void st_stream64(uint64_t *p, uint64_t v) {
 #ifndef B2C_EMU

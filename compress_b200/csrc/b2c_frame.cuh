@@ -115,14 +115,7 @@ B2C_DEV void frame_place_block(const uint8_t *slots, uint64_t slot_stride, const
     const bool ok = sz > 0 && at + (uint64_t)sz + 4 <= cap;
     if (tid == 0) pos[c0 + c] = ok ? at : ~0ull;        // ~0: block failed or does not fit
     if (!ok) return;
-    const uint8_t *s = slots + (uint64_t)c * slot_stride;
-    uint8_t *d = packed + at;
-    uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15);
-    if (head > (uint32_t)sz) head = (uint32_t)sz;
-    for (uint32_t i = tid; i < head; i += nthreads) d[i] = s[i];
-    const uint32_t body = ((uint32_t)sz - head) & ~3u;
-    for (uint32_t i = tid * 4; i < body; i += nthreads * 4) *reinterpret_cast<uint32_t *>(d + head + i) = ld32u(s, head + i);
-    for (uint32_t i = head + body + tid; i < (uint32_t)sz; i += nthreads) d[i] = s[i];
+    coop_copy(packed + at, slots + (uint64_t)c * slot_stride, (uint32_t)sz, tid, nthreads);
 }
 // Device, one thread per frame: header in front of its first block, checksum behind its last, offset and size for the
 // caller.  sizes_all: encoded size of every block of the call (<= 0 = error)

@@ -139,8 +139,7 @@ B2C_DEV void s2s_place_block(const S2StreamParams &P, uint32_t c, unsigned tid, 
         d[4] = (uint8_t)crc; d[5] = (uint8_t)(crc >> 8); d[6] = (uint8_t)(crc >> 16); d[7] = (uint8_t)(crc >> 24);
     }
     const uint8_t *s = stored ? P.src + (uint64_t)(P.c0 + c) * P.block : P.slots + (uint64_t)c * P.slot_stride;
-    const uint32_t sz = (uint32_t)pc - 8;
-    for (uint32_t i = tid; i < sz; i += nthreads) d[8 + i] = s[i];
+    coop_copy(d + 8, s, (uint32_t)pc - 8, tid, nthreads);
 }
 
 // ---- reading a stream: the chunk table is made on the host (a serial walk over 4-byte headers); the device decodes the

@@ -89,6 +89,23 @@ if "--s2" in sys.argv and level == 1:
         torch.cuda.synchronize()
         ms = a0.elapsed_time(a1) / 3
         print("  %-10s %.3f ms = %.1f GB/s; ratio %.4f" % (name, ms, n * CH / ms / 1e6, float(ss.sum()) / (n * CH)))
+if "--s2stream" in sys.argv and level == 1:
+    from compress_b200 import s2 as s2mod
+    c = s2mod.Codec()
+    sdst = torch.empty(int(_lib.lib.b2c_s2_stream_bound(n * CH, 65536)) + 16, dtype=torch.uint8, device=dev)
+    for name, better in (("s2 stream", False), ("s2 stream (better)", True)):
+        for _ in range(2):
+            _, tot, err = c.encode_stream_device(src, better=better, dst=sdst)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(3):
+            _, tot, err = c.encode_stream_device(src, better=better, dst=sdst)
+        a1.record()
+        torch.cuda.synchronize()
+        ms = a0.elapsed_time(a1) / 3
+        assert int(err.item()) == 0
+        print("  %-18s %.3f ms = %.1f GB/s; ratio %.4f" % (name, ms, n * CH / ms / 1e6, int(tot.cpu().numpy()[0]) / (n * CH)))
 if "--frames" in sys.argv:
     # frame mode: the same bytes as 1 MiB inputs, one frame each (blocks see their history)
     fs = 1 << 20
