@@ -211,6 +211,8 @@ b2c_ctx *b2c_ctx_create(int device, size_t max_chunks) {
                                     (int)HUF0_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_huf_decompress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(b2c_huf_dec_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_huf_read_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)DEC_SMEM_BYTES) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(b2c_zstd_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1043,11 +1045,15 @@ static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st, uint64
             cudaEventRecord(ctx->dec_ev[2], st);
             b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
         } else {
+            // Order matters (tools/probe/coresidency.cu): CTAs of two kernels share an SM only if its shared-memory
+            // carveout suits both.  The literal kernel (shared memory) goes first, on the caller's stream, so the SMs are
+            // configured for it when the sequence walk (no shared memory; it arrives later, after the event round trip of the
+            // auxiliary stream) fills in beside it; the other way round the literal kernel waits for the SMs to drain.
             CK(cudaEventRecord(ctx->dec_fork, st));
             CK(cudaStreamWaitEvent(ctx->dec_aux, ctx->dec_fork, 0));
-            b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, ctx->dec_aux>>>(P);
+            b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, st>>>(P);
+            b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, ctx->dec_aux>>>(P);
             CK(cudaEventRecord(ctx->dec_join, ctx->dec_aux));
-            b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
             CK(cudaStreamWaitEvent(st, ctx->dec_join, 0));
         }
         if (prof) cudaEventRecord(ctx->dec_ev[3], st);
@@ -1631,9 +1637,32 @@ int b2c_huf_decompress_device(b2c_ctx *ctx, int flags, const void *d_src, size_t
     const unsigned ctasPerSm = (227u * 1024u) / (DEC_SMEM_BYTES + 1024u);
     unsigned grid = (nchunks + DEC_WARPS - 1) / DEC_WARPS, maxGrid = (unsigned)ctx->sm_count * (ctasPerSm ? ctasPerSm : 1);
     if (grid > maxGrid) grid = maxGrid;
-    b2c_huf_decompress_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, (cudaStream_t)stream>>>(P);
+    cudaStream_t st = (cudaStream_t)stream;
+    // Staged form (the default): table pass -> the staged zstd decoder's literal-stream kernel -> the one-warp kernel over what
+    // is left (errors, unusual blocks).  B2C_DEC=onewarp, very large batches and unaligned slots keep the one-warp kernel alone.
+    const bool staged = ctx->dec_staged && nchunks <= 65536 && (dst_stride & 3) == 0;
+    if (staged) {
+        const size_t recBytes = (((size_t)nchunks * sizeof(FdChunk)) + 255) & ~(size_t)255;
+        const size_t hufBytes = (size_t)nchunks * FD_MAXB * 2048 * sizeof(uint16_t);
+        { int r = ctx_order_begin(ctx, st); if (r) return r; }
+        int rc = grow(ctx, &ctx->d_fd, &ctx->fd_cap, recBytes + hufBytes);
+        if (rc) return rc;
+        P.fd = reinterpret_cast<FdChunk *>(ctx->d_fd);
+        P.fd_huf = reinterpret_cast<uint16_t *>(ctx->d_fd + recBytes);
+        b2c_huf_dec_prep_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, st>>>(P);
+        ZstdDecParams Z;
+        memset(&Z, 0, sizeof(Z));
+        Z.src_base = P.src_base; Z.src_stride = src_stride; Z.src_sizes = d_src_sizes;
+        Z.dst_base = P.dst_base; Z.dst_stride = dst_stride; Z.out_sizes = d_out_sizes; Z.nchunks = nchunks;
+        Z.fd = P.fd; Z.fd_huf = P.fd_huf; Z.fd_lits = P.dst_base; Z.fd_lit_stride = dst_stride;
+        const unsigned groups = (nchunks + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
+        b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, st>>>(Z);
+        ctx->launches += 2;
+    }
+    b2c_huf_decompress_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, st>>>(P);
     ctx->launches += 1;
     CK(cudaGetLastError());
+    if (staged) return ctx_order_end(ctx, st);
     return B2C_OK;
 }
 

@@ -11,6 +11,7 @@
 #pragma once
 #include "b2c_huff.cuh"
 #include "b2c_zstd_dec.cuh"
+#include "b2c_zstd_dec_staged.cuh"
 
 namespace b2c {
 
@@ -33,7 +34,12 @@ struct Huf0Params {
     int64_t *out_sizes;
     uint32_t nchunks;
     uint32_t flags;
+    // staged decompress: records of the preparation pass; state 0 = decoded by the stream kernel, FD_LEGACY = this kernel's
+    // job, HUF0_STATE_ERR = the error in pad[0]
+    FdChunk *fd;
+    uint16_t *fd_huf;
 };
+constexpr uint32_t HUF0_STATE_ERR = 2;
 
 B2C_DEV void huf0_compress_block(Huf0Shared *sh, const Huf0Params &P, uint32_t chunk) {
     const unsigned tid = threadIdx.x;
@@ -88,6 +94,43 @@ B2C_DEV int64_t huf0_decompress_block(DecWarp *dw, const uint8_t *src, uint32_t 
     return (int64_t)dstSize;
 }
 
+// Staged decompress, pass 1 (one warp per block): ReadTable, the decoding table to global memory and a one-block record for
+// the literal-stream kernel of the staged zstd decoder (fd_lit_warp: four lanes per block, eight blocks per warp, two-level
+// tables in shared memory, 16-byte stores) -- the same Huffman streams, so the same kernel.  Whatever is unusual keeps the
+// one-warp path (state FD_LEGACY), which also produces the error values.
+B2C_DEV void huf0_prep_block(DecWarp *dw, const Huf0Params &P, uint32_t c, unsigned lane) {
+    const uint8_t *src = P.src_base + (uint64_t)c * P.src_stride;
+    const uint32_t n = P.src_sizes[c], want = P.dst_sizes ? P.dst_sizes[c] : P.dst_cap;
+    FdChunk *ck = P.fd + c;
+    uint32_t state = FD_LEGACY;
+    int64_t err = 0;
+    uint32_t tl = 0;
+    int used = 0;
+    if (P.dst_stride && want > P.dst_stride && want <= HUF0_BLOCK_MAX) { state = HUF0_STATE_ERR; err = HUF0_ERR_DST; }
+    else if (want > HUF0_BLOCK_MAX) { state = HUF0_STATE_ERR; err = HUF0_ERR_TOO_BIG; }
+    else {
+        used = dec_huf_read_table(dw, src, n, &tl, lane);
+        __syncwarp();
+        if (used == -2) { state = HUF0_STATE_ERR; err = HUF0_ERR_UNSUPPORTED; }
+        else if (used < 0) { state = HUF0_STATE_ERR; err = HUF0_ERR_CORRUPT; }
+        else if (n - (uint32_t)used < (1u << 18) && want > 0 && (reinterpret_cast<uintptr_t>(P.dst_base + (uint64_t)c * P.dst_stride) & 3) == 0) {
+            uint16_t *dt = P.fd_huf + (uint64_t)c * FD_MAXB * 2048;
+            for (uint32_t i = lane; i < (1u << tl); i += 32) dt[i] = dw->hufDt[i];
+            state = 0;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        ck->state = state; ck->nBlocks = 1; ck->hasCheck = 0; ck->check = 0; ck->fcs = want; ck->windowSize = 0;
+        ck->pad[0] = (uint32_t)(int32_t)err;
+        FdBlock *bk = &ck->blk[0];
+        bk->type = 2; bk->size = 0; bk->srcOff = 0; bk->litKind = 2; bk->litOff = 0; bk->litRegen = want;
+        bk->nSeqs = 0; bk->bitsOff = 0; bk->bitsLen = 0; bk->tab[0] = bk->tab[1] = bk->tab[2] = 0; bk->tlog = 0; bk->seqOff = 0;
+        bk->hufOff = (uint32_t)(used > 0 ? used : 0);
+        bk->hufInfo = ((n - (uint32_t)(used > 0 ? used : 0)) & 0x3ffffu) | (((P.flags & HUF0_FLAG_4X) ? 1u : 0u) << 18) | (tl << 19);
+    }
+}
+
 // huff0.ReadTable (huff0/decompress.go:29-166) as a service: one warp per input.  Row i of `tables` (260 bytes) receives
 // [0] actualTableLog, [1] 0, [2..3] bytes the table description occupies (LE), [4..259] the code length of every symbol
 // (0 = not present); out_sizes[i] = the same byte count, or a negative error.
@@ -118,6 +161,17 @@ extern "C" __global__ void __launch_bounds__(DEC_WARPS * 32) b2c_huf_read_table_
         __syncwarp();
     }
 }
+extern "C" __global__ void __launch_bounds__(DEC_WARPS * 32) b2c_huf_dec_prep_kernel(Huf0Params P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    DecWarp *dw = reinterpret_cast<DecWarp *>(smem + w * DEC_WARP_BYTES);
+    const uint32_t totalWarps = gridDim.x * DEC_WARPS;
+    for (uint32_t c = blockIdx.x * DEC_WARPS + w; c < P.nchunks; c += totalWarps) {
+        __syncwarp();
+        huf0_prep_block(dw, P, c, lane);
+        __syncwarp();
+    }
+}
 extern "C" __global__ void __launch_bounds__(HUF0_NT, 1) b2c_huf_compress_kernel(Huf0Params P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     Huf0Shared *sh = reinterpret_cast<Huf0Shared *>(smem);
@@ -131,6 +185,11 @@ extern "C" __global__ void __launch_bounds__(DEC_WARPS * 32) b2c_huf_decompress_
     for (uint32_t c = blockIdx.x * DEC_WARPS + w; c < P.nchunks; c += totalWarps) {
         __syncwarp();
         const uint32_t want = P.dst_sizes ? P.dst_sizes[c] : P.dst_cap;
+        if (P.fd) {             // staged call: only what the stream kernel left
+            const uint32_t st = P.fd[c].state;
+            if (st == 0) { if (lane == 0) P.out_sizes[c] = (int64_t)want; continue; }
+            if (st == HUF0_STATE_ERR) { if (lane == 0) P.out_sizes[c] = (int64_t)(int32_t)P.fd[c].pad[0]; continue; }
+        }
         // the exact decoded size must fit the block's slot (it is the caller's number, not the stream's)
         const int64_t r = (P.dst_stride && want > P.dst_stride && want <= HUF0_BLOCK_MAX) ? (int64_t)HUF0_ERR_DST
                           : huf0_decompress_block(dw, P.src_base + (uint64_t)c * P.src_stride, P.src_sizes[c],

@@ -320,13 +320,45 @@ int emu_huf_compress(const uint8_t *src, uint64_t stride, const uint32_t *sizes,
 }
 int emu_huf_decompress(const uint8_t *src, uint64_t stride, const uint32_t *sizes, uint32_t n, uint8_t *dst,
                        uint64_t dst_stride, const uint32_t *dst_sizes, int64_t *out_sizes, int four) {
+    // the device's launch sequence: table pass, the staged decoder's literal-stream kernel, the one-warp kernel over the rest
+    Huf0Params P;
+    memset(&P, 0, sizeof(P));
+    P.src_base = src; P.src_stride = stride; P.src_sizes = sizes; P.dst_base = dst; P.dst_stride = dst_stride;
+    P.dst_sizes = dst_sizes; P.out_sizes = out_sizes; P.nchunks = n; P.flags = four ? HUF0_FLAG_4X : 0;
+    std::vector<FdChunk> fd(n);
+    memset(fd.data(), 0xCD, sizeof(FdChunk) * (size_t)n);
+    std::vector<uint16_t> hufs((size_t)n * FD_MAXB * 2048, 0xCDCD);
+    const bool staged = (dst_stride & 3) == 0 && n > 0;
+    if (staged) {
+        P.fd = fd.data(); P.fd_huf = hufs.data();
+        emu::launch(1, DEC_WARPS * 32, DEC_SMEM_BYTES, [&]() {
+            const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+            DecWarp *dw = reinterpret_cast<DecWarp *>(emu::dyn_smem + w * DEC_WARP_BYTES);
+            for (uint32_t c = w; c < n; c += DEC_WARPS) { __syncwarp(); huf0_prep_block(dw, P, c, lane); __syncwarp(); }
+        });
+        ZstdDecParams Z;
+        memset(&Z, 0, sizeof(Z));
+        Z.src_base = src; Z.src_stride = stride; Z.src_sizes = sizes; Z.dst_base = dst; Z.dst_stride = dst_stride;
+        Z.out_sizes = out_sizes; Z.nchunks = n; Z.fd = fd.data(); Z.fd_huf = hufs.data(); Z.fd_lits = dst; Z.fd_lit_stride = dst_stride;
+        const unsigned groups = (n + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
+        emu::launch((groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, [&]() {
+            const unsigned w = threadIdx.x >> 5;
+            fd_lit_warp(emu::dyn_smem + w * FD_LIT_WARP_BYTES, Z, blockIdx.x * FD_LIT_WARPS + w, threadIdx.x & 31);
+        });
+    }
     emu::launch(1, DEC_WARPS * 32, DEC_SMEM_BYTES, [&]() {
         const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
         DecWarp *dw = reinterpret_cast<DecWarp *>(emu::dyn_smem + w * DEC_WARP_BYTES);
         for (uint32_t c = w; c < n; c += DEC_WARPS) {
             __syncwarp();
-            int64_t r = huf0_decompress_block(dw, src + (uint64_t)c * stride, sizes[c], dst + (uint64_t)c * dst_stride,
-                                              dst_sizes[c], four != 0, lane);
+            if (P.fd) {
+                const uint32_t st = P.fd[c].state;
+                if (st == 0) { if (lane == 0) out_sizes[c] = (int64_t)dst_sizes[c]; continue; }
+                if (st == HUF0_STATE_ERR) { if (lane == 0) out_sizes[c] = (int64_t)(int32_t)P.fd[c].pad[0]; continue; }
+            }
+            const int64_t r = (dst_stride && dst_sizes[c] > dst_stride && dst_sizes[c] <= HUF0_BLOCK_MAX) ? (int64_t)HUF0_ERR_DST
+                              : huf0_decompress_block(dw, src + (uint64_t)c * stride, sizes[c], dst + (uint64_t)c * dst_stride,
+                                                      dst_sizes[c], four != 0, lane);
             __syncwarp();
             if (lane == 0) out_sizes[c] = r;
         }
