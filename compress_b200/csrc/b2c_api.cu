@@ -1045,15 +1045,13 @@ static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st, uint64
             cudaEventRecord(ctx->dec_ev[2], st);
             b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
         } else {
-            // Order matters (tools/probe/coresidency.cu): CTAs of two kernels share an SM only if its shared-memory
-            // carveout suits both.  The literal kernel (shared memory) goes first, on the caller's stream, so the SMs are
-            // configured for it when the sequence walk (no shared memory; it arrives later, after the event round trip of the
-            // auxiliary stream) fills in beside it; the other way round the literal kernel waits for the SMs to drain.
+            // (measured both ways round: the literal kernel on the auxiliary stream is 0.6 ms per GiB better than the sequence
+            // walk there; neither order overlaps the two fully -- see DESIGN.md section 3.2 on shared-memory carveouts)
             CK(cudaEventRecord(ctx->dec_fork, st));
             CK(cudaStreamWaitEvent(ctx->dec_aux, ctx->dec_fork, 0));
-            b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, st>>>(P);
-            b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, ctx->dec_aux>>>(P);
+            b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, ctx->dec_aux>>>(P);
             CK(cudaEventRecord(ctx->dec_join, ctx->dec_aux));
+            b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
             CK(cudaStreamWaitEvent(st, ctx->dec_join, 0));
         }
         if (prof) cudaEventRecord(ctx->dec_ev[3], st);
