@@ -41,6 +41,46 @@ def MaxEncodedLen(n):
     return r if (r or n == 0) and n <= 0xffffffff else -1
 
 
+def _decoded_len(block):
+    """decodedLen (s2/decode.go:36-49): (length, header bytes) of a block, ErrCorrupt on a bad varint."""
+    v, shift = 0, 0
+    for k in range(10):
+        if k >= len(block):
+            raise ErrCorrupt("s2: corrupt input")
+        b = block[k]
+        v |= (b & 0x7F) << shift
+        if b < 0x80:
+            if k + 1 > 5 or v > 0xFFFFFFFF:
+                raise ErrCorrupt("s2: corrupt input")
+            return v, k + 1
+        shift += 7
+    raise ErrCorrupt("s2: corrupt input")
+
+
+def ConcatBlocks(blocks, dst=None):
+    """s2.ConcatBlocks (s2/encode.go:322-361): the blocks' bodies behind one length header -- a single valid block.  Host-side
+    byte work, as in the reference (the blocks are not validated)."""
+    total, bodies = 0, []
+    for b in blocks:
+        n, hdr = _decoded_len(b)
+        total += n
+        bodies.append(bytes(b[hdr:]))
+    out = bytearray() if dst is None else dst
+    if total == 0:
+        out.append(0)
+        return bytes(out) if dst is None else out
+    if total > 0xFFFFFFFF:
+        raise ErrTooLarge("s2: decoded block is too large")
+    v = total
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    for body in bodies:
+        out += body
+    return bytes(out) if dst is None else out
+
+
 class Codec:
     """Batch S2 block encoder/decoder on one B200."""
 
@@ -124,24 +164,35 @@ class Codec:
             return [], []
         return self._host(lib.b2c_s2_decode_chunks, blocks, caps)
 
+    def _encode_any(self, src, snappy=False, better=False):
+        """One block for an input of any size: pieces of 64 KiB are encoded as one device batch and joined with ConcatBlocks
+        (every piece's copies stay inside the piece, so the joined bodies are one valid block)."""
+        if len(src) <= BLOCK:
+            return self.encode_blocks([src], snappy=snappy, better=better)[0]
+        src = bytes(src)
+        parts = self.encode_blocks([src[o:o + BLOCK] for o in range(0, len(src), BLOCK)], snappy=snappy, better=better)
+        return ConcatBlocks(parts)
+
     def Encode(self, src):
-        """s2.Encode(nil, src) for one block (s2/encode.go:29)."""
-        return self.encode_blocks([src])[0]
+        """s2.Encode(nil, src) (s2/encode.go:29)."""
+        return self._encode_any(src)
 
     def EncodeBetter(self, src):
         """s2.EncodeBetter(nil, src) (s2/encode.go:117): the two-table match finder."""
-        return self.encode_blocks([src], better=True)[0]
+        return self._encode_any(src, better=True)
 
     def EncodeSnappyBetter(self, src):
         """s2.EncodeSnappyBetter(nil, src) (s2/encode.go:248)."""
-        return self.encode_blocks([src], snappy=True, better=True)[0]
+        return self._encode_any(src, snappy=True, better=True)
 
     def EncodeSnappy(self, src):
         """s2.EncodeSnappy(nil, src) (s2/encode.go:204): output any Snappy decoder accepts."""
-        return self.encode_blocks([src], snappy=True)[0]
+        return self._encode_any(src, snappy=True)
 
-    def Decode(self, src, max_len=BLOCK):
-        """s2.Decode(nil, src) (s2/decode.go:58)."""
+    def Decode(self, src, max_len=None):
+        """s2.Decode(nil, src) (s2/decode.go:58); max_len defaults to the block's own declared length."""
+        if max_len is None:
+            max_len = max(_decoded_len(src)[0], 1)
         outs, codes = self.decode_blocks([src], [max_len])
         if codes[0] == -4:
             raise ErrTooLarge("s2: decoded block is too large")

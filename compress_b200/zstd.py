@@ -231,6 +231,42 @@ class Encoder:
         return out
 
 
+class Writer:
+    """The streaming face of zstd.Encoder (Write / Flush / Close, zstd/encoder.go:123-260) over frame mode: bytes written
+    are gathered and leave as complete frames -- one per Flush / Close, or every `frame_bytes` of input -- each a multi-block
+    frame whose blocks see their history.  Concatenated frames are one valid zstd stream (zstd/encoder.go:719)."""
+
+    def __init__(self, w, level=SpeedFastest, crc=True, device=0, frame_bytes=8 << 20):
+        self._w = w
+        self._enc = Encoder(level=level, crc=crc, device=device, max_chunks=64)
+        self._buf = bytearray()
+        self._frame_bytes = frame_bytes
+        self._wrote = False
+
+    def Write(self, p):
+        self._buf += p
+        while len(self._buf) >= self._frame_bytes:
+            self._emit(self._frame_bytes)
+        return len(p)
+
+    def _emit(self, n):
+        part = bytes(self._buf[:n])
+        del self._buf[:n]
+        self._w.write(self._enc.encode_frames([part])[0])
+        self._wrote = True
+
+    def Flush(self):
+        if self._buf:
+            self._emit(len(self._buf))
+
+    def Close(self):
+        self.Flush()
+        if not self._wrote:          # an empty stream is still a frame (WithZeroFrames, zstd/encoder.go:732-751)
+            self._w.write(self._enc.encode_frames([b""])[0])
+            self._wrote = True
+        self._enc.close()
+
+
 # ---- decoder ------------------------------------------------------------------------------------
 class ZstdError(B2CError):
     """Decode error; ``code`` is the C-ABI error code, ``str`` the reference's message class."""

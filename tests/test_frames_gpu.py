@@ -59,3 +59,25 @@ def test_frames_device_batch_one_mib_frames():
     torch.cuda.synchronize()
     assert int(fz.sum()) < int(outs.sum())
     enc.close()
+
+
+def test_writer_streams_frames():
+    """zstd.Writer (Write / Flush / Close over frame mode): the concatenated frames decode to what was written."""
+    import io
+    from compress_b200 import zstd
+    tw = H.golden("twain.txt")
+    sink = io.BytesIO()
+    w = zstd.Writer(sink, level=2, frame_bytes=150000)
+    for o in range(0, len(tw), 70001):
+        w.Write(tw[o:o + 70001])
+    w.Close()
+    out = sink.getvalue()
+    r, dec = H.oracle_decode(out, len(tw) + 64)
+    assert r == len(tw) and dec == tw
+    d = zstd.Decoder()
+    assert d.DecodeAll(out, size_hint=len(tw) + 64) == tw
+    d.close()
+    sink = io.BytesIO()
+    w = zstd.Writer(sink)
+    w.Close()
+    assert H.oracle_decode(sink.getvalue(), 16)[0] == 0

@@ -124,3 +124,14 @@ def test_stream_device_one_gib_shape():
     st = bytes(dst[:n].cpu().numpy())
     assert c.DecodeStream(st, max_size=64 << 20) == bytes(src.cpu().numpy())
     c.close()
+
+
+def test_encode_any_size_is_one_block(codec):
+    """s2.Encode of an input larger than the device's 64 KiB block: pieces encoded as one batch, joined with ConcatBlocks
+    (s2/encode.go:322-361) -- one block the oracle's s2Decode and the device decode."""
+    tw = H.golden("twain.txt")
+    for fn in (codec.Encode, codec.EncodeBetter, codec.EncodeSnappy):
+        blk = fn(tw)
+        r, out = orc_s2_decode(blk, len(tw))
+        assert r == len(tw) and out == tw
+        assert codec.Decode(blk) == tw

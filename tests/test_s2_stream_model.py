@@ -61,3 +61,25 @@ def test_model_round_trip_with_oracle_blocks():
     bad = bytearray(st); bad[14] ^= 1
     with pytest.raises(ValueError, match="crc"):
         R.read_stream(bytes(bad), dec)
+
+
+def test_concat_blocks_matches_the_reference_rule():
+    """s2.ConcatBlocks (s2/encode.go:322-361) in the host mirror: the joined block decodes (oracle s2Decode) to the joined
+    content; empty input gives the one-byte block; a bad varint is ErrCorrupt."""
+    import importlib.util, sys, types
+    # the mirror module imports torch and the CUDA library: load only its pure helpers
+    src = open(os.path.join(os.path.dirname(__file__), "..", "compress_b200", "s2.py")).read()
+    ns = {}
+    pre = src[src.index("class ErrCorrupt"):src.index("class Codec:")]
+    exec("class B2CError(RuntimeError):\n    pass\n" + pre, ns)
+    from test_oracle_s2 import s2_encode, s2_decode
+    tw = H.golden("twain.txt")
+    pieces = [tw[:65536], tw[65536:100000], b"", tw[100000:100007]]
+    blocks = [s2_encode(p_, 0) for p_ in pieces]
+    joined = ns["ConcatBlocks"](blocks)
+    want = b"".join(pieces)
+    r, out = s2_decode(joined, len(want))
+    assert r == len(want) and out == want
+    assert ns["ConcatBlocks"]([s2_encode(b"", 0)]) == b"\x00"
+    with pytest.raises(ns["ErrCorrupt"]):
+        ns["ConcatBlocks"]([b"\xff\xff\xff\xff\xff\xff"])
