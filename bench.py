@@ -496,7 +496,7 @@ def main():
                 "numa_node": numa,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind, "kernel": dom,
-                             "algorithmic_bytes_per_launch": in_bytes + out_bytes,
+                             "algorithmic_bytes_per_launch": (in_bytes + out_bytes) / max(1, kcalls // max(1, args.steps)),
                              "kernel_ms_per_step": per_step, "pipeline_launches_per_step": kcalls // max(args.steps, 1),
                              "pipeline_frac": (in_bytes + out_bytes) / step_s / 1e9 / peak},
                 "e2e": {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": ne * CHUNK, "d2h_bytes_per_step": int(e_total),

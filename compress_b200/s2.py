@@ -3,8 +3,10 @@
 Names follow klauspost/compress/s2: ``Encode`` (s2/encode.go:29), ``EncodeBetter`` (:117), ``EncodeSnappy`` (:204),
 ``EncodeSnappyBetter`` (:248), ``Decode``
 (s2/decode.go:58), ``MaxEncodedLen`` (s2/encode.go:389), ``ErrCorrupt`` / ``ErrTooLarge`` (s2/decode.go:17-26).
-The work is done by libb200comp.so through the C ABI in include/b2c.h; blocks are at most 64 KiB (the
-``WriterBlockSize`` the GPU path is built for), larger inputs raise ``ErrTooLarge``.
+The work is done by libb200comp.so through the C ABI in include/b2c.h; device blocks are at most 64 KiB (the
+``WriterBlockSize`` the GPU path is built for): ``encode_blocks`` raises ``ErrTooLarge`` beyond that, ``Encode*`` join
+64 KiB pieces into one block with ``ConcatBlocks`` (s2/encode.go:322), ``EncodeStream`` / ``DecodeStream`` are the framing
+format (s2.Writer / s2.Reader over a buffer).
 """
 import ctypes
 

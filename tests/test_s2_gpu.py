@@ -31,7 +31,10 @@ def test_s2_encode_blocks(codec, oracle_lib):
                 n, got = orc_decode(c, len(b))
                 assert n == len(b) and got == b, (better, snappy, i)
     with pytest.raises(s2.ErrTooLarge):
-        codec.Encode(bytes(65537))
+        codec.encode_blocks([bytes(65537)])           # one device block is at most 64 KiB ...
+    big = codec.Encode(bytes(65537))                  # ... s2.Encode joins pieces into one block (ConcatBlocks)
+    n, got = orc_decode(big, 65537)
+    assert n == 65537 and got == bytes(65537)
     assert s2.MaxEncodedLen(0) == 1 and s2.MaxEncodedLen(0xffffffff) == -1
 
 
