@@ -236,11 +236,13 @@ class Writer:
     are gathered and leave as complete frames -- one per Flush / Close, or every `frame_bytes` of input -- each a multi-block
     frame whose blocks see their history.  Concatenated frames are one valid zstd stream (zstd/encoder.go:719)."""
 
-    def __init__(self, w, level=SpeedFastest, crc=True, device=0, frame_bytes=8 << 20):
+    def __init__(self, w, level=SpeedFastest, crc=True, device=0, frame_bytes=None):
+        """frame_bytes: input bytes per frame; default four frame-mode blocks (192 KiB at SpeedFastest, 384 KiB above), the
+        longest frames the staged GPU decoder takes on its fast path."""
         self._w = w
         self._enc = Encoder(level=level, crc=crc, device=device, max_chunks=64)
         self._buf = bytearray()
-        self._frame_bytes = frame_bytes
+        self._frame_bytes = frame_bytes if frame_bytes else 4 * (49152 if level == SpeedFastest else 98304)
         self._wrote = False
 
     def Write(self, p):

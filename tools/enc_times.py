@@ -107,8 +107,11 @@ if "--s2stream" in sys.argv and level == 1:
         assert int(err.item()) == 0
         print("  %-18s %.3f ms = %.1f GB/s; ratio %.4f" % (name, ms, n * CH / ms / 1e6, int(tot.cpu().numpy()[0]) / (n * CH)))
 if "--frames" in sys.argv:
-    # frame mode: the same bytes as 1 MiB inputs, one frame each (blocks see their history)
+    # frame mode: the same bytes as 1 MiB inputs, one frame each (blocks see their history); --frame-bytes=N: other frame size
     fs = 1 << 20
+    for a in sys.argv:
+        if a.startswith("--frame-bytes="):
+            fs = int(a.split("=")[1])
     nf = (n * CH) // fs
     offs, lens = [i * fs for i in range(nf)], [fs] * nf
     fdst = torch.empty(nf * (fs + 4096), dtype=torch.uint8, device=dev)
@@ -124,7 +127,7 @@ if "--frames" in sys.argv:
     fms = f0.elapsed_time(f1) / 3
     fz = fsz.cpu()
     assert int(fz.min()) > 0
-    print("  frame mode (%d x 1 MiB frames) %.3f ms = %.1f GB/s; ratio %.4f" % (nf, fms, nf * fs / fms / 1e6, float(fz.sum()) / (nf * fs)))
+    print("  frame mode (%d x %d KiB frames) %.3f ms = %.1f GB/s; ratio %.4f" % (nf, fs >> 10, fms, nf * fs / fms / 1e6, float(fz.sum()) / (nf * fs)))
     enc.profile(True)
     for _ in range(2):
         enc.encode_frames_device(src, offs, lens, dst=fdst)
@@ -150,4 +153,4 @@ if "--frames-decode" in sys.argv:
     torch.cuda.synchronize()
     gms = g0.elapsed_time(g1) / 2
     assert bool((dres == fs).all()) and torch.equal(dout.view(-1), src[: nf * fs])
-    print("  decode of the %d multi-block frames %.3f ms = %.1f GB/s (output bytes)" % (nf, gms, nf * fs / gms / 1e6))
+    print("  decode of the %d multi-block frames (%d KiB each) %.3f ms = %.1f GB/s (output bytes)" % (nf, fs >> 10, gms, nf * fs / gms / 1e6))
