@@ -291,6 +291,57 @@ int emu_s2_encode(const uint8_t *src, uint64_t stride, const uint32_t *sizes, ui
     return emu_s2_encode_lv(src, stride, sizes, nchunks, dst, dst_stride, out_sizes, snappy, 0, 0);
 }
 
+// b2c_s2_encode_stream_device with the device's kernels (one sub-batch): blocks, checksums, scan, placement.
+// Returns the stream length, or a negative error.
+int64_t emu_s2_encode_stream(const uint8_t *src, uint64_t n, uint32_t block, uint8_t *dst, uint64_t cap, int snappy, int better) {
+    const uint32_t nblocks = (uint32_t)((n + block - 1) / block);
+    const char *magic = snappy ? "\xff\x06\x00\x00sNaPpY" : "\xff\x06\x00\x00S2sTwO";
+    if (cap < 10) return -4;
+    if (nblocks == 0) { memcpy(dst, magic, 10); return 10; }
+    uint64_t slotB = block + (block / 6) + 64;           // >= s2.MaxEncodedLen(block)
+    slotB = (slotB + 15) & ~15ull;
+    std::vector<uint8_t> slots((size_t)slotB * nblocks + 64, 0xCD), scratch(std::max<size_t>(16, std::max(LzLayout<3>::SCRATCH_BYTES, LzLayout<4>::SCRATCH_BYTES)), 0xCD);
+    std::vector<int64_t> enc(nblocks, 0), piece(nblocks, 0);
+    std::vector<uint32_t> crc(nblocks, 0);
+    std::vector<uint64_t> scan(nblocks + 1, 0), base(2, 0);
+    ZstdEncParams E;
+    memset(&E, 0, sizeof(E));
+    E.src_base = src; E.src_stride = block; E.src_size_all = block; E.src_total = n;
+    E.dst_base = slots.data(); E.dst_stride = slotB; E.dst_cap = (uint32_t)slotB;
+    E.out_sizes = enc.data(); E.nchunks = nblocks; E.scratch = scratch.data(); E.blockmax = 65536;
+    if (better)
+        emu::launch(1, LzCfg<4>::NT, LzLayout<4>::SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < E.nchunks; c++) {
+                if (snappy) lz_parse_chunk<4, LZ_MODE_SNAPPY>(emu::dyn_smem, E, c, E.scratch);
+                else lz_parse_chunk<4, LZ_MODE_S2>(emu::dyn_smem, E, c, E.scratch);
+            }
+        });
+    else
+        emu::launch(1, LzCfg<3>::NT, LzLayout<3>::SMEM_BYTES, [&]() {
+            for (uint32_t c = 0; c < E.nchunks; c++) {
+                if (snappy) lz_parse_chunk<3, LZ_MODE_SNAPPY>(emu::dyn_smem, E, c, E.scratch);
+                else lz_parse_chunk<3, LZ_MODE_S2>(emu::dyn_smem, E, c, E.scratch);
+            }
+        });
+    int32_t err = 0;
+    S2StreamParams P;
+    memset(&P, 0, sizeof(P));
+    P.src = src; P.total = n; P.block = block; P.slots = slots.data(); P.slot_stride = slotB; P.enc_sizes = enc.data();
+    P.crc = crc.data(); P.piece = piece.data(); P.offsets = scan.data(); P.base = base.data(); P.k = 0;
+    P.dst = dst; P.cap = cap; P.c0 = 0; P.m = nblocks; P.snappy = snappy ? 1u : 0u; P.err = &err;
+    emu::launch((nblocks + 3) / 4, 128, 1024, [&]() {
+        uint32_t *tab = reinterpret_cast<uint32_t *>(emu::dyn_smem);
+        crc32c_fill_table(tab, threadIdx.x, blockDim.x);
+        __syncthreads();
+        const uint32_t c = blockIdx.x * 4 + (threadIdx.x >> 5);
+        if (c < P.m) s2s_crc_block(P, c, tab, threadIdx.x & 31);
+    });
+    for (uint32_t i = 0; i < nblocks; i++) scan[i + 1] = scan[i] + (piece[i] > 0 ? (uint64_t)piece[i] : 0);
+    emu::launch(nblocks, 256, 0, [&]() { s2s_place_block(P, blockIdx.x, threadIdx.x, blockDim.x); });
+    if (err) return err;
+    return (int64_t)(10 + scan[nblocks]);
+}
+
 int emu_s2_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t *src_sizes, uint32_t n, uint8_t *dst,
                   const uint64_t *dst_off, const uint32_t *dst_caps, int64_t *out_sizes) {
     S2DecParams P;

@@ -135,3 +135,11 @@ def test_encode_any_size_is_one_block(codec):
         r, out = orc_s2_decode(blk, len(tw))
         assert r == len(tw) and out == tw
         assert codec.Decode(blk) == tw
+
+
+def test_device_stream_equals_emulated_kernels(codec, emu_lib):
+    from test_s2_stream_model import _emu_stream
+    tw = H.golden("twain.txt")
+    for data in (tw[:200001], tw[:65536], b"xy" * 40000):
+        for snappy, better in ((False, False), (False, True), (True, False)):
+            assert codec.EncodeStream(data, better=better, snappy=snappy) == _emu_stream(emu_lib, data, snappy=snappy, better=better)

@@ -83,3 +83,41 @@ def test_concat_blocks_matches_the_reference_rule():
     assert ns["ConcatBlocks"]([s2_encode(b"", 0)]) == b"\x00"
     with pytest.raises(ns["ErrCorrupt"]):
         ns["ConcatBlocks"]([b"\xff\xff\xff\xff\xff\xff"])
+
+
+def _emu_stream(E, data, block=65536, snappy=False, better=False):
+    E.emu_s2_encode_stream.restype = ctypes.c_int64
+    E.emu_s2_encode_stream.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
+                                       ctypes.c_int]
+    src = np.frombuffer(bytes(data) + bytes(64), dtype=np.uint8).copy()
+    cap = len(data) + len(data) // 5 + 8 * (len(data) // block + 2) + 64
+    dst = np.zeros(cap, dtype=np.uint8)
+    r = E.emu_s2_encode_stream(src.ctypes.data, len(data), block, dst.ctypes.data, cap, 1 if snappy else 0, 1 if better else 0)
+    assert r >= 10, r
+    return bytes(dst[:r])
+
+
+def test_emulated_stream_writer_against_the_model(emu_lib):
+    """The device's stream assembly (block encode, per-block checksum, scan, placement) under the emulator: the stream is read
+    by the model of s2.Reader with the oracle's s2Decode; incompressible blocks are uncompressed chunks; the last block is ragged."""
+    from test_oracle_s2 import s2_decode
+
+    def dec(body, n):
+        r, out = s2_decode(body, n)
+        return out if r == n else None
+    tw = H.golden("twain.txt")
+    rng = np.random.default_rng(12)
+    cases = [b"", b"a", tw[:100], tw[:65536], tw[:65537], tw[:200001],
+             tw[:70000] + rng.integers(0, 256, 70000, dtype=np.uint8).tobytes() + tw[70000:90000]]
+    for data in cases:
+        for snappy, better in ((False, False), (False, True), (True, False)):
+            st = _emu_stream(emu_lib, data, snappy=snappy, better=better)
+            assert st[:10] == (R.MAGIC_SNAPPY if snappy else R.MAGIC_S2)
+            assert R.read_stream(st, dec) == data
+    st = _emu_stream(emu_lib, tw[:50000], block=4096)
+    assert R.read_stream(st, dec) == tw[:50000]
+    o, types = 10, []
+    st = _emu_stream(emu_lib, cases[-1])
+    while o < len(st):
+        types.append(st[o]); o += 4 + (st[o + 1] | st[o + 2] << 8 | st[o + 3] << 16)
+    assert 1 in types and 0 in types          # the random block travels uncompressed, the text blocks compressed
