@@ -1047,31 +1047,46 @@ static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st, uint64
     { int r = ctx_order_begin(ctx, st); if (r) return r; }    // the context's scratch is shared by all streams
     const uint32_t n = P.nchunks;
     const bool prof = ctx->dec_prof != 0;
-    const bool staged = ctx->dec_staged && lit_span > 0 && lit_span <= kStagedSpanLimit && (uint64_t)n * FD_MAXB * FD_TAB_ENTRIES < (1ull << 31);
+    // Blocks per input the staged kernels take: FD_MAXB with one lane / quad per input (many inputs), up to FD_MAXB_LONG with one
+    // lane / quad per (input, block) when the inputs are few -- then long frames are decoded block-parallel.  The tables are
+    // [n][maxb], so n * maxb is bounded.
+    uint32_t maxb = FD_MAXB;
+    if (n <= 4096) { maxb = (uint32_t)(65536 / n); if (maxb > FD_MAXB_LONG) maxb = FD_MAXB_LONG; }      // (>= 16 blocks per input)
+    const bool perBlock = maxb > FD_MAXB;
+    const bool staged = ctx->dec_staged && lit_span > 0 && lit_span <= kStagedSpanLimit && (uint64_t)n * maxb * FD_TAB_ENTRIES < (1ull << 31);
     if (staged) {
         const size_t recBytes = (((size_t)n * sizeof(FdChunk)) + 255) & ~(size_t)255;
-        const size_t tabBytes = (size_t)n * FD_MAXB * FD_TAB_ENTRIES * sizeof(uint32_t);
-        const size_t hufBytes = (size_t)n * FD_MAXB * 2048 * sizeof(uint16_t);
-        if ((rc = grow(ctx, &ctx->d_fd, &ctx->fd_cap, recBytes + tabBytes + hufBytes))) return rc;
+        const size_t blkBytes = (((size_t)n * maxb * sizeof(FdBlock)) + 255) & ~(size_t)255;
+        const size_t tabBytes = (size_t)n * maxb * FD_TAB_ENTRIES * sizeof(uint32_t);
+        const size_t hufBytes = (size_t)n * maxb * 2048 * sizeof(uint16_t);
+        if ((rc = grow(ctx, &ctx->d_fd, &ctx->fd_cap, recBytes + blkBytes + tabBytes + hufBytes))) return rc;
         if ((rc = grow(ctx, &ctx->d_fd_seq, &ctx->fd_seq_cap, 8 * ((size_t)(lit_span / 3) + 2 * (size_t)n + 8)))) return rc;
         if ((rc = grow(ctx, &ctx->d_fd_lit, &ctx->fd_lit_cap, (size_t)lit_span + 64))) return rc;
         P.fd = reinterpret_cast<FdChunk *>(ctx->d_fd);
-        P.fd_tabs = reinterpret_cast<uint32_t *>(ctx->d_fd + recBytes);
-        P.fd_huf = reinterpret_cast<uint16_t *>(ctx->d_fd + recBytes + tabBytes);
+        P.fd_blk = reinterpret_cast<FdBlock *>(ctx->d_fd + recBytes);
+        P.fd_maxb = maxb; P.fd_per_block = perBlock ? 1u : 0u;
+        P.fd_tabs = reinterpret_cast<uint32_t *>(ctx->d_fd + recBytes + blkBytes);
+        P.fd_huf = reinterpret_cast<uint16_t *>(ctx->d_fd + recBytes + blkBytes + tabBytes);
         P.fd_const = ctx->d_fd_const;
         P.fd_seqs = reinterpret_cast<uint64_t *>(ctx->d_fd_seq);
         P.fd_lits = ctx->d_fd_lit;
         P.fd_lit_stride = lit_stride;
-        const unsigned groups = (n + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
+        const uint32_t units = perBlock ? n * maxb : n;            // what the literal and sequence kernels spread over
+        const unsigned groups = (units + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
         if (prof) cudaEventRecord(ctx->dec_ev[0], st);
         b2c_zstd_dec_scan_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+        if (perBlock) {             // index pass above; now the blocks' contents side by side, then the per-input link pass
+            b2c_zstd_dec_scan_block_kernel<<<(units + 31) / 32, 32, 0, st>>>(P);
+            b2c_zstd_dec_link_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+            ctx->launches += 2;
+        }
         // the literal kernel and the sequence walk both depend on the scan only and both are bound by the latency of their
         // serial walks, not by any unit: they run side by side (one after the other when per-kernel times are wanted)
         if (prof) {
             cudaEventRecord(ctx->dec_ev[1], st);
             b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, st>>>(P);
             cudaEventRecord(ctx->dec_ev[2], st);
-            b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+            b2c_zstd_dec_seq_kernel<<<(units + 31) / 32, 32, 0, st>>>(P);
         } else {
             // (measured both ways round: the literal kernel on the auxiliary stream is 0.6 ms per GiB better than the sequence
             // walk there; neither order overlaps the two fully -- see DESIGN.md section 3.2 on shared-memory carveouts)
@@ -1079,13 +1094,14 @@ static int launch_decode(b2c_ctx *ctx, ZstdDecParams &P, cudaStream_t st, uint64
             CK(cudaStreamWaitEvent(ctx->dec_aux, ctx->dec_fork, 0));
             b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, ctx->dec_aux>>>(P);
             CK(cudaEventRecord(ctx->dec_join, ctx->dec_aux));
-            b2c_zstd_dec_seq_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+            b2c_zstd_dec_seq_kernel<<<(units + 31) / 32, 32, 0, st>>>(P);
             CK(cudaStreamWaitEvent(st, ctx->dec_join, 0));
         }
         if (prof) cudaEventRecord(ctx->dec_ev[3], st);
         b2c_zstd_dec_exec_kernel<<<(n + FD_EXEC_WARPS - 1) / FD_EXEC_WARPS, FD_EXEC_WARPS * 32, 0, st>>>(P);
         if (prof) cudaEventRecord(ctx->dec_ev[4], st);
-        b2c_zstd_dec_xxh_kernel<<<(unsigned)(((uint64_t)n * 4 + 127) / 128), 128, 0, st>>>(P);
+        if (perBlock) b2c_zstd_dec_xxh_warp_kernel<<<(n + 3) / 4, 128, 0, st>>>(P);     // few, long inputs: a warp streams each
+        else b2c_zstd_dec_xxh_kernel<<<(unsigned)(((uint64_t)n * 4 + 127) / 128), 128, 0, st>>>(P);
         if (prof) cudaEventRecord(ctx->dec_ev[5], st);
         ctx->launches += 5;
     }
@@ -1666,21 +1682,23 @@ int b2c_huf_decompress_device(b2c_ctx *ctx, int flags, const void *d_src, size_t
     cudaStream_t st = (cudaStream_t)stream;
     // Staged form (the default): table pass -> the staged zstd decoder's literal-stream kernel -> the one-warp kernel over what
     // is left (errors, unusual blocks).  B2C_DEC=onewarp, very large batches and unaligned slots keep the one-warp kernel alone.
-    const bool staged = ctx->dec_staged && nchunks <= 65536 && (dst_stride & 3) == 0;
+    const bool staged = ctx->dec_staged && nchunks <= (1u << 20) && (dst_stride & 3) == 0;
     if (staged) {
         const size_t recBytes = (((size_t)nchunks * sizeof(FdChunk)) + 255) & ~(size_t)255;
-        const size_t hufBytes = (size_t)nchunks * FD_MAXB * 2048 * sizeof(uint16_t);
+        const size_t blkBytes = (((size_t)nchunks * sizeof(FdBlock)) + 255) & ~(size_t)255;
+        const size_t hufBytes = (size_t)nchunks * 2048 * sizeof(uint16_t);
         { int r = ctx_order_begin(ctx, st); if (r) return r; }
-        int rc = grow(ctx, &ctx->d_fd, &ctx->fd_cap, recBytes + hufBytes);
+        int rc = grow(ctx, &ctx->d_fd, &ctx->fd_cap, recBytes + blkBytes + hufBytes);
         if (rc) return rc;
         P.fd = reinterpret_cast<FdChunk *>(ctx->d_fd);
-        P.fd_huf = reinterpret_cast<uint16_t *>(ctx->d_fd + recBytes);
+        P.fd_blk = reinterpret_cast<FdBlock *>(ctx->d_fd + recBytes);
+        P.fd_huf = reinterpret_cast<uint16_t *>(ctx->d_fd + recBytes + blkBytes);
         b2c_huf_dec_prep_kernel<<<grid, DEC_WARPS * 32, DEC_SMEM_BYTES, st>>>(P);
         ZstdDecParams Z;
         memset(&Z, 0, sizeof(Z));
         Z.src_base = P.src_base; Z.src_stride = src_stride; Z.src_sizes = d_src_sizes;
         Z.dst_base = P.dst_base; Z.dst_stride = dst_stride; Z.out_sizes = d_out_sizes; Z.nchunks = nchunks;
-        Z.fd = P.fd; Z.fd_huf = P.fd_huf; Z.fd_lits = P.dst_base; Z.fd_lit_stride = dst_stride;
+        Z.fd = P.fd; Z.fd_blk = P.fd_blk; Z.fd_maxb = 1; Z.fd_per_block = 0; Z.fd_huf = P.fd_huf; Z.fd_lits = P.dst_base; Z.fd_lit_stride = dst_stride;
         const unsigned groups = (nchunks + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
         b2c_zstd_dec_lit_kernel<<<(groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, st>>>(Z);
         ctx->launches += 2;

@@ -37,6 +37,7 @@ struct Huf0Params {
     // staged decompress: records of the preparation pass; state 0 = decoded by the stream kernel, FD_LEGACY = this kernel's
     // job, HUF0_STATE_ERR = the error in pad[0]
     FdChunk *fd;
+    FdBlock *fd_blk;             // one block record per input (fd_maxb = 1)
     uint16_t *fd_huf;
 };
 constexpr uint32_t HUF0_STATE_ERR = 2;
@@ -114,7 +115,7 @@ B2C_DEV void huf0_prep_block(DecWarp *dw, const Huf0Params &P, uint32_t c, unsig
         if (used == -2) { state = HUF0_STATE_ERR; err = HUF0_ERR_UNSUPPORTED; }
         else if (used < 0) { state = HUF0_STATE_ERR; err = HUF0_ERR_CORRUPT; }
         else if (n - (uint32_t)used < (1u << 18) && want > 0 && (reinterpret_cast<uintptr_t>(P.dst_base + (uint64_t)c * P.dst_stride) & 3) == 0) {
-            uint16_t *dt = P.fd_huf + (uint64_t)c * FD_MAXB * 2048;
+            uint16_t *dt = P.fd_huf + (uint64_t)c * 2048;
             for (uint32_t i = lane; i < (1u << tl); i += 32) dt[i] = dw->hufDt[i];
             state = 0;
         }
@@ -123,7 +124,7 @@ B2C_DEV void huf0_prep_block(DecWarp *dw, const Huf0Params &P, uint32_t c, unsig
     if (lane == 0) {
         ck->state = state; ck->nBlocks = 1; ck->hasCheck = 0; ck->check = 0; ck->fcs = want; ck->windowSize = 0;
         ck->pad[0] = (uint32_t)(int32_t)err;
-        FdBlock *bk = &ck->blk[0];
+        FdBlock *bk = P.fd_blk + c;
         bk->type = 2; bk->size = 0; bk->srcOff = 0; bk->litKind = 2; bk->litOff = 0; bk->litRegen = want;
         bk->nSeqs = 0; bk->bitsOff = 0; bk->bitsLen = 0; bk->tab[0] = bk->tab[1] = bk->tab[2] = 0; bk->tlog = 0; bk->seqOff = 0;
         bk->hufOff = (uint32_t)(used > 0 ? used : 0);

@@ -64,8 +64,11 @@ struct ZstdDecParams {
     // staged path (b2c_zstd_dec_staged.cuh); fd == nullptr: every input goes through the one-warp decoder, else only the
     // inputs the staged stages marked
     struct FdChunk *fd;                                                        // [nchunks]
-    uint32_t *fd_tabs;                                                         // [nchunks][FD_MAXB][FD_TAB_ENTRIES] packed entries
-    uint16_t *fd_huf;                                                          // [nchunks][FD_MAXB][2048] Huffman decoding tables
+    struct FdBlock *fd_blk;                                                    // [nchunks][fd_maxb] block records
+    uint32_t fd_maxb;                                                          // blocks per input the staged path takes (FD_MAXB, or up to FD_MAXB_LONG)
+    uint32_t fd_per_block;                                                     // 1: the literal and sequence kernels run one unit per (input, block)
+    uint32_t *fd_tabs;                                                         // [nchunks][fd_maxb][FD_TAB_ENTRIES] packed entries
+    uint16_t *fd_huf;                                                          // [nchunks][fd_maxb][2048] Huffman decoding tables
     const uint32_t *fd_const;                                                   // code maps + predefined tables (FD_CONST_*)
     uint64_t *fd_seqs;                                                         // sequence records, fd_seq_off(c)
     uint8_t *fd_lits;                                                          // decoded literals, fd_lit_off(c)

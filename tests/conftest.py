@@ -22,3 +22,13 @@ def oracle_lib():
 def emu_lib():
     import helpers
     return helpers.emu()
+
+
+@pytest.fixture(params=["per-block", "per-input"])
+def staged_form(request, emu_lib):
+    """Both forms of the staged zstd decoder under the emulator: 'per-block' (one lane / quad per (input, block), up to 32
+    blocks per input: what the device picks for few inputs -- and the emulator's default, since test batches are small) and
+    'per-input' (at most four blocks per input: what it picks for many)."""
+    emu_lib.emu_set_dec_maxb(4 if request.param == "per-input" else 0)
+    yield request.param
+    emu_lib.emu_set_dec_maxb(0)

@@ -18,6 +18,8 @@ using namespace b2c;
 extern "C" {
 
 void emu_set_lane_order(int desc) { emu::lane_order_desc = desc; }
+static int emu_dec_maxb = 0;      // 0: the device's policy; else the staged decoder's blocks-per-input (4: per input, > 4: per block)
+void emu_set_dec_maxb(int maxb) { emu_dec_maxb = maxb; }
 
 // Encode nchunks chunks laid out contiguously (chunk i = src + i*stride, size sizes[i]) with the same kernels the
 // device runs.  level 1 / 2 / 3; parse must be 0 (kept in the signature for the test helpers).  dst slots of dst_stride bytes.  Optional debug dumps (may be null; dbg_lits rows of blockmax bytes).
@@ -207,45 +209,76 @@ int emu_zstd_decode_mode(const uint8_t *src, const uint64_t *src_off, const uint
     P.dst_base = dst; P.dst_offsets = dst_off; P.dst_caps = dst_caps;
     P.out_sizes = out_sizes; P.nchunks = n; P.lit_scratch = lit.data();
     std::vector<FdChunk> fd;
+    std::vector<FdBlock> fdb;
     std::vector<uint32_t> tabs;
     std::vector<uint64_t> seqs;
     std::vector<uint8_t> lits;
     std::vector<uint16_t> hufs;
     if (mode == 0 && n > 0) {
         const uint64_t span = dst_off[n - 1] + dst_caps[n - 1];
+        // the device's choice of the staged form (b2c_api.cu launch_decode); emu_dec_maxb overrides it (tests)
+        uint32_t maxb = FD_MAXB;
+        if (n <= 4096) { maxb = 65536 / n; if (maxb > FD_MAXB_LONG) maxb = FD_MAXB_LONG; }
+        if (emu_dec_maxb) maxb = (uint32_t)emu_dec_maxb;
+        const bool perBlock = maxb > FD_MAXB;
         fd.resize(n);
         memset(fd.data(), 0xCD, sizeof(FdChunk) * (size_t)n);
-        tabs.assign((size_t)n * FD_MAXB * FD_TAB_ENTRIES, 0xCDCDCDCDu);
+        fdb.resize((size_t)n * maxb);
+        memset(fdb.data(), 0xCD, sizeof(FdBlock) * (size_t)n * maxb);
+        tabs.assign((size_t)n * maxb * FD_TAB_ENTRIES, 0xCDCDCDCDu);
         seqs.assign((size_t)(span / 3) + 2 * (size_t)n + 8, 0xCDCDCDCDCDCDCDCDull);
         lits.assign((size_t)span + 64, 0xCD);
-        P.fd = fd.data(); P.fd_tabs = tabs.data(); P.fd_seqs = seqs.data(); P.fd_lits = lits.data(); P.fd_lit_stride = 0;
+        P.fd = fd.data(); P.fd_blk = fdb.data(); P.fd_maxb = maxb; P.fd_per_block = perBlock ? 1u : 0u;
+        P.fd_tabs = tabs.data(); P.fd_seqs = seqs.data(); P.fd_lits = lits.data(); P.fd_lit_stride = 0;
         std::vector<uint32_t> fdc(FD_CONST_ENTRIES);
-        hufs.assign((size_t)n * FD_MAXB * 2048, 0xCDCD);
+        hufs.assign((size_t)n * maxb * 2048, 0xCDCD);
         emu::launch(1, 32, DEC_WARP_BYTES, [&]() { fd_init_warp(emu::dyn_smem, fdc.data(), threadIdx.x); });
         P.fd_huf = hufs.data(); P.fd_const = fdc.data();
+        const uint32_t units = perBlock ? n * maxb : n;
         emu::launch((n + 31) / 32, 32, 0, [&]() {
             const uint32_t c = blockIdx.x * 32 + threadIdx.x;
             if (c < P.nchunks) fd_scan_lane(P, c);
         });
+        if (perBlock) {
+            emu::launch((units + 31) / 32, 32, 0, [&]() {
+                const uint32_t u = blockIdx.x * 32 + threadIdx.x;
+                const uint32_t c = u / P.fd_maxb;
+                if (c < P.nchunks) fd_scan_block_lane(P, c, u % P.fd_maxb);
+            });
+            emu::launch((n + 31) / 32, 32, 0, [&]() {
+                const uint32_t c = blockIdx.x * 32 + threadIdx.x;
+                if (c < P.nchunks) fd_link_input(P, c);
+            });
+        }
         {
-            const unsigned groups = (n + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
+            const unsigned groups = (units + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
             emu::launch((groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, [&]() {
                 const unsigned w = threadIdx.x >> 5;
                 fd_lit_warp(emu::dyn_smem + w * FD_LIT_WARP_BYTES, P, blockIdx.x * FD_LIT_WARPS + w, threadIdx.x & 31);
             });
         }
-        emu::launch((n + 31) / 32, 32, 0, [&]() {
-            const uint32_t c = blockIdx.x * 32 + threadIdx.x;
-            if (c < P.nchunks) fd_seq_lane(P, c, P.fd_const + FD_CONST_BASE, P.fd_const + FD_CONST_BASE + 128);
+        emu::launch((units + 31) / 32, 32, 0, [&]() {
+            const uint32_t u = blockIdx.x * 32 + threadIdx.x;
+            const uint32_t *bl = P.fd_const + FD_CONST_BASE, *bm = P.fd_const + FD_CONST_BASE + 128;
+            if (P.fd_per_block) {
+                const uint32_t c = u / P.fd_maxb;
+                if (c < P.nchunks) fd_seq_lane(P, c, bl, bm, (int)(u % P.fd_maxb));
+            } else if (u < P.nchunks) fd_seq_lane(P, u, bl, bm);
         });
         emu::launch((n + FD_EXEC_WARPS - 1) / FD_EXEC_WARPS, FD_EXEC_WARPS * 32, 0, [&]() {
             const uint32_t c = blockIdx.x * FD_EXEC_WARPS + (threadIdx.x >> 5);
             if (c < P.nchunks) fd_exec_input(P, c, threadIdx.x & 31);
         });
-        emu::launch((unsigned)(((uint64_t)n * 4 + 127) / 128), 128, 0, [&]() {
-            const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
-            fd_xxh_quad(P, gt >> 2, gt & 3, (threadIdx.x & 31) & ~3u);
-        });
+        if (perBlock)
+            emu::launch((n + 3) / 4, 128, 4 * 2 * XXH_TILE, [&]() {
+                const uint32_t c = blockIdx.x * 4 + (threadIdx.x >> 5);
+                if (c < P.nchunks) fd_xxh_warp(P, c, emu::dyn_smem + (threadIdx.x >> 5) * 2 * XXH_TILE, threadIdx.x & 31);
+            });
+        else
+            emu::launch((unsigned)(((uint64_t)n * 4 + 127) / 128), 128, 0, [&]() {
+                const unsigned gt = blockIdx.x * blockDim.x + threadIdx.x;
+                fd_xxh_quad(P, gt >> 2, gt & 3, (threadIdx.x & 31) & ~3u);
+            });
         if (staged_out) for (uint32_t i = 0; i < n; i++) staged_out[i] = fd[i].state == 0;
     }
     emu::launch(grid, DEC_WARPS * 32, DEC_SMEM_BYTES, [&]() {
@@ -378,10 +411,12 @@ int emu_huf_decompress(const uint8_t *src, uint64_t stride, const uint32_t *size
     P.dst_sizes = dst_sizes; P.out_sizes = out_sizes; P.nchunks = n; P.flags = four ? HUF0_FLAG_4X : 0;
     std::vector<FdChunk> fd(n);
     memset(fd.data(), 0xCD, sizeof(FdChunk) * (size_t)n);
-    std::vector<uint16_t> hufs((size_t)n * FD_MAXB * 2048, 0xCDCD);
+    std::vector<FdBlock> fdb(n);
+    memset(fdb.data(), 0xCD, sizeof(FdBlock) * (size_t)n);
+    std::vector<uint16_t> hufs((size_t)n * 2048, 0xCDCD);
     const bool staged = (dst_stride & 3) == 0 && n > 0;
     if (staged) {
-        P.fd = fd.data(); P.fd_huf = hufs.data();
+        P.fd = fd.data(); P.fd_blk = fdb.data(); P.fd_huf = hufs.data();
         emu::launch(1, DEC_WARPS * 32, DEC_SMEM_BYTES, [&]() {
             const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
             DecWarp *dw = reinterpret_cast<DecWarp *>(emu::dyn_smem + w * DEC_WARP_BYTES);
@@ -390,7 +425,7 @@ int emu_huf_decompress(const uint8_t *src, uint64_t stride, const uint32_t *size
         ZstdDecParams Z;
         memset(&Z, 0, sizeof(Z));
         Z.src_base = src; Z.src_stride = stride; Z.src_sizes = sizes; Z.dst_base = dst; Z.dst_stride = dst_stride;
-        Z.out_sizes = out_sizes; Z.nchunks = n; Z.fd = fd.data(); Z.fd_huf = hufs.data(); Z.fd_lits = dst; Z.fd_lit_stride = dst_stride;
+        Z.out_sizes = out_sizes; Z.nchunks = n; Z.fd = fd.data(); Z.fd_blk = fdb.data(); Z.fd_maxb = 1; Z.fd_huf = hufs.data(); Z.fd_lits = dst; Z.fd_lit_stride = dst_stride;
         const unsigned groups = (n + FD_LIT_GROUP - 1) / FD_LIT_GROUP;
         emu::launch((groups + FD_LIT_WARPS - 1) / FD_LIT_WARPS, FD_LIT_WARPS * 32, FD_LIT_WARPS * FD_LIT_WARP_BYTES, [&]() {
             const unsigned w = threadIdx.x >> 5;

@@ -30,7 +30,7 @@ def _mutations(blob, rng, count):
     return out
 
 
-def test_zstd_decoder_mutations(emu_lib, oracle_lib):
+def test_zstd_decoder_mutations(emu_lib, oracle_lib, staged_form):
     rng = np.random.default_rng(2024)
     tw = H.golden("twain.txt")
     sources = [tw[:3000], tw[1000:1000 + 70000], H.golden("html.txt")[:20000], bytes(5000), b"ab" * 4000,

@@ -159,3 +159,41 @@ def test_frames_unaligned_inputs(emu_lib):
         assert a == b
     for data, fr in zip(inputs, a):
         assert H.libzstd_decode(fr, len(data)) == data
+
+
+def test_long_frames_decode_block_parallel(emu_lib):
+    """Frames with more than four blocks on the staged decoder: in its per-block form (one lane / quad per (input, block),
+    the form the device picks for few inputs) frame mode's own output stays on the staged path -- its blocks never use a
+    repeat offset of an earlier block -- while the per-input form (at most four blocks) hands it to the one-warp decoder.
+    Both give the input back; single-block frames are staged either way.  libzstd frames, which do use repeat offsets across
+    blocks, are decoded correctly whichever path takes them."""
+    from emu_util import emu_decode
+    tw = H.golden("twain.txt")
+    inputs = [tw, tw[:49152 * 6 + 5], tw[:1000], bytes(200000) + tw[:100000]]
+    frames = emu_encode_frames(emu_lib, inputs, level=1, dump=False)[0]
+    z = H.libzstd()
+    import ctypes
+    big = tw[:300000]
+    cap = z.ZSTD_compressBound(len(big))
+    buf = ctypes.create_string_buffer(cap)
+    zn = z.ZSTD_compress(buf, cap, big, len(big), 3)
+    frames_all = frames + [buf.raw[:zn]]
+    inputs_all = inputs + [big]
+    caps = [len(x) + 16 for x in inputs_all]
+    try:
+        emu_lib.emu_set_dec_maxb(32)
+        staged = []
+        sizes, outs = emu_decode(emu_lib, frames_all, caps, staged=staged)
+        assert outs == inputs_all, sizes
+        assert staged[:4] == [1, 1, 1, 1], staged          # 8, 7, 1 and 7 blocks: all staged, block-parallel
+        emu_lib.emu_set_dec_maxb(4)
+        staged4 = []
+        sizes, outs = emu_decode(emu_lib, frames_all, caps, staged=staged4)
+        assert outs == inputs_all, sizes
+        assert staged4[:4] == [0, 0, 1, 0], staged4
+        for desc in (1,):
+            emu_lib.emu_set_dec_maxb(32)
+            sizes, outs = emu_decode(emu_lib, frames_all, caps, desc=desc)
+            assert outs == inputs_all
+    finally:
+        emu_lib.emu_set_dec_maxb(0)

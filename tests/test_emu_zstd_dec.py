@@ -17,7 +17,7 @@ def _pairs(zf):
             yield nm, zf.read(nm), zf.read(nm[:-4])
 
 
-def test_emu_decoder_zip_subset(emu_lib):
+def test_emu_decoder_zip_subset(emu_lib, staged_form):
     # zstd/decoder_test.go:201-216 TestNewDecoder
     zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_decoder.zip"))
     items = sorted(_pairs(zf), key=lambda it: len(it[2]))[:24]      # the emulator is slow: the 24 smallest pairs
@@ -43,7 +43,7 @@ def test_emu_good_zip(emu_lib, oracle_lib):
         assert r == len(want) and got == want, nm
 
 
-def test_emu_bad_zip(emu_lib, oracle_lib):
+def test_emu_bad_zip(emu_lib, oracle_lib, staged_form):
     # zstd/decoder_test.go:409-455 TestNewDecoderBad: every input must be rejected, as the oracle does
     zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_bad.zip"))
     comps, names = [], []
@@ -92,7 +92,7 @@ def test_emu_decode_own_frames(emu_lib):
     assert staged == [1] * len(frames)
 
 
-def test_emu_decode_staged_levels_and_marks(emu_lib):
+def test_emu_decode_staged_levels_and_marks(emu_lib, staged_form):
     # frames of every encoder level through the staged kernels (reversed lane order too); a flipped content checksum, a
     # flipped payload bit and a short destination are marked by a staged stage and answered by the one-warp decoder
     # exactly as it answers them alone

@@ -154,3 +154,10 @@ if "--frames-decode" in sys.argv:
     gms = g0.elapsed_time(g1) / 2
     assert bool((dres == fs).all()) and torch.equal(dout.view(-1), src[: nf * fs])
     print("  decode of the %d multi-block frames (%d KiB each) %.3f ms = %.1f GB/s (output bytes)" % (nf, fs >> 10, gms, nf * fs / gms / 1e6))
+    dec.profile(True)
+    for _ in range(2):
+        dec.decode_device(fdst, fsz32, src_offsets=foff, dst=dout, dst_cap=fs, out_sizes=dres)
+    pm = dec.profile_read()
+    dec.profile(False)
+    print("  frame decode per step: " + "  ".join("%s %.3f" % (k.replace("b2c_zstd_", "").replace("_kernel", ""), v / 2) for k, v in pm.items())
+          + "   staged inputs: %d of %d" % (dec.staged_count(nf), nf))
