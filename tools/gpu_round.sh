@@ -16,7 +16,7 @@ SECONDS=0
 timeout 900 python bench.py > $O/bench_L1.json 2> $O/bench_L1.err; tail -1 $O/bench_L1.json | cut -c1-600; echo "bench default took ${SECONDS}s"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; tail -1 $O/bench_ref.json | cut -c1-300
 timeout 900 python bench.py --level 2 --no-cpu-baseline > $O/bench_L2.json 2> $O/bench_L2.err; tail -1 $O/bench_L2.json | cut -c1-400
-timeout 600 ncu --kernel-name regex:b2c_ --metrics gpu__time_duration.sum --clock-control none -c 160 --csv --log-file $O/launches.csv \
+timeout 600 ncu --kernel-name regex:b2c_ --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/launches.csv \
    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/bench_under_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:b2c_lz_parse1 -s 2 -c 1 -f -o $O/prof_parse1 \
    python tools/enc_times.py 1 0.5 > $O/ncu_parse1.log 2>&1
