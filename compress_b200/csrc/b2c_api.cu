@@ -62,6 +62,7 @@ struct b2c_ctx {
     cudaStream_t dec_aux = nullptr;                        // staged decode: the literal kernel runs beside the sequence walk
     uint8_t *d_fr = nullptr; size_t fr_cap = 0;            // frame mode: block / frame tables, block slots (grown on demand)
     uint8_t *d_fr_io = nullptr; size_t fr_io_cap = 0;      // frame mode, host-buffer call: staged input | packed output | results
+    uint8_t *d_s2d = nullptr; size_t s2d_cap = 0;          // staged S2 block decode: block heads + element records
     uint8_t *d_s2s = nullptr; size_t s2s_cap = 0;          // S2 stream calls: block slots, sizes, checksums, scan, tables (grown on demand)
     uint8_t *d_s2s_io = nullptr; size_t s2s_io_cap = 0;    //   host-buffer calls: staged input | output
     uint32_t *d_counters = nullptr; uint32_t counter_seq = 0;   // chunk counters of the persistent parse kernels (one per launch, rotating)
@@ -296,7 +297,7 @@ void b2c_ctx_destroy(b2c_ctx *ctx) {
     cudaFreeHost(ctx->h_stg_in); cudaFreeHost(ctx->h_stg_out);
     cudaFree(ctx->d_fd); cudaFree(ctx->d_fd_const); cudaFree(ctx->d_fd_seq); cudaFree(ctx->d_fd_lit);
     cudaFree(ctx->d_dec_lit); cudaFree(ctx->d_dec_in); cudaFree(ctx->d_dec_out); cudaFree(ctx->d_dec_meta);
-    cudaFree(ctx->d_fr); cudaFree(ctx->d_fr_io); cudaFree(ctx->d_counters); cudaFree(ctx->d_s2s); cudaFree(ctx->d_s2s_io);
+    cudaFree(ctx->d_fr); cudaFree(ctx->d_fr_io); cudaFree(ctx->d_counters); cudaFree(ctx->d_s2s); cudaFree(ctx->d_s2s_io); cudaFree(ctx->d_s2d);
     cudaFree(ctx->d_scratch); cudaFree(ctx->d_work[0]); cudaFree(ctx->d_work[1]); cudaFree(ctx->d_pool[0]); cudaFree(ctx->d_pool[1]);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy); cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_packed);
     cudaFree(ctx->d_sizes); cudaFree(ctx->d_offsets); cudaFree(ctx->d_src_sizes);
@@ -1337,6 +1338,8 @@ int b2c_s2_encode_device(b2c_ctx *ctx, int level, int flags, const void *d_src, 
                             (cudaStream_t)stream);
 }
 
+static int launch_s2_decode(b2c_ctx *ctx, S2DecParams &P, uint64_t span, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------ S2 / Snappy streams
 // s2.Writer.EncodeBuffer / s2.Reader for whole buffers (s2/writer.go:357-470, s2/reader.go:249-420): the framing format
 // around the block codecs -- stream identifier, one chunk per block with the masked CRC32-C of its uncompressed bytes.
@@ -1528,20 +1531,45 @@ int b2c_s2_decode_stream(b2c_ctx *ctx, const void *src, size_t n, void *dst, siz
     P.src_base = B + oIn; P.src_offsets = (const uint64_t *)(B + oSrcOff); P.src_sizes = (const uint32_t *)(B + oSrcSz);
     P.dst_base = B + oOut; P.dst_offsets = (const uint64_t *)(B + oDstOff); P.dst_caps = (const uint32_t *)(B + oCaps);
     P.out_sizes = (int64_t *)(B + oRes); P.nchunks = nb;
-    unsigned grid = (nb + S2DEC_WARPS - 1) / S2DEC_WARPS;
-    if (grid > (unsigned)ctx->sm_count * 16) grid = (unsigned)ctx->sm_count * 16;
-    b2c_s2_decode_kernel<<<grid, S2DEC_WARPS * 32, 0, st>>>(P);
+    { int r = launch_s2_decode(ctx, P, n, st); if (r) return r; }
     unsigned g2 = (nb + S2S_WARPS - 1) / S2S_WARPS;
     if (g2 > (unsigned)ctx->sm_count * 16) g2 = (unsigned)ctx->sm_count * 16;
     b2c_s2_stream_verify_kernel<<<g2, S2S_WARPS * 32, 0, st>>>((const S2StreamBlock *)(B + oBlk), B + oIn, B + oOut,
                                                                 (const int64_t *)(B + oRes), (int32_t *)(B + oStat), nb);
-    ctx->launches += 2;
+    ctx->launches += 1;
     std::vector<int32_t> stat(nb);
     CK(cudaMemcpyAsync(stat.data(), B + oStat, 4 * (size_t)nb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     for (uint32_t i = 0; i < nb; i++)
         if (stat[i]) return stat[i] == -4 ? B2C_ERR_CORRUPT : stat[i];      // (a block longer than its declared length is corrupt)
     CK(cudaMemcpy(dst, B + oOut, total, cudaMemcpyDeviceToHost));
+    return B2C_OK;
+}
+
+// S2 block decode launch.  span = bytes of the input layout (blocks lie inside [0, span) at increasing, non-overlapping offsets) or
+// 0 when the host does not know it.  With a span the staged form runs first (tag walk one lane per block, execution one warp per
+// block); the one-warp kernel then takes what they left (large or unusual blocks, errors).
+static int launch_s2_decode(b2c_ctx *ctx, S2DecParams &P, uint64_t span, cudaStream_t st) {
+    const uint32_t n = P.nchunks;
+    const bool staged = ctx->dec_staged && span > 0 && span <= ((uint64_t)8 << 30);
+    if (staged) {
+        const size_t headBytes = (((size_t)n * sizeof(S2Head)) + 255) & ~(size_t)255;
+        const size_t recBytes = ((size_t)(span / 4) + n + 16) * sizeof(uint64_t);
+        { int r = ctx_order_begin(ctx, st); if (r) return r; }
+        int rc = grow(ctx, &ctx->d_s2d, &ctx->s2d_cap, headBytes + recBytes);
+        if (rc) return rc;
+        P.heads = reinterpret_cast<S2Head *>(ctx->d_s2d);
+        P.recs = reinterpret_cast<uint64_t *>(ctx->d_s2d + headBytes);
+        b2c_s2_walk_kernel<<<(n + 31) / 32, 32, 0, st>>>(P);
+        b2c_s2_exec_kernel<<<(n + S2DEC_WARPS - 1) / S2DEC_WARPS, S2DEC_WARPS * 32, 0, st>>>(P);
+        ctx->launches += 2;
+    }
+    unsigned grid = (n + S2DEC_WARPS - 1) / S2DEC_WARPS, maxGrid = (unsigned)ctx->sm_count * 16;
+    if (grid > maxGrid) grid = maxGrid;
+    b2c_s2_decode_kernel<<<grid, S2DEC_WARPS * 32, 0, st>>>(P);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    if (staged) return ctx_order_end(ctx, st);
     return B2C_OK;
 }
 
@@ -1557,12 +1585,7 @@ int b2c_s2_decode_device(b2c_ctx *ctx, const void *d_src, size_t src_stride, con
     P.src_base = (const uint8_t *)d_src; P.src_stride = src_stride; P.src_offsets = d_src_offsets; P.src_sizes = d_src_sizes;
     P.dst_base = (uint8_t *)d_dst; P.dst_stride = dst_stride; P.dst_offsets = d_dst_offsets; P.dst_cap = dst_cap;
     P.out_sizes = d_out_sizes; P.nchunks = nchunks;
-    unsigned grid = (nchunks + S2DEC_WARPS - 1) / S2DEC_WARPS, maxGrid = (unsigned)ctx->sm_count * 16;
-    if (grid > maxGrid) grid = maxGrid;
-    b2c_s2_decode_kernel<<<grid, S2DEC_WARPS * 32, 0, (cudaStream_t)stream>>>(P);
-    ctx->launches += 1;
-    CK(cudaGetLastError());
-    return B2C_OK;
+    return launch_s2_decode(ctx, P, d_src_offsets ? 0 : (uint64_t)nchunks * src_stride, (cudaStream_t)stream);
 }
 
 // Host-buffer batches for the block API (s2.Encode / s2.EncodeSnappy / s2.Decode per element).  Inputs are packed
@@ -1612,12 +1635,7 @@ static int s2_host_batch(b2c_ctx *ctx, bool encode, int level, int flags, const 
         P.src_base = ctx->d_dec_in; P.src_offsets = dm; P.src_sizes = d_ss;
         P.dst_base = ctx->d_dec_out; P.dst_offsets = dm + n; P.dst_caps = d_ss + n;
         P.out_sizes = d_res; P.nchunks = (uint32_t)n;
-        unsigned grid = ((unsigned)n + S2DEC_WARPS - 1) / S2DEC_WARPS, maxGrid = (unsigned)ctx->sm_count * 16;
-        if (grid > maxGrid) grid = maxGrid;
-        b2c_s2_decode_kernel<<<grid, S2DEC_WARPS * 32, 0, st>>>(P);
-        ctx->launches += 1;
-        CK(cudaGetLastError());
-        rc = B2C_OK;
+        rc = launch_s2_decode(ctx, P, inb, st);
     }
     if (rc) return rc;
     CK(cudaMemcpyAsync(sizes_out, d_res, n * sizeof(int64_t), cudaMemcpyDeviceToHost, st));

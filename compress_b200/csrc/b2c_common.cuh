@@ -323,6 +323,73 @@ B2C_DEV void coop_copy(uint8_t *d, const uint8_t *s, uint32_t sz, unsigned tid, 
     for (uint32_t i = head + body + tid; i < sz; i += nthreads) d[i] = s[i];
 }
 
+// Execute up to 32 matches (lane i: copy myML bytes from out + myDst - myMO to out + myDst; mine = this lane has one), whose
+// destinations increase with the lane: in waves -- a match runs once its source ends before the destination of every pending
+// match; short ones as per-lane word copies, long ones (>= 64 bytes) by the whole warp.  All lanes call.
+B2C_DEV void lz_exec_match_waves(uint8_t *out, bool mine, uint32_t myDst, uint32_t myMO, uint32_t myML, unsigned lane) {
+    // ---- matches in waves: a match runs once its source ends before the destination of every pending match
+    bool pending = mine;
+    const uint32_t srcEnd = (myMO >= myML) ? myDst - myMO + myML : myDst;   // self-overlap: source ends at dst
+    for (;;) {
+        const uint32_t minDst = __reduce_min_sync(FULLMASK, pending ? myDst : 0xffffffffu);
+        if (minDst == 0xffffffffu) break;
+        const bool ready = pending && (srcEnd <= minDst || myDst == minDst);
+        const bool longM = ready && myML >= 64;
+        if (ready && !longM) {
+            const uint8_t *from = out + myDst - myMO;
+            uint8_t *to = out + myDst;
+            if (myMO >= 8 || myMO >= myML) {
+                // Word copy: bytes up to the destination's 4-byte boundary, then aligned destination words whose
+                // source words are assembled from aligned loads with a funnel shift (one new load per word), then
+                // the last bytes.  A source word is read at most 7 bytes ahead of the byte being produced, so with a
+                // distance of 8 or more (or no overlap at all) everything it holds that is used is final.
+                uint32_t k = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(to) & 3)) & 3);
+                if (k > myML) k = myML;
+                for (uint32_t q = 0; q < k; q++) to[q] = from[q];
+                const uint32_t nw = (myML - k) >> 2;
+                if (nw) {
+                    const uint8_t *f = from + k;
+                    const uint32_t fa = (uint32_t)(reinterpret_cast<uintptr_t>(f) & 3), sh = fa * 8;
+                    const uint32_t *fw = reinterpret_cast<const uint32_t *>(f - fa);
+                    uint32_t *tw = reinterpret_cast<uint32_t *>(to + k);
+                    if (sh == 0) {
+                        for (uint32_t i = 0; i < nw; i++) tw[i] = fw[i];
+                    } else {
+                        uint32_t w0 = fw[0];
+                        for (uint32_t i = 0; i < nw; i++) {
+                            const uint32_t w1 = fw[i + 1];
+                            tw[i] = __funnelshift_r(w0, w1, sh);
+                            w0 = w1;
+                        }
+                    }
+                    k += nw * 4;
+                }
+                for (; k < myML; k++) to[k] = from[k];
+            } else {
+                for (uint32_t k = 0; k < myML; k++) to[k] = from[k];
+            }
+        }
+        for (unsigned m = __ballot_sync(FULLMASK, longM); m; m &= m - 1) {
+            const int f = __ffs((int)m) - 1;
+            const uint32_t fd = __shfl_sync(FULLMASK, myDst, f);
+            const uint32_t fo = __shfl_sync(FULLMASK, myMO, f), fn = __shfl_sync(FULLMASK, myML, f);
+            const uint8_t *from = out + fd - fo;
+            if (fo >= fn || fo >= 32) {
+                for (uint32_t k0 = 0; k0 < fn; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    if (k < fn) out[fd + k] = from[k];
+                    if (fo < fn) __syncwarp();
+                }
+            } else {
+                for (uint32_t k = lane; k < fn; k += 32) out[fd + k] = from[k % fo];
+            }
+            __syncwarp();
+        }
+        if (ready) pending = false;
+        __syncwarp();
+    }
+}
+
 // streaming (evict-first) 8-byte store: data another kernel reads once should not push reused lines out of L2
 B2C_DEV void st_stream64(uint64_t *p, uint64_t v) {
 #ifndef B2C_EMU

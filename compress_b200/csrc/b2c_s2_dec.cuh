@@ -14,11 +14,15 @@ namespace b2c {
 constexpr int S2DEC_WARPS = 4;
 enum { S2_ERR_DST = -4, S2_ERR_CORRUPT = -5 };
 
+struct S2Head { uint32_t state, nrec, firstLit, dlen; };     // staged form: per block; state 0 = the staged kernels' job, 1 = the one-warp kernel's
 struct S2DecParams {
     const uint8_t *src_base; uint64_t src_stride; const uint64_t *src_offsets; const uint32_t *src_sizes;
     uint8_t *dst_base; uint64_t dst_stride; const uint64_t *dst_offsets; const uint32_t *dst_caps; uint32_t dst_cap;
     int64_t *out_sizes;      // decoded bytes or negative error
     uint32_t nchunks;
+    // staged form (nullptr: every block goes through the one-warp kernel)
+    S2Head *heads;           // [nchunks]
+    uint64_t *recs;          // block c: s2_rec_off(P, c), capacity src_sizes[c] / 4 + 1 records
 };
 
 B2C_DEV int64_t s2_decode_block(const uint8_t *src, uint32_t slen, uint8_t *dst, uint32_t cap, unsigned lane) {
@@ -109,6 +113,194 @@ B2C_DEV int64_t s2_decode_block(const uint8_t *src, uint32_t slen, uint8_t *dst,
     return (int64_t)dlen;
 }
 
+// ------------------------------------------------------------------------------------------------ staged form
+// The one-warp decoder above walks the tags with all 32 lanes in lockstep: the walk is serial, so 31 lanes idle through
+// it.  The staged form splits the two halves of s2Decode (s2/decode_other.go:22-287) the way the staged zstd decoder does:
+//   walk  one LANE per block: the tag stream -> one 8-byte record per element: literal length | copy length << 17 |
+//         offset << 34 | gap << 51, where an element is "a literal run (possibly empty) followed by a copy (possibly none)"
+//         and gap = bytes between the end of this element's literal bytes and the start of the next element's (the copy tag
+//         and the next literal header), so a prefix sum places every literal run in the input
+//   exec  one WARP per block: 32 elements per step, places by warp scans, literal bytes gathered from the step's window of
+//         the input (staged in shared memory), copies in dependency waves (lz_exec_match_waves)
+// Blocks of at most 64 KiB decoded / 128 KiB encoded with at most size/4 + 1 elements; anything else, and anything a stage
+// does not like, is left to the one-warp kernel (state 1), which also produces the error values.
+constexpr uint32_t S2S_MAX_DLEN = 65536, S2S_MAX_SLEN = 1u << 17, S2S_WIN = 1024;
+B2C_DEV const uint8_t *s2_src(const S2DecParams &P, uint32_t c) { return P.src_base + (P.src_offsets ? P.src_offsets[c] : (uint64_t)c * P.src_stride); }
+B2C_DEV uint64_t s2_rec_off(const S2DecParams &P, uint32_t c) {
+    return (P.src_offsets ? P.src_offsets[c] : (uint64_t)c * P.src_stride) / 4 + c;
+}
+B2C_DEV uint64_t s2_rec_pack(uint32_t ll, uint32_t ml, uint32_t off, uint32_t gap) {
+    return (uint64_t)ll | ((uint64_t)ml << 17) | ((uint64_t)off << 34) | ((uint64_t)gap << 51);
+}
+B2C_DEV void s2s_walk_lane(const S2DecParams &P, uint32_t c) {
+    const uint8_t *src = s2_src(P, c);
+    const uint32_t slen = P.src_sizes[c], cap = P.dst_caps ? P.dst_caps[c] : P.dst_cap;
+    S2Head *hd = P.heads + c;
+    uint64_t *recs = P.recs + s2_rec_off(P, c);
+    const uint32_t recCap = slen / 4 + 1;
+#define S2LEG() do { hd->state = 1; return; } while (0)
+    if (slen == 0 || slen > S2S_MAX_SLEN) S2LEG();
+    uint64_t v = 0;
+    uint32_t s = 0, shift = 0;
+    for (;;) {
+        if (s >= slen || s >= 5) S2LEG();
+        const uint8_t b = src[s++];
+        v |= (uint64_t)(b & 0x7f) << shift;
+        if (b < 0x80) break;
+        shift += 7;
+    }
+    if (v > S2S_MAX_DLEN || v > cap) S2LEG();
+    const uint32_t dlen = (uint32_t)v;
+    // Element i = [literal run of ll_i bytes at L_i][copy].  L_i = where its literal bytes start (the position of its copy tag
+    // when it has none); gap_i = L_(i+1) - (L_i + ll_i) = bytes of its copy tag + bytes of the next element's literal header.
+    uint32_t nrec = 0, offset = 0;
+    bool open = false; uint32_t openLL = 0;           // an element whose literal run has been read and that awaits its copy
+    bool havePrev = false; uint64_t prevRec = 0; uint32_t prevTb = 0;
+    bool firstSet = false; uint32_t firstLit = s;
+#define S2_EMIT(ll_, ml_, off_, tb_)                                                       \
+    do {                                                                                   \
+        if (nrec >= recCap) S2LEG();                                                       \
+        prevRec = s2_rec_pack((ll_), (ml_), (off_), 0); recs[nrec++] = prevRec;            \
+        prevTb = (tb_); havePrev = true;                                                   \
+    } while (0)
+#define S2_START(hb_, pos_)                                                                \
+    do {                                                                                   \
+        if (havePrev) { recs[nrec - 1] = prevRec | ((uint64_t)(prevTb + (hb_)) << 51); havePrev = false; } \
+        if (!firstSet) { firstLit = (pos_); firstSet = true; }                             \
+    } while (0)
+    while (s < slen) {
+        const uint32_t tag = src[s];
+        if ((tag & 3) == 0) {
+            uint32_t x = tag >> 2, hb;
+            if (x < 60) hb = 1;
+            else if (x == 60) { hb = 2; if (s + hb > slen) S2LEG(); x = src[s + 1]; }
+            else if (x == 61) { hb = 3; if (s + hb > slen) S2LEG(); x = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8; }
+            else if (x == 62) { hb = 4; if (s + hb > slen) S2LEG(); x = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8 | (uint32_t)src[s + 3] << 16; }
+            else { hb = 5; if (s + hb > slen) S2LEG(); x = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8 | (uint32_t)src[s + 3] << 16 | (uint32_t)src[s + 4] << 24; }
+            if (x >= S2S_MAX_DLEN) S2LEG();
+            const uint32_t length = x + 1;
+            if (length > slen - (s + hb)) S2LEG();
+            if (open) S2_EMIT(openLL, 0, 0, 0);          // two literal runs in a row: the first is an element without a copy
+            S2_START(hb, s + hb);
+            open = true; openLL = length;
+            s += hb + length;
+            continue;
+        }
+        uint32_t length, tb;
+        if ((tag & 3) == 1) {
+            tb = 2;
+            if (s + tb > slen) S2LEG();
+            length = (tag >> 2) & 7;
+            const uint32_t toffset = ((tag & 0xe0) << 3) | src[s + 1];
+            if (toffset == 0) {            // repeat: the last offset, extended length codes (decode_other.go:74-101)
+                if (length == 5) { tb = 3; if (s + tb > slen) S2LEG(); length = (uint32_t)src[s + 2] + 4; }
+                else if (length == 6) { tb = 4; if (s + tb > slen) S2LEG(); length = ((uint32_t)src[s + 2] | (uint32_t)src[s + 3] << 8) + (1 << 8); }
+                else if (length == 7) { tb = 5; if (s + tb > slen) S2LEG(); length = ((uint32_t)src[s + 2] | (uint32_t)src[s + 3] << 8 | (uint32_t)src[s + 4] << 16) + (1 << 16); }
+            } else offset = toffset;
+            length += 4;
+        } else if ((tag & 3) == 2) {
+            tb = 3;
+            if (s + tb > slen) S2LEG();
+            length = 1 + (tag >> 2);
+            offset = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8;
+        } else {
+            tb = 5;
+            if (s + tb > slen) S2LEG();
+            length = 1 + (tag >> 2);
+            offset = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8 | (uint32_t)src[s + 3] << 16 | (uint32_t)src[s + 4] << 24;
+        }
+        if (offset == 0 || offset > S2S_MAX_DLEN || length > S2S_MAX_DLEN) S2LEG();
+        if (!open) S2_START(0, s);                       // an element without a literal run: L = its copy tag
+        S2_EMIT(open ? openLL : 0u, length, offset, tb);
+        open = false;
+        s += tb;
+    }
+    if (open) S2_EMIT(openLL, 0, 0, 0);                  // trailing literal run
+#undef S2_EMIT
+#undef S2_START
+    hd->state = 0; hd->nrec = nrec; hd->firstLit = firstLit; hd->dlen = dlen;
+#undef S2LEG
+}
+
+// stg: S2S_WIN + 8 bytes of shared memory for this warp
+B2C_DEV void s2s_exec_warp(const S2DecParams &P, uint32_t c, uint8_t *stg, unsigned lane) {
+    S2Head *hd = P.heads + c;
+    if (hd->state != 0) return;
+    const uint8_t *src = s2_src(P, c);
+    uint8_t *out = P.dst_base + (P.dst_offsets ? P.dst_offsets[c] : (uint64_t)c * P.dst_stride);
+    const uint32_t slen = P.src_sizes[c], nrec = hd->nrec, dlen = hd->dlen;
+    const uint64_t *recs = P.recs + s2_rec_off(P, c);
+    uint32_t d = 0, litSrc = hd->firstLit;
+    bool bad = false;
+    uint64_t nextRec = lane < nrec ? recs[lane] : 0;
+    for (uint32_t base = 0; base < nrec; base += 32) {
+        const uint32_t cnt = nrec - base < 32 ? nrec - base : 32;
+        const bool mine = lane < cnt;
+        const uint64_t rec = mine ? nextRec : 0;
+        if (base + 32 < nrec) nextRec = (base + 32 + lane < nrec) ? recs[base + 32 + lane] : 0;
+        const uint32_t myLL = (uint32_t)(rec & 0x1ffff), myML = (uint32_t)((rec >> 17) & 0x1ffff), myMO = (uint32_t)((rec >> 34) & 0x1ffff);
+        const uint32_t myGap = (uint32_t)((rec >> 51) & 15);
+        const uint32_t lenIncl = warp_scan_incl(myLL + myML), llIncl = warp_scan_incl(myLL), srcIncl = warp_scan_incl(myLL + myGap);
+        const uint32_t myOut = d + (lenIncl - (myLL + myML)), myDst = myOut + myLL;
+        const uint32_t myLit = litSrc + (srcIncl - (myLL + myGap));
+        bool err = false;
+        if (mine) {
+            if (lenIncl > dlen - d) err = true;                          // (d <= dlen always)
+            else if (myLL > slen || myLit > slen - myLL) err = true;
+            else if (myML && (myMO == 0 || myMO > myDst)) err = true;
+        }
+        if (__any_sync(FULLMASK, err)) { bad = true; break; }
+        // ---- literal runs: every literal byte of the step finds its element by a binary search over the lanes' counts; the
+        // bytes come from the step's window of the input [litSrc, litSrc + sum(ll + gap)), staged in shared memory when it is
+        // small enough (else straight from global memory)
+        {
+            const uint32_t totLit = __shfl_sync(FULLMASK, llIncl, 31);
+            const uint32_t win = __shfl_sync(FULLMASK, srcIncl, 31);
+            const bool useS = win <= S2S_WIN && totLit > 0;
+            if (useS) {
+                const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src + litSrc) & 3);
+                const uint32_t *gw = reinterpret_cast<const uint32_t *>(src + litSrc - mis);
+                const uint32_t nw = (win + mis + 3) >> 2;                 // aligned words holding window bytes
+                uint32_t *sw = reinterpret_cast<uint32_t *>(stg);
+                for (uint32_t i = lane; i < nw; i += 32) sw[i] = gw[i];
+                __syncwarp();
+                const uint8_t *wb = stg + mis;                             // window byte j at wb[j]
+                for (uint32_t k0 = 0; k0 < totLit; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    uint32_t owner = 0;
+#pragma unroll
+                    for (int st = 16; st > 0; st >>= 1) {
+                        const uint32_t cc = owner + st - 1;
+                        const uint32_t v = __shfl_sync(FULLMASK, llIncl, (int)(cc & 31));
+                        if (cc < 32 && v <= k) owner += st;
+                    }
+                    const uint32_t oIncl = __shfl_sync(FULLMASK, llIncl, (int)(owner & 31)), oLL = __shfl_sync(FULLMASK, myLL, (int)(owner & 31));
+                    const uint32_t oOut = __shfl_sync(FULLMASK, myOut, (int)(owner & 31)), oLit = __shfl_sync(FULLMASK, myLit, (int)(owner & 31));
+                    if (k < totLit) { const uint32_t j = k - (oIncl - oLL); out[oOut + j] = wb[oLit - litSrc + j]; }
+                }
+                __syncwarp();
+            } else if (totLit) {
+                // long runs: each by the whole warp
+                for (int l = 0; l < 32; l++) {
+                    const uint32_t n = __shfl_sync(FULLMASK, myLL, l), from = __shfl_sync(FULLMASK, myLit, l), to = __shfl_sync(FULLMASK, myOut, l);
+                    for (uint32_t i = lane; i < n; i += 32) out[to + i] = src[from + i];
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        lz_exec_match_waves(out, mine && myML != 0, myDst, myMO, myML, lane);
+        d += __shfl_sync(FULLMASK, lenIncl, 31);
+        litSrc += __shfl_sync(FULLMASK, srcIncl, 31);
+    }
+    if (!bad && d != dlen) bad = true;
+    __syncwarp();
+    if (lane == 0) {
+        if (bad) hd->state = 1;
+        else P.out_sizes[c] = (int64_t)dlen;
+    }
+}
+
 B2C_DEV void s2_decode_warp(const S2DecParams &P, uint32_t warpGlobal, uint32_t totalWarps) {
     const unsigned lane = threadIdx.x & 31;
     for (uint32_t c = warpGlobal; c < P.nchunks; c += totalWarps) {
@@ -116,6 +308,7 @@ B2C_DEV void s2_decode_warp(const S2DecParams &P, uint32_t warpGlobal, uint32_t 
         uint8_t *dst = P.dst_base + (P.dst_offsets ? P.dst_offsets[c] : (uint64_t)c * P.dst_stride);
         const uint32_t cap = P.dst_caps ? P.dst_caps[c] : P.dst_cap;
         __syncwarp();
+        if (P.heads && P.heads[c].state == 0) continue;       // decoded by the staged kernels
         const int64_t r = s2_decode_block(src, P.src_sizes[c], dst, cap, lane);
         __syncwarp();
         if (lane == 0) P.out_sizes[c] = r;
@@ -123,6 +316,15 @@ B2C_DEV void s2_decode_warp(const S2DecParams &P, uint32_t warpGlobal, uint32_t 
 }
 
 #ifndef B2C_EMU
+extern "C" __global__ void __launch_bounds__(32) b2c_s2_walk_kernel(S2DecParams P) {
+    const uint32_t c = blockIdx.x * 32 + threadIdx.x;
+    if (c < P.nchunks) s2s_walk_lane(P, c);
+}
+extern "C" __global__ void __launch_bounds__(S2DEC_WARPS * 32) b2c_s2_exec_kernel(S2DecParams P) {
+    __shared__ __align__(16) uint8_t stg[S2DEC_WARPS][S2S_WIN + 16];
+    const uint32_t c = blockIdx.x * S2DEC_WARPS + (threadIdx.x >> 5);
+    if (c < P.nchunks) s2s_exec_warp(P, c, stg[threadIdx.x >> 5], threadIdx.x & 31);
+}
 extern "C" __global__ void __launch_bounds__(S2DEC_WARPS * 32) b2c_s2_decode_kernel(S2DecParams P) {
     s2_decode_warp(P, blockIdx.x * S2DEC_WARPS + (threadIdx.x >> 5), gridDim.x * S2DEC_WARPS);
 }

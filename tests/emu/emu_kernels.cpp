@@ -18,6 +18,9 @@ using namespace b2c;
 extern "C" {
 
 void emu_set_lane_order(int desc) { emu::lane_order_desc = desc; }
+static int emu_s2_staged = 1, emu_s2_staged_count = 0;
+void emu_set_s2_staged(int on) { emu_s2_staged = on; }
+int emu_get_s2_staged_count(void) { return emu_s2_staged_count; }     // blocks of the last emu_s2_decode the staged kernels finished
 static int emu_dec_maxb = 0;      // 0: the device's policy; else the staged decoder's blocks-per-input (4: per input, > 4: per block)
 void emu_set_dec_maxb(int maxb) { emu_dec_maxb = maxb; }
 
@@ -382,6 +385,28 @@ int emu_s2_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t *s
     P.src_base = src; P.src_offsets = src_off; P.src_sizes = src_sizes;
     P.dst_base = dst; P.dst_offsets = dst_off; P.dst_caps = dst_caps;
     P.out_sizes = out_sizes; P.nchunks = n;
+    // the device's launch sequence: tag walk (one lane per block), execution (one warp per block), then the one-warp kernel over
+    // what they left.  emu_s2_staged = 0 runs the one-warp kernel alone.  staged_out (optional): 1 where the staged kernels did it.
+    std::vector<S2Head> heads;
+    std::vector<uint64_t> recs;
+    if (emu_s2_staged && n > 0) {
+        uint64_t span = 0;
+        for (uint32_t i = 0; i < n; i++) span = std::max<uint64_t>(span, src_off[i] + src_sizes[i]);
+        heads.resize(n);
+        memset(heads.data(), 0xCD, sizeof(S2Head) * (size_t)n);
+        recs.assign((size_t)(span / 4) + n + 16, 0xCDCDCDCDCDCDCDCDull);
+        P.heads = heads.data(); P.recs = recs.data();
+        emu::launch((n + 31) / 32, 32, 0, [&]() {
+            const uint32_t c = blockIdx.x * 32 + threadIdx.x;
+            if (c < P.nchunks) s2s_walk_lane(P, c);
+        });
+        emu::launch((n + S2DEC_WARPS - 1) / S2DEC_WARPS, S2DEC_WARPS * 32, S2DEC_WARPS * (S2S_WIN + 16), [&]() {
+            const uint32_t c = blockIdx.x * S2DEC_WARPS + (threadIdx.x >> 5);
+            if (c < P.nchunks) s2s_exec_warp(P, c, emu::dyn_smem + (threadIdx.x >> 5) * (S2S_WIN + 16), threadIdx.x & 31);
+        });
+        emu_s2_staged_count = 0;
+        for (uint32_t i = 0; i < n; i++) emu_s2_staged_count += heads[i].state == 0;
+    }
     emu::launch(2, S2DEC_WARPS * 32, 0, [&]() {
         s2_decode_warp(P, blockIdx.x * S2DEC_WARPS + (threadIdx.x >> 5), gridDim.x * S2DEC_WARPS);
     });

@@ -121,3 +121,47 @@ def test_s2_decode_copy4_and_length_offset(emu_lib, oracle_lib):
         assert r == len(want) and got == want, i
         tail = dst[int(dst_off[i]) + len(want):int(dst_off[i]) + len(want) + 40]
         assert (tail == 0x5A).all(), i
+
+
+def test_emu_s2_staged_decode_forms(emu_lib, oracle_lib):
+    """The staged S2 block decoder (tag walk one lane per block, execution one warp per block) and the one-warp decoder give
+    the same bytes and the same results; the staged kernels really take the encoders' blocks (all tag kinds: literals of every
+    header size, copy1 / copy2, repeats with extended lengths, long runs), in both lane orders; what they cannot take (a block
+    above 64 KiB, damaged blocks) is answered by the one-warp kernel with the reference's error."""
+    from emu_util import emu_s2_decode, emu_s2_encode
+    from test_oracle_s2 import s2_encode
+    import numpy as np
+    tw = H.golden("twain.txt")
+    rng = np.random.default_rng(21)
+    blocks = [tw[:65536], tw[100000:100000 + 30011], b"", b"a", b"ab" * 30000, bytes(65536), H.golden("html.txt"),
+              rng.integers(0, 256, 5000, dtype=np.uint8).tobytes() + tw[:20000] + rng.integers(0, 256, 300, dtype=np.uint8).tobytes(),
+              tw[:100] + bytes(40000) + tw[:100]]
+    comps = []
+    for better in (False, True):
+        for snappy in (False, True):
+            comps += emu_s2_encode(emu_lib, blocks, snappy=snappy, better=better)[0]
+    srcs = blocks * 4
+    comps += [s2_encode(b, m) for b in blocks[:2] for m in (0, 1, 2)]          # the reference encoders' blocks too
+    srcs += [b for b in blocks[:2] for _ in range(3)]
+    big = s2_encode(tw[:70000], 0)                                                # > 64 KiB decoded: one-warp kernel
+    damaged = bytearray(comps[0]); damaged[len(damaged) // 2] ^= 0x41
+    comps_all = comps + [big, bytes(damaged), comps[0][:-7]]
+    caps = [len(x) for x in srcs] + [70000, 65536, 65536]
+    results = {}
+    for staged in (1, 0):
+        for desc in (0, 1):
+            emu_lib.emu_set_s2_staged(staged)
+            outs, res, _, _ = emu_s2_decode(emu_lib, comps_all, caps, desc=desc)
+            results[(staged, desc)] = (list(outs), res)
+            if staged:
+                k = emu_lib.emu_get_s2_staged_count()
+                assert k >= len(comps) - 8, k          # (empty / tiny blocks may go either way)
+    emu_lib.emu_set_s2_staged(1)
+    base = results[(0, 0)]
+    for key, val in results.items():
+        assert val == base, key
+    outs, res = base
+    for i, sblk in enumerate(srcs):
+        assert outs[i] == len(sblk) and res[i] == sblk, i
+    assert outs[len(srcs)] == 70000 and res[len(srcs)] == tw[:70000]
+    assert outs[-1] < 0
