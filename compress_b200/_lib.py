@@ -48,6 +48,8 @@ def _load():
     lib.b2c_zstd_encode_chunks.restype = c.c_int
     lib.b2c_zstd_encode_chunks.argtypes = [
         c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_size_t]
+    lib.b2c_s2_decode_staged_count.restype = c.c_int
+    lib.b2c_s2_decode_staged_count.argtypes = [c.c_void_p, c.c_uint32, c.c_void_p]
     lib.b2c_s2_stream_bound.restype = c.c_size_t
     lib.b2c_s2_stream_bound.argtypes = [c.c_size_t, c.c_size_t]
     lib.b2c_s2_encode_stream_device.restype = c.c_int
@@ -142,7 +144,7 @@ EXPORTED_SYMBOLS = [
     "b2c_device_count", "b2c_ctx_create", "b2c_ctx_destroy", "b2c_strerror", "b2c_last_cuda_error",
     "b2c_sm_count", "b2c_launch_count", "b2c_zstd_bound", "b2c_zstd_encode_device",
     "b2c_zstd_encode_chunks", "b2c_zstd_encode_device_debug", "b2c_zstd_encode_packed", "b2c_zstd_encode_device_timed",
-    "b2c_zstd_decode_device", "b2c_zstd_decode_chunks", "b2c_profile_enable", "b2c_profile_read", "b2c_decode_profile_enable", "b2c_decode_profile_read", "b2c_decode_staged_count",
+    "b2c_zstd_decode_device", "b2c_zstd_decode_chunks", "b2c_profile_enable", "b2c_profile_read", "b2c_decode_profile_enable", "b2c_decode_profile_read", "b2c_decode_staged_count", "b2c_s2_decode_staged_count",
     "b2c_huf_compress_device", "b2c_huf_decompress_device",
     "b2c_s2_bound", "b2c_s2_encode_device", "b2c_s2_decode_device", "b2c_s2_encode_chunks", "b2c_s2_decode_chunks",
     "b2c_huf_compress_chunks", "b2c_huf_decompress_chunks", "b2c_huf_read_table",

@@ -388,6 +388,21 @@ int b2c_decode_staged_count(b2c_ctx *ctx, uint32_t nchunks, uint32_t *staged) {
     *staged = k;
     return B2C_OK;
 }
+// The same for the most recent S2 block decode launch: blocks finished by the staged kernels (tag walk + execution).
+int b2c_s2_decode_staged_count(b2c_ctx *ctx, uint32_t nchunks, uint32_t *staged) {
+    if (!ctx || !staged) return B2C_ERR_ARG;
+    *staged = 0;
+    if (!ctx->d_s2d || !ctx->dec_staged || nchunks == 0) return B2C_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    if ((size_t)nchunks * sizeof(S2Head) > ctx->s2d_cap) return B2C_ERR_ARG;
+    std::vector<uint32_t> st(nchunks);
+    CK(cudaMemcpy2D(st.data(), sizeof(uint32_t), ctx->d_s2d, sizeof(S2Head), sizeof(uint32_t), nchunks, cudaMemcpyDeviceToHost));
+    uint32_t k = 0;
+    for (uint32_t v : st) k += v == 0;
+    *staged = k;
+    return B2C_OK;
+}
 int b2c_decode_profile_read(b2c_ctx *ctx, double *ms) {
     if (!ctx) return B2C_ERR_NO_DEVICE;
     for (int i = 0; i < 6; i++) { ms[i] = (double)ctx->dec_ms[i]; ctx->dec_ms[i] = 0.f; }

@@ -168,15 +168,26 @@ B2C_DEV void s2s_walk_lane(const S2DecParams &P, uint32_t c) {
         if (havePrev) { recs[nrec - 1] = prevRec | ((uint64_t)(prevTb + (hb_)) << 51); havePrev = false; } \
         if (!firstSet) { firstLit = (pos_); firstSet = true; }                             \
     } while (0)
+    // Every step fetches the tag and the four bytes behind it with three aligned word loads (independent of the tag, so they
+    // are in flight together) and derives header size, length and offset from them with selects: the 32 lanes of a warp sit on
+    // 32 different tags, and a branch per tag kind would make the warp run every kind's path at every step.
+    const uint32_t smis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - smis);
+    const uint32_t nsw = (slen + smis + 3) >> 2;                  // aligned words that hold block bytes
     while (s < slen) {
-        const uint32_t tag = src[s];
-        if ((tag & 3) == 0) {
-            uint32_t x = tag >> 2, hb;
-            if (x < 60) hb = 1;
-            else if (x == 60) { hb = 2; if (s + hb > slen) S2LEG(); x = src[s + 1]; }
-            else if (x == 61) { hb = 3; if (s + hb > slen) S2LEG(); x = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8; }
-            else if (x == 62) { hb = 4; if (s + hb > slen) S2LEG(); x = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8 | (uint32_t)src[s + 3] << 16; }
-            else { hb = 5; if (s + hb > slen) S2LEG(); x = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8 | (uint32_t)src[s + 3] << 16 | (uint32_t)src[s + 4] << 24; }
+        const uint32_t wi = (s + smis) >> 2, sh = ((s + smis) & 3) * 8;
+        // (read-only path: the block's lines stay in L1 while the lane moves through them; the line after next is requested early)
+        const uint32_t w0 = B2C_LDG(sw + wi), w1 = wi + 1 < nsw ? B2C_LDG(sw + wi + 1) : 0u, w2 = wi + 2 < nsw ? B2C_LDG(sw + wi + 2) : 0u;
+        if ((wi & 31) == 0 && wi + 64 < nsw) prefetch_l1(sw + wi + 64);
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);   // bytes s .. s+3, s+4 .. s+7
+        const uint32_t tag = lo & 0xff;
+        const uint32_t ext = (lo >> 8) | (hi << 24);                                         // bytes s+1 .. s+4
+        const uint32_t kind = tag & 3, x6 = tag >> 2;
+        if (kind == 0) {
+            const uint32_t nb = x6 < 60 ? 0u : x6 - 59;                                      // extra length bytes (0 .. 4)
+            const uint32_t hb = 1 + nb;
+            if (s + hb > slen) S2LEG();
+            const uint32_t x = nb == 0 ? x6 : (nb == 4 ? ext : (ext & ((1u << (8 * nb)) - 1)));
             if (x >= S2S_MAX_DLEN) S2LEG();
             const uint32_t length = x + 1;
             if (length > slen - (s + hb)) S2LEG();
@@ -186,29 +197,17 @@ B2C_DEV void s2s_walk_lane(const S2DecParams &P, uint32_t c) {
             s += hb + length;
             continue;
         }
-        uint32_t length, tb;
-        if ((tag & 3) == 1) {
-            tb = 2;
-            if (s + tb > slen) S2LEG();
-            length = (tag >> 2) & 7;
-            const uint32_t toffset = ((tag & 0xe0) << 3) | src[s + 1];
-            if (toffset == 0) {            // repeat: the last offset, extended length codes (decode_other.go:74-101)
-                if (length == 5) { tb = 3; if (s + tb > slen) S2LEG(); length = (uint32_t)src[s + 2] + 4; }
-                else if (length == 6) { tb = 4; if (s + tb > slen) S2LEG(); length = ((uint32_t)src[s + 2] | (uint32_t)src[s + 3] << 8) + (1 << 8); }
-                else if (length == 7) { tb = 5; if (s + tb > slen) S2LEG(); length = ((uint32_t)src[s + 2] | (uint32_t)src[s + 3] << 8 | (uint32_t)src[s + 4] << 16) + (1 << 16); }
-            } else offset = toffset;
-            length += 4;
-        } else if ((tag & 3) == 2) {
-            tb = 3;
-            if (s + tb > slen) S2LEG();
-            length = 1 + (tag >> 2);
-            offset = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8;
-        } else {
-            tb = 5;
-            if (s + tb > slen) S2LEG();
-            length = 1 + (tag >> 2);
-            offset = (uint32_t)src[s + 1] | (uint32_t)src[s + 2] << 8 | (uint32_t)src[s + 3] << 16 | (uint32_t)src[s + 4] << 24;
-        }
+        // copies: copy1 (2 bytes; offset 0 = repeat with 0 .. 3 extra length bytes), copy2 (3 bytes), copy4 (5 bytes)
+        const uint32_t l3 = x6 & 7;
+        const uint32_t toff1 = ((tag & 0xe0) << 3) | (ext & 0xff);
+        const bool rep = kind == 1 && toff1 == 0;
+        const uint32_t rb = (rep && l3 >= 5) ? l3 - 4 : 0u;                                   // repeat: extra length bytes
+        const uint32_t tb = kind == 1 ? 2 + rb : (kind == 2 ? 3u : 5u);
+        if (s + tb > slen) S2LEG();
+        const uint32_t rext = (ext >> 8) & (rb == 0 ? 0u : ((1u << (8 * rb)) - 1));           // bytes s+2 .. of a repeat
+        const uint32_t len1 = (rb == 0 ? l3 : rext + (rb == 1 ? 4u : (rb == 2 ? 256u : 65536u))) + 4;
+        const uint32_t length = kind == 1 ? len1 : 1 + x6;
+        if (!rep) offset = kind == 1 ? toff1 : (kind == 2 ? (ext & 0xffff) : ext);
         if (offset == 0 || offset > S2S_MAX_DLEN || length > S2S_MAX_DLEN) S2LEG();
         if (!open) S2_START(0, s);                       // an element without a literal run: L = its copy tag
         S2_EMIT(open ? openLL : 0u, length, offset, tb);

@@ -136,6 +136,12 @@ class Codec:
         return dst, out_sizes
 
     # ---- host buffers ------------------------------------------------------------------------------
+    def staged_count(self, n):
+        """How many of the first n blocks of the last decode launch were finished by the staged kernels (diagnostics)."""
+        k = ctypes.c_uint32(0)
+        check(lib.b2c_s2_decode_staged_count(self._ctx, n, ctypes.byref(k)), self._ctx)
+        return int(k.value)
+
     def _host(self, fn, blobs, caps, *pre):
         n = len(blobs)
         bufs = [np.frombuffer(bytes(b), dtype=np.uint8) if len(b) else np.zeros(0, dtype=np.uint8) for b in blobs]

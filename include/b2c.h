@@ -91,6 +91,7 @@ B2C_API int b2c_decode_profile_read(b2c_ctx *ctx, double *ms);
 /* diagnostics: of the first nchunks inputs of the most recent decode launch, how many the staged kernels completed (the
  * rest were decoded by the one-warp decoder).  Synchronises the device. */
 B2C_API int b2c_decode_staged_count(b2c_ctx *ctx, uint32_t nchunks, uint32_t *staged);
+B2C_API int b2c_s2_decode_staged_count(b2c_ctx *ctx, uint32_t nchunks, uint32_t *staged);   /* the same for S2 block decode */
 
 /* Encoder.MaxEncodedSize for one chunk of n bytes (zstd/encoder.go:843-873) */
 B2C_API size_t b2c_zstd_bound(size_t n, int level);
