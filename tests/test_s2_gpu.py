@@ -111,3 +111,18 @@ def test_s2_roundtrip_device_256mib(codec):
         assert torch.equal(out.view(-1), src)
         ratio = float(sizes.sum()) / src.numel()
         assert 0.3 < ratio < 0.8, ratio
+
+
+def test_s2_staged_decode_is_used_and_equals_one_warp(codec, emu_lib):
+    """The staged S2 decoder (tag walk per lane, execution per warp) takes the encoders' blocks on the device, and its bytes
+    equal the emulated kernels' (which tests/test_emu_s2.py compares with the one-warp decoder and the oracle)."""
+    from emu_util import emu_s2_decode
+    tw = H.golden("twain.txt")
+    blocks = [tw[i:i + 65536] for i in range(0, 5 * 65536, 65536)] + [b"ab" * 20000, bytes(50000), tw[:1000]]
+    for better in (False, True):
+        comps = codec.encode_blocks(blocks, better=better)
+        outs, codes = codec.decode_blocks(comps, [len(b) for b in blocks])
+        assert outs == blocks, codes
+        assert codec.staged_count(len(blocks)) == len(blocks)
+        _, res, _, _ = emu_s2_decode(emu_lib, comps, [len(b) for b in blocks])
+        assert res == blocks
