@@ -1569,7 +1569,7 @@ static int launch_s2_decode(b2c_ctx *ctx, S2DecParams &P, uint64_t span, cudaStr
     const bool staged = ctx->dec_staged && span > 0 && span <= ((uint64_t)8 << 30);
     if (staged) {
         const size_t headBytes = (((size_t)n * sizeof(S2Head)) + 255) & ~(size_t)255;
-        const size_t recBytes = ((size_t)(span / 4) + n + 16) * sizeof(uint64_t);
+        const size_t recBytes = ((size_t)(span / 3) + n + 16) * sizeof(uint64_t);
         { int r = ctx_order_begin(ctx, st); if (r) return r; }
         int rc = grow(ctx, &ctx->d_s2d, &ctx->s2d_cap, headBytes + recBytes);
         if (rc) return rc;

@@ -22,7 +22,7 @@ struct S2DecParams {
     uint32_t nchunks;
     // staged form (nullptr: every block goes through the one-warp kernel)
     S2Head *heads;           // [nchunks]
-    uint64_t *recs;          // block c: s2_rec_off(P, c), capacity src_sizes[c] / 4 + 1 records
+    uint64_t *recs;          // block c: s2_rec_off(P, c), capacity src_sizes[c] / 3 + 1 records
 };
 
 B2C_DEV int64_t s2_decode_block(const uint8_t *src, uint32_t slen, uint8_t *dst, uint32_t cap, unsigned lane) {
@@ -122,12 +122,12 @@ B2C_DEV int64_t s2_decode_block(const uint8_t *src, uint32_t slen, uint8_t *dst,
 //         and the next literal header), so a prefix sum places every literal run in the input
 //   exec  one WARP per block: 32 elements per step, places by warp scans, literal bytes gathered from the step's window of
 //         the input (staged in shared memory), copies in dependency waves (lz_exec_match_waves)
-// Blocks of at most 64 KiB decoded / 128 KiB encoded with at most size/4 + 1 elements; anything else, and anything a stage
+// Blocks of at most 64 KiB decoded / 128 KiB encoded with at most size/3 + 1 elements; anything else, and anything a stage
 // does not like, is left to the one-warp kernel (state 1), which also produces the error values.
 constexpr uint32_t S2S_MAX_DLEN = 65536, S2S_MAX_SLEN = 1u << 17, S2S_WIN = 1024;
 B2C_DEV const uint8_t *s2_src(const S2DecParams &P, uint32_t c) { return P.src_base + (P.src_offsets ? P.src_offsets[c] : (uint64_t)c * P.src_stride); }
 B2C_DEV uint64_t s2_rec_off(const S2DecParams &P, uint32_t c) {
-    return (P.src_offsets ? P.src_offsets[c] : (uint64_t)c * P.src_stride) / 4 + c;
+    return (P.src_offsets ? P.src_offsets[c] : (uint64_t)c * P.src_stride) / 3 + c;
 }
 B2C_DEV uint64_t s2_rec_pack(uint32_t ll, uint32_t ml, uint32_t off, uint32_t gap) {
     return (uint64_t)ll | ((uint64_t)ml << 17) | ((uint64_t)off << 34) | ((uint64_t)gap << 51);
@@ -137,7 +137,7 @@ B2C_DEV void s2s_walk_lane(const S2DecParams &P, uint32_t c) {
     const uint32_t slen = P.src_sizes[c], cap = P.dst_caps ? P.dst_caps[c] : P.dst_cap;
     S2Head *hd = P.heads + c;
     uint64_t *recs = P.recs + s2_rec_off(P, c);
-    const uint32_t recCap = slen / 4 + 1;
+    const uint32_t recCap = slen / 3 + 1;         // (an element is at least a two-byte copy; three bytes on average holds for all but degenerate blocks)
 #define S2LEG() do { hd->state = 1; return; } while (0)
     if (slen == 0 || slen > S2S_MAX_SLEN) S2LEG();
     uint64_t v = 0;

@@ -394,7 +394,7 @@ int emu_s2_decode(const uint8_t *src, const uint64_t *src_off, const uint32_t *s
         for (uint32_t i = 0; i < n; i++) span = std::max<uint64_t>(span, src_off[i] + src_sizes[i]);
         heads.resize(n);
         memset(heads.data(), 0xCD, sizeof(S2Head) * (size_t)n);
-        recs.assign((size_t)(span / 4) + n + 16, 0xCDCDCDCDCDCDCDCDull);
+        recs.assign((size_t)(span / 3) + n + 16, 0xCDCDCDCDCDCDCDCDull);
         P.heads = heads.data(); P.recs = recs.data();
         emu::launch((n + 31) / 32, 32, 0, [&]() {
             const uint32_t c = blockIdx.x * 32 + threadIdx.x;
