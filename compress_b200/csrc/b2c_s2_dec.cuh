@@ -118,8 +118,8 @@ B2C_DEV int64_t s2_decode_block(const uint8_t *src, uint32_t slen, uint8_t *dst,
 // it.  The staged form splits the two halves of s2Decode (s2/decode_other.go:22-287) the way the staged zstd decoder does:
 //   walk  one LANE per block: the tag stream -> one 8-byte record per element: literal length | copy length << 17 |
 //         offset << 34 | gap << 51, where an element is "a literal run (possibly empty) followed by a copy (possibly none)"
-//         and gap = bytes between the end of this element's literal bytes and the start of the next element's (the copy tag
-//         and the next literal header), so a prefix sum places every literal run in the input
+//         and gap = bytes between the end of the previous element's literal bytes and the start of this element's (the
+//         previous copy tag and this literal header), so a prefix sum places every literal run in the input
 //   exec  one WARP per block: 32 elements per step, places by warp scans, literal bytes gathered from the step's window of
 //         the input (staged in shared memory), copies in dependency waves (lz_exec_match_waves)
 // Blocks of at most 64 KiB decoded / 128 KiB encoded with at most size/3 + 1 elements; anything else, and anything a stage
@@ -151,72 +151,65 @@ B2C_DEV void s2s_walk_lane(const S2DecParams &P, uint32_t c) {
     }
     if (v > S2S_MAX_DLEN || v > cap) S2LEG();
     const uint32_t dlen = (uint32_t)v;
-    // Element i = [literal run of ll_i bytes at L_i][copy].  L_i = where its literal bytes start (the position of its copy tag
-    // when it has none); gap_i = L_(i+1) - (L_i + ll_i) = bytes of its copy tag + bytes of the next element's literal header.
-    uint32_t nrec = 0, offset = 0;
-    bool open = false; uint32_t openLL = 0;           // an element whose literal run has been read and that awaits its copy
-    bool havePrev = false; uint64_t prevRec = 0; uint32_t prevTb = 0;
-    bool firstSet = false; uint32_t firstLit = s;
-#define S2_EMIT(ll_, ml_, off_, tb_)                                                       \
-    do {                                                                                   \
-        if (nrec >= recCap) S2LEG();                                                       \
-        prevRec = s2_rec_pack((ll_), (ml_), (off_), 0); recs[nrec++] = prevRec;            \
-        prevTb = (tb_); havePrev = true;                                                   \
-    } while (0)
-#define S2_START(hb_, pos_)                                                                \
-    do {                                                                                   \
-        if (havePrev) { recs[nrec - 1] = prevRec | ((uint64_t)(prevTb + (hb_)) << 51); havePrev = false; } \
-        if (!firstSet) { firstLit = (pos_); firstSet = true; }                             \
-    } while (0)
-    // Every step fetches the tag and the four bytes behind it with three aligned word loads (independent of the tag, so they
-    // are in flight together) and derives header size, length and offset from them with selects: the 32 lanes of a warp sit on
-    // 32 different tags, and a branch per tag kind would make the warp run every kind's path at every step.
+    // Element i = [literal run of ll_i bytes][copy]; its record carries gap_i = the bytes between the end of the previous
+    // element's literal data and the start of its own (the previous copy tag + its own literal header), so the execution
+    // kernel finds every literal run with one prefix sum: L_i = C_(i-1) + gap_i, C_i = L_i + ll_i, C_(-1) = end of the varint.
+    // One step of the loop takes one element: a literal tag (if there is one) and the copy tag behind it.  Tags and the four
+    // bytes behind them arrive as aligned words through the read-only path and are decoded with selects: the 32 lanes of a
+    // warp sit on 32 different tags, and a branch per tag kind would make the warp run every kind's path at every step.
+    uint32_t nrec = 0, offset = 0, prevTb = 0;
+    const uint32_t firstLit = s;
     const uint32_t smis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3);
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(src - smis);
     const uint32_t nsw = (slen + smis + 3) >> 2;                  // aligned words that hold block bytes
+#define S2_FETCH(pos_, tag_, ext_)                                                                                          \
+    do {                                                                                                                    \
+        const uint32_t wi_ = ((pos_) + smis) >> 2, sh_ = (((pos_) + smis) & 3) * 8;                                          \
+        const uint32_t w0_ = B2C_LDG(sw + wi_), w1_ = wi_ + 1 < nsw ? B2C_LDG(sw + wi_ + 1) : 0u,                            \
+                       w2_ = wi_ + 2 < nsw ? B2C_LDG(sw + wi_ + 2) : 0u;                                                     \
+        const uint32_t lo_ = __funnelshift_r(w0_, w1_, sh_), hi_ = __funnelshift_r(w1_, w2_, sh_);                          \
+        (tag_) = lo_ & 0xff; (ext_) = (lo_ >> 8) | (hi_ << 24);          /* the tag byte; bytes pos+1 .. pos+4 */           \
+    } while (0)
     while (s < slen) {
-        const uint32_t wi = (s + smis) >> 2, sh = ((s + smis) & 3) * 8;
-        // (read-only path: the block's lines stay in L1 while the lane moves through them; the line after next is requested early)
-        const uint32_t w0 = B2C_LDG(sw + wi), w1 = wi + 1 < nsw ? B2C_LDG(sw + wi + 1) : 0u, w2 = wi + 2 < nsw ? B2C_LDG(sw + wi + 2) : 0u;
-        if ((wi & 31) == 0 && wi + 64 < nsw) prefetch_l1(sw + wi + 64);
-        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);   // bytes s .. s+3, s+4 .. s+7
-        const uint32_t tag = lo & 0xff;
-        const uint32_t ext = (lo >> 8) | (hi << 24);                                         // bytes s+1 .. s+4
-        const uint32_t kind = tag & 3, x6 = tag >> 2;
-        if (kind == 0) {
+        uint32_t tag, ext;
+        S2_FETCH(s, tag, ext);
+        uint32_t ll = 0, hb = 0;
+        bool copyFollows = true;
+        if ((tag & 3) == 0) {
+            const uint32_t x6 = tag >> 2;
             const uint32_t nb = x6 < 60 ? 0u : x6 - 59;                                      // extra length bytes (0 .. 4)
-            const uint32_t hb = 1 + nb;
+            hb = 1 + nb;
             if (s + hb > slen) S2LEG();
             const uint32_t x = nb == 0 ? x6 : (nb == 4 ? ext : (ext & ((1u << (8 * nb)) - 1)));
             if (x >= S2S_MAX_DLEN) S2LEG();
-            const uint32_t length = x + 1;
-            if (length > slen - (s + hb)) S2LEG();
-            if (open) S2_EMIT(openLL, 0, 0, 0);          // two literal runs in a row: the first is an element without a copy
-            S2_START(hb, s + hb);
-            open = true; openLL = length;
-            s += hb + length;
-            continue;
+            ll = x + 1;
+            if (ll > slen - (s + hb)) S2LEG();
+            s += hb + ll;
+            if (s < slen) { S2_FETCH(s, tag, ext); copyFollows = (tag & 3) != 0; }           // (another literal: no copy in this element)
+            else copyFollows = false;                                                         // trailing literal run
         }
-        // copies: copy1 (2 bytes; offset 0 = repeat with 0 .. 3 extra length bytes), copy2 (3 bytes), copy4 (5 bytes)
-        const uint32_t l3 = x6 & 7;
-        const uint32_t toff1 = ((tag & 0xe0) << 3) | (ext & 0xff);
-        const bool rep = kind == 1 && toff1 == 0;
-        const uint32_t rb = (rep && l3 >= 5) ? l3 - 4 : 0u;                                   // repeat: extra length bytes
-        const uint32_t tb = kind == 1 ? 2 + rb : (kind == 2 ? 3u : 5u);
-        if (s + tb > slen) S2LEG();
-        const uint32_t rext = (ext >> 8) & (rb == 0 ? 0u : ((1u << (8 * rb)) - 1));           // bytes s+2 .. of a repeat
-        const uint32_t len1 = (rb == 0 ? l3 : rext + (rb == 1 ? 4u : (rb == 2 ? 256u : 65536u))) + 4;
-        const uint32_t length = kind == 1 ? len1 : 1 + x6;
-        if (!rep) offset = kind == 1 ? toff1 : (kind == 2 ? (ext & 0xffff) : ext);
-        if (offset == 0 || offset > S2S_MAX_DLEN || length > S2S_MAX_DLEN) S2LEG();
-        if (!open) S2_START(0, s);                       // an element without a literal run: L = its copy tag
-        S2_EMIT(open ? openLL : 0u, length, offset, tb);
-        open = false;
-        s += tb;
+        uint32_t length = 0, off = 0, tb = 0;
+        if (copyFollows) {
+            // copy1 (2 bytes; offset 0 = repeat with 0 .. 3 extra length bytes), copy2 (3 bytes), copy4 (5 bytes)
+            const uint32_t kind = tag & 3, x6 = tag >> 2, l3 = x6 & 7;
+            const uint32_t toff1 = ((tag & 0xe0) << 3) | (ext & 0xff);
+            const bool rep = kind == 1 && toff1 == 0;
+            const uint32_t rb = (rep && l3 >= 5) ? l3 - 4 : 0u;                               // repeat: extra length bytes
+            tb = kind == 1 ? 2 + rb : (kind == 2 ? 3u : 5u);
+            if (s + tb > slen) S2LEG();
+            const uint32_t rext = (ext >> 8) & (rb == 0 ? 0u : ((1u << (8 * rb)) - 1));       // bytes s+2 .. of a repeat
+            const uint32_t len1 = (rb == 0 ? l3 : rext + (rb == 1 ? 4u : (rb == 2 ? 256u : 65536u))) + 4;
+            length = kind == 1 ? len1 : 1 + x6;
+            if (!rep) offset = kind == 1 ? toff1 : (kind == 2 ? (ext & 0xffff) : ext);
+            if (offset == 0 || offset > S2S_MAX_DLEN || length > S2S_MAX_DLEN) S2LEG();
+            off = offset;
+            s += tb;
+        }
+        if (nrec >= recCap) S2LEG();
+        recs[nrec++] = s2_rec_pack(ll, length, off, prevTb + hb);
+        prevTb = tb;
     }
-    if (open) S2_EMIT(openLL, 0, 0, 0);                  // trailing literal run
-#undef S2_EMIT
-#undef S2_START
+#undef S2_FETCH
     hd->state = 0; hd->nrec = nrec; hd->firstLit = firstLit; hd->dlen = dlen;
 #undef S2LEG
 }
@@ -241,7 +234,7 @@ B2C_DEV void s2s_exec_warp(const S2DecParams &P, uint32_t c, uint8_t *stg, unsig
         const uint32_t myGap = (uint32_t)((rec >> 51) & 15);
         const uint32_t lenIncl = warp_scan_incl(myLL + myML), llIncl = warp_scan_incl(myLL), srcIncl = warp_scan_incl(myLL + myGap);
         const uint32_t myOut = d + (lenIncl - (myLL + myML)), myDst = myOut + myLL;
-        const uint32_t myLit = litSrc + (srcIncl - (myLL + myGap));
+        const uint32_t myLit = litSrc + (srcIncl - myLL);                // L_i = C_start + sum_(j <= i)(gap_j + ll_j) - ll_i
         bool err = false;
         if (mine) {
             if (lenIncl > dlen - d) err = true;                          // (d <= dlen always)
