@@ -197,3 +197,29 @@ def test_long_frames_decode_block_parallel(emu_lib):
             assert outs == inputs_all
     finally:
         emu_lib.emu_set_dec_maxb(0)
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_frames_random_structures(emu_lib, level):
+    """Frame mode on random LZ-structured inputs of random sizes (block boundaries land anywhere, long runs and far copies cross
+    them): every block equals the oracle's blockEnc.encode for the kernel's parse, frames decode with the oracle and libzstd,
+    and both forms of the staged decoder give the input back."""
+    from emu_util import emu_decode
+    from test_emu_encoder_random import _structured
+    rng = np.random.Generator(np.random.PCG64(100 + level))
+    fblock = 49152 if level == 1 else 98304
+    inputs = []
+    for k in range(6):
+        n = int(rng.integers(1, 4 * fblock))
+        inputs.append(_structured(rng, n))
+    inputs += [_structured(rng, fblock), _structured(rng, 2 * fblock + 1)]
+    frames, blocks, _ = emu_encode_frames(emu_lib, inputs, level=level)
+    check_frame_mode(inputs, frames, blocks, level, "frames-rnd-L%d" % level)
+    caps = [len(x) + 8 for x in inputs]
+    try:
+        for maxb in (0, 4):
+            emu_lib.emu_set_dec_maxb(maxb)
+            sizes, outs = emu_decode(emu_lib, frames, caps)
+            assert outs == inputs, (maxb, list(sizes))
+    finally:
+        emu_lib.emu_set_dec_maxb(0)
