@@ -16,6 +16,10 @@ everything the -m gpu tests, smoke() and bench.py need lives here.
   zstd_large.zip                 the .zst members of zstd/testdata/large.zip (TestNewDecoderLarge; contents are zeros)
   zstd_decode_regression.zip     zstd/testdata/decode-regression.zip
   s2_dec_block_regressions.zip   s2/testdata/dec-block-regressions.zip (TestDecodeRegression, s2/decode_test.go:19)
+  zstd_regression.zip            zstd/testdata/regression.zip: 36 decoder regression inputs (TestDecoderRegression, decoder_test.go:682)
+  zstd_benchdecoder.zip          zstd/testdata/benchdecoder.zip: 12 .zst files (TestDecoderMultiFrame :911, TestDecoder_Reset :964, benchmarks)
+  zstd_z000028, zstd_z000028.zst the decoded / encoded pair of TestPredefTables / TestDecoderDrain (decoder_test.go:539-624, :845)
+  zstd_xml.zst                   zstd/testdata/xml.zst (5 345 280 bytes decoded; benchmarks)
 """
 import io, os, shutil, zipfile
 
@@ -52,6 +56,11 @@ def main():
     oz.close()
     shutil.copy(f"{REF}/zstd/testdata/decode-regression.zip", f"{HERE}/zstd_decode_regression.zip")
     shutil.copy(f"{REF}/s2/testdata/dec-block-regressions.zip", f"{HERE}/s2_dec_block_regressions.zip")
+    shutil.copy(f"{REF}/zstd/testdata/regression.zip", f"{HERE}/zstd_regression.zip")
+    shutil.copy(f"{REF}/zstd/testdata/benchdecoder.zip", f"{HERE}/zstd_benchdecoder.zip")
+    shutil.copy(f"{REF}/zstd/testdata/z000028", f"{HERE}/zstd_z000028")
+    shutil.copy(f"{REF}/zstd/testdata/z000028.zst", f"{HERE}/zstd_z000028.zst")
+    shutil.copy(f"{REF}/zstd/testdata/xml.zst", f"{HERE}/zstd_xml.zst")
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

