@@ -236,13 +236,21 @@ class Writer:
     are gathered and leave as complete frames -- one per Flush / Close, or every `frame_bytes` of input -- each a multi-block
     frame whose blocks see their history.  Concatenated frames are one valid zstd stream (zstd/encoder.go:719)."""
 
-    def __init__(self, w, level=SpeedFastest, crc=True, device=0, frame_bytes=None):
+    def __init__(self, w, level=SpeedFastest, crc=True, device=0, frame_bytes=None, encoder=None):
         """frame_bytes: input bytes per frame; default four frame-mode blocks (192 KiB at SpeedFastest, 384 KiB above), the
-        longest frames the staged GPU decoder takes on its fast path."""
+        longest frames the staged GPU decoder takes on its fast path.  encoder: an Encoder to share
+        (its level and checksum setting apply); by default the writer owns one."""
         self._w = w
-        self._enc = Encoder(level=level, crc=crc, device=device, max_chunks=64)
+        self._enc = encoder if encoder is not None else Encoder(level=level, crc=crc, device=device, max_chunks=64)
+        self._own = encoder is None
         self._buf = bytearray()
         self._frame_bytes = frame_bytes if frame_bytes else 4 * (49152 if level == SpeedFastest else 98304)
+        self._wrote = False
+
+    def Reset(self, w):
+        """Discard pending state and write to w from now on, keeping the device context (zstd/encoder.go:100-121)."""
+        self._w = w
+        self._buf = bytearray()
         self._wrote = False
 
     def Write(self, p):
@@ -266,7 +274,8 @@ class Writer:
         if not self._wrote:          # an empty stream is still a frame (WithZeroFrames, zstd/encoder.go:732-751)
             self._w.write(self._enc.encode_frames([b""])[0])
             self._wrote = True
-        self._enc.close()
+        if self._own:
+            self._enc.close()
 
 
 # ---- decoder ------------------------------------------------------------------------------------
@@ -380,6 +389,233 @@ class Decoder:
             dst += outs[0]
             return dst
         return outs[0]
+
+
+# ---- stream reader (zstd.NewReader over an io.Reader) ---------------------------------------------------------------
+FRAME_MAGIC = 0xFD2FB528
+SKIPPABLE_MAGIC = 0x184D2A50          # .. 0x184D2A5F (zstd/framedec.go:49-50)
+MIN_WINDOW = 1 << 10                  # MinWindowSize, zstd/zstd.go
+MAX_BLOCK = 128 << 10                 # maxCompressedBlockSize, zstd/blockdec.go:41-45
+ErrReservedBit = ErrCorrupt
+ErrUnexpectedEOF = -5
+
+
+class FrameSpan:
+    """One frame of a stream as the host walk sees it: ``length`` compressed bytes; ``content_size`` from the header or None;
+    ``bound`` = an upper bound of the decoded size from the block headers; ``skippable`` for 0x184D2A5x frames."""
+    __slots__ = ("length", "content_size", "bound", "window", "skippable", "blocks")
+
+    def __init__(self, length, content_size, bound, window, skippable, blocks):
+        self.length, self.content_size, self.bound, self.window = length, content_size, bound, window
+        self.skippable, self.blocks = skippable, blocks
+
+
+def frame_span(buf, off=0, max_window=None):
+    """Find the frame starting at buf[off] without touching block contents: the frame header fields of frameDec.reset
+    (zstd/framedec.go:62-230) and then the 3-byte block headers (zstd/blockdec.go:129-190) up to the last block and the
+    optional checksum.  Returns a FrameSpan, or None when buf ends inside the frame (more input needed).  Raises ZstdError for
+    what the reference rejects at this level: bad magic, reserved bit, window limits, reserved block type."""
+    n = len(buf)
+    if n - off < 4:
+        return None
+    magic = int.from_bytes(buf[off:off + 4], "little")
+    if magic & 0xFFFFFFF0 == SKIPPABLE_MAGIC:
+        if n - off < 8:
+            return None
+        ln = 8 + int.from_bytes(buf[off + 4:off + 8], "little")
+        return FrameSpan(ln, 0, 0, 0, True, 0) if n - off >= ln else None
+    if magic != FRAME_MAGIC:
+        raise ZstdError(ErrMagicMismatch)
+    p = off + 4
+    if p >= n:
+        return None
+    fhd = buf[p]; p += 1
+    if fhd & 8:
+        raise ZstdError(ErrReservedBit)
+    single = bool(fhd & 0x20)
+    window = 0
+    if not single:
+        if p >= n:
+            return None
+        wd = buf[p]; p += 1
+        base = 1 << (10 + (wd >> 3))
+        window = base + (base // 8) * (wd & 7)
+    p += (0, 1, 2, 4)[fhd & 3]                       # dictionary id (ignored here; the decoder rejects what it cannot serve)
+    flag = fhd >> 6
+    fcs_len = (1 if single else 0, 2, 4, 8)[flag]
+    if p + fcs_len > n:
+        return None
+    content = None
+    if fcs_len:
+        content = int.from_bytes(buf[p:p + fcs_len], "little") + (256 if fcs_len == 2 else 0)
+        p += fcs_len
+    if single:
+        window = content
+    elif window < MIN_WINDOW:
+        raise ZstdError(ErrWindowSizeExceeded)        # (ErrWindowSizeTooSmall shares the window error class of the C ABI)
+    if max_window is not None and window > max_window:
+        raise ZstdError(ErrWindowSizeExceeded)
+    bound = blocks = 0
+    while True:
+        if p + 3 > n:
+            return None
+        bh = buf[p] | buf[p + 1] << 8 | buf[p + 2] << 16
+        p += 3
+        last, typ, size = bh & 1, (bh >> 1) & 3, bh >> 3
+        if typ == 3:
+            raise ZstdError(ErrCorrupt)               # ErrReservedBlockType
+        if typ == 1:
+            p += 1; bound += size
+        elif typ == 0:
+            p += size; bound += size
+        else:
+            if size > MAX_BLOCK:
+                raise ZstdError(ErrCorrupt)           # ErrCompressedSizeTooBig
+            p += size; bound += MAX_BLOCK if not window else min(MAX_BLOCK, max(window, 1))
+        blocks += 1
+        if last:
+            break
+    if fhd & 4:
+        p += 4
+    if p > n:
+        return None
+    return FrameSpan(p - off, content, bound, window, False, blocks)
+
+
+class Reader:
+    """zstd.NewReader / Decoder.Read / WriteTo / Reset (zstd/decoder.go:84-310) for a stream of frames.  The reference runs a
+    three-stage goroutine pipeline over the blocks of one frame at a time (startStreamDecoder, zstd/decoder.go:655-950); on
+    the GPU the unit of parallelism is the frame: the reader walks frame and block headers on the host (frame_span), gathers
+    complete frames up to ``batch_bytes`` of input and decodes the batch in one call -- every frame its own warp / block set.
+    A stream written by this package's Writer (frames of four blocks) is decoded on the staged fast path."""
+
+    def __init__(self, r, device=0, max_window=128 << 20, max_frame=256 << 20, batch_bytes=16 << 20, read_size=1 << 20,
+                 decoder=None):
+        self._dec = decoder if decoder is not None else Decoder(device=device)
+        self._own = decoder is None
+        self._max_window, self._max_frame, self._batch, self._rs = max_window, max_frame, batch_bytes, read_size
+        self.Reset(r)
+
+    def Reset(self, r):
+        """Start over on a new source, keeping the device context (zstd/decoder.go:166-232)."""
+        self._r = r
+        self._in = bytearray()
+        self._out = bytearray()
+        self._eof = False
+        self._err = None
+        self.frames = 0
+
+    def _fill(self, push=False):
+        """Decode the next batch of complete frames into the output queue.  Returns False at the clean end of the stream; an
+        error is raised once everything decoded before it has been handed out.  push: never read the source -- stop at the
+        first incomplete frame."""
+        if self._err:
+            raise self._err
+        spans, pos = [], 0
+        while True:
+            sp = None
+            if pos < len(self._in):
+                try:
+                    sp = frame_span(self._in, pos, self._max_window)
+                except ZstdError as e:
+                    self._err = e
+                    break
+            if sp is None:                                   # the input ends inside a frame (or exactly between frames)
+                if push:
+                    break
+                if self._eof:
+                    if pos < len(self._in):
+                        self._err = ZstdError(ErrUnexpectedEOF)        # io.ErrUnexpectedEOF
+                    break
+                if spans and len(self._in) >= self._batch:
+                    break                                    # enough for a batch; the partial frame waits for the next call
+                chunk = self._r.read(self._rs)
+                if chunk:
+                    self._in += chunk
+                else:
+                    self._eof = True
+                continue
+            if not sp.skippable:
+                cap = sp.content_size if sp.content_size is not None else sp.bound
+                if cap > self._max_frame:
+                    self._err = ZstdError(ErrDecoderSizeExceeded)
+                    break
+                spans.append((pos, sp.length, cap))
+            pos += sp.length
+            if pos >= self._batch:
+                break
+        before = len(self._out)
+        if spans:
+            view = bytes(self._in[:pos])
+            outs, codes = self._dec.decode_chunks([view[o:o + ln] for o, ln, _ in spans], [max(c, 1) for _, _, c in spans])
+            for out, code in zip(outs, codes):
+                if code < 0:
+                    self._err = ZstdError(code)
+                    break
+                self._out += out
+                self.frames += 1
+        del self._in[:pos]
+        if self._err:
+            if len(self._out) > before or self._out:
+                return True                                  # hand out what was decoded; the error comes with the next call
+            raise self._err
+        return bool(spans) or pos > 0 or not self._eof
+
+    def read(self, size=-1):
+        """Up to ``size`` decoded bytes (all that remains for size < 0); b"" at the end of the stream."""
+        while size < 0 or len(self._out) < size:
+            if self._err and self._out:
+                break                                        # what precedes an error is delivered first
+            if not self._fill():
+                break
+        if size < 0 or size >= len(self._out):
+            out = bytes(self._out); self._out.clear()
+            return out
+        out = bytes(self._out[:size])
+        del self._out[:size]
+        return out
+
+    Read = read
+
+    def Feed(self, data):
+        """Push form, for callers that are handed the compressed bytes piecewise (a zip reader): append data, decode every
+        complete frame now buffered and return the decoded bytes; a partial frame stays pending (see Pending)."""
+        self._in += data
+        while self._in and not self._err:
+            before = len(self._in)
+            self._fill(push=True)
+            if len(self._in) == before:
+                break
+        if self._err and not self._out:
+            raise self._err
+        out = bytes(self._out)
+        self._out.clear()
+        return out
+
+    def Pending(self):
+        """Compressed bytes buffered but not yet decoded (an incomplete frame)."""
+        return len(self._in)
+
+    def WriteTo(self, w):
+        """Decode everything that remains into w; returns the byte count (zstd/decoder.go:287-310)."""
+        total = 0
+        while True:
+            if self._out:
+                total += len(self._out)
+                w.write(bytes(self._out)); self._out.clear()
+            if not self._fill():
+                break
+        if self._out:
+            total += len(self._out)
+            w.write(bytes(self._out)); self._out.clear()
+        return total
+
+    def Close(self):
+        if self._own and self._dec is not None:
+            self._dec.close()
+        self._dec = None
+
+    close = Close
 
 
 # ---- coalescing queue (the shim's batching of concurrent one-block calls) ----------------------------------------
