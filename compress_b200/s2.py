@@ -6,7 +6,8 @@ Names follow klauspost/compress/s2: ``Encode`` (s2/encode.go:29), ``EncodeBetter
 The work is done by libb200comp.so through the C ABI in include/b2c.h; device blocks are at most 64 KiB (the
 ``WriterBlockSize`` the GPU path is built for): ``encode_blocks`` raises ``ErrTooLarge`` beyond that, ``Encode*`` join
 64 KiB pieces into one block with ``ConcatBlocks`` (s2/encode.go:322), ``EncodeStream`` / ``DecodeStream`` are the framing
-format (s2.Writer / s2.Reader over a buffer).
+format (s2.Writer / s2.Reader over a buffer), ``EncodeStream(index=True)`` / ``DecodeStreamRange`` the seek index on top of it
+(``s2_index.py``).
 """
 import ctypes
 
@@ -14,6 +15,8 @@ import numpy as np
 import torch
 
 from ._lib import lib, check, B2CError
+from . import s2_index
+from .s2_index import Index, IndexStream, RemoveIndexHeaders, RestoreIndexHeaders   # noqa: F401  (s2/index.go)
 
 BLOCK = 1 << 16
 SLOT = BLOCK + 512
@@ -209,7 +212,7 @@ class Codec:
         return outs[0]
 
     # ---- streams: the framing format (s2.Writer.EncodeBuffer / s2.Reader, s2/writer.go:357-470, s2/reader.go:249-420) ----
-    def EncodeStream(self, src, better=False, snappy=False, block_size=BLOCK):
+    def EncodeStream(self, src, better=False, snappy=False, block_size=BLOCK, index=False):
         """Writer.EncodeBuffer(src) + Close(): a complete S2 (or Snappy) stream -- identifier, one checksummed chunk per
         block.  block_size <= 64 KiB (WriterBlockSize)."""
         buf = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(0, dtype=np.uint8)
@@ -219,7 +222,16 @@ class Codec:
         rc = lib.b2c_s2_encode_stream(self._ctx, BETTER if better else FAST, FLAG_SNAPPY if snappy else 0, buf.ctypes.data, len(src),
                                       block_size, out.ctypes.data, cap, ctypes.byref(n))
         check(rc, self._ctx)
-        return out[: n.value].tobytes()
+        stream = out[: n.value].tobytes()
+        if index:                          # WriterAddIndex(): the seek index as a trailing skippable chunk (s2/writer.go, s2/index.go)
+            stream += s2_index.IndexStream(stream, est_block=block_size)
+        return stream
+
+    def DecodeStreamRange(self, stream, start, length=None, index=None):
+        """Content bytes [start, start+length) of an indexed stream, decoding only the chunks that cover them (the
+        ReadSeeker use of the index, s2/index_test.go:16-104).  index: separately stored index bytes; default: the one
+        appended to the stream."""
+        return s2_index.read_range(stream, start, length, self.DecodeStream, index)
 
     def encode_stream_device(self, src, better=False, snappy=False, block_size=BLOCK, dst=None):
         """src: uint8 CUDA tensor.  Returns (dst uint8 CUDA tensor, total uint64 CUDA tensor [1], err int32 CUDA tensor [1]).  Async."""
