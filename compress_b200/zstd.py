@@ -26,14 +26,12 @@ FLAG_FRAME = 2
 
 
 class Encoder:
-    """zstd.Encoder for independent chunks on one B200.
+    """zstd.Encoder on one B200: batches of independent blocks (one-block frames: encode_device / encode_chunks /
+    encode_packed) and frame mode (encode_frames / EncodeAll: one multi-block frame per input, blocks with history).
+    padding: WithEncoderPadding -- EncodeAll output and a Writer's total are brought to a multiple of it with a skippable
+    frame (zstd/encoder_options.go, zstd/frameenc.go:96-137)."""
 
-    EncodeAll(src) splits src into chunks of the level's block size (64 KiB at SpeedFastest, 128 KiB at
-    SpeedDefault), each encoded as one complete zstd frame (the reference's EncodeAll emits a single multi-block
-    frame with cross-block history; concatenated frames decode to the same bytes, zstd/encoder.go:719).
-    """
-
-    def __init__(self, level=SpeedFastest, crc=True, device=0, max_chunks=4096):
+    def __init__(self, level=SpeedFastest, crc=True, device=0, max_chunks=4096, padding=0):
         if not torch.cuda.is_available() or lib.b2c_device_count() == 0:
             raise B2CError("no CUDA device: compress_b200 has no CPU fallback")
         if level not in BLOCK:
@@ -44,6 +42,9 @@ class Encoder:
         self.flags = (FLAG_CRC if crc else 0) | FLAG_FRAME
         self.device = device
         self.max_chunks = max_chunks
+        if padding < 0 or padding > 1 << 30:
+            raise B2CError("padding must be in [0, 1 GiB]")
+        self.padding = padding
         self._ctx = lib.b2c_ctx_create(device, max_chunks)
         if not self._ctx:
             raise B2CError("b2c_ctx_create failed")
@@ -225,6 +226,8 @@ class Encoder:
         else:
             buf, total, _, _ = self.encode_packed(src)
             out = bytes(buf[:total].numpy())
+        if self.padding:
+            out = skippableFrame(out, calcSkippableFrame((len(dst) if dst is not None else 0) + len(out), self.padding))
         if dst is not None:
             dst += out
             return dst
@@ -236,22 +239,30 @@ class Writer:
     are gathered and leave as complete frames -- one per Flush / Close, or every `frame_bytes` of input -- each a multi-block
     frame whose blocks see their history.  Concatenated frames are one valid zstd stream (zstd/encoder.go:719)."""
 
-    def __init__(self, w, level=SpeedFastest, crc=True, device=0, frame_bytes=None, encoder=None):
+    def __init__(self, w, level=SpeedFastest, crc=True, device=0, frame_bytes=None, encoder=None, padding=0):
         """frame_bytes: input bytes per frame; default four frame-mode blocks (192 KiB at SpeedFastest, 384 KiB above), the
         longest frames the staged GPU decoder takes on its fast path.  encoder: an Encoder to share
         (its level and checksum setting apply); by default the writer owns one."""
         self._w = w
-        self._enc = encoder if encoder is not None else Encoder(level=level, crc=crc, device=device, max_chunks=64)
+        self._enc = encoder if encoder is not None else Encoder(level=level, crc=crc, device=device, max_chunks=64,
+                                                                padding=padding)
         self._own = encoder is None
         self._buf = bytearray()
         self._frame_bytes = frame_bytes if frame_bytes else 4 * (49152 if level == SpeedFastest else 98304)
         self._wrote = False
+        self._nwritten = 0
 
     def Reset(self, w):
         """Discard pending state and write to w from now on, keeping the device context (zstd/encoder.go:100-121)."""
         self._w = w
         self._buf = bytearray()
         self._wrote = False
+        self._nwritten = 0
+
+    def _put(self, frame):
+        self._w.write(frame)
+        self._nwritten += len(frame)
+        self._wrote = True
 
     def Write(self, p):
         self._buf += p
@@ -262,8 +273,7 @@ class Writer:
     def _emit(self, n):
         part = bytes(self._buf[:n])
         del self._buf[:n]
-        self._w.write(self._enc.encode_frames([part])[0])
-        self._wrote = True
+        self._put(self._enc.encode_frames([part])[0])
 
     def Flush(self):
         if self._buf:
@@ -272,8 +282,10 @@ class Writer:
     def Close(self):
         self.Flush()
         if not self._wrote:          # an empty stream is still a frame (WithZeroFrames, zstd/encoder.go:732-751)
-            self._w.write(self._enc.encode_frames([b""])[0])
-            self._wrote = True
+            self._put(self._enc.encode_frames([b""])[0])
+        pad = getattr(self._enc, "padding", 0)
+        if pad:                      # WithEncoderPadding: the stream's total becomes a multiple (zstd/encoder.go Close)
+            self._put(skippableFrame(b"", calcSkippableFrame(self._nwritten, pad)))
         if self._own:
             self._enc.close()
 
@@ -398,6 +410,188 @@ MIN_WINDOW = 1 << 10                  # MinWindowSize, zstd/zstd.go
 MAX_BLOCK = 128 << 10                 # maxCompressedBlockSize, zstd/blockdec.go:41-45
 ErrReservedBit = ErrCorrupt
 ErrUnexpectedEOF = -5
+
+
+HeaderMaxSize = 14 + 3                 # zstd/decodeheader.go:13
+
+
+class ErrUnexpectedEOFHeader(B2CError):
+    """io.ErrUnexpectedEOF from Header.Decode: the input ends inside the header."""
+
+
+def frame_header_bytes(content_size, window_size=0, single_segment=False, checksum=False, dict_id=0):
+    """frameHeader.appendTo (zstd/frameenc.go:25-92): magic, descriptor, window byte unless single segment, dictionary id,
+    content size in the shortest of the 0/1/2/4/8-byte forms (frames < 256 bytes store none unless single segment)."""
+    fhd = (4 if checksum else 0) | (0x20 if single_segment else 0)
+    did = b""
+    if dict_id > 0:
+        if dict_id < 256:
+            fhd |= 1; did = bytes([dict_id])
+        elif dict_id < 1 << 16:
+            fhd |= 2; did = dict_id.to_bytes(2, "little")
+        else:
+            fhd |= 3; did = dict_id.to_bytes(4, "little")
+    fcs = (content_size >= 256) + (content_size >= 65536 + 256) + (content_size >= 0xFFFFFFFF)
+    fhd |= fcs << 6
+    out = bytearray(b"\x28\xb5\x2f\xfd")
+    out.append(fhd)
+    if not single_segment:
+        out.append(((max(int(window_size) - 1, 0).bit_length() - 10) << 3) & 0xFF)
+    out += did
+    if fcs == 0:
+        if single_segment:
+            out.append(content_size & 0xFF)
+    elif fcs == 1:
+        out += (content_size - 256).to_bytes(2, "little")
+    elif fcs == 2:
+        out += content_size.to_bytes(4, "little")
+    else:
+        out += content_size.to_bytes(8, "little")
+    return bytes(out)
+
+
+def calcSkippableFrame(written, want_multiple):
+    """Bytes to add so that `written` becomes a multiple of want_multiple: 0, or a total >= 8 (a skippable frame's header)
+    (zstd/frameenc.go:96-116)."""
+    if want_multiple <= 0:
+        raise ValueError("wantMultiple <= 0")
+    if written < 0:
+        raise ValueError("written < 0")
+    left = written % want_multiple
+    if left == 0:
+        return 0
+    add = want_multiple - left
+    while add < 8:
+        add += want_multiple
+    return add
+
+
+def skippableFrame(dst, total, fill=None):
+    """Append a skippable frame of `total` bytes in all (zstd/frameenc.go:118-137); its content comes from fill(n) -> bytes
+    (default os.urandom, the reference's crypto/rand.Reader)."""
+    if total == 0:
+        return dst
+    if total < 8:
+        raise ValueError("requested skippable frame (%d) < 8" % total)
+    if total > 0xFFFFFFFF:
+        raise ValueError("requested skippable frame (%d) > max uint32" % total)
+    import os
+    body = (fill or os.urandom)(total - 8)
+    if len(body) != total - 8:
+        raise ErrUnexpectedEOFHeader("short read filling a skippable frame")
+    return dst + b"\x50\x2a\x4d\x18" + (total - 8).to_bytes(4, "little") + body
+
+
+class Header:
+    """zstd.Header (zstd/decodeheader.go:15-76): what the first bytes of a frame say, without decoding anything."""
+
+    class Block:
+        __slots__ = ("OK", "Last", "Compressed", "DecompressedSize", "CompressedSize")
+
+        def __init__(self):
+            self.OK = self.Last = self.Compressed = False
+            self.DecompressedSize = self.CompressedSize = 0
+
+    def __init__(self):
+        self._clear()
+
+    def _clear(self):
+        self.SingleSegment = False
+        self.WindowSize = 0
+        self.DictionaryID = 0
+        self.HasFCS = False
+        self.FrameContentSize = 0
+        self.Skippable = False
+        self.SkippableID = 0
+        self.SkippableSize = 0
+        self.HeaderSize = 0
+        self.FirstBlock = Header.Block()
+        self.HasCheckSum = False
+
+    def Decode(self, data):
+        """Header.Decode (zstd/decodeheader.go:78-86); at least HeaderMaxSize bytes give every field."""
+        self.DecodeAndStrip(data)
+
+    def DecodeAndStrip(self, data):
+        """-> the bytes after the header (zstd/decodeheader.go:88-229).  ErrUnexpectedEOFHeader when the input ends inside
+        the header, ZstdError(ErrMagicMismatch / ErrReservedBit) as the reference."""
+        self._clear()
+        b = bytes(data)
+        if len(b) < 4:
+            raise ErrUnexpectedEOFHeader("unexpected EOF")
+        self.HeaderSize = 4
+        if b[:4] != b"\x28\xb5\x2f\xfd":
+            if b[1:4] != b"\x2a\x4d\x18" or b[0] & 0xF0 != 0x50:
+                raise ZstdError(ErrMagicMismatch)
+            if len(b) < 8:
+                raise ErrUnexpectedEOFHeader("unexpected EOF")
+            self.HeaderSize = 8
+            self.Skippable = True
+            self.SkippableID = b[0] & 0xF
+            self.SkippableSize = int.from_bytes(b[4:8], "little")
+            return b[8:]
+        p = 4
+        if len(b) <= p:
+            raise ErrUnexpectedEOFHeader("unexpected EOF")
+        fhd = b[p]; p += 1
+        self.SingleSegment = bool(fhd & 0x20)
+        self.HasCheckSum = bool(fhd & 4)
+        if fhd & 8:
+            raise ZstdError(ErrReservedBit)
+        if not self.SingleSegment:
+            if len(b) <= p:
+                raise ErrUnexpectedEOFHeader("unexpected EOF")
+            wd = b[p]; p += 1
+            base = 1 << (10 + (wd >> 3))
+            self.WindowSize = base + (base // 8) * (wd & 7)
+        size = (0, 1, 2, 4)[fhd & 3]
+        if size:
+            if len(b) - p < size:
+                raise ErrUnexpectedEOFHeader("unexpected EOF")
+            self.DictionaryID = int.from_bytes(b[p:p + size], "little")
+            p += size
+        v = fhd >> 6
+        fcs = (1 if self.SingleSegment else 0) if v == 0 else 1 << v
+        if fcs:
+            self.HasFCS = True
+            if len(b) - p < fcs:
+                raise ErrUnexpectedEOFHeader("unexpected EOF")
+            self.FrameContentSize = int.from_bytes(b[p:p + fcs], "little") + (256 if fcs == 2 else 0)
+            p += fcs
+        self.HeaderSize = p
+        rest = b[p:]
+        if len(rest) < 3:
+            return rest
+        bh = rest[0] | rest[1] << 8 | rest[2] << 16
+        fb = self.FirstBlock
+        fb.Last = bool(bh & 1)
+        typ, size = (bh >> 1) & 3, bh >> 3
+        if typ == 3:
+            return rest
+        if typ == 1:
+            fb.Compressed, fb.DecompressedSize, fb.CompressedSize = True, size, 1
+        elif typ == 2:
+            fb.Compressed, fb.CompressedSize = True, size
+        else:
+            fb.DecompressedSize = fb.CompressedSize = size
+        fb.OK = True
+        return rest
+
+    def AppendTo(self, dst=b""):
+        """The header these fields describe, appended to dst (zstd/decodeheader.go:231-252)."""
+        if self.Skippable:
+            return dst + bytes([0x50 | (self.SkippableID & 0xF), 0x2A, 0x4D, 0x18]) + (self.SkippableSize & 0xFFFFFFFF).to_bytes(4, "little")
+        return dst + frame_header_bytes(self.FrameContentSize, self.WindowSize & 0xFFFFFFFF, self.SingleSegment, self.HasCheckSum,
+                                        self.DictionaryID)
+
+    def as_dict(self):
+        fb = self.FirstBlock
+        return {"SingleSegment": self.SingleSegment, "WindowSize": self.WindowSize, "DictionaryID": self.DictionaryID,
+                "HasFCS": self.HasFCS, "FrameContentSize": self.FrameContentSize, "Skippable": self.Skippable,
+                "SkippableID": self.SkippableID, "SkippableSize": self.SkippableSize, "HeaderSize": self.HeaderSize,
+                "FirstBlock": {"OK": fb.OK, "Last": fb.Last, "Compressed": fb.Compressed, "DecompressedSize": fb.DecompressedSize,
+                               "CompressedSize": fb.CompressedSize},
+                "HasCheckSum": self.HasCheckSum}
 
 
 class FrameSpan:

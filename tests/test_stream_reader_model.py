@@ -239,3 +239,86 @@ def test_zip_adapters(oracle_lib, tmp_path):
         ZZ.Unregister()
     with pytest.raises(NotImplementedError):
         zipfile.ZipFile(str(tmp_path / "c.zip"), "w", compression=93)
+
+
+def test_header_decode_golden_vectors():
+    """TestHeader_Decode (zstd/decodeheader_test.go:12): every entry of headers.zip gives exactly the Header of
+    headers-want.json.zst through the host mirror's Header.Decode, or fails where the reference has no entry; AppendTo of a
+    decoded header decodes to the same fields again."""
+    import json
+    golden = json.loads(H.libzstd_decode(open(os.path.join(H.GOLDEN, "zstd_headers-want.json.zst"), "rb").read(), 32 << 20))
+    zh = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_headers.zip"))
+    ok = bad = 0
+    for nm in zh.namelist():
+        b = zh.read(nm)
+        h = Z.Header()
+        try:
+            h.Decode(b)
+        except (Z.ZstdError, Z.ErrUnexpectedEOFHeader):
+            assert nm not in golden, nm
+            bad += 1
+            continue
+        assert h.as_dict() == golden[nm], nm
+        ok += 1
+        if not h.Skippable and h.WindowSize <= 0xFFFFFFFF and not (h.SingleSegment and not h.HasFCS):
+            again = Z.Header()
+            again.Decode(h.AppendTo())
+            for f in ("SingleSegment", "DictionaryID", "HasCheckSum"):
+                assert getattr(again, f) == getattr(h, f), (nm, f)
+            if h.SingleSegment or h.FrameContentSize >= 256:     # smaller sizes are not stored (zstd/frameenc.go:75-79)
+                assert again.FrameContentSize == h.FrameContentSize, nm
+            if not h.SingleSegment and h.WindowSize >= 1 << 10:
+                assert again.WindowSize >= h.WindowSize // 2, nm   # the writer stores a power of two that covers it
+    assert ok == len(golden) and ok + bad == len(zh.namelist()) and ok > 1000 and bad > 1000
+
+
+def test_frame_header_and_padding(oracle_lib):
+    # frame_header_bytes == the header of the oracle's frames (frameHeader.appendTo) for sizes around every form change
+    for n in (0, 1, 255, 256, 257, 1024, 1025, 65535, 65536, 65791, 65792, 70000):
+        data = bytes(n)
+        frame = H.oracle_encode(data, 1)[1]
+        h = Z.Header(); h.Decode(frame)
+        assert frame.startswith(h.AppendTo()), n
+        assert Z.frame_span(frame).content_size in (n, None)
+    # calcSkippableFrame (zstd/frameenc.go:96-116): result is 0 or >= 8, and lands on the multiple
+    for written in (0, 1, 7, 8, 100, 1023, 1024, 1025, 4095):
+        for mult in (1, 2, 8, 16, 1000, 1024, 4096):
+            add = Z.calcSkippableFrame(written, mult)
+            assert (written + add) % mult == 0 and (add == 0 or add >= 8)
+            if written % mult == 0:
+                assert add == 0
+            elif mult - written % mult >= 8:
+                assert add == mult - written % mult
+    with pytest.raises(ValueError):
+        Z.calcSkippableFrame(10, 0)
+    with pytest.raises(ValueError):
+        Z.calcSkippableFrame(-1, 8)
+    # skippableFrame: invisible to decoders
+    frame = H.oracle_encode(b"hello world" * 50, 1)[1]
+    add = Z.calcSkippableFrame(len(frame), 512)
+    padded = Z.skippableFrame(frame, add)
+    assert len(padded) == 512 and padded[len(frame):len(frame) + 4] == b"\x50\x2a\x4d\x18"
+    assert H.libzstd_decode(padded, 1000) == b"hello world" * 50
+    r, got = H.oracle_decode(padded, 1000)
+    assert got == b"hello world" * 50
+    sp = Z.frame_span(padded, len(frame))
+    assert sp.skippable and sp.length == add
+    assert Z.skippableFrame(b"x", 0) == b"x"
+    with pytest.raises(ValueError):
+        Z.skippableFrame(b"", 7)
+    assert Z.skippableFrame(b"", 12, fill=lambda n: b"\x01" * n) == b"\x50\x2a\x4d\x18\x04\x00\x00\x00\x01\x01\x01\x01"
+
+
+def test_writer_padding(oracle_lib):
+    """WithEncoderPadding on the stream writer: the total written is a multiple, the padding a skippable frame."""
+    enc = LibzstdEncoder(); enc.padding = 4096
+    sink = io.BytesIO()
+    w = Z.Writer(sink, encoder=enc, frame_bytes=30000)
+    data = H.golden("twain.txt")[:100000]
+    w.Write(data); w.Close()
+    out = sink.getvalue()
+    assert len(out) % 4096 == 0
+    assert Z.Reader(io.BytesIO(out), decoder=OracleDecoder()).read() == data
+    assert H.libzstd_decode(out, len(data)) == data
+    h = Z.Header(); h.Decode(out[out.rindex(b"\x50\x2a\x4d\x18"):])
+    assert h.Skippable and h.HeaderSize == 8
