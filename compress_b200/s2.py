@@ -263,3 +263,322 @@ class Codec:
             raise ErrUnsupported("s2: unsupported input")
         check(rc, self._ctx)
         return out[: n.value].tobytes()
+
+
+# ---- stream writer / reader over io objects (s2.NewWriter / s2.NewReader) --------------------------------------------------
+MAGIC_S2 = b"\xff\x06\x00\x00S2sTwO"
+MAGIC_SNAPPY = b"\xff\x06\x00\x00sNaPpY"
+_CHUNK_PADDING = 0xFE
+
+
+def calcSkippableFrame(written, want_multiple):
+    """s2/writer.go:854-874: bytes to add (0, or >= the 4-byte chunk header) to reach a multiple."""
+    if want_multiple <= 0 or written < 0:
+        raise ValueError("calcSkippableFrame: bad arguments")
+    left = written % want_multiple
+    if left == 0:
+        return 0
+    add = want_multiple - left
+    while add < 4:
+        add += want_multiple
+    return add
+
+
+def skippableFrame(total, fill=None):
+    """A padding chunk (type 0xfe) of `total` bytes in all (s2/writer.go:876-898); content from fill(n), default os.urandom."""
+    if total == 0:
+        return b""
+    if total < 4:
+        raise ValueError("s2: requested skippable frame (%d) < 4" % total)
+    if total >= (4 << 20) + 4:
+        raise ValueError("s2: requested skippable frame (%d) >= max 1<<24" % total)
+    import os
+    return bytes([_CHUNK_PADDING]) + (total - 4).to_bytes(3, "little") + (fill or os.urandom)(total - 4)
+
+
+def _walk_chunks(buf, pos, end):
+    """Yield (type, start, length incl. header, decoded length or None) for the complete chunks of buf[pos:end]."""
+    while end - pos >= 4:
+        typ = buf[pos]
+        ln = buf[pos + 1] | buf[pos + 2] << 8 | buf[pos + 3] << 16
+        if pos + 4 + ln > end:
+            return
+        d = None
+        if typ == 0x00 and ln >= 5:
+            d = _decoded_len(bytes(buf[pos + 8:pos + 4 + min(ln, 14)]))[0]
+        elif typ == 0x01 and ln >= 4:
+            d = ln - 4
+        yield typ, pos, 4 + ln, d
+        pos += 4 + ln
+
+
+class Writer:
+    """s2.Writer (NewWriter / Write / EncodeBuffer / ReadFrom / Flush / Close / CloseIndex / Reset, s2/writer.go:34-852) over
+    the device stream encoder: input is gathered and leaves in batches of `batch_bytes` (a multiple of the block size) through
+    ONE EncodeStream call each -- all blocks of the batch in parallel -- with the stream identifier kept on the first batch
+    only.  add_index = WriterAddIndex, padding = WriterPadding (the padding chunk comes before the index so that the index
+    stays at the end), better / snappy / block_size = WriterBetterCompression / WriterSnappyCompat / WriterBlockSize."""
+
+    def __init__(self, w, codec=None, device=0, block_size=BLOCK, better=False, snappy=False, add_index=False, padding=0,
+                 batch_bytes=8 << 20, rand=None):
+        if not 4096 <= block_size <= BLOCK:
+            raise ErrUnsupported("s2: block size on the device path: 4 KiB .. 64 KiB")
+        self._codec = codec if codec is not None else Codec(device=device)
+        self._own = codec is None
+        self._bs, self._better, self._snappy = block_size, better, snappy
+        self._add_index, self._pad, self._rand = add_index, padding, rand
+        self._batch = max(block_size, batch_bytes // block_size * block_size)
+        self.Reset(w)
+
+    def Reset(self, w):
+        self._w = w
+        self._buf = bytearray()
+        self._wrote_header = False
+        self.written = 0                 # compressed bytes handed to w
+        self.uncomp_written = 0
+        self._index = s2_index.Index()
+        self._index.reset(self._bs)
+        self._closed = False
+
+    def _out(self, b):
+        self._w.write(b)
+        self.written += len(b)
+
+    def _emit(self, data):
+        piece = self._codec.EncodeStream(bytes(data), better=self._better, snappy=self._snappy, block_size=self._bs)
+        body = piece[10:]
+        if not self._wrote_header:
+            self._out(piece[:10])
+            self._wrote_header = True
+        base, u = self.written, self.uncomp_written
+        for typ, start, ln, d in _walk_chunks(body, 0, len(body)):
+            if d is not None:
+                self._index.add(base + start, u)
+                u += d
+        if u - self.uncomp_written != len(data):
+            raise ErrCorrupt("s2: stream encoder returned %d bytes of content for %d" % (u - self.uncomp_written, len(data)))
+        self._out(body)
+        self.uncomp_written = u
+
+    def Write(self, p):
+        if self._closed:
+            raise B2CError("s2: Writer is closed")
+        self._buf += p
+        while len(self._buf) >= self._batch:
+            self._emit(self._buf[:self._batch])
+            del self._buf[:self._batch]
+        return len(p)
+
+    def EncodeBuffer(self, buf):
+        """Encode a whole buffer (after whatever is pending): s2/writer.go:357-470."""
+        self.Flush()
+        view = memoryview(bytes(buf))
+        for o in range(0, len(view), self._batch):
+            self._emit(view[o:o + self._batch])
+
+    def ReadFrom(self, r):
+        """Encode everything r yields until EOF; returns the byte count (s2/writer.go:220-300)."""
+        n = 0
+        while True:
+            chunk = r.read(self._batch)
+            if not chunk:
+                break
+            n += len(chunk)
+            self.Write(chunk)
+        return n
+
+    def Flush(self):
+        if self._buf:
+            self._emit(self._buf)
+            self._buf = bytearray()
+
+    def _close(self, want_index):
+        if self._closed:
+            raise B2CError("s2: Writer is closed")
+        self.Flush()
+        index = b""
+        if want_index or self._add_index:
+            if not self._wrote_header:                         # an index needs a stream to sit in
+                self._out(MAGIC_SNAPPY if self._snappy else MAGIC_S2)
+                self._wrote_header = True
+            comp = self.written if self._pad <= 1 else -1
+            index = self._index.appendTo(b"", self.uncomp_written, comp)
+            if self._add_index:
+                self.written += len(index)                     # counted for the padding; written last
+        if self._pad > 1 and self._wrote_header:
+            self._w.write(skippableFrame(calcSkippableFrame(self.written, self._pad), self._rand))
+        if index and self._add_index:
+            self._w.write(index)
+        self._closed = True
+        if self._own:
+            self._codec.close()
+        return index
+
+    def Close(self):
+        self._close(False)
+
+    def CloseIndex(self):
+        """Close and return the index for separate storage (s2/writer.go:787-796)."""
+        return self._close(True)
+
+
+class Reader:
+    """s2.Reader (NewReader / Read / Skip / DecodeConcurrent / Reset, s2/reader.go:31-672) over the device stream decoder: the
+    4-byte chunk headers are walked on the host to cut the input at chunk boundaries, complete chunks are gathered up to
+    `batch_bytes` and decoded by ONE DecodeStream call (all blocks of the batch in parallel, checksums verified on the device).
+    Skip drops whole chunks without decoding them where it can (as the reference does); what was decoded before a damaged chunk is
+    delivered before the error."""
+
+    def __init__(self, r, codec=None, device=0, batch_bytes=8 << 20, read_size=1 << 20, ignore_stream_identifier=False):
+        self._codec = codec if codec is not None else Codec(device=device)
+        self._own = codec is None
+        self._batch, self._rs, self._ignore_id = batch_bytes, read_size, ignore_stream_identifier
+        self.Reset(r)
+
+    def Reset(self, r):
+        self._r = r
+        self._in = bytearray()
+        self._out = bytearray()
+        self._eof = False
+        self._err = None
+        self._seen_id = self._ignore_id
+        self._magic = MAGIC_S2
+        self._skip = 0
+
+    def _decode(self, pieces):
+        """pieces: list of chunk byte strings.  Decode as one batch; on an error find the chunk it belongs to, keeping the
+        output of the chunks before it."""
+        try:
+            return self._codec.DecodeStream(self._magic + b"".join(pieces)), None
+        except (ErrCorrupt, ErrCRC, ErrUnsupported) as e:
+            if len(pieces) == 1:
+                return b"", e
+        out = bytearray()
+        for p in pieces:
+            try:
+                out += self._codec.DecodeStream(self._magic + p)
+            except (ErrCorrupt, ErrCRC, ErrUnsupported) as e:
+                return bytes(out), e
+        return bytes(out), ErrCorrupt("s2: corrupt input")
+
+    def _fill(self):
+        if self._err:
+            raise self._err
+        pieces, pos, flushed = [], 0, bytearray()
+        while True:
+            got = None
+            try:
+                for got in _walk_chunks(self._in, pos, len(self._in)):
+                    break
+            except ErrCorrupt as e:                            # a block length that is not a valid uvarint
+                self._err = e
+                break
+            if got is None:
+                if self._eof:
+                    if pos < len(self._in):
+                        self._err = ErrCorrupt("s2: corrupt input (unexpected EOF)")
+                    break
+                if pieces and len(self._in) >= self._batch:
+                    break
+                chunk = self._r.read(self._rs)
+                if chunk:
+                    self._in += chunk
+                else:
+                    self._eof = True
+                continue
+            typ, start, ln, d = got
+            if not self._seen_id:
+                if typ != 0xFF:
+                    self._err = ErrCorrupt("s2: corrupt input")
+                    break
+                self._seen_id = True
+            piece = bytes(self._in[start:start + ln])
+            pos = start + ln
+            if typ == 0xFF:
+                if pieces:                                     # a new stream: decode what precedes under the old identifier
+                    pos = start
+                    break
+                if piece == MAGIC_SNAPPY:
+                    self._magic = MAGIC_SNAPPY
+                elif piece == MAGIC_S2:
+                    self._magic = MAGIC_S2
+                else:
+                    self._err = ErrCorrupt("s2: corrupt input")
+                    break
+                continue
+            if d is not None and self._skip >= d > 0 and typ in (0, 1):
+                self._skip -= d                                # Skip: the whole block is not wanted, do not decode it
+                continue
+            if typ >= 0x80:
+                continue                                       # padding, index and other skippable chunks
+            pieces.append(piece)
+            if pos >= self._batch:
+                break
+        if pieces:
+            out, err = self._decode(pieces)
+            if self._skip:
+                k = min(self._skip, len(out))
+                out = out[k:]
+                self._skip -= k
+            self._out += out
+            if err is not None:
+                self._err = err                                # (comes before any later structural error)
+        del self._in[:pos]
+        if self._err:
+            if self._out:
+                return True
+            raise self._err
+        return bool(pieces) or pos > 0 or not self._eof
+
+    def read(self, size=-1):
+        while size < 0 or len(self._out) < size:
+            if self._err and self._out:
+                break
+            if not self._fill():
+                break
+        if size < 0 or size >= len(self._out):
+            out = bytes(self._out)
+            self._out.clear()
+            return out
+        out = bytes(self._out[:size])
+        del self._out[:size]
+        return out
+
+    Read = read
+
+    def Skip(self, n):
+        """Skip n bytes of content forward (s2/reader.go:674-800)."""
+        if n < 0:
+            raise ValueError("attempted negative skip")
+        k = min(n, len(self._out))
+        del self._out[:k]
+        n -= k
+        self._skip += n
+        while self._skip:
+            if not self._fill():
+                raise ErrCorrupt("s2: corrupt input (unexpected EOF)")     # io.ErrUnexpectedEOF: skipped past the end
+            if self._skip == 0:
+                break
+            if self._out:                      # (cannot happen: _fill consumes the skip first)
+                break
+
+    def DecodeConcurrent(self, w, concurrent=0):
+        """Decode all that remains into w; returns the byte count (s2/reader.go:413-672; the concurrency is the device's)."""
+        total = 0
+        while True:
+            if self._out:
+                total += len(self._out)
+                w.write(bytes(self._out))
+                self._out.clear()
+            if not self._fill():
+                break
+        if self._out:
+            total += len(self._out)
+            w.write(bytes(self._out))
+            self._out.clear()
+        return total
+
+    def Close(self):
+        if self._own and self._codec is not None:
+            self._codec.close()
+        self._codec = None

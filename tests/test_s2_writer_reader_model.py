@@ -1,0 +1,172 @@
+"""Host logic of the S2 stream Writer / Reader mirrors (s2.NewWriter / s2.NewReader) with a stand-in
+codec: the stream model of tests/s2_stream_ref.py over the oracle's block codecs plays EncodeStream / DecodeStream, which the
+product classes get from the GPU codec.  Batching, index and padding at Close, Skip, error order, Snappy streams,
+concatenated streams.  CPU only."""
+import ctypes
+import io
+
+import numpy as np
+import pytest
+
+import helpers as H
+import s2_stream_ref as R
+from compress_b200 import s2 as S
+from compress_b200 import s2_index as X
+
+
+class ModelCodec:
+    def __init__(self):
+        from test_oracle_s2 import s2_decode, _L
+        L = _L()
+        L.orc_s2_encode_block.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64, ctypes.c_int]
+        self.L, self.s2_decode = L, s2_decode
+        self.enc_calls, self.dec_calls = [], []
+
+    def _enc(self, mode):
+        def enc(blk):
+            out = ctypes.create_string_buffer(self.L.orc_s2_max_encoded_len(len(blk)) + 16)
+            r = self.L.orc_s2_encode_block(out, bytes(blk), len(blk), mode)
+            return out.raw[:r]                    # the block body (no length prefix); b"" = not compressible
+        return enc
+
+    def EncodeStream(self, src, better=False, snappy=False, block_size=65536, index=False):
+        self.enc_calls.append(len(src))
+        return R.write_stream(bytes(src), self._enc(2 if snappy else (1 if better else 0)), block_size=block_size, snappy=snappy)
+
+    def DecodeStream(self, stream, max_size=None):
+        self.dec_calls.append(len(stream))
+
+        def dec(body, n):
+            r, out = self.s2_decode(body, n)
+            return out if r == n else None
+        try:
+            return R.read_stream(bytes(stream), dec)
+        except ValueError as e:
+            raise {"corrupt": S.ErrCorrupt, "crc": S.ErrCRC, "unsupported": S.ErrUnsupported}[str(e)](str(e))
+
+    def close(self):
+        pass
+
+
+def _data(n, seed=1):
+    rng = np.random.default_rng(seed)
+    tw = H.golden("twain.txt")
+    return (tw * (n // len(tw) + 1))[:n // 2] + (rng.integers(0, 4, n - n // 2, dtype=np.uint8) + 48).astype(np.uint8).tobytes()
+
+
+def test_stand_in_codec(oracle_lib):
+    c = ModelCodec()
+    st = c.EncodeStream(b"hello hello hello hello hello hello hello hello hello hello hello hello hello hello hello")
+    assert c.DecodeStream(st).startswith(b"hello hello")
+
+
+def test_writer_batches_index_padding(oracle_lib):
+    data = _data(3 << 20)
+    c = ModelCodec()
+    sink = io.BytesIO()
+    w = S.Writer(sink, codec=c, batch_bytes=1 << 20, add_index=True, padding=4096, rand=lambda n: b"\x00" * n)
+    for o in range(0, len(data), 300001):
+        w.Write(data[o:o + 300001])
+    w.Close()
+    out = sink.getvalue()
+    assert c.enc_calls[:3] == [1 << 20] * 3 and sum(c.enc_calls) == len(data)      # one device call per full batch
+    assert out.count(S.MAGIC_S2) == 1 and out.startswith(S.MAGIC_S2)
+    assert len(out) % 4096 == 0
+    assert c.DecodeStream(out) == data
+    idx = X.Index(); idx.LoadStream(io.BytesIO(out))                                # the index is the last thing in the stream
+    assert idx.TotalUncompressed == len(data) and idx.TotalCompressed == -1          # unknown with padding (s2/writer.go:810-813)
+    assert idx.info[0] == (10, 0) and len(idx.info) == 3
+    for cmp_off, u in idx.info:
+        assert out[cmp_off] in (0, 1) and u % 65536 == 0
+    assert X.read_range(out, 2500000, 100, c.DecodeStream, idx) == data[2500000:2500100]
+    # without padding the index equals what IndexStream makes of the finished stream; CloseIndex returns it instead of appending
+    sink2 = io.BytesIO()
+    w = S.Writer(sink2, codec=c, batch_bytes=1 << 20)
+    w.EncodeBuffer(data)
+    ib = w.CloseIndex()
+    assert sink2.getvalue() + ib == sink2.getvalue() + X.IndexStream(sink2.getvalue(), est_block=65536)
+    with pytest.raises(S.B2CError):
+        w.Write(b"x")
+    # Flush cuts a short block; ReadFrom; Reset; Snappy + better flags reach the codec
+    sink3 = io.BytesIO()
+    w = S.Writer(sink3, codec=c, snappy=True, block_size=32768)
+    w.Write(b"abc" * 1000); w.Flush(); assert w.ReadFrom(io.BytesIO(data[:100000])) == 100000; w.Close()
+    assert sink3.getvalue().startswith(S.MAGIC_SNAPPY) and c.DecodeStream(sink3.getvalue()) == b"abc" * 1000 + data[:100000]
+    w.Reset(io.BytesIO()); w.Close()
+    with pytest.raises(S.ErrUnsupported):
+        S.Writer(io.BytesIO(), codec=c, block_size=1 << 20)
+
+
+class Dribble:
+    def __init__(self, data, k):
+        self.d, self.k, self.p = data, k, 0
+
+    def read(self, n=-1):
+        n = self.k if n < 0 else min(n, self.k)
+        out = self.d[self.p:self.p + n]
+        self.p += len(out)
+        return out
+
+
+@pytest.mark.parametrize("piece,batch", [(13, 1 << 20), (70000, 100000), (1 << 22, 1 << 22)])
+def test_reader_batches_skip_and_concat(oracle_lib, piece, batch):
+    data = _data(1 << 20, seed=2)
+    c = ModelCodec()
+    st = c.EncodeStream(data) + X.IndexStream(c.EncodeStream(data))
+    st2 = c.EncodeStream(data[:99999], snappy=True)
+    c.dec_calls.clear()
+    r = S.Reader(Dribble(st + st2, piece), codec=c, batch_bytes=batch, read_size=piece)
+    assert r.read(1000) == data[:1000]
+    r.Skip(300000)                                          # whole blocks inside are never decoded
+    assert r.read(5) == data[301000:301005]
+    rest = r.read()
+    assert rest == data[301005:] + data[:99999]
+    assert r.read() == b""
+    if batch >= 1 << 22:
+        assert len(c.dec_calls) == 2                        # one call per stream (the identifier ends a batch)
+    out = io.BytesIO()
+    r.Reset(io.BytesIO(st))
+    assert r.DecodeConcurrent(out) == len(data) and out.getvalue() == data
+    r.Reset(io.BytesIO(st))
+    with pytest.raises(S.ErrCorrupt):
+        r.Skip(len(data) + 1)
+
+
+def test_reader_errors(oracle_lib):
+    data = _data(400000, seed=3)
+    c = ModelCodec()
+    st = c.EncodeStream(data)
+    chunks = list(S._walk_chunks(st, 0, len(st)))
+    # damage the payload of the 4th data chunk: the three blocks before it are delivered, then the error
+    typ, start, ln, d = chunks[4]
+    bad = bytearray(st); bad[start + 8 + 20] ^= 0xFF
+    r = S.Reader(io.BytesIO(bytes(bad)), codec=c)
+    got = r.read()
+    assert got == data[:3 * 65536]
+    with pytest.raises((S.ErrCorrupt, S.ErrCRC)):
+        r.read()
+    with pytest.raises((S.ErrCorrupt, S.ErrCRC)):
+        r.read()
+    # truncated stream
+    r = S.Reader(io.BytesIO(st[:-7]), codec=c)
+    assert r.read() == data[:len(data) // 65536 * 65536]
+    with pytest.raises(S.ErrCorrupt):
+        r.read()
+    # no identifier
+    with pytest.raises(S.ErrCorrupt):
+        S.Reader(io.BytesIO(st[10:]), codec=c).read()
+    assert S.Reader(io.BytesIO(st[10:]), codec=c, ignore_stream_identifier=True).read() == data
+    # reserved unskippable chunk
+    with pytest.raises(S.ErrUnsupported):
+        S.Reader(io.BytesIO(S.MAGIC_S2 + b"\x05\x04\x00\x00abcd"), codec=c).read()
+    assert S.Reader(io.BytesIO(b""), codec=c).read() == b""
+
+
+def test_padding_helpers():
+    for written in (0, 1, 3, 4, 5, 100, 1023, 1024):
+        for mult in (1, 2, 4, 8, 512, 1024):
+            add = S.calcSkippableFrame(written, mult)
+            assert (written + add) % mult == 0 and (add == 0 or add >= 4)
+    assert S.skippableFrame(0) == b"" and S.skippableFrame(6, lambda n: b"ab") == b"\xfe\x02\x00\x00ab"
+    with pytest.raises(ValueError):
+        S.skippableFrame(3)
