@@ -49,11 +49,22 @@ def test_benchdecoder_files(oracle_lib, emu_lib):
     assert outs[0] == wants[pick[0]] + wants[pick[1]]
 
 
+def _xxh64(data):
+    import ctypes
+    L = H.oracle()
+    L.orc_xxh64.restype = ctypes.c_uint64
+    L.orc_xxh64.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint64]
+    return L.orc_xxh64(data, len(data), 0)
+
+
 def test_xml_zst(oracle_lib):
     comp = H.golden("zstd_xml.zst")
     r, got = H.oracle_decode(comp, 6 << 20)
     assert r == 5345280
     assert _libz(comp, r) == got
+    # the reference's known answers for the decoded content (XXH64 as big-endian bytes, zstd/encoder_test.go:538-561)
+    assert _xxh64(got) == 0x5654698E4050110E                      # TestEncoder_EncoderXML
+    assert _xxh64(H.golden("zstd_z000028")) == 0x8B023770920B9895  # TestEncoder_EncoderSimple
 
 
 def test_regression_zip(oracle_lib, emu_lib, staged_form):
