@@ -270,6 +270,17 @@ class Writer:
             self._emit(self._frame_bytes)
         return len(p)
 
+    def ReadFrom(self, r):
+        """Encode everything r yields until EOF (frames leave as they fill); returns the byte count; does not close
+        (zstd/encoder.go:203-260)."""
+        n = 0
+        while True:
+            chunk = r.read(self._frame_bytes)
+            if not chunk:
+                return n
+            n += len(chunk)
+            self.Write(chunk)
+
     def _emit(self, n):
         part = bytes(self._buf[:n])
         del self._buf[:n]

@@ -170,3 +170,23 @@ def test_padding_helpers():
     assert S.skippableFrame(0) == b"" and S.skippableFrame(6, lambda n: b"ab") == b"\xfe\x02\x00\x00ab"
     with pytest.raises(ValueError):
         S.skippableFrame(3)
+
+
+@pytest.mark.parametrize("better", [False, True])
+def test_framing_format(oracle_lib, better):
+    """TestFramingFormat / TestFramingFormatBetter (s2/s2_test.go:755-826): 1e6 bytes alternating 1e5 of noise and 1e5 of one
+    byte value -- larger than a block -- through Writer.Write + Close and back through the Reader."""
+    rng = np.random.default_rng(1)
+    src = bytearray(1000000)
+    for i in range(10):
+        src[100000 * i:100000 * (i + 1)] = bytes(rng.integers(0, 256, 100000, dtype=np.uint8)) if i % 2 == 0 else bytes([i]) * 100000
+    src = bytes(src)
+    c = ModelCodec()
+    buf = io.BytesIO()
+    bw = S.Writer(buf, codec=c, better=better)
+    assert bw.Write(src) == len(src)
+    bw.Close()
+    st = buf.getvalue()
+    types = [t for t, _, _, _ in S._walk_chunks(st, 0, len(st))]
+    assert 0x00 in types and 0x01 in types                   # both compressed and uncompressed chunks occur
+    assert S.Reader(io.BytesIO(st), codec=c).read() == src

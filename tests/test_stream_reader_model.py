@@ -179,7 +179,7 @@ def test_writer_reader_pipe(oracle_lib):
     for o in range(0, len(data), 33333):
         w.Write(data[o:o + 33333])
     w.Flush()
-    w.Write(b"tail")
+    assert w.ReadFrom(io.BytesIO(b"tail")) == 4
     w.Close()
     stream = sink.getvalue()
     r = Z.Reader(io.BytesIO(stream), decoder=OracleDecoder())
