@@ -2,8 +2,9 @@
 """Round-trip campaign of the emulated encode kernels (the shape of the reference's FuzzEncoding, zstd/fuzz_test.go:154-322;
 a longer run of tests/test_emu_encoder_random.py): random structured inputs at ragged sizes through
   * the chunk encoders at levels 1-3 (both lane orders),
-  * frame mode at levels 1-2 (inputs of several blocks, with history),
+  * frame mode at levels 1-3 (inputs of several blocks, with history),
   * S2 fast / better and the Snappy-compatible variants,
+  * standalone huff0 4X / 1X (output bytes equal to the oracle's),
 each decoded by the oracle, by libzstd (zstd) and by the emulated decode kernels, which must return the input.
 Test infrastructure, CPU only.   python tools/fuzz_emu_enc.py [--seed S] [--rounds R]"""
 import argparse
@@ -18,7 +19,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, ROOT)
 
 import helpers as H                                                                  # noqa: E402
-from emu_util import emu_encode, emu_decode, emu_s2_encode, emu_s2_decode, emu_encode_frames   # noqa: E402
+from emu_util import (emu_encode, emu_decode, emu_s2_encode, emu_s2_decode, emu_encode_frames,          # noqa: E402
+                      emu_huf_compress, emu_huf_decompress)
+from test_emu_huf0 import orc_compress as orc_huf_compress, orc_decompress as orc_huf_decompress   # noqa: E402
 from test_emu_encoder_random import _structured                                     # noqa: E402
 from test_oracle_s2 import s2_decode as orc_s2_decode                               # noqa: E402
 
@@ -51,7 +54,7 @@ def one_round(E, rng, stats):
         frames = emu_encode(E, chunks, level=level, desc=int(rng.integers(0, 2)))[0]
         check_zstd(E, "chunks_L%d" % level, chunks, frames)
         stats["chunks"] = stats.get("chunks", 0) + len(chunks)
-    for level in (1, 2):
+    for level in (1, 2, 3):
         inputs = [_structured(rng, int(rng.integers(1, 400000))) for _ in range(4)] + [_structured(rng, 49152 * 2), b""]
         inputs = [x for x in inputs if x]
         frames = emu_encode_frames(E, inputs, level=level, dump=False, desc=int(rng.integers(0, 2)))[0]
@@ -69,6 +72,23 @@ def one_round(E, rng, stats):
                 if int(sizes2[i]) != len(b) or outs[i] != b:
                     fail("s2_emudec_%d%d" % (snappy, better), i, b)
             stats["s2"] = stats.get("s2", 0) + len(blocks)
+    # standalone huff0: bytes and result class equal the oracle's, and the emulated decompressor returns the input
+    hb = [_structured(rng, int(rng.integers(1, 200000))) for _ in range(6)] + [bytes(rng.integers(0, int(rng.integers(2, 200)), int(rng.integers(100, 100000)), dtype=np.uint8)) for _ in range(6)]
+    for four in (True, False):
+        got = emu_huf_compress(E, hb, four)
+        ok = []
+        for i, (b, (comp, code)) in enumerate(zip(hb, got)):
+            wcomp, wcode = orc_huf_compress(b, four)
+            if (code if code < 0 else 0) != (wcode if wcode < 0 else 0) or comp != wcomp:
+                fail("huf0_compress_%d" % four, i, b)
+            if code > 0:
+                ok.append((comp, b))
+        if ok:
+            back = emu_huf_decompress(E, [c for c, _ in ok], [len(b) for _, b in ok], four)
+            for i, ((c, b), (out, code)) in enumerate(zip(ok, back)):
+                if out != b or orc_huf_decompress(c, len(b), four)[1] != b:
+                    fail("huf0_decompress_%d" % four, i, b)
+        stats["huf0"] = stats.get("huf0", 0) + len(hb)
 
 
 def main():
