@@ -320,13 +320,14 @@ class Writer:
     stays at the end), better / snappy / block_size = WriterBetterCompression / WriterSnappyCompat / WriterBlockSize."""
 
     def __init__(self, w, codec=None, device=0, block_size=BLOCK, better=False, snappy=False, add_index=False, padding=0,
-                 batch_bytes=8 << 20, rand=None):
+                 batch_bytes=8 << 20, rand=None, flush_on_write=False):
         if not 4096 <= block_size <= BLOCK:
             raise ErrUnsupported("s2: block size on the device path: 4 KiB .. 64 KiB")
         self._codec = codec if codec is not None else Codec(device=device)
         self._own = codec is None
         self._bs, self._better, self._snappy = block_size, better, snappy
         self._add_index, self._pad, self._rand = add_index, padding, rand
+        self._flush_on_write = flush_on_write               # WriterFlushOnWrite: nothing stays buffered after Write
         self._batch = max(block_size, batch_bytes // block_size * block_size)
         self.Reset(w)
 
@@ -367,6 +368,8 @@ class Writer:
         while len(self._buf) >= self._batch:
             self._emit(self._buf[:self._batch])
             del self._buf[:self._batch]
+        if self._flush_on_write:
+            self.Flush()
         return len(p)
 
     def EncodeBuffer(self, buf):

@@ -190,3 +190,24 @@ def test_framing_format(oracle_lib, better):
     types = [t for t, _, _, _ in S._walk_chunks(st, 0, len(st))]
     assert 0x00 in types and 0x01 in types                   # both compressed and uncompressed chunks occur
     assert S.Reader(io.BytesIO(st), codec=c).read() == src
+
+
+def test_snappy_package_forwarders(oracle_lib):
+    """snappy.NewBufferedWriter / NewWriter / NewReader (snappy/encode.go:41-54, snappy/decode.go:53-55) forward to the S2
+    classes in Snappy-compatible, better mode; the unbuffered writer leaves nothing pending after Write."""
+    from compress_b200 import snappy
+    c = ModelCodec()
+    data = _data(300000, seed=9)
+    buf = io.BytesIO()
+    w = snappy.NewBufferedWriter(buf, codec=c)
+    w.Write(data[:1000]); assert buf.getvalue() == b""      # buffered
+    w.Write(data[1000:]); w.Close()
+    assert buf.getvalue().startswith(S.MAGIC_SNAPPY)
+    assert snappy.NewReader(io.BytesIO(buf.getvalue()), codec=c).read() == data
+    buf2 = io.BytesIO()
+    w = snappy.NewWriter(buf2, codec=c)
+    w.Write(data[:1000])
+    assert snappy.NewReader(io.BytesIO(buf2.getvalue()), codec=c).read() == data[:1000]   # already complete
+    w.Write(data[1000:5000]); w.Close()
+    assert snappy.NewReader(io.BytesIO(buf2.getvalue()), codec=c).read() == data[:5000]
+    assert snappy.DecodedLen(b"\xe8\x07rest") == 1000 and snappy.MaxEncodedLen(0) >= 0
