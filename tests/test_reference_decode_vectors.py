@@ -3,11 +3,8 @@ emulated kernels (the device's code): z000028 (.zst <-> decoded pair, zstd/decod
 (12 .zst files; TestDecoderMultiFrame :911 decodes them concatenated), xml.zst (5 345 280 bytes decoded) and regression.zip
 (36 inputs of TestDecoderRegression :682, which only requires the decoders to agree with each other -- here: the oracle, the
 emulated kernels in both staged forms, and libzstd wherever it accepts the input).  CPU only."""
-import io
 import os
 import zipfile
-
-import pytest
 
 import helpers as H
 from emu_util import emu_decode

@@ -9,7 +9,6 @@ import io
 import numpy as np
 import pytest
 
-import helpers as H
 import s2_stream_ref as R
 from compress_b200 import s2_index as X
 
