@@ -20,6 +20,8 @@ everything the -m gpu tests, smoke() and bench.py need lives here.
   zstd_benchdecoder.zip          zstd/testdata/benchdecoder.zip: 12 .zst files (TestDecoderMultiFrame :911, TestDecoder_Reset :964, benchmarks)
   zstd_z000028, zstd_z000028.zst the decoded / encoded pair of TestPredefTables / TestDecoderDrain (decoder_test.go:539-624, :845)
   zstd_xml.zst                   zstd/testdata/xml.zst (5 345 280 bytes decoded; benchmarks)
+  zstd_fuzz_decode_subset.zip    every 16th entry of zstd/testdata/fuzz/decode-corpus-raw.zip (the reference's FuzzDecodeAll seeds,
+                                 zstd/fuzz_test.go:17-19; the whole corpora run through tools/fuzz_ref_corpora.py here)
 """
 import io, os, shutil, zipfile
 
@@ -27,7 +29,19 @@ REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def fuzz_subset():
+    src = zipfile.ZipFile(f"{REF}/zstd/testdata/fuzz/decode-corpus-raw.zip")
+    out = zipfile.ZipFile(f"{HERE}/zstd_fuzz_decode_subset.zip", "w", zipfile.ZIP_DEFLATED, compresslevel=9)
+    for k, info in enumerate(sorted(src.infolist(), key=lambda i: i.filename)):
+        if k % 16 == 0 and not info.is_dir():
+            zi = zipfile.ZipInfo(info.filename, date_time=(2020, 1, 1, 0, 0, 0))     # fixed stamp: the file is reproducible
+            zi.compress_type = zipfile.ZIP_DEFLATED
+            out.writestr(zi, src.read(info))
+    out.close()
+
+
 def main():
+    fuzz_subset()
     shutil.copy(f"{REF}/zstd/testdata/good.zip", f"{HERE}/zstd_good.zip")
     shutil.copy(f"{REF}/zstd/testdata/bad.zip", f"{HERE}/zstd_bad.zip")
     shutil.copy(f"{REF}/testdata/Mark.Twain-Tom.Sawyer.txt", f"{HERE}/twain.txt")

@@ -87,3 +87,30 @@ def test_regression_zip(oracle_lib, emu_lib, staged_form):
             assert sizes[k] == r and outs[k] == got, names[i]
         else:
             assert sizes[k] < 0, names[i]
+
+
+def test_reference_fuzz_seeds_subset(oracle_lib, emu_lib, staged_form):
+    """Every 16th seed of the reference's FuzzDecodeAll corpus (zstd/testdata/fuzz/decode-corpus-raw.zip, zstd/fuzz_test.go:17-82;
+    the test there requires its decoder configurations to agree): oracle = emulated kernels in verdict and bytes, and libzstd's
+    bytes equal the oracle's wherever both accept.  tools/fuzz_ref_corpora.py runs the complete corpora in the build container."""
+    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_fuzz_decode_subset.zip"))
+    items = [zf.read(n) for n in zf.namelist()]
+    assert len(items) == 501
+    cap = 1 << 20
+    want = [H.oracle_decode(b, cap) for b in items]
+    acc = 0
+    for base in range(0, len(items), 128):
+        grp = items[base:base + 128]
+        sizes, outs = emu_decode(emu_lib, grp, [cap] * len(grp))
+        for k, b in enumerate(grp):
+            ro, wb = want[base + k]
+            if int(sizes[k]) == -11 and ro < 0:
+                continue        # both reject; the kernels stop at a Huffman-weight table with tableLog > 9 ("unsupported",
+                                # DESIGN.md section 4) where the reference reads on to an error of its own
+            assert int(sizes[k]) == ro, (base + k, ro, int(sizes[k]))
+            if ro >= 0:
+                assert outs[k] == wb
+                acc += 1
+                z = _libz(b, cap)
+                assert z is None or z == wb
+    assert 0 < acc < len(items)
