@@ -322,3 +322,32 @@ def test_writer_padding(oracle_lib):
     assert H.libzstd_decode(out, len(data)) == data
     h = Z.Header(); h.Decode(out[out.rindex(b"\x50\x2a\x4d\x18"):])
     assert h.Skippable and h.HeaderSize == 8
+
+
+def test_reader_on_reference_fuzz_seeds(oracle_lib):
+    """The stream reader's host walk on the reference's FuzzDecodeAll seeds (every 16th, tests/golden): with the decoder oracle
+    behind it, Reader.read of a whole input ends the way DecodeAll of the same bytes does -- the same content, or an error
+    where DecodeAll fails (frames whose declared or bounded size exceeds the limit are errors on both sides)."""
+    zf = zipfile.ZipFile(os.path.join(H.GOLDEN, "zstd_fuzz_decode_subset.zip"))
+    cap = 1 << 20
+    ok = err = 0
+    for nm in zf.namelist():
+        b = zf.read(nm)
+        ro, want = H.oracle_decode(b, cap)
+        r = Z.Reader(io.BytesIO(b), decoder=OracleDecoder(), max_frame=cap, max_window=1 << 30)
+        got, failed = b"", False
+        try:
+            while True:                      # (what precedes a bad frame is delivered first; the error comes with the next read)
+                part = r.read()
+                if not part:
+                    break
+                got += part
+        except Z.B2CError:
+            failed = True
+        if ro >= 0:
+            assert not failed and got == want, nm
+            ok += 1
+        else:
+            assert failed, (nm, ro)
+            err += 1
+    assert ok > 3 and err > 300
