@@ -211,3 +211,38 @@ def test_snappy_package_forwarders(oracle_lib):
     w.Write(data[1000:5000]); w.Close()
     assert snappy.NewReader(io.BytesIO(buf2.getvalue()), codec=c).read() == data[:5000]
     assert snappy.DecodedLen(b"\xe8\x07rest") == 1000 and snappy.MaxEncodedLen(0) >= 0
+
+
+def test_reader_equals_whole_stream_decode_on_mutations(oracle_lib):
+    """Cutting the input at chunk boundaries and decoding in batches must not change the verdict: for mutated streams the Reader
+    (small batches, dribbled input) ends like one DecodeStream of the whole input -- same content, or an error."""
+    from test_emu_decoder_mutations import _mutations
+    rng = np.random.default_rng(77)
+    c = ModelCodec()
+    data = _data(200000, seed=5)
+    streams = [c.EncodeStream(data), c.EncodeStream(data[:70000], snappy=True) + c.EncodeStream(data[:5]),
+               c.EncodeStream(data[:3000], block_size=4096)]
+    ok = bad = 0
+    for st in streams:
+        for m in [st] + _mutations(st, rng, 60):
+            try:
+                want = c.DecodeStream(m)
+            except S.B2CError:
+                want = None
+            r = S.Reader(Dribble(m, 999), codec=c, batch_bytes=70000, read_size=999)
+            got, failed = b"", False
+            try:
+                while True:
+                    part = r.read(50000)
+                    if not part:
+                        break
+                    got += part
+            except S.B2CError:
+                failed = True
+            if want is None:
+                assert failed
+                bad += 1
+            else:
+                assert not failed and got == want
+                ok += 1
+    assert ok >= 3 and bad > 50                         # (the checksums catch nearly every mutation)
