@@ -447,6 +447,8 @@ class Reader:
         self._seen_id = self._ignore_id
         self._magic = MAGIC_S2
         self._skip = 0
+        self._pos = 0                      # content offset of the next byte read() returns
+        self._index = None
 
     def _decode(self, pieces):
         """pieces: list of chunk byte strings.  Decode as one batch; on an error find the chunk it belongs to, keeping the
@@ -542,9 +544,10 @@ class Reader:
         if size < 0 or size >= len(self._out):
             out = bytes(self._out)
             self._out.clear()
-            return out
-        out = bytes(self._out[:size])
-        del self._out[:size]
+        else:
+            out = bytes(self._out[:size])
+            del self._out[:size]
+        self._pos += len(out)
         return out
 
     Read = read
@@ -553,6 +556,7 @@ class Reader:
         """Skip n bytes of content forward (s2/reader.go:674-800)."""
         if n < 0:
             raise ValueError("attempted negative skip")
+        self._pos += n
         k = min(n, len(self._out))
         del self._out[:k]
         n -= k
@@ -581,7 +585,105 @@ class Reader:
             self._out.clear()
         return total
 
+    def ReadSeeker(self, random=False, index=None):
+        """-> ReadSeeker over this reader (s2/reader.go:855-920).  index: serialised index bytes; without one it is loaded from
+        the end of a seekable input.  random=True needs a seekable input and an index; otherwise seeking is forward only."""
+        if index:
+            self._index = s2_index.Index()
+            try:
+                self._index.Load(index)
+            except (ValueError, EOFError) as e:
+                raise ErrCantSeek("loading index returned: %s" % e)
+        seekable = hasattr(self._r, "seek") and (not hasattr(self._r, "seekable") or self._r.seekable())
+        if not seekable:
+            if random:
+                raise ErrCantSeek("input stream isn't seekable")
+            return ReadSeeker(self)
+        if self._index is None:
+            pos = self._r.tell()
+            idx = s2_index.Index()
+            try:
+                idx.LoadStream(self._r)
+                self._index = idx
+            except s2_index.ErrUnsupported:
+                if random:
+                    raise ErrCantSeek("input stream does not contain an index")
+            except (ValueError, EOFError) as e:
+                raise ErrCantSeek("reading index returned: %s" % e)
+            finally:
+                self._r.seek(pos)
+        return ReadSeeker(self)
+
     def Close(self):
         if self._own and self._codec is not None:
             self._codec.close()
         self._codec = None
+
+
+class ErrCantSeek(B2CError):
+    """s2.ErrCantSeek"""
+
+
+class ReadSeeker:
+    """s2.ReadSeeker (s2/reader.go:845-1060): Seek / ReadAt on the content of a stream.  With an index and a seekable input a
+    seek goes to the chunk Index.Find names and skips forward inside it (whole blocks on the way are dropped undecoded);
+    without them only forward seeks work, by skipping."""
+
+    def __init__(self, reader):
+        self.Reader = reader
+
+    def read(self, size=-1):
+        return self.Reader.read(size)
+
+    Read = read
+
+    def Seek(self, offset, whence=0):
+        r = self.Reader
+        if whence == 0:
+            target = offset
+        elif whence == 1:
+            target = r._pos + offset
+        elif whence == 2:
+            if r._index is None:
+                raise ErrUnsupported("s2: unsupported input")
+            target = r._index.TotalUncompressed + offset
+        else:
+            raise ErrUnsupported("s2: unsupported input")
+        if target < 0:
+            raise ValueError("seek before start of file")
+        if isinstance(r._err, (ErrCorrupt, ErrCRC, ErrUnsupported)):
+            raise r._err
+        buffered = len(r._out)
+        if r._pos <= target <= r._pos + buffered and not r._skip:
+            r.Skip(target - r._pos)                           # inside what is already decoded
+            return target
+        seekable = hasattr(r._r, "seek") and (not hasattr(r._r, "seekable") or r._r.seekable())
+        if r._index is None or not seekable:
+            if target >= r._pos:
+                r.Skip(target - r._pos)
+                return target
+            raise ErrUnsupported("s2: unsupported input")
+        try:
+            c, u = r._index.Find(target)
+        except EOFError:
+            raise ErrCorrupt("s2: corrupt input (unexpected EOF)")
+        magic, seen, idx = r._magic, r._seen_id, r._index
+        r._r.seek(c)
+        r.Reset(r._r)                                          # drop everything buffered; the next chunk read starts at c
+        r._index = idx
+        r._magic, r._seen_id = magic, True if c else seen      # (mid-stream there is no identifier in front)
+        r._pos = u
+        if target > u:
+            r.Skip(target - u)
+        return target
+
+    def ReadAt(self, n, offset):
+        """n bytes of content at `offset` (fewer only at the end of the stream)."""
+        self.Seek(offset, 0)
+        out = bytearray()
+        while len(out) < n:
+            part = self.Reader.read(n - len(out))
+            if not part:
+                break
+            out += part
+        return bytes(out)

@@ -246,3 +246,55 @@ def test_reader_equals_whole_stream_decode_on_mutations(oracle_lib):
                 assert not failed and got == want
                 ok += 1
     assert ok >= 3 and bad > 50                         # (the checksums catch nearly every mutation)
+
+
+def test_read_seeker(oracle_lib):
+    """TestSeeking (s2/index_test.go:105-300): random seeks with an index on a seekable input (from the stream's end or passed
+    separately), forward-only seeking without one, ReadAt, seeks relative to the position and the end."""
+    rng = np.random.default_rng(11)
+    c = ModelCodec()
+    data = _data(4 << 20, seed=7)
+    sink = io.BytesIO()
+    w = S.Writer(sink, codec=c, add_index=True)
+    w.Write(data); w.Close()
+    st = sink.getvalue()
+    plain = c.EncodeStream(data)
+    idx_bytes = X.IndexStream(plain)
+    for stream, index in ((st, None), (plain, idx_bytes)):
+        rs = S.Reader(io.BytesIO(stream), codec=c).ReadSeeker(random=True, index=index)
+        for _ in range(25):
+            off = int(rng.integers(0, len(data)))
+            assert rs.Seek(off, 0) == off
+            n = int(rng.integers(1, 5000))
+            assert rs.read(n) == data[off:off + n]
+        assert rs.Seek(-100, 2) == len(data) - 100 and rs.read() == data[-100:]
+        assert rs.Seek(1000, 0) == 1000 and rs.read(10) == data[1000:1010]
+        assert rs.Seek(5, 1) == 1015 and rs.read(10) == data[1015:1025]          # relative to the position
+        assert rs.Seek(-1025, 1) == 0 and rs.read(3) == data[:3]                 # backwards through the index
+        assert rs.ReadAt(100, 3 << 20) == data[3 << 20:(3 << 20) + 100]
+        assert rs.ReadAt(100, len(data) - 10) == data[-10:]
+        with pytest.raises(ValueError):
+            rs.Seek(-1, 0)
+        with pytest.raises(S.ErrCorrupt):
+            rs.Seek(len(data) + 1, 0)
+    # seeks decode only what they need: far less input than the stream is handed to the codec
+    c.dec_calls.clear()
+    rs = S.Reader(io.BytesIO(st), codec=c, batch_bytes=1 << 20).ReadSeeker(random=True)
+    rs.Seek(3500000, 0); rs.read(10)
+    assert sum(c.dec_calls) < len(st) // 2
+    # no index: forward only
+    with pytest.raises(S.ErrCantSeek):
+        S.Reader(io.BytesIO(plain), codec=c).ReadSeeker(random=True)
+    rs = S.Reader(io.BytesIO(plain), codec=c).ReadSeeker(random=False)
+    assert rs.Seek(100000, 0) == 100000 and rs.read(5) == data[100000:100005]
+    with pytest.raises(S.ErrUnsupported):
+        rs.Seek(10, 0)
+    with pytest.raises(S.ErrUnsupported):
+        rs.Seek(-1, 2)
+    # an input that cannot seek
+    with pytest.raises(S.ErrCantSeek):
+        S.Reader(Dribble(st, 1000), codec=c).ReadSeeker(random=True)
+    rs = S.Reader(Dribble(st, 100000), codec=c).ReadSeeker(random=False, index=idx_bytes)
+    assert rs.Seek(200000, 0) == 200000 and rs.read(4) == data[200000:200004]
+    with pytest.raises(S.ErrCantSeek):
+        S.Reader(io.BytesIO(plain), codec=c).ReadSeeker(index=b"\x99garbage-that-is-long-enough-to-parse")
